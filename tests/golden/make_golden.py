@@ -1,0 +1,156 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) on seeded inputs.
+
+Run in the build container only (the GPU box has no /root/reference):  python tests/golden/make_golden.py
+The reference never seeds anything — seeds are set here, around its calls.
+Config is injected the way SURVEY.md §1 describes: config_utils._config_cache is set before model construction."""
+import os
+import random
+import sys
+
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+os.chdir("/tmp")  # the reference writes relative paths; keep /root/reference untouched
+
+import config_utils  # noqa: E402
+
+
+def set_cfg(block_size, n_embd, n_head, n_layer, batch_size, dropout=0.0):
+    config_utils._config_cache = dict(device="cpu", batch_size=batch_size, block_size=block_size, eval_iters=2,
+                                      n_embd=n_embd, n_head=n_head, n_layer=n_layer, dropout=dropout, fixed_values=[],
+                                      output_file_name="", project_file_path="/tmp/")
+
+
+def params_list(cross, names=None, is_pct=None):
+    out = []
+    for i, c in enumerate(cross):
+        out.append(["synthetic", i + 1, None, bool(is_pct[i]) if is_pct else False, None, None, None, None, c,
+                    names[i] if names else f"mod{i}", None, None])
+    return out
+
+
+def model_case(name, M, V, cross, B, T, C, H, L, T_run=None, steps=3, lr=1e-3):
+    set_cfg(T, C, H, L, B)
+    import model as ref_model
+    torch.manual_seed(0)
+    m = ref_model.MultimodalTransformer(M, V, params_list(cross))
+    # make LayerNorm affine params and biases non-trivial so parity exercises them
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "ln" in k or "norm" in k:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            elif k.endswith(".bias"):
+                p.add_(0.02 * torch.randn(p.shape, generator=g))
+    m.eval()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    Tr = T_run or T
+    gi = torch.Generator().manual_seed(11)
+    idx = [torch.randint(0, V[i], (B, Tr), generator=gi) for i in range(M)]
+    tgt = [torch.randint(0, V[i], (B, Tr), generator=gi) for i in range(M)]
+    logits, losses = m(idx, tgt)
+    m.zero_grad()
+    sum(losses).backward()
+    grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()}
+    logits_nt, none = m(idx)
+    assert none is None
+    # k AdamW steps on the same batch (main.py:464, 646-650)
+    opt = torch.optim.AdamW(m.parameters(), lr=lr)
+    curve = []
+    for _ in range(steps):
+        lg, ls = m(idx, tgt)
+        tot = sum(ls)
+        opt.zero_grad(set_to_none=True)
+        tot.backward()
+        opt.step()
+        curve.append(float(tot))
+    sd_after = {k: v.clone() for k, v in m.state_dict().items() if not k.endswith(".tril")}
+    keys_with_tril = list(sd0.keys())
+    sd0 = {k: v for k, v in sd0.items() if not k.endswith(".tril")}  # tril is derivable; keep fixtures small
+    torch.save(dict(cfg=dict(M=M, V=V, cross=cross, B=B, T=T, C=C, H=H, L=L, T_run=Tr, lr=lr, steps=steps),
+                    state_dict=sd0, state_dict_keys=keys_with_tril, idx=idx, tgt=tgt,
+                    logits=[t.detach() for t in logits], losses=[t.detach() for t in losses], grads=grads,
+                    curve=curve, state_dict_after=sd_after), os.path.join(OUT, f"model_{name}.pt"))
+    print(name, "losses", [round(float(x), 5) for x in losses], "curve", [round(c, 5) for c in curve])
+
+
+def index_cases():
+    import training_utils as tu
+    cases = []
+    spec = [
+        # data_size, block, batch, split, file_lengths, is_percents
+        (900, 16, 32, "train", [1000], False),
+        (100, 16, 32, "val", [1000], True),
+        (900, 8, 64, "train", [300, 250, 450], False),
+        (900, 8, 64, "train", [300, 250, 450], True),
+        (100, 8, 64, "val", [300, 250, 450], False),
+        (500, 8, 64, "val", [300, 250, 450], True),
+        (620, 4, 33, "train", [5, 300, 3, 400, 200], False),
+        (288, 4, 33, "val", [5, 300, 3, 400, 200], True),
+        (90, 4, 4, "train", [100], False),
+    ]
+    for n, (ds, T, B, split, fl, pct) in enumerate(spec):
+        torch.manual_seed(100 + n)
+        ix = tu.generate_batch_starting_indices(ds, T, B, split, fl, pct)
+        ix2 = tu.generate_batch_starting_indices(ds, T, B, split, fl, pct)  # second draw from the same stream
+        cases.append(dict(args=(ds, T, B, split, fl, pct), seed=100 + n, ix=ix, ix2=ix2))
+    torch.save(cases, os.path.join(OUT, "indices.pt"))
+    print("indices:", len(cases), "cases")
+
+
+def get_batch_case():
+    """get_batch end to end through the reference's module globals (main.py:387-396), quirk off ([2] = None)."""
+    import training_utils as tu
+    set_cfg(8, 32, 4, 1, 6)
+    M, N = 3, 400
+    g = torch.Generator().manual_seed(5)
+    full = [torch.randint(0, 50, (N,), generator=g) for _ in range(M)]
+    n_val = 40
+    tu.all_train_sets = [d[:-n_val].tolist() for d in full]
+    tu.all_val_sets = [d[-n_val:].clone() for d in full]
+    tu.all_vocabularies = [[float(k) for k in range(50)]] * M
+    tu.all_modality_params = params_list([True, False, False])
+    tu.file_lengths = [150, 250]
+    tu.num_modalities = M
+    tu.is_percents = False
+    out = {}
+    torch.manual_seed(42)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for split in ("train", "val", "train"):
+            xb, yb = tu.get_batch(split, 1)
+            out.setdefault("calls", []).append(dict(split=split, xb=xb, yb=yb))
+    torch.save(dict(full=full, n_val=n_val, file_lengths=[150, 250], block_size=8, batch_size=6, seed=42, **out),
+               os.path.join(OUT, "get_batch.pt"))
+    print("get_batch: 3 calls")
+
+
+def metrics_case():
+    import training_utils as tu
+    M, B, T = 3, 16, 6
+    V = [21, 9, 5]
+    g = torch.Generator().manual_seed(3)
+    logits = [torch.randn(B, T, V[i], generator=g) for i in range(M)]
+    xb = [torch.randint(0, V[i], (B, T), generator=g) for i in range(M)]
+    yb = [torch.randint(0, V[i], (B, T), generator=g) for i in range(M)]
+    vocabs = [[float(k) * 0.5 - 3 for k in range(V[0])], [float(k - 4) for k in range(V[1])], ["a", "b", "c", "d", "e"]]
+    params = params_list([True, False, False], is_pct=[False, True, False])
+    res = tu.calculate_evaluation_metrics(logits, xb, yb, M, vocabs, params, None)
+    torch.save(dict(logits=logits, xb=xb, yb=yb, vocabs=vocabs, params=params, result=res),
+               os.path.join(OUT, "metrics.pt"))
+    print("metrics:", res)
+
+
+if __name__ == "__main__":
+    random.seed(0)
+    model_case("demo", M=2, V=[57, 3], cross=[True, False], B=4, T=4, C=32, H=4, L=2)
+    model_case("m3", M=3, V=[57, 3, 20], cross=[True, False, True], B=3, T=8, C=32, H=4, L=2)
+    model_case("m3_short", M=3, V=[24, 10, 20], cross=[False, True, True], B=2, T=8, C=32, H=2, L=1, T_run=5)
+    model_case("hs32", M=2, V=[40, 33], cross=[True, True], B=2, T=16, C=64, H=2, L=1)
+    model_case("nocross", M=1, V=[30], cross=[True], B=2, T=8, C=32, H=4, L=1)
+    index_cases()
+    get_batch_case()
+    metrics_case()

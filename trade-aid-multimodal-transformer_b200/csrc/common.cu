@@ -1,0 +1,45 @@
+// Error reporting, launch counting and device queries for libtradeaid_b200.so.
+#include "common.cuh"
+
+#include <atomic>
+#include <cstring>
+
+#include "../../include/tradeaid_b200.h"
+
+namespace ta {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+char* err_buf() { return g_err; }
+
+int set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace ta
+
+extern "C" {
+const char* ta_last_error(void) { return ta::err_buf(); }
+int32_t ta_abi_version(void) { return TA_ABI_VERSION; }
+int64_t ta_launch_count(void) { return ta::g_launches.load(std::memory_order_relaxed); }
+void ta_reset_launch_count(void) { ta::g_launches.store(0, std::memory_order_relaxed); }
+}

@@ -1,0 +1,399 @@
+// K2 — grouped bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (UMMA 128 x BLOCK_N x 16,
+// fp32 accumulators double-buffered in TMEM) -> tcgen05.ld epilogue with fused bias / tanh / ReLU / activation
+// backward / residual add, fp32 and/or bf16 stores. Persistent grid, warp-specialised:
+//   warp 0    TMA producer (one lane)
+//   warp 1    TMEM allocator + MMA issuer (one lane)
+//   warps 2-5 epilogue (each owns the 32 TMEM lanes of its warp-id % 4 quarter)
+// Replaces every nn.Linear forward/backward of /root/reference/model.py (see include/tradeaid_b200.h).
+#include <cuda_bf16.h>
+
+#include "../../include/tradeaid_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ta {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+
+struct GemmParams {
+  int M, N, K, G0, G1;
+  int a_mn, b_mn;
+  int m_blocks, n_blocks, k_blocks;
+  float alpha;
+  int act, aux_mode;
+  const float* bias;
+  long long bias_gs0, bias_gs1;
+  const __nv_bfloat16* aux;
+  long long ld_aux, aux_gs0, aux_gs1;
+  const float* res;
+  long long ld_res, res_gs0, res_gs1;
+  float* out_f32;
+  long long ld_f32, f32_gs0, f32_gs1;
+  __nv_bfloat16* out_bf16;
+  long long ld_bf16, bf16_gs0, bf16_gs1;
+  int vec_f32, vec_bf16, vec_res, vec_aux;
+};
+
+__device__ __forceinline__ float epi_apply(float v, float bias, int act) {
+  v += bias;
+  if (act == TA_ACT_TANH) v = tanhf(v);
+  else if (act == TA_ACT_RELU) v = fmaxf(v, 0.f);
+  return v;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int tiles_per_group = p.m_blocks * p.n_blocks;
+  const int total_tiles = tiles_per_group * p.G0 * p.G1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int g = tile / tiles_per_group;
+        const int t = tile - g * tiles_per_group;
+        const int m0 = (t / p.n_blocks) * BLOCK_M;
+        const int n0 = (t % p.n_blocks) * BLOCK_N;
+        const int g0 = g % p.G0, g1 = g / p.G0;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn) {
+            tma_load_4d(sA, &tmA, &full_bar[stage], k0, m0, g0, g1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_4d(sA + c * (64 * BLOCK_K * 2), &tmA, &full_bar[stage], m0 + c * 64, k0, g0, g1);
+          }
+          if (!p.b_mn) {
+            tma_load_4d(sB, &tmB, &full_bar[stage], k0, n0, g0, g1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              tma_load_4d(sB + c * (64 * BLOCK_K * 2), &tmB, &full_bar[stage], n0 + c * 64, k0, g0, g1);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, p.a_mn, p.b_mn);
+    // K-major SW128: 8-row groups 1024 B apart (SBO), 16 k-elements = 32 B inside the swizzle row.
+    // MN-major SW128: boxes of [64 k-rows][64 mn] (8 KB): next 64-mn chunk = LBO 8192, next 8 k-rows = SBO 1024,
+    //                 16 k-rows = 2048 B.
+    const uint32_t a_lbo = p.a_mn ? 64 * BLOCK_K * 2 : 16, a_kstep = p.a_mn ? 16 * 128 : 32;
+    const uint32_t b_lbo = p.b_mn ? 64 * BLOCK_K * 2 : 16, b_kstep = p.b_mn ? 16 * 128 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + A_STAGE_BYTES;
+          const int krem = p.K - kb * BLOCK_K;
+          const int nk = krem >= BLOCK_K ? BLOCK_K / 16 : (krem + 15) / 16;
+          for (int j = 0; j < nk; ++j) {
+            const uint64_t da = umma_desc_sw128(sA + j * a_kstep, a_lbo, 1024);
+            const uint64_t db = umma_desc_sw128(sB + j * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | j) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int g = tile / tiles_per_group;
+      const int t = tile - g * tiles_per_group;
+      const int m0 = (t / p.n_blocks) * BLOCK_M;
+      const int n0 = (t % p.n_blocks) * BLOCK_N;
+      const int g0 = g % p.G0, g1 = g / p.G0;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float* bias = p.bias ? p.bias + g0 * p.bias_gs0 + g1 * p.bias_gs1 : nullptr;
+      const __nv_bfloat16* aux = p.aux ? p.aux + g0 * p.aux_gs0 + g1 * p.aux_gs1 + (long long)row * p.ld_aux : nullptr;
+      const float* res = p.res ? p.res + g0 * p.res_gs0 + g1 * p.res_gs1 + (long long)row * p.ld_res : nullptr;
+      float* of = p.out_f32 ? p.out_f32 + g0 * p.f32_gs0 + g1 * p.f32_gs1 + (long long)row * p.ld_f32 : nullptr;
+      __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr_row + c * 32, v);
+        tmem_wait_ld();
+        if (!row_ok) continue;
+        const bool full = col0 + 32 <= p.N;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+        if (bias || p.act) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float b = (bias && (full || col0 + i < p.N)) ? __ldg(bias + col0 + i) : 0.f;
+            f[i] = epi_apply(f[i], b, p.act);
+          }
+        }
+        if (aux) {
+          if (full && p.vec_aux) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(aux + col0 + i);
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a = __bfloat162float(h[j]);
+                f[i + j] = p.aux_mode == TA_AUX_TANH_BWD ? f[i + j] * (1.f - a * a) : (a > 0.f ? f[i + j] : 0.f);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) {
+                const float a = __bfloat162float(aux[col0 + i]);
+                f[i] = p.aux_mode == TA_AUX_TANH_BWD ? f[i] * (1.f - a * a) : (a > 0.f ? f[i] : 0.f);
+              }
+          }
+        }
+        if (res) {
+          if (full && p.vec_res) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 r = *reinterpret_cast<const float4*>(res + col0 + i);
+              f[i] += r.x; f[i + 1] += r.y; f[i + 2] += r.z; f[i + 3] += r.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) f[i] += res[col0 + i];
+          }
+        }
+        if (of) {
+          if (full && p.vec_f32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(of + col0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) of[col0 + i] = f[i];
+          }
+        }
+        if (ob) {
+          if (full && p.vec_bf16) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 u;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[i + 2 * j], f[i + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(ob + col0 + i) = u;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// operand: logical (MN x K) bf16 matrix with two group dims; box_mn = rows of the MN dim per smem tile
+static int make_operand_map(CUtensorMap* out, const ta_operand* op, int64_t MN, int64_t K, int G0, int G1, int box_mn) {
+  EncodeTiledFn enc = get_encode_fn();
+  TA_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  TA_CHECK_ARG((reinterpret_cast<uintptr_t>(op->ptr) & 15) == 0, "gemm operand pointer must be 16-byte aligned");
+  TA_CHECK_ARG(op->ld % 8 == 0, "gemm operand ld (%lld) must be a multiple of 8 elements", (long long)op->ld);
+  TA_CHECK_ARG(G0 == 1 || op->gs0 % 8 == 0, "gemm operand gs0 (%lld) must be a multiple of 8", (long long)op->gs0);
+  TA_CHECK_ARG(G1 == 1 || op->gs1 % 8 == 0, "gemm operand gs1 (%lld) must be a multiple of 8", (long long)op->gs1);
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint64_t safe = 16;
+  if (op->major == 0) {  // stored [MN][K]
+    TA_CHECK_ARG(op->ld >= K, "K-major operand ld < K");
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)MN;
+    box[0] = BLOCK_K; box[1] = (cuuint32_t)box_mn;
+  } else {               // stored [K][MN]
+    TA_CHECK_ARG(op->ld >= MN, "MN-major operand ld < MN");
+    dims[0] = (cuuint64_t)MN; dims[1] = (cuuint64_t)K;
+    box[0] = 64; box[1] = BLOCK_K;
+  }
+  dims[2] = (cuuint64_t)G0; dims[3] = (cuuint64_t)G1;
+  box[2] = 1; box[3] = 1;
+  strides[0] = (cuuint64_t)op->ld * 2;
+  strides[1] = G0 > 1 ? (cuuint64_t)op->gs0 * 2 : safe;
+  strides[2] = G1 > 1 ? (cuuint64_t)op->gs1 * 2 : safe;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op->ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TA_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu %llu %llu %llu ld %lld)",
+               (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+               (unsigned long long)dims[3], (long long)op->ld);
+  return 0;
+}
+
+template <int BLOCK_N>
+static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  if (make_operand_map(&tmA, A, p.M, p.K, p.G0, p.G1, BLOCK_M)) return 1;
+  if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, BLOCK_N)) return 1;
+  p.n_blocks = (int)ceil_div(p.N, BLOCK_N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long total = (long long)p.m_blocks * p.n_blocks * p.G0 * p.G1;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  gemm_bf16_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  TA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace ta
+
+extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_t M, int64_t N, int64_t K, int32_t G0,
+                                int32_t G1, const ta_epilogue* ep, void* stream) {
+  using namespace ta;
+  TA_CHECK_ARG(A && B && ep, "ta_gemm_bf16: null argument");
+  TA_CHECK_ARG(M > 0 && N > 0 && K > 0 && G0 > 0 && G1 > 0, "ta_gemm_bf16: non-positive shape");
+  TA_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "ta_gemm_bf16: shape too large");
+  TA_CHECK_ARG(ep->out_f32 || ep->out_bf16, "ta_gemm_bf16: no output");
+  TA_CHECK_ARG(ep->dropout_p == 0.f, "ta_gemm_bf16: epilogue dropout not implemented in this build");
+  TA_CHECK_ARG(!ep->aux || ep->aux_mode != TA_AUX_NONE, "ta_gemm_bf16: aux given without aux_mode");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G0 = G0; p.G1 = G1;
+  p.a_mn = A->major ? 1 : 0; p.b_mn = B->major ? 1 : 0;
+  p.m_blocks = (int)ceil_div(M, BLOCK_M);
+  p.k_blocks = (int)ceil_div(K, BLOCK_K);
+  p.alpha = ep->alpha; p.act = ep->act; p.aux_mode = ep->aux ? ep->aux_mode : 0;
+  p.bias = ep->bias; p.bias_gs0 = ep->bias_gs0; p.bias_gs1 = ep->bias_gs1;
+  p.aux = static_cast<const __nv_bfloat16*>(ep->aux); p.ld_aux = ep->ld_aux; p.aux_gs0 = ep->aux_gs0; p.aux_gs1 = ep->aux_gs1;
+  p.res = ep->residual; p.ld_res = ep->ld_res; p.res_gs0 = ep->res_gs0; p.res_gs1 = ep->res_gs1;
+  p.out_f32 = ep->out_f32; p.ld_f32 = ep->ld_f32; p.f32_gs0 = ep->f32_gs0; p.f32_gs1 = ep->f32_gs1;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(ep->out_bf16); p.ld_bf16 = ep->ld_bf16; p.bf16_gs0 = ep->bf16_gs0; p.bf16_gs1 = ep->bf16_gs1;
+  auto al = [](const void* ptr, long long ld, long long s0, long long s1, int elems, int bytes) {
+    return ptr && (reinterpret_cast<uintptr_t>(ptr) % bytes == 0) && ld % elems == 0 && s0 % elems == 0 && s1 % elems == 0;
+  };
+  p.vec_f32 = al(p.out_f32, p.ld_f32, p.f32_gs0, p.f32_gs1, 4, 16);
+  p.vec_res = al(p.res, p.ld_res, p.res_gs0, p.res_gs1, 4, 16);
+  p.vec_bf16 = al(p.out_bf16, p.ld_bf16, p.bf16_gs0, p.bf16_gs1, 8, 16);
+  p.vec_aux = al(p.aux, p.ld_aux, p.aux_gs0, p.aux_gs1, 8, 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tile width: the widest UMMA N that still yields about a wave of tiles
+  const long long groups = (long long)G0 * G1;
+  auto tiles = [&](int bn) { return groups * p.m_blocks * ceil_div(N, bn); };
+  int bn = 256;
+  if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else if (tiles(256) < num_sms() && tiles(128) > tiles(256)) bn = 128;
+  if (bn == 128 && N > 64 && tiles(128) < num_sms() / 2 && tiles(64) > tiles(128)) bn = 64;
+  if (bn == 256) return launch_gemm<256>(A, B, p, st);
+  if (bn == 128) return launch_gemm<128>(A, B, p, st);
+  return launch_gemm<64>(A, B, p, st);
+}
