@@ -78,6 +78,93 @@ typedef struct ta_epilogue {
 int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_t M, int64_t N, int64_t K, int32_t G0,
                      int32_t G1, const ta_epilogue* ep, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------ K3: attention
+ * Causal softmax(q k^T * hs^-0.5) v per (group, batch, head) without materialising T x T in HBM (tcgen05 + TMEM,
+ * online softmax). Self-attention: model.py:60-73 (n_src = 1). Cross-attention: model.py:136-159 — one independent
+ * causal softmax per key/value source, outputs summed (n_src = number of other modalities).
+ * Every tensor is a bf16 activation [G][B*T][ld] whose head h occupies columns [h*head_stride, h*head_stride + hs);
+ * ptr already points at column 0 of head 0 (so q/k/v slices of a packed buffer are expressed by ptr offsets).
+ * lse: fp32 [n_src][G][B][H][T] (natural log), saved for backward. o_src (optional, required by backward when
+ * n_src > 1): per-source normalised outputs, bf16 [n_src] x (same layout as o), o_src_stride elements apart.
+ */
+typedef struct ta_attn_tensor {
+  const void* ptr;
+  int64_t ld;          /* elements between consecutive token rows */
+  int64_t head_stride; /* elements between consecutive heads      */
+  int64_t gs;          /* elements between consecutive groups     */
+} ta_attn_tensor;
+
+int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v, int32_t n_src,
+                         void* o_bf16, int64_t ldo, int64_t o_gs, void* o_src_bf16, int64_t o_src_stride, float* lse,
+                         int32_t G, int32_t B, int32_t T, int32_t H, int32_t hs, float dropout_p, uint64_t seed,
+                         void* stream);
+
+/* Backward of the above (recompute): given dO (layout of o) produces dq (layout of q), and per source dk, dv (layouts
+ * of k[s], v[s]); all bf16. T <= 256 in this build. */
+int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v, int32_t n_src,
+                         const void* o_bf16, const void* o_src_bf16, int64_t o_src_stride, const void* do_bf16,
+                         int64_t ldo, int64_t o_gs, const float* lse, const ta_attn_tensor* dq,
+                         const ta_attn_tensor* dk, const ta_attn_tensor* dv, int32_t G, int32_t B, int32_t T, int32_t H,
+                         int32_t hs, float dropout_p, uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ K7: get_batch
+ * xb[m,b,t] = store[m, ix[b]+t], yb[m,b,t] = store[m, ix[b]+t+1] (training_utils.py:378-379). store: int32 token ids
+ * [M][store_stride] resident in HBM; ix: int64 [B] (drawn on the host by torch.randint, training_utils.py:104/150, so
+ * the index stream is bit-exact); xb/yb: int64 [M][B][T]. */
+int32_t ta_gather_batch(const int32_t* store, int64_t store_stride, int32_t M, const int64_t* ix, int32_t B, int32_t T,
+                        int64_t* xb, int64_t* yb, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ K1: embedding
+ * x[m, r, :] = tok[voff[m] + idx[m, r], :] + pos[r % T, :] (model.py:300-319). idx int64 [M][rows]; tok fp32
+ * [sum V, C] (tables of all modalities stacked, voff int64 [M+1] row offsets); pos fp32 [>=T, C]; x fp32 [M][rows][C].
+ * Backward: dtok rows (deterministic, ordered accumulation) and dpos[t] = sum over modalities and batch. */
+int32_t ta_embed_fwd(const int64_t* idx, const float* tok, const int64_t* voff, const float* pos, float* x, int32_t M,
+                     int64_t rows, int32_t T, int32_t C, void* stream);
+int32_t ta_embed_bwd(const int64_t* idx, const float* dx, const int64_t* voff, int32_t max_vocab, float* dtok,
+                     float* dpos, int32_t M, int32_t B, int32_t T, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ K4: LayerNorm
+ * nn.LayerNorm(C), eps inside the sqrt, affine (model.py:189-190, 210, 330). x fp32 [rows_total][C] -> y bf16 (ldy);
+ * gamma/beta fp32 [G][C] with G = rows_total / rows_per_group; mean/rstd fp32 [rows_total] saved for backward.
+ * Backward: dy bf16; dstream_out = dstream_in (nullable) + dx (fp32) with an optional bf16 copy; dgamma/dbeta [G][C].
+ */
+int32_t ta_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t ldy, float* mean,
+                         float* rstd, int64_t rows_total, int64_t rows_per_group, int32_t C, float eps, void* stream);
+int64_t ta_layernorm_bwd_workspace_floats(int64_t rows_total, int64_t rows_per_group, int32_t C);
+int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, const float* gamma, const float* mean,
+                         const float* rstd, const float* dstream_in, float* dstream_out, void* dstream_bf16,
+                         int64_t ld_dbf, float* dgamma, float* dbeta, float* workspace, int64_t rows_total,
+                         int64_t rows_per_group, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ K5: cross-entropy
+ * F.cross_entropy(logits.view(B*T, V), targets.view(B*T)) mean reduction (model.py:394-399), fused with its backward:
+ * row_loss[r] = logsumexp - logit[target]; loss_mean[0] = mean_r row_loss (fixed-order reduction);
+ * dlogits (bf16, nullable) = (softmax - onehot) * grad_scale / rows. */
+int32_t ta_cross_entropy(const float* logits, int64_t ldl, const int64_t* targets, float* row_loss, float* loss_mean,
+                         void* dlogits_bf16, int64_t ldd, int64_t rows, int32_t V, float grad_scale, void* stream);
+
+/* bias gradients: out[g, c] = sum_r dy[g, r, c] (dy bf16 [G][rows][ld]); deterministic two-stage reduction. */
+int64_t ta_colsum_workspace_floats(int64_t rows, int32_t N, int32_t G);
+int32_t ta_colsum_bf16(const void* dy_bf16, int64_t ld, int64_t gs, float* out, int64_t out_gs, float* workspace,
+                       int64_t rows, int32_t N, int32_t G, void* stream);
+
+/* fp32 -> bf16 casts (bf16 GEMM-operand shadows of weights and of the un-normalised stream, model.py:143). */
+int32_t ta_cast_pad_bf16(const float* src, int64_t sg, int64_t sr, void* dst_bf16, int64_t dg, int64_t dr, int32_t G,
+                         int32_t R, int32_t Cs, int32_t Rd, int32_t Cd, void* stream);
+int32_t ta_unpad_f32(const float* src, int64_t sg, int64_t sr, float* dst, int64_t dg, int64_t dr, int32_t G, int32_t R,
+                     int32_t Cn, void* stream);
+int32_t ta_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ K6: AdamW
+ * torch.optim.AdamW defaults (main.py:464, 650): betas (0.9, 0.999), eps 1e-8, decoupled weight_decay 0.01, on the flat
+ * fp32 master buffer; also writes the bf16 shadow (nullable). ta_adamw_tick advances the device-resident step counter
+ * (int64[1]) and derives the bias-corrected scalars (float[4]) so the step replays inside a CUDA graph. */
+int32_t ta_adamw_tick(int64_t* step_dev, float* scalars_dev, double lr, double beta1, double beta2, double weight_decay,
+                      void* stream);
+int32_t ta_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* scalars_dev,
+                      float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

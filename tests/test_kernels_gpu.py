@@ -1,0 +1,278 @@
+"""Per-kernel parity on the GPU: every C-ABI op against a plain PyTorch fp32 statement of the same op (bit-exact for
+integer work; fp tolerances written next to each check)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tradeaid_b200 import lib as L
+    return L
+
+
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_CASES = [
+    # M, N, K, groups, a_major, b_major, epilogue
+    (128, 64, 64, (), 0, 0, "none"),
+    (100, 72, 40, (), 0, 0, "none"),
+    (16, 28, 32, (2,), 0, 0, "none"),
+    (16, 3, 1, (2,), 0, 0, "bias"),          # demo head: V = 3, V // 2 = 1
+    (256, 512, 512, (), 0, 1, "none"),
+    (256, 512, 512, (), 1, 1, "none"),
+    (200, 136, 72, (2, 3), 0, 1, "none"),
+    (200, 136, 72, (2, 3), 1, 1, "none"),
+    (300, 200, 136, (3, 2), 0, 0, "bias_tanh"),
+    (300, 200, 136, (2,), 0, 0, "bias_relu"),
+    (300, 200, 136, (), 0, 0, "res"),
+    (300, 200, 136, (), 0, 1, "tanh_bwd"),
+    (300, 200, 136, (), 0, 1, "relu_bwd"),
+    (4096, 1024, 1024, (), 0, 0, "bias_relu"),
+    (1024, 512, 4096, (), 1, 1, "none"),
+]
+
+
+@pytest.mark.parametrize("M,N,K,g,am,bm,epi", GEMM_CASES)
+def test_gemm(lib, M, N, K, g, am, bm, epi):
+    torch.manual_seed(0)
+    dev = "cuda"
+
+    def mk(rows, cols):
+        return torch.randn(*g, rows, _r8(cols) + 8, device=dev).to(torch.bfloat16)[..., :cols]
+
+    A = mk(M, K) if am == 0 else mk(K, M)
+    B = mk(N, K) if bm == 0 else mk(K, N)
+    Af = A.float() if am == 0 else A.float().transpose(-1, -2)
+    Bf = B.float() if bm == 0 else B.float().transpose(-1, -2)
+    ref = Af @ Bf.transpose(-1, -2)
+    kw = {}
+    if epi in ("bias", "bias_tanh", "bias_relu"):
+        bias = torch.randn(*g, N, device=dev)
+        act = {"bias": lib.ACT_NONE, "bias_tanh": lib.ACT_TANH, "bias_relu": lib.ACT_RELU}[epi]
+        kw.update(bias=bias, act=act, alpha=0.05)
+        ref = ref * 0.05 + bias[..., None, :]
+        ref = torch.tanh(ref) if epi == "bias_tanh" else (torch.relu(ref) if epi == "bias_relu" else ref)
+    elif epi == "res":
+        res, bias = torch.randn(*g, M, N, device=dev), torch.randn(*g, N, device=dev)
+        kw.update(residual=res, bias=bias)
+        ref = ref + bias[..., None, :] + res
+    elif epi in ("tanh_bwd", "relu_bwd"):
+        aux = torch.randn(*g, M, _r8(N), device=dev).to(torch.bfloat16)[..., :N]
+        kw.update(aux=aux, aux_mode=lib.AUX_TANH_BWD if epi == "tanh_bwd" else lib.AUX_RELU_BWD)
+        ref = ref * (1 - aux.float() ** 2) if epi == "tanh_bwd" else torch.where(aux.float() > 0, ref, torch.zeros_like(ref))
+    of = torch.full((*g, M, N + 3), float("nan"), device=dev)[..., :N]
+    ob = torch.zeros(*g, M, _r8(N), device=dev, dtype=torch.bfloat16)[..., :N]
+    lib.gemm(A, B, a_major=am, b_major=bm, out_f32=of, out_bf16=ob, **kw)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item() + 1e-6
+    # operands are exactly representable bf16, accumulation fp32: only summation-order error remains
+    assert (of - ref).abs().max().item() <= 1e-4 * scale + 1e-5
+    assert (ob.float() - ref).abs().max().item() <= 8e-3 * scale + 1e-3   # bf16 output rounding (2^-8 relative)
+
+
+# ------------------------------------------------------------------------------------------------ get_batch gather
+@pytest.mark.parametrize("M,N,B,T", [(2, 1000, 4, 4), (8, 100000, 64, 256), (3, 50, 1, 49)])
+def test_gather_batch_bit_exact(lib, M, N, B, T):
+    g = torch.Generator().manual_seed(1)
+    store = torch.randint(0, 2 ** 31 - 1, (M, N), generator=g, dtype=torch.int64).to(torch.int32)
+    ix = torch.randint(0, N - T, (B,), generator=g)
+    xb = torch.empty(M, B, T, dtype=torch.int64, device="cuda")
+    yb = torch.empty_like(xb)
+    lib.gather_batch(store.cuda(), ix.cuda(), T, xb, yb)
+    ar = torch.arange(T)
+    ref_x = store.long()[:, ix[:, None] + ar]
+    ref_y = store.long()[:, ix[:, None] + ar + 1]
+    assert torch.equal(xb.cpu(), ref_x) and torch.equal(yb.cpu(), ref_y)
+
+
+# ------------------------------------------------------------------------------------------------ embedding
+@pytest.mark.parametrize("V,B,T,C", [([57, 3], 4, 4, 32), ([1024, 1024, 512], 16, 64, 256), ([30], 2, 5, 36)])
+def test_embedding_fwd_bwd(lib, V, B, T, C):
+    torch.manual_seed(2)
+    M = len(V)
+    voff = torch.tensor([0] + list(torch.tensor(V).cumsum(0)), dtype=torch.int64, device="cuda")
+    tok = torch.randn(sum(V), C, device="cuda")
+    pos = torch.randn(T + 3, C, device="cuda")
+    idx = torch.stack([torch.randint(0, V[m], (B * T,)) for m in range(M)]).cuda()
+    x = torch.empty(M, B * T, C, device="cuda")
+    lib.embed_fwd(idx, tok, voff, pos, x, T)
+    ref = torch.stack([tok[voff[m] + idx[m]] + pos[:T].repeat(B, 1) for m in range(M)])
+    assert torch.equal(x, ref)  # one fp32 add per element: bit-exact
+    dx = torch.randn(M, B * T, C, device="cuda")
+    dtok = torch.full_like(tok, float("nan"))
+    dpos = torch.zeros(T, C, device="cuda")
+    lib.embed_bwd(idx, dx, voff, max(V), dtok, dpos, B, T)
+    ref_tok = torch.zeros_like(tok)
+    for m in range(M):
+        ref_tok.index_add_(0, voff[m] + idx[m], dx[m])
+    assert torch.allclose(dtok, ref_tok, rtol=1e-5, atol=1e-5)
+    ref_pos = dx.view(M, B, T, C).sum((0, 1))
+    assert torch.allclose(dpos, ref_pos, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("G,rows,C", [(2, 16, 32), (3, 192, 256), (1, 100, 512), (2, 128, 1024), (1, 40, 36)])
+def test_layernorm_fwd_bwd(lib, G, rows, C):
+    torch.manual_seed(3)
+    x = (torch.randn(G, rows, C, device="cuda") * 2 + 0.5).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(G, C, device="cuda")).requires_grad_(True)
+    beta = (0.1 * torch.randn(G, C, device="cuda")).requires_grad_(True)
+    ld = _r8(C) + 8
+    y = torch.zeros(G, rows, ld, device="cuda", dtype=torch.bfloat16)[..., :C]
+    mean = torch.empty(G * rows, device="cuda")
+    rstd = torch.empty(G * rows, device="cuda")
+    lib.layernorm_fwd(x.detach(), gamma.detach(), beta.detach(), y, mean, rstd)
+    ref = torch.stack([F.layer_norm(x[g], (C,), gamma[g], beta[g], 1e-5) for g in range(G)])
+    assert (y.float() - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item() + 1e-6   # bf16 rounding of y
+    assert torch.allclose(mean.view(G, rows), x.mean(-1), atol=1e-5)
+    assert torch.allclose(rstd.view(G, rows), (x.var(-1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-5)
+    dy = torch.randn(G, rows, ld, device="cuda").to(torch.bfloat16)[..., :C]
+    din = torch.randn(G, rows, C, device="cuda")
+    ref.backward(dy.float())
+    dout = torch.empty_like(din)
+    dbf = torch.zeros(G, rows, ld, device="cuda", dtype=torch.bfloat16)[..., :C]
+    dgamma = torch.empty(G, C, device="cuda")
+    dbeta = torch.empty(G, C, device="cuda")
+    ws = torch.empty(lib.layernorm_bwd_workspace(G, rows, C), device="cuda")
+    lib.layernorm_bwd(dy, x.detach(), gamma.detach(), mean, rstd, din, dout, dbf, dgamma, dbeta, ws)
+    sc = x.grad.abs().max().item()
+    assert (dout - (din + x.grad)).abs().max().item() <= 1e-5 * sc + 1e-5
+    assert (dbf.float() - dout).abs().max().item() <= 2 ** -8 * dout.abs().max().item()
+    assert torch.allclose(dgamma, gamma.grad, rtol=1e-4, atol=1e-4 * gamma.grad.abs().max().item())
+    assert torch.allclose(dbeta, beta.grad, rtol=1e-4, atol=1e-4 * beta.grad.abs().max().item())
+    # dstream_in = None (first contribution to the stream gradient)
+    lib.layernorm_bwd(dy, x.detach(), gamma.detach(), mean, rstd, None, dout, None, dgamma, dbeta, ws)
+    assert (dout - x.grad).abs().max().item() <= 1e-5 * sc + 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ cross-entropy
+@pytest.mark.parametrize("rows,V", [(16, 57), (16, 3), (4096, 1024), (100, 1000)])
+def test_cross_entropy(lib, rows, V):
+    torch.manual_seed(4)
+    ldl = V + 5
+    logits = (torch.randn(rows, ldl, device="cuda") * 3)[:, :V]
+    tgt = torch.randint(0, V, (rows,), device="cuda")
+    row_loss = torch.empty(rows, device="cuda")
+    loss = torch.empty(1, device="cuda")
+    dl = torch.zeros(rows, _r8(V), device="cuda", dtype=torch.bfloat16)[:, :V]
+    lib.cross_entropy(logits, tgt, row_loss, loss, dl, grad_scale=1.0)
+    lg = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lg, tgt)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item()) + 1e-6
+    sc = lg.grad.abs().max().item()
+    assert (dl.float() - lg.grad).abs().max().item() <= 2 ** -8 * sc + 1e-9
+    lib.cross_entropy(logits, tgt, row_loss, loss, None)
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item()) + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ colsum / casts
+@pytest.mark.parametrize("G,rows,N", [(2, 16, 28), (3, 600, 136), (1, 8192, 512), (2, 5000, 65)])
+def test_colsum(lib, G, rows, N):
+    torch.manual_seed(5)
+    dy = torch.randn(G, rows, _r8(N) + 8, device="cuda").to(torch.bfloat16)[..., :N]
+    out = torch.empty(G, N + 3, device="cuda")[:, :N]
+    ws = torch.empty(lib.colsum_workspace(rows, N, G), device="cuda")
+    lib.colsum(dy, out, ws)
+    ref = dy.float().sum(1)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-4 * math.sqrt(rows))
+
+
+def test_casts(lib):
+    torch.manual_seed(6)
+    src = torch.randn(5, 7, 13, device="cuda")
+    dst = torch.full((5, 8, 16), 7.0, device="cuda", dtype=torch.bfloat16)
+    lib.cast_pad(src, dst)
+    ref = torch.zeros(5, 8, 16, device="cuda")
+    ref[:, :7, :13] = src
+    assert torch.equal(dst, ref.to(torch.bfloat16))
+    back = torch.empty(5, 7, 13, device="cuda")
+    lib.unpad(ref, back)
+    assert torch.equal(back, src)
+    flat = torch.randn(100003, device="cuda")
+    out = torch.empty(100003, device="cuda", dtype=torch.bfloat16)
+    lib.cast_bf16(flat, out)
+    assert torch.equal(out, flat.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ AdamW
+def test_adamw_matches_torch(lib):
+    torch.manual_seed(7)
+    n = 100003
+    p0 = torch.randn(n, device="cuda")
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    shadow = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    sc = torch.zeros(4, device="cuda")
+    for _ in range(5):
+        g = torch.randn(n, device="cuda") * 0.1
+        ref_p.grad = g.clone()
+        opt.step()
+        lib.adamw_tick(step, sc, 1e-3)
+        lib.adamw_step(p, g, m, v, shadow, sc)
+    assert step.item() == 5
+    assert (p - ref_p.detach()).abs().max().item() <= 2e-6      # fp32, same operation order as torch's AdamW
+    assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ attention forward
+def _ref_attention(q, ks, vs, B, T, H, hs):
+    """q [G, B*T, H*hs] fp32; ks/vs lists of same. Returns o [G, B*T, H*hs], per-source o, lse [S, G, B, H, T]."""
+    G = q.shape[0]
+    qh = q.view(G, B, T, H, hs).permute(0, 1, 3, 2, 4)
+    mask = torch.ones(T, T, dtype=torch.bool, device=q.device).tril()
+    outs, lses = [], []
+    for k, v in zip(ks, vs):
+        kh = k.reshape(G, B, T, H, hs).permute(0, 1, 3, 2, 4)
+        vh = v.reshape(G, B, T, H, hs).permute(0, 1, 3, 2, 4)
+        s = (qh @ kh.transpose(-1, -2)) * hs ** -0.5
+        s = s.masked_fill(~mask, float("-inf"))
+        lses.append(torch.logsumexp(s, -1))
+        outs.append((torch.softmax(s, -1) @ vh).permute(0, 1, 3, 2, 4).reshape(G, B * T, H * hs))
+    return sum(outs), torch.stack(outs), torch.stack(lses)
+
+
+ATTN_CASES = [
+    # G, B, T, H, hs, n_src
+    (1, 2, 4, 4, 8, 1),       # demo shape
+    (2, 3, 64, 8, 32, 1),     # c2 self
+    (1, 2, 128, 8, 64, 1),    # c3 self
+    (2, 2, 256, 4, 64, 1),    # c4 self
+    (1, 2, 256, 2, 64, 3),    # cross, 3 sources
+    (1, 1, 1024, 2, 64, 2),   # c5 long context
+    (1, 2, 100, 2, 16, 2),    # ragged T
+    (1, 3, 5, 2, 8, 1),       # T < block_size (generate)
+]
+
+
+@pytest.mark.parametrize("G,B,T,H,hs,S", ATTN_CASES)
+def test_attention_fwd(lib, G, B, T, H, hs, S):
+    torch.manual_seed(8)
+    C = H * hs
+    q = torch.randn(G, B * T, C, device="cuda").to(torch.bfloat16)
+    # k and v of a source interleaved per head like the cross-attention kv projection output: [.., H, 2*hs]
+    kv = [torch.randn(G, B * T, H, 2 * hs, device="cuda").to(torch.bfloat16) for _ in range(S)]
+    ks = [t[..., :hs] for t in kv]
+    vs = [t[..., hs:] for t in kv]
+    o = torch.zeros(G, B * T, C, device="cuda", dtype=torch.bfloat16)
+    o_src = torch.zeros(S, G, B * T, C, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(S, G, B, H, T, device="cuda")
+    k_views = [t.view(G, B * T, 2 * C) for t in kv]
+    v_views = [t.view(G, B * T, 2 * C)[..., hs:] for t in kv]
+    lib.attention_fwd(q, k_views, v_views, o, lse, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs, o_src=o_src)
+    torch.cuda.synchronize()
+    ro, ros, rl = _ref_attention(q.float(), [k.float() for k in ks], [v.float() for v in vs], B, T, H, hs)
+    # P is rounded to bf16 before P V and o is stored in bf16: 2^-8 relative each
+    assert (o.float() - ro).abs().max().item() <= 1.5e-2 * ro.abs().max().item()
+    assert (o_src.float() - ros).abs().max().item() <= 1.5e-2 * ros.abs().max().item()
+    assert (lse - rl).abs().max().item() <= 2e-3

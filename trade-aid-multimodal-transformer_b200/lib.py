@@ -148,3 +148,167 @@ def gemm(A, B, *, a_major=0, b_major=0, out_f32=None, out_bf16=None, bias=None, 
         ep.out_bf16, ep.ld_bf16, ep.bf16_gs0, ep.bf16_gs1 = out_bf16.data_ptr(), out_bf16.stride(-2), s0, s1
     a, b = _operand(A, a_major), _operand(B, b_major)
     _check(_lib.ta_gemm_bf16(C.byref(a), C.byref(b), M, N, K, G0, G1, C.byref(ep), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+class TaAttnTensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("head_stride", C.c_int64), ("gs", C.c_int64)]
+
+
+_lib.ta_attention_fwd.restype = C.c_int32
+_lib.ta_attention_fwd.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.c_int32,
+                                  C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_void_p]
+
+
+def _attn_tensor(t, head_stride):
+    """t: bf16 view [G, B*T, >=H*hs] (or [B*T, ...] for G = 1) whose column 0 is head 0 / dim 0."""
+    assert t.element_size() == 2 and t.stride(-1) == 1
+    gs = t.stride(0) if t.dim() == 3 else 0
+    return TaAttnTensor(t.data_ptr(), t.stride(-2), head_stride, gs)
+
+
+def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None, o_src=None):
+    """q: [G, B*T, *]; ks/vs: lists (one per source) of [G, B*T, *] views; o: [G, B*T, H*hs] bf16;
+    lse: fp32 [n_src, G, B, H, T]; o_src: optional [n_src, G, B*T, H*hs] bf16."""
+    n_src = len(ks)
+    G = q.shape[0] if q.dim() == 3 else 1
+    hq = head_stride_q if head_stride_q is not None else hs
+    hkv = head_stride_kv if head_stride_kv is not None else hs
+    qa = (TaAttnTensor * 1)(_attn_tensor(q, hq))
+    ka = (TaAttnTensor * n_src)(*[_attn_tensor(k, hkv) for k in ks])
+    va = (TaAttnTensor * n_src)(*[_attn_tensor(v, hkv) for v in vs])
+    assert o.stride(-1) == 1 and lse.is_contiguous() and lse.numel() == n_src * G * B * H * T
+    o_gs = o.stride(0) if o.dim() == 3 else 0
+    if o_src is not None:
+        assert o_src.stride(-2) == o.stride(-2) and (o.dim() < 3 or o_src.stride(1) == o.stride(0))
+    _check(_lib.ta_attention_fwd(qa, ka, va, n_src, _ptr(o), o.stride(-2), o_gs, _ptr(o_src),
+                                 o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, 0.0, 0,
+                                 _stream()))
+
+
+# ---------------------------------------------------------------------------------------------------- row ops
+def _sig(name, *argtypes, restype=C.c_int32):
+    fn = getattr(_lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_P, _I32, _I64, _F32, _F64, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_uint64
+_gather_batch = _sig("ta_gather_batch", _P, _I64, _I32, _P, _I32, _I32, _P, _P, _P)
+_embed_fwd = _sig("ta_embed_fwd", _P, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _P)
+_embed_bwd = _sig("ta_embed_bwd", _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _P)
+_ln_fwd = _sig("ta_layernorm_fwd", _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _F32, _P)
+_ln_bwd_ws = _sig("ta_layernorm_bwd_workspace_floats", _I64, _I64, _I32, restype=_I64)
+_ln_bwd = _sig("ta_layernorm_bwd", _P, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _P)
+_ce = _sig("ta_cross_entropy", _P, _I64, _P, _P, _P, _P, _I64, _I64, _I32, _F32, _P)
+_colsum_ws = _sig("ta_colsum_workspace_floats", _I64, _I32, _I32, restype=_I64)
+_colsum = _sig("ta_colsum_bf16", _P, _I64, _I64, _P, _I64, _P, _I64, _I32, _I32, _P)
+_cast_pad = _sig("ta_cast_pad_bf16", _P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P)
+_unpad = _sig("ta_unpad_f32", _P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P)
+_cast = _sig("ta_cast_bf16", _P, _P, _I64, _P)
+_adamw_tick = _sig("ta_adamw_tick", _P, _P, _F64, _F64, _F64, _F64, _P)
+_adamw_step = _sig("ta_adamw_step", _P, _P, _P, _P, _P, _I64, _P, _F32, _F32, _F32, _F32, _P)
+
+
+def gather_batch(store, ix, T, xb, yb):
+    """store int32 [M, N]; ix int64 [B] (device); xb, yb int64 [M, B, T] (training_utils.py:378-379)."""
+    M, B = store.shape[0], ix.shape[0]
+    assert store.stride(1) == 1 and xb.is_contiguous() and yb.is_contiguous() and xb.shape == (M, B, T)
+    _check(_gather_batch(_ptr(store), store.stride(0), M, _ptr(ix), B, T, _ptr(xb), _ptr(yb), _stream()))
+
+
+def embed_fwd(idx, tok, voff, pos, x, T):
+    """idx int64 [M, rows]; tok fp32 [sumV, C]; voff int64 [M+1]; pos fp32 [block, C]; x fp32 [M, rows, C]."""
+    M, rows = idx.shape
+    Cc = tok.shape[1]
+    assert idx.is_contiguous() and tok.is_contiguous() and pos.is_contiguous() and x.is_contiguous()
+    _check(_embed_fwd(_ptr(idx), _ptr(tok), _ptr(voff), _ptr(pos), _ptr(x), M, rows, T, Cc, _stream()))
+
+
+def embed_bwd(idx, dx, voff, max_vocab, dtok, dpos, B, T):
+    M = idx.shape[0]
+    Cc = dx.shape[-1]
+    assert idx.is_contiguous() and dx.is_contiguous() and dtok.is_contiguous() and dpos.is_contiguous()
+    _check(_embed_bwd(_ptr(idx), _ptr(dx), _ptr(voff), max_vocab, _ptr(dtok), _ptr(dpos), M, B, T, Cc, _stream()))
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
+    """x fp32 [G, rows, C] contiguous; gamma/beta fp32 [G, C]; y bf16 [G, rows, ldy] (ldy = stride of rows)."""
+    G, rows, Cc = x.shape
+    assert x.is_contiguous() and gamma.is_contiguous() and beta.is_contiguous() and y.stride(-1) == 1
+    assert y.stride(0) == rows * y.stride(1)
+    _check(_ln_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), y.stride(1), _ptr(mean), _ptr(rstd), G * rows, rows, Cc,
+                   eps, _stream()))
+
+
+def layernorm_bwd_workspace(G, rows, Cc):
+    return int(_ln_bwd_ws(G * rows, rows, Cc))
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dstream_in, dstream_out, dstream_bf16, dgamma, dbeta, workspace):
+    G, rows, Cc = x.shape
+    assert x.is_contiguous() and dy.stride(-1) == 1 and dy.stride(0) == rows * dy.stride(1)
+    assert dstream_out.is_contiguous() and (dstream_in is None or dstream_in.is_contiguous())
+    assert dgamma.is_contiguous() and dbeta.is_contiguous()
+    ldb = 0
+    if dstream_bf16 is not None:
+        assert dstream_bf16.stride(-1) == 1 and dstream_bf16.stride(0) == rows * dstream_bf16.stride(1)
+        ldb = dstream_bf16.stride(1)
+    assert workspace.numel() >= layernorm_bwd_workspace(G, rows, Cc)
+    _check(_ln_bwd(_ptr(dy), dy.stride(1), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dstream_in),
+                   _ptr(dstream_out), _ptr(dstream_bf16), ldb, _ptr(dgamma), _ptr(dbeta), _ptr(workspace), G * rows,
+                   rows, Cc, _stream()))
+
+
+def cross_entropy(logits, targets, row_loss, loss_mean, dlogits=None, grad_scale=1.0):
+    """logits fp32 [rows, V] (ld = stride 0); targets int64 [rows]; loss_mean fp32 [1]; dlogits bf16 [rows, ldd]."""
+    rows, V = logits.shape
+    assert logits.stride(1) == 1 and targets.is_contiguous()
+    _check(_ce(_ptr(logits), logits.stride(0), _ptr(targets), _ptr(row_loss), _ptr(loss_mean), _ptr(dlogits),
+               dlogits.stride(0) if dlogits is not None else 0, rows, V, grad_scale, _stream()))
+
+
+def colsum_workspace(rows, N, G):
+    return int(_colsum_ws(rows, N, G))
+
+
+def colsum(dy, out, workspace):
+    """dy bf16 [G, rows, N] (row stride ld); out fp32 [G, N] (group stride out.stride(0))."""
+    G, rows, N = dy.shape
+    assert dy.stride(-1) == 1 and out.stride(-1) == 1 and workspace.numel() >= colsum_workspace(rows, N, G)
+    _check(_colsum(_ptr(dy), dy.stride(1), dy.stride(0), _ptr(out), out.stride(0), _ptr(workspace), rows, N, G,
+                   _stream()))
+
+
+def cast_pad(src, dst):
+    """src fp32 [G, R, Cs] (inner stride 1), dst bf16 [G, Rd, Cd] with Rd >= R, Cd >= Cs: zero padded cast."""
+    G, R, Cs = src.shape
+    _, Rd, Cd = dst.shape
+    assert src.stride(2) == 1 and dst.stride(2) == 1 and dst.shape[0] == G and Rd >= R and Cd >= Cs
+    _check(_cast_pad(_ptr(src), src.stride(0), src.stride(1), _ptr(dst), dst.stride(0), dst.stride(1), G, R, Cs, Rd, Cd,
+                     _stream()))
+
+
+def unpad(src, dst):
+    """dst fp32 [G, R, Cn] = src fp32 [G, >=R, >=Cn][:, :R, :Cn]."""
+    G, R, Cn = dst.shape
+    assert src.stride(2) == 1 and dst.stride(2) == 1
+    _check(_unpad(_ptr(src), src.stride(0), src.stride(1), _ptr(dst), dst.stride(0), dst.stride(1), G, R, Cn, _stream()))
+
+
+def cast_bf16(src, dst):
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    _check(_cast(_ptr(src), _ptr(dst), src.numel(), _stream()))
+
+
+def adamw_tick(step_dev, scalars_dev, lr, beta1=0.9, beta2=0.999, weight_decay=0.01):
+    _check(_adamw_tick(_ptr(step_dev), _ptr(scalars_dev), lr, beta1, beta2, weight_decay, _stream()))
+
+
+def adamw_step(p, g, m, v, shadow, scalars_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n and (shadow is None or shadow.numel() == n)
+    _check(_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), n, _ptr(scalars_dev), beta1, beta2, eps,
+                       grad_scale, _stream()))
