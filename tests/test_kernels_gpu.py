@@ -276,3 +276,36 @@ def test_attention_fwd(lib, G, B, T, H, hs, S):
     assert (o.float() - ro).abs().max().item() <= 1.5e-2 * ro.abs().max().item()
     assert (o_src.float() - ros).abs().max().item() <= 1.5e-2 * ros.abs().max().item()
     assert (lse - rl).abs().max().item() <= 2e-3
+
+
+ATTN_BWD_CASES = [c for c in ATTN_CASES if c[2] <= 256]
+
+
+@pytest.mark.parametrize("G,B,T,H,hs,S", ATTN_BWD_CASES)
+def test_attention_bwd(lib, G, B, T, H, hs, S):
+    torch.manual_seed(9)
+    C = H * hs
+    q = torch.randn(G, B * T, C, device="cuda").to(torch.bfloat16)
+    kv = [torch.randn(G, B * T, H, 2 * hs, device="cuda").to(torch.bfloat16) for _ in range(S)]
+    d_o = torch.randn(G, B * T, C, device="cuda").to(torch.bfloat16)
+    o = torch.zeros(G, B * T, C, device="cuda", dtype=torch.bfloat16)
+    o_src = torch.zeros(S, G, B * T, C, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(S, G, B, H, T, device="cuda")
+    k_views = [t.view(G, B * T, 2 * C) for t in kv]
+    v_views = [t.view(G, B * T, 2 * C)[..., hs:] for t in kv]
+    lib.attention_fwd(q, k_views, v_views, o, lse, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs, o_src=o_src)
+    dq = torch.full_like(q, float("nan"))
+    dkv = [torch.full((G, B * T, 2 * C), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(S)]
+    lib.attention_bwd(q, k_views, v_views, o, d_o, lse, dq, dkv, [t[..., hs:] for t in dkv], B=B, T=T, H=H, hs=hs,
+                      head_stride_kv=2 * hs, o_src=o_src if S > 1 else None)
+    torch.cuda.synchronize()
+    qf = q.float().requires_grad_(True)
+    kvf = [t.float().requires_grad_(True) for t in kv]
+    ro, _, _ = _ref_attention(qf, [t[..., :hs] for t in kvf], [t[..., hs:] for t in kvf], B, T, H, hs)
+    ro.backward(d_o.float())
+    # P, dS are rounded to bf16 before the gradient UMMAs and outputs are bf16: ~2^-8 relative per rounding
+    tol = 2e-2
+    assert (dq.float() - qf.grad).abs().max().item() <= tol * qf.grad.abs().max().item()
+    for s in range(S):
+        ref = kvf[s].grad.view(G, B * T, 2 * C)
+        assert (dkv[s].float() - ref).abs().max().item() <= tol * ref.abs().max().item()

@@ -44,13 +44,17 @@ struct AttnBwdParams {
   GradOut dv[ATTB_MAX_SRC];
 };
 
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float* v, int n) {
-  for (int i = 0; i < n; i += 8) {
-    uint4 u;
-    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+template <int DP>
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[DP], int n) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[i + 2 * e], v[i + 2 * e + 1]);
-    *reinterpret_cast<uint4*>(dst + i) = u;
+  for (int i = 0; i < DP; i += 8) {
+    if (i < n) {
+      uint4 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[i + 2 * e], v[i + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(dst + i) = u;
+    }
   }
 }
 

@@ -312,3 +312,31 @@ def adamw_step(p, g, m, v, shadow, scalars_dev, beta1=0.9, beta2=0.999, eps=1e-8
     assert g.numel() == n and m.numel() == n and v.numel() == n and (shadow is None or shadow.numel() == n)
     _check(_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), n, _ptr(scalars_dev), beta1, beta2, eps,
                        grad_scale, _stream()))
+
+
+_lib.ta_attention_bwd.restype = C.c_int32
+_lib.ta_attention_bwd.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor),
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_void_p]
+
+
+def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None,
+                  o_src=None):
+    """Gradients of attention_fwd. d_o has the layout of o; dq of q; dks[s]/dvs[s] of ks[s]/vs[s] (bf16)."""
+    n_src = len(ks)
+    G = q.shape[0] if q.dim() == 3 else 1
+    hq = head_stride_q if head_stride_q is not None else hs
+    hkv = head_stride_kv if head_stride_kv is not None else hs
+    qa = (TaAttnTensor * 1)(_attn_tensor(q, hq))
+    ka = (TaAttnTensor * n_src)(*[_attn_tensor(k, hkv) for k in ks])
+    va = (TaAttnTensor * n_src)(*[_attn_tensor(v, hkv) for v in vs])
+    dqa = (TaAttnTensor * 1)(_attn_tensor(dq, hq))
+    dka = (TaAttnTensor * n_src)(*[_attn_tensor(k, hkv) for k in dks])
+    dva = (TaAttnTensor * n_src)(*[_attn_tensor(v, hkv) for v in dvs])
+    assert o.stride(-1) == 1 and d_o.stride(-1) == 1 and d_o.stride(-2) == o.stride(-2)
+    o_gs = o.stride(0) if o.dim() == 3 else 0
+    assert o.dim() < 3 or d_o.stride(0) == o.stride(0)
+    _check(_lib.ta_attention_bwd(qa, ka, va, n_src, _ptr(o), _ptr(o_src), o_src.stride(0) if o_src is not None else 0,
+                                 _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), dqa, dka, dva, G, B, T, H, hs, 0.0, 0,
+                                 _stream()))
