@@ -1,0 +1,78 @@
+"""Host-logic tests of the engine on CPU: the forward/backward PROGRAM (buffer wiring, grouping, packed layouts, the
+hand-written backward) driven through tests/emu_ops.py and compared with fixtures made by the reference itself.
+float32 activations: must agree with the reference to fp32 round-off (proves the wiring exactly);
+bfloat16 activations: must agree within the bf16 budget of SURVEY.md appendix D."""
+import pytest
+import torch
+
+import emu_ops
+from conftest import load_golden
+from tradeaid_b200.engine import Engine
+from tradeaid_b200.params import Dims
+
+CASES = ["demo", "m3", "m3_short", "hs32", "nocross"]
+
+
+def build(name, act_dtype):
+    g = load_golden(f"model_{name}.pt")
+    c = g["cfg"]
+    dims = Dims(c["V"], c["cross"], c["T"], c["C"], c["H"], c["L"])
+    eng = Engine(dims, "cpu", ops=emu_ops, act_dtype=act_dtype)
+    nv = eng.layout.named_views(eng.master)
+    assert set(nv) == set(g["state_dict"])
+    for k, v in g["state_dict"].items():
+        nv[k].copy_(v)
+    return g, eng
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_backward_exact_wiring(name):
+    g, eng = build(name, torch.float32)
+    idx, tgt = torch.stack(g["idx"]), torch.stack(g["tgt"])
+    logits, losses = eng.forward(idx, tgt, save=True)
+    for a, b in zip(logits, g["logits"]):
+        assert (a - b).abs().max().item() <= 2e-5, (a - b).abs().max()
+    for a, b in zip(losses, g["losses"]):
+        assert abs(float(a) - float(b)) <= 2e-6 * max(1.0, abs(float(b)))
+    eng.backward()
+    gv = eng.layout.named_views(eng.grad)
+    for k, ref in g["grads"].items():
+        if not eng.layout.is_active(k):
+            assert gv[k].abs().max().item() == 0.0
+            continue
+        sc = ref.abs().max().item() + 1e-8
+        assert (gv[k] - ref).abs().max().item() <= 1e-4 * sc + 1e-7, k
+    # inference mode (no saved activations, buffers reused across layers) gives the same logits
+    logits2, none = eng.forward(idx, None, save=False)
+    assert none is None
+    for a, b in zip(logits2, g["logits"]):
+        assert (a - b).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_backward_bf16_budget(name):
+    g, eng = build(name, torch.bfloat16)
+    idx, tgt = torch.stack(g["idx"]), torch.stack(g["tgt"])
+    logits, losses = eng.forward(idx, tgt, save=True)
+    for a, b in zip(logits, g["logits"]):
+        rel = (a - b).norm() / b.norm()
+        assert rel <= 1.5e-2, rel          # normwise; SURVEY.md D measured ~6e-3 at init for bf16 operands
+    for a, b in zip(losses, g["losses"]):
+        assert abs(float(a) - float(b)) <= 2e-3 * abs(float(b))
+    eng.backward()
+    gv = eng.layout.named_views(eng.grad)
+    num = den = 0.0
+    for k, ref in g["grads"].items():
+        if eng.layout.is_active(k):
+            num += float((gv[k] - ref).pow(2).sum())
+            den += float(ref.pow(2).sum())
+    assert (num / den) ** 0.5 <= 3e-2
+
+
+def test_runs_helper():
+    from tradeaid_b200.engine import _runs
+    assert _runs([0, 3]) == [(0, 3, 2)]
+    assert _runs([0, 1, 2, 3]) == [(0, 1, 4)]
+    assert _runs([1]) == [(1, 1, 1)]
+    assert _runs([0, 1, 3, 7]) == [(0, 1, 2), (3, 4, 2)]
+    assert _runs([0, 2, 4, 5]) == [(0, 2, 3), (5, 1, 1)]

@@ -1,0 +1,426 @@
+"""The forward/backward program of the trade-AId multimodal transformer as a sequence of C-ABI kernel launches.
+
+Restates /root/reference/model.py:380-402 (forward + loss) and its autograd backward over packed buffers:
+every modality of a layer goes through ONE grouped launch per op (the reference loops over modalities, heads and
+key/value sources in Python: model.py:90, 222-242), activations live in bf16 between GEMMs, the residual stream, the
+LayerNorm statistics, softmax, tanh and the loss stay in fp32.
+
+`ops` is the kernel namespace — `tradeaid_b200.lib` (ctypes over libtradeaid_b200.so) in the product. Tests inject a
+CPU emulation of the same ops to check this host logic without a GPU; the engine itself never falls back.
+"""
+from __future__ import annotations
+
+import torch
+
+from .params import Dims, Layout, r8
+
+ACT_NONE, ACT_TANH, ACT_RELU = 0, 1, 2
+AUX_TANH_BWD, AUX_RELU_BWD = 1, 2
+
+
+def _runs(idxs):
+    """Split a sorted index list into maximal arithmetic progressions -> list of (start, step, count)."""
+    out, k = [], 0
+    while k < len(idxs):
+        if k + 1 == len(idxs):
+            out.append((idxs[k], 1, 1))
+            break
+        step = idxs[k + 1] - idxs[k]
+        n = 2
+        while k + n < len(idxs) and idxs[k + n] - idxs[k + n - 1] == step:
+            n += 1
+        out.append((idxs[k], step, n))
+        k += n
+    return out
+
+
+class Engine:
+    def __init__(self, dims: Dims, device, ops=None, act_dtype=torch.bfloat16):
+        self.d = dims
+        # storage type of GEMM operands / saved activations. bf16 in the product (the CUDA kernels accept nothing
+        # else); the CPU test-suite also runs the host logic with float32 to check the backward wiring exactly.
+        self.act_dtype = act_dtype
+        self.layout = Layout(dims)
+        self.device = torch.device(device)
+        if ops is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("tradeaid_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+            from . import lib as ops  # raises ImportError if libtradeaid_b200.so is missing
+        self.ops = ops
+        n = self.layout.total
+        self.master = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.shadow = torch.zeros(n, dtype=act_dtype, device=self.device)
+        self.P = self.layout.views(self.master)
+        self.G = self.layout.views(self.grad)
+        self.S = self.layout.views(self.shadow)
+        self._padded = {}      # kind -> zero-padded bf16 (or fp32 for biases) copy when the direct view is not TMA-able
+        self._make_padded()
+        self._bufs = {}
+        self._voff = torch.tensor(dims.voff, dtype=torch.int64, device=self.device)
+        self._saved = None
+        self.shadows_stale = True
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _make_padded(self):
+        d = self.d
+        dev = self.device
+        L, M, H = d.n_layer, d.M, d.n_head
+        if d.h2p != d.h2:
+            self._padded["sa_w1"] = torch.zeros(L, M, 3, H, d.h2p, d.n_embd, dtype=self.act_dtype, device=dev)
+            self._padded["sa_b1"] = torch.zeros(L, M, 3, H, d.h2p, dtype=torch.float32, device=dev)
+            self._padded["sa_w2"] = torch.zeros(L, M, 3, H, d.hs, d.h2p, dtype=self.act_dtype, device=dev)
+        for k, (off, shape) in self.layout.kinds.items():
+            if k in self._padded or len(shape) < 2 or k in ("tok", "pos") or k.startswith("ln"):
+                continue
+            if k.split("_")[1].startswith(("b", "pb")):
+                continue
+            if shape[-1] % 8 != 0 and shape[-1] > 0:
+                self._padded[k] = torch.zeros(*shape[:-1], r8(shape[-1]), dtype=self.act_dtype, device=dev)
+
+    def refresh_shadows(self, flat_cast=True):
+        """bf16 GEMM-operand copies of the fp32 master weights. `flat_cast=False` when the fused AdamW has already
+        written the flat shadow and only the zero-padded copies (odd shapes) are left to do."""
+        ops, d = self.ops, self.d
+        if flat_cast:
+            ops.cast_bf16(self.master, self.shadow)
+        for k, dst in self._padded.items():
+            src = self.P[k]
+            if k == "sa_w1":
+                ops.cast_pad(src.reshape(-1, d.h2, d.n_embd), dst.view(-1, d.h2p, d.n_embd))
+            elif k == "sa_b1":
+                ops.unpad(src.reshape(-1, 1, d.h2), dst.view(-1, 1, d.h2p)[..., :d.h2])
+            else:
+                ops.cast_pad(src.reshape(-1, src.shape[-2], src.shape[-1]), dst.view(-1, dst.shape[-2], dst.shape[-1]))
+        self.shadows_stale = False
+
+    def W(self, kind):
+        """bf16 operand view of a weight kind (logical shape, possibly with a padded pitch)."""
+        if kind in self._padded and kind not in ("sa_b1",):
+            src_shape = self.layout.kinds[kind][1]
+            t = self._padded[kind]
+            if kind in ("sa_w1",):
+                return t
+            return t[..., :src_shape[-1]]
+        return self.S[kind]
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def buf(self, name, shape, dtype):
+        key = name
+        t = self._bufs.get(key)
+        shape = tuple(int(s) for s in shape)
+        if t is None or t.shape != shape or t.dtype != dtype:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def release_buffers(self):
+        self._bufs.clear()
+        self._saved = None
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, idx, targets=None, save=True):
+        """idx, targets: int64 [M, B, T'] on the device (T' <= block_size). Returns (logits list of fp32 [B, T', V_i],
+        losses fp32 [M] or None). With save=True the activations needed by backward() are kept."""
+        d, ops, P = self.d, self.ops, self.P
+        if self.shadows_stale:
+            self.refresh_shadows()
+        M, C, H, hs, L = d.M, d.n_embd, d.n_head, d.hs, d.n_layer
+        h2p = d.h2p
+        assert idx.dim() == 3 and idx.shape[0] == M and idx.dtype == torch.int64 and idx.is_contiguous()
+        _, B, T = idx.shape
+        if T > d.block_size:
+            raise ValueError(f"sequence length {T} exceeds block_size {d.block_size}")
+        BT = B * T
+        bf, f32 = self.act_dtype, torch.float32
+        S = {"B": B, "T": T, "layers": [], "idx": idx}
+
+        def nb(name, l, shape, dtype):
+            return self.buf(f"{name}.{l}" if save else name, shape, dtype)
+
+        x = nb("x0", 0, (M, BT, C), f32)
+        ops.embed_fwd(idx.view(M, BT), P["tok"], self._voff, P["pos"], x, T)
+        for l in range(L):
+            Sl = {}
+            Sl["x0"] = x
+            h1 = nb("h1", l, (M, BT, C), bf)
+            st1 = nb("st1", l, (2, M * BT), f32)
+            ops.layernorm_fwd(x, P["ln1_w"][l], P["ln1_b"][l], h1, st1[0], st1[1])
+            # q/k/v tanh-MLPs, stage 1: all heads and q|k|v in one GEMM (N = 3*H*h2p)   model.py:36-50, 62-63, 71
+            hid = nb("hid", l, (M, BT, 3 * H * h2p), bf)
+            b1 = (self._padded["sa_b1"] if "sa_b1" in self._padded else P["sa_b1"])[l].reshape(M, 3 * H * h2p)
+            ops.gemm(h1, self.W("sa_w1")[l].reshape(M, 3 * H * h2p, C), bias=b1, act=ACT_TANH, out_bf16=hid)
+            # stage 2: block-diagonal [hs x h2] per (q|k|v, head): grouped GEMM, groups (3H within the row, modality)
+            qkv = nb("qkv", l, (M, BT, 3 * C), bf)
+            ops.gemm(self._hid_groups(hid, BT), self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1),
+                     out_bf16=self._qkv_groups(qkv, BT))
+            o = nb("o", l, (M, BT, C), bf)
+            lse = nb("lse", l, (1, M, B, H, T), f32)
+            ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs)
+            # projection MLP + residual   model.py:82-91, 224
+            p1 = nb("p1", l, (M, BT, C // 2), bf)
+            ops.gemm(o, self.W("sa_pw1")[l], bias=P["sa_pb1"][l], act=ACT_TANH, out_bf16=p1)
+            x1 = nb("x1", l, (M, BT, C), f32)
+            ops.gemm(p1, self.W("sa_pw2")[l], bias=P["sa_pb2"][l], residual=x, out_f32=x1)
+            # feed-forward + residual   model.py:167-172, 225
+            hh = nb("h2", l, (M, BT, C), bf)
+            st2 = nb("st2", l, (2, M * BT), f32)
+            ops.layernorm_fwd(x1, P["ln2_w"][l], P["ln2_b"][l], hh, st2[0], st2[1])
+            ffh = nb("ffh", l, (M, BT, 4 * C), bf)
+            ops.gemm(hh, self.W("ff_w1")[l], bias=P["ff_b1"][l], act=ACT_RELU, out_bf16=ffh)
+            x2 = nb("x2", l, (M, BT, C), f32)
+            a_bf = nb("a_bf", l, (M, BT, C), bf) if d.Xc else None
+            ops.gemm(ffh, self.W("ff_w2")[l], bias=P["ff_b2"][l], residual=x1, out_f32=x2, out_bf16=a_bf)
+            Sl.update(h1=h1, st1=st1, hid=hid, qkv=qkv, o=o, lse=lse, p1=p1, x1=x1, h2=hh, st2=st2, ffh=ffh, x2=x2,
+                      a_bf=a_bf)
+            x = x2
+            if d.Xc:
+                x = self._cross_forward(l, Sl, x2, a_bf, B, T, nb)
+            S["layers"].append(Sl)
+        # output heads   model.py:339-352
+        hf = nb("hf", 0, (M, BT, C), bf)
+        stf = nb("stf", 0, (2, M * BT), f32)
+        ops.layernorm_fwd(x, P["lnf_w"], P["lnf_b"], hf, stf[0], stf[1])
+        logits, hhs = [], []
+        for i, V in enumerate(d.vocab_sizes):
+            V2 = V // 2
+            hd = nb(f"hd{i}", 0, (BT, r8(max(V2, 1))), bf)[:, :V2]
+            lg = nb(f"logits{i}", 0, (BT, V), f32)
+            if V2 > 0:
+                ops.gemm(hf[i], self.W(f"hd_w1_{i}"), bias=P[f"hd_b1_{i}"], act=ACT_TANH, out_bf16=hd)
+                ops.gemm(hd, self.W(f"hd_w2_{i}"), bias=P[f"hd_b2_{i}"], out_f32=lg)
+            else:  # V == 1: Linear(V//2 = 0 -> 1) is just its bias
+                lg.copy_(P[f"hd_b2_{i}"].expand(BT, V))
+            logits.append(lg)
+            hhs.append(hd)
+        S.update(x_final=x, hf=hf, stf=stf, hd=hhs, logits=logits)
+        losses = None
+        if targets is not None:
+            assert targets.shape == idx.shape and targets.dtype == torch.int64 and targets.is_contiguous()
+            losses = nb("losses", 0, (M,), f32)
+            dls = []
+            for i, V in enumerate(d.vocab_sizes):
+                row_loss = nb(f"rowloss{i}", 0, (BT,), f32)
+                dl = nb(f"dlogits{i}", 0, (BT, r8(V)), bf)[:, :V] if save else None
+                ops.cross_entropy(logits[i], targets[i].view(BT), row_loss, losses[i:i + 1], dl, 1.0)
+                dls.append(dl)
+            S["dlogits"] = dls
+        self._saved = S if save else None
+        return [lg.view(B, T, -1) for lg in logits], losses
+
+    def _hid_groups(self, hid, BT):
+        d = self.d
+        M, H, h2, h2p = d.M, d.n_head, d.h2, d.h2p
+        return hid.as_strided((M, 3 * H, BT, h2), (BT * 3 * H * h2p, h2p, 3 * H * h2p, 1))
+
+    def _qkv_groups(self, qkv, BT):
+        d = self.d
+        M, H, hs, C = d.M, d.n_head, d.hs, d.n_embd
+        return qkv.as_strided((M, 3 * H, BT, hs), (BT * 3 * C, hs, 3 * C, 1))
+
+    def _sub(self, t, idxs):
+        """Views of t[idxs] (first dim) as a list of (view, positions-in-idxs) with arithmetic-progression strides."""
+        out, pos = [], 0
+        for start, step, n in _runs(idxs):
+            out.append((t[start:start + step * (n - 1) + 1:step], list(range(pos, pos + n))))
+            pos += n
+        return out
+
+    def _cross_forward(self, l, Sl, x2, a_bf, B, T, nb):
+        """Selective cross-attention of layer l (model.py:136-159, 229-242). Every enabled modality queries the SAME
+        snapshot x2 of all other modalities, so all K/V projections are issued before any residual update."""
+        d, ops, P = self.d, self.ops, self.P
+        M, C, H, hs, Xc = d.M, d.n_embd, d.n_head, d.hs, d.Xc
+        BT = B * T
+        bf, f32 = self.act_dtype, torch.float32
+        K = M - 1
+        hc = nb("hc", l, (Xc, BT, C), bf)
+        stc = nb("stc", l, (2, Xc * BT), f32)
+        for xv, pos in self._sub(x2, d.xc):
+            for k, p in enumerate(pos):  # LayerNorm wants a dense [G, rows, C] block: one launch per enabled modality
+                ops.layernorm_fwd(xv[k:k + 1], P["lnc_w"][l][p:p + 1], P["lnc_b"][l][p:p + 1], hc[p:p + 1],
+                                  stc[0][p * BT:(p + 1) * BT], stc[1][p * BT:(p + 1) * BT])
+        qc = nb("qc", l, (Xc, BT, C), bf)
+        ops.gemm(hc, self.W("ca_wq")[l].reshape(Xc, C, C), out_bf16=qc)
+        kvs = []
+        Wkv = self.W("ca_wkv")[l]  # [sum_j nq_j, H, 2hs, C]
+        for j in range(M):
+            nq = len(d.queriers[j])
+            if nq == 0:
+                kvs.append(None)
+                continue
+            kv = nb(f"kv{j}", l, (BT, nq * 2 * C), bf)
+            ops.gemm(a_bf[j], Wkv[d.qoff[j]:d.qoff[j + 1]].reshape(nq * 2 * C, C), out_bf16=kv)
+            kvs.append(kv)
+        oc = nb("oc", l, (Xc, BT, C), bf)
+        ocs = nb("ocs", l, (Xc, K, 1, BT, C), bf) if K > 1 else None
+        lsec = nb("lsec", l, (Xc, K, 1, B, H, T), f32)
+        for xi, i in enumerate(d.xc):
+            ks, vs = self._kv_views(kvs, i)
+            ops.attention_fwd(qc[xi:xi + 1], ks, vs, oc[xi:xi + 1], lsec[xi], B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
+                              o_src=ocs[xi] if ocs is not None else None)
+        pc1 = nb("pc1", l, (Xc, BT, C // 2), bf)
+        ops.gemm(oc, self.W("ca_pw1")[l], bias=P["ca_pb1"][l], act=ACT_TANH, out_bf16=pc1)
+        x3 = nb("x3", l, (M, BT, C), f32)
+        for (xv, pos), (ov, _) in zip(self._sub(x2, d.xc), self._sub(x3, d.xc)):
+            p0, p1 = pos[0], pos[-1] + 1
+            ops.gemm(pc1[p0:p1], self.W("ca_pw2")[l][p0:p1], bias=P["ca_pb2"][l][p0:p1], residual=xv, out_f32=ov)
+        for i in range(M):
+            if i not in d.xc:
+                x3[i].copy_(x2[i])
+        Sl.update(hc=hc, stc=stc, qc=qc, kvs=kvs, oc=oc, ocs=ocs, lsec=lsec, pc1=pc1, x3=x3)
+        return x3
+
+    def _kv_views(self, kvs, i, grads=False):
+        """K and V column views (head 0, dim 0) of querier i inside each source's stacked K/V buffer."""
+        d = self.d
+        C, hs = d.n_embd, d.hs
+        ks, vs = [], []
+        for j in d.others(i):
+            p = d.queriers[j].index(i)
+            blk = kvs[j][:, p * 2 * C:(p + 1) * 2 * C].unsqueeze(0)
+            ks.append(blk)
+            vs.append(blk[..., hs:])
+        return ks, vs
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, loss_weights=None):
+        """Gradients of sum_i w_i * loss_i (w_i = 1: main.py:646) into self.grad; needs forward(..., save=True)."""
+        S = self._saved
+        if S is None or "dlogits" not in S:
+            raise RuntimeError("backward() needs a preceding forward(idx, targets, save=True)")
+        d, ops, G = self.d, self.ops, self.G
+        M, C, H, hs, L = d.M, d.n_embd, d.n_head, d.hs, d.n_layer
+        h2p = d.h2p
+        B, T = S["B"], S["T"]
+        BT = B * T
+        bf, f32 = self.act_dtype, torch.float32
+        cs_ws = self.buf("cs_ws", (max(ops.colsum_workspace(BT, 4 * C, M), ops.colsum_workspace(BT, max(d.vocab_sizes), 1),
+                                       ops.colsum_workspace(BT, 3 * H * h2p, M)),), f32)
+        ln_ws = self.buf("ln_ws", (ops.layernorm_bwd_workspace(M, BT, C),), f32)
+        dx = self.buf("dx", (M, BT, C), f32)
+        dxb = self.buf("dxb", (M, BT, C), bf)
+        # ---- output heads
+        dhf = self.buf("dhf", (M, BT, C), bf)
+        for i, V in enumerate(d.vocab_sizes):
+            V2 = V // 2
+            dl = S["dlogits"][i]
+            w = 1.0 if loss_weights is None else float(loss_weights[i])
+            ops.colsum(dl.unsqueeze(0), G[f"hd_b2_{i}"].unsqueeze(0), cs_ws)
+            if w != 1.0:
+                G[f"hd_b2_{i}"].mul_(w)
+            if V2 == 0:
+                dhf[i].zero_()
+                continue
+            hd = S["hd"][i]
+            ops.gemm(dl, hd, a_major=1, b_major=1, out_f32=G[f"hd_w2_{i}"], alpha=w)
+            dhd = self.buf(f"dhd{i}", (BT, r8(V2)), bf)[:, :V2]
+            ops.gemm(dl, self.W(f"hd_w2_{i}"), b_major=1, aux=hd, aux_mode=AUX_TANH_BWD, out_bf16=dhd, alpha=w)
+            ops.gemm(dhd, S["hf"][i], a_major=1, b_major=1, out_f32=G[f"hd_w1_{i}"])
+            ops.colsum(dhd.unsqueeze(0), G[f"hd_b1_{i}"].unsqueeze(0), cs_ws)
+            ops.gemm(dhd, self.W(f"hd_w1_{i}"), b_major=1, out_bf16=dhf[i])
+        ops.layernorm_bwd(dhf, S["x_final"], self.P["lnf_w"], S["stf"][0], S["stf"][1], None, dx, dxb, G["lnf_w"],
+                          G["lnf_b"], ln_ws)
+        # ---- layers, last to first
+        for l in reversed(range(L)):
+            Sl = S["layers"][l]
+            if d.Xc:
+                self._cross_backward(l, Sl, dx, dxb, B, T, cs_ws, ln_ws)
+            # feed-forward
+            ops.gemm(dxb, Sl["ffh"], a_major=1, b_major=1, out_f32=G["ff_w2"][l])
+            ops.colsum(dxb, G["ff_b2"][l], cs_ws)
+            dffh = self.buf("dffh", (M, BT, 4 * C), bf)
+            ops.gemm(dxb, self.W("ff_w2")[l], b_major=1, aux=Sl["ffh"], aux_mode=AUX_RELU_BWD, out_bf16=dffh)
+            ops.gemm(dffh, Sl["h2"], a_major=1, b_major=1, out_f32=G["ff_w1"][l])
+            ops.colsum(dffh, G["ff_b1"][l], cs_ws)
+            dh = self.buf("dh", (M, BT, C), bf)
+            ops.gemm(dffh, self.W("ff_w1")[l], b_major=1, out_bf16=dh)
+            ops.layernorm_bwd(dh, Sl["x1"], self.P["ln2_w"][l], Sl["st2"][0], Sl["st2"][1], dx, dx, dxb, G["ln2_w"][l],
+                              G["ln2_b"][l], ln_ws)
+            # self-attention projection MLP
+            ops.gemm(dxb, Sl["p1"], a_major=1, b_major=1, out_f32=G["sa_pw2"][l])
+            ops.colsum(dxb, G["sa_pb2"][l], cs_ws)
+            dp1 = self.buf("dp1", (M, BT, C // 2), bf)
+            ops.gemm(dxb, self.W("sa_pw2")[l], b_major=1, aux=Sl["p1"], aux_mode=AUX_TANH_BWD, out_bf16=dp1)
+            ops.gemm(dp1, Sl["o"], a_major=1, b_major=1, out_f32=G["sa_pw1"][l])
+            ops.colsum(dp1, G["sa_pb1"][l], cs_ws)
+            do = self.buf("do", (M, BT, C), bf)
+            ops.gemm(dp1, self.W("sa_pw1")[l], b_major=1, out_bf16=do)
+            # attention
+            qkv = Sl["qkv"]
+            dqkv = self.buf("dqkv", (M, BT, 3 * C), bf)
+            ops.attention_bwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], Sl["o"], do, Sl["lse"],
+                              dqkv[..., 0:C], [dqkv[..., C:2 * C]], [dqkv[..., 2 * C:3 * C]], B=B, T=T, H=H, hs=hs)
+            # q/k/v MLP stage 2 (block diagonal) and stage 1
+            hidg, dqkvg = self._hid_groups(Sl["hid"], BT), self._qkv_groups(dqkv, BT)
+            ops.gemm(dqkvg, hidg, a_major=1, b_major=1, out_f32=G["sa_w2"][l].reshape(M, 3 * H, hs, d.h2))
+            dhid = self.buf("dhid", (M, BT, 3 * H * h2p), bf)
+            ops.gemm(dqkvg, self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1), b_major=1, aux=hidg, aux_mode=AUX_TANH_BWD,
+                     out_bf16=self._hid_groups(dhid, BT))
+            if h2p == d.h2:
+                ops.gemm(dhid, Sl["h1"], a_major=1, b_major=1, out_f32=G["sa_w1"][l].reshape(M, 3 * H * h2p, C))
+                ops.colsum(dhid, G["sa_b1"][l].reshape(M, 3 * H * h2p), cs_ws)
+            else:
+                gw = self.buf("gw1_pad", (M, 3 * H * h2p, C), f32)
+                gb = self.buf("gb1_pad", (M, 3 * H * h2p), f32)
+                ops.gemm(dhid, Sl["h1"], a_major=1, b_major=1, out_f32=gw)
+                ops.colsum(dhid, gb, cs_ws)
+                ops.unpad(gw.view(M * 3 * H, h2p, C), G["sa_w1"][l].reshape(M * 3 * H, d.h2, C))
+                ops.unpad(gb.view(M * 3 * H, 1, h2p), G["sa_b1"][l].reshape(M * 3 * H, 1, d.h2))
+            ops.gemm(dhid, self.W("sa_w1")[l].reshape(M, 3 * H * h2p, C), b_major=1, out_bf16=dh)
+            ops.layernorm_bwd(dh, Sl["x0"], self.P["ln1_w"][l], Sl["st1"][0], Sl["st1"][1], dx, dx, dxb, G["ln1_w"][l],
+                              G["ln1_b"][l], ln_ws)
+        ops.embed_bwd(S["idx"].view(M, BT), dx, self._voff, max(d.vocab_sizes), G["tok"], G["pos"][:T], B, T)
+        if T < d.block_size:
+            G["pos"][T:].zero_()
+
+    def _cross_backward(self, l, Sl, dx, dxb, B, T, cs_ws, ln_ws):
+        d, ops, G = self.d, self.ops, self.G
+        M, C, H, hs, Xc = d.M, d.n_embd, d.n_head, d.hs, d.Xc
+        BT = B * T
+        bf, f32 = self.act_dtype, torch.float32
+        K = M - 1
+        # projection MLP of every enabled modality (its upstream gradient is the stream gradient of that modality)
+        dpc1 = self.buf("dpc1", (Xc, BT, C // 2), bf)
+        for dv, pos in self._sub(dxb, d.xc):
+            p0, p1 = pos[0], pos[-1] + 1
+            ops.gemm(dv, Sl["pc1"][p0:p1], a_major=1, b_major=1, out_f32=G["ca_pw2"][l][p0:p1])
+            ops.colsum(dv, G["ca_pb2"][l][p0:p1], cs_ws)
+            ops.gemm(dv, self.W("ca_pw2")[l][p0:p1], b_major=1, aux=Sl["pc1"][p0:p1], aux_mode=AUX_TANH_BWD,
+                     out_bf16=dpc1[p0:p1])
+        ops.gemm(dpc1, Sl["oc"], a_major=1, b_major=1, out_f32=G["ca_pw1"][l])
+        ops.colsum(dpc1, G["ca_pb1"][l], cs_ws)
+        doc = self.buf("doc", (Xc, BT, C), bf)
+        ops.gemm(dpc1, self.W("ca_pw1")[l], b_major=1, out_bf16=doc)
+        dqc = self.buf("dqc", (Xc, BT, C), bf)
+        dkvs = [self.buf(f"dkv{j}", Sl["kvs"][j].shape, bf) if Sl["kvs"][j] is not None else None for j in range(M)]
+        for xi, i in enumerate(d.xc):
+            ks, vs = self._kv_views(Sl["kvs"], i)
+            dks, dvs = self._kv_views(dkvs, i)
+            ops.attention_bwd(Sl["qc"][xi:xi + 1], ks, vs, Sl["oc"][xi:xi + 1], doc[xi:xi + 1], Sl["lsec"][xi],
+                              dqc[xi:xi + 1], dks, dvs, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
+                              o_src=Sl["ocs"][xi] if Sl["ocs"] is not None else None)
+        # query projection and its LayerNorm (input: the snapshot x2 of the querying modality)
+        ops.gemm(dqc, Sl["hc"], a_major=1, b_major=1, out_f32=G["ca_wq"][l].reshape(Xc, C, C))
+        dhc = self.buf("dhc", (Xc, BT, C), bf)
+        ops.gemm(dqc, self.W("ca_wq")[l].reshape(Xc, C, C), b_major=1, out_bf16=dhc)
+        for xi, i in enumerate(d.xc):
+            ops.layernorm_bwd(dhc[xi:xi + 1], Sl["x2"][i:i + 1], self.P["lnc_w"][l][xi:xi + 1],
+                              Sl["stc"][0][xi * BT:(xi + 1) * BT], Sl["stc"][1][xi * BT:(xi + 1) * BT], dx[i:i + 1],
+                              dx[i:i + 1], dxb[i:i + 1], G["lnc_w"][l][xi:xi + 1], G["lnc_b"][l][xi:xi + 1], ln_ws)
+        # key/value projections: gradients land on the (un-normalised) stream of every SOURCE modality
+        Wkv, Gkv = self.W("ca_wkv")[l], G["ca_wkv"][l]
+        for j in range(M):
+            nq = len(d.queriers[j])
+            if nq == 0:
+                continue
+            sl = slice(d.qoff[j], d.qoff[j + 1])
+            ops.gemm(dkvs[j], Sl["a_bf"][j], a_major=1, b_major=1, out_f32=Gkv[sl].reshape(nq * 2 * C, C))
+            ops.gemm(dkvs[j], Wkv[sl].reshape(nq * 2 * C, C), b_major=1, residual=dx[j], out_f32=dx[j], out_bf16=dxb[j])
+
+    # ------------------------------------------------------------------------------------------ bookkeeping
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def activation_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
