@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — training throughput of the trade-AId multimodal-transformer hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic input: get_batch (host torch.randint -> index upload ->
+device window gather) -> forward -> backward -> [gradient all-reduce] -> fused AdamW. One JSON line on stdout (rank 0).
+Metric (BASELINE.json): training tokens/s (tokens = modalities x batch x block_size per step, whole job).
+`--impl reference` times the reference's algorithm on the host CPU cores: the oracle port (oracle/restatement.py) —
+the reference is pure Python and /root/reference does not exist on the GPU box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("TRADEAID_BENCH_CONFIG", "c4"))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--rows", type=int, default=0, help="synthetic rows override")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tc_burst=d.get("bf16_tflops", 1590.0),
+                    tc_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ CPU side
+def cpu_oracle_run(cfg, batch, steps, warmup, lr=3e-4):
+    """The reference algorithm on the host cores (oracle port): get_batch + forward + backward + AdamW per step.
+    Returns (tokens_per_s, seconds_per_step, threads)."""
+    from oracle import restatement as R
+    from tradeaid_b200 import synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    T, V = cfg["block_size"], cfg["vocab"]
+    M = len(V)
+    ocfg = R.Cfg(T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"], V, cfg["cross"])
+    sd = R.random_state_dict(ocfg, seed=0)
+    rows = min(cfg["rows"], 200_000)
+    data = syn.make_streams(cfg, "cpu", rows)
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in sd.items()}
+    torch.manual_seed(1)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        ix = R.batch_starting_indices(rows, T, batch, "train", [rows], False)
+        xb, yb = R.gather_batch(data, ix, T)
+        _, _, grads = R.forward_backward(sd, ocfg, xb, yb)
+        R.adamw_step(sd, grads, m, v2, s + 1, lr)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return M * batch * T / sec, sec, torch.get_num_threads()
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch or max(1, min(cfg["batch"], {"c1": 4, "c2": 16, "c3": 2, "c4": 1, "c5": 1}.get(args.config, 1)))
+    tps, sec, threads = cpu_oracle_run(cfg, B, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "training tokens/s", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, B, 1),
+        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                         "sample": f"oracle port (oracle/restatement.py) of model.py fwd+bwd + AdamW + get_batch on CPU, "
+                                   f"full model, batch {B} of {cfg['batch']} per step"},
+        "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, batch, world):
+    return {"workload": f"{args.config}: {cfg['note']}", "modalities": len(cfg["vocab"]), "cross_attention": cfg["cross"],
+            "vocab": cfg["vocab"], "rows": args.rows or cfg["rows"], "n_embd": cfg["n_embd"], "n_head": cfg["n_head"],
+            "n_layer": cfg["n_layer"], "block_size": cfg["block_size"], "batch_per_gpu": batch,
+            "global_batch": batch * world, "parallelism": f"dp{world}", "dropout": 0.0,
+            "l2": "working set per step (activations + weights) exceeds the 126 MB L2 many times over"
+                  if args.config in ("c3", "c4", "c5") else "inputs smaller than L2; a 256 MB buffer is written between steps"}
+
+
+# ------------------------------------------------------------------------------------------------ instrumentation
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class TimedOps:
+    """Proxy of the kernel namespace that brackets every call with CUDA events on the launching stream."""
+
+    def __init__(self, ops):
+        self._ops = ops
+        self.records = []   # (name, start_event, end_event, flops)
+
+    def __getattr__(self, name):
+        fn = getattr(self._ops, name)
+        if not callable(fn) or name.endswith("workspace") or name in ("launch_count", "reset_launch_count", "raw"):
+            return fn
+
+        def wrapped(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flops = 0.0
+            if name == "gemm":
+                A, B = a[0], a[1]
+                am, bm = kw.get("a_major", 0), kw.get("b_major", 0)
+                K = A.shape[-1] if am == 0 else A.shape[-2]
+                Mm = A.shape[-2] if am == 0 else A.shape[-1]
+                N = B.shape[-2] if bm == 0 else B.shape[-1]
+                G = 1
+                for s in A.shape[:-2]:
+                    G *= s
+                flops = 2.0 * Mm * N * K * G
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            self.records.append((name, e0, e1, flops))
+            return out
+
+        return wrapped
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, fl in self.records:
+            a = agg.setdefault(name, [0.0, 0, 0.0])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1
+            a[2] += fl
+        return agg
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def run_ours(args, cfg):
+    import torch.distributed as dist
+    from tradeaid_b200 import lib, synthetic as syn
+    from tradeaid_b200.engine import Engine
+    from tradeaid_b200.feeder import TokenStore, generate_batch_starting_indices
+    from tradeaid_b200.params import Dims
+    from tradeaid_b200.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    pk = peaks()
+    B = args.batch or cfg["batch"]
+    T, V = cfg["block_size"], cfg["vocab"]
+    M = len(V)
+    rows = args.rows or cfg["rows"]
+
+    # ---- model, data, trainer
+    dims = Dims(V, cfg["cross"], T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"])
+    eng = Engine(dims, dev)
+    eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))   # same weights on every rank
+    tr = Trainer(eng, lr=3e-4, process_group=pg, world_size=world)
+    streams = syn.make_streams(cfg, dev, rows)
+    n_train = int(rows * 0.9)
+    store = TokenStore([s[:n_train] for s in streams], dev)
+    del streams
+    torch.manual_seed(1 + rank)     # each rank samples its own batch shard
+    idx = torch.zeros(M, B, T, dtype=torch.int64, device=dev)
+    tgt = torch.zeros_like(idx)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.config in ("c1", "c2") else None
+
+    def feed():
+        ix = generate_batch_starting_indices(n_train, T, B, "train", [n_train], False)
+        store.gather(ix, T, out=(idx, tgt))
+
+    feed()
+    use_graph = not args.no_graph
+    if use_graph:
+        tr.capture(idx, tgt)
+        launches_per_step = tr.launches_per_step + 1      # + the gather kernel
+        step = tr.replay
+    else:
+        lib.reset_launch_count()
+        tr.step(idx, tgt)
+        launches_per_step = lib.launch_count() + 1
+        step = lambda: tr.step(idx, tgt)  # noqa: E731
+
+    def one_step():
+        if flush is not None:
+            flush.zero_()
+        feed()
+        return step()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses = one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    tokens_per_step = M * B * T * world
+    value = tokens_per_step / (ms_per_step * 1e-3)
+    loss_now = float(losses.sum().item())
+
+    # ---- end to end through the public step API with HOST buffers: pinned xb/yb -> H2D, step, losses -> D2H
+    e2e = None
+    if not args.no_e2e:
+        host_store = store.store.cpu()
+        xh = torch.empty(M, B, T, dtype=torch.int64).pin_memory()
+        yh = torch.empty(M, B, T, dtype=torch.int64).pin_memory()
+        lh = torch.empty(M, dtype=torch.float32).pin_memory()
+        ar = torch.arange(T)
+        n_e2e = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            ix = generate_batch_starting_indices(n_train, T, B, "train", [n_train], False)
+            pos = ix[:, None] + ar
+            xh.copy_(host_store[:, pos]); yh.copy_(host_store[:, pos + 1])
+            idx.copy_(xh, non_blocking=True); tgt.copy_(yh, non_blocking=True)
+            ls = step()
+            lh.copy_(ls, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(lh.sum())
+
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": tokens_per_step * n_e2e / dt, "unit": "tokens/s", "h2d_bytes_per_step": 2 * M * B * T * 8,
+               "d2h_bytes_per_step": 4 * M, "steps": n_e2e,
+               "api": "host index draw + host window gather into pinned int64 [M,B,T] x2 -> cudaMemcpyAsync -> "
+                      "Trainer step (fwd+bwd+AdamW) -> per-modality losses copied back and read on the host every step"}
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), from one instrumented eager step
+    timed = TimedOps(lib)
+    eng.ops = tr.ops = timed
+    tr.step(idx, tgt)          # un-timed settle
+    timed.records.clear()
+    tr.step(idx, tgt)
+    agg = timed.summary()
+    eng.ops = tr.ops = lib
+    tot_ms = sum(v[0] for v in agg.values())
+    gm = agg.get("gemm", [0.0, 0, 0.0])
+    gemm_tflops = gm[2] / (gm[0] * 1e-3) / 1e12 if gm[0] > 0 else 0.0
+    breakdown = {k: {"ms": round(v[0], 3), "launches": v[1], "share": round(v[0] / tot_ms, 4)} for k, v in
+                 sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    flops_step = syn.train_flops_per_step(cfg, B)
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05.mma + TMA, all nn.Linear fwd/bwd)",
+                "achieved": gemm_tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
+                "frac": gemm_tflops / pk["tc_sustained"], "traffic": None,
+                "peak_source": f"{pk['source']} (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
+                "launches_per_step": gm[1], "gemm_ms_per_step": round(gm[0], 3), "gemm_share_of_step": round(gm[0] / tot_ms, 4),
+                "algorithmic_flops_per_step_gemm": gm[2],
+                "step_mfu": {"algorithmic_train_tflop_per_step": flops_step / 1e12,
+                             "achieved_tflops_per_gpu": flops_step / (ms_per_step * 1e-3) / 1e12,
+                             "frac_of_measured_sustained": flops_step / (ms_per_step * 1e-3) / 1e12 / pk["tc_sustained"],
+                             "frac_of_nominal_2250": flops_step / (ms_per_step * 1e-3) / 1e12 / 2250.0}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = args.cpu_batch or {"c1": 4, "c2": 16, "c3": 2, "c4": 1, "c5": 1}.get(args.config, 1)
+        tps, sec, threads = cpu_oracle_run(cfg, cb, 2, 1)
+        cpu_baseline = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                        "sample": f"oracle port of the reference step (get_batch + fwd + bwd + AdamW, fp32) on the host CPU, "
+                                  f"full model, batch {cb} of {B}, 2 timed steps ({sec:.2f} s/step)"}
+    if rank == 0:
+        line = {"metric": "training tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, B, world),
+                "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "breakdown_eager_step": breakdown, "cuda_graph": use_graph,
+                "loss_sum_last_step": loss_now, "positions_per_s": value / M,
+                "hbm_bytes_allocated": torch.cuda.max_memory_allocated(dev)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from tradeaid_b200 import synthetic as syn
+    cfg = syn.CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+"""CPU tests of the drop-in surface: state-dict compatibility with the reference, feeder host logic (bit-exact indices
+and windows through the emulated gather), metrics, and that the C-ABI library exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import emu_ops
+from conftest import ROOT, load_golden
+
+
+def _model(name):
+    from tradeaid_b200 import model as tm
+    g = load_golden(f"model_{name}.pt")
+    c = g["cfg"]
+    tm.configure(c["T"], c["C"], c["H"], c["L"])
+    params = [["f", i, None, False, None, None, None, None, c["cross"][i], f"m{i}"] for i in range(c["M"])]
+    return g, tm.MultimodalTransformer(c["M"], c["V"], params)
+
+
+@pytest.mark.parametrize("name", ["demo", "m3", "nocross"])
+def test_state_dict_is_reference_compatible(name):
+    g, m = _model(name)
+    sd = m.state_dict()
+    assert list(sd.keys()) == g["state_dict_keys"]          # same keys, same order, incl. the tril buffers
+    T = g["cfg"]["T"]
+    for k, v in sd.items():
+        if k.endswith(".tril"):
+            assert torch.equal(v, torch.tril(torch.ones(T, T)))
+        else:
+            assert v.shape == g["state_dict"][k].shape
+    # load a reference checkpoint (with tril buffers), strict
+    ref_sd = dict(g["state_dict"])
+    for k in g["state_dict_keys"]:
+        if k.endswith(".tril"):
+            ref_sd[k] = torch.tril(torch.ones(T, T))
+    m.load_state_dict(ref_sd, strict=True)
+    for k, v in g["state_dict"].items():
+        assert torch.equal(m.state_dict()[k], v)
+    # parameters are views into ONE flat buffer
+    flat = m._flat
+    for _, p in m.named_parameters():
+        assert p.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+    assert [n for n, _ in m.named_parameters()] == [k for k in g["state_dict_keys"] if not k.endswith(".tril")]
+
+
+def test_init_statistics():
+    _, m = _model("m3")
+    sd = m.state_dict()
+    w = sd["blocks.0.ffwd_layers.0.net.0.weight"]
+    assert abs(float(w.std()) - 0.02) < 2e-3 and abs(float(w.mean())) < 2e-3
+    assert float(sd["blocks.0.ffwd_layers.0.net.0.bias"].abs().max()) == 0.0
+    assert torch.equal(sd["blocks.0.ln1_layers.0.weight"], torch.ones(32))
+    assert float(sd["blocks.0.ln1_layers.0.bias"].abs().max()) == 0.0
+
+
+def test_cpu_forward_fails_loudly():
+    _, m = _model("demo")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m([torch.zeros(2, 4, dtype=torch.long)] * 2)
+
+
+def test_indices_bit_exact_product_side():
+    from tradeaid_b200.feeder import generate_batch_starting_indices
+    for c in load_golden("indices.pt"):
+        torch.manual_seed(c["seed"])
+        assert torch.equal(generate_batch_starting_indices(*c["args"]), c["ix"])
+        assert torch.equal(generate_batch_starting_indices(*c["args"]), c["ix2"])
+    with pytest.raises(ValueError, match="cannot be equal to or greater"):
+        generate_batch_starting_indices(8, 8, 4, "train", [8], False)
+    with pytest.raises(TypeError, match="'batch_size' must be a positive integer"):
+        generate_batch_starting_indices(80, 8, 0, "train", [80], False)
+    with pytest.raises(ValueError, match="No valid starting positions"):
+        generate_batch_starting_indices(20, 8, 4, "train", [5, 5, 5, 5], False)
+
+
+def test_get_batch_bit_exact_through_module_globals():
+    from tradeaid_b200 import training_utils as tu
+    g = load_golden("get_batch.pt")
+    full, n_val = g["full"], g["n_val"]
+    tu.configure(device="cpu", batch_size=g["batch_size"], block_size=g["block_size"], eval_iters=2)
+    tu._ops_override = emu_ops
+    tu._stores.clear()
+    tu.all_train_sets = [d[:-n_val].tolist() for d in full]     # python lists, as main.py provides them
+    tu.all_val_sets = [d[-n_val:].clone() for d in full]
+    tu.all_vocabularies = [[float(k) for k in range(50)]] * 3
+    tu.all_modality_params = [["s", i, None, False, None, None, None, None, False, f"m{i}"] for i in range(3)]
+    tu.file_lengths = g["file_lengths"]
+    tu.num_modalities = 3
+    tu.is_percents = False
+    torch.manual_seed(g["seed"])
+    try:
+        for call in g["calls"]:
+            xb, yb = tu.get_batch(call["split"], 1)
+            for a, b in zip(xb, call["xb"]):
+                assert a.dtype == torch.int64 and torch.equal(a, b)
+            for a, b in zip(yb, call["yb"]):
+                assert torch.equal(a, b)
+    finally:
+        tu._ops_override = None
+        tu._stores.clear()
+
+
+def test_directional_metrics_match_reference():
+    from tradeaid_b200 import training_utils as tu
+    g = load_golden("metrics.pt")
+    w, l, c, p = tu.calculate_evaluation_metrics(g["logits"], g["xb"], g["yb"], 3, g["vocabs"], g["params"], None)
+    rw, rl, rc, rp = g["result"]
+    assert w == rw and l == rl and p == rp
+    for a, b in zip(c, rc):
+        assert abs(a - b) <= 1e-5
+
+
+def test_library_exports_every_declared_symbol():
+    """The C ABI: libtradeaid_b200.so must load and export every function include/tradeaid_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "tradeaid_b200.h")).read()
+    names = set(re.findall(r"\b(ta_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    path = os.path.join(ROOT, "trade-aid-multimodal-transformer_b200", "libtradeaid_b200.so")
+    assert os.path.exists(path), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(path)
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    lib.ta_abi_version.restype = ctypes.c_int32
+    assert lib.ta_abi_version() == 1

@@ -545,7 +545,11 @@ int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, cons
   const size_t shm = (size_t)2 * 8 * C * sizeof(float);
 #define TA_LN_BWD(NV)                                                                                                  \
   do {                                                                                                                 \
-    if (shm > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 128 * NV * 4);     \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
     ln_bwd_kernel<NV><<<grid, 256, shm, st>>>((const __nv_bfloat16*)dy_bf16, lddy, x, gamma, mean, rstd, dstream_in,   \
                                               dstream_out, (__nv_bfloat16*)dstream_bf16, ld_dbf, pg, pb, rows_total,   \
                                               rows_per_group, rpb, C);                                                 \

@@ -1,0 +1,225 @@
+"""Drop-in replacement for /root/reference/model.py's public surface:
+
+    MultimodalTransformer(num_modalities, vocab_sizes, all_modality_params)      (model.py:358)
+        .forward(idx_list, targets_list=None) -> (logits_list, losses_list | None) (model.py:380-402)
+        .generate(idx_list, max_new_tokens=1, modality_to_generate=0)             (model.py:404-446)
+    an nn.Module whose parameters()/state_dict()/load_state_dict() carry the reference's names and shapes, including
+    the persistent per-head `tril` buffers, so main.py (main.py:463-483, 635, 646-650) runs unchanged.
+
+Hyper-parameters are ambient, as in the reference: read from the reference's `config_utils` getters at construction
+(model.py:25-27) — or from `configure(...)` when used standalone.
+
+Every parameter is a VIEW into the engine's flat fp32 master buffer; forward/backward are sequences of sm_100a kernel
+launches (tradeaid_b200.engine). `sum(losses).backward()` works through a torch.autograd.Function whose backward runs the
+engine's backward program and deposits `.grad` views on the parameters, so a stock torch.optim.AdamW can step them.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .params import Dims, Layout
+
+_explicit_cfg = None
+
+
+def configure(block_size, n_embd, n_head, n_layer, dropout=0.0):
+    """Standalone alternative to the reference's config_utils cache."""
+    global _explicit_cfg
+    _explicit_cfg = dict(block_size=int(block_size), n_embd=int(n_embd), n_head=int(n_head), n_layer=int(n_layer),
+                         dropout=float(dropout))
+
+
+def _hyper():
+    if _explicit_cfg is not None:
+        return dict(_explicit_cfg)
+    try:
+        from config_utils import _get_block_size, _get_dropout, _get_n_embd, _get_n_head, _get_n_layer
+    except ImportError as e:
+        raise RuntimeError("no configuration: call tradeaid_b200.model.configure(...) or put the reference's "
+                           "config_utils on sys.path") from e
+    return dict(block_size=_get_block_size(), n_embd=_get_n_embd(), n_head=_get_n_head(), n_layer=_get_n_layer(),
+                dropout=_get_dropout())
+
+
+class _Node(nn.Module):
+    """Empty container used to reproduce the reference's dotted parameter names."""
+
+
+class _Bridge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, model, idx, tgt):
+        logits, losses = model._engine.forward(idx, tgt, save=True)
+        ctx.model = model
+        return losses.clone()
+
+    @staticmethod
+    def backward(ctx, dlosses):
+        model = ctx.model
+        w = dlosses.tolist()
+        model._engine.backward(None if all(x == 1.0 for x in w) else w)
+        model._deposit_grads()
+        return None, None, None, None
+
+
+class MultimodalTransformer(nn.Module):
+    def __init__(self, num_modalities, vocab_sizes, all_modality_params):
+        super().__init__()
+        self.num_modalities = num_modalities
+        self.vocab_sizes = vocab_sizes
+        self.all_modality_params = all_modality_params
+        hp = _hyper()
+        cross = [bool(all_modality_params[i][8]) for i in range(num_modalities)]
+        self._dims = Dims(list(vocab_sizes)[:num_modalities], cross, hp["block_size"], hp["n_embd"], hp["n_head"],
+                          hp["n_layer"], hp["dropout"])
+        self._layout = Layout(self._dims)
+        flat = torch.zeros(self._layout.total, dtype=torch.float32)
+        self._layout.init_(flat)
+        self._flat = flat
+        self._engine = None
+        self._anchor = None
+        self._param_list = []
+        for name, view in self._layout.named_views(flat).items():
+            node = self
+            parts = name.split(".")
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Node())
+                node = node._modules[p]
+            par = nn.Parameter(view)
+            node.register_parameter(parts[-1], par)
+            self._param_list.append((name, par))
+        self._tril_names = self._layout.tril_names()
+        self._register_state_dict_hook(self._add_tril)
+        self._register_load_state_dict_pre_hook(self._drop_tril)
+
+    # ------------------------------------------------------------------------------------------ state dict
+    def _add_tril(self, module, state_dict, prefix, local_metadata):
+        """The reference keeps a persistent [T, T] lower-triangular buffer per head (model.py:55, 133). The engine never
+        needs one; they are synthesised here, at the reference's positions, for checkpoint compatibility."""
+        T = self._dims.block_size
+        dev = next(iter(state_dict.values())).device if state_dict else "cpu"
+        tril = torch.tril(torch.ones(T, T, device=dev))
+        out = OrderedDict()
+        done = set()
+        for k, v in state_dict.items():
+            # `tril` is registered before the head's sub-modules: emit it when the first key of a head shows up
+            if ".heads." in k:
+                head = k[len(prefix):].split(".heads.")[0] + ".heads." + k[len(prefix):].split(".heads.")[1].split(".")[0]
+                if head not in done:
+                    done.add(head)
+                    out[prefix + head + ".tril"] = tril
+            out[k] = v
+        state_dict.clear()
+        state_dict.update(out)
+        return state_dict
+
+    def _drop_tril(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for k in [k for k in state_dict if k.startswith(prefix) and k.endswith(".tril")]:
+            del state_dict[k]
+        self._dirty = True
+
+    # ------------------------------------------------------------------------------------------ device placement
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        self._reflatten()
+        return self
+
+    def _reflatten(self):
+        """nn.Module.to()/cuda() moves every parameter separately (main.py:463); gather them back into one flat
+        buffer on the new device and re-point each parameter at its view."""
+        dev = self._param_list[0][1].device
+        dtype = self._param_list[0][1].dtype
+        if dtype != torch.float32:
+            raise TypeError("tradeaid_b200 keeps fp32 master parameters (bf16 operand copies are internal)")
+        if dev.type == "cuda":
+            from .engine import Engine
+            eng = Engine(self._dims, dev)
+            flat = eng.master
+        else:
+            eng, flat = None, torch.zeros(self._layout.total, dtype=torch.float32, device=dev)
+        views = self._layout.named_views(flat)
+        with torch.no_grad():
+            for name, par in self._param_list:
+                views[name].copy_(par.data)
+                par.data = views[name]
+                par.grad = None
+        self._flat, self._engine = flat, eng
+        self._anchor = torch.zeros(1, device=dev, requires_grad=True) if eng is not None else None
+        self._dirty = True
+
+    def _deposit_grads(self):
+        gviews = self._grad_views
+        for name, par in self._param_list:
+            if not self._layout.is_active(name):
+                continue  # never used by forward: the reference leaves .grad = None and AdamW skips it
+            g = gviews[name]
+            if par.grad is None:
+                par.grad = g
+            elif par.grad.data_ptr() != g.data_ptr():
+                par.grad.add_(g)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _require_engine(self):
+        if self._engine is None:
+            raise RuntimeError("tradeaid_b200.MultimodalTransformer runs on a CUDA device only (sm_100a kernels, no CPU "
+                               "fallback): move the model with .to('cuda') first")
+        eng = self._engine
+        if self._param_list[0][1].data_ptr() != eng.master.data_ptr():
+            self._reflatten()
+            eng = self._engine
+        if not hasattr(self, "_grad_views") or self._grad_views_of is not eng:
+            self._grad_views = eng.layout.named_views(eng.grad)
+            self._grad_views_of = eng
+        return eng
+
+    def forward(self, idx_list, targets_list=None):
+        eng = self._require_engine()
+        if self.training and self._dims.dropout > 0.0 and os.environ.get("TRADEAID_B200_IGNORE_DROPOUT") != "1":
+            raise NotImplementedError(
+                f"dropout={self._dims.dropout} in training mode is not implemented by the sm_100a kernels of this build; "
+                "set dropout: 0.0 (or TRADEAID_B200_IGNORE_DROPOUT=1 to train without dropout)")
+        M = self.num_modalities
+        idx = torch.stack([t.to(eng.device, torch.int64) for t in idx_list[:M]]).contiguous()
+        if self.training or getattr(self, "_dirty", True):
+            eng.shadows_stale = True     # a stock optimizer updates the fp32 views in place between forwards
+            self._dirty = False
+        B, T = idx.shape[1], idx.shape[2]
+        if targets_list is None:
+            logits, _ = eng.forward(idx, None, save=False)
+            return [l.clone() for l in logits], None
+        tgt = torch.stack([t.to(eng.device, torch.int64) for t in targets_list[:M]]).contiguous()
+        if torch.is_grad_enabled():
+            par_grads = [p.grad for _, p in self._param_list[:1]]  # noqa: F841 (keeps alias semantics explicit)
+            losses = _Bridge.apply(self._anchor, self, idx, tgt)
+            logits = [l.view(B, T, -1).clone() for l in eng._saved["logits"]]
+        else:
+            logits, losses = eng.forward(idx, tgt, save=False)
+            logits, losses = [l.clone() for l in logits], losses.clone()
+        return logits, [losses[i] for i in range(M)]
+
+    @torch.no_grad()
+    def generate(self, idx_list, max_new_tokens=1, modality_to_generate=0):
+        """Same sequence bookkeeping as the reference (model.py:404-446): crop to block_size, full forward, sample the
+        last position of the target modality, append; other modalities are padded with their last token or cropped."""
+        T = self._dims.block_size
+        seqs = [idx.clone() for idx in idx_list]
+        for _ in range(max_new_tokens):
+            cond = [s[:, -T:] for s in seqs]
+            logits_list, _ = self(cond)
+            probs = F.softmax(logits_list[modality_to_generate][:, -1, :], dim=-1)
+            nxt = torch.multinomial(probs, num_samples=1)
+            seqs[modality_to_generate] = torch.cat((seqs[modality_to_generate], nxt.to(seqs[modality_to_generate].device)), dim=1)
+            tl = seqs[modality_to_generate].shape[1]
+            for i in range(self.num_modalities):
+                if i == modality_to_generate:
+                    continue
+                if seqs[i].shape[1] < tl:
+                    seqs[i] = torch.cat((seqs[i], seqs[i][:, -1:]), dim=1)
+                elif seqs[i].shape[1] > tl:
+                    seqs[i] = seqs[i][:, :tl]
+        return seqs

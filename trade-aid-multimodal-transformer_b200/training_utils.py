@@ -1,0 +1,201 @@
+"""Drop-in replacement for the public surface of /root/reference/training_utils.py:
+
+    generate_batch_starting_indices(...)   (:33)    same validation, messages and RNG consumption
+    get_batch(split, is_training)          (:333)   token store resident in HBM, one gather kernel (K7)
+    calculate_evaluation_metrics(...)      (:215)   same counts, computed from the last-position logits in one pass
+    estimate_loss(current_step, max_steps) (:387)   same prints and log lines
+
+and the module globals main.py injects (main.py:387-396, 485): all_train_sets, all_val_sets, all_vocabularies,
+all_modality_params, all_file_info, file_lengths, num_modalities, is_percents, m.
+"""
+from __future__ import annotations
+
+import numbers
+import os
+from datetime import datetime
+
+import torch
+import torch.nn.functional as F
+
+from .feeder import TokenStore, generate_batch_starting_indices  # noqa: F401  (re-exported)
+
+__all__ = ['generate_batch_starting_indices', 'get_batch', 'estimate_loss', 'calculate_evaluation_metrics']
+
+_explicit_cfg = None
+
+
+def configure(**kw):
+    """Standalone alternative to the reference's config_utils cache: device, batch_size, block_size, eval_iters,
+    output_file_name, project_file_path."""
+    global _explicit_cfg
+    _explicit_cfg = dict(output_file_name='', project_file_path='')
+    _explicit_cfg.update(kw)
+
+
+def _cfg():
+    if _explicit_cfg is not None:
+        return _explicit_cfg
+    from config_utils import _get_config
+    return _get_config()
+
+
+def _get(key):
+    return _cfg()[key]
+
+
+# ------------------------------------------------------------------------------------------------ feeder
+_stores = {}
+_ops_override = None   # tests inject a CPU emulation of the kernel namespace; the product leaves this None
+
+
+def _store(split):
+    """Device-resident token store of a split, rebuilt when main.py (re)assigns the global lists."""
+    src = all_train_sets if split == 'train' else all_val_sets
+    key = (split, id(src), tuple(id(s) for s in src), str(_get('device')))
+    ent = _stores.get(split)
+    if ent is None or ent[0] != key:
+        dev = _get('device')
+        ent = (key, TokenStore(src, dev, ops=_ops_override))
+        _stores[split] = ent
+    return ent[1]
+
+
+def get_batch(split, is_training):
+    """training_utils.py:333-384. Returns (xb_list, yb_list): per modality int64 [batch_size, block_size] on `device`."""
+    train_store = _store('train')
+    for r in range(num_modalities):
+        this_rand_size = all_modality_params[r][2]
+        if this_rand_size is not None and is_training == 1:
+            # The reference reads the augmentation size from index 2 of the legacy list, which holds `has_header`
+            # (training_utils.py:353; schema.py:213-248): with a truthy value it applies a +-1 random walk to the whole
+            # training list in place, on the host, every call. Kept verbatim by delegating to the reference's own
+            # function; the mutated modality is re-uploaded. O(N) per step by construction — see INTEGRATION.md.
+            from data_utils import add_rand_to_data_points
+            all_train_sets[r] = add_rand_to_data_points(all_train_sets[r], this_rand_size, len(all_vocabularies[r]))
+            train_store.update_modality(r, all_train_sets[r])
+            _stores['train'] = ((('train', id(all_train_sets), tuple(id(s) for s in all_train_sets), str(_get('device')))),
+                                train_store)
+    store = train_store if split == 'train' else _store('val')
+    T, B = _get('block_size'), _get('batch_size')
+    ix = generate_batch_starting_indices(store.N, T, B, split, file_lengths, is_percents)
+    xb, yb = store.gather(ix, T)
+    return [xb[r] for r in range(num_modalities)], [yb[r] for r in range(num_modalities)]
+
+
+# ------------------------------------------------------------------------------------------------ metrics
+def _direction_table(vocab, is_percentage_data, device):
+    """values of a numeric vocabulary as a device tensor (float64 keeps python-float comparisons exact)."""
+    return torch.tensor([float(v) for v in vocab], dtype=torch.float64, device=device)
+
+
+def calculate_evaluation_metrics(logits_list, xb_list, yb_list, num_modalities, all_vocabularies, all_modality_params,
+                                 all_file_info):
+    """training_utils.py:215-330, vectorised over the batch: directional wins / losses of the arg-max prediction at the
+    last position against the actual next value, and the probability mass on the predicted direction."""
+    wins = [0] * num_modalities
+    losses = [0] * num_modalities
+    cert = [0.0] * num_modalities
+    processed = [0] * num_modalities
+    for i in range(num_modalities):
+        if not (len(logits_list) > i and len(yb_list) > i):
+            continue
+        vocab = all_vocabularies[i]
+        is_pct = all_modality_params[i][3]
+        numeric = all(isinstance(v, numbers.Number) for v in vocab)
+        y = yb_list[i]
+        if not (numeric and y.ndim >= 2 and y.shape[1] >= (1 if is_pct else 2) and y.shape[0] > 0):
+            continue
+        processed[i] = 1
+        last = logits_list[i][:, -1, :].float()
+        dev = last.device
+        vals = _direction_table(vocab, is_pct, dev)
+        pred_v = vals[last.argmax(-1)]
+        act_v = vals[y[:, -1].to(dev)]
+        if is_pct:
+            ref = torch.zeros_like(pred_v)
+            tok_sign = torch.sign(vals)[None, :].expand(last.shape[0], -1)
+        else:
+            if xb_list[i].shape[1] < 1:
+                continue  # no previous value: direction undefined for every sample (training_utils.py:278-287)
+            ref = vals[xb_list[i][:, -1].to(dev)]
+            tok_sign = torch.sign(vals[None, :] - ref[:, None])
+        ps, as_ = torch.sign(pred_v - ref), torch.sign(act_v - ref)
+        wins[i] = int((ps == as_).sum())
+        losses[i] = int((ps != as_).sum())
+        probs = F.softmax(last, dim=-1).double()
+        cert[i] = float((probs * (tok_sign == ps[:, None])).sum())
+    return wins, losses, cert, processed
+
+
+def estimate_loss(current_step=None, max_steps=None):
+    """training_utils.py:387-520: eval_iters batches of each split through the model in eval mode; mean summed loss,
+    directional metrics, same console and log-file lines."""
+    out = {}
+    m.eval()
+    eval_iters, batch_size = _get('eval_iters'), _get('batch_size')
+    for state in ['train', 'val']:
+        current_time = datetime.now().strftime("%H:%M:%S")
+        step_info = f'Step {current_step}/{max_steps} | ' if current_step is not None else ''
+        batch_calc = f' * {batch_size} batches = {eval_iters * batch_size} samples'
+        print(f'Evaluation: {step_info}{state.title()} set ({eval_iters} iterations{batch_calc}) | {current_time}')
+        tot_proc = [0] * num_modalities
+        tot_ok = [0] * num_modalities
+        tot_bad = [0] * num_modalities
+        tot_cert = [0.0] * num_modalities
+        total_losses = []
+        for k in range(eval_iters):
+            xb_list, yb_list = get_batch(state, 0)
+            with torch.no_grad():
+                logits_list, losses_list = m(xb_list, yb_list)
+            if losses_list and all(l is not None for l in losses_list):
+                total_losses.append(sum(losses_list).item())
+            else:
+                print(f"Warning: Iteration {k} losses not calculated, skipping")
+            ok, bad, cert, proc = calculate_evaluation_metrics(logits_list, xb_list, yb_list, num_modalities,
+                                                               all_vocabularies, all_modality_params, all_file_info)
+            for i in range(num_modalities):
+                tot_ok[i] += ok[i]; tot_bad[i] += bad[i]; tot_cert[i] += cert[i]; tot_proc[i] += proc[i]
+        out[state] = sum(total_losses) / len(total_losses) if total_losses else float('nan')
+        disp = 'Train Set' if state == 'train' else 'Val Set'
+        print(f"\nDIRECTIONAL METRICS - {disp} (Correct/Total)")
+        for i in range(num_modalities):
+            name = all_modality_params[i][9] if all_modality_params[i][9] else f"Modality {i+1}"
+            if tot_proc[i] > 0:
+                total = tot_ok[i] + tot_bad[i]
+                if total > 0:
+                    print(f"  - {name:<30}{tot_ok[i]}/{total} ({round((tot_ok[i] / total) * 100, 1)}%)")
+                else:
+                    print(f"  - {name}: No directional predictions")
+            else:
+                print(f"  - {name}: No data processed (non-numeric)")
+        cfg = _cfg()
+        if cfg['output_file_name'] != '':
+            path = cfg['project_file_path'] + 'output/' + cfg['output_file_name']
+            with open(path, 'a', encoding='utf-8') as f:
+                for i in range(num_modalities):
+                    name = all_modality_params[i][9] if all_modality_params[i][9] else f"Modality {i+1}"
+                    if tot_proc[i] > 0:
+                        total = tot_ok[i] + tot_bad[i]
+                        acc = f"{round((tot_ok[i] / total) * 100, 1)}%" if total > 0 else "N/A"
+                        f.write(f"   DIRECTIONAL PREDICTION {disp} - {name}: Correct={tot_ok[i]:,} | Incorrect={tot_bad[i]:,} | Accuracy={acc}\n")
+                    else:
+                        f.write(f"   DIRECTIONAL PREDICTION {disp} - {name}: Correct=0 | Incorrect=0 | Accuracy=N/A\n")
+                if state == 'train':
+                    f.write("\n")
+        if state == 'train':
+            print()
+    m.train()
+    return out
+
+
+# Globals set by main.py after data loading (training_utils.py:523-534)
+all_full_datasets = None
+all_train_sets = None
+all_val_sets = None
+all_vocabularies = None
+all_modality_params = None
+all_file_info = None
+file_lengths = None
+num_modalities = None
+is_percents = False
+m = None
