@@ -22,7 +22,7 @@ constexpr int ATTB_MAX_SRC = 8;
 int make_head_map(CUtensorMap* out, const ta_attn_tensor* t, int hs, int H, int T, int B, int G, int box_rows);
 
 struct AttnBwdMaps {
-  CUtensorMap q, d_o;
+  CUtensorMap q, d_o, o;
   CUtensorMap k[ATTB_MAX_SRC];
   CUtensorMap v[ATTB_MAX_SRC];
 };
@@ -58,19 +58,29 @@ __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (
   }
 }
 
+constexpr int ATTB_THREADS = 288;   // warps 0-7: softmax/gradient math (two column halves), warp 8: TMA + UMMA issuer
+
 template <int DP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ATTB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant__ AttnBwdParams p) {
   constexpr int TILE = 16384;  // 128 rows x 128 B
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_kv[2], bar_sp, bar_g;
-  __shared__ uint32_t tmem_base_smem;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                // 2 tiles
   uint8_t* sdO = smem + 2 * TILE;    // 2 tiles
   uint8_t* sKV = smem + 4 * TILE;    // 2 stages x (K, V)
-  uint8_t* sP = smem + 8 * TILE;     // 2 halves (kv 0-63, 64-127)
+  uint8_t* sP = smem + 8 * TILE;     // 2 halves (kv 0-63, 64-127); also the landing zone of the O tiles for D
   uint8_t* sdS = smem + 10 * TILE;   // 2 halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * TILE);
+  uint64_t& bar_q = bars[0];         // Q and dO tiles landed
+  uint64_t* bar_kv = bars + 1;       // [2] K/V stage landed
+  uint64_t& bar_sp = bars[3];        // S and dP of a pair are in TMEM
+  uint64_t& bar_g = bars[4];         // gradient UMMAs of a pair are complete (P/dS smem and dV/dK/dQ TMEM readable)
+  uint64_t& bar_pr = bars[5];        // 256 arrivals: P/dS of a pair written to smem, S/dP TMEM consumed
+  uint64_t& bar_o = bars[6];         // O tiles of a source landed (for D)
+  uint64_t& bar_od = bars[7];        // 256 arrivals: D computed, O tiles consumed
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 8);
+  float* sD = reinterpret_cast<float*>(bars + 10);   // [2][128] rowsum(dO * O_src) per query tile
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   const int tid = threadIdx.x, warp = tid >> 5;
   int bid = blockIdx.x;
@@ -79,6 +89,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   const int g = bid / p.B;
   const int n_qt = p.n_qt;  // == number of kv tiles
   const int total_ks = p.n_src * n_qt;
+  const int pairs_per_src = n_qt * (n_qt + 1) / 2;
+  const int total_pairs = p.n_src * pairs_per_src;
 
   if (tid == 0) {
     mbar_init(&bar_q, 1);
@@ -86,6 +98,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
     mbar_init(&bar_kv[1], 1);
     mbar_init(&bar_sp, 1);
     mbar_init(&bar_g, 1);
+    mbar_init(&bar_pr, 256);
+    mbar_init(&bar_o, 1);
+    mbar_init(&bar_od, 256);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -98,182 +113,199 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
   const uint32_t tm_dQ = tmem_base + 384;  // + 64 * i
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-
-  auto issue_kv = [&](int ks) {
-    const int s = ks / n_qt, j = ks - s * n_qt, st = ks & 1;
-    uint8_t* dK = sKV + st * 2 * TILE;
-    mbar_expect_tx(&bar_kv[st], 2 * TILE);
-    tma_load_5d(dK, &maps.k[s], &bar_kv[st], 0, h, j * 128, b, g);
-    tma_load_5d(dK + TILE, &maps.v[s], &bar_kv[st], 0, h, j * 128, b, g);
-  };
-  if (tid == 0) {
-    mbar_expect_tx(&bar_q, n_qt * 2 * TILE);
-    for (int i = 0; i < n_qt; ++i) {
-      tma_load_5d(sQ + i * TILE, &maps.q, &bar_q, 0, h, i * 128, b, g);
-      tma_load_5d(sdO + i * TILE, &maps.d_o, &bar_q, 0, h, i * 128, b, g);
-    }
-    issue_kv(0);
-  }
-  mbar_wait(&bar_q, 0);
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
-  constexpr uint32_t idesc_kv = umma_idesc_bf16(128, DP, 1, 1);   // dV, dK : A = P/dS seen MN-major, B = dO/Q MN-major
-  constexpr uint32_t idesc_q = umma_idesc_bf16(128, DP, 0, 1);    // dQ     : A = dS K-major, B = K MN-major
   const int nk_qk = (p.hs + 15) / 16;
-  uint32_t pc = 0;
 
-  for (int s = 0; s < p.n_src; ++s) {
-    // per-row softmax statistics of this source for the (up to two) query tiles this thread serves
-    float Dv[2] = {0.f, 0.f}, L2[2] = {0.f, 0.f};
-    const __nv_bfloat16* osrc = (p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o) + (long long)g * p.o_gs;
-    for (int i = 0; i < n_qt; ++i) {
-      const int row = i * 128 + tid;
-      if (row < p.T) {
-        const __nv_bfloat16* orow = osrc + ((long long)b * p.T + row) * p.ldo + h * p.hs;
-        const uint8_t* drow = sdO + i * TILE + tid * 128;
-        float acc = 0.f;
-        for (int c = 0; c < p.hs / 8; ++c) {
-          const uint4 a = *reinterpret_cast<const uint4*>(drow + ((c ^ (tid & 7)) << 4));
-          const uint4 o4 = *reinterpret_cast<const uint4*>(orow + c * 8);
-          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-          const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&o4);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            acc += __low2float(ah[e]) * __low2float(oh[e]) + __high2float(ah[e]) * __high2float(oh[e]);
+  if (warp == 8) {
+    // ================================================================== TMA + UMMA issuer (one lane)
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, DP, 1, 1);   // dV, dK: A = P/dS seen MN-major, B = dO/Q MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, DP, 0, 1);    // dQ: A = dS K-major, B = K MN-major
+      auto issue_kv = [&](int ks) {
+        const int s = ks / n_qt, j = ks - s * n_qt, st = ks & 1;
+        uint8_t* dK = sKV + st * 2 * TILE;
+        mbar_expect_tx(&bar_kv[st], 2 * TILE);
+        tma_load_5d(dK, &maps.k[s], &bar_kv[st], 0, h, j * 128, b, g);
+        tma_load_5d(dK + TILE, &maps.v[s], &bar_kv[st], 0, h, j * 128, b, g);
+      };
+      auto issue_o = [&](int s) {   // O_src tiles of source s -> sP region (free: no gradient UMMA in flight)
+        mbar_expect_tx(&bar_o, n_qt * TILE);
+        for (int i = 0; i < n_qt; ++i) tma_load_5d(sP + i * TILE, &maps.o, &bar_o, 0, h, i * 128, b, p.o_src ? s : g);
+      };
+      auto issue_sdp = [&](int j, int i, int st) {
+        const uint32_t aQ = smem_u32(sQ + i * TILE), aO = smem_u32(sdO + i * TILE);
+        const uint32_t aK = smem_u32(sKV + st * 2 * TILE), aV = aK + TILE;
+        for (int kk = 0; kk < nk_qk; ++kk)
+          umma_bf16(tm_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
+        for (int kk = 0; kk < nk_qk; ++kk)
+          umma_bf16(tm_dP, umma_desc_sw128(aO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024), idesc_s, kk != 0);
+        umma_commit(&bar_sp);
+      };
+      mbar_expect_tx(&bar_q, n_qt * 2 * TILE);
+      for (int i = 0; i < n_qt; ++i) {
+        tma_load_5d(sQ + i * TILE, &maps.q, &bar_q, 0, h, i * 128, b, g);
+        tma_load_5d(sdO + i * TILE, &maps.d_o, &bar_q, 0, h, i * 128, b, g);
+      }
+      issue_o(0);
+      issue_kv(0);
+      if (total_ks > 1) issue_kv(1);
+      mbar_wait(&bar_q, 0);
+      int pc = 0;
+      for (int s = 0; s < p.n_src; ++s) {
+        if (s > 0) issue_o(s);   // the last pair of the previous source was waited on (bar_g) below
+        mbar_wait(&bar_od, s & 1);           // every math thread is done with the O tiles: sP may be overwritten
+        for (int j = 0; j < n_qt; ++j) {
+          const int ks = s * n_qt + j, st = ks & 1;
+          mbar_wait(&bar_kv[st], (ks >> 1) & 1);
+          for (int i = j; i < n_qt; ++i, ++pc) {
+            // S/dP TMEM is free: the math threads arrived on bar_pr of the previous pair before we got here
+            tc_fence_after();
+            issue_sdp(j, i, st);
+            mbar_wait(&bar_pr, pc & 1);        // P, dS of this pair are in smem
+            tc_fence_after();
+            const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS), aQ = smem_u32(sQ + i * TILE), aO = smem_u32(sdO + i * TILE);
+            const uint32_t aK = smem_u32(sKV + st * 2 * TILE);
+            for (int kk = 0; kk < 8; ++kk)     // dV_j += P^T dO_i
+              umma_bf16(tm_dV, umma_desc_sw128(aP + kk * 2048, TILE, 1024), umma_desc_sw128(aO + kk * 2048, TILE, 1024),
+                        idesc_kv, (i > j) || kk != 0);
+            for (int kk = 0; kk < 8; ++kk)     // dK_j += dS^T Q_i
+              umma_bf16(tm_dK, umma_desc_sw128(aS + kk * 2048, TILE, 1024), umma_desc_sw128(aQ + kk * 2048, TILE, 1024),
+                        idesc_kv, (i > j) || kk != 0);
+            for (int kk = 0; kk < 8; ++kk)     // dQ_i += dS K_j
+              umma_bf16(tm_dQ + 64 * i, umma_desc_sw128(aS + (kk >> 2) * TILE + (kk & 3) * 32, 16, 1024),
+                        umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, !(s == 0 && j == 0) || kk != 0);
+            umma_commit(&bar_g);
+            // P/dS smem and this pair's K/V must outlive the gradient UMMAs
+            mbar_wait(&bar_g, pc & 1);
+          }
+          if (ks + 2 < total_ks) issue_kv(ks + 2);   // stage st is free: its last reader (dQ += dS K) has completed
         }
-        Dv[i] = acc;
-        L2[i] = p.lse[((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T + row] * 1.4426950408889634f;
       }
     }
-    for (int j = 0; j < n_qt; ++j) {
-      const int ks = s * n_qt + j, st = ks & 1;
-      const int kv0 = j * 128;
-      uint8_t* sK = sKV + st * 2 * TILE;
-      uint8_t* sV = sK + TILE;
-      if (tid == 0) {
-        if (ks + 1 < total_ks) issue_kv(ks + 1);
-        mbar_wait(&bar_kv[st], (ks >> 1) & 1);
-      }
-      for (int i = j; i < n_qt; ++i) {
-        const uint32_t par = pc & 1;
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t aQ = smem_u32(sQ + i * TILE), aO = smem_u32(sdO + i * TILE), aK = smem_u32(sK), aV = smem_u32(sV);
-          for (int kk = 0; kk < nk_qk; ++kk)
-            umma_bf16(tm_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
-          for (int kk = 0; kk < nk_qk; ++kk)
-            umma_bf16(tm_dP, umma_desc_sw128(aO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024), idesc_s, kk != 0);
-          umma_commit(&bar_sp);
-        }
-        mbar_wait(&bar_sp, par);
-        tc_fence_after();
-        const int row = i * 128 + tid;
-        const int warp_last_row = i * 128 + warp * 32 + 31;
-        int n_chunks = (warp_last_row - kv0) / 32 + 1;
-        if (n_chunks > 4) n_chunks = 4;
-        const float Dr = Dv[i], Lr = L2[i];
-        const bool row_ok = row < p.T;
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pp[16], dd[16];
-          if (c < n_chunks) {
-            uint32_t sv[32], dv[32];
-            tmem_ld_32x32(tm_S + lane_off + c * 32, sv);
-            tmem_ld_32x32(tm_dP + lane_off + c * 32, dv);
-            tmem_wait_ld();
+  } else {
+    // ================================================================== math warps
+    const int r = tid & 127;          // row of the 128 x 128 pair tile (query row inside its tile / key row for dK, dV)
+    const int half = tid >> 7;        // column half of the pair tile this thread handles
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    mbar_wait(&bar_q, 0);
+    int pc = 0;
+    for (int s = 0; s < p.n_src; ++s) {
+      // D[row] = rowsum(dO * O_src): half 0 serves query tile 0, half 1 query tile 1, results shared through smem
+      mbar_wait(&bar_o, s & 1);
+      if (half < n_qt) {
+        const int row = half * 128 + r;
+        float acc = 0.f;
+        if (row < p.T) {
+          const uint8_t* orow = sP + half * TILE + r * 128;
+          const uint8_t* drow = sdO + half * TILE + r * 128;
+          for (int c = 0; c < p.hs / 8; ++c) {
+            const uint4 a = *reinterpret_cast<const uint4*>(drow + ((c ^ (r & 7)) << 4));
+            const uint4 o4 = *reinterpret_cast<const uint4*>(orow + ((c ^ (r & 7)) << 4));
+            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&o4);
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-              if (row_ok && kv0 + c * 32 + e <= row) {
-                p0 = exp2f(__uint_as_float(sv[e]) * p.scale_log2 - Lr);
-                d0 = p0 * (__uint_as_float(dv[e]) - Dr) * p.scale;
-              }
-              if (row_ok && kv0 + c * 32 + e + 1 <= row) {
-                p1 = exp2f(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
-                d1 = p1 * (__uint_as_float(dv[e + 1]) - Dr) * p.scale;
-              }
-              __nv_bfloat162 ph = __floats2bfloat162_rn(p0, p1), dh = __floats2bfloat162_rn(d0, d1);
-              pp[e / 2] = *reinterpret_cast<uint32_t*>(&ph);
-              dd[e / 2] = *reinterpret_cast<uint32_t*>(&dh);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) pp[e] = dd[e] = 0u;
+            for (int e = 0; e < 4; ++e)
+              acc += __low2float(ah[e]) * __low2float(oh[e]) + __high2float(ah[e]) * __high2float(oh[e]);
           }
-          const int off = (c >> 1) * TILE + tid * 128;
+        }
+        sD[half * 128 + r] = acc;
+      }
+      // named barrier over the 256 math threads only (the issuer warp never joins)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float D0 = sD[r], D1 = n_qt > 1 ? sD[128 + r] : 0.f;
+      const float* lse_s = p.lse + ((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T;
+      const float L0 = r < p.T ? lse_s[r] * 1.4426950408889634f : 0.f;
+      const float L1 = (n_qt > 1 && 128 + r < p.T) ? lse_s[128 + r] * 1.4426950408889634f : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // sD is rewritten by the next source only after everyone has read it
+      mbar_arrive(&bar_od);
+      for (int j = 0; j < n_qt; ++j) {
+        const int kv0 = j * 128;
+        for (int i = j; i < n_qt; ++i, ++pc) {
+          const int row = i * 128 + r;
+          const bool row_ok = row < p.T;
+          const float Dr = i == 0 ? D0 : D1, Lr = i == 0 ? L0 : L1;
+          mbar_wait(&bar_sp, pc & 1);
+          tc_fence_after();
+          uint32_t pp[32], dd[32];    // this thread's 64 columns of P and dS, packed bf16x2
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int lc = ((c & 1) * 4 + q) ^ (tid & 7);
+          for (int c = 0; c < 2; ++c) {
+            const int col0 = kv0 + half * 64 + c * 32;
+            // warp-uniform skip of chunks that are entirely above the diagonal for this warp's 32 rows
+            if (col0 <= i * 128 + (warp & 3) * 32 + 31) {
+              uint32_t sv[32], dv[32];
+              tmem_ld_32x32(tm_S + lane_off + half * 64 + c * 32, sv);
+              tmem_ld_32x32(tm_dP + lane_off + half * 64 + c * 32, dv);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                if (row_ok && col0 + e <= row) {
+                  p0 = exp2f(__uint_as_float(sv[e]) * p.scale_log2 - Lr);
+                  d0 = p0 * (__uint_as_float(dv[e]) - Dr) * p.scale;
+                }
+                if (row_ok && col0 + e + 1 <= row) {
+                  p1 = exp2f(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
+                  d1 = p1 * (__uint_as_float(dv[e + 1]) - Dr) * p.scale;
+                }
+                __nv_bfloat162 ph = __floats2bfloat162_rn(p0, p1), dh = __floats2bfloat162_rn(d0, d1);
+                pp[c * 16 + e / 2] = *reinterpret_cast<uint32_t*>(&ph);
+                dd[c * 16 + e / 2] = *reinterpret_cast<uint32_t*>(&dh);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pp[c * 16 + e] = dd[c * 16 + e] = 0u;
+            }
+          }
+          // the gradient UMMAs of the previous pair (and, for the first pair of a source, the D pass) are done with sP/sdS:
+          // the issuer waits on bar_g before it issues this pair's S/dP, so bar_sp above already implies it.
+          const int off = half * TILE + r * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int lc = q ^ (r & 7);
             *reinterpret_cast<uint4*>(sP + off + (lc << 4)) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
             *reinterpret_cast<uint4*>(sdS + off + (lc << 4)) = make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]);
           }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&bar_pr);
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS), aQ = smem_u32(sQ + i * TILE), aO = smem_u32(sdO + i * TILE);
-          const uint32_t aK = smem_u32(sK);
-          // dV_j += P^T dO_i ; dK_j += dS^T Q_i   (reduction over the 128 query rows of tile i)
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tm_dV, umma_desc_sw128(aP + kk * 2048, TILE, 1024), umma_desc_sw128(aO + kk * 2048, TILE, 1024),
-                      idesc_kv, (i > j) || kk != 0);
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tm_dK, umma_desc_sw128(aS + kk * 2048, TILE, 1024), umma_desc_sw128(aQ + kk * 2048, TILE, 1024),
-                      idesc_kv, (i > j) || kk != 0);
-          // dQ_i += dS K_j   (reduction over the 128 key rows of tile j)
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tm_dQ + 64 * i, umma_desc_sw128(aS + (kk >> 2) * TILE + (kk & 3) * 32, 16, 1024),
-                      umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, !(s == 0 && j == 0) || kk != 0);
-          umma_commit(&bar_g);
-        }
-        mbar_wait(&bar_g, par);
+        // dV_j (half 0) and dK_j (half 1) of this source are complete after the last pair's gradient UMMAs
+        mbar_wait(&bar_g, (pc - 1) & 1);
         tc_fence_after();
-        ++pc;
-      }
-      // dK_j, dV_j are complete for this source: TMEM -> bf16 -> HBM, thread r owns key row kv0 + r
-      {
-        const int kvrow = kv0 + tid;
-        float val[DP];
+        {
+          const int kvrow = kv0 + r;
+          const GradOut& go = half == 0 ? p.dv[s] : p.dk[s];
+          const uint32_t src = (half == 0 ? tm_dV : tm_dK) + lane_off;
+          float val[DP];
 #pragma unroll
-        for (int c = 0; c < DP / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld_32x16(tm_dV + lane_off + c * 16, v);
-          tmem_wait_ld();
+          for (int c = 0; c < DP / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x16(src + c * 16, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) val[c * 16 + e] = __uint_as_float(v[e]);
+            for (int e = 0; e < 16; ++e) val[c * 16 + e] = __uint_as_float(v[e]);
+          }
+          if (kvrow < p.T)
+            store_row_bf16<DP>(go.ptr + (long long)g * go.gs + ((long long)b * p.T + kvrow) * go.ld + h * go.head_stride, val, p.hs);
+          tc_fence_before();
         }
-        if (kvrow < p.T)
-          store_row_bf16(p.dv[s].ptr + (long long)g * p.dv[s].gs + ((long long)b * p.T + kvrow) * p.dv[s].ld + h * p.dv[s].head_stride, val, p.hs);
-#pragma unroll
-        for (int c = 0; c < DP / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld_32x16(tm_dK + lane_off + c * 16, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) val[c * 16 + e] = __uint_as_float(v[e]);
-        }
-        if (kvrow < p.T)
-          store_row_bf16(p.dk[s].ptr + (long long)g * p.dk[s].gs + ((long long)b * p.T + kvrow) * p.dk[s].ld + h * p.dk[s].head_stride, val, p.hs);
-        tc_fence_before();
       }
     }
-  }
-  // dQ tiles
-  for (int i = 0; i < n_qt; ++i) {
-    const int row = i * 128 + tid;
-    float val[DP];
+    // dQ tiles: half 0 stores tile 0, half 1 tile 1 (all gradient UMMAs have completed: bar_g of the last pair was waited)
+    if (half < n_qt) {
+      const int row = half * 128 + r;
+      float val[DP];
 #pragma unroll
-    for (int c = 0; c < DP / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld_32x16(tm_dQ + 64 * i + lane_off + c * 16, v);
-      tmem_wait_ld();
+      for (int c = 0; c < DP / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tm_dQ + 64 * half + lane_off + c * 16, v);
+        tmem_wait_ld();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) val[c * 16 + e] = __uint_as_float(v[e]);
+        for (int e = 0; e < 16; ++e) val[c * 16 + e] = __uint_as_float(v[e]);
+      }
+      if (row < p.T)
+        store_row_bf16<DP>(p.dq.ptr + (long long)g * p.dq.gs + ((long long)b * p.T + row) * p.dq.ld + h * p.dq.head_stride, val, p.hs);
     }
-    if (row < p.T)
-      store_row_bf16(p.dq.ptr + (long long)g * p.dq.gs + ((long long)b * p.T + row) * p.dq.ld + h * p.dq.head_stride, val, p.hs);
   }
   tc_fence_before();
   __syncthreads();
@@ -282,7 +314,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
 
 template <int DP>
 static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t st) {
-  constexpr int SMEM = 12 * 16384 + 1024;
+  constexpr int SMEM = 12 * 16384 + 80 + 1024;
   static bool attr = false;
   if (!attr) {
     TA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -290,7 +322,7 @@ static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cuda
   }
   const long long grid = (long long)p.H * p.B * p.G;
   TA_CHECK_ARG(grid < (1ll << 31), "attention grid too large");
-  attn_bwd_kernel<DP><<<(unsigned)grid, 128, SMEM, st>>>(maps, p);
+  attn_bwd_kernel<DP><<<(unsigned)grid, ATTB_THREADS, SMEM, st>>>(maps, p);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -324,6 +356,16 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
   if (make_head_map(&maps.q, q, hs, H, T, B, G, 128)) return 1;
   ta_attn_tensor dot{do_bf16, ldo, hs, o_gs};
   if (make_head_map(&maps.d_o, &dot, hs, H, T, B, G, 128)) return 1;
+  // O tiles for D = rowsum(dO * O_src): self-attention reads o (group dim = modality); cross-attention (G == 1) reads
+  // the per-source outputs, with the source index in the group dim of the tensor map
+  TA_CHECK_ARG(n_src == 1 || G == 1, "ta_attention_bwd: n_src > 1 requires G == 1");
+  if (n_src > 1) {
+    ta_attn_tensor ot{o_src_bf16, ldo, hs, o_src_stride};
+    if (make_head_map(&maps.o, &ot, hs, H, T, B, n_src, 128)) return 1;
+  } else {
+    ta_attn_tensor ot{o_bf16, ldo, hs, o_gs};
+    if (make_head_map(&maps.o, &ot, hs, H, T, B, G, 128)) return 1;
+  }
   AttnBwdParams p{};
   for (int s = 0; s < n_src; ++s) {
     if (make_head_map(&maps.k[s], &k[s], hs, H, T, B, G, 128)) return 1;

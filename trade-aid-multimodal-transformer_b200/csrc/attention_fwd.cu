@@ -42,13 +42,19 @@ __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnFwdParams p) {
   constexpr int KV_TILE_BYTES = KVB * 128;
   constexpr int TMEM_COLS = (KVB + DP) <= 128 ? 128 : 256;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_kv[2], bar_s, bar_o;
-  __shared__ uint32_t tmem_base_smem;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                 // [128][128 B]
-  uint8_t* sKV = smem + 16384;                        // 2 stages x (K tile, V tile)
-  uint8_t* sP = sKV + 4 * KV_TILE_BYTES;              // KVB/64 halves of [128][128 B]
+  // all shared memory is dynamic (no static part), so the tile base is the 1024-byte aligned start of the CTA window
+  // and two CTAs fit one SM: [Q 16 KB][2 x (K, V)][P KVB/64 x 16 KB][barriers]
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + 16384;
+  uint8_t* sP = sKV + 4 * KV_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (KVB / 64) * 16384);
+  uint64_t& bar_q = bars[0];
+  uint64_t* bar_kv = bars + 1;
+  uint64_t& bar_s = bars[3];
+  uint64_t& bar_o = bars[4];
+  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 5);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   const int tid = threadIdx.x, warp = tid >> 5;
   int bid = blockIdx.x;
@@ -89,10 +95,24 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnFwdParams p) {
     tma_load_5d(dK + KV_TILE_BYTES, &maps.v[s], &bar_kv[st], 0, h, j * KVB, b, g);
   };
 
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, KVB, 0, 0);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, DP, 0, 1);
+  const int nk_qk = (p.hs + 15) / 16;
+  auto issue_s = [&](int step) {   // S = Q K^T of a step whose K tile has landed
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sKV + (step & 1) * 2 * KV_TILE_BYTES);
+    for (int kk = 0; kk < nk_qk; ++kk)
+      umma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
+    umma_commit(&bar_s);
+  };
   if (tid == 0) {
     mbar_expect_tx(&bar_q, 16384);
     tma_load_5d(sQ, &maps.q, &bar_q, 0, h, q0, b, g);
     issue_kv(0);
+    if (total_steps > 1) issue_kv(1);
+    mbar_wait(&bar_q, 0);
+    mbar_wait(&bar_kv[0], 0);
+    tc_fence_after();
+    issue_s(0);
   }
 
   const int row = q0 + tid;  // query position of this thread
@@ -100,24 +120,11 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnFwdParams p) {
 #pragma unroll
   for (int i = 0; i < DP; ++i) o_tot[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, KVB, 0, 0);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, DP, 0, 1);
-  const int nk_qk = (p.hs + 15) / 16;
 
   for (int step = 0; step < total_steps; ++step) {
     const int s = step / n_kvb, j = step - s * n_kvb, st = step & 1;
     const int kv0 = j * KVB;
     const uint32_t par = step & 1;
-    if (tid == 0) {
-      if (step + 1 < total_steps) issue_kv(step + 1);
-      if (step == 0) mbar_wait(&bar_q, 0);
-      mbar_wait(&bar_kv[st], (step >> 1) & 1);
-      tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sKV + st * 2 * KV_TILE_BYTES);
-      for (int kk = 0; kk < nk_qk; ++kk)
-        umma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
-      umma_commit(&bar_s);
-    }
     if (j == 0) {
       m_run = -INFINITY;
       l_run = 0.f;
@@ -188,9 +195,16 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnFwdParams p) {
         umma_bf16(tmem_O, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                   umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, kk != 0);
       umma_commit(&bar_o);
+      // run ahead: S of the next step goes to the tensor pipe right behind P V (every thread has finished reading S)
+      if (step + 1 < total_steps) {
+        mbar_wait(&bar_kv[(step + 1) & 1], ((step + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s(step + 1);
+      }
     }
     mbar_wait(&bar_o, par);
     tc_fence_after();
+    if (tid == 0 && step + 2 < total_steps) issue_kv(step + 2);   // this step's K/V stage is free again
 #pragma unroll
     for (int c = 0; c < DP / 16; ++c) {
       uint32_t v[16];
@@ -281,7 +295,7 @@ int make_head_map(CUtensorMap* out, const ta_attn_tensor* t, int hs, int H, int 
 
 template <int KVB, int DP>
 static int launch_attn_fwd(const AttnMaps& maps, const AttnFwdParams& p, cudaStream_t st) {
-  constexpr int SMEM = 16384 + 4 * KVB * 128 + (KVB / 64) * 16384 + 1024;
+  constexpr int SMEM = 16384 + 4 * KVB * 128 + (KVB / 64) * 16384 + 64;
   static bool attr = false;
   if (!attr) {
     TA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<KVB, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));

@@ -44,7 +44,7 @@ struct GemmParams {
   long long ld_f32, f32_gs0, f32_gs1;
   __nv_bfloat16* out_bf16;
   long long ld_bf16, bf16_gs0, bf16_gs1;
-  int vec_f32, vec_bf16, vec_res, vec_aux;
+  int vec_f32, vec_bf16, vec_res, vec_aux, vec_bias;
 };
 
 __device__ __forceinline__ float epi_apply(float v, float bias, int act) {
@@ -189,84 +189,112 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* of = p.out_f32 ? p.out_f32 + g0 * p.f32_gs0 + g1 * p.f32_gs1 + (long long)row * p.ld_f32 : nullptr;
       __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(taddr_row + c * 32, v);
-        tmem_wait_ld();
-        if (!row_ok) continue;
-        const bool full = col0 + 32 <= p.N;
-        float f[32];
+      constexpr int NCH = BLOCK_N / 32;
+      int nch = (p.N - n0 + 31) / 32;
+      if (nch > NCH) nch = NCH;
+      // TMEM -> registers is software-pipelined: the load of chunk c+1 is in flight while chunk c is processed
+      uint32_t v[2][32];
+      tmem_ld_32x32(taddr_row, v[0]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-        if (bias || p.act) {
+      for (int c = 0; c < NCH; ++c) {
+        if (c < nch) {
+          const int col0 = n0 + c * 32;
+          const bool full = col0 + 32 <= p.N;
+          // bias for these 32 columns: 8 independent 128-bit broadcast loads, issued before waiting on TMEM
+          float4 b4[8];
+          const bool vb = bias && full && p.vec_bias;
+          if (vb) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float b = (bias && (full || col0 + i < p.N)) ? __ldg(bias + col0 + i) : 0.f;
-            f[i] = epi_apply(f[i], b, p.act);
+            for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
           }
-        }
-        if (aux) {
-          if (full && p.vec_aux) {
+          tmem_wait_ld();
+          if (c + 1 < nch) tmem_ld_32x32(taddr_row + (c + 1) * 32, v[(c + 1) & 1]);
+          if (row_ok) {
+            float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(aux + col0 + i);
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[c & 1][i]) * p.alpha;
+            if (vb) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float a = __bfloat162float(h[j]);
-                f[i + j] = p.aux_mode == TA_AUX_TANH_BWD ? f[i + j] * (1.f - a * a) : (a > 0.f ? f[i + j] : 0.f);
+              for (int i = 0; i < 8; ++i) {
+                f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
+              }
+            } else if (bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (full || col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
+            }
+            if (p.act == TA_ACT_TANH) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+            } else if (p.act == TA_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (aux) {
+              if (full && p.vec_aux) {
+                uint4 u4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) u4[i] = *reinterpret_cast<const uint4*>(aux + col0 + 8 * i);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u4[i]);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float a = __bfloat162float(h[j]);
+                    f[8 * i + j] = p.aux_mode == TA_AUX_TANH_BWD ? f[8 * i + j] * (1.f - a * a) : (a > 0.f ? f[8 * i + j] : 0.f);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) {
+                    const float a = __bfloat162float(aux[col0 + i]);
+                    f[i] = p.aux_mode == TA_AUX_TANH_BWD ? f[i] * (1.f - a * a) : (a > 0.f ? f[i] : 0.f);
+                  }
               }
             }
-          } else {
+            if (res) {
+              if (full && p.vec_res) {
+                float4 r4[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) {
-                const float a = __bfloat162float(aux[col0 + i]);
-                f[i] = p.aux_mode == TA_AUX_TANH_BWD ? f[i] * (1.f - a * a) : (a > 0.f ? f[i] : 0.f);
+                for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(res + col0 + 4 * i);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  f[4 * i] += r4[i].x; f[4 * i + 1] += r4[i].y; f[4 * i + 2] += r4[i].z; f[4 * i + 3] += r4[i].w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) f[i] += res[col0 + i];
               }
-          }
-        }
-        if (res) {
-          if (full && p.vec_res) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 r = *reinterpret_cast<const float4*>(res + col0 + i);
-              f[i] += r.x; f[i + 1] += r.y; f[i + 2] += r.z; f[i + 3] += r.w;
             }
-          } else {
+            if (of) {
+              if (full && p.vec_f32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) f[i] += res[col0 + i];
-          }
-        }
-        if (of) {
-          if (full && p.vec_f32) {
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(of + col0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              } else {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(of + col0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) of[col0 + i] = f[i];
-          }
-        }
-        if (ob) {
-          if (full && p.vec_bf16) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 u;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[i + 2 * j], f[i + 2 * j + 1]);
-              *reinterpret_cast<uint4*>(ob + col0 + i) = u;
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) of[col0 + i] = f[i];
+              }
             }
-          } else {
+            if (ob) {
+              if (full && p.vec_bf16) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 u;
+                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[i + 2 * j], f[i + 2 * j + 1]);
+                  *reinterpret_cast<uint4*>(ob + col0 + i) = u;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
+              }
+            }
           }
         }
       }
@@ -384,6 +412,7 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   p.vec_res = al(p.res, p.ld_res, p.res_gs0, p.res_gs1, 4, 16);
   p.vec_bf16 = al(p.out_bf16, p.ld_bf16, p.bf16_gs0, p.bf16_gs1, 8, 16);
   p.vec_aux = al(p.aux, p.ld_aux, p.aux_gs0, p.aux_gs1, 8, 16);
+  p.vec_bias = al(p.bias, 4, p.bias_gs0, p.bias_gs1, 4, 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tile width: the widest UMMA N that still yields about a wave of tiles
   const long long groups = (long long)G0 * G1;
