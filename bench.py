@@ -164,6 +164,7 @@ class TimedOps:
     def __init__(self, ops):
         self._ops = ops
         self.records = []   # (name, start_event, end_event, flops)
+        self.detail = {}
 
     def __getattr__(self, name):
         fn = getattr(self._ops, name)
@@ -183,6 +184,10 @@ class TimedOps:
                 for s in A.shape[:-2]:
                     G *= s
                 flops = 2.0 * Mm * N * K * G
+                name_key = f"gemm M={Mm} N={N} K={K} G={G} maj={am}{bm} act={kw.get('act', 0)} aux={kw.get('aux_mode', 0)} " \
+                           f"res={int(kw.get('residual') is not None)} f32={int(kw.get('out_f32') is not None)} " \
+                           f"bf16={int(kw.get('out_bf16') is not None)}"
+                self.detail.setdefault(name_key, []).append((e0, e1, flops))
             e0.record()
             out = fn(*a, **kw)
             e1.record()
@@ -339,6 +344,16 @@ def run_ours(args, cfg):
     tr.step(idx, tgt)
     agg = timed.summary()
     eng.ops = tr.ops = lib
+    if rank == 0 and os.environ.get("TRADEAID_BENCH_DETAIL"):
+        rows = []
+        for k, evs in timed.detail.items():
+            evs = evs[len(evs) // 2:]       # second (timed) step only
+            ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+            fl = sum(f for _, _, f in evs)
+            rows.append((ms, len(evs), fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, k))
+        with open(os.environ["TRADEAID_BENCH_DETAIL"], "w") as f:
+            for ms, n, tf, k in sorted(rows, reverse=True):
+                f.write(f"{ms:9.3f} ms  {n:4d} launches  {tf:8.1f} TF/s  {k}\n")
     tot_ms = sum(v[0] for v in agg.values())
     gm = agg.get("gemm", [0.0, 0, 0.0])
     gemm_tflops = gm[2] / (gm[0] * 1e-3) / 1e12 if gm[0] > 0 else 0.0

@@ -78,6 +78,77 @@ def test_gemm(lib, M, N, K, g, am, bm, epi):
     assert (ob.float() - ref).abs().max().item() <= 8e-3 * scale + 1e-3   # bf16 output rounding (2^-8 relative)
 
 
+GEMM_TMA_CASES = [
+    # M, N, K, groups, a_major, b_major, epilogue, outputs   (16-byte pitches everywhere: TMA-staged epilogue)
+    (128, 64, 64, (), 0, 0, "none", "bf16"),
+    (128, 64, 64, (), 0, 0, "none", "f32"),
+    (100, 72, 40, (), 0, 0, "bias_relu", "bf16"),
+    (100, 72, 40, (2,), 0, 0, "bias_tanh", "f32"),
+    (16, 24, 32, (2,), 0, 0, "none", "bf16"),           # N < one 32-column box
+    (300, 200, 136, (3, 2), 0, 0, "bias_tanh", "bf16"),
+    (300, 200, 136, (2,), 0, 0, "res", "f32"),
+    (300, 200, 136, (2,), 0, 0, "res_inplace", "f32"),
+    (300, 200, 136, (), 0, 0, "res", "both"),
+    (300, 200, 136, (), 0, 0, "bias", "both"),
+    (300, 200, 136, (2,), 0, 1, "tanh_bwd", "bf16"),
+    (300, 200, 136, (), 0, 1, "relu_bwd", "bf16"),
+    (1000, 520, 264, (), 0, 0, "res", "f32"),            # several tiles per CTA along N and M
+    (4096, 1024, 1024, (2,), 0, 0, "bias_relu", "bf16"),
+    (4096, 1024, 512, (2,), 0, 0, "res", "f32"),          # more tiles than SMs: buffer rotation across tiles
+    (4096, 1024, 1024, (), 0, 1, "relu_bwd", "bf16"),
+    (1024, 512, 4096, (3,), 1, 1, "none", "f32"),
+    (2048, 64, 32, (2, 24), 0, 0, "none", "bf16"),        # block-diagonal q/k/v stage 2 shape
+]
+
+
+@pytest.mark.parametrize("M,N,K,g,am,bm,epi,outs", GEMM_TMA_CASES)
+def test_gemm_tma_epilogue(lib, M, N, K, g, am, bm, epi, outs):
+    torch.manual_seed(1)
+    dev = "cuda"
+
+    def mk(rows, cols):
+        return torch.randn(*g, rows, _r8(cols) + 8, device=dev).to(torch.bfloat16)[..., :cols]
+
+    A = mk(M, K) if am == 0 else mk(K, M)
+    B = mk(N, K) if bm == 0 else mk(K, N)
+    Af = A.float() if am == 0 else A.float().transpose(-1, -2)
+    Bf = B.float() if bm == 0 else B.float().transpose(-1, -2)
+    ref = Af @ Bf.transpose(-1, -2)
+    kw = {}
+    ldf = _r8(N) + 4
+    of = torch.full((*g, M, ldf), float("nan"), device=dev)[..., :N] if outs in ("f32", "both") else None
+    ob = torch.zeros(*g, M, _r8(N) + 8, device=dev, dtype=torch.bfloat16)[..., :N] if outs in ("bf16", "both") else None
+    if epi in ("bias", "bias_tanh", "bias_relu"):
+        bias = torch.randn(*g, N, device=dev)
+        act = {"bias": lib.ACT_NONE, "bias_tanh": lib.ACT_TANH, "bias_relu": lib.ACT_RELU}[epi]
+        kw.update(bias=bias, act=act, alpha=0.05)
+        ref = ref * 0.05 + bias[..., None, :]
+        ref = torch.tanh(ref) if epi == "bias_tanh" else (torch.relu(ref) if epi == "bias_relu" else ref)
+    elif epi == "res":
+        res, bias = torch.randn(*g, M, N + 4, device=dev)[..., :N], torch.randn(*g, N, device=dev)
+        kw.update(residual=res, bias=bias)
+        ref = ref + bias[..., None, :] + res
+    elif epi == "res_inplace":      # engine.py: dx = dx + dkv @ Wkv (residual and output are the same buffer)
+        of.copy_(torch.randn(*g, M, N, device=dev))
+        kw.update(residual=of)
+        ref = ref + of
+    elif epi in ("tanh_bwd", "relu_bwd"):
+        aux = torch.randn(*g, M, _r8(N), device=dev).to(torch.bfloat16)[..., :N]
+        kw.update(aux=aux, aux_mode=lib.AUX_TANH_BWD if epi == "tanh_bwd" else lib.AUX_RELU_BWD)
+        ref = ref * (1 - aux.float() ** 2) if epi == "tanh_bwd" else torch.where(aux.float() > 0, ref, torch.zeros_like(ref))
+    lib.gemm(A, B, a_major=am, b_major=bm, out_f32=of, out_bf16=ob, **kw)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item() + 1e-6
+    if of is not None:
+        assert (of - ref).abs().max().item() <= 1e-4 * scale + 1e-5
+        pad = of.as_strided((*g, M, ldf), of.stride())[..., N:]          # the pitch padding must stay untouched
+        assert torch.isnan(pad).all() or epi == "res_inplace"
+    if ob is not None:
+        assert (ob.float() - ref).abs().max().item() <= 8e-3 * scale + 1e-3
+        pad = ob.as_strided((*g, M, _r8(N) + 8), ob.stride())[..., N:]
+        assert (pad == 0).all()
+
+
 # ------------------------------------------------------------------------------------------------ get_batch gather
 @pytest.mark.parametrize("M,N,B,T", [(2, 1000, 4, 4), (8, 100000, 64, 256), (3, 50, 1, 49)])
 def test_gather_batch_bit_exact(lib, M, N, B, T):

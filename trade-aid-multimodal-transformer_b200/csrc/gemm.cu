@@ -1,10 +1,16 @@
 // K2 — grouped bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (UMMA 128 x BLOCK_N x 16,
 // fp32 accumulators double-buffered in TMEM) -> tcgen05.ld epilogue with fused bias / tanh / ReLU / activation
-// backward / residual add, fp32 and/or bf16 stores. Persistent grid, warp-specialised:
+// backward / residual add, fp32 and/or bf16 outputs. The epilogue moves its global traffic with TMA: the saved
+// activation / residual tile is TMA-loaded into a swizzled per-warp staging buffer, combined in place with the
+// accumulators (thread = row) and TMA-stored, so every global transaction is a full line (a row-per-thread store
+// costs one LSU wavefront per 16 bytes and capped K=1024 GEMMs at ~0.6 of the mainloop rate). Operands that do not
+// meet TMA's 16-byte pitch rules take the direct row-per-thread path. Persistent grid, warp-specialised:
 //   warp 0    TMA producer (one lane)
 //   warp 1    TMEM allocator + MMA issuer (one lane)
 //   warps 2-5 epilogue (each owns the 32 TMEM lanes of its warp-id % 4 quarter)
 // Replaces every nn.Linear forward/backward of /root/reference/model.py (see include/tradeaid_b200.h).
+#include <cstdlib>
+#include <cstring>
 #include <cuda_bf16.h>
 
 #include "../../include/tradeaid_b200.h"
@@ -17,14 +23,15 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int GEMM_THREADS = 192;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_LIMIT = 227 * 1024 - 1024 - 512;  // opt-in maximum minus alignment slack and static barriers
+constexpr int MAX_STAGES = 8;
+constexpr int EPI_F32_BYTES = 32 * 32 * 4;           // one 32x32 fp32 chunk, 128-byte rows (SWIZZLE_128B)
+constexpr int EPI_BF16_BYTES = 32 * 32 * 2;          // one 32x32 bf16 chunk, 64-byte rows (SWIZZLE_64B)
 
 template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
@@ -45,25 +52,36 @@ struct GemmParams {
   __nv_bfloat16* out_bf16;
   long long ld_bf16, bf16_gs0, bf16_gs1;
   int vec_f32, vec_bf16, vec_res, vec_aux, vec_bias;
+  int stages;          // depth of the A/B smem ring
+  int tma_epi;         // 1: TMA-staged epilogue (maps below are valid)
+  int nbf, nbb;        // staging buffers per epilogue warp: fp32 chunks / bf16 chunks
+  int bf16_direct;     // tma_epi with both outputs: bf16 goes out with row-per-thread stores
+  int epi_warp_bytes;
+  int debug;           // TA_GEMM_DEBUG (dev only): 1 = skip global stores, 2 = skip the epilogue math and stores
 };
 
-__device__ __forceinline__ float epi_apply(float v, float bias, int act) {
-  v += bias;
-  if (act == TA_ACT_TANH) v = tanhf(v);
-  else if (act == TA_ACT_RELU) v = fmaxf(v, 0.f);
-  return v;
+struct EpiMaps {
+  CUtensorMap f32, bf16, res, aux;
+};
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ EpiMaps em, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t epi_bar[4][3];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -81,6 +99,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 4);
     }
+    for (int s = 0; s < 12; ++s) mbar_init(&epi_bar[0][0] + s, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -171,6 +190,200 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ epilogue
     const int quarter = warp & 3;
     int local = 0;
+    if (p.tma_epi) {
+      // ---- TMA-staged epilogue. Per warp: nbf fp32 chunk buffers (SWIZZLE_128B) then nbb bf16 chunk buffers
+      // (SWIZZLE_64B). Thread = accumulator row; 16-byte smem accesses hit swizzled chunk (j ^ row bits): conflict-free.
+      const bool has_res = p.res != nullptr, has_aux = p.aux != nullptr, has_f32 = p.out_f32 != nullptr,
+                 has_bf = p.out_bf16 != nullptr;
+      const bool has_load = has_res || has_aux;
+      const int nl = has_res ? p.nbf : p.nbb;          // rotation depth of the loaded buffer family
+      const int dbg = p.debug, act = p.act;
+      const float alpha = p.alpha;
+      const bool aux_tanh = p.aux_mode == TA_AUX_TANH_BWD;
+      const uint32_t wbase = smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + (warp - 2) * p.epi_warp_bytes;
+      const uint32_t fbuf0 = wbase, bbuf0 = wbase + p.nbf * EPI_F32_BYTES;
+      const uint32_t lbar0 = smem_u32(&epi_bar[warp - 2][0]);
+      const uint32_t frow = lane * 128, fsw = lane & 7;            // fp32 row offset, swizzle key
+      const uint32_t brow = lane * 64, bsw = (lane >> 1) & 3;      // bf16 row offset, swizzle key
+      uint32_t lphase = 0;    // bit b: parity the next wait on loaded buffer b uses
+      uint32_t sc = 0;        // running count of chunks stored (rotation of the store-only buffers)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int g = tile / tiles_per_group;
+        const int t = tile - g * tiles_per_group;
+        const int m0 = (t / p.n_blocks) * BLOCK_M;
+        const int n0 = (t % p.n_blocks) * BLOCK_N;
+        const int g0 = g % p.G0, g1 = g / p.G0;
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        const int row0 = m0 + quarter * 32;
+        constexpr int NCH = BLOCK_N / 32;
+        int nch = (p.N - n0 + 31) / 32;
+        if (nch > NCH) nch = NCH;
+        int next_load = 0;
+        // residual / saved-activation chunk q of this tile -> loaded buffer q % nl
+        auto issue_load = [&](int q) {
+          const int b = q % nl;
+          const uint32_t bar = lbar0 + b * 8;
+          if (has_res) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EPI_F32_BYTES) : "memory");
+            tma_load_4d_u32(fbuf0 + b * EPI_F32_BYTES, &em.res, bar, n0 + q * 32, row0, g0, g1);
+          } else {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EPI_BF16_BYTES) : "memory");
+            tma_load_4d_u32(bbuf0 + b * EPI_BF16_BYTES, &em.aux, bar, n0 + q * 32, row0, g0, g1);
+          }
+        };
+        if (has_load && row0 < p.M) {
+          if (lane == 0) {
+            bulk_wait_read<0>();     // every staging buffer of the previous tile has been read by its store
+            for (; next_load < nch && next_load < nl; ++next_load) issue_load(next_load);
+          }
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const int row = row0 + lane;
+        const bool row_ok = row < p.M;
+        const float* bias = p.bias ? p.bias + g0 * p.bias_gs0 + g1 * p.bias_gs1 : nullptr;
+        __nv_bfloat16* ob = p.bf16_direct ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
+        const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+        if (row0 >= p.M) {   // this warp's 32 rows lie entirely beyond M: nothing to store
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          continue;
+        }
+        // The chunk loop stays ROLLED: unrolled x8 the kernel was ~0.5 MB of SASS and the epilogue warps spent most of
+        // their time in instruction-fetch stalls (ncu: stall_no_inst on nearly every line).
+        uint32_t v[32];
+        tmem_ld_32x32(taddr_row, v);
+        int lb = 0;             // loaded buffer of this chunk (c % nl)
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          {
+            const int col0 = n0 + c * 32;
+            const bool full = col0 + 32 <= p.N;
+            float4 b4[8];
+            const bool vb = bias && full && p.vec_bias;
+            if (vb) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+            }
+            tmem_wait_ld();
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha;
+            if (c + 1 < nch) {   // v is dead: the next chunk's TMEM read overlaps the rest of this chunk
+              tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
+            } else {
+              // all TMEM reads of this accumulator are done: hand it back to the MMA warp before the stores
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            const uint32_t fbuf = fbuf0 + (has_res ? lb : (int)(sc & 1)) * EPI_F32_BYTES;
+            const uint32_t bbuf = bbuf0 + (has_aux ? lb : (int)(sc & 1)) * EPI_BF16_BYTES;
+            if (dbg != 2) {
+              if (vb) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
+                }
+              } else if (bias) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (full || col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
+              }
+              if (act == TA_ACT_TANH) {
+                if (has_f32) {   // fp32 consumers get the accurate tanh
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+                } else {         // bf16-only output: MUFU tanh (rel. error 2^-11) sits below the 2^-9 rounding of the
+                                 // store; tanhf costs ~60 issue cycles per warp and made the epilogue the bottleneck
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
+                }
+              } else if (act == TA_ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+              if (has_load) {
+                mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
+                lphase ^= 1u << lb;
+              }
+              if (has_aux) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 u = dbg == 3 ? make_uint4(0, 0, 0, 0) : lds128(bbuf + brow + ((j ^ bsw) << 4));
+                  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float a = __bfloat162float(h[k]);
+                    f[8 * j + k] = aux_tanh ? f[8 * j + k] * (1.f - a * a) : (a > 0.f ? f[8 * j + k] : 0.f);
+                  }
+                }
+              }
+              if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint4 u = dbg == 3 ? make_uint4(0, 0, 0, 0) : lds128(fbuf + frow + ((j ^ fsw) << 4));
+                  f[4 * j] += __uint_as_float(u.x); f[4 * j + 1] += __uint_as_float(u.y);
+                  f[4 * j + 2] += __uint_as_float(u.z); f[4 * j + 3] += __uint_as_float(u.w);
+                }
+              }
+              if (has_f32 && dbg != 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  sts128(fbuf + frow + ((j ^ fsw) << 4),
+                         make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                    __float_as_uint(f[4 * j + 3])));
+              }
+              if (has_bf) {
+                uint4 u[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u[j]);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+                }
+                if (!p.bf16_direct) {
+                  if (dbg != 4)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) sts128(bbuf + brow + ((j ^ bsw) << 4), u[j]);
+                } else if (row_ok && dbg != 1) {
+                  if (full && p.vec_bf16) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(ob + col0 + 8 * j) = u[j];
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                      if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
+                  }
+                }
+              }
+            } else if (has_load) {
+              mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
+              lphase ^= 1u << lb;
+            }
+            if (dbg != 5) fence_proxy_async_smem();   // generic-proxy writes above -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) {
+              if (dbg == 0 || dbg == 5) {
+                if (has_f32) tma_store_4d(&em.f32, fbuf, col0, row0, g0, g1);
+                if (has_bf && !p.bf16_direct) tma_store_4d(&em.bf16, bbuf, col0, row0, g0, g1);
+              }
+              bulk_commit_group();
+              bulk_wait_read<1>();      // the store of the previous chunk has drained its buffer
+              if (has_load)
+                for (; next_load < nch && next_load <= c + nl - 1; ++next_load) issue_load(next_load);
+            }
+            ++sc;
+            if (++lb == nl) lb = 0;
+            __syncwarp();
+          }
+        }
+      }
+      if (lane == 0) bulk_wait_all<0>();
+    } else
+    {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int g = tile / tiles_per_group;
       const int t = tile - g * tiles_per_group;
@@ -192,12 +405,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr int NCH = BLOCK_N / 32;
       int nch = (p.N - n0 + 31) / 32;
       if (nch > NCH) nch = NCH;
-      // TMEM -> registers is software-pipelined: the load of chunk c+1 is in flight while chunk c is processed
-      uint32_t v[2][32];
-      tmem_ld_32x32(taddr_row, v[0]);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (c < nch) {
+      // rolled chunk loop (code size, see above); the TMEM read of chunk c+1 overlaps the processing of chunk c
+      uint32_t v[32];
+      tmem_ld_32x32(taddr_row, v);
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        {
           const int col0 = n0 + c * 32;
           const bool full = col0 + 32 <= p.N;
           // bias for these 32 columns: 8 independent 128-bit broadcast loads, issued before waiting on TMEM
@@ -208,11 +421,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
           }
           tmem_wait_ld();
-          if (c + 1 < nch) tmem_ld_32x32(taddr_row + (c + 1) * 32, v[(c + 1) & 1]);
-          if (row_ok) {
-            float f[32];
+          float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[c & 1][i]) * p.alpha;
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+          if (c + 1 < nch) tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
+          if (row_ok) {
             if (vb) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -224,8 +437,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (full || col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
             }
             if (p.act == TA_ACT_TANH) {
+              if (of) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+                for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
+              }
             } else if (p.act == TA_ACT_RELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -303,6 +521,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    }
   }
 
   tc_fence_before();
@@ -363,6 +582,32 @@ static int make_operand_map(CUtensorMap* out, const ta_operand* op, int64_t MN, 
   return 0;
 }
 
+// epilogue tile map: logical [rows x cols] matrix of `es`-byte elements with two group dims, 32x32 boxes.
+// Returns false when the operand does not satisfy TMA's alignment rules (caller takes the direct path).
+static bool make_epi_map(CUtensorMap* out, const void* ptr, long long ld, long long gs0, long long gs1, int64_t rows,
+                         int64_t cols, int G0, int G1, bool is_f32) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc || !ptr) return false;
+  const int es = is_f32 ? 4 : 2;
+  const int q = 16 / es;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ld % q || ld < cols) return false;
+  if ((G0 > 1 && (gs0 % q || gs0 == 0)) || (G1 > 1 && (gs1 % q || gs1 == 0))) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)G0, (cuuint64_t)G1};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * es, G0 > 1 ? (cuuint64_t)gs0 * es : 16, G1 > 1 ? (cuuint64_t)gs1 * es : 16};
+  cuuint32_t box[4] = {32, 32, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <int BLOCK_N>
 static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -370,15 +615,48 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   if (make_operand_map(&tmA, A, p.M, p.K, p.G0, p.G1, BLOCK_M)) return 1;
   if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, BLOCK_N)) return 1;
   p.n_blocks = (int)ceil_div(p.N, BLOCK_N);
+  // ---- epilogue plan
+  static const int force_legacy = env_int("TA_GEMM_LEGACY_EPI", 0);
+  static const int force_nl = env_int("TA_GEMM_NLOAD", 0);
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  const bool need_f = p.res || p.out_f32, need_b = p.aux || p.out_bf16;
+  bool tma_ok = !force_legacy && !(p.aux && need_f);
+  if (tma_ok && p.out_f32) tma_ok = make_epi_map(&em.f32, p.out_f32, p.ld_f32, p.f32_gs0, p.f32_gs1, p.M, p.N, p.G0, p.G1, true);
+  if (tma_ok && p.res) tma_ok = make_epi_map(&em.res, p.res, p.ld_res, p.res_gs0, p.res_gs1, p.M, p.N, p.G0, p.G1, true);
+  if (tma_ok && p.aux) tma_ok = make_epi_map(&em.aux, p.aux, p.ld_aux, p.aux_gs0, p.aux_gs1, p.M, p.N, p.G0, p.G1, false);
+  p.bf16_direct = need_f && p.out_bf16 ? 1 : 0;
+  if (tma_ok && p.out_bf16 && !p.bf16_direct)
+    tma_ok = make_epi_map(&em.bf16, p.out_bf16, p.ld_bf16, p.bf16_gs0, p.bf16_gs1, p.M, p.N, p.G0, p.G1, false);
+  p.tma_epi = tma_ok ? 1 : 0;
+  p.nbf = p.nbb = 0;
+  if (tma_ok) {
+    if (need_f) p.nbf = p.res ? 3 : 2;
+    else if (need_b) p.nbb = p.aux ? 3 : 2;
+    if (force_nl == 2 || force_nl == 3) { if (p.res) p.nbf = force_nl; if (p.aux) p.nbb = force_nl; }
+    auto epi_bytes = [&]() { return 4 * (p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES); };
+    // keep the A/B ring at >= 4 stages when dropping the third (prefetch) buffer buys it
+    if (!force_nl && p.nbf == 3 && (SMEM_LIMIT - epi_bytes()) / Cfg::STAGE_BYTES < 4 &&
+        (SMEM_LIMIT - 4 * 2 * EPI_F32_BYTES) / Cfg::STAGE_BYTES >= 4 && p.k_blocks >= 16)
+      p.nbf = 2;
+    p.epi_warp_bytes = p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES;
+  } else {
+    p.bf16_direct = 0;
+    p.epi_warp_bytes = 0;
+  }
+  int stages = (SMEM_LIMIT - 4 * p.epi_warp_bytes) / Cfg::STAGE_BYTES;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  p.stages = stages;
+  const int smem_bytes = stages * Cfg::STAGE_BYTES + 4 * p.epi_warp_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     TA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
+                                       SMEM_LIMIT + 1024));
     attr_set = true;
   }
   const long long total = (long long)p.m_blocks * p.n_blocks * p.G0 * p.G1;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  gemm_bf16_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BLOCK_N><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -413,12 +691,15 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   p.vec_bf16 = al(p.out_bf16, p.ld_bf16, p.bf16_gs0, p.bf16_gs1, 8, 16);
   p.vec_aux = al(p.aux, p.ld_aux, p.aux_gs0, p.aux_gs1, 8, 16);
   p.vec_bias = al(p.bias, 4, p.bias_gs0, p.bias_gs1, 4, 16);
+  { static const int dbg = env_int("TA_GEMM_DEBUG", 0); p.debug = dbg; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tile width: the widest UMMA N that still yields about a wave of tiles
   const long long groups = (long long)G0 * G1;
   auto tiles = [&](int bn) { return groups * p.m_blocks * ceil_div(N, bn); };
+  static const int force_bn = env_int("TA_GEMM_BN", 0);
   int bn = 256;
-  if (N <= 64) bn = 64;
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) bn = force_bn;
+  else if (N <= 64) bn = 64;
   else if (N <= 128) bn = 128;
   else if (tiles(256) < num_sms() && tiles(128) > tiles(256)) bn = 128;
   if (bn == 128 && N > 64 && tiles(128) < num_sms() / 2 && tiles(64) > tiles(128)) bn = 64;
