@@ -206,101 +206,161 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 // LayerNorm backward. dy bf16 (gradient w.r.t. the LN output), x fp32 (saved LN input), mean/rstd saved.
 //   dx = rstd * (g*dy - mean_c(g*dy) - xhat * mean_c(g*dy*xhat))
 //   dstream_out = dstream_in + dx   (fp32, residual-stream gradient; dstream_in may be NULL => 0) and its bf16 copy
-//   partial dgamma/dbeta per block (rows handled by the block), reduced by ln_bwd_reduce_kernel.
-template <int NV>
-__global__ void __launch_bounds__(256)
+//   partial dgamma/dbeta per block, reduced in fixed order by partial_reduce_kernel.
+// Layout: TPR threads share one row (thread t owns float4 columns (k*TPR + t)*4), 256/TPR rows side by side ("slots"),
+// R independent row sets per pass so that R x slots rows (x, dy and the incoming stream gradient: 10 bytes/element) are
+// in flight before the first reduction. The first version kept a whole row plus its dgamma/dbeta accumulators in one
+// warp (193 registers, 8 warps per SM) and reached 27% of the HBM roofline on c4.
+template <int TPR, int NV, int R>
+__global__ void __launch_bounds__(256, NV == 1 ? 3 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ dstream_in, float* __restrict__ dstream_out, __nv_bfloat16* __restrict__ dstream_bf16,
-              long long ld_dbf, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, long long rows_total,
-              long long rows_per_group, int rows_per_block, int C) {
-  extern __shared__ float sh[];  // [2][warps][C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const long long row0 = (long long)blockIdx.x * rows_per_block;
-  // a block never straddles two groups: rows_per_group % rows_per_block == 0 is enforced by the host
-  const int g = (int)(row0 / rows_per_group);
+              long long ld_dbf, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, long long rows_per_group,
+              int C) {
+  constexpr int SLOTS = 256 / TPR;
+  constexpr int WPR = TPR / 32;                 // warps per row
+  __shared__ float red[2][2 * R][SLOTS][WPR > 1 ? WPR : 1];
+  __shared__ float4 slot_sum[SLOTS > 1 ? 2 * SLOTS * TPR * NV : 1];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int slot = tid / TPR, t = tid % TPR, wr = t >> 5;
+  const int g = blockIdx.y;
+  const long long grow0 = (long long)g * rows_per_group;
   const float* gm = gamma + (long long)g * C;
   float4 gg[NV], dg[NV], db[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const int c = (k * 32 + lane) * 4;
+    const int c = (k * TPR + t) * 4;
     gg[k] = c < C ? *reinterpret_cast<const float4*>(gm + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     dg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int rr = warp; rr < rows_per_block; rr += nwarp) {
-    const long long row = row0 + rr;
-    if (row >= rows_total) break;
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float* xr = x + row * C;
-    const __nv_bfloat16* dyr = dy + row * lddy;
-    float4 xh[NV], d[NV];
-    float s1 = 0.f, s2 = 0.f;
+  constexpr int RPP = R * SLOTS;                // rows per pass
+  const float inv_c = 1.f / C;
+  int par = 0;
+  for (long long pass = blockIdx.x; pass * RPP < rows_per_group; pass += gridDim.x, par ^= 1) {
+    float4 xv[R][NV], din[R][NV];
+    uint2 dv[R][NV];
+    float mean[R], rstd[R];
+    long long row[R];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = (k * 32 + lane) * 4;
-      if (c < C) {
-        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-        const uint2 u = *reinterpret_cast<const uint2*>(dyr + c);
-        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-        d[k] = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
-        xh[k] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-        dg[k].x += d[k].x * xh[k].x; dg[k].y += d[k].y * xh[k].y; dg[k].z += d[k].z * xh[k].z; dg[k].w += d[k].w * xh[k].w;
-        db[k].x += d[k].x; db[k].y += d[k].y; db[k].z += d[k].z; db[k].w += d[k].w;
-        d[k].x *= gg[k].x; d[k].y *= gg[k].y; d[k].z *= gg[k].z; d[k].w *= gg[k].w;
-        s1 += d[k].x + d[k].y + d[k].z + d[k].w;
-        s2 += d[k].x * xh[k].x + d[k].y * xh[k].y + d[k].z * xh[k].z + d[k].w * xh[k].w;
-      } else {
-        xh[k] = d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < R; ++r) {
+      const long long rg = pass * RPP + r * SLOTS + slot;
+      const bool ok = rg < rows_per_group;
+      row[r] = ok ? grow0 + rg : -1;
+      mean[r] = ok ? mean_in[row[r]] : 0.f;
+      rstd[r] = ok ? rstd_in[row[r]] : 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * TPR + t) * 4;
+        const bool in = ok && c < C;
+        xv[r][k] = in ? *reinterpret_cast<const float4*>(x + row[r] * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dv[r][k] = in ? *reinterpret_cast<const uint2*>(dy + row[r] * lddy + c) : make_uint2(0u, 0u);
+        din[r][k] = in && dstream_in ? *reinterpret_cast<const float4*>(dstream_in + row[r] * C + c)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
-    const float* din = dstream_in ? dstream_in + row * C : nullptr;
-    float* dout = dstream_out + row * C;
-    __nv_bfloat16* dbf = dstream_bf16 ? dstream_bf16 + row * ld_dbf : nullptr;
+    float s1[R], s2[R];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = (k * 32 + lane) * 4;
-      if (c < C) {
-        float4 r = make_float4(rstd * (d[k].x - s1 - xh[k].x * s2), rstd * (d[k].y - s1 - xh[k].y * s2),
-                               rstd * (d[k].z - s1 - xh[k].z * s2), rstd * (d[k].w - s1 - xh[k].w * s2));
-        if (din) {
-          const float4 a = *reinterpret_cast<const float4*>(din + c);
-          r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+    for (int r = 0; r < R; ++r) {
+      s1[r] = s2[r] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&dv[r][k].x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&dv[r][k].y);
+        const float4 d = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+        float4& xh = xv[r][k];     // x -> xhat in place (zero-filled columns/rows: rstd = 0 or dy = 0 keep them inert)
+        xh = make_float4((xh.x - mean[r]) * rstd[r], (xh.y - mean[r]) * rstd[r], (xh.z - mean[r]) * rstd[r],
+                         (xh.w - mean[r]) * rstd[r]);
+        dg[k].x += d.x * xh.x; dg[k].y += d.y * xh.y; dg[k].z += d.z * xh.z; dg[k].w += d.w * xh.w;
+        db[k].x += d.x; db[k].y += d.y; db[k].z += d.z; db[k].w += d.w;
+        const float4 gd = make_float4(d.x * gg[k].x, d.y * gg[k].y, d.z * gg[k].z, d.w * gg[k].w);
+        s1[r] += gd.x + gd.y + gd.z + gd.w;
+        s2[r] += gd.x * xh.x + gd.y * xh.y + gd.z * xh.z + gd.w * xh.w;
+      }
+      s1[r] = warp_sum(s1[r]);
+      s2[r] = warp_sum(s2[r]);
+    }
+    if (WPR > 1) {
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          red[par][2 * r][slot][wr] = s1[r];
+          red[par][2 * r + 1][slot][wr] = s2[r];
         }
-        *reinterpret_cast<float4*>(dout + c) = r;
-        if (dbf) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) {
+          a += red[par][2 * r][slot][w];
+          b += red[par][2 * r + 1][slot][w];
+        }
+        s1[r] = a;
+        s2[r] = b;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row[r] < 0) continue;
+      const float m1 = s1[r] * inv_c, m2 = s2[r] * inv_c;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * TPR + t) * 4;
+        if (c >= C) continue;
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&dv[r][k].x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&dv[r][k].y);
+        const float4 xh = xv[r][k];
+        float4 o;
+        o.x = rstd[r] * (__low2float(lo) * gg[k].x - m1 - xh.x * m2) + din[r][k].x;
+        o.y = rstd[r] * (__high2float(lo) * gg[k].y - m1 - xh.y * m2) + din[r][k].y;
+        o.z = rstd[r] * (__low2float(hi) * gg[k].z - m1 - xh.z * m2) + din[r][k].z;
+        o.w = rstd[r] * (__high2float(hi) * gg[k].w - m1 - xh.w * m2) + din[r][k].w;
+        *reinterpret_cast<float4*>(dstream_out + row[r] * C + c) = o;
+        if (dstream_bf16) {
+          __nv_bfloat162 plo = __floats2bfloat162_rn(o.x, o.y), phi = __floats2bfloat162_rn(o.z, o.w);
           uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&lo);
-          u.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(dbf + c) = u;
+          u.x = *reinterpret_cast<uint32_t*>(&plo);
+          u.y = *reinterpret_cast<uint32_t*>(&phi);
+          *reinterpret_cast<uint2*>(dstream_bf16 + row[r] * ld_dbf + c) = u;
         }
       }
     }
   }
-  // block reduction of dgamma / dbeta partials over warps (fixed order => deterministic)
-  float* sg = sh;
-  float* sb = sh + (size_t)nwarp * C;
+  // dgamma / dbeta partial of this block: sum over slots in fixed order, one row of the partial buffers per block
+  const long long prow = ((long long)g * gridDim.x + blockIdx.x) * C;
+  if (SLOTS > 1) {
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = (k * 32 + lane) * 4;
-    if (c < C) {
-      *reinterpret_cast<float4*>(sg + (size_t)warp * C + c) = dg[k];
-      *reinterpret_cast<float4*>(sb + (size_t)warp * C + c) = db[k];
+    for (int k = 0; k < NV; ++k) {
+      slot_sum[(slot * NV + k) * TPR + t] = dg[k];
+      slot_sum[((SLOTS + slot) * NV + k) * TPR + t] = db[k];
+    }
+    __syncthreads();
+    if (slot == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        for (int sl = 0; sl < SLOTS; ++sl) {
+          const float4 u = slot_sum[(sl * NV + k) * TPR + t], w = slot_sum[((SLOTS + sl) * NV + k) * TPR + t];
+          a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+          b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+        }
+        dg[k] = a;
+        db[k] = b;
+      }
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < nwarp; ++w) {
-      a += sg[(size_t)w * C + c];
-      b += sb[(size_t)w * C + c];
+  if (slot == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * TPR + t) * 4;
+      if (c < C) {
+        *reinterpret_cast<float4*>(part_dgamma + prow + c) = dg[k];
+        *reinterpret_cast<float4*>(part_dbeta + prow + c) = db[k];
+      }
     }
-    part_dgamma[(long long)blockIdx.x * C + c] = a;
-    part_dbeta[(long long)blockIdx.x * C + c] = b;
   }
 }
 
@@ -515,16 +575,23 @@ int32_t ta_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
   return 0;
 }
 
-static int ln_bwd_rows_per_block(int64_t rows_total, int64_t rows_per_group) {
-  int rpb = 64;
-  if (rows_total != rows_per_group)  // grouped: a block must not straddle two groups
-    while (rows_per_group % rpb) rpb >>= 1;
-  return rpb;
+// launch shape of ln_bwd_kernel: TPR threads per row, R row sets per pass, grid.x blocks per group
+static void ln_bwd_shape(int64_t rows_per_group, int64_t G, int C, int* tpr, int* r, int* gx) {
+  *tpr = C <= 128 ? 32 : C <= 256 ? 64 : C <= 512 ? 128 : 256;
+  *r = 4;
+  const int64_t rpp = (int64_t)*r * (256 / *tpr);
+  int64_t want = ((int64_t)num_sms() * 3) / G;              // 3 resident blocks per SM over all groups, one wave
+  const int64_t passes = ceil_div(rows_per_group, rpp);
+  if (want > passes) want = passes;
+  if (want < 1) want = 1;
+  *gx = (int)want;
 }
 
 int64_t ta_layernorm_bwd_workspace_floats(int64_t rows_total, int64_t rows_per_group, int32_t C) {
-  const int rpb = ln_bwd_rows_per_block(rows_total, rows_per_group);
-  return 2 * (rows_total / rows_per_group) * ceil_div(rows_per_group, rpb) * C;
+  int tpr, r, gx;
+  const int64_t G = rows_total / rows_per_group;
+  ln_bwd_shape(rows_per_group, G, C, &tpr, &r, &gx);
+  return 2 * G * gx * C;
 }
 
 int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, const float* gamma, const float* mean,
@@ -535,36 +602,28 @@ int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, cons
                "ta_layernorm_bwd: null pointer");
   TA_CHECK_ARG(C % 4 == 0 && C <= 2048 && lddy % 4 == 0 && ld_dbf % 4 == 0, "ta_layernorm_bwd: n_embd % 4 != 0 or > 2048");
   TA_CHECK_ARG(rows_total > 0 && rows_per_group > 0 && rows_total % rows_per_group == 0, "ta_layernorm_bwd: bad rows");
-  const int rpb = ln_bwd_rows_per_block(rows_total, rows_per_group);
-  const long long blocks_per_group = ceil_div(rows_per_group, rpb);
   const int G = (int)(rows_total / rows_per_group);
-  const int grid = (int)(blocks_per_group * G);
+  int tpr, r, gx;
+  ln_bwd_shape(rows_per_group, G, C, &tpr, &r, &gx);
   float* pg = workspace;
-  float* pb = workspace + (long long)grid * C;
+  float* pb = workspace + (long long)G * gx * C;
   auto st = (cudaStream_t)stream;
-  const size_t shm = (size_t)2 * 8 * C * sizeof(float);
-#define TA_LN_BWD(NV)                                                                                                  \
-  do {                                                                                                                 \
-    static bool attr_set = false;                                                                                      \
-    if (!attr_set) {                                                                                                   \
-      cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 128 * NV * 4);     \
-      attr_set = true;                                                                                                 \
-    }                                                                                                                  \
-    ln_bwd_kernel<NV><<<grid, 256, shm, st>>>((const __nv_bfloat16*)dy_bf16, lddy, x, gamma, mean, rstd, dstream_in,   \
-                                              dstream_out, (__nv_bfloat16*)dstream_bf16, ld_dbf, pg, pb, rows_total,   \
-                                              rows_per_group, rpb, C);                                                 \
-  } while (0)
-  if (C <= 128) TA_LN_BWD(1);
-  else if (C <= 256) TA_LN_BWD(2);
-  else if (C <= 512) TA_LN_BWD(4);
-  else if (C <= 1024) TA_LN_BWD(8);
-  else TA_LN_BWD(16);
+  dim3 grid((unsigned)gx, (unsigned)G);
+#define TA_LN_BWD(TPR, NV)                                                                                             \
+  ln_bwd_kernel<TPR, NV, 4><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy_bf16, lddy, x, gamma, mean, rstd, dstream_in, \
+                                                  dstream_out, (__nv_bfloat16*)dstream_bf16, ld_dbf, pg, pb,            \
+                                                  rows_per_group, C)
+  if (tpr == 32) TA_LN_BWD(32, 1);
+  else if (tpr == 64) TA_LN_BWD(64, 1);
+  else if (tpr == 128) TA_LN_BWD(128, 1);
+  else if (C <= 1024) TA_LN_BWD(256, 1);
+  else TA_LN_BWD(256, 2);
 #undef TA_LN_BWD
   TA_CHECK_LAUNCH();
   dim3 rg((unsigned)ceil_div(C, 256), G);
-  partial_reduce_kernel<<<rg, 256, 0, st>>>(pg, dgamma, (int)blocks_per_group, C, C);
+  partial_reduce_kernel<<<rg, 256, 0, st>>>(pg, dgamma, gx, C, C);
   TA_CHECK_LAUNCH();
-  partial_reduce_kernel<<<rg, 256, 0, st>>>(pb, dbeta, (int)blocks_per_group, C, C);
+  partial_reduce_kernel<<<rg, 256, 0, st>>>(pb, dbeta, gx, C, C);
   TA_CHECK_LAUNCH();
   return 0;
 }

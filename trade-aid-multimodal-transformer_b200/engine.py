@@ -297,7 +297,9 @@ class Engine:
         bf, f32 = self.act_dtype, torch.float32
         cs_ws = self.buf("cs_ws", (max(ops.colsum_workspace(BT, 4 * C, M), ops.colsum_workspace(BT, max(d.vocab_sizes), 1),
                                        ops.colsum_workspace(BT, 3 * H * h2p, M)),), f32)
-        ln_ws = self.buf("ln_ws", (ops.layernorm_bwd_workspace(M, BT, C),), f32)
+        # the workspace depends on the launch shape: grouped launches (all modalities) and the per-modality launches
+        # of the cross-attention LayerNorm share one buffer
+        ln_ws = self.buf("ln_ws", (max(ops.layernorm_bwd_workspace(M, BT, C), ops.layernorm_bwd_workspace(1, BT, C)),), f32)
         dx = self.buf("dx", (M, BT, C), f32)
         dxb = self.buf("dxb", (M, BT, C), bf)
         # ---- output heads
