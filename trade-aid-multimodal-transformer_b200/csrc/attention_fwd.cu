@@ -2,14 +2,18 @@
 // (/root/reference/model.py:60-73) and the selective cross-attention heads (model.py:136-159, one independent causal
 // softmax per key/value source modality, outputs summed).
 //
-// One CTA (128 threads) per (group g, batch b, head h, 128-row query tile). Per key/value block of KVB rows:
-//   TMA  : Q tile once; K and V tiles double-buffered (prefetch of the next block/source overlaps the current one)
-//   UMMA : S = Q K^T  (128 x KVB x hs, fp32 in TMEM)             -- issued by thread 0
-//   SIMT : thread r owns row r of S: tcgen05.ld, scale, causal mask, online softmax (running max / sum, exp2),
-//          P (bf16) written to 128B-swizzled smem as the A operand of the second UMMA
-//   UMMA : O_blk = P V   (128 x hs x KVB; V is the MN-major B operand straight from its [kv, d] TMA tile)
-//   SIMT : O = O * alpha + O_blk in registers; at the end of a source: O_total += O / l, lse stored
-// Nothing of size T x T ever touches HBM. head_size <= 64 (padded with TMA zero-fill to a 128-byte row).
+// Persistent, warp-specialised: one CTA per SM walks (group, batch, head) work items; inside an item the schedule is
+// q tile i (128 rows) -> source s -> key/value block j <= i (128 rows): one (i, s) pass is a softmax "segment".
+//   warp 16  loader : TMA Q tiles (2 slots) and K/V blocks (3-stage ring); runs ahead across segments and work items
+//   warp 17  issuer : S = Q K^T (128x128x hs) into one of two TMEM S buffers, one pair AHEAD of the softmax;
+//                     O += P V (128 x hs x 128, V as the MN-major B operand) into one of two TMEM O buffers
+//   warps 0-15 math : thread (row r, column quarter) owns 32 S columns: tcgen05.ld, causal mask, online softmax with exp2
+//                     (row max exchanged between the four quarters through smem, lazy rescale of O in TMEM only when the
+//                     max moves by more than 2^8), P (bf16) into one of two 128B-swizzled smem buffers; the segment
+//                     epilogue (O / l, += over sources, lse) is deferred behind the next pair's exponentials so the
+//                     last P V of a segment never stalls the math warps.
+// The first version ran these phases one after another in a 128-thread CTA (tensor pipe 8% active, warps mostly
+// waiting on mbarriers: profiles/r01_ncu_attn_v2_*.csv). Nothing of size T x T ever touches HBM. head_size <= 64.
 #include <cmath>
 #include <cuda_bf16.h>
 
@@ -20,6 +24,10 @@
 namespace ta {
 
 constexpr int ATT_MAX_SRC = 8;
+constexpr int AF_MATH_WARPS = 16;
+constexpr int AF_THREADS = (AF_MATH_WARPS + 4) * 32;   // warps 0-15 math, 16 loader, 17 issuer, 18-19 idle (whole warpgroup for setmaxnreg)
+constexpr int AF_KV_STAGES = 3;
+constexpr int AF_TILE = 16384;   // 128 rows x 128 bytes
 
 struct AttnMaps {
   CUtensorMap q;
@@ -28,7 +36,7 @@ struct AttnMaps {
 };
 
 struct AttnFwdParams {
-  int T, B, H, G, hs, n_src, n_qtiles;
+  int T, B, H, G, hs, n_src, n_qtiles, total_work;
   float scale_log2;
   __nv_bfloat16* o;       // [G][B*T][ldo], head h at column h*hs
   long long ldo, o_gs;
@@ -37,222 +45,330 @@ struct AttnFwdParams {
   float* lse;             // [n_src][G][B][H][T], natural log
 };
 
-template <int KVB, int DP>
-__global__ void __launch_bounds__(128)
-attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnFwdParams p) {
-  constexpr int KV_TILE_BYTES = KVB * 128;
-  constexpr int TMEM_COLS = (KVB + DP) <= 128 ? 128 : 256;
-  // all shared memory is dynamic (no static part), so the tile base is the 1024-byte aligned start of the CTA window
-  // and two CTAs fit one SM: [Q 16 KB][2 x (K, V)][P KVB/64 x 16 KB][barriers]
+// The (work, i, s, j) schedule; every warp role walks the same sequence with its own copy.
+struct AfIter {
+  int total, n_qt, n_src, stride;
+  int work, i, s, j;
+  int n, k, qc;   // running counters over the CTA's lifetime: pairs, segments, q tiles
+  __device__ __forceinline__ void init(int total_, int n_qt_, int n_src_, int first, int stride_) {
+    total = total_; n_qt = n_qt_; n_src = n_src_; stride = stride_;
+    work = first; i = s = j = 0; n = k = qc = 0;
+  }
+  __device__ __forceinline__ bool valid() const { return work < total; }
+  __device__ __forceinline__ bool first_in_seg() const { return j == 0; }
+  __device__ __forceinline__ bool last_in_seg() const { return j == i; }
+  __device__ __forceinline__ bool new_q() const { return j == 0 && s == 0; }
+  __device__ __forceinline__ bool last_of_q() const { return j == i && s == n_src - 1; }
+  __device__ __forceinline__ void next() {
+    ++n;
+    if (j < i) { ++j; return; }
+    ++k; j = 0;
+    if (s + 1 < n_src) { ++s; return; }
+    s = 0; ++qc;
+    if (i + 1 < n_qt) { ++i; return; }
+    i = 0; work += stride;
+  }
+};
+
+template <int DP, bool MULTI>
+__global__ void __launch_bounds__(AF_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnFwdParams p) {
+  constexpr int EC = DP / 4 < 8 ? 8 : DP / 4;   // output columns per (active) math thread
+  constexpr int NS = AF_KV_STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sKV = smem + 16384;
-  uint8_t* sP = sKV + 4 * KV_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (KVB / 64) * 16384);
-  uint64_t& bar_q = bars[0];
-  uint64_t* bar_kv = bars + 1;
-  uint64_t& bar_s = bars[3];
-  uint64_t& bar_o = bars[4];
-  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* sQ = smem;                              // 2 slots
+  uint8_t* sKV = smem + 2 * AF_TILE;               // NS x (K, V)
+  uint8_t* sP = sKV + NS * 2 * AF_TILE;            // 2 buffers x 2 column halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * AF_TILE);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2]
+  uint64_t* kv_full = bars + 4;       // [NS]
+  uint64_t* kv_empty = bars + 4 + NS; // [NS]
+  uint64_t* s_full = bars + 4 + 2 * NS;   // [2]
+  uint64_t* s_empty = s_full + 2;     // [2] 256 arrivals
+  uint64_t* p_full = s_full + 4;      // [2] 256 arrivals
+  uint64_t* p_empty = s_full + 6;     // [2] P V of the pair complete (P buffer free, O updated)
+  uint64_t* o_full = s_full + 8;      // [2]
+  uint64_t* o_empty = s_full + 10;    // [2] 256 arrivals
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(s_full + 12);
+  float* sMax = reinterpret_cast<float*>(s_full + 13);   // [2 parity][4 quarters][128]
+  float* sL = sMax + 1024;                                // [2 parity][4 quarters][128]
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  int bid = blockIdx.x;
-  const int qt = bid % p.n_qtiles; bid /= p.n_qtiles;
-  const int h = bid % p.H; bid /= p.H;
-  const int b = bid % p.B;
-  const int g = bid / p.B;
-  const int q0 = qt * 128;
-  const int last_row = (q0 + 127 < p.T - 1) ? q0 + 127 : p.T - 1;
-  const int n_kvb = last_row / KVB + 1;
-  const int total_steps = p.n_src * n_kvb;
-
   if (tid == 0) {
-    mbar_init(&bar_q, 1);
-    mbar_init(&bar_kv[0], 1);
-    mbar_init(&bar_kv[1], 1);
-    mbar_init(&bar_s, 1);
-    mbar_init(&bar_o, 1);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&q_full[x], 1); mbar_init(&q_empty[x], 1);
+      mbar_init(&s_full[x], 1); mbar_init(&s_empty[x], AF_MATH_WARPS * 32);
+      mbar_init(&p_full[x], AF_MATH_WARPS * 32); mbar_init(&p_empty[x], 1);
+      mbar_init(&o_full[x], 1); mbar_init(&o_empty[x], AF_MATH_WARPS * 32);
+    }
+    for (int x = 0; x < NS; ++x) { mbar_init(&kv_full[x], 1); mbar_init(&kv_empty[x], 1); }
     fence_mbar_init();
   }
-  if (warp == 0) {
-    tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  if (warp == AF_MATH_WARPS + 1) {
+    tmem_alloc(tmem_base_smem, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + KVB;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t tmem_base = *tmem_base_smem;
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+DP) O1 [320,320+DP)
+  AfIter it;
+  it.init(p.total_work, p.n_qtiles, p.n_src, blockIdx.x, gridDim.x);
 
-  auto issue_kv = [&](int step) {
-    const int s = step / n_kvb, j = step - s * n_kvb, st = step & 1;
-    uint8_t* dK = sKV + st * 2 * KV_TILE_BYTES;
-    mbar_expect_tx(&bar_kv[st], 2 * KV_TILE_BYTES);
-    tma_load_5d(dK, &maps.k[s], &bar_kv[st], 0, h, j * KVB, b, g);
-    tma_load_5d(dK + KV_TILE_BYTES, &maps.v[s], &bar_kv[st], 0, h, j * KVB, b, g);
-  };
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, KVB, 0, 0);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, DP, 0, 1);
-  const int nk_qk = (p.hs + 15) / 16;
-  auto issue_s = [&](int step) {   // S = Q K^T of a step whose K tile has landed
-    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sKV + (step & 1) * 2 * KV_TILE_BYTES);
-    for (int kk = 0; kk < nk_qk; ++kk)
-      umma_bf16(tmem_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
-    umma_commit(&bar_s);
-  };
-  if (tid == 0) {
-    mbar_expect_tx(&bar_q, 16384);
-    tma_load_5d(sQ, &maps.q, &bar_q, 0, h, q0, b, g);
-    issue_kv(0);
-    if (total_steps > 1) issue_kv(1);
-    mbar_wait(&bar_q, 0);
-    mbar_wait(&bar_kv[0], 0);
-    tc_fence_after();
-    issue_s(0);
-  }
-
-  const int row = q0 + tid;  // query position of this thread
-  float o_tot[DP], o_acc[DP];
-#pragma unroll
-  for (int i = 0; i < DP; ++i) o_tot[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-
-  for (int step = 0; step < total_steps; ++step) {
-    const int s = step / n_kvb, j = step - s * n_kvb, st = step & 1;
-    const int kv0 = j * KVB;
-    const uint32_t par = step & 1;
-    if (j == 0) {
-      m_run = -INFINITY;
-      l_run = 0.f;
-#pragma unroll
-      for (int i = 0; i < DP; ++i) o_acc[i] = 0.f;
-    }
-    mbar_wait(&bar_s, par);
-    tc_fence_after();
-    // number of 32-column chunks that hold at least one unmasked column for some row of this warp
-    const int warp_last_row = q0 + warp * 32 + 31;
-    int n_chunks = (warp_last_row - kv0) / 32 + 1;
-    if (n_chunks > KVB / 32) n_chunks = KVB / 32;
-    if (n_chunks < 0) n_chunks = 0;
-    // pass 1: row maximum
-    float mx = m_run;
-    for (int c = 0; c < n_chunks; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x = (kv0 + c * 32 + i <= row) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-        mx = fmaxf(mx, x);
-      }
-    }
-    const float alpha = exp2f(m_run - mx);  // m_run = -inf on the first block => 0
-    float psum = 0.f;
-    // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
-    for (int c = 0; c < KVB / 32; ++c) {
-      uint32_t packed[16];
-      if (c < n_chunks) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float x0 = (kv0 + c * 32 + i <= row) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - mx) : 0.f;
-          const float x1 = (kv0 + c * 32 + i + 1 <= row) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - mx) : 0.f;
-          psum += x0 + x1;
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-          packed[i / 2] = *reinterpret_cast<uint32_t*>(&h2);
+  if (warp >= AF_MATH_WARPS) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  if (warp == AF_MATH_WARPS) {
+    // ================================================================== loader
+    if ((tid & 31) == 0) {
+      for (; it.valid(); it.next()) {
+        int w = it.work;
+        const int h = w % p.H; w /= p.H;
+        const int b = w % p.B;
+        const int g = w / p.B;
+        if (it.new_q()) {
+          const int qs = it.qc & 1;
+          mbar_wait(&q_empty[qs], ((it.qc >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[qs], AF_TILE);
+          tma_load_5d(sQ + qs * AF_TILE, &maps.q, &q_full[qs], 0, h, it.i * 128, b, g);
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) packed[i] = 0u;
-      }
-      // 32 columns = 4 chunks of 16 B at logical chunk index (c%2)*4 + q inside half c/2
-      uint8_t* rowp = sP + (c >> 1) * 16384 + tid * 128;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int lc = (c & 1) * 4 + q;
-        *reinterpret_cast<uint4*>(rowp + ((lc ^ (tid & 7)) << 4)) =
-            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        const int st = it.n % NS, u = it.n / NS;
+        mbar_wait(&kv_empty[st], (u & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * AF_TILE);
+        uint8_t* dK = sKV + st * 2 * AF_TILE;
+        tma_load_5d(dK, &maps.k[it.s], &kv_full[st], 0, h, it.j * 128, b, g);
+        tma_load_5d(dK + AF_TILE, &maps.v[it.s], &kv_full[st], 0, h, it.j * 128, b, g);
       }
     }
-    l_run = l_run * alpha + psum;
-    m_run = mx;
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t aP = smem_u32(sP), aV = smem_u32(sKV + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES);
-      // only the k-steps that can hold unmasked columns for some row of the tile
-      int nk = (last_row - kv0) / 16 + 1;
-      if (nk > KVB / 16) nk = KVB / 16;
-      for (int kk = 0; kk < nk; ++kk)
-        umma_bf16(tmem_O, umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                  umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, kk != 0);
-      umma_commit(&bar_o);
-      // run ahead: S of the next step goes to the tensor pipe right behind P V (every thread has finished reading S)
-      if (step + 1 < total_steps) {
-        mbar_wait(&bar_kv[(step + 1) & 1], ((step + 1) >> 1) & 1);
+  } else if (warp == AF_MATH_WARPS + 1) {
+    // ================================================================== UMMA issuer
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DP, 0, 1);
+      const int nk_qk = (p.hs + 15) / 16;
+      auto issue_s = [&](const AfIter& a) {
+        const int qs = a.qc & 1, st = a.n % NS, sb = a.n & 1;
+        if (a.new_q()) mbar_wait(&q_full[qs], (a.qc >> 1) & 1);
+        mbar_wait(&kv_full[st], (a.n / NS) & 1);
+        mbar_wait(&s_empty[sb], ((a.n >> 1) & 1) ^ 1);
         tc_fence_after();
-        issue_s(step + 1);
+        const uint32_t aQ = smem_u32(sQ + qs * AF_TILE), aK = smem_u32(sKV + st * 2 * AF_TILE);
+        for (int kk = 0; kk < nk_qk; ++kk)
+          umma_bf16(tmem_base + sb * 128, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+                    idesc_s, kk != 0);
+        umma_commit(&s_full[sb]);
+      };
+      auto issue_pv = [&](const AfIter& a) {
+        const int st = a.n % NS, pb = a.n & 1, ob = a.k & 1;
+        if (a.first_in_seg()) mbar_wait(&o_empty[ob], ((a.k >> 1) & 1) ^ 1);
+        mbar_wait(&p_full[pb], (a.n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aP = smem_u32(sP + pb * 2 * AF_TILE), aV = smem_u32(sKV + st * 2 * AF_TILE + AF_TILE);
+        // only the k-steps that can hold unmasked columns for some row of the tile
+        const int last_row = (a.i * 128 + 127 < p.T - 1) ? a.i * 128 + 127 : p.T - 1;
+        int nk = (last_row - a.j * 128) / 16 + 1;
+        if (nk > 8) nk = 8;
+        for (int kk = 0; kk < nk; ++kk)
+          umma_bf16(tmem_base + 256 + ob * 64, umma_desc_sw128(aP + (kk >> 2) * AF_TILE + (kk & 3) * 32, 16, 1024),
+                    umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, !a.first_in_seg() || kk != 0);
+        umma_commit(&p_empty[pb]);
+        umma_commit(&kv_empty[st]);
+        if (a.last_in_seg()) umma_commit(&o_full[ob]);
+        if (a.last_of_q()) umma_commit(&q_empty[a.qc & 1]);
+      };
+      AfIter is = it;   // S runs one pair ahead of P V
+      if (is.valid()) { issue_s(is); is.next(); }
+      for (; it.valid(); it.next()) {
+        if (is.valid()) { issue_s(is); is.next(); }
+        issue_pv(it);
       }
     }
-    mbar_wait(&bar_o, par);
-    tc_fence_after();
-    if (tid == 0 && step + 2 < total_steps) issue_kv(step + 2);   // this step's K/V stage is free again
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ================================================================== math warps
+    // thread = (row r, column quarter qd): 32 S columns and EC output columns; the four warps that share a TMEM lane
+    // quarter (warp % 4) exchange row maxima / row sums through smem and a 128-thread named barrier
+    const int r = tid & 127, qd = tid >> 7, wq = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const int bar_id = 1 + wq;
+    const bool ep_active = qd * EC < DP;        // DP = 16: only two quarters own output columns
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_tot[MULTI ? EC : 1];
 #pragma unroll
-    for (int c = 0; c < DP / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld_32x16(tmem_O + lane_off + c * 16, v);
-      tmem_wait_ld();
+    for (int e = 0; e < (MULTI ? EC : 1); ++e) o_tot[e] = 0.f;
+    // deferred segment epilogue
+    bool pend = false;
+    int pe_work = 0, pe_i = 0, pe_s = 0, pe_k = 0;
+    bool pe_last_src = false;
+    float pe_m = 0.f, pe_l = 0.f;
+    int xpar = 0;     // parity of the max-exchange buffer
+    auto epilogue = [&]() {
+      float* sl = sL + (pe_k & 1) * 512;
+      sl[qd * 128 + r] = pe_l;
+      named_bar_sync(bar_id, 128);
+      const float l = (sl[r] + sl[128 + r]) + (sl[256 + r] + sl[384 + r]);
+      const float inv = 1.f / l;
+      const int ob = pe_k & 1;
+      mbar_wait(&o_full[ob], (pe_k >> 1) & 1);
+      tc_fence_after();
+      uint32_t ov[EC];
+      if (ep_active) {
+        tmem_ld_cols<EC>(tmem_base + 256 + ob * 64 + lane_off + qd * EC, ov);
+        tmem_wait_ld();
+      }
+      tc_fence_before();
+      mbar_arrive(&o_empty[ob]);
+      int w = pe_work;
+      const int h = w % p.H; w /= p.H;
+      const int b = w % p.B;
+      const int g = w / p.B;
+      const int row = pe_i * 128 + r;
+      const bool row_ok = row < p.T;
+      if (ep_active) {
+        const long long off = (long long)g * p.o_gs + ((long long)b * p.T + row) * p.ldo + h * p.hs + qd * EC;
+        float val[EC];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = o_acc[c * 16 + i] * alpha + __uint_as_float(v[i]);
-    }
-    if (j == n_kvb - 1) {
-      const float inv = 1.f / l_run;
-      if (row < p.T) {
-        p.lse[((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T + row] = m_run * 0.6931471805599453f + logf(l_run);
-        if (p.o_src) {
-          __nv_bfloat16* dst = p.o_src + (long long)s * p.o_src_stride + (long long)g * p.o_gs +
-                               ((long long)b * p.T + row) * p.ldo + h * p.hs;
+        for (int e = 0; e < EC; ++e) val[e] = __uint_as_float(ov[e]) * inv;
+        auto store = [&](__nv_bfloat16* dst, const float (&x)[EC]) {
 #pragma unroll
-          for (int i = 0; i < DP; i += 8) {
-            if (i < p.hs) {
+          for (int e = 0; e < EC; e += 8) {
+            if (qd * EC + e < p.hs) {
               uint4 u;
               __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(o_acc[i + 2 * e] * inv, o_acc[i + 2 * e + 1] * inv);
-              *reinterpret_cast<uint4*>(dst + i) = u;
+              for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(x[e + 2 * q], x[e + 2 * q + 1]);
+              *reinterpret_cast<uint4*>(dst + e) = u;
             }
           }
+        };
+        if constexpr (MULTI) {
+          if (p.o_src && row_ok) store(p.o_src + (long long)pe_s * p.o_src_stride + off, val);
+#pragma unroll
+          for (int e = 0; e < EC; ++e) o_tot[e] += val[e];
+          if (pe_last_src) {
+#pragma unroll
+            for (int e = 0; e < EC; ++e) val[e] = o_tot[e];
+            if (row_ok) store(p.o + off, val);
+#pragma unroll
+            for (int e = 0; e < EC; ++e) o_tot[e] = 0.f;
+          }
+        } else if (row_ok) {
+          store(p.o + off, val);
+          if (p.o_src) store(p.o_src + off, val);
         }
       }
-#pragma unroll
-      for (int i = 0; i < DP; ++i) o_tot[i] += o_acc[i] * inv;
-    }
-  }
+      if (qd == 0 && row_ok)
+        p.lse[((((long long)pe_s * p.G + g) * p.B + b) * p.H + h) * p.T + row] = pe_m * 0.6931471805599453f + logf(l);
+      pend = false;
+    };
 
-  if (row < p.T) {
-    __nv_bfloat16* dst = p.o + (long long)g * p.o_gs + ((long long)b * p.T + row) * p.ldo + h * p.hs;
+    for (; it.valid(); it.next()) {
+      const int sb = it.n & 1, pb = sb;
+      const int row = it.i * 128 + r, kv0 = it.j * 128;
+      const bool diag = it.j == it.i;
+      if (it.first_in_seg()) { m_run = -INFINITY; l_run = 0.f; }
+      mbar_wait(&s_full[sb], (it.n >> 1) & 1);
+      tc_fence_after();
+      // this thread's 32 columns: needed unless they lie above the diagonal for every row of the warp (warp-uniform)
+      const int col_base = kv0 + qd * 32;
+      const bool need = !diag || col_base <= it.i * 128 + wq * 32 + 31;
+      // columns of this chunk that are unmasked for this row: all 32 below the diagonal tile, else a prefix
+      const int nvalid = !diag ? 32 : (row - col_base + 1 < 0 ? 0 : (row - col_base + 1 > 32 ? 32 : row - col_base + 1));
+      uint32_t sv[32];
+      if (need) {
+        tmem_ld_32x32(tmem_base + sb * 128 + lane_off + qd * 32, sv);
+        tmem_wait_ld();
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[sb]);             // the issuer may overwrite this S buffer (pair n + 2)
+      float mx = -INFINITY;
+      if (need) {
+        if (nvalid == 32) {
 #pragma unroll
-    for (int i = 0; i < DP; i += 8) {
-      if (i < p.hs) {
-        uint4 u;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(o_tot[i + 2 * e], o_tot[i + 2 * e + 1]);
-        *reinterpret_cast<uint4*>(dst + i) = u;
+          for (int e = 0; e < 32; ++e) mx = e < nvalid ? fmaxf(mx, __uint_as_float(sv[e])) : mx;
+        }
+      }
+      float* sm = sMax + xpar * 512;
+      xpar ^= 1;
+      sm[qd * 128 + r] = mx;
+      named_bar_sync(bar_id, 128);
+      mx = fmaxf(fmaxf(sm[r], sm[128 + r]), fmaxf(sm[256 + r], sm[384 + r])) * p.scale_log2;  // column 0 is never masked
+      float m_new = fmaxf(m_run, mx);
+      if (m_run != -INFINITY && m_new - m_run <= 8.f) m_new = m_run;   // lazy rescale: P <= 2^8, exact after / l
+      const float alpha = ex2_approx(m_run - m_new);                    // first block: exp2(-inf) = 0
+      float psum = 0.f;
+      uint32_t pk[16];
+      if (need) {
+        if (nvalid == 32) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float x0 = ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - m_new);
+            const float x1 = ex2_approx(__uint_as_float(sv[e + 1]) * p.scale_log2 - m_new);
+            psum += x0 + x1;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+            pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float x0 = ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - m_new);
+            float x1 = ex2_approx(__uint_as_float(sv[e + 1]) * p.scale_log2 - m_new);
+            x0 = e < nvalid ? x0 : 0.f;
+            x1 = e + 1 < nvalid ? x1 : 0.f;
+            psum += x0 + x1;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+            pk[e / 2] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+      }
+      l_run = l_run * alpha + psum;
+      if (pend) epilogue();                  // previous segment: its last P V has had the exponentials above to finish
+      // P -> smem (A operand of P V); the P V that last read this buffer (pair n - 2) must be complete
+      mbar_wait(&p_empty[pb], ((it.n >> 1) & 1) ^ 1);
+      uint8_t* rowp = sP + pb * 2 * AF_TILE + (qd >> 1) * AF_TILE + r * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(rowp + ((((qd & 1) * 4 + q) ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      fence_proxy_async_smem();
+      if (!it.first_in_seg() && __any_sync(0xffffffffu, alpha != 1.f)) {
+        // the running max of some row moved: rescale this thread's O columns in TMEM once P V of pair n - 1 is done
+        mbar_wait(&p_empty[pb ^ 1], ((it.n - 1) >> 1) & 1);
+        tc_fence_after();
+        if (ep_active) {
+          uint32_t ov[EC];
+          const uint32_t to = tmem_base + 256 + (it.k & 1) * 64 + lane_off + qd * EC;
+          tmem_ld_cols<EC>(to, ov);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < EC; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+          tmem_st_cols<EC>(to, ov);
+          tmem_wait_st();
+        }
+      }
+      m_run = m_new;
+      tc_fence_before();
+      mbar_arrive(&p_full[pb]);
+      if (it.last_in_seg()) {
+        pend = true;
+        pe_work = it.work; pe_i = it.i; pe_s = it.s; pe_k = it.k; pe_last_src = it.s == p.n_src - 1;
+        pe_m = m_run; pe_l = l_run;
       }
     }
+    if (pend) epilogue();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == AF_MATH_WARPS + 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -293,17 +409,16 @@ int make_head_map(CUtensorMap* out, const ta_attn_tensor* t, int hs, int H, int 
   return 0;
 }
 
-template <int KVB, int DP>
+template <int DP, bool MULTI>
 static int launch_attn_fwd(const AttnMaps& maps, const AttnFwdParams& p, cudaStream_t st) {
-  constexpr int SMEM = 16384 + 4 * KVB * 128 + (KVB / 64) * 16384 + 64;
+  constexpr int SMEM = (2 + 2 * AF_KV_STAGES + 4) * AF_TILE + 256 + 8192 + 64;
   static bool attr = false;
   if (!attr) {
-    TA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<KVB, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    TA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DP, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
-  const long long grid = (long long)p.n_qtiles * p.H * p.B * p.G;
-  TA_CHECK_ARG(grid < (1ll << 31), "attention grid too large");
-  attn_fwd_kernel<KVB, DP><<<(unsigned)grid, 128, SMEM, st>>>(maps, p);
+  const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
+  attn_fwd_kernel<DP, MULTI><<<grid, AF_THREADS, SMEM, st>>>(maps, p);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -323,12 +438,11 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
   TA_CHECK_ARG(G > 0 && B > 0 && T > 0 && H > 0, "ta_attention_fwd: non-positive size");
   TA_CHECK_ARG(ldo % 8 == 0 && o_gs % 8 == 0 && (reinterpret_cast<uintptr_t>(o_bf16) & 15) == 0, "ta_attention_fwd: output alignment");
   TA_CHECK_ARG(dropout_p == 0.f, "ta_attention_fwd: attention dropout not implemented in this build");
-  const int KVB = T <= 64 ? 64 : 128;
   AttnMaps maps;
   if (make_head_map(&maps.q, q, hs, H, T, B, G, 128)) return 1;
   for (int s = 0; s < n_src; ++s) {
-    if (make_head_map(&maps.k[s], &k[s], hs, H, T, B, G, KVB)) return 1;
-    if (make_head_map(&maps.v[s], &v[s], hs, H, T, B, G, KVB)) return 1;
+    if (make_head_map(&maps.k[s], &k[s], hs, H, T, B, G, 128)) return 1;
+    if (make_head_map(&maps.v[s], &v[s], hs, H, T, B, G, 128)) return 1;
   }
   AttnFwdParams p{};
   p.T = T; p.B = B; p.H = H; p.G = G; p.hs = hs; p.n_src = n_src;
@@ -337,14 +451,16 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
   p.o = (__nv_bfloat16*)o_bf16; p.ldo = ldo; p.o_gs = o_gs;
   p.o_src = (__nv_bfloat16*)o_src_bf16; p.o_src_stride = o_src_stride;
   p.lse = lse;
+  const long long total = (long long)G * B * H;
+  TA_CHECK_ARG(total < (1ll << 31), "attention grid too large");
+  p.total_work = (int)total;
   auto st = (cudaStream_t)stream;
-  const int DP = hs <= 16 ? 16 : (hs <= 32 ? 32 : 64);
-  if (KVB == 64) {
-    if (DP == 16) return launch_attn_fwd<64, 16>(maps, p, st);
-    if (DP == 32) return launch_attn_fwd<64, 32>(maps, p, st);
-    return launch_attn_fwd<64, 64>(maps, p, st);
+  if (n_src > 1) {
+    if (hs <= 16) return launch_attn_fwd<16, true>(maps, p, st);
+    if (hs <= 32) return launch_attn_fwd<32, true>(maps, p, st);
+    return launch_attn_fwd<64, true>(maps, p, st);
   }
-  if (DP == 16) return launch_attn_fwd<128, 16>(maps, p, st);
-  if (DP == 32) return launch_attn_fwd<128, 32>(maps, p, st);
-  return launch_attn_fwd<128, 64>(maps, p, st);
+  if (hs <= 16) return launch_attn_fwd<16, false>(maps, p, st);
+  if (hs <= 32) return launch_attn_fwd<32, false>(maps, p, st);
+  return launch_attn_fwd<64, false>(maps, p, st);
 }
