@@ -1,14 +1,23 @@
 // K3 backward — recompute attention backward on tcgen05/TMEM (autograd of /root/reference/model.py:60-73, 136-159).
 //
-// One CTA (128 threads) per (group, batch, head); the whole causal T x T triangle (T <= 256) is walked in 128 x 128
-// tiles with every accumulator resident in TMEM (512 columns):
-//   S, dP          2 x 128 columns   recomputed per tile pair:  S = Q_i K_j^T,  dP = dO_i V_j^T
+// Persistent, warp-specialised: one CTA per SM walks (group, batch, head) work items; inside an item the whole causal
+// T x T triangle (T <= 256) is walked in 128 x 128 tile pairs, source s -> key/value tile j -> query tile i >= j, with
+// every accumulator resident in TMEM (512 columns):
+//   S, dP          2 x 128 columns   recomputed per pair:  S = Q_i K_j^T,  dP = dO_i V_j^T
 //   dV_j, dK_j     2 x 64  columns   accumulated over the query tiles i >= j
 //   dQ_0, dQ_1     2 x 64  columns   accumulated over key/value tiles j <= i AND over all key/value sources
-// Thread r owns row r of the tile: P = exp2(S*c - lse), dS = P * (dP - D) * hs^-0.5 with D = rowsum(dO * O_src);
-// P and dS go to 128B-swizzled smem once and are consumed by three UMMAs through two descriptor views of the same
-// bytes: K-major (dQ += dS K) and MN-major (dV += P^T dO, dK += dS^T Q). K_j, V_j, Q_i, dO_i are read straight from
-// their TMA tiles as MN-major B operands. No T x T tensor and no atomics; dq/dk/dv are written once, in bf16.
+//   warp 16  loader : TMA Q/dO tiles of the head, K/V tiles through a 2-stage ring (runs ahead)
+//   warp 17  issuer : S and dP of pair n+1 are issued as soon as the math warps have pulled S / dP of pair n out of
+//                     TMEM; the three gradient UMMAs of pair n run while the math warps work on pair n+1
+//   warps 0-15 math : thread (row r, column quarter) owns 32 columns: P = exp2(S*c - lse), dS = P * (dP - D) with
+//                     D = rowsum(dO * O_src) computed once per head straight from global memory; P and dS go to
+//                     128B-swizzled smem once and are consumed by three UMMAs through two descriptor views of the same
+//                     bytes: K-major (dQ += dS K) and MN-major (dV += P^T dO, dK += dS^T Q). The dK/dV/dQ read-outs are
+//                     deferred behind the next pair's math so the gradient UMMAs never stall the math warps.
+// K_j, V_j, Q_i, dO_i are read straight from their TMA tiles as MN-major B operands. hs^-0.5 is applied to dQ / dK at
+// read-out. No T x T tensor and no atomics; dq/dk/dv are written once, in bf16.
+// The previous version ran S/dP -> math -> gradient UMMAs strictly one after another in a 9-warp CTA (tensor pipe 8%
+// active, 43% of the samples waiting on mbarriers: profiles/r01_ncu_attn_v2.txt).
 #include <cmath>
 #include <cuda_bf16.h>
 
@@ -22,7 +31,7 @@ constexpr int ATTB_MAX_SRC = 8;
 int make_head_map(CUtensorMap* out, const ta_attn_tensor* t, int hs, int H, int T, int B, int G, int box_rows);
 
 struct AttnBwdMaps {
-  CUtensorMap q, d_o, o;
+  CUtensorMap q, d_o;
   CUtensorMap k[ATTB_MAX_SRC];
   CUtensorMap v[ATTB_MAX_SRC];
 };
@@ -33,8 +42,9 @@ struct GradOut {
 };
 
 struct AttnBwdParams {
-  int T, B, H, G, hs, n_src, n_qt;
+  int T, B, H, G, hs, n_src, n_qt, total_work;
   float scale, scale_log2;
+  const __nv_bfloat16* d_o;    // [G][B*T][ldo]
   const __nv_bfloat16* o;      // [G][B*T][ldo]
   const __nv_bfloat16* o_src;  // [n_src] x same, or NULL when n_src == 1
   long long ldo, o_gs, o_src_stride;
@@ -44,287 +54,387 @@ struct AttnBwdParams {
   GradOut dv[ATTB_MAX_SRC];
 };
 
-template <int DP>
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[DP], int n) {
-#pragma unroll
-  for (int i = 0; i < DP; i += 8) {
-    if (i < n) {
-      uint4 u;
-      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[i + 2 * e], v[i + 2 * e + 1]);
-      *reinterpret_cast<uint4*>(dst + i) = u;
-    }
+constexpr int AB_MATH_WARPS = 16;
+constexpr int AB_MATH_THREADS = AB_MATH_WARPS * 32;
+constexpr int AB_THREADS = (AB_MATH_WARPS + 4) * 32;   // warps 0-15 math, 16 loader, 17 issuer, 18-19 idle (setmaxnreg)
+constexpr int AB_TILE = 16384;                          // 128 rows x 128 B
+
+// The (work, s, j, i) pair schedule; every warp role walks the same sequence with its own copy.
+struct AbIter {
+  int work, s, j, i;
+  int n, ks, hc;   // running counters over the CTA's lifetime: pairs, (s, j) key/value tiles, heads
+  __device__ __forceinline__ void init(int first) { work = first; s = j = i = 0; n = ks = hc = 0; }
+  __device__ __forceinline__ bool first_of_head() const { return s == 0 && j == 0 && i == 0; }
+  __device__ __forceinline__ bool first_i() const { return i == j; }
+  __device__ __forceinline__ void next(int n_qt, int n_src, int stride) {
+    ++n;
+    if (i + 1 < n_qt) { ++i; return; }
+    ++ks;
+    if (j + 1 < n_qt) { ++j; i = j; return; }
+    j = i = 0;
+    if (s + 1 < n_src) { ++s; return; }
+    s = 0; ++hc;
+    work += stride;
   }
-}
+};
 
-constexpr int ATTB_THREADS = 288;   // warps 0-7: softmax/gradient math (two column halves), warp 8: TMA + UMMA issuer
+// barrier table (index * 8 bytes from the table base)
+enum : uint32_t {
+  AB_Q_FULL = 0, AB_Q_EMPTY = 2, AB_KV_FULL = 4, AB_KV_EMPTY = 6, AB_S_FULL = 8, AB_DP_FULL = 10, AB_S_EMPTY = 12,
+  AB_DP_EMPTY = 14, AB_PDS_FULL = 16, AB_G_DONE = 17, AB_DKV_EMPTY = 18, AB_DQ_EMPTY = 19, AB_NBARS = 20
+};
 
 template <int DP>
-__global__ void __launch_bounds__(ATTB_THREADS, 1)
+__global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant__ AttnBwdParams p) {
-  constexpr int TILE = 16384;  // 128 rows x 128 B
+  constexpr int TILE = AB_TILE;
+  constexpr int OC = DP / 2;   // gradient columns per math thread at read-out
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                // 2 tiles
-  uint8_t* sdO = smem + 2 * TILE;    // 2 tiles
-  uint8_t* sKV = smem + 4 * TILE;    // 2 stages x (K, V)
-  uint8_t* sP = smem + 8 * TILE;     // 2 halves (kv 0-63, 64-127); also the landing zone of the O tiles for D
-  uint8_t* sdS = smem + 10 * TILE;   // 2 halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * TILE);
-  uint64_t& bar_q = bars[0];         // Q and dO tiles landed
-  uint64_t* bar_kv = bars + 1;       // [2] K/V stage landed
-  uint64_t& bar_sp = bars[3];        // S and dP of a pair are in TMEM
-  uint64_t& bar_g = bars[4];         // gradient UMMAs of a pair are complete (P/dS smem and dV/dK/dQ TMEM readable)
-  uint64_t& bar_pr = bars[5];        // 256 arrivals: P/dS of a pair written to smem, S/dP TMEM consumed
-  uint64_t& bar_o = bars[6];         // O tiles of a source landed (for D)
-  uint64_t& bar_od = bars[7];        // 256 arrivals: D computed, O tiles consumed
-  uint32_t& tmem_base_smem = *reinterpret_cast<uint32_t*>(bars + 8);
-  float* sD = reinterpret_cast<float*>(bars + 10);   // [2][128] rowsum(dO * O_src) per query tile
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  // [Q 2 slots][dO 2 slots][2 stages x (K, V)][P: 2 column halves][dS: 2 column halves][barriers][D][lse]
+  const uint32_t sQ = smem_u32(smem), sdO = sQ + 2 * TILE, sKV = sQ + 4 * TILE, sP = sQ + 8 * TILE, sdS = sQ + 10 * TILE;
+  const uint32_t bb = sQ + 12 * TILE;                        // barrier i at bb + 8 * i
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + 12 * TILE + AB_NBARS * 8);
+  const uint32_t sD = bb + AB_NBARS * 8 + 16;                // fp32 [n_src][256] rowsum(dO * O_src)
+  const uint32_t sLse = sD + ATTB_MAX_SRC * 256 * 4;         // fp32 [n_src][256] lse * log2(e)
+  if ((sQ & 1023u) != 0) __trap();
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  int bid = blockIdx.x;
-  const int h = bid % p.H; bid /= p.H;
-  const int b = bid % p.B;
-  const int g = bid / p.B;
-  const int n_qt = p.n_qt;  // == number of kv tiles
-  const int total_ks = p.n_src * n_qt;
-
   if (tid == 0) {
-    mbar_init(&bar_q, 1);
-    mbar_init(&bar_kv[0], 1);
-    mbar_init(&bar_kv[1], 1);
-    mbar_init(&bar_sp, 1);
-    mbar_init(&bar_g, 1);
-    mbar_init(&bar_pr, 256);
-    mbar_init(&bar_o, 1);
-    mbar_init(&bar_od, 256);
+    for (uint32_t x = 0; x < AB_NBARS; ++x) {
+      const bool wide = x == AB_S_EMPTY || x == AB_S_EMPTY + 1 || x == AB_DP_EMPTY || x == AB_DP_EMPTY + 1 ||
+                        x == AB_PDS_FULL || x == AB_DKV_EMPTY || x == AB_DQ_EMPTY;
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bb + 8 * x), "r"(wide ? AB_MATH_THREADS : 1));
+    }
     fence_mbar_init();
   }
-  if (warp == 0) {
-    tmem_alloc(&tmem_base_smem, 512);
+  if (warp == AB_MATH_WARPS + 1) {
+    tmem_alloc(tmem_base_smem, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
-  const uint32_t tm_dQ = tmem_base + 384;  // + 64 * i
-  const int nk_qk = (p.hs + 15) / 16;
+  const uint32_t tmem_base = *tmem_base_smem;
+  // TMEM columns: S halves [0,128) dP halves [128,256) dV [256,320) dK [320,384) dQ_0 [384,448) dQ_1 [448,512)
+  const int n_qt = p.n_qt, n_src = p.n_src, stride = gridDim.x, total = p.total_work;
+  AbIter it;
+  it.init(blockIdx.x);
+  // Q/dO smem slot of query tile ti: two tiles per head use slot = tile, one tile per head alternates between heads
+  auto slot = [&](const AbIter& a, int ti) { return n_qt == 2 ? ti : (a.hc & 1); };
+  auto slot_use = [&](const AbIter& a) { return n_qt == 2 ? a.hc : (a.hc >> 1); };
 
-  if (warp == 8) {
-    // ================================================================== TMA + UMMA issuer (one lane)
-    if ((tid & 31) == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
-      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, DP, 1, 1);   // dV, dK: A = P/dS seen MN-major, B = dO/Q MN-major
-      constexpr uint32_t idesc_q = umma_idesc_bf16(128, DP, 0, 1);    // dQ: A = dS K-major, B = K MN-major
-      auto issue_kv = [&](int ks) {
-        const int s = ks / n_qt, j = ks - s * n_qt, st = ks & 1;
-        uint8_t* dK = sKV + st * 2 * TILE;
-        mbar_expect_tx(&bar_kv[st], 2 * TILE);
-        tma_load_5d(dK, &maps.k[s], &bar_kv[st], 0, h, j * 128, b, g);
-        tma_load_5d(dK + TILE, &maps.v[s], &bar_kv[st], 0, h, j * 128, b, g);
-      };
-      auto issue_o = [&](int s) {   // O_src tiles of source s -> sP region (free: no gradient UMMA in flight)
-        mbar_expect_tx(&bar_o, n_qt * TILE);
-        for (int i = 0; i < n_qt; ++i) tma_load_5d(sP + i * TILE, &maps.o, &bar_o, 0, h, i * 128, b, p.o_src ? s : g);
-      };
-      auto issue_sdp = [&](int j, int i, int st) {
-        const uint32_t aQ = smem_u32(sQ + i * TILE), aO = smem_u32(sdO + i * TILE);
-        const uint32_t aK = smem_u32(sKV + st * 2 * TILE), aV = aK + TILE;
-        for (int kk = 0; kk < nk_qk; ++kk)
-          umma_bf16(tm_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc_s, kk != 0);
-        for (int kk = 0; kk < nk_qk; ++kk)
-          umma_bf16(tm_dP, umma_desc_sw128(aO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024), idesc_s, kk != 0);
-        umma_commit(&bar_sp);
-      };
-      mbar_expect_tx(&bar_q, n_qt * 2 * TILE);
-      for (int i = 0; i < n_qt; ++i) {
-        tma_load_5d(sQ + i * TILE, &maps.q, &bar_q, 0, h, i * 128, b, g);
-        tma_load_5d(sdO + i * TILE, &maps.d_o, &bar_q, 0, h, i * 128, b, g);
-      }
-      issue_o(0);
-      issue_kv(0);
-      if (total_ks > 1) issue_kv(1);
-      mbar_wait(&bar_q, 0);
-      int pc = 0, g_seen = 0;
-      for (int s = 0; s < p.n_src; ++s) {
-        if (s > 0) issue_o(s);   // the last pair of the previous source was waited on (bar_g) below
-        mbar_wait(&bar_od, s & 1);           // every math thread is done with the O tiles: sP may be overwritten
-        for (int j = 0; j < n_qt; ++j) {
-          const int ks = s * n_qt + j, st = ks & 1;
-          mbar_wait(&bar_kv[st], (ks >> 1) & 1);
-          for (int i = j; i < n_qt; ++i, ++pc) {
-            // S/dP TMEM is free: the math threads arrived on bar_pr of the previous pair before we got here
-            tc_fence_after();
-            issue_sdp(j, i, st);
-            mbar_wait(&bar_pr, pc & 1);        // P, dS of this pair are in smem
-            tc_fence_after();
-            const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS), aQ = smem_u32(sQ + i * TILE), aO = smem_u32(sdO + i * TILE);
-            const uint32_t aK = smem_u32(sKV + st * 2 * TILE);
-            for (int kk = 0; kk < 8; ++kk)     // dV_j += P^T dO_i
-              umma_bf16(tm_dV, umma_desc_sw128(aP + kk * 2048, TILE, 1024), umma_desc_sw128(aO + kk * 2048, TILE, 1024),
-                        idesc_kv, (i > j) || kk != 0);
-            for (int kk = 0; kk < 8; ++kk)     // dK_j += dS^T Q_i
-              umma_bf16(tm_dK, umma_desc_sw128(aS + kk * 2048, TILE, 1024), umma_desc_sw128(aQ + kk * 2048, TILE, 1024),
-                        idesc_kv, (i > j) || kk != 0);
-            for (int kk = 0; kk < 8; ++kk)     // dQ_i += dS K_j
-              umma_bf16(tm_dQ + 64 * i, umma_desc_sw128(aS + (kk >> 2) * TILE + (kk & 3) * 32, 16, 1024),
-                        umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, !(s == 0 && j == 0) || kk != 0);
-            umma_commit(&bar_g);
-            // P/dS smem and this pair's K/V must outlive the gradient UMMAs. (Issuing the next pair's S/dP before this
-            // wait was measured slower: 1.41 ms vs 1.30 ms for the c4 self-attention layer.)
-            mbar_wait(&bar_g, pc & 1);
-            g_seen = pc + 1;
+  if (warp >= AB_MATH_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == AB_MATH_WARPS) {
+      // ================================================================== loader (one lane)
+      if ((tid & 31) == 0) {
+        auto bar = [&](uint32_t i) { return reinterpret_cast<uint64_t*>(smem + 12 * TILE) + i; };
+        auto load_kv = [&](const AbIter& a, int h, int b, int g) {
+          const int st = a.ks & 1;
+          mbar_wait_a(bb + 8 * (AB_KV_EMPTY + st), ((a.ks >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar(AB_KV_FULL + st), 2 * TILE);
+          uint8_t* dK = smem + 4 * TILE + st * 2 * TILE;
+          tma_load_5d(dK, &maps.k[a.s], bar(AB_KV_FULL + st), 0, h, a.j * 128, b, g);
+          tma_load_5d(dK + TILE, &maps.v[a.s], bar(AB_KV_FULL + st), 0, h, a.j * 128, b, g);
+        };
+        for (; it.work < total; it.next(n_qt, n_src, stride)) {
+          if (!it.first_i()) continue;       // one K/V tile per (s, j); Q/dO once per head
+          int w = it.work;
+          const int h = w % p.H; w /= p.H;
+          const int b = w % p.B;
+          const int g = w / p.B;
+          if (it.first_of_head()) {
+            // tile 0 is released two pairs before the end of the previous head, so its reload (and the first pair of
+            // this head) overlaps the previous head's tail; tile 1 lands during the first pair
+            for (int i = 0; i < n_qt; ++i) {
+              const int sl = slot(it, i);
+              mbar_wait_a(bb + 8 * (AB_Q_EMPTY + sl), (slot_use(it) & 1) ^ 1);
+              mbar_expect_tx(bar(AB_Q_FULL + sl), 2 * TILE);
+              tma_load_5d(smem + sl * TILE, &maps.q, bar(AB_Q_FULL + sl), 0, h, i * 128, b, g);
+              tma_load_5d(smem + 2 * TILE + sl * TILE, &maps.d_o, bar(AB_Q_FULL + sl), 0, h, i * 128, b, g);
+              if (i == 0) load_kv(it, h, b, g);   // the first pair needs K/V tile 0 next: before waiting for slot 1
+            }
+          } else {
+            load_kv(it, h, b, g);
           }
-          for (; g_seen < pc; ++g_seen) mbar_wait(&bar_g, g_seen & 1);   // phases must be consumed one by one
-          if (ks + 2 < total_ks) issue_kv(ks + 2);
+        }
+      }
+    } else if (warp == AB_MATH_WARPS + 1) {
+      // ================================================================== UMMA issuer (one lane)
+      if ((tid & 31) == 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // S, dP column halves
+        constexpr uint32_t idesc_kv = umma_idesc_bf16(128, DP, 1, 1);   // dV, dK: A = P/dS seen MN-major, B = dO/Q MN-major
+        constexpr uint32_t idesc_q = umma_idesc_bf16(128, DP, 0, 1);    // dQ: A = dS K-major, B = K MN-major
+        auto bar = [&](uint32_t i) { return reinterpret_cast<uint64_t*>(smem + 12 * TILE) + i; };
+        const int nk_qk = (p.hs + 15) / 16;
+        // S and dP of pair a, 64 key/value columns (half hh) at a time; each half has its own TMEM tile and barriers,
+        // so the math warps release a tile after a single 16-column read
+        auto issue_sdp = [&](const AbIter& a) {
+          const int sl = slot(a, a.i), st = a.ks & 1;
+          // first pair of the head that touches query tile i: (s = 0, j = 0, i)
+          if (a.s == 0 && a.j == 0) mbar_wait_a(bb + 8 * (AB_Q_FULL + sl), slot_use(a) & 1);
+          if (a.first_i()) mbar_wait_a(bb + 8 * (AB_KV_FULL + st), (a.ks >> 1) & 1);
+          const uint32_t aQ = sQ + sl * TILE, aO = sdO + sl * TILE, aK = sKV + st * 2 * TILE, aV = aK + TILE;
+          for (int hh = 0; hh < 2; ++hh) {
+            mbar_wait_a(bb + 8 * (AB_S_EMPTY + hh), (a.n & 1) ^ 1);
+            tc_fence_after();
+            for (int kk = 0; kk < nk_qk; ++kk)
+              umma_bf16(tmem_base + hh * 64, umma_desc_sw128(aQ + kk * 32, 16, 1024),
+                        umma_desc_sw128(aK + hh * 8192 + kk * 32, 16, 1024), idesc_s, kk != 0);
+            umma_commit(bar(AB_S_FULL + hh));
+            mbar_wait_a(bb + 8 * (AB_DP_EMPTY + hh), (a.n & 1) ^ 1);
+            tc_fence_after();
+            for (int kk = 0; kk < nk_qk; ++kk)
+              umma_bf16(tmem_base + 128 + hh * 64, umma_desc_sw128(aO + kk * 32, 16, 1024),
+                        umma_desc_sw128(aV + hh * 8192 + kk * 32, 16, 1024), idesc_s, kk != 0);
+            umma_commit(bar(AB_DP_FULL + hh));
+          }
+        };
+        auto issue_grads = [&](const AbIter& a) {
+          const int st = a.ks & 1, sl = slot(a, a.i);
+          mbar_wait_a(bb + 8 * AB_PDS_FULL, a.n & 1);
+          if (a.first_i()) mbar_wait_a(bb + 8 * AB_DKV_EMPTY, (a.ks & 1) ^ 1);        // dV/dK of the previous tile were read out
+          if (a.first_of_head()) mbar_wait_a(bb + 8 * AB_DQ_EMPTY, (a.hc & 1) ^ 1);   // dQ of the previous head was read out
+          tc_fence_after();
+          const uint32_t aQ = sQ + sl * TILE, aO = sdO + sl * TILE, aK = sKV + st * 2 * TILE;
+          for (int kk = 0; kk < 8; ++kk)     // dV_j += P^T dO_i
+            umma_bf16(tmem_base + 256, umma_desc_sw128(sP + kk * 2048, TILE, 1024), umma_desc_sw128(aO + kk * 2048, TILE, 1024),
+                      idesc_kv, !a.first_i() || kk != 0);
+          for (int kk = 0; kk < 8; ++kk)     // dK_j += dS^T Q_i
+            umma_bf16(tmem_base + 320, umma_desc_sw128(sdS + kk * 2048, TILE, 1024), umma_desc_sw128(aQ + kk * 2048, TILE, 1024),
+                      idesc_kv, !a.first_i() || kk != 0);
+          for (int kk = 0; kk < 8; ++kk)     // dQ_i += dS K_j
+            umma_bf16(tmem_base + 384 + 64 * a.i, umma_desc_sw128(sdS + (kk >> 2) * TILE + (kk & 3) * 32, 16, 1024),
+                      umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, !(a.s == 0 && a.j == 0) || kk != 0);
+          umma_commit(bar(AB_G_DONE));
+          if (a.i == n_qt - 1) umma_commit(bar(AB_KV_EMPTY + st));                    // last pair of this key/value tile
+          if (a.s == n_src - 1 && a.j == a.i) umma_commit(bar(AB_Q_EMPTY + sl));      // last pair that reads query tile i
+        };
+        if (it.work < total) issue_sdp(it);
+        while (it.work < total) {
+          AbIter nx = it;
+          nx.next(n_qt, n_src, stride);
+          // S / dP of the next pair go out as soon as the math warps have emptied the TMEM tiles, before this pair's
+          // gradient UMMAs. The smem slots they read are guarded by their own barriers, and a slot of the NEXT head
+          // is always released by gradient UMMAs issued earlier (query tile 0 two pairs before the end of a two-tile
+          // head, the other slot of a one-tile head a whole head earlier), so running ahead cannot deadlock.
+          if (nx.work < total) issue_sdp(nx);
+          issue_grads(it);
+          it = nx;
         }
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ================================================================== math warps
-    const int r = tid & 127;          // row of the 128 x 128 pair tile (query row inside its tile / key row for dK, dV)
-    const int half = tid >> 7;        // column half of the pair tile this thread handles
-    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    mbar_wait(&bar_q, 0);
-    int pc = 0, g_seen = 0;
-    for (int s = 0; s < p.n_src; ++s) {
-      // D[row] = rowsum(dO * O_src): half 0 serves query tile 0, half 1 query tile 1, results shared through smem
-      mbar_wait(&bar_o, s & 1);
-      if (half < n_qt) {
-        const int row = half * 128 + r;
-        float acc = 0.f;
-        if (row < p.T) {
-          const uint8_t* orow = sP + half * TILE + r * 128;
-          const uint8_t* drow = sdO + half * TILE + r * 128;
-          for (int c = 0; c < p.hs / 8; ++c) {
-            const uint4 a = *reinterpret_cast<const uint4*>(drow + ((c ^ (r & 7)) << 4));
-            const uint4 o4 = *reinterpret_cast<const uint4*>(orow + ((c ^ (r & 7)) << 4));
-            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&o4);
+    const int r = tid & 127, qd = tid >> 7, wq = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    // deferred read-outs, packed: bit 0 dK/dV pending, bit 1 dQ pending, bit 2/3 their g_done parities,
+    // bit 4 key/value tile j, bits 5-8 source s, bit 9/10 "belongs to the previous head"
+    uint32_t pend = 0;
+    int g = 0, b = 0, h = 0;       // current head
+    int pg = 0, pb = 0, ph = 0;    // previous head (for read-outs that cross the head boundary)
+    // RC columns at a time keep the read-outs' register footprint small (they run between the two column halves of
+    // a pair, and any spill goes to L2: the L1 is all shared memory here)
+    constexpr int RC = OC < 16 ? OC : 16;
+    auto read_store = [&](uint32_t taddr, __nv_bfloat16* dst, int col0, float mul, bool do_ld, bool do_st) {
+#pragma unroll
+      for (int c = 0; c < OC; c += RC) {
+        uint32_t v[RC];
+        if (do_ld) {
+          tmem_ld_cols<RC>(taddr + col0 + c, v);
+          tmem_wait_ld();
+        }
+        if (do_st) {
+#pragma unroll
+          for (int e = 0; e < RC; e += 8) {
+            if (col0 + c + e < p.hs) {
+              uint4 u;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                h2[q] = __floats2bfloat162_rn(__uint_as_float(v[e + 2 * q]) * mul, __uint_as_float(v[e + 2 * q + 1]) * mul);
+              *reinterpret_cast<uint4*>(dst + col0 + c + e) = u;
+            }
+          }
+        }
+      }
+    };
+    // dV_j (quarters 0, 1) / dK_j (quarters 2, 3) of the key/value tile recorded in `pend`
+    auto readout_kv = [&]() {
+      mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 2) & 1);
+      tc_fence_after();
+      const bool is_k = qd >= 2;
+      const bool prev = (pend >> 9) & 1;
+      const int gg = prev ? pg : g, bq = prev ? pb : b, hq = prev ? ph : h;
+      const int kvrow = ((pend >> 4) & 1) * 128 + r, ps = (pend >> 5) & 15;
+      const GradOut& go = is_k ? p.dk[ps] : p.dv[ps];
+      read_store(tmem_base + (is_k ? 320 : 256) + lane_off,
+                 go.ptr + (long long)gg * go.gs + ((long long)bq * p.T + kvrow) * go.ld + hq * go.head_stride, (qd & 1) * OC,
+                 is_k ? p.scale : 1.f, true, kvrow < p.T);
+      tc_fence_before();
+      mbar_arrive_a(bb + 8 * AB_DKV_EMPTY);
+      pend &= ~0x3f5u;   // clear bits 0, 2, 4-9
+    };
+    // dQ_0 (quarters 0, 1) / dQ_1 (quarters 2, 3) of the head recorded in `pend`
+    auto readout_q = [&]() {
+      mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 3) & 1);
+      tc_fence_after();
+      const int ti = qd >> 1;
+      const bool prev = (pend >> 10) & 1;
+      const int gg = prev ? pg : g, bq = prev ? pb : b, hq = prev ? ph : h;
+      const int row = ti * 128 + r;
+      read_store(tmem_base + 384 + 64 * ti + lane_off,
+                 p.dq.ptr + (long long)gg * p.dq.gs + ((long long)bq * p.T + row) * p.dq.ld + hq * p.dq.head_stride, (qd & 1) * OC,
+                 p.scale, ti < n_qt, ti < n_qt && row < p.T);
+      tc_fence_before();
+      mbar_arrive_a(bb + 8 * AB_DQ_EMPTY);
+      pend &= ~0x40au;   // clear bits 1, 3, 10
+    };
+    // per-thread piece of the D / lse prologue: row tid >> 1, 16-byte vectors 2v + (tid & 1) of the head's hs columns
+    const int drow = tid >> 1, dpart = tid & 1, nvec = p.hs >> 3;
+
+    for (; it.work < total; it.next(n_qt, n_src, stride)) {
+      if (it.first_of_head()) {
+        pg = g; pb = b; ph = h;
+        {
+          int w = it.work;
+          h = w % p.H; w /= p.H;
+          b = w % p.B;
+          g = w / p.B;
+        }
+        if (pend & 1) pend |= 1u << 9;
+        if (pend & 2) pend |= 1u << 10;
+        // D[s][row] = rowsum(dO * O_s) and lse * log2(e) for the whole head, straight from global memory (two threads
+        // per row). The NEXT head's inputs are prefetched into L2 here, a whole head ahead of their use.
+        named_bar_sync(5, AB_MATH_THREADS);     // sD / sLse of the previous head are no longer read
+        const bool rok = drow < p.T;
+        const long long roff = ((long long)b * p.T + drow) * p.ldo + h * p.hs;
+        if (it.work + stride < total && rok && dpart == 0) {
+          int w = it.work + stride;
+          const int h2 = w % p.H; w /= p.H;
+          const int b2 = w % p.B;
+          const int g2 = w / p.B;
+          const long long roff2 = ((long long)b2 * p.T + drow) * p.ldo + h2 * p.hs;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_o + (long long)g2 * p.o_gs + roff2));
+          for (int s = 0; s < n_src; ++s) {
+            const __nv_bfloat16* ob = p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o + (long long)g2 * p.o_gs;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ob + roff2));
+          }
+        }
+        if (pend & 1) readout_kv();
+        if (pend & 2) readout_q();
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 dvv[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          dvv[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(p.d_o + (long long)g * p.o_gs + roff + (2 * v + dpart) * 8) : z4;
+        for (int s = 0; s < n_src; ++s) {
+          const __nv_bfloat16* ob = p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o + (long long)g * p.o_gs;
+          uint4 ov[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            ov[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(ob + roff + (2 * v + dpart) * 8) : z4;
+          const float lv = (rok && dpart == 0) ? p.lse[((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T + drow] : 0.f;
+          float acc = 0.f;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&dvv[v]);
+            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov[v]);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               acc += __low2float(ah[e]) * __low2float(oh[e]) + __high2float(ah[e]) * __high2float(oh[e]);
           }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          if (dpart == 0) {
+            sts_f32(sD + (s * 256 + drow) * 4, acc);
+            sts_f32(sLse + (s * 256 + drow) * 4, lv * 1.4426950408889634f);
+          }
         }
-        sD[half * 128 + r] = acc;
+        named_bar_sync(5, AB_MATH_THREADS);
       }
-      // named barrier over the 256 math threads only (the issuer warp never joins)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float D0 = sD[r], D1 = n_qt > 1 ? sD[128 + r] : 0.f;
-      const float* lse_s = p.lse + ((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T;
-      const float L0 = r < p.T ? lse_s[r] * 1.4426950408889634f : 0.f;
-      const float L1 = (n_qt > 1 && 128 + r < p.T) ? lse_s[128 + r] * 1.4426950408889634f : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // sD is rewritten by the next source only after everyone has read it
-      mbar_arrive(&bar_od);
-      for (int j = 0; j < n_qt; ++j) {
-        const int kv0 = j * 128;
-        for (int i = j; i < n_qt; ++i, ++pc) {
-          const int row = i * 128 + r;
-          const bool row_ok = row < p.T;
-          const float Dr = i == 0 ? D0 : D1, Lr = i == 0 ? L0 : L1;
-          mbar_wait(&bar_sp, pc & 1);
-          for (; g_seen < pc; ++g_seen) mbar_wait(&bar_g, g_seen & 1);   // complete by construction; keeps the phase in step
-          tc_fence_after();
-          uint32_t pp[32], dd[32];    // this thread's 64 columns of P and dS, packed bf16x2
+      const int row = it.i * 128 + r;
+      const bool diag = it.i == it.j;
+      const float Lr = lds_f32(sLse + (it.s * 256 + row) * 4);
+      const float Dr = lds_f32(sD + (it.s * 256 + row) * 4);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int col0 = kv0 + half * 64 + c * 32;
-            // warp-uniform skip of chunks that are entirely above the diagonal for this warp's 32 rows
-            if (col0 <= i * 128 + (warp & 3) * 32 + 31) {
-              uint32_t sv[32], dv[32];
-              tmem_ld_32x32(tm_S + lane_off + half * 64 + c * 32, sv);
-              tmem_ld_32x32(tm_dP + lane_off + half * 64 + c * 32, dv);
-              tmem_wait_ld();
-#pragma unroll
-              for (int e = 0; e < 32; e += 2) {
-                float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-                if (row_ok && col0 + e <= row) {
-                  p0 = exp2f(__uint_as_float(sv[e]) * p.scale_log2 - Lr);
-                  d0 = p0 * (__uint_as_float(dv[e]) - Dr) * p.scale;
-                }
-                if (row_ok && col0 + e + 1 <= row) {
-                  p1 = exp2f(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
-                  d1 = p1 * (__uint_as_float(dv[e + 1]) - Dr) * p.scale;
-                }
-                __nv_bfloat162 ph = __floats2bfloat162_rn(p0, p1), dh = __floats2bfloat162_rn(d0, d1);
-                pp[c * 16 + e / 2] = *reinterpret_cast<uint32_t*>(&ph);
-                dd[c * 16 + e / 2] = *reinterpret_cast<uint32_t*>(&dh);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) pp[c * 16 + e] = dd[c * 16 + e] = 0u;
-            }
-          }
-          // the gradient UMMAs of the previous pair (and, for the first pair of a source, the D pass) are done with sP/sdS:
-          // the issuer waits on bar_g before it issues this pair's S/dP, so bar_sp above already implies it.
-          const int off = half * TILE + r * 128;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int lc = q ^ (r & 7);
-            *reinterpret_cast<uint4*>(sP + off + (lc << 4)) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
-            *reinterpret_cast<uint4*>(sdS + off + (lc << 4)) = make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]);
-          }
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(&bar_pr);
-        }
-        // dV_j (half 0) and dK_j (half 1) of this source are complete after the last pair's gradient UMMAs
-        for (; g_seen < pc; ++g_seen) mbar_wait(&bar_g, g_seen & 1);   // phases must be consumed one by one
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col_base = it.j * 128 + hh * 64 + qd * 16;
+        // these 16 columns are needed unless they lie above the diagonal for every row of the warp (warp-uniform)
+        const bool need = !diag || col_base <= it.i * 128 + wq * 32 + 31;
+        int nvalid = !diag ? 16 : (row - col_base + 1 < 0 ? 0 : (row - col_base + 1 > 16 ? 16 : row - col_base + 1));
+        if (row >= p.T) nvalid = 0;
+        uint32_t pp[8], dd[8];     // 16 columns of P and dS, packed bf16x2
+        mbar_wait_a(bb + 8 * (AB_S_FULL + hh), it.n & 1);
+        mbar_wait_a(bb + 8 * (AB_DP_FULL + hh), it.n & 1);   // issued right behind S: no register is held across a wait
         tc_fence_after();
-        {
-          const int kvrow = kv0 + r;
-          const GradOut& go = half == 0 ? p.dv[s] : p.dk[s];
-          const uint32_t src = (half == 0 ? tm_dV : tm_dK) + lane_off;
-          float val[DP];
-#pragma unroll
-          for (int c = 0; c < DP / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x16(src + c * 16, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) val[c * 16 + e] = __uint_as_float(v[e]);
-          }
-          if (kvrow < p.T)
-            store_row_bf16<DP>(go.ptr + (long long)g * go.gs + ((long long)b * p.T + kvrow) * go.ld + h * go.head_stride, val, p.hs);
+        if (need) {
+          uint32_t sv[16], dv[16];
+          tmem_ld_32x16(tmem_base + hh * 64 + lane_off + qd * 16, sv);
+          tmem_ld_32x16(tmem_base + 128 + hh * 64 + lane_off + qd * 16, dv);
+          tmem_wait_ld();
           tc_fence_before();
+          mbar_arrive_a(bb + 8 * (AB_S_EMPTY + hh));
+          mbar_arrive_a(bb + 8 * (AB_DP_EMPTY + hh));
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            float p0 = ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - Lr);
+            float p1 = ex2_approx(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
+            p0 = e < nvalid ? p0 : 0.f;
+            p1 = e + 1 < nvalid ? p1 : 0.f;
+            const float d0 = p0 * (__uint_as_float(dv[e]) - Dr), d1 = p1 * (__uint_as_float(dv[e + 1]) - Dr);
+            __nv_bfloat162 pv = __floats2bfloat162_rn(p0, p1), dh = __floats2bfloat162_rn(d0, d1);
+            pp[e / 2] = *reinterpret_cast<uint32_t*>(&pv);
+            dd[e / 2] = *reinterpret_cast<uint32_t*>(&dh);
+          }
+        } else {
+          tc_fence_before();
+          mbar_arrive_a(bb + 8 * (AB_S_EMPTY + hh));
+          mbar_arrive_a(bb + 8 * (AB_DP_EMPTY + hh));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pp[e] = dd[e] = 0u;
+        }
+        // P/dS smem is free once the gradient UMMAs of the previous pair are complete (they had the math above to run)
+        if (hh == 0) mbar_wait_a(bb + 8 * AB_G_DONE, (it.n & 1) ^ 1);
+        const uint32_t off = hh * TILE + r * 128;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t lc = ((qd * 2 + q) ^ (r & 7)) << 4;
+          sts128(sP + off + lc, make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]));
+          sts128(sdS + off + lc, make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]));
+        }
+        if (hh == 0) {
+          // deferred read-outs of the previous key/value tile / head (their last gradient UMMAs are the ones waited
+          // for above); placed here because no P/dS registers are live between the two column halves
+          if (pend & 1) readout_kv();
+          if (pend & 2) readout_q();
         }
       }
+      fence_proxy_async_smem();
+      mbar_arrive_a(bb + 8 * AB_PDS_FULL);
+      if (it.i == n_qt - 1)   // last pair of this key/value tile: dK/dV read-out after the next pair's math
+        pend = (pend & ~0x3f4u) | 1u | ((it.n & 1u) << 2) | ((uint32_t)it.j << 4) | ((uint32_t)it.s << 5);
+      if (it.i == n_qt - 1 && it.j == n_qt - 1 && it.s == n_src - 1)   // last pair of the head
+        pend = (pend & ~0x408u) | 2u | ((it.n & 1u) << 3);
     }
-    // dQ tiles: half 0 stores tile 0, half 1 tile 1 (all gradient UMMAs have completed: bar_g of the last pair was waited)
-    if (half < n_qt) {
-      const int row = half * 128 + r;
-      float val[DP];
-#pragma unroll
-      for (int c = 0; c < DP / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(tm_dQ + 64 * half + lane_off + c * 16, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) val[c * 16 + e] = __uint_as_float(v[e]);
-      }
-      if (row < p.T)
-        store_row_bf16<DP>(p.dq.ptr + (long long)g * p.dq.gs + ((long long)b * p.T + row) * p.dq.ld + h * p.dq.head_stride, val, p.hs);
-    }
+    if (pend & 1) readout_kv();
+    if (pend & 2) readout_q();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == AB_MATH_WARPS + 1) tmem_dealloc(tmem_base, 512);
 }
 
 template <int DP>
 static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t st) {
-  constexpr int SMEM = 12 * 16384 + 80 + 1024;
+  constexpr int SMEM = 12 * AB_TILE + AB_NBARS * 8 + 16 + 2 * ATTB_MAX_SRC * 256 * 4 + 64;
   static bool attr = false;
   if (!attr) {
     TA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
-  const long long grid = (long long)p.H * p.B * p.G;
-  TA_CHECK_ARG(grid < (1ll << 31), "attention grid too large");
-  attn_bwd_kernel<DP><<<(unsigned)grid, ATTB_THREADS, SMEM, st>>>(maps, p);
+  const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
+  attn_bwd_kernel<DP><<<grid, AB_THREADS, SMEM, st>>>(maps, p);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -358,16 +468,7 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
   if (make_head_map(&maps.q, q, hs, H, T, B, G, 128)) return 1;
   ta_attn_tensor dot{do_bf16, ldo, hs, o_gs};
   if (make_head_map(&maps.d_o, &dot, hs, H, T, B, G, 128)) return 1;
-  // O tiles for D = rowsum(dO * O_src): self-attention reads o (group dim = modality); cross-attention (G == 1) reads
-  // the per-source outputs, with the source index in the group dim of the tensor map
   TA_CHECK_ARG(n_src == 1 || G == 1, "ta_attention_bwd: n_src > 1 requires G == 1");
-  if (n_src > 1) {
-    ta_attn_tensor ot{o_src_bf16, ldo, hs, o_src_stride};
-    if (make_head_map(&maps.o, &ot, hs, H, T, B, n_src, 128)) return 1;
-  } else {
-    ta_attn_tensor ot{o_bf16, ldo, hs, o_gs};
-    if (make_head_map(&maps.o, &ot, hs, H, T, B, G, 128)) return 1;
-  }
   AttnBwdParams p{};
   for (int s = 0; s < n_src; ++s) {
     if (make_head_map(&maps.k[s], &k[s], hs, H, T, B, G, 128)) return 1;
@@ -378,6 +479,10 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
   p.T = T; p.B = B; p.H = H; p.G = G; p.hs = hs; p.n_src = n_src; p.n_qt = (T + 127) / 128;
   p.scale = (float)(1.0 / sqrt((double)hs));
   p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)hs));
+  const long long total = (long long)G * B * H;
+  TA_CHECK_ARG(total < (1ll << 31), "attention grid too large");
+  p.total_work = (int)total;
+  p.d_o = (const __nv_bfloat16*)do_bf16;
   p.o = (const __nv_bfloat16*)o_bf16;
   p.o_src = n_src > 1 ? (const __nv_bfloat16*)o_src_bf16 : nullptr;
   p.ldo = ldo; p.o_gs = o_gs; p.o_src_stride = o_src_stride;
