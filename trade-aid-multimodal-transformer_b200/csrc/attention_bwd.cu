@@ -19,6 +19,7 @@
 // The previous version ran S/dP -> math -> gradient UMMAs strictly one after another in a 9-warp CTA (tensor pipe 8%
 // active, 43% of the samples waiting on mbarriers: profiles/r01_ncu_attn_v2.txt).
 #include <cmath>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "../../include/tradeaid_b200.h"
@@ -34,6 +35,9 @@ struct AttnBwdMaps {
   CUtensorMap q, d_o;
   CUtensorMap k[ATTB_MAX_SRC];
   CUtensorMap v[ATTB_MAX_SRC];
+  CUtensorMap dq;                  // TMA store targets (same head geometry as q / k / v)
+  CUtensorMap dk[ATTB_MAX_SRC];
+  CUtensorMap dv[ATTB_MAX_SRC];
 };
 
 struct GradOut {
@@ -43,6 +47,8 @@ struct GradOut {
 
 struct AttnBwdParams {
   int T, B, H, G, hs, n_src, n_qt, total_work;
+  long long* trace;   // TA_ATTN_TRACE=<device address> (dev only): clock64 stamps of CTA 0, 4 roles x 1024 slots
+  int debug;   // TA_ATTN_DEBUG (dev only): 1 = no D/lse prologue loads, 2 = no read-out stores, 4 = no P/dS math
   float scale, scale_log2;
   const __nv_bfloat16* d_o;    // [G][B*T][ldo]
   const __nv_bfloat16* o;      // [G][B*T][ldo]
@@ -54,9 +60,19 @@ struct AttnBwdParams {
   GradOut dv[ATTB_MAX_SRC];
 };
 
+// dev-only timeline: role 0 loader, 1 S/dP issuer, 2 math (warp 0), 3 gradient issuer; slot = running event index
+#define AB_TRACE(role, cnt, tag)                                                                     \
+  do {                                                                                               \
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (cnt) < 1024) {                     \
+      p.trace[(role) * 1024 + (cnt)] = (clock64() << 8) | (tag);                                     \
+      ++(cnt);                                                                                       \
+    }                                                                                                \
+  } while (0)
+
 constexpr int AB_MATH_WARPS = 16;
 constexpr int AB_MATH_THREADS = AB_MATH_WARPS * 32;
-constexpr int AB_THREADS = (AB_MATH_WARPS + 4) * 32;   // warps 0-15 math, 16 loader, 17 issuer, 18-19 idle (setmaxnreg)
+// warps 0-15 math, 16 loader, 17 S/dP issuer, 18 gradient issuer, 19 storer (TMA stores of dK/dV/dQ)
+constexpr int AB_THREADS = (AB_MATH_WARPS + 4) * 32;
 constexpr int AB_TILE = 16384;                          // 128 rows x 128 B
 
 // The (work, s, j, i) pair schedule; every warp role walks the same sequence with its own copy.
@@ -81,7 +97,8 @@ struct AbIter {
 // barrier table (index * 8 bytes from the table base)
 enum : uint32_t {
   AB_Q_FULL = 0, AB_Q_EMPTY = 2, AB_KV_FULL = 4, AB_KV_EMPTY = 6, AB_S_FULL = 8, AB_DP_FULL = 10, AB_S_EMPTY = 12,
-  AB_DP_EMPTY = 14, AB_PDS_FULL = 16, AB_G_DONE = 17, AB_DKV_EMPTY = 18, AB_DQ_EMPTY = 19, AB_NBARS = 20
+  AB_DP_EMPTY = 14, AB_PDS_FULL = 16, AB_G_DONE = 17, AB_DKV_EMPTY = 18, AB_DQ_EMPTY = 19,
+  AB_SKV_FULL = 20, AB_SKV_FREE = 21, AB_SQ_FULL = 22, AB_SQ_FREE = 23, AB_NBARS = 24
 };
 
 template <int DP>
@@ -91,6 +108,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   constexpr int OC = DP / 2;   // gradient columns per math thread at read-out
   extern __shared__ __align__(1024) uint8_t smem[];
   // [Q 2 slots][dO 2 slots][2 stages x (K, V)][P: 2 column halves][dS: 2 column halves][barriers][D][lse]
+  // The P/dS halves double as the staging tiles of the gradient read-outs (TMA stores): dV -> P half 1, dK -> dS
+  // half 1 (free between the two column halves of a pair), dQ_0 -> P half 0, dQ_1 -> dS half 0 (head boundary only).
   const uint32_t sQ = smem_u32(smem), sdO = sQ + 2 * TILE, sKV = sQ + 4 * TILE, sP = sQ + 8 * TILE, sdS = sQ + 10 * TILE;
   const uint32_t bb = sQ + 12 * TILE;                        // barrier i at bb + 8 * i
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + 12 * TILE + AB_NBARS * 8);
@@ -102,7 +121,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   if (tid == 0) {
     for (uint32_t x = 0; x < AB_NBARS; ++x) {
       const bool wide = x == AB_S_EMPTY || x == AB_S_EMPTY + 1 || x == AB_DP_EMPTY || x == AB_DP_EMPTY + 1 ||
-                        x == AB_PDS_FULL || x == AB_DKV_EMPTY || x == AB_DQ_EMPTY;
+                        x == AB_PDS_FULL || x == AB_DKV_EMPTY || x == AB_DQ_EMPTY || x == AB_SKV_FULL || x == AB_SQ_FULL;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bb + 8 * x), "r"(wide ? AB_MATH_THREADS : 1));
     }
     fence_mbar_init();
@@ -122,16 +141,18 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   // Q/dO smem slot of query tile ti: two tiles per head use slot = tile, one tile per head alternates between heads
   auto slot = [&](const AbIter& a, int ti) { return n_qt == 2 ? ti : (a.hc & 1); };
   auto slot_use = [&](const AbIter& a) { return n_qt == 2 ? a.hc : (a.hc >> 1); };
+  auto bar = [&](uint32_t i) { return reinterpret_cast<uint64_t*>(smem + 12 * TILE) + i; };
 
   if (warp >= AB_MATH_WARPS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == AB_MATH_WARPS) {
       // ================================================================== loader (one lane)
       if ((tid & 31) == 0) {
-        auto bar = [&](uint32_t i) { return reinterpret_cast<uint64_t*>(smem + 12 * TILE) + i; };
+        int tc = 0;
         auto load_kv = [&](const AbIter& a, int h, int b, int g) {
           const int st = a.ks & 1;
           mbar_wait_a(bb + 8 * (AB_KV_EMPTY + st), ((a.ks >> 1) & 1) ^ 1);
+          AB_TRACE(0, tc, 1);
           mbar_expect_tx(bar(AB_KV_FULL + st), 2 * TILE);
           uint8_t* dK = smem + 4 * TILE + st * 2 * TILE;
           tma_load_5d(dK, &maps.k[a.s], bar(AB_KV_FULL + st), 0, h, a.j * 128, b, g);
@@ -149,6 +170,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
             for (int i = 0; i < n_qt; ++i) {
               const int sl = slot(it, i);
               mbar_wait_a(bb + 8 * (AB_Q_EMPTY + sl), (slot_use(it) & 1) ^ 1);
+              AB_TRACE(0, tc, 2 + sl);
               mbar_expect_tx(bar(AB_Q_FULL + sl), 2 * TILE);
               tma_load_5d(smem + sl * TILE, &maps.q, bar(AB_Q_FULL + sl), 0, h, i * 128, b, g);
               tma_load_5d(smem + 2 * TILE + sl * TILE, &maps.d_o, bar(AB_Q_FULL + sl), 0, h, i * 128, b, g);
@@ -159,68 +181,108 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
           }
         }
       }
-    } else if (warp == AB_MATH_WARPS + 1) {
-      // ================================================================== UMMA issuer (one lane)
+    } else if (warp == AB_MATH_WARPS + 3) {
+      // ================================================================== storer (one lane): TMA stores of the read-outs
       if ((tid & 31) == 0) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // S, dP column halves
-        constexpr uint32_t idesc_kv = umma_idesc_bf16(128, DP, 1, 1);   // dV, dK: A = P/dS seen MN-major, B = dO/Q MN-major
-        constexpr uint32_t idesc_q = umma_idesc_bf16(128, DP, 0, 1);    // dQ: A = dS K-major, B = K MN-major
-        auto bar = [&](uint32_t i) { return reinterpret_cast<uint64_t*>(smem + 12 * TILE) + i; };
+        int ekv = 0, eq = 0;
+        for (; it.work < total; it.next(n_qt, n_src, stride)) {
+          if (it.i != n_qt - 1) continue;
+          int w = it.work;
+          const int h = w % p.H; w /= p.H;
+          const int b = w % p.B;
+          const int g = w / p.B;
+          // dV_j, dK_j of the key/value tile whose last pair this is
+          mbar_wait_a(bb + 8 * AB_SKV_FULL, ekv & 1);
+          if (!(p.debug & 2)) {
+            tma_store_5d(&maps.dv[it.s], sP + TILE, 0, h, it.j * 128, b, g);
+            tma_store_5d(&maps.dk[it.s], sdS + TILE, 0, h, it.j * 128, b, g);
+          }
+          bulk_commit_group();
+          bulk_wait_read<0>();
+          mbar_arrive_a(bb + 8 * AB_SKV_FREE);
+          ++ekv;
+          if (it.j == n_qt - 1 && it.s == n_src - 1) {   // last pair of the head: dQ tiles
+            mbar_wait_a(bb + 8 * AB_SQ_FULL, eq & 1);
+            if (!(p.debug & 2)) {
+              tma_store_5d(&maps.dq, sP, 0, h, 0, b, g);
+              if (n_qt > 1) tma_store_5d(&maps.dq, sdS, 0, h, 128, b, g);
+            }
+            bulk_commit_group();
+            bulk_wait_read<0>();
+            mbar_arrive_a(bb + 8 * AB_SQ_FREE);
+            ++eq;
+          }
+        }
+        bulk_wait_all<0>();
+      }
+    } else {
+      // ================================================================== UMMA issuers (whole warp, one elected lane issues)
+      // warp 17: S = Q K^T and dP = dO V^T of every pair, as early as the math warps free the TMEM tiles
+      // warp 18: the three gradient UMMAs of every pair, as soon as P / dS are in smem
+      // Two warps because issuing costs ~50 cycles per tcgen05.mma here: one warp serialised 40 of them per pair
+      // (2000 cycles, longer than the tensor pipe needs to execute them).
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // S, dP column halves
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, DP, 1, 1);   // dV, dK: A = P/dS seen MN-major, B = dO/Q MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, DP, 0, 1);    // dQ: A = dS K-major, B = K MN-major
+      // descriptors advance by adding (bytes >> 4) to the low word: the address field sits in bits [0, 14)
+      const uint64_t d_k = umma_desc_sw128(0, 16, 1024);       // K-major operand, 128-byte rows
+      const uint64_t d_mn = umma_desc_sw128(0, TILE, 1024);    // MN-major view of a 128 x 128 B tile
+      auto dk = [&](uint32_t addr) { return d_k + ((addr & 0x3FFFF) >> 4); };
+      auto dmn = [&](uint32_t addr) { return d_mn + ((addr & 0x3FFFF) >> 4); };
+      int tc = 0;
+      if (warp == AB_MATH_WARPS + 1) {
         const int nk_qk = (p.hs + 15) / 16;
-        // S and dP of pair a, 64 key/value columns (half hh) at a time; each half has its own TMEM tile and barriers,
-        // so the math warps release a tile after a single 16-column read
-        auto issue_sdp = [&](const AbIter& a) {
+        for (; it.work < total; it.next(n_qt, n_src, stride)) {
+          const AbIter& a = it;
           const int sl = slot(a, a.i), st = a.ks & 1;
           // first pair of the head that touches query tile i: (s = 0, j = 0, i)
           if (a.s == 0 && a.j == 0) mbar_wait_a(bb + 8 * (AB_Q_FULL + sl), slot_use(a) & 1);
           if (a.first_i()) mbar_wait_a(bb + 8 * (AB_KV_FULL + st), (a.ks >> 1) & 1);
-          const uint32_t aQ = sQ + sl * TILE, aO = sdO + sl * TILE, aK = sKV + st * 2 * TILE, aV = aK + TILE;
+          AB_TRACE(1, tc, 1);   // operands of S/dP in smem
+          const uint64_t aQ = dk(sQ + sl * TILE), aO = dk(sdO + sl * TILE), aK = dk(sKV + st * 2 * TILE), aV = dk(sKV + st * 2 * TILE + TILE);
+          // 64 key/value columns (half hh) at a time; each half has its own TMEM tile and barriers, so the math warps
+          // release a tile after a single 16-column read
+#pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             mbar_wait_a(bb + 8 * (AB_S_EMPTY + hh), (a.n & 1) ^ 1);
             tc_fence_after();
             for (int kk = 0; kk < nk_qk; ++kk)
-              umma_bf16(tmem_base + hh * 64, umma_desc_sw128(aQ + kk * 32, 16, 1024),
-                        umma_desc_sw128(aK + hh * 8192 + kk * 32, 16, 1024), idesc_s, kk != 0);
-            umma_commit(bar(AB_S_FULL + hh));
+              umma_bf16_ws(tmem_base + hh * 64, aQ + kk * 2, aK + hh * 512 + kk * 2, idesc_s, kk != 0);
+            umma_commit_ws(bb + 8 * (AB_S_FULL + hh));
             mbar_wait_a(bb + 8 * (AB_DP_EMPTY + hh), (a.n & 1) ^ 1);
             tc_fence_after();
             for (int kk = 0; kk < nk_qk; ++kk)
-              umma_bf16(tmem_base + 128 + hh * 64, umma_desc_sw128(aO + kk * 32, 16, 1024),
-                        umma_desc_sw128(aV + hh * 8192 + kk * 32, 16, 1024), idesc_s, kk != 0);
-            umma_commit(bar(AB_DP_FULL + hh));
+              umma_bf16_ws(tmem_base + 128 + hh * 64, aO + kk * 2, aV + hh * 512 + kk * 2, idesc_s, kk != 0);
+            umma_commit_ws(bb + 8 * (AB_DP_FULL + hh));
+            AB_TRACE(1, tc, 2 + hh);   // S/dP half issued
           }
-        };
-        auto issue_grads = [&](const AbIter& a) {
+        }
+      } else {
+        for (; it.work < total; it.next(n_qt, n_src, stride)) {
+          const AbIter& a = it;
           const int st = a.ks & 1, sl = slot(a, a.i);
           mbar_wait_a(bb + 8 * AB_PDS_FULL, a.n & 1);
           if (a.first_i()) mbar_wait_a(bb + 8 * AB_DKV_EMPTY, (a.ks & 1) ^ 1);        // dV/dK of the previous tile were read out
           if (a.first_of_head()) mbar_wait_a(bb + 8 * AB_DQ_EMPTY, (a.hc & 1) ^ 1);   // dQ of the previous head was read out
           tc_fence_after();
-          const uint32_t aQ = sQ + sl * TILE, aO = sdO + sl * TILE, aK = sKV + st * 2 * TILE;
-          for (int kk = 0; kk < 8; ++kk)     // dV_j += P^T dO_i
-            umma_bf16(tmem_base + 256, umma_desc_sw128(sP + kk * 2048, TILE, 1024), umma_desc_sw128(aO + kk * 2048, TILE, 1024),
-                      idesc_kv, !a.first_i() || kk != 0);
+          AB_TRACE(3, tc, 4);   // pds_full seen
+          const uint64_t mQ = dmn(sQ + sl * TILE), mO = dmn(sdO + sl * TILE), mK = dmn(sKV + st * 2 * TILE);
+          const uint64_t mP = dmn(sP), mS = dmn(sdS), kS = dk(sdS);
+          const uint32_t acc_kv = a.first_i() ? 0u : 1u, acc_q = (a.s == 0 && a.j == 0) ? 0u : 1u;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)     // dV_j += P^T dO_i   (k-step = 16 query rows = 2048 B in both tiles)
+            umma_bf16_ws(tmem_base + 256, mP + kk * 128, mO + kk * 128, idesc_kv, acc_kv | (kk != 0));
+#pragma unroll
           for (int kk = 0; kk < 8; ++kk)     // dK_j += dS^T Q_i
-            umma_bf16(tmem_base + 320, umma_desc_sw128(sdS + kk * 2048, TILE, 1024), umma_desc_sw128(aQ + kk * 2048, TILE, 1024),
-                      idesc_kv, !a.first_i() || kk != 0);
-          for (int kk = 0; kk < 8; ++kk)     // dQ_i += dS K_j
-            umma_bf16(tmem_base + 384 + 64 * a.i, umma_desc_sw128(sdS + (kk >> 2) * TILE + (kk & 3) * 32, 16, 1024),
-                      umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, !(a.s == 0 && a.j == 0) || kk != 0);
-          umma_commit(bar(AB_G_DONE));
-          if (a.i == n_qt - 1) umma_commit(bar(AB_KV_EMPTY + st));                    // last pair of this key/value tile
-          if (a.s == n_src - 1 && a.j == a.i) umma_commit(bar(AB_Q_EMPTY + sl));      // last pair that reads query tile i
-        };
-        if (it.work < total) issue_sdp(it);
-        while (it.work < total) {
-          AbIter nx = it;
-          nx.next(n_qt, n_src, stride);
-          // S / dP of the next pair go out as soon as the math warps have emptied the TMEM tiles, before this pair's
-          // gradient UMMAs. The smem slots they read are guarded by their own barriers, and a slot of the NEXT head
-          // is always released by gradient UMMAs issued earlier (query tile 0 two pairs before the end of a two-tile
-          // head, the other slot of a one-tile head a whole head earlier), so running ahead cannot deadlock.
-          if (nx.work < total) issue_sdp(nx);
-          issue_grads(it);
-          it = nx;
+            umma_bf16_ws(tmem_base + 320, mS + kk * 128, mQ + kk * 128, idesc_kv, acc_kv | (kk != 0));
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)     // dQ_i += dS K_j   (A: 32 B per k-step inside a column half, halves TILE apart)
+            umma_bf16_ws(tmem_base + 384 + 64 * a.i, kS + (kk >> 2) * (TILE >> 4) + (kk & 3) * 2, mK + kk * 128, idesc_q,
+                         acc_q | (kk != 0));
+          umma_commit_ws(bb + 8 * AB_G_DONE);
+          AB_TRACE(3, tc, 5);   // grads issued
+          if (a.i == n_qt - 1) umma_commit_ws(bb + 8 * (AB_KV_EMPTY + st));                    // last pair of this key/value tile
+          if (a.s == n_src - 1 && a.j == a.i) umma_commit_ws(bb + 8 * (AB_Q_EMPTY + sl));      // last pair that reads query tile i
         }
       }
     }
@@ -230,85 +292,78 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
     const int r = tid & 127, qd = tid >> 7, wq = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     // deferred read-outs, packed: bit 0 dK/dV pending, bit 1 dQ pending, bit 2/3 their g_done parities,
-    // bit 4 key/value tile j, bits 5-8 source s, bit 9/10 "belongs to the previous head"
+    // bit 4/5 parity of the next staging event (dK/dV, dQ), bit 6/7 "staging tiles of the last event not yet stored"
     uint32_t pend = 0;
-    int g = 0, b = 0, h = 0;       // current head
-    int pg = 0, pb = 0, ph = 0;    // previous head (for read-outs that cross the head boundary)
-    // RC columns at a time keep the read-outs' register footprint small (they run between the two column halves of
-    // a pair, and any spill goes to L2: the L1 is all shared memory here)
+    // TMEM -> scale -> bf16 -> staging tile row r (128B-swizzled, the layout of the TMA store box), RC columns at a time
     constexpr int RC = OC < 16 ? OC : 16;
-    auto read_store = [&](uint32_t taddr, __nv_bfloat16* dst, int col0, float mul, bool do_ld, bool do_st) {
+    auto read_stage = [&](uint32_t taddr, uint32_t stile, int col0, float mul, bool do_ld) {
 #pragma unroll
       for (int c = 0; c < OC; c += RC) {
         uint32_t v[RC];
         if (do_ld) {
           tmem_ld_cols<RC>(taddr + col0 + c, v);
           tmem_wait_ld();
-        }
-        if (do_st) {
 #pragma unroll
           for (int e = 0; e < RC; e += 8) {
-            if (col0 + c + e < p.hs) {
-              uint4 u;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                h2[q] = __floats2bfloat162_rn(__uint_as_float(v[e + 2 * q]) * mul, __uint_as_float(v[e + 2 * q + 1]) * mul);
-              *reinterpret_cast<uint4*>(dst + col0 + c + e) = u;
-            }
+            for (int q = 0; q < 4; ++q)
+              h2[q] = __floats2bfloat162_rn(__uint_as_float(v[e + 2 * q]) * mul, __uint_as_float(v[e + 2 * q + 1]) * mul);
+            sts128(stile + r * 128 + ((((col0 + c + e) >> 3) ^ (r & 7)) << 4), u);
           }
         }
       }
     };
-    // dV_j (quarters 0, 1) / dK_j (quarters 2, 3) of the key/value tile recorded in `pend`
+    // dV_j (quarters 0, 1) -> P half 1, dK_j (quarters 2, 3) -> dS half 1; the storer warp issues the TMA stores
     auto readout_kv = [&]() {
       mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 2) & 1);
       tc_fence_after();
       const bool is_k = qd >= 2;
-      const bool prev = (pend >> 9) & 1;
-      const int gg = prev ? pg : g, bq = prev ? pb : b, hq = prev ? ph : h;
-      const int kvrow = ((pend >> 4) & 1) * 128 + r, ps = (pend >> 5) & 15;
-      const GradOut& go = is_k ? p.dk[ps] : p.dv[ps];
-      read_store(tmem_base + (is_k ? 320 : 256) + lane_off,
-                 go.ptr + (long long)gg * go.gs + ((long long)bq * p.T + kvrow) * go.ld + hq * go.head_stride, (qd & 1) * OC,
-                 is_k ? p.scale : 1.f, true, kvrow < p.T);
+      read_stage(tmem_base + (is_k ? 320 : 256) + lane_off, (is_k ? sdS : sP) + TILE, (qd & 1) * OC, is_k ? p.scale : 1.f, true);
       tc_fence_before();
       mbar_arrive_a(bb + 8 * AB_DKV_EMPTY);
-      pend &= ~0x3f5u;   // clear bits 0, 2, 4-9
+      fence_proxy_async_smem();
+      mbar_arrive_a(bb + 8 * AB_SKV_FULL);
+      pend = (pend & ~0x5u) | 0x40u;
     };
-    // dQ_0 (quarters 0, 1) / dQ_1 (quarters 2, 3) of the head recorded in `pend`
+    // dQ_0 (quarters 0, 1) -> P half 0, dQ_1 (quarters 2, 3) -> dS half 0 (head boundary: P/dS are idle)
     auto readout_q = [&]() {
       mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 3) & 1);
       tc_fence_after();
       const int ti = qd >> 1;
-      const bool prev = (pend >> 10) & 1;
-      const int gg = prev ? pg : g, bq = prev ? pb : b, hq = prev ? ph : h;
-      const int row = ti * 128 + r;
-      read_store(tmem_base + 384 + 64 * ti + lane_off,
-                 p.dq.ptr + (long long)gg * p.dq.gs + ((long long)bq * p.T + row) * p.dq.ld + hq * p.dq.head_stride, (qd & 1) * OC,
-                 p.scale, ti < n_qt, ti < n_qt && row < p.T);
+      read_stage(tmem_base + 384 + 64 * ti + lane_off, ti ? sdS : sP, (qd & 1) * OC, p.scale, ti < n_qt);
       tc_fence_before();
       mbar_arrive_a(bb + 8 * AB_DQ_EMPTY);
-      pend &= ~0x40au;   // clear bits 1, 3, 10
+      fence_proxy_async_smem();
+      mbar_arrive_a(bb + 8 * AB_SQ_FULL);
+      pend = (pend & ~0xau) | 0x80u;
+    };
+    // before P/dS are written again: the TMA stores of the last read-outs have drained their staging tiles
+    auto wait_staging = [&](uint32_t which) {
+      if (pend & which & 0x40u) { mbar_wait_a(bb + 8 * AB_SKV_FREE, (pend >> 4) & 1); pend = (pend & ~0x40u) ^ 0x10u; }
+      if (pend & which & 0x80u) { mbar_wait_a(bb + 8 * AB_SQ_FREE, (pend >> 5) & 1); pend = (pend & ~0x80u) ^ 0x20u; }
     };
     // per-thread piece of the D / lse prologue: row tid >> 1, 16-byte vectors 2v + (tid & 1) of the head's hs columns
     const int drow = tid >> 1, dpart = tid & 1, nvec = p.hs >> 3;
+    int tc = 0;
+    const bool ttr = warp == 0;
+    int g = 0, b = 0, h = 0;
 
     for (; it.work < total; it.next(n_qt, n_src, stride)) {
       if (it.first_of_head()) {
-        pg = g; pb = b; ph = h;
         {
           int w = it.work;
           h = w % p.H; w /= p.H;
           b = w % p.B;
           g = w / p.B;
         }
-        if (pend & 1) pend |= 1u << 9;
-        if (pend & 2) pend |= 1u << 10;
         // D[s][row] = rowsum(dO * O_s) and lse * log2(e) for the whole head, straight from global memory (two threads
-        // per row). The NEXT head's inputs are prefetched into L2 here, a whole head ahead of their use.
+        // per row). The NEXT head's inputs are prefetched into L2 here, a whole head ahead of their use; this head's
+        // dO and first-source loads are issued before the pending read-outs so that their latency overlaps them.
+        if (ttr) AB_TRACE(2, tc, 7);            // prologue start
         named_bar_sync(5, AB_MATH_THREADS);     // sD / sLse of the previous head are no longer read
-        const bool rok = drow < p.T;
+        const bool rok = drow < p.T && !(p.debug & 1);
         const long long roff = ((long long)b * p.T + drow) * p.ldo + h * p.hs;
         if (it.work + stride < total && rok && dpart == 0) {
           int w = it.work + stride;
@@ -322,20 +377,25 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ob + roff2));
           }
         }
-        if (pend & 1) readout_kv();
-        if (pend & 2) readout_q();
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        uint4 dvv[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          dvv[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(p.d_o + (long long)g * p.o_gs + roff + (2 * v + dpart) * 8) : z4;
-        for (int s = 0; s < n_src; ++s) {
+        uint4 dvv[4], ov[4];
+        float lv;
+        auto load_src = [&](int s) {
           const __nv_bfloat16* ob = p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o + (long long)g * p.o_gs;
-          uint4 ov[4];
 #pragma unroll
           for (int v = 0; v < 4; ++v)
             ov[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(ob + roff + (2 * v + dpart) * 8) : z4;
-          const float lv = (rok && dpart == 0) ? p.lse[((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T + drow] : 0.f;
+          lv = (rok && dpart == 0) ? p.lse[((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T + drow] : 0.f;
+        };
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          dvv[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(p.d_o + (long long)g * p.o_gs + roff + (2 * v + dpart) * 8) : z4;
+        load_src(0);
+        if (pend & 1) readout_kv();
+        if (pend & 2) readout_q();
+        if (ttr) AB_TRACE(2, tc, 9);            // read-outs done
+        for (int s = 0; s < n_src; ++s) {
+          if (s > 0) load_src(s);
           float acc = 0.f;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
@@ -351,7 +411,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
             sts_f32(sLse + (s * 256 + drow) * 4, lv * 1.4426950408889634f);
           }
         }
+        if (ttr) AB_TRACE(2, tc, 10);           // D stored
         named_bar_sync(5, AB_MATH_THREADS);
+        if (ttr) AB_TRACE(2, tc, 1);            // head prologue done
       }
       const int row = it.i * 128 + r;
       const bool diag = it.i == it.j;
@@ -361,13 +423,14 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
       for (int hh = 0; hh < 2; ++hh) {
         const int col_base = it.j * 128 + hh * 64 + qd * 16;
         // these 16 columns are needed unless they lie above the diagonal for every row of the warp (warp-uniform)
-        const bool need = !diag || col_base <= it.i * 128 + wq * 32 + 31;
+        const bool need = (!diag || col_base <= it.i * 128 + wq * 32 + 31) && !(p.debug & 4);
         int nvalid = !diag ? 16 : (row - col_base + 1 < 0 ? 0 : (row - col_base + 1 > 16 ? 16 : row - col_base + 1));
         if (row >= p.T) nvalid = 0;
         uint32_t pp[8], dd[8];     // 16 columns of P and dS, packed bf16x2
         mbar_wait_a(bb + 8 * (AB_S_FULL + hh), it.n & 1);
         mbar_wait_a(bb + 8 * (AB_DP_FULL + hh), it.n & 1);   // issued right behind S: no register is held across a wait
         tc_fence_after();
+        if (ttr) AB_TRACE(2, tc, 2 + hh);   // S/dP half available
         if (need) {
           uint32_t sv[16], dv[16];
           tmem_ld_32x16(tmem_base + hh * 64 + lane_off + qd * 16, sv);
@@ -394,8 +457,16 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 8; ++e) pp[e] = dd[e] = 0u;
         }
-        // P/dS smem is free once the gradient UMMAs of the previous pair are complete (they had the math above to run)
-        if (hh == 0) mbar_wait_a(bb + 8 * AB_G_DONE, (it.n & 1) ^ 1);
+        if (hh == 0) {
+          if (ttr) AB_TRACE(2, tc, 4);      // half 0 math done
+          // P/dS smem is free once the gradient UMMAs of the previous pair are complete (they had the math above to
+          // run) and, after a head boundary, once the dQ staging tiles in the half-0 regions have been stored
+          mbar_wait_a(bb + 8 * AB_G_DONE, (it.n & 1) ^ 1);
+          wait_staging(0x80u);
+          if (ttr) AB_TRACE(2, tc, 5);      // g_done(n-1) seen
+        } else {
+          wait_staging(0x40u);              // dV/dK staging tiles (half-1 regions) stored
+        }
         const uint32_t off = hh * TILE + r * 128;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -404,18 +475,19 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
           sts128(sdS + off + lc, make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]));
         }
         if (hh == 0) {
-          // deferred read-outs of the previous key/value tile / head (their last gradient UMMAs are the ones waited
-          // for above); placed here because no P/dS registers are live between the two column halves
+          // deferred read-out of the previous key/value tile (its last gradient UMMAs are the ones waited for above);
+          // placed here because no P/dS registers are live between the two column halves and the half-1 regions of
+          // P/dS are free to stage the tiles
           if (pend & 1) readout_kv();
-          if (pend & 2) readout_q();
         }
       }
       fence_proxy_async_smem();
       mbar_arrive_a(bb + 8 * AB_PDS_FULL);
-      if (it.i == n_qt - 1)   // last pair of this key/value tile: dK/dV read-out after the next pair's math
-        pend = (pend & ~0x3f4u) | 1u | ((it.n & 1u) << 2) | ((uint32_t)it.j << 4) | ((uint32_t)it.s << 5);
+      if (ttr) AB_TRACE(2, tc, 6);          // pds_full arrive
+      if (it.i == n_qt - 1)   // last pair of this key/value tile: dK/dV read-out after the next pair's first half
+        pend = (pend & ~0x4u) | 1u | ((it.n & 1u) << 2);
       if (it.i == n_qt - 1 && it.j == n_qt - 1 && it.s == n_src - 1)   // last pair of the head
-        pend = (pend & ~0x408u) | 2u | ((it.n & 1u) << 3);
+        pend = (pend & ~0x8u) | 2u | ((it.n & 1u) << 3);
     }
     if (pend & 1) readout_kv();
     if (pend & 2) readout_q();
@@ -474,14 +546,19 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
     if (make_head_map(&maps.k[s], &k[s], hs, H, T, B, G, 128)) return 1;
     if (make_head_map(&maps.v[s], &v[s], hs, H, T, B, G, 128)) return 1;
     if (grad_out(&p.dk[s], &dk[s], G) || grad_out(&p.dv[s], &dv[s], G)) return 1;
+    if (make_head_map(&maps.dk[s], &dk[s], hs, H, T, B, G, 128)) return 1;
+    if (make_head_map(&maps.dv[s], &dv[s], hs, H, T, B, G, 128)) return 1;
   }
   if (grad_out(&p.dq, dq, G)) return 1;
+  if (make_head_map(&maps.dq, dq, hs, H, T, B, G, 128)) return 1;
   p.T = T; p.B = B; p.H = H; p.G = G; p.hs = hs; p.n_src = n_src; p.n_qt = (T + 127) / 128;
   p.scale = (float)(1.0 / sqrt((double)hs));
   p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)hs));
   const long long total = (long long)G * B * H;
   TA_CHECK_ARG(total < (1ll << 31), "attention grid too large");
   p.total_work = (int)total;
+  { const char* e = getenv("TA_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("TA_ATTN_TRACE"); p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   p.d_o = (const __nv_bfloat16*)do_bf16;
   p.o = (const __nv_bfloat16*)o_bf16;
   p.o_src = n_src > 1 ? (const __nv_bfloat16*)o_src_bf16 : nullptr;
