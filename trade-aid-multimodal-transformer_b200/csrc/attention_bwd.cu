@@ -98,7 +98,7 @@ struct AbIter {
 enum : uint32_t {
   AB_Q_FULL = 0, AB_Q_EMPTY = 2, AB_KV_FULL = 4, AB_KV_EMPTY = 6, AB_S_FULL = 8, AB_DP_FULL = 10, AB_S_EMPTY = 12,
   AB_DP_EMPTY = 14, AB_PDS_FULL = 16, AB_G_DONE = 17, AB_DKV_EMPTY = 18, AB_DQ_EMPTY = 19,
-  AB_SKV_FULL = 20, AB_SKV_FREE = 21, AB_SQ_FULL = 22, AB_SQ_FREE = 23, AB_NBARS = 24
+  AB_SKV_FULL = 20, AB_SQ_FULL = 21, AB_NBARS = 22
 };
 
 template <int DP>
@@ -108,8 +108,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   constexpr int OC = DP / 2;   // gradient columns per math thread at read-out
   extern __shared__ __align__(1024) uint8_t smem[];
   // [Q 2 slots][dO 2 slots][2 stages x (K, V)][P: 2 column halves][dS: 2 column halves][barriers][D][lse]
-  // The P/dS halves double as the staging tiles of the gradient read-outs (TMA stores): dV -> P half 1, dK -> dS
-  // half 1 (free between the two column halves of a pair), dQ_0 -> P half 0, dQ_1 -> dS half 0 (head boundary only).
+  // Dead operand tiles double as the staging tiles of the gradient read-outs (TMA stores): dK_j / dV_j go into the
+  // K_j / V_j tiles of their own ring stage, dQ into the Q/dO slot of the head's last query tile; the STORER warp
+  // releases those tiles to the loader once the TMA store has drained them.
   const uint32_t sQ = smem_u32(smem), sdO = sQ + 2 * TILE, sKV = sQ + 4 * TILE, sP = sQ + 8 * TILE, sdS = sQ + 10 * TILE;
   const uint32_t bb = sQ + 12 * TILE;                        // barrier i at bb + 8 * i
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + 12 * TILE + AB_NBARS * 8);
@@ -117,7 +118,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   const uint32_t sLse = sD + ATTB_MAX_SRC * 256 * 4;         // fp32 [n_src][256] lse * log2(e)
   if ((sQ & 1023u) != 0) __trap();
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // the shuffle tells the compiler that `warp` is warp-uniform: the issuer branches then compute their descriptors in
+  // uniform registers instead of moving every tcgen05.mma operand across with R2UR
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid == 0) {
     for (uint32_t x = 0; x < AB_NBARS; ++x) {
       const bool wide = x == AB_S_EMPTY || x == AB_S_EMPTY + 1 || x == AB_DP_EMPTY || x == AB_DP_EMPTY + 1 ||
@@ -191,25 +194,27 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
           const int h = w % p.H; w /= p.H;
           const int b = w % p.B;
           const int g = w / p.B;
-          // dV_j, dK_j of the key/value tile whose last pair this is
+          // dK_j, dV_j of the key/value tile whose last pair this is: staged in the K/V tiles of its own stage
+          const int st = it.ks & 1;
           mbar_wait_a(bb + 8 * AB_SKV_FULL, ekv & 1);
           if (!(p.debug & 2)) {
-            tma_store_5d(&maps.dv[it.s], sP + TILE, 0, h, it.j * 128, b, g);
-            tma_store_5d(&maps.dk[it.s], sdS + TILE, 0, h, it.j * 128, b, g);
+            tma_store_5d(&maps.dk[it.s], sKV + st * 2 * TILE, 0, h, it.j * 128, b, g);
+            tma_store_5d(&maps.dv[it.s], sKV + st * 2 * TILE + TILE, 0, h, it.j * 128, b, g);
           }
           bulk_commit_group();
           bulk_wait_read<0>();
-          mbar_arrive_a(bb + 8 * AB_SKV_FREE);
+          mbar_arrive_a(bb + 8 * (AB_KV_EMPTY + st));      // the loader may refill this stage
           ++ekv;
-          if (it.j == n_qt - 1 && it.s == n_src - 1) {   // last pair of the head: dQ tiles
+          if (it.j == n_qt - 1 && it.s == n_src - 1) {   // last pair of the head: dQ tiles, staged in the slot of tile n_qt - 1
+            const int sl = slot(it, n_qt - 1);
             mbar_wait_a(bb + 8 * AB_SQ_FULL, eq & 1);
             if (!(p.debug & 2)) {
-              tma_store_5d(&maps.dq, sP, 0, h, 0, b, g);
-              if (n_qt > 1) tma_store_5d(&maps.dq, sdS, 0, h, 128, b, g);
+              tma_store_5d(&maps.dq, sQ + sl * TILE, 0, h, 0, b, g);
+              if (n_qt > 1) tma_store_5d(&maps.dq, sdO + sl * TILE, 0, h, 128, b, g);
             }
             bulk_commit_group();
             bulk_wait_read<0>();
-            mbar_arrive_a(bb + 8 * AB_SQ_FREE);
+            mbar_arrive_a(bb + 8 * (AB_Q_EMPTY + sl));     // the loader may refill this slot
             ++eq;
           }
         }
@@ -281,8 +286,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
                          acc_q | (kk != 0));
           umma_commit_ws(bb + 8 * AB_G_DONE);
           AB_TRACE(3, tc, 5);   // grads issued
-          if (a.i == n_qt - 1) umma_commit_ws(bb + 8 * (AB_KV_EMPTY + st));                    // last pair of this key/value tile
-          if (a.s == n_src - 1 && a.j == a.i) umma_commit_ws(bb + 8 * (AB_Q_EMPTY + sl));      // last pair that reads query tile i
+          // last pair that reads query tile i < n_qt - 1: its slot goes back to the loader. (The K/V stage and the slot
+          // of the last query tile are released by the storer: they stage the dK/dV and dQ read-outs first.)
+          if (a.s == n_src - 1 && a.j == a.i && a.i != n_qt - 1) umma_commit_ws(bb + 8 * (AB_Q_EMPTY + sl));
         }
       }
     }
@@ -292,7 +298,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
     const int r = tid & 127, qd = tid >> 7, wq = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     // deferred read-outs, packed: bit 0 dK/dV pending, bit 1 dQ pending, bit 2/3 their g_done parities,
-    // bit 4/5 parity of the next staging event (dK/dV, dQ), bit 6/7 "staging tiles of the last event not yet stored"
+    // bit 4 ring stage of the pending key/value tile, bit 5 Q/dO slot that stages dQ
     uint32_t pend = 0;
     // TMEM -> scale -> bf16 -> staging tile row r (128B-swizzled, the layout of the TMA store box), RC columns at a time
     constexpr int RC = OC < 16 ? OC : 16;
@@ -315,68 +321,75 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
         }
       }
     };
-    // dV_j (quarters 0, 1) -> P half 1, dK_j (quarters 2, 3) -> dS half 1; the storer warp issues the TMA stores
+    // dK_j (quarters 2, 3) -> K tile, dV_j (quarters 0, 1) -> V tile of the stage the tile was loaded into (dead: every
+    // UMMA that reads it is complete); the storer warp issues the TMA stores and hands the stage back to the loader
     auto readout_kv = [&]() {
       mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 2) & 1);
       tc_fence_after();
       const bool is_k = qd >= 2;
-      read_stage(tmem_base + (is_k ? 320 : 256) + lane_off, (is_k ? sdS : sP) + TILE, (qd & 1) * OC, is_k ? p.scale : 1.f, true);
+      read_stage(tmem_base + (is_k ? 320 : 256) + lane_off, sKV + ((pend >> 4) & 1) * 2 * TILE + (is_k ? 0 : TILE), (qd & 1) * OC,
+                 is_k ? p.scale : 1.f, true);
       tc_fence_before();
       mbar_arrive_a(bb + 8 * AB_DKV_EMPTY);
       fence_proxy_async_smem();
       mbar_arrive_a(bb + 8 * AB_SKV_FULL);
-      pend = (pend & ~0x5u) | 0x40u;
+      pend &= ~0x15u;
     };
-    // dQ_0 (quarters 0, 1) -> P half 0, dQ_1 (quarters 2, 3) -> dS half 0 (head boundary: P/dS are idle)
+    // dQ_0 (quarters 0, 1) -> Q tile, dQ_1 (quarters 2, 3) -> dO tile of the slot of the head's last query tile
     auto readout_q = [&]() {
       mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 3) & 1);
       tc_fence_after();
       const int ti = qd >> 1;
-      read_stage(tmem_base + 384 + 64 * ti + lane_off, ti ? sdS : sP, (qd & 1) * OC, p.scale, ti < n_qt);
+      read_stage(tmem_base + 384 + 64 * ti + lane_off, (ti ? sdO : sQ) + ((pend >> 5) & 1) * TILE, (qd & 1) * OC, p.scale, ti < n_qt);
       tc_fence_before();
       mbar_arrive_a(bb + 8 * AB_DQ_EMPTY);
       fence_proxy_async_smem();
       mbar_arrive_a(bb + 8 * AB_SQ_FULL);
-      pend = (pend & ~0xau) | 0x80u;
-    };
-    // before P/dS are written again: the TMA stores of the last read-outs have drained their staging tiles
-    auto wait_staging = [&](uint32_t which) {
-      if (pend & which & 0x40u) { mbar_wait_a(bb + 8 * AB_SKV_FREE, (pend >> 4) & 1); pend = (pend & ~0x40u) ^ 0x10u; }
-      if (pend & which & 0x80u) { mbar_wait_a(bb + 8 * AB_SQ_FREE, (pend >> 5) & 1); pend = (pend & ~0x80u) ^ 0x20u; }
+      pend &= ~0x2au;
     };
     // per-thread piece of the D / lse prologue: row tid >> 1, 16-byte vectors 2v + (tid & 1) of the head's hs columns
     const int drow = tid >> 1, dpart = tid & 1, nvec = p.hs >> 3;
+    int g2 = 0, b2 = 0, h2 = 0;
     int tc = 0;
     const bool ttr = warp == 0;
     int g = 0, b = 0, h = 0;
 
     for (; it.work < total; it.next(n_qt, n_src, stride)) {
       if (it.first_of_head()) {
-        {
+        if (it.hc == 0) {
           int w = it.work;
           h = w % p.H; w /= p.H;
           b = w % p.B;
           g = w / p.B;
+        } else {
+          g = g2; b = b2; h = h2;      // decoded one head ahead (below)
         }
         // D[s][row] = rowsum(dO * O_s) and lse * log2(e) for the whole head, straight from global memory (two threads
         // per row). The NEXT head's inputs are prefetched into L2 here, a whole head ahead of their use; this head's
         // dO and first-source loads are issued before the pending read-outs so that their latency overlaps them.
+        // (Eight lanes per row - whole 128-byte lines per load instruction - measured slower: 0.61 vs 0.57 ms.)
         if (ttr) AB_TRACE(2, tc, 7);            // prologue start
         named_bar_sync(5, AB_MATH_THREADS);     // sD / sLse of the previous head are no longer read
+        if (ttr) AB_TRACE(2, tc, 8);            // first barrier passed
         const bool rok = drow < p.T && !(p.debug & 1);
         const long long roff = ((long long)b * p.T + drow) * p.ldo + h * p.hs;
-        if (it.work + stride < total && rok && dpart == 0) {
+        if (it.work + stride < total) {
           int w = it.work + stride;
-          const int h2 = w % p.H; w /= p.H;
-          const int b2 = w % p.B;
-          const int g2 = w / p.B;
-          const long long roff2 = ((long long)b2 * p.T + drow) * p.ldo + h2 * p.hs;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_o + (long long)g2 * p.o_gs + roff2));
-          for (int s = 0; s < n_src; ++s) {
-            const __nv_bfloat16* ob = p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o + (long long)g2 * p.o_gs;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ob + roff2));
+          h2 = w % p.H; w /= p.H;
+          b2 = w % p.B;
+          g2 = w / p.B;
+          if (rok && dpart == 0) {
+            const long long roff2 = ((long long)b2 * p.T + drow) * p.ldo + h2 * p.hs;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_o + (long long)g2 * p.o_gs + roff2));
+            for (int s = 0; s < n_src; ++s) {
+              const __nv_bfloat16* ob = p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o + (long long)g2 * p.o_gs;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(ob + roff2));
+              if ((drow & 31) == 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lse + ((((long long)s * p.G + g2) * p.B + b2) * p.H + h2) * p.T + drow));
+            }
           }
         }
+        if (ttr) AB_TRACE(2, tc, 14);           // prefetches issued
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         uint4 dvv[4], ov[4];
         float lv;
@@ -391,7 +404,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
         for (int v = 0; v < 4; ++v)
           dvv[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(p.d_o + (long long)g * p.o_gs + roff + (2 * v + dpart) * 8) : z4;
         load_src(0);
+        if (ttr) AB_TRACE(2, tc, 11);           // loads issued
         if (pend & 1) readout_kv();
+        if (ttr) AB_TRACE(2, tc, 13);           // kv read-out done
         if (pend & 2) readout_q();
         if (ttr) AB_TRACE(2, tc, 9);            // read-outs done
         for (int s = 0; s < n_src; ++s) {
@@ -459,13 +474,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
         }
         if (hh == 0) {
           if (ttr) AB_TRACE(2, tc, 4);      // half 0 math done
-          // P/dS smem is free once the gradient UMMAs of the previous pair are complete (they had the math above to
-          // run) and, after a head boundary, once the dQ staging tiles in the half-0 regions have been stored
+          // P/dS smem is free once the gradient UMMAs of the previous pair are complete (they had the math above to run)
           mbar_wait_a(bb + 8 * AB_G_DONE, (it.n & 1) ^ 1);
-          wait_staging(0x80u);
           if (ttr) AB_TRACE(2, tc, 5);      // g_done(n-1) seen
-        } else {
-          wait_staging(0x40u);              // dV/dK staging tiles (half-1 regions) stored
         }
         const uint32_t off = hh * TILE + r * 128;
 #pragma unroll
@@ -476,8 +487,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
         }
         if (hh == 0) {
           // deferred read-out of the previous key/value tile (its last gradient UMMAs are the ones waited for above);
-          // placed here because no P/dS registers are live between the two column halves and the half-1 regions of
-          // P/dS are free to stage the tiles
+          // placed here because no P/dS registers are live between the two column halves
           if (pend & 1) readout_kv();
         }
       }
@@ -485,9 +495,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
       mbar_arrive_a(bb + 8 * AB_PDS_FULL);
       if (ttr) AB_TRACE(2, tc, 6);          // pds_full arrive
       if (it.i == n_qt - 1)   // last pair of this key/value tile: dK/dV read-out after the next pair's first half
-        pend = (pend & ~0x4u) | 1u | ((it.n & 1u) << 2);
+        pend = (pend & ~0x14u) | 1u | ((it.n & 1u) << 2) | ((uint32_t)(it.ks & 1) << 4);
       if (it.i == n_qt - 1 && it.j == n_qt - 1 && it.s == n_src - 1)   // last pair of the head
-        pend = (pend & ~0x8u) | 2u | ((it.n & 1u) << 3);
+        pend = (pend & ~0x28u) | 2u | ((it.n & 1u) << 3) | ((uint32_t)slot(it, n_qt - 1) << 5);
     }
     if (pend & 1) readout_kv();
     if (pend & 2) readout_q();
