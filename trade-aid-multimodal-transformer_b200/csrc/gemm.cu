@@ -84,7 +84,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t epi_bar[4][3];
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5;
+  // the shuffle tells the compiler that `warp` is warp-uniform: producer and issuer then keep their TMA / UMMA operands
+  // in uniform registers (no per-instruction R2UR waterfall)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -115,8 +117,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int total_tiles = tiles_per_group * p.G0 * p.G1;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
+      const uint32_t smem_a = smem_u32(smem), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -126,63 +129,61 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = (t % p.n_blocks) * BLOCK_N;
         const int g0 = g % p.G0, g1 = g / p.G0;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_wait_a(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t fb = full0 + 8 * stage;
+          mbar_expect_tx_ws(fb, Cfg::STAGE_BYTES);
+          const uint32_t sA = smem_a + stage * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + A_STAGE_BYTES;
           const int k0 = kb * BLOCK_K;
           if (!p.a_mn) {
-            tma_load_4d(sA, &tmA, &full_bar[stage], k0, m0, g0, g1);
+            tma_load_4d_ws(sA, &tmA, fb, k0, m0, g0, g1);
           } else {
 #pragma unroll
             for (int c = 0; c < BLOCK_M / 64; ++c)
-              tma_load_4d(sA + c * (64 * BLOCK_K * 2), &tmA, &full_bar[stage], m0 + c * 64, k0, g0, g1);
+              tma_load_4d_ws(sA + c * (64 * BLOCK_K * 2), &tmA, fb, m0 + c * 64, k0, g0, g1);
           }
           if (!p.b_mn) {
-            tma_load_4d(sB, &tmB, &full_bar[stage], k0, n0, g0, g1);
+            tma_load_4d_ws(sB, &tmB, fb, k0, n0, g0, g1);
           } else {
 #pragma unroll
             for (int c = 0; c < BLOCK_N / 64; ++c)
-              tma_load_4d(sB + c * (64 * BLOCK_K * 2), &tmB, &full_bar[stage], n0 + c * 64, k0, g0, g1);
+              tma_load_4d_ws(sB + c * (64 * BLOCK_K * 2), &tmB, fb, n0 + c * 64, k0, g0, g1);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, p.a_mn, p.b_mn);
     // K-major SW128: 8-row groups 1024 B apart (SBO), 16 k-elements = 32 B inside the swizzle row.
     // MN-major SW128: boxes of [64 k-rows][64 mn] (8 KB): next 64-mn chunk = LBO 8192, next 8 k-rows = SBO 1024,
     //                 16 k-rows = 2048 B.
-    const uint32_t a_lbo = p.a_mn ? 64 * BLOCK_K * 2 : 16, a_kstep = p.a_mn ? 16 * 128 : 32;
-    const uint32_t b_lbo = p.b_mn ? 64 * BLOCK_K * 2 : 16, b_kstep = p.b_mn ? 16 * 128 : 32;
+    // The address field of a descriptor sits in its low bits: stepping an operand = adding (bytes >> 4).
+    const uint64_t da0 = umma_desc_sw128(0, p.a_mn ? 64 * BLOCK_K * 2 : 16, 1024);
+    const uint64_t db0 = umma_desc_sw128(0, p.b_mn ? 64 * BLOCK_K * 2 : 16, 1024);
+    const uint32_t a_kstep = (p.a_mn ? 16 * 128 : 32) >> 4, b_kstep = (p.b_mn ? 16 * 128 : 32) >> 4;
+    const uint32_t smem_a = smem_u32(smem), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      mbar_wait_a(tempty0 + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_a(full0 + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sB = sA + A_STAGE_BYTES;
-          const int krem = p.K - kb * BLOCK_K;
-          const int nk = krem >= BLOCK_K ? BLOCK_K / 16 : (krem + 15) / 16;
-          for (int j = 0; j < nk; ++j) {
-            const uint64_t da = umma_desc_sw128(sA + j * a_kstep, a_lbo, 1024);
-            const uint64_t db = umma_desc_sw128(sB + j * b_kstep, b_lbo, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb | j) != 0);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (kb == p.k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
-        }
-        __syncwarp();
+        const uint32_t sA = smem_a + stage * Cfg::STAGE_BYTES;
+        const uint64_t da = da0 + ((sA & 0x3FFFF) >> 4), db = db0 + (((sA + A_STAGE_BYTES) & 0x3FFFF) >> 4);
+        const int krem = p.K - kb * BLOCK_K;
+        const int nk = krem >= BLOCK_K ? BLOCK_K / 16 : (krem + 15) / 16;
+        for (int j = 0; j < nk; ++j) umma_bf16_ws(tmem_d, da + j * a_kstep, db + j * b_kstep, idesc, (kb | j) != 0);
+        umma_commit_ws(empty0 + 8 * stage);
+        if (kb == p.k_blocks - 1) umma_commit_ws(tfull0 + 8 * acc);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
