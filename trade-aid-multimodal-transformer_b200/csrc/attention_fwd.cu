@@ -7,6 +7,7 @@
 //   warp 16  loader : TMA Q tiles (2 slots) and K/V blocks (3-stage ring); runs ahead across segments and work items
 //   warp 17  issuer : S = Q K^T (128x128x hs) into one of two TMEM S buffers, one pair AHEAD of the softmax;
 //                     O += P V (128 x hs x 128, V as the MN-major B operand) into one of two TMEM O buffers
+//   warp 18  storer : TMA stores of the output tiles the math warps stage in smem
 //   warps 0-15 math : thread (row r, column quarter) owns 32 S columns: tcgen05.ld, causal mask, online softmax with exp2
 //                     (row max exchanged between the four quarters through smem, lazy rescale of O in TMEM only when the
 //                     max moves by more than 2^8), P (bf16) into one of two 128B-swizzled smem buffers; the segment
@@ -15,6 +16,7 @@
 // The first version ran these phases one after another in a 128-thread CTA (tensor pipe 8% active, warps mostly
 // waiting on mbarriers: profiles/r01_ncu_attn_v2_*.csv). Nothing of size T x T ever touches HBM. head_size <= 64.
 #include <cmath>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "../../include/tradeaid_b200.h"
@@ -33,10 +35,13 @@ struct AttnMaps {
   CUtensorMap q;
   CUtensorMap k[ATT_MAX_SRC];
   CUtensorMap v[ATT_MAX_SRC];
+  CUtensorMap o;                     // TMA store targets
+  CUtensorMap o_src[ATT_MAX_SRC];
 };
 
 struct AttnFwdParams {
   int T, B, H, G, hs, n_src, n_qtiles, total_work;
+  int debug;   // TA_ATTN_DEBUG (dev only): 16 = no TMEM source sum, 32 = no output staging / stores
   float scale_log2;
   __nv_bfloat16* o;       // [G][B*T][ldo], head h at column h*hs
   long long ldo, o_gs;
@@ -47,19 +52,13 @@ struct AttnFwdParams {
 
 // The (work, i, s, j) schedule; every warp role walks the same sequence with its own copy.
 struct AfIter {
-  int total, n_qt, n_src, stride;
   int work, i, s, j;
   int n, k, qc;   // running counters over the CTA's lifetime: pairs, segments, q tiles
-  __device__ __forceinline__ void init(int total_, int n_qt_, int n_src_, int first, int stride_) {
-    total = total_; n_qt = n_qt_; n_src = n_src_; stride = stride_;
-    work = first; i = s = j = 0; n = k = qc = 0;
-  }
-  __device__ __forceinline__ bool valid() const { return work < total; }
+  __device__ __forceinline__ void init(int first) { work = first; i = s = j = 0; n = k = qc = 0; }
   __device__ __forceinline__ bool first_in_seg() const { return j == 0; }
   __device__ __forceinline__ bool last_in_seg() const { return j == i; }
   __device__ __forceinline__ bool new_q() const { return j == 0 && s == 0; }
-  __device__ __forceinline__ bool last_of_q() const { return j == i && s == n_src - 1; }
-  __device__ __forceinline__ void next() {
+  __device__ __forceinline__ void next(int n_qt, int n_src, int stride) {
     ++n;
     if (j < i) { ++j; return; }
     ++k; j = 0;
@@ -79,7 +78,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
   uint8_t* sQ = smem;                              // 2 slots
   uint8_t* sKV = smem + 2 * AF_TILE;               // NS x (K, V)
   uint8_t* sP = sKV + NS * 2 * AF_TILE;            // 2 buffers x 2 column halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * AF_TILE);
+  uint8_t* sStage = sP + 4 * AF_TILE;              // one 128 x 128 B output tile staged for the TMA store
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + AF_TILE);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = bars + 2;       // [2]
   uint64_t* kv_full = bars + 4;       // [NS]
@@ -90,12 +90,15 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
   uint64_t* p_empty = s_full + 6;     // [2] P V of the pair complete (P buffer free, O updated)
   uint64_t* o_full = s_full + 8;      // [2]
   uint64_t* o_empty = s_full + 10;    // [2] 256 arrivals
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(s_full + 12);
-  float* sMax = reinterpret_cast<float*>(s_full + 13);   // [2 parity][4 quarters][128]
+  uint64_t* stg_full = s_full + 12;   // 512 arrivals: the staging tile holds an output tile
+  uint64_t* stg_free = s_full + 13;   // the TMA store has read it
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(s_full + 14);
+  float* sMax = reinterpret_cast<float*>(s_full + 15);   // [2 parity][4 quarters][128]
   float* sL = sMax + 1024;                                // [2 parity][4 quarters][128]
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // the shuffle tells the compiler that `warp` is warp-uniform (TMA / UMMA operands then stay in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid == 0) {
     for (int x = 0; x < 2; ++x) {
       mbar_init(&q_full[x], 1); mbar_init(&q_empty[x], 1);
@@ -104,6 +107,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
       mbar_init(&o_full[x], 1); mbar_init(&o_empty[x], AF_MATH_WARPS * 32);
     }
     for (int x = 0; x < NS; ++x) { mbar_init(&kv_full[x], 1); mbar_init(&kv_empty[x], 1); }
+    mbar_init(stg_full, AF_MATH_WARPS * 32); mbar_init(stg_free, 1);
     fence_mbar_init();
   }
   if (warp == AF_MATH_WARPS + 1) {
@@ -114,76 +118,116 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+DP) O1 [320,320+DP)
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+DP) O1 [320,320+DP) sum over sources [384,384+DP)
   AfIter it;
-  it.init(p.total_work, p.n_qtiles, p.n_src, blockIdx.x, gridDim.x);
+  it.init(blockIdx.x);
+  const int n_qt = p.n_qtiles, n_src = p.n_src, stride = gridDim.x, total = p.total_work;
 
   if (warp >= AF_MATH_WARPS) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == AF_MATH_WARPS) {
-    // ================================================================== loader
-    if ((tid & 31) == 0) {
-      for (; it.valid(); it.next()) {
+    // ================================================================== loader (whole warp, one elected lane issues)
+    {
+      const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
+      const uint32_t bq_full = smem_u32(q_full), bq_empty = smem_u32(q_empty), bkv_full = smem_u32(kv_full), bkv_empty = smem_u32(kv_empty);
+      for (; it.work < total; it.next(n_qt, n_src, stride)) {
         int w = it.work;
         const int h = w % p.H; w /= p.H;
         const int b = w % p.B;
         const int g = w / p.B;
         if (it.new_q()) {
           const int qs = it.qc & 1;
-          mbar_wait(&q_empty[qs], ((it.qc >> 1) & 1) ^ 1);
-          mbar_expect_tx(&q_full[qs], AF_TILE);
-          tma_load_5d(sQ + qs * AF_TILE, &maps.q, &q_full[qs], 0, h, it.i * 128, b, g);
+          mbar_wait_a(bq_empty + 8 * qs, ((it.qc >> 1) & 1) ^ 1);
+          mbar_expect_tx_ws(bq_full + 8 * qs, AF_TILE);
+          tma_load_5d_ws(aQ + qs * AF_TILE, &maps.q, bq_full + 8 * qs, 0, h, it.i * 128, b, g);
         }
         const int st = it.n % NS, u = it.n / NS;
-        mbar_wait(&kv_empty[st], (u & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * AF_TILE);
-        uint8_t* dK = sKV + st * 2 * AF_TILE;
-        tma_load_5d(dK, &maps.k[it.s], &kv_full[st], 0, h, it.j * 128, b, g);
-        tma_load_5d(dK + AF_TILE, &maps.v[it.s], &kv_full[st], 0, h, it.j * 128, b, g);
+        mbar_wait_a(bkv_empty + 8 * st, (u & 1) ^ 1);
+        mbar_expect_tx_ws(bkv_full + 8 * st, 2 * AF_TILE);
+        const uint32_t dK = aKV + st * 2 * AF_TILE;
+        tma_load_5d_ws(dK, &maps.k[it.s], bkv_full + 8 * st, 0, h, it.j * 128, b, g);
+        tma_load_5d_ws(dK + AF_TILE, &maps.v[it.s], bkv_full + 8 * st, 0, h, it.j * 128, b, g);
       }
     }
   } else if (warp == AF_MATH_WARPS + 1) {
-    // ================================================================== UMMA issuer
-    if ((tid & 31) == 0) {
+    // ================================================================== UMMA issuer (whole warp, one elected lane issues)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DP, 0, 1);
       const int nk_qk = (p.hs + 15) / 16;
+      const uint32_t aQ0 = smem_u32(sQ), aKV = smem_u32(sKV), aP0 = smem_u32(sP);
+      const uint32_t bq_full = smem_u32(q_full), bq_empty = smem_u32(q_empty), bkv_full = smem_u32(kv_full), bkv_empty = smem_u32(kv_empty);
+      const uint32_t bs_full = smem_u32(s_full), bs_empty = smem_u32(s_empty), bp_full = smem_u32(p_full), bp_empty = smem_u32(p_empty);
+      const uint32_t bo_full = smem_u32(o_full), bo_empty = smem_u32(o_empty);
+      // descriptors step by adding (bytes >> 4) to the low word
+      const uint64_t d_k = umma_desc_sw128(0, 16, 1024);        // K-major operand (Q, K, P), 128-byte rows
+      const uint64_t d_v = umma_desc_sw128(0, 8192, 1024);      // V: MN-major B operand
       auto issue_s = [&](const AfIter& a) {
         const int qs = a.qc & 1, st = a.n % NS, sb = a.n & 1;
-        if (a.new_q()) mbar_wait(&q_full[qs], (a.qc >> 1) & 1);
-        mbar_wait(&kv_full[st], (a.n / NS) & 1);
-        mbar_wait(&s_empty[sb], ((a.n >> 1) & 1) ^ 1);
+        if (a.new_q()) mbar_wait_a(bq_full + 8 * qs, (a.qc >> 1) & 1);
+        mbar_wait_a(bkv_full + 8 * st, (a.n / NS) & 1);
+        mbar_wait_a(bs_empty + 8 * sb, ((a.n >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ + qs * AF_TILE), aK = smem_u32(sKV + st * 2 * AF_TILE);
-        for (int kk = 0; kk < nk_qk; ++kk)
-          umma_bf16(tmem_base + sb * 128, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
-                    idesc_s, kk != 0);
-        umma_commit(&s_full[sb]);
+        const uint64_t dq = d_k + (((aQ0 + qs * AF_TILE) & 0x3FFFF) >> 4), dkk = d_k + (((aKV + st * 2 * AF_TILE) & 0x3FFFF) >> 4);
+        for (int kk = 0; kk < nk_qk; ++kk) umma_bf16_ws(tmem_base + sb * 128, dq + kk * 2, dkk + kk * 2, idesc_s, kk != 0);
+        umma_commit_ws(bs_full + 8 * sb);
       };
       auto issue_pv = [&](const AfIter& a) {
         const int st = a.n % NS, pb = a.n & 1, ob = a.k & 1;
-        if (a.first_in_seg()) mbar_wait(&o_empty[ob], ((a.k >> 1) & 1) ^ 1);
-        mbar_wait(&p_full[pb], (a.n >> 1) & 1);
+        if (a.first_in_seg()) mbar_wait_a(bo_empty + 8 * ob, ((a.k >> 1) & 1) ^ 1);
+        mbar_wait_a(bp_full + 8 * pb, (a.n >> 1) & 1);
         tc_fence_after();
-        const uint32_t aP = smem_u32(sP + pb * 2 * AF_TILE), aV = smem_u32(sKV + st * 2 * AF_TILE + AF_TILE);
+        const uint64_t dp = d_k + (((aP0 + pb * 2 * AF_TILE) & 0x3FFFF) >> 4);
+        const uint64_t dv = d_v + (((aKV + st * 2 * AF_TILE + AF_TILE) & 0x3FFFF) >> 4);
         // only the k-steps that can hold unmasked columns for some row of the tile
         const int last_row = (a.i * 128 + 127 < p.T - 1) ? a.i * 128 + 127 : p.T - 1;
         int nk = (last_row - a.j * 128) / 16 + 1;
         if (nk > 8) nk = 8;
+        const uint32_t accf = a.first_in_seg() ? 0u : 1u;
         for (int kk = 0; kk < nk; ++kk)
-          umma_bf16(tmem_base + 256 + ob * 64, umma_desc_sw128(aP + (kk >> 2) * AF_TILE + (kk & 3) * 32, 16, 1024),
-                    umma_desc_sw128(aV + kk * 2048, 8192, 1024), idesc_o, !a.first_in_seg() || kk != 0);
-        umma_commit(&p_empty[pb]);
-        umma_commit(&kv_empty[st]);
-        if (a.last_in_seg()) umma_commit(&o_full[ob]);
-        if (a.last_of_q()) umma_commit(&q_empty[a.qc & 1]);
+          umma_bf16_ws(tmem_base + 256 + ob * 64, dp + (kk >> 2) * (AF_TILE >> 4) + (kk & 3) * 2, dv + kk * 128, idesc_o,
+                       accf | (kk != 0));
+        umma_commit_ws(bp_empty + 8 * pb);
+        umma_commit_ws(bkv_empty + 8 * st);
+        if (a.last_in_seg()) umma_commit_ws(bo_full + 8 * ob);
+        if ((a.j == a.i && a.s == n_src - 1)) umma_commit_ws(bq_empty + 8 * (a.qc & 1));
       };
       AfIter is = it;   // S runs one pair ahead of P V
-      if (is.valid()) { issue_s(is); is.next(); }
-      for (; it.valid(); it.next()) {
-        if (is.valid()) { issue_s(is); is.next(); }
+      if (is.work < total) { issue_s(is); is.next(n_qt, n_src, stride); }
+      for (; it.work < total; it.next(n_qt, n_src, stride)) {
+        if (is.work < total) { issue_s(is); is.next(n_qt, n_src, stride); }
         issue_pv(it);
       }
+    }
+  } else if (warp == AF_MATH_WARPS + 2) {
+    // ================================================================== storer (one lane): TMA stores of the output tiles
+    if ((tid & 31) == 0) {
+      const uint32_t aStage = smem_u32(sStage), bfull = smem_u32(stg_full), bfree = smem_u32(stg_free);
+      int ev = 0;
+      auto store_event = [&](const CUtensorMap* m0, const CUtensorMap* m1, int h, int i, int b, int g) {
+        if (p.debug & 32) return;
+        mbar_wait_a(bfull, ev & 1);
+        tma_store_5d(m0, aStage, 0, h, i * 128, b, g);
+        if (m1) tma_store_5d(m1, aStage, 0, h, i * 128, b, g);
+        bulk_commit_group();
+        bulk_wait_read<0>();
+        mbar_arrive_a(bfree);
+        ++ev;
+      };
+      for (; it.work < total; it.next(n_qt, n_src, stride)) {
+        if (!it.last_in_seg()) continue;
+        int w = it.work;
+        const int h = w % p.H; w /= p.H;
+        const int b = w % p.B;
+        const int g = w / p.B;
+        if constexpr (MULTI) {
+          if (p.o_src) store_event(&maps.o_src[it.s], nullptr, h, it.i, b, g);     // this source's normalised output
+          if (it.s == p.n_src - 1) store_event(&maps.o, nullptr, h, it.i, b, g);   // sum over the sources
+        } else {
+          store_event(&maps.o, p.o_src ? &maps.o_src[0] : nullptr, h, it.i, b, g);
+        }
+      }
+      bulk_wait_all<0>();
     }
   }
   } else {
@@ -196,15 +240,24 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
     const int bar_id = 1 + wq;
     const bool ep_active = qd * EC < DP;        // DP = 16: only two quarters own output columns
     float m_run = -INFINITY, l_run = 0.f;
-    float o_tot[MULTI ? EC : 1];
-#pragma unroll
-    for (int e = 0; e < (MULTI ? EC : 1); ++e) o_tot[e] = 0.f;
     // deferred segment epilogue
     bool pend = false;
     int pe_work = 0, pe_i = 0, pe_s = 0, pe_k = 0;
     bool pe_last_src = false;
     float pe_m = 0.f, pe_l = 0.f;
     int xpar = 0;     // parity of the max-exchange buffer
+    int sev = 0;      // staging events so far (parity of stg_free)
+    const uint32_t aStage = smem_u32(sStage), bstg_full = smem_u32(stg_full), bstg_free = smem_u32(stg_free);
+    // Output path: 8 fp32 columns at a time (small temporaries: any spill goes to L2 here, the L1 is all shared
+    // memory) TMEM -> normalise -> bf16 -> this thread's row of the staging tile (128B-swizzled like the TMA store
+    // box); the storer warp issues the store. Rows beyond T and columns beyond hs are clipped by the tensor map.
+    auto stage8 = [&](int c, const float (&x)[8]) {
+      uint4 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+      sts128(aStage + r * 128 + ((((qd * EC + c) >> 3) ^ (r & 7)) << 4), u);
+    };
     auto epilogue = [&]() {
       float* sl = sL + (pe_k & 1) * 512;
       sl[qd * 128 + r] = pe_l;
@@ -212,60 +265,78 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
       const float l = (sl[r] + sl[128 + r]) + (sl[256 + r] + sl[384 + r]);
       const float inv = 1.f / l;
       const int ob = pe_k & 1;
+      const bool skip = p.debug & 32;
+      // event A: this segment's normalised output (the only output for a single source; o_src[s] otherwise)
+      const bool ev_a = (MULTI ? p.o_src != nullptr : true) && !skip;
       mbar_wait(&o_full[ob], (pe_k >> 1) & 1);
       tc_fence_after();
-      uint32_t ov[EC];
+      if (ev_a) mbar_wait_a(bstg_free, (sev & 1) ^ 1);    // the previous tile has been read out of the staging buffer
       if (ep_active) {
-        tmem_ld_cols<EC>(tmem_base + 256 + ob * 64 + lane_off + qd * EC, ov);
-        tmem_wait_ld();
+        const uint32_t to = tmem_base + 256 + ob * 64 + lane_off + qd * EC;
+        const uint32_t tt = tmem_base + 384 + lane_off + qd * EC;   // running sum over the sources (MULTI)
+#pragma unroll
+        for (int c = 0; c < EC; c += 8) {
+          uint32_t ov[8];
+          float val[8];
+          tmem_ld_32x8(to + c, ov);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) val[e] = __uint_as_float(ov[e]) * inv;
+          if (ev_a) stage8(c, val);
+          if constexpr (MULTI) {
+            if (pe_s > 0) {
+              tmem_ld_32x8(tt + c, ov);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) val[e] += __uint_as_float(ov[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ov[e] = __float_as_uint(val[e]);
+            tmem_st_cols<8>(tt + c, ov);
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(&o_empty[ob]);
-      int w = pe_work;
-      const int h = w % p.H; w /= p.H;
-      const int b = w % p.B;
-      const int g = w / p.B;
-      const int row = pe_i * 128 + r;
-      const bool row_ok = row < p.T;
-      if (ep_active) {
-        const long long off = (long long)g * p.o_gs + ((long long)b * p.T + row) * p.ldo + h * p.hs + qd * EC;
-        float val[EC];
+      if (ev_a) {
+        fence_proxy_async_smem();
+        mbar_arrive_a(bstg_full);
+        ++sev;
+      }
+      if constexpr (MULTI) {
+        if (pe_last_src && !skip) {     // event B: the sum over the sources
+          mbar_wait_a(bstg_free, (sev & 1) ^ 1);
+          if (ep_active) {
+            tmem_wait_st();
+            const uint32_t tt = tmem_base + 384 + lane_off + qd * EC;
 #pragma unroll
-        for (int e = 0; e < EC; ++e) val[e] = __uint_as_float(ov[e]) * inv;
-        auto store = [&](__nv_bfloat16* dst, const float (&x)[EC]) {
+            for (int c = 0; c < EC; c += 8) {
+              uint32_t ov[8];
+              float val[8];
+              tmem_ld_32x8(tt + c, ov);
+              tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < EC; e += 8) {
-            if (qd * EC + e < p.hs) {
-              uint4 u;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(x[e + 2 * q], x[e + 2 * q + 1]);
-              *reinterpret_cast<uint4*>(dst + e) = u;
+              for (int e = 0; e < 8; ++e) val[e] = __uint_as_float(ov[e]);
+              stage8(c, val);
             }
           }
-        };
-        if constexpr (MULTI) {
-          if (p.o_src && row_ok) store(p.o_src + (long long)pe_s * p.o_src_stride + off, val);
-#pragma unroll
-          for (int e = 0; e < EC; ++e) o_tot[e] += val[e];
-          if (pe_last_src) {
-#pragma unroll
-            for (int e = 0; e < EC; ++e) val[e] = o_tot[e];
-            if (row_ok) store(p.o + off, val);
-#pragma unroll
-            for (int e = 0; e < EC; ++e) o_tot[e] = 0.f;
-          }
-        } else if (row_ok) {
-          store(p.o + off, val);
-          if (p.o_src) store(p.o_src + off, val);
+          fence_proxy_async_smem();
+          mbar_arrive_a(bstg_full);
+          ++sev;
         }
       }
-      if (qd == 0 && row_ok)
+      const int row = pe_i * 128 + r;
+      if (qd == 0 && row < p.T) {
+        int w = pe_work;
+        const int h = w % p.H; w /= p.H;
+        const int b = w % p.B;
+        const int g = w / p.B;
         p.lse[((((long long)pe_s * p.G + g) * p.B + b) * p.H + h) * p.T + row] = pe_m * 0.6931471805599453f + logf(l);
+      }
       pend = false;
     };
 
-    for (; it.valid(); it.next()) {
+    for (; it.work < total; it.next(n_qt, n_src, stride)) {
       const int sb = it.n & 1, pb = sb;
       const int row = it.i * 128 + r, kv0 = it.j * 128;
       const bool diag = it.j == it.i;
@@ -411,7 +482,7 @@ int make_head_map(CUtensorMap* out, const ta_attn_tensor* t, int hs, int H, int 
 
 template <int DP, bool MULTI>
 static int launch_attn_fwd(const AttnMaps& maps, const AttnFwdParams& p, cudaStream_t st) {
-  constexpr int SMEM = (2 + 2 * AF_KV_STAGES + 4) * AF_TILE + 256 + 8192 + 64;
+  constexpr int SMEM = (2 + 2 * AF_KV_STAGES + 4 + 1) * AF_TILE + 256 + 8192 + 64;
   static bool attr = false;
   if (!attr) {
     TA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DP, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -444,10 +515,20 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
     if (make_head_map(&maps.k[s], &k[s], hs, H, T, B, G, 128)) return 1;
     if (make_head_map(&maps.v[s], &v[s], hs, H, T, B, G, 128)) return 1;
   }
+  {
+    ta_attn_tensor ot{o_bf16, ldo, hs, o_gs};
+    if (make_head_map(&maps.o, &ot, hs, H, T, B, G, 128)) return 1;
+    if (o_src_bf16)
+      for (int s = 0; s < n_src; ++s) {
+        ta_attn_tensor st{static_cast<const __nv_bfloat16*>(o_src_bf16) + (long long)s * o_src_stride, ldo, hs, o_gs};
+        if (make_head_map(&maps.o_src[s], &st, hs, H, T, B, G, 128)) return 1;
+      }
+  }
   AttnFwdParams p{};
   p.T = T; p.B = B; p.H = H; p.G = G; p.hs = hs; p.n_src = n_src;
   p.n_qtiles = (T + 127) / 128;
   p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)hs));
+  { const char* e = getenv("TA_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.o = (__nv_bfloat16*)o_bf16; p.ldo = ldo; p.o_gs = o_gs;
   p.o_src = (__nv_bfloat16*)o_src_bf16; p.o_src_stride = o_src_stride;
   p.lse = lse;
