@@ -57,6 +57,7 @@ struct GemmParams {
   int nbf, nbb;        // staging buffers per epilogue warp: fp32 chunks / bf16 chunks
   int bf16_direct;     // tma_epi with both outputs: bf16 goes out with row-per-thread stores
   int epi_warp_bytes;
+  int m_major;         // tile order, see decode_tile
   int debug;           // TA_GEMM_DEBUG (dev only): 1 = skip global stores, 2 = skip the epilogue math and stores
 };
 
@@ -68,6 +69,368 @@ __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// tile index -> (group, m0, n0). Default order: group-major (tiles of a group are neighbours: its operands stay hot in
+// L2). m_major: row-block-major, for the block-diagonal q/k/v stage-2 problems (hundreds of groups that are column
+// slices of the SAME rows, K <= 64): concurrently running tiles then read / write adjacent segments of the same rows.
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int tiles_per_group, int block_n, int block_m, int& g,
+                                            int& m0, int& n0) {
+  if (p.m_major) {
+    const int per_m = p.n_blocks * p.G0 * p.G1;
+    const int mb = tile / per_m, rem = tile - mb * per_m;
+    g = rem / p.n_blocks;
+    m0 = mb * block_m;
+    n0 = (rem - g * p.n_blocks) * block_n;
+  } else {
+    g = tile / tiles_per_group;
+    const int t = tile - g * tiles_per_group;
+    m0 = (t / p.n_blocks) * block_m;
+    n0 = (t % p.n_blocks) * block_n;
+  }
+}
+
+// Epilogue of one warp (warps 2-5; warp % 4 = TMEM lane quarter): shared by the 1-CTA and the 2-CTA kernels.
+//   epi_smem    shared-window address of the staging buffers (4 warps x p.epi_warp_bytes)
+//   tmem_empty0 address of tmem_empty_bar[0] of the CTA whose issuer warp waits on it: the own CTA's (m_off == 0, plain
+//               shared address) or the leader's through the cluster window (PAIR peer, m_off != 0)
+//   m_off       row offset of this CTA inside the tile (PAIR: rank * 128)
+template <int BLOCK_N, bool PAIR>
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps& em, uint32_t epi_smem, uint64_t* tmem_full_bar,
+                                              uint32_t tmem_empty0, uint64_t (*epi_bar)[3], uint32_t tmem_base, int warp, int lane,
+                                              int first_tile, int tile_stride, int total_tiles, int tiles_per_group, int m_off) {
+  const int quarter = warp & 3;
+  int local = 0;
+  if (p.tma_epi) {
+    // ---- TMA-staged epilogue. Per warp: nbf fp32 chunk buffers (SWIZZLE_128B) then nbb bf16 chunk buffers
+    // (SWIZZLE_64B). Thread = accumulator row; 16-byte smem accesses hit swizzled chunk (j ^ row bits): conflict-free.
+    const bool has_res = p.res != nullptr, has_aux = p.aux != nullptr, has_f32 = p.out_f32 != nullptr,
+               has_bf = p.out_bf16 != nullptr;
+    const bool has_load = has_res || has_aux;
+    const int nl = has_res ? p.nbf : p.nbb;          // rotation depth of the loaded buffer family
+    const int dbg = p.debug, act = p.act;
+    const float alpha = p.alpha;
+    const bool aux_tanh = p.aux_mode == TA_AUX_TANH_BWD;
+    const uint32_t wbase = epi_smem + (warp - 2) * p.epi_warp_bytes;
+    const uint32_t fbuf0 = wbase, bbuf0 = wbase + p.nbf * EPI_F32_BYTES;
+    const uint32_t lbar0 = smem_u32(&epi_bar[warp - 2][0]);
+    const uint32_t frow = lane * 128, fsw = lane & 7;            // fp32 row offset, swizzle key
+    const uint32_t brow = lane * 64, bsw = (lane >> 1) & 3;      // bf16 row offset, swizzle key
+    uint32_t lphase = 0;    // bit b: parity the next wait on loaded buffer b uses
+    uint32_t sc = 0;        // running count of chunks stored (rotation of the store-only buffers)
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+      int g, m0, n0;
+      decode_tile(p, tile, tiles_per_group, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M, g, m0, n0);
+      m0 += m_off;
+      const int g0 = g % p.G0, g1 = g / p.G0;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int row0 = m0 + quarter * 32;
+      constexpr int NCH = BLOCK_N / 32;
+      int nch = (p.N - n0 + 31) / 32;
+      if (nch > NCH) nch = NCH;
+      int next_load = 0;
+      // residual / saved-activation chunk q of this tile -> loaded buffer q % nl
+      auto issue_load = [&](int q) {
+        const int b = q % nl;
+        const uint32_t bar = lbar0 + b * 8;
+        if (has_res) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EPI_F32_BYTES) : "memory");
+          tma_load_4d_u32(fbuf0 + b * EPI_F32_BYTES, &em.res, bar, n0 + q * 32, row0, g0, g1);
+        } else {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EPI_BF16_BYTES) : "memory");
+          tma_load_4d_u32(bbuf0 + b * EPI_BF16_BYTES, &em.aux, bar, n0 + q * 32, row0, g0, g1);
+        }
+      };
+      if (has_load && row0 < p.M) {
+        if (lane == 0) {
+          bulk_wait_read<0>();     // every staging buffer of the previous tile has been read by its store
+          for (; next_load < nch && next_load < nl; ++next_load) issue_load(next_load);
+        }
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      const float* bias = p.bias ? p.bias + g0 * p.bias_gs0 + g1 * p.bias_gs1 : nullptr;
+      __nv_bfloat16* ob = p.bf16_direct ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      if (row0 >= p.M) {   // this warp's 32 rows lie entirely beyond M: nothing to store
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR && m_off != 0) mbar_arrive_cluster(tmem_empty0 + 8 * acc); else mbar_arrive_a(tmem_empty0 + 8 * acc); }
+        continue;
+      }
+      // The chunk loop stays ROLLED: unrolled x8 the kernel was ~0.5 MB of SASS and the epilogue warps spent most of
+      // their time in instruction-fetch stalls (ncu: stall_no_inst on nearly every line).
+      uint32_t v[32];
+      tmem_ld_32x32(taddr_row, v);
+      int lb = 0;             // loaded buffer of this chunk (c % nl)
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        {
+          const int col0 = n0 + c * 32;
+          const bool full = col0 + 32 <= p.N;
+          float4 b4[8];
+          const bool vb = bias && full && p.vec_bias;
+          if (vb) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+          }
+          tmem_wait_ld();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha;
+          if (c + 1 < nch) {   // v is dead: the next chunk's TMEM read overlaps the rest of this chunk
+            tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
+          } else {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR && m_off != 0) mbar_arrive_cluster(tmem_empty0 + 8 * acc); else mbar_arrive_a(tmem_empty0 + 8 * acc); }
+          }
+          const uint32_t fbuf = fbuf0 + (has_res ? lb : (int)(sc & 1)) * EPI_F32_BYTES;
+          const uint32_t bbuf = bbuf0 + (has_aux ? lb : (int)(sc & 1)) * EPI_BF16_BYTES;
+          if (dbg != 2) {
+            if (vb) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
+              }
+            } else if (bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (full || col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
+            }
+            if (act == TA_ACT_TANH) {
+              if (has_f32) {   // fp32 consumers get the accurate tanh
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+              } else {         // bf16-only output: MUFU tanh (rel. error 2^-11) sits below the 2^-9 rounding of the
+                               // store; tanhf costs ~60 issue cycles per warp and made the epilogue the bottleneck
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
+              }
+            } else if (act == TA_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (has_load) {
+              mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
+              lphase ^= 1u << lb;
+            }
+            if (has_aux) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = dbg == 3 ? make_uint4(0, 0, 0, 0) : lds128(bbuf + brow + ((j ^ bsw) << 4));
+                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float a = __bfloat162float(h[k]);
+                  f[8 * j + k] = aux_tanh ? f[8 * j + k] * (1.f - a * a) : (a > 0.f ? f[8 * j + k] : 0.f);
+                }
+              }
+            }
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 u = dbg == 3 ? make_uint4(0, 0, 0, 0) : lds128(fbuf + frow + ((j ^ fsw) << 4));
+                f[4 * j] += __uint_as_float(u.x); f[4 * j + 1] += __uint_as_float(u.y);
+                f[4 * j + 2] += __uint_as_float(u.z); f[4 * j + 3] += __uint_as_float(u.w);
+              }
+            }
+            if (has_f32 && dbg != 4) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(fbuf + frow + ((j ^ fsw) << 4),
+                       make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                  __float_as_uint(f[4 * j + 3])));
+            }
+            if (has_bf) {
+              uint4 u[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u[j]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+              }
+              if (!p.bf16_direct) {
+                if (dbg != 4)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sts128(bbuf + brow + ((j ^ bsw) << 4), u[j]);
+              } else if (row_ok && dbg != 1) {
+                if (full && p.vec_bf16) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(ob + col0 + 8 * j) = u[j];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
+                }
+              }
+            }
+          } else if (has_load) {
+            mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
+            lphase ^= 1u << lb;
+          }
+          if (dbg != 5) fence_proxy_async_smem();   // generic-proxy writes above -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            if (dbg == 0 || dbg == 5) {
+              if (has_f32) tma_store_4d(&em.f32, fbuf, col0, row0, g0, g1);
+              if (has_bf && !p.bf16_direct) tma_store_4d(&em.bf16, bbuf, col0, row0, g0, g1);
+            }
+            bulk_commit_group();
+            bulk_wait_read<1>();      // the store of the previous chunk has drained its buffer
+            if (has_load)
+              for (; next_load < nch && next_load <= c + nl - 1; ++next_load) issue_load(next_load);
+          }
+          ++sc;
+          if (++lb == nl) lb = 0;
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+  } else
+  {
+  for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+    int g, m0, n0;
+    decode_tile(p, tile, tiles_per_group, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M, g, m0, n0);
+      m0 += m_off;
+    const int g0 = g % p.G0, g1 = g / p.G0;
+    const int acc = local & 1;
+    const uint32_t acc_phase = (local >> 1) & 1;
+    mbar_wait(&tmem_full_bar[acc], acc_phase);
+    tc_fence_after();
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+    const float* bias = p.bias ? p.bias + g0 * p.bias_gs0 + g1 * p.bias_gs1 : nullptr;
+    const __nv_bfloat16* aux = p.aux ? p.aux + g0 * p.aux_gs0 + g1 * p.aux_gs1 + (long long)row * p.ld_aux : nullptr;
+    const float* res = p.res ? p.res + g0 * p.res_gs0 + g1 * p.res_gs1 + (long long)row * p.ld_res : nullptr;
+    float* of = p.out_f32 ? p.out_f32 + g0 * p.f32_gs0 + g1 * p.f32_gs1 + (long long)row * p.ld_f32 : nullptr;
+    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+    constexpr int NCH = BLOCK_N / 32;
+    int nch = (p.N - n0 + 31) / 32;
+    if (nch > NCH) nch = NCH;
+    // rolled chunk loop (code size, see above); the TMEM read of chunk c+1 overlaps the processing of chunk c
+    uint32_t v[32];
+    tmem_ld_32x32(taddr_row, v);
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      {
+        const int col0 = n0 + c * 32;
+        const bool full = col0 + 32 <= p.N;
+        // bias for these 32 columns: 8 independent 128-bit broadcast loads, issued before waiting on TMEM
+        float4 b4[8];
+        const bool vb = bias && full && p.vec_bias;
+        if (vb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+        }
+        tmem_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+        if (c + 1 < nch) tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
+        if (row_ok) {
+          if (vb) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
+            }
+          } else if (bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
+          }
+          if (p.act == TA_ACT_TANH) {
+            if (of) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
+            }
+          } else if (p.act == TA_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (aux) {
+            if (full && p.vec_aux) {
+              uint4 u4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) u4[i] = *reinterpret_cast<const uint4*>(aux + col0 + 8 * i);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u4[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float a = __bfloat162float(h[j]);
+                  f[8 * i + j] = p.aux_mode == TA_AUX_TANH_BWD ? f[8 * i + j] * (1.f - a * a) : (a > 0.f ? f[8 * i + j] : 0.f);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) {
+                  const float a = __bfloat162float(aux[col0 + i]);
+                  f[i] = p.aux_mode == TA_AUX_TANH_BWD ? f[i] * (1.f - a * a) : (a > 0.f ? f[i] : 0.f);
+                }
+            }
+          }
+          if (res) {
+            if (full && p.vec_res) {
+              float4 r4[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(res + col0 + 4 * i);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[4 * i] += r4[i].x; f[4 * i + 1] += r4[i].y; f[4 * i + 2] += r4[i].z; f[4 * i + 3] += r4[i].w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) f[i] += res[col0 + i];
+            }
+          }
+          if (of) {
+            if (full && p.vec_f32) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(of + col0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) of[col0 + i] = f[i];
+            }
+          }
+          if (ob) {
+            if (full && p.vec_bf16) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[i + 2 * j], f[i + 2 * j + 1]);
+                *reinterpret_cast<uint4*>(ob + col0 + i) = u;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
+            }
+          }
+        }
+      }
+    }
+    // release this accumulator stage back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) { if (PAIR && m_off != 0) mbar_arrive_cluster(tmem_empty0 + 8 * acc); else mbar_arrive_a(tmem_empty0 + 8 * acc); }
+  }
+  }
 }
 
 template <int BLOCK_N>
@@ -123,10 +486,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int g = tile / tiles_per_group;
-        const int t = tile - g * tiles_per_group;
-        const int m0 = (t / p.n_blocks) * BLOCK_M;
-        const int n0 = (t % p.n_blocks) * BLOCK_N;
+        int g, m0, n0;
+        decode_tile(p, tile, tiles_per_group, BLOCK_N, BLOCK_M, g, m0, n0);
         const int g0 = g % p.G0, g1 = g / p.G0;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait_a(empty0 + 8 * stage, phase ^ 1);
@@ -189,345 +550,154 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int quarter = warp & 3;
-    int local = 0;
-    if (p.tma_epi) {
-      // ---- TMA-staged epilogue. Per warp: nbf fp32 chunk buffers (SWIZZLE_128B) then nbb bf16 chunk buffers
-      // (SWIZZLE_64B). Thread = accumulator row; 16-byte smem accesses hit swizzled chunk (j ^ row bits): conflict-free.
-      const bool has_res = p.res != nullptr, has_aux = p.aux != nullptr, has_f32 = p.out_f32 != nullptr,
-                 has_bf = p.out_bf16 != nullptr;
-      const bool has_load = has_res || has_aux;
-      const int nl = has_res ? p.nbf : p.nbb;          // rotation depth of the loaded buffer family
-      const int dbg = p.debug, act = p.act;
-      const float alpha = p.alpha;
-      const bool aux_tanh = p.aux_mode == TA_AUX_TANH_BWD;
-      const uint32_t wbase = smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + (warp - 2) * p.epi_warp_bytes;
-      const uint32_t fbuf0 = wbase, bbuf0 = wbase + p.nbf * EPI_F32_BYTES;
-      const uint32_t lbar0 = smem_u32(&epi_bar[warp - 2][0]);
-      const uint32_t frow = lane * 128, fsw = lane & 7;            // fp32 row offset, swizzle key
-      const uint32_t brow = lane * 64, bsw = (lane >> 1) & 3;      // bf16 row offset, swizzle key
-      uint32_t lphase = 0;    // bit b: parity the next wait on loaded buffer b uses
-      uint32_t sc = 0;        // running count of chunks stored (rotation of the store-only buffers)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const int g = tile / tiles_per_group;
-        const int t = tile - g * tiles_per_group;
-        const int m0 = (t / p.n_blocks) * BLOCK_M;
-        const int n0 = (t % p.n_blocks) * BLOCK_N;
-        const int g0 = g % p.G0, g1 = g / p.G0;
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        const int row0 = m0 + quarter * 32;
-        constexpr int NCH = BLOCK_N / 32;
-        int nch = (p.N - n0 + 31) / 32;
-        if (nch > NCH) nch = NCH;
-        int next_load = 0;
-        // residual / saved-activation chunk q of this tile -> loaded buffer q % nl
-        auto issue_load = [&](int q) {
-          const int b = q % nl;
-          const uint32_t bar = lbar0 + b * 8;
-          if (has_res) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EPI_F32_BYTES) : "memory");
-            tma_load_4d_u32(fbuf0 + b * EPI_F32_BYTES, &em.res, bar, n0 + q * 32, row0, g0, g1);
-          } else {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EPI_BF16_BYTES) : "memory");
-            tma_load_4d_u32(bbuf0 + b * EPI_BF16_BYTES, &em.aux, bar, n0 + q * 32, row0, g0, g1);
-          }
-        };
-        if (has_load && row0 < p.M) {
-          if (lane == 0) {
-            bulk_wait_read<0>();     // every staging buffer of the previous tile has been read by its store
-            for (; next_load < nch && next_load < nl; ++next_load) issue_load(next_load);
-          }
-        }
-        mbar_wait(&tmem_full_bar[acc], acc_phase);
-        tc_fence_after();
-        const int row = row0 + lane;
-        const bool row_ok = row < p.M;
-        const float* bias = p.bias ? p.bias + g0 * p.bias_gs0 + g1 * p.bias_gs1 : nullptr;
-        __nv_bfloat16* ob = p.bf16_direct ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
-        const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-        if (row0 >= p.M) {   // this warp's 32 rows lie entirely beyond M: nothing to store
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-          continue;
-        }
-        // The chunk loop stays ROLLED: unrolled x8 the kernel was ~0.5 MB of SASS and the epilogue warps spent most of
-        // their time in instruction-fetch stalls (ncu: stall_no_inst on nearly every line).
-        uint32_t v[32];
-        tmem_ld_32x32(taddr_row, v);
-        int lb = 0;             // loaded buffer of this chunk (c % nl)
-#pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
-          {
-            const int col0 = n0 + c * 32;
-            const bool full = col0 + 32 <= p.N;
-            float4 b4[8];
-            const bool vb = bias && full && p.vec_bias;
-            if (vb) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
-            }
-            tmem_wait_ld();
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha;
-            if (c + 1 < nch) {   // v is dead: the next chunk's TMEM read overlaps the rest of this chunk
-              tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
-            } else {
-              // all TMEM reads of this accumulator are done: hand it back to the MMA warp before the stores
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            }
-            const uint32_t fbuf = fbuf0 + (has_res ? lb : (int)(sc & 1)) * EPI_F32_BYTES;
-            const uint32_t bbuf = bbuf0 + (has_aux ? lb : (int)(sc & 1)) * EPI_BF16_BYTES;
-            if (dbg != 2) {
-              if (vb) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
-                }
-              } else if (bias) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (full || col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
-              }
-              if (act == TA_ACT_TANH) {
-                if (has_f32) {   // fp32 consumers get the accurate tanh
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
-                } else {         // bf16-only output: MUFU tanh (rel. error 2^-11) sits below the 2^-9 rounding of the
-                                 // store; tanhf costs ~60 issue cycles per warp and made the epilogue the bottleneck
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
-                }
-              } else if (act == TA_ACT_RELU) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-              if (has_load) {
-                mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
-                lphase ^= 1u << lb;
-              }
-              if (has_aux) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 u = dbg == 3 ? make_uint4(0, 0, 0, 0) : lds128(bbuf + brow + ((j ^ bsw) << 4));
-                  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    const float a = __bfloat162float(h[k]);
-                    f[8 * j + k] = aux_tanh ? f[8 * j + k] * (1.f - a * a) : (a > 0.f ? f[8 * j + k] : 0.f);
-                  }
-                }
-              }
-              if (has_res) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const uint4 u = dbg == 3 ? make_uint4(0, 0, 0, 0) : lds128(fbuf + frow + ((j ^ fsw) << 4));
-                  f[4 * j] += __uint_as_float(u.x); f[4 * j + 1] += __uint_as_float(u.y);
-                  f[4 * j + 2] += __uint_as_float(u.z); f[4 * j + 3] += __uint_as_float(u.w);
-                }
-              }
-              if (has_f32 && dbg != 4) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  sts128(fbuf + frow + ((j ^ fsw) << 4),
-                         make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                                    __float_as_uint(f[4 * j + 3])));
-              }
-              if (has_bf) {
-                uint4 u[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u[j]);
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
-                }
-                if (!p.bf16_direct) {
-                  if (dbg != 4)
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) sts128(bbuf + brow + ((j ^ bsw) << 4), u[j]);
-                } else if (row_ok && dbg != 1) {
-                  if (full && p.vec_bf16) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(ob + col0 + 8 * j) = u[j];
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                      if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
-                  }
-                }
-              }
-            } else if (has_load) {
-              mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
-              lphase ^= 1u << lb;
-            }
-            if (dbg != 5) fence_proxy_async_smem();   // generic-proxy writes above -> visible to the TMA store
-            __syncwarp();
-            if (lane == 0) {
-              if (dbg == 0 || dbg == 5) {
-                if (has_f32) tma_store_4d(&em.f32, fbuf, col0, row0, g0, g1);
-                if (has_bf && !p.bf16_direct) tma_store_4d(&em.bf16, bbuf, col0, row0, g0, g1);
-              }
-              bulk_commit_group();
-              bulk_wait_read<1>();      // the store of the previous chunk has drained its buffer
-              if (has_load)
-                for (; next_load < nch && next_load <= c + nl - 1; ++next_load) issue_load(next_load);
-            }
-            ++sc;
-            if (++lb == nl) lb = 0;
-            __syncwarp();
-          }
-        }
-      }
-      if (lane == 0) bulk_wait_all<0>();
-    } else
-    {
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      const int g = tile / tiles_per_group;
-      const int t = tile - g * tiles_per_group;
-      const int m0 = (t / p.n_blocks) * BLOCK_M;
-      const int n0 = (t % p.n_blocks) * BLOCK_N;
-      const int g0 = g % p.G0, g1 = g / p.G0;
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const float* bias = p.bias ? p.bias + g0 * p.bias_gs0 + g1 * p.bias_gs1 : nullptr;
-      const __nv_bfloat16* aux = p.aux ? p.aux + g0 * p.aux_gs0 + g1 * p.aux_gs1 + (long long)row * p.ld_aux : nullptr;
-      const float* res = p.res ? p.res + g0 * p.res_gs0 + g1 * p.res_gs1 + (long long)row * p.ld_res : nullptr;
-      float* of = p.out_f32 ? p.out_f32 + g0 * p.f32_gs0 + g1 * p.f32_gs1 + (long long)row * p.ld_f32 : nullptr;
-      __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
-      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      constexpr int NCH = BLOCK_N / 32;
-      int nch = (p.N - n0 + 31) / 32;
-      if (nch > NCH) nch = NCH;
-      // rolled chunk loop (code size, see above); the TMEM read of chunk c+1 overlaps the processing of chunk c
-      uint32_t v[32];
-      tmem_ld_32x32(taddr_row, v);
-#pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        {
-          const int col0 = n0 + c * 32;
-          const bool full = col0 + 32 <= p.N;
-          // bias for these 32 columns: 8 independent 128-bit broadcast loads, issued before waiting on TMEM
-          float4 b4[8];
-          const bool vb = bias && full && p.vec_bias;
-          if (vb) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
-          }
-          tmem_wait_ld();
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-          if (c + 1 < nch) tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
-          if (row_ok) {
-            if (vb) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
-              }
-            } else if (bias) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (full || col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
-            }
-            if (p.act == TA_ACT_TANH) {
-              if (of) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
-              }
-            } else if (p.act == TA_ACT_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            if (aux) {
-              if (full && p.vec_aux) {
-                uint4 u4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) u4[i] = *reinterpret_cast<const uint4*>(aux + col0 + 8 * i);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u4[i]);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float a = __bfloat162float(h[j]);
-                    f[8 * i + j] = p.aux_mode == TA_AUX_TANH_BWD ? f[8 * i + j] * (1.f - a * a) : (a > 0.f ? f[8 * i + j] : 0.f);
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.N) {
-                    const float a = __bfloat162float(aux[col0 + i]);
-                    f[i] = p.aux_mode == TA_AUX_TANH_BWD ? f[i] * (1.f - a * a) : (a > 0.f ? f[i] : 0.f);
-                  }
-              }
-            }
-            if (res) {
-              if (full && p.vec_res) {
-                float4 r4[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(res + col0 + 4 * i);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  f[4 * i] += r4[i].x; f[4 * i + 1] += r4[i].y; f[4 * i + 2] += r4[i].z; f[4 * i + 3] += r4[i].w;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.N) f[i] += res[col0 + i];
-              }
-            }
-            if (of) {
-              if (full && p.vec_f32) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  *reinterpret_cast<float4*>(of + col0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.N) of[col0 + i] = f[i];
-              }
-            }
-            if (ob) {
-              if (full && p.vec_bf16) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  uint4 u;
-                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[i + 2 * j], f[i + 2 * j + 1]);
-                  *reinterpret_cast<uint4*>(ob + col0 + i) = u;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.N) ob[col0 + i] = __float2bfloat16_rn(f[i]);
-              }
-            }
-          }
-        }
-      }
-      // release this accumulator stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-    }
-    }
+    gemm_epilogue<BLOCK_N, false>(p, em, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES, tmem_full_bar, smem_u32(&tmem_empty_bar[0]),
+                                  epi_bar, tmem_base, warp, lane, blockIdx.x, gridDim.x, total_tiles, tiles_per_group, 0);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ 2-CTA kernel
+// CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x 256 output tile per pair. Each CTA owns 128 rows (its A tile,
+// its TMEM accumulator, its epilogue) and stages only HALF of the B tile (128 of the 256 n-rows): the UMMA of the leader
+// CTA reads both halves. L2 -> smem traffic per output tile drops from 48 KB to 32 KB per k-block and CTA, which is
+// what bounds the 1-CTA kernel (~6300 B/clk L2 throughput chip-wide: 148 x 48 KB per 512 tensor-pipe cycles is 2x that).
+//   leader (rank 0): producer, UMMA issuer, epilogue        peer (rank 1): producer, epilogue
+//   full_bar[s]   (leader's): both CTAs' TMA loads complete_tx on it; the leader's producer expects 2 x STAGE bytes
+//   empty_bar[s], tmem_full_bar[a] (both CTAs): signalled by the leader's multicast tcgen05.commit
+//   tmem_empty_bar[a] (leader's): 8 arrivals, 4 epilogue warps of each CTA (the peer's arrive through the cluster window)
+constexpr int G2_BLOCK_N = 256;
+constexpr int G2_B_HALF = G2_BLOCK_N / 2;
+constexpr int G2_STAGE_BYTES = A_STAGE_BYTES + G2_B_HALF * BLOCK_K * 2;   // 32 KB per CTA
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ EpiMaps em, const GemmParams p) {
+  const int STAGES = p.stages;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t epi_bar[4][3];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 8);
+    }
+    for (int s = 0; s < 12; ++s) mbar_init(&epi_bar[0][0] + s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(&tmem_base_smem, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int tiles_per_group = m_pairs * p.n_blocks;
+  const int total_tiles = tiles_per_group * p.G0 * p.G1;
+  const int first_tile = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    const uint32_t smem_a = smem_u32(smem), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t full0_leader = mapa_u32(smem_u32(&full_bar[0]), 0);   // the leader's full barriers
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+      int g, m0, n0;
+      decode_tile(p, tile, tiles_per_group, G2_BLOCK_N, 2 * BLOCK_M, g, m0, n0);
+      m0 += rank * BLOCK_M;
+      n0 += rank * G2_B_HALF;
+      const int g0 = g % p.G0, g1 = g / p.G0;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait_a(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t fb = full0_leader + 8 * stage;
+        if (rank == 0) mbar_expect_tx_ws(smem_u32(&full_bar[stage]), 2 * G2_STAGE_BYTES);
+        const uint32_t sA = smem_a + stage * G2_STAGE_BYTES;
+        const uint32_t sB = sA + A_STAGE_BYTES;
+        const int k0 = kb * BLOCK_K;
+        if (!p.a_mn) {
+          tma_load_4d_2cta_ws(sA, &tmA, fb, k0, m0, g0, g1);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BLOCK_M / 64; ++c)
+            tma_load_4d_2cta_ws(sA + c * (64 * BLOCK_K * 2), &tmA, fb, m0 + c * 64, k0, g0, g1);
+        }
+        if (!p.b_mn) {
+          tma_load_4d_2cta_ws(sB, &tmB, fb, k0, n0, g0, g1);
+        } else {
+#pragma unroll
+          for (int c = 0; c < G2_B_HALF / 64; ++c)
+            tma_load_4d_2cta_ws(sB + c * (64 * BLOCK_K * 2), &tmB, fb, n0 + c * 64, k0, g0, g1);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, G2_BLOCK_N, p.a_mn, p.b_mn);
+      const uint64_t da0 = umma_desc_sw128(0, p.a_mn ? 64 * BLOCK_K * 2 : 16, 1024);
+      const uint64_t db0 = umma_desc_sw128(0, p.b_mn ? 64 * BLOCK_K * 2 : 16, 1024);
+      const uint32_t a_kstep = (p.a_mn ? 16 * 128 : 32) >> 4, b_kstep = (p.b_mn ? 16 * 128 : 32) >> 4;
+      const uint32_t smem_a = smem_u32(smem), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait_a(tempty0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * G2_BLOCK_N;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait_a(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sA = smem_a + stage * G2_STAGE_BYTES;
+          const uint64_t da = da0 + ((sA & 0x3FFFF) >> 4), db = db0 + (((sA + A_STAGE_BYTES) & 0x3FFFF) >> 4);
+          const int krem = p.K - kb * BLOCK_K;
+          const int nk = krem >= BLOCK_K ? BLOCK_K / 16 : (krem + 15) / 16;
+          for (int j = 0; j < nk; ++j) umma_bf16_2cta_ws(tmem_d, da + j * a_kstep, db + j * b_kstep, idesc, (kb | j) != 0);
+          umma_commit_2cta_ws(empty0 + 8 * stage, 3);
+          if (kb == p.k_blocks - 1) umma_commit_2cta_ws(tfull0 + 8 * acc, 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, their own 128 rows)
+    // the leader's warps arrive on their own barrier (CTA scope), the peer's through the cluster window
+    gemm_epilogue<G2_BLOCK_N, true>(p, em, smem_u32(smem) + STAGES * G2_STAGE_BYTES, tmem_full_bar,
+                                    rank == 0 ? smem_u32(&tmem_empty_bar[0]) : mapa_u32(smem_u32(&tmem_empty_bar[0]), 0), epi_bar, tmem_base, warp, lane, first_tile,
+                                    tile_stride, total_tiles, tiles_per_group, rank * BLOCK_M);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // no CTA leaves (or frees TMEM) while its peer may still touch its smem / barriers
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -609,17 +779,10 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int BLOCK_N>
-static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  CUtensorMap tmA, tmB;
-  if (make_operand_map(&tmA, A, p.M, p.K, p.G0, p.G1, BLOCK_M)) return 1;
-  if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, BLOCK_N)) return 1;
-  p.n_blocks = (int)ceil_div(p.N, BLOCK_N);
-  // ---- epilogue plan
+// Epilogue plan: which outputs go through TMA staging, how many staging buffers, and how many A/B ring stages are left.
+static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes) {
   static const int force_legacy = env_int("TA_GEMM_LEGACY_EPI", 0);
   static const int force_nl = env_int("TA_GEMM_NLOAD", 0);
-  EpiMaps em;
   memset(&em, 0, sizeof(em));
   const bool need_f = p.res || p.out_f32, need_b = p.aux || p.out_bf16;
   bool tma_ok = !force_legacy && !(p.aux && need_f);
@@ -637,17 +800,29 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
     if (force_nl == 2 || force_nl == 3) { if (p.res) p.nbf = force_nl; if (p.aux) p.nbb = force_nl; }
     auto epi_bytes = [&]() { return 4 * (p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES); };
     // keep the A/B ring at >= 4 stages when dropping the third (prefetch) buffer buys it
-    if (!force_nl && p.nbf == 3 && (SMEM_LIMIT - epi_bytes()) / Cfg::STAGE_BYTES < 4 &&
-        (SMEM_LIMIT - 4 * 2 * EPI_F32_BYTES) / Cfg::STAGE_BYTES >= 4 && p.k_blocks >= 16)
+    if (!force_nl && p.nbf == 3 && (SMEM_LIMIT - epi_bytes()) / stage_bytes < 4 &&
+        (SMEM_LIMIT - 4 * 2 * EPI_F32_BYTES) / stage_bytes >= 4 && p.k_blocks >= 16)
       p.nbf = 2;
     p.epi_warp_bytes = p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES;
   } else {
     p.bf16_direct = 0;
     p.epi_warp_bytes = 0;
   }
-  int stages = (SMEM_LIMIT - 4 * p.epi_warp_bytes) / Cfg::STAGE_BYTES;
+  int stages = (SMEM_LIMIT - 4 * p.epi_warp_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
+}
+
+template <int BLOCK_N>
+static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  if (make_operand_map(&tmA, A, p.M, p.K, p.G0, p.G1, BLOCK_M)) return 1;
+  if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, BLOCK_N)) return 1;
+  p.n_blocks = (int)ceil_div(p.N, BLOCK_N);
+  EpiMaps em;
+  plan_epilogue(p, em, Cfg::STAGE_BYTES);
+  const int stages = p.stages;
   const int smem_bytes = stages * Cfg::STAGE_BYTES + 4 * p.epi_warp_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -658,6 +833,29 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   const long long total = (long long)p.m_blocks * p.n_blocks * p.G0 * p.G1;
   const int grid = (int)(total < num_sms() ? total : num_sms());
   gemm_bf16_kernel<BLOCK_N><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
+  TA_CHECK_LAUNCH();
+  return 0;
+}
+
+// 2-CTA (CTA pair) launch: 256 x 256 tiles, clusters of 2 along x
+static int launch_gemm2(const ta_operand* A, const ta_operand* B, GemmParams& p, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  if (make_operand_map(&tmA, A, p.M, p.K, p.G0, p.G1, BLOCK_M)) return 1;
+  if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, G2_B_HALF)) return 1;
+  p.n_blocks = (int)ceil_div(p.N, G2_BLOCK_N);
+  EpiMaps em;
+  plan_epilogue(p, em, G2_STAGE_BYTES);
+  const int smem_bytes = p.stages * G2_STAGE_BYTES + 4 * p.epi_warp_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TA_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));
+    attr_set = true;
+  }
+  const long long m_pairs = ceil_div(p.M, 2 * BLOCK_M);
+  const long long total = m_pairs * p.n_blocks * p.G0 * p.G1;
+  const long long max_clusters = num_sms() / 2;
+  const int clusters = (int)(total < max_clusters ? total : max_clusters);
+  gemm2_bf16_kernel<<<2 * clusters, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -693,6 +891,10 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   p.vec_aux = al(p.aux, p.ld_aux, p.aux_gs0, p.aux_gs1, 8, 16);
   p.vec_bias = al(p.bias, 4, p.bias_gs0, p.bias_gs1, 4, 16);
   { static const int dbg = env_int("TA_GEMM_DEBUG", 0); p.debug = dbg; }
+  {
+    static const int force_mm = env_int("TA_GEMM_M_MAJOR", -1);
+    p.m_major = force_mm >= 0 ? force_mm : ((long long)G0 * G1 >= 16 && p.k_blocks == 1 && p.m_blocks > 1);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tile width: the widest UMMA N that still yields about a wave of tiles
   const long long groups = (long long)G0 * G1;
@@ -704,6 +906,11 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   else if (N <= 128) bn = 128;
   else if (tiles(256) < num_sms() && tiles(128) > tiles(256)) bn = 128;
   if (bn == 128 && N > 64 && tiles(128) < num_sms() / 2 && tiles(64) > tiles(128)) bn = 64;
+  // CTA pairs (256 x 256 tiles, B split across the pair) for the large problems: a third less L2 -> smem traffic
+  static const int use_2cta = env_int("TA_GEMM_2CTA", 1);
+  if (use_2cta && bn == 256 && M >= 256 && N >= 256 && K >= 256 &&
+      groups * ceil_div(M, 2 * BLOCK_M) * ceil_div(N, 256) >= num_sms() / 4)
+    return launch_gemm2(A, B, p, st);
   if (bn == 256) return launch_gemm<256>(A, B, p, st);
   if (bn == 128) return launch_gemm<128>(A, B, p, st);
   return launch_gemm<64>(A, B, p, st);
