@@ -95,11 +95,14 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int t
 //   tmem_empty0 address of tmem_empty_bar[0] of the CTA whose issuer warp waits on it: the own CTA's (m_off == 0, plain
 //               shared address) or the leader's through the cluster window (PAIR peer, m_off != 0)
 //   m_off       row offset of this CTA inside the tile (PAIR: rank * 128)
-template <int BLOCK_N, bool PAIR>
+template <int BLOCK_N, bool PAIR, int NW>
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps& em, uint32_t epi_smem, uint64_t* tmem_full_bar,
                                               uint32_t tmem_empty0, uint64_t (*epi_bar)[3], uint32_t tmem_base, int warp, int lane,
                                               int first_tile, int tile_stride, int total_tiles, int tiles_per_group, int m_off) {
-  const int quarter = warp & 3;
+  // NW = 4: one warp per TMEM lane quarter, all columns. NW = 8: two warps per quarter, each half of the columns.
+  const int quarter = warp & 3, ep = warp - 2;
+  constexpr int NCH_W = (BLOCK_N / 32) / (NW / 4);     // chunks per warp
+  const int c0 = (ep >> 2) * NCH_W;
   int local = 0;
   if (p.tma_epi) {
     // ---- TMA-staged epilogue. Per warp: nbf fp32 chunk buffers (SWIZZLE_128B) then nbb bf16 chunk buffers
@@ -111,9 +114,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
     const int dbg = p.debug, act = p.act;
     const float alpha = p.alpha;
     const bool aux_tanh = p.aux_mode == TA_AUX_TANH_BWD;
-    const uint32_t wbase = epi_smem + (warp - 2) * p.epi_warp_bytes;
+    const uint32_t wbase = epi_smem + ep * p.epi_warp_bytes;
     const uint32_t fbuf0 = wbase, bbuf0 = wbase + p.nbf * EPI_F32_BYTES;
-    const uint32_t lbar0 = smem_u32(&epi_bar[warp - 2][0]);
+    const uint32_t lbar0 = smem_u32(&epi_bar[ep][0]);
     const uint32_t frow = lane * 128, fsw = lane & 7;            // fp32 row offset, swizzle key
     const uint32_t brow = lane * 64, bsw = (lane >> 1) & 3;      // bf16 row offset, swizzle key
     uint32_t lphase = 0;    // bit b: parity the next wait on loaded buffer b uses
@@ -129,10 +132,11 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
       constexpr int NCH = BLOCK_N / 32;
       int nch = (p.N - n0 + 31) / 32;
       if (nch > NCH) nch = NCH;
-      int next_load = 0;
-      // residual / saved-activation chunk q of this tile -> loaded buffer q % nl
+      const int c1 = nch < c0 + NCH_W ? nch : c0 + NCH_W;   // this warp's chunks: [c0, c1)
+      int next_load = c0;
+      // residual / saved-activation chunk q of this tile -> loaded buffer (q - c0) % nl
       auto issue_load = [&](int q) {
-        const int b = q % nl;
+        const int b = (q - c0) % nl;
         const uint32_t bar = lbar0 + b * 8;
         if (has_res) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(EPI_F32_BYTES) : "memory");
@@ -142,10 +146,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
           tma_load_4d_u32(bbuf0 + b * EPI_BF16_BYTES, &em.aux, bar, n0 + q * 32, row0, g0, g1);
         }
       };
-      if (has_load && row0 < p.M) {
+      if (has_load && row0 < p.M && c0 < c1) {
         if (lane == 0) {
           bulk_wait_read<0>();     // every staging buffer of the previous tile has been read by its store
-          for (; next_load < nch && next_load < nl; ++next_load) issue_load(next_load);
+          for (; next_load < c1 && next_load < c0 + nl; ++next_load) issue_load(next_load);
         }
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -155,7 +159,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
       const float* bias = p.bias ? p.bias + g0 * p.bias_gs0 + g1 * p.bias_gs1 : nullptr;
       __nv_bfloat16* ob = p.bf16_direct ? p.out_bf16 + g0 * p.bf16_gs0 + g1 * p.bf16_gs1 + (long long)row * p.ld_bf16 : nullptr;
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      if (row0 >= p.M) {   // this warp's 32 rows lie entirely beyond M: nothing to store
+      if (row0 >= p.M || c0 >= c1) {   // this warp's rows lie beyond M or its columns beyond N: nothing to store
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR && m_off != 0) mbar_arrive_cluster(tmem_empty0 + 8 * acc); else mbar_arrive_a(tmem_empty0 + 8 * acc); }
@@ -164,10 +168,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
       // The chunk loop stays ROLLED: unrolled x8 the kernel was ~0.5 MB of SASS and the epilogue warps spent most of
       // their time in instruction-fetch stalls (ncu: stall_no_inst on nearly every line).
       uint32_t v[32];
-      tmem_ld_32x32(taddr_row, v);
-      int lb = 0;             // loaded buffer of this chunk (c % nl)
+      tmem_ld_32x32(taddr_row + c0 * 32, v);
+      int lb = 0;             // loaded buffer of this chunk ((c - c0) % nl)
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
+      for (int c = c0; c < c1; ++c) {
         {
           const int col0 = n0 + c * 32;
           const bool full = col0 + 32 <= p.N;
@@ -181,7 +185,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha;
-          if (c + 1 < nch) {   // v is dead: the next chunk's TMEM read overlaps the rest of this chunk
+          if (c + 1 < c1) {   // v is dead: the next chunk's TMEM read overlaps the rest of this chunk
             tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
           } else {
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp before the stores
@@ -216,7 +220,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (has_load) {
-              mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
+              mbar_wait(&epi_bar[ep][lb], (lphase >> lb) & 1);
               lphase ^= 1u << lb;
             }
             if (has_aux) {
@@ -270,7 +274,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
               }
             }
           } else if (has_load) {
-            mbar_wait(&epi_bar[warp - 2][lb], (lphase >> lb) & 1);
+            mbar_wait(&epi_bar[ep][lb], (lphase >> lb) & 1);
             lphase ^= 1u << lb;
           }
           if (dbg != 5) fence_proxy_async_smem();   // generic-proxy writes above -> visible to the TMA store
@@ -283,7 +287,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
             bulk_commit_group();
             bulk_wait_read<1>();      // the store of the previous chunk has drained its buffer
             if (has_load)
-              for (; next_load < nch && next_load <= c + nl - 1; ++next_load) issue_load(next_load);
+              for (; next_load < c1 && next_load <= c + nl - 1; ++next_load) issue_load(next_load);
           }
           ++sc;
           if (++lb == nl) lb = 0;
@@ -315,10 +319,11 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
     int nch = (p.N - n0 + 31) / 32;
     if (nch > NCH) nch = NCH;
     // rolled chunk loop (code size, see above); the TMEM read of chunk c+1 overlaps the processing of chunk c
+    const int c1 = nch < c0 + NCH_W ? nch : c0 + NCH_W;
     uint32_t v[32];
-    tmem_ld_32x32(taddr_row, v);
+    if (c0 < c1) tmem_ld_32x32(taddr_row + c0 * 32, v);
 #pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
+    for (int c = c0; c < c1; ++c) {
       {
         const int col0 = n0 + c * 32;
         const bool full = col0 + 32 <= p.N;
@@ -333,7 +338,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-        if (c + 1 < nch) tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
+        if (c + 1 < c1) tmem_ld_32x32(taddr_row + (c + 1) * 32, v);
         if (row_ok) {
           if (vb) {
 #pragma unroll
@@ -550,7 +555,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    gemm_epilogue<BLOCK_N, false>(p, em, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES, tmem_full_bar, smem_u32(&tmem_empty_bar[0]),
+    gemm_epilogue<BLOCK_N, false, 4>(p, em, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES, tmem_full_bar, smem_u32(&tmem_empty_bar[0]),
                                   epi_bar, tmem_base, warp, lane, blockIdx.x, gridDim.x, total_tiles, tiles_per_group, 0);
   }
 
@@ -567,12 +572,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //   leader (rank 0): producer, UMMA issuer, epilogue        peer (rank 1): producer, epilogue
 //   full_bar[s]   (leader's): both CTAs' TMA loads complete_tx on it; the leader's producer expects 2 x STAGE bytes
 //   empty_bar[s], tmem_full_bar[a] (both CTAs): signalled by the leader's multicast tcgen05.commit
-//   tmem_empty_bar[a] (leader's): 8 arrivals, 4 epilogue warps of each CTA (the peer's arrive through the cluster window)
+//   tmem_empty_bar[a] (leader's): 16 arrivals, 8 epilogue warps of each CTA (the peer's arrive through the cluster window)
 constexpr int G2_BLOCK_N = 256;
 constexpr int G2_B_HALF = G2_BLOCK_N / 2;
 constexpr int G2_STAGE_BYTES = A_STAGE_BYTES + G2_B_HALF * BLOCK_K * 2;   // 32 KB per CTA
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+constexpr int GEMM2_THREADS = 320;   // producer, issuer, 8 epilogue warps (two per TMEM lane quarter)
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ EpiMaps em, const GemmParams p) {
   const int STAGES = p.stages;
@@ -581,7 +588,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ __align__(8) uint64_t epi_bar[4][3];
+  __shared__ __align__(8) uint64_t epi_bar[8][3];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -598,9 +605,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 8);
+      mbar_init(&tmem_empty_bar[s], 16);
     }
-    for (int s = 0; s < 12; ++s) mbar_init(&epi_bar[0][0] + s, 1);
+    for (int s = 0; s < 24; ++s) mbar_init(&epi_bar[0][0] + s, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -689,7 +696,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, their own 128 rows)
     // the leader's warps arrive on their own barrier (CTA scope), the peer's through the cluster window
-    gemm_epilogue<G2_BLOCK_N, true>(p, em, smem_u32(smem) + STAGES * G2_STAGE_BYTES, tmem_full_bar,
+    gemm_epilogue<G2_BLOCK_N, true, 8>(p, em, smem_u32(smem) + STAGES * G2_STAGE_BYTES, tmem_full_bar,
                                     rank == 0 ? smem_u32(&tmem_empty_bar[0]) : mapa_u32(smem_u32(&tmem_empty_bar[0]), 0), epi_bar, tmem_base, warp, lane, first_tile,
                                     tile_stride, total_tiles, tiles_per_group, rank * BLOCK_M);
   }
@@ -780,7 +787,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 // Epilogue plan: which outputs go through TMA staging, how many staging buffers, and how many A/B ring stages are left.
-static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes) {
+static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes, int ep_warps) {
   static const int force_legacy = env_int("TA_GEMM_LEGACY_EPI", 0);
   static const int force_nl = env_int("TA_GEMM_NLOAD", 0);
   memset(&em, 0, sizeof(em));
@@ -798,17 +805,19 @@ static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes) {
     if (need_f) p.nbf = p.res ? 3 : 2;
     else if (need_b) p.nbb = p.aux ? 3 : 2;
     if (force_nl == 2 || force_nl == 3) { if (p.res) p.nbf = force_nl; if (p.aux) p.nbb = force_nl; }
-    auto epi_bytes = [&]() { return 4 * (p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES); };
+    auto epi_bytes = [&]() { return ep_warps * (p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES); };
+    // long K: the epilogue has slack, the A/B ring does not - two buffers (no residual prefetch distance of 2) are enough
+    if (!force_nl && p.nbf == 3 && p.k_blocks >= 32) p.nbf = 2;
     // keep the A/B ring at >= 4 stages when dropping the third (prefetch) buffer buys it
     if (!force_nl && p.nbf == 3 && (SMEM_LIMIT - epi_bytes()) / stage_bytes < 4 &&
-        (SMEM_LIMIT - 4 * 2 * EPI_F32_BYTES) / stage_bytes >= 4 && p.k_blocks >= 16)
+        (SMEM_LIMIT - ep_warps * 2 * EPI_F32_BYTES) / stage_bytes >= 4 && p.k_blocks >= 16)
       p.nbf = 2;
     p.epi_warp_bytes = p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES;
   } else {
     p.bf16_direct = 0;
     p.epi_warp_bytes = 0;
   }
-  int stages = (SMEM_LIMIT - 4 * p.epi_warp_bytes) / stage_bytes;
+  int stages = (SMEM_LIMIT - ep_warps * p.epi_warp_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
 }
@@ -821,7 +830,7 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, BLOCK_N)) return 1;
   p.n_blocks = (int)ceil_div(p.N, BLOCK_N);
   EpiMaps em;
-  plan_epilogue(p, em, Cfg::STAGE_BYTES);
+  plan_epilogue(p, em, Cfg::STAGE_BYTES, 4);
   const int stages = p.stages;
   const int smem_bytes = stages * Cfg::STAGE_BYTES + 4 * p.epi_warp_bytes + 1024;
   static bool attr_set = false;
@@ -844,8 +853,8 @@ static int launch_gemm2(const ta_operand* A, const ta_operand* B, GemmParams& p,
   if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, G2_B_HALF)) return 1;
   p.n_blocks = (int)ceil_div(p.N, G2_BLOCK_N);
   EpiMaps em;
-  plan_epilogue(p, em, G2_STAGE_BYTES);
-  const int smem_bytes = p.stages * G2_STAGE_BYTES + 4 * p.epi_warp_bytes + 1024;
+  plan_epilogue(p, em, G2_STAGE_BYTES, 8);
+  const int smem_bytes = p.stages * G2_STAGE_BYTES + 8 * p.epi_warp_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     TA_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));
@@ -855,7 +864,7 @@ static int launch_gemm2(const ta_operand* A, const ta_operand* B, GemmParams& p,
   const long long total = m_pairs * p.n_blocks * p.G0 * p.G1;
   const long long max_clusters = num_sms() / 2;
   const int clusters = (int)(total < max_clusters ? total : max_clusters);
-  gemm2_bf16_kernel<<<2 * clusters, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
+  gemm2_bf16_kernel<<<2 * clusters, GEMM2_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
   TA_CHECK_LAUNCH();
   return 0;
 }
