@@ -51,6 +51,18 @@ def peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback")
 
 
+def traffic_of_dominant_launch():
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/r01_roofline_traffic.json names the launch and its algorithmic bytes); None if the file is missing."""
+    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return {"bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"], "algorithmic_bytes": d["algorithmic_bytes"],
+            "launch": d["launch"], "tensor_pipe_active_pct": d.get("tensor_pipe_active_pct"), "source": d["source"]}
+
+
 # ------------------------------------------------------------------------------------------------ CPU side
 def cpu_oracle_run(cfg, batch, steps, warmup, lr=3e-4):
     """The reference algorithm on the host cores (oracle port): get_batch + forward + backward + AdamW per step.
@@ -362,7 +374,7 @@ def run_ours(args, cfg):
     flops_step = syn.train_flops_per_step(cfg, B)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05.mma + TMA, all nn.Linear fwd/bwd)",
                 "achieved": gemm_tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / pk["tc_sustained"], "traffic": None,
+                "frac": gemm_tflops / pk["tc_sustained"], "traffic": traffic_of_dominant_launch(),
                 "peak_source": f"{pk['source']} (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": gm[1], "gemm_ms_per_step": round(gm[0], 3), "gemm_share_of_step": round(gm[0] / tot_ms, 4),
                 "algorithmic_flops_per_step_gemm": gm[2],
