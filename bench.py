@@ -374,7 +374,8 @@ def run_ours(args, cfg):
     flops_step = syn.train_flops_per_step(cfg, B)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05.mma + TMA, all nn.Linear fwd/bwd)",
                 "achieved": gemm_tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / pk["tc_sustained"], "traffic": traffic_of_dominant_launch(),
+                "frac": gemm_tflops / pk["tc_sustained"], "traffic": (traffic_of_dominant_launch() or {}).get("bytes_per_launch"),
+                "traffic_detail": traffic_of_dominant_launch(),
                 "peak_source": f"{pk['source']} (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": gm[1], "gemm_ms_per_step": round(gm[0], 3), "gemm_share_of_step": round(gm[0] / tot_ms, 4),
                 "algorithmic_flops_per_step_gemm": gm[2],
