@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 1
+#define TA_ABI_VERSION 2
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -74,6 +74,18 @@ typedef struct ta_epilogue {
   int32_t _pad2;
   uint64_t dropout_seed;
 } ta_epilogue;
+
+/* Dropout (model.py:69, 91, 116, 151, 171). Masks are a pure function of (seed, coordinates): Philox4x32-7 keyed by the
+ * 64-bit seed of the call, one draw per 8 consecutive columns of a row (csrc/philox.cuh), so backward regenerates them.
+ * ta_dropout_set_step_counter registers a device counter whose value is mixed into every seed at kernel run time: a
+ * captured CUDA graph then draws fresh masks on every replay (the trainer increments the counter inside the graph).
+ * ta_dropout_bf16: dst = keep ? src / (1 - p) : 0 with the GEMM-epilogue mask of the same seed (backward of the three
+ * projection / feed-forward dropout sites). ta_dropout_attn_mask: the attention keep mask as bytes, for tests. */
+int32_t ta_dropout_set_step_counter(const uint64_t* device_counter);
+int32_t ta_dropout_bf16(const void* src, int64_t ld_src, int64_t gs_src, void* dst, int64_t ld_dst, int64_t gs_dst, int32_t G,
+                        int64_t rows, int32_t cols, float p, uint64_t seed, void* stream);
+int32_t ta_dropout_attn_mask(uint8_t* mask, int32_t n_src, int32_t G, int32_t B, int32_t H, int32_t T, float p, uint64_t seed,
+                             void* stream);
 
 int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_t M, int64_t N, int64_t K, int32_t G0,
                      int32_t G1, const ta_epilogue* ep, void* stream);

@@ -380,3 +380,96 @@ def test_attention_bwd(lib, G, B, T, H, hs, S):
     for s in range(S):
         ref = kvf[s].grad.view(G, B * T, 2 * C)
         assert (dkv[s].float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ dropout
+# The reference draws its dropout masks from torch's own Philox stream (nn.Dropout, model.py:69, 91, 116, 151, 171), which
+# cannot be reproduced outside torch; the kernels use their own counter-based Philox4x32-7 masks. Parity is therefore
+# checked against a reference that applies the SAME mask (read back through the mask kernels), plus the mask statistics.
+def test_dropout_mask_statistics(lib):
+    G, rows, cols, p = 3, 1000, 264, 0.2
+    src = torch.ones(G, rows, cols + 8, device="cuda", dtype=torch.bfloat16)[..., :cols]
+    dst = torch.full_like(src, float("nan"))
+    lib.dropout_bf16(src, dst, p, seed=1234)
+    keep = dst > 0
+    assert abs(keep.float().mean().item() - (1 - p)) < 5e-3                       # 792 k draws: sigma = 4.5e-4
+    assert torch.allclose(dst[keep].float(), torch.tensor(1 / (1 - p), device="cuda"), rtol=4e-3)   # bf16 rounding of 1.25
+    assert (dst[~keep] == 0).all()
+    dst2 = torch.empty_like(dst)
+    lib.dropout_bf16(src, dst2, p, seed=1234)
+    assert torch.equal(dst, dst2)                                                 # a pure function of (seed, coordinates)
+    lib.dropout_bf16(src, dst2, p, seed=1235)
+    assert (dst2 != dst).float().mean().item() > 0.2                              # another seed, another mask
+    # rows and groups are decorrelated
+    assert abs((keep[0] & keep[1]).float().mean().item() - (1 - p) ** 2) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K,g,outs", [(300, 200, 136, (2,), "f32"), (300, 264, 136, (), "both"), (4096, 1024, 512, (2,), "f32"),
+                                          (100, 72, 40, (), "legacy")])
+def test_gemm_epilogue_dropout(lib, M, N, K, g, outs):
+    torch.manual_seed(11)
+    dev, p, seed = "cuda", 0.25, 987654321
+    A = torch.randn(*g, M, _r8(K) + 8, device=dev).to(torch.bfloat16)[..., :K]
+    B = torch.randn(*g, N, _r8(K) + 8, device=dev).to(torch.bfloat16)[..., :K]
+    bias = torch.randn(*g, N, device=dev)
+    res = torch.randn(*g, M, N + 4, device=dev)[..., :N]
+    ldf = _r8(N) + (3 if outs == "legacy" else 4)          # N + 3: pitch not TMA-able -> direct-store path
+    of = torch.full((*g, M, ldf), float("nan"), device=dev)[..., :N]
+    ob = torch.zeros(*g, M, _r8(N) + 8, device=dev, dtype=torch.bfloat16)[..., :N] if outs == "both" else None
+    lib.gemm(A, B, bias=bias, act=lib.ACT_RELU, residual=res, out_f32=of, out_bf16=ob, dropout_p=p, dropout_seed=seed)
+    ones = torch.ones(max(1, len(g) and g[0]), M, _r8(N), device=dev, dtype=torch.bfloat16)[..., :N]
+    mask = torch.empty_like(ones)
+    lib.dropout_bf16(ones, mask, p, seed)                  # = keep / (1 - p), bf16
+    torch.cuda.synchronize()
+    keep = (mask > 0).float().view(*g, M, N)
+    ref = torch.relu(A.float() @ B.float().transpose(-1, -2) + bias[..., None, :]) * keep / (1 - p) + res
+    scale = ref.abs().max().item()
+    assert (of - ref).abs().max().item() <= 1e-4 * scale + 1e-5
+    if ob is not None:
+        assert (ob.float() - ref).abs().max().item() <= 8e-3 * scale + 1e-3
+    assert abs(keep.mean().item() - (1 - p)) < 2e-2
+
+
+@pytest.mark.parametrize("G,B,T,H,hs,S", [(2, 2, 256, 4, 64, 1), (1, 2, 256, 2, 64, 3), (1, 3, 100, 2, 16, 2), (2, 3, 64, 8, 32, 1)])
+def test_attention_dropout_fwd_bwd(lib, G, B, T, H, hs, S):
+    torch.manual_seed(12)
+    p, seed = 0.2, 55555
+    C = H * hs
+    q = torch.randn(G, B * T, C, device="cuda").to(torch.bfloat16)
+    kv = [torch.randn(G, B * T, H, 2 * hs, device="cuda").to(torch.bfloat16) for _ in range(S)]
+    d_o = torch.randn(G, B * T, C, device="cuda").to(torch.bfloat16)
+    o = torch.zeros(G, B * T, C, device="cuda", dtype=torch.bfloat16)
+    o_src = torch.zeros(S, G, B * T, C, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(S, G, B, H, T, device="cuda")
+    k_views = [t.view(G, B * T, 2 * C) for t in kv]
+    v_views = [t.view(G, B * T, 2 * C)[..., hs:] for t in kv]
+    lib.attention_fwd(q, k_views, v_views, o, lse, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs, o_src=o_src, dropout_p=p,
+                      dropout_seed=seed)
+    dq = torch.full_like(q, float("nan"))
+    dkv = [torch.full((G, B * T, 2 * C), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(S)]
+    lib.attention_bwd(q, k_views, v_views, o, d_o, lse, dq, dkv, [t[..., hs:] for t in dkv], B=B, T=T, H=H, hs=hs,
+                      head_stride_kv=2 * hs, o_src=o_src if S > 1 else None, dropout_p=p, dropout_seed=seed)
+    mask = torch.empty(S, G, B, H, T, T, device="cuda", dtype=torch.uint8)
+    lib.dropout_attn_mask(mask, S, G, B, H, T, p, seed)
+    torch.cuda.synchronize()
+    tril = torch.ones(T, T, dtype=torch.bool, device="cuda").tril()
+    assert abs(mask[..., tril].float().mean().item() - (1 - p)) < 1e-2
+    # reference with the same mask: softmax, THEN inverted dropout on the probabilities, THEN P V (model.py:67-72)
+    qf = q.float().requires_grad_(True)
+    kvf = [t.float().requires_grad_(True) for t in kv]
+    qh = qf.view(G, B, T, H, hs).permute(0, 1, 3, 2, 4)
+    outs = []
+    for s in range(S):
+        kh = kvf[s][..., :hs].reshape(G, B, T, H, hs).permute(0, 1, 3, 2, 4)
+        vh = kvf[s][..., hs:].reshape(G, B, T, H, hs).permute(0, 1, 3, 2, 4)
+        sc = (qh @ kh.transpose(-1, -2)) * hs ** -0.5
+        pr = torch.softmax(sc.masked_fill(~tril, float("-inf")), -1) * mask[s].float() / (1 - p)
+        outs.append((pr @ vh).permute(0, 1, 3, 2, 4).reshape(G, B * T, C))
+    ro = sum(outs)
+    ro.backward(d_o.float())
+    assert (o.float() - ro).abs().max().item() <= 2e-2 * ro.abs().max().item()
+    tol = 2.5e-2
+    assert (dq.float() - qf.grad).abs().max().item() <= tol * qf.grad.abs().max().item()
+    for s in range(S):
+        ref = kvf[s].grad.view(G, B * T, 2 * C)
+        assert (dkv[s].float() - ref).abs().max().item() <= tol * ref.abs().max().item()

@@ -24,6 +24,7 @@
 
 #include "../../include/tradeaid_b200.h"
 #include "common.cuh"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ta {
@@ -48,6 +49,10 @@ struct GradOut {
 struct AttnBwdParams {
   int T, B, H, G, hs, n_src, n_qt, total_work;
   long long* trace;   // TA_ATTN_TRACE=<device address> (dev only): clock64 stamps of CTA 0, 4 roles x 1024 slots
+  uint32_t drop_thresh;            // dropout on the probabilities: 16-bit lane threshold, 0 = off (philox.cuh)
+  float drop_scale;                // 1 / (1 - p)
+  unsigned long long drop_seed;
+  const unsigned long long* drop_step;
   int debug;   // TA_ATTN_DEBUG (dev only): 1 = no D/lse prologue loads, 2 = no read-out stores, 4 = no P/dS math
   float scale, scale_log2;
   const __nv_bfloat16* d_o;    // [G][B*T][ldo]
@@ -454,14 +459,25 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
           tc_fence_before();
           mbar_arrive_a(bb + 8 * (AB_S_EMPTY + hh));
           mbar_arrive_a(bb + 8 * (AB_DP_EMPTY + hh));
+          // dropout (model.py:69, 151): O = (P o M / (1-p)) V, so dV takes the dropped P~ = P o M / (1-p) and
+          // dS = P o (dP o M / (1-p) - D); the mask is regenerated from (seed, plane, row, column) as in the forward
+          uint32_t keep = 0xFFFFu;
+          if (p.drop_thresh) {
+            const unsigned long long sd = p.drop_seed + (p.drop_step ? *p.drop_step * 0x9E3779B97F4A7C15ull : 0ull);
+            const uint32_t plane = (uint32_t)it.s * (uint32_t)total + (uint32_t)it.work;
+            keep = dropout_keep8(sd, 1u, plane, (uint32_t)row, (uint32_t)(col_base >> 3), p.drop_thresh) |
+                   (dropout_keep8(sd, 1u, plane, (uint32_t)row, (uint32_t)(col_base >> 3) + 1, p.drop_thresh) << 8);
+          }
+          const float dsc = p.drop_scale;
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
             float p0 = ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - Lr);
             float p1 = ex2_approx(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
             p0 = e < nvalid ? p0 : 0.f;
             p1 = e + 1 < nvalid ? p1 : 0.f;
-            const float d0 = p0 * (__uint_as_float(dv[e]) - Dr), d1 = p1 * (__uint_as_float(dv[e + 1]) - Dr);
-            __nv_bfloat162 pv = __floats2bfloat162_rn(p0, p1), dh = __floats2bfloat162_rn(d0, d1);
+            const float m0 = (keep >> e) & 1u ? dsc : 0.f, m1 = (keep >> (e + 1)) & 1u ? dsc : 0.f;
+            const float d0 = p0 * (__uint_as_float(dv[e]) * m0 - Dr), d1 = p1 * (__uint_as_float(dv[e + 1]) * m1 - Dr);
+            __nv_bfloat162 pv = __floats2bfloat162_rn(p0 * m0, p1 * m1), dh = __floats2bfloat162_rn(d0, d1);
             pp[e / 2] = *reinterpret_cast<uint32_t*>(&pv);
             dd[e / 2] = *reinterpret_cast<uint32_t*>(&dh);
           }
@@ -538,13 +554,12 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
                                     const ta_attn_tensor* dq, const ta_attn_tensor* dk, const ta_attn_tensor* dv,
                                     int32_t G, int32_t B, int32_t T, int32_t H, int32_t hs, float dropout_p, uint64_t seed,
                                     void* stream) {
-  (void)seed;
   TA_CHECK_ARG(q && k && v && o_bf16 && do_bf16 && lse && dq && dk && dv, "ta_attention_bwd: null pointer");
   TA_CHECK_ARG(n_src >= 1 && n_src <= ATTB_MAX_SRC, "ta_attention_bwd: n_src must be in [1, %d]", ATTB_MAX_SRC);
   TA_CHECK_ARG(n_src == 1 || o_src_bf16, "ta_attention_bwd: per-source outputs are required when n_src > 1");
   TA_CHECK_ARG(hs >= 8 && hs <= 64 && hs % 8 == 0, "ta_attention_bwd: head_size %d not supported", hs);
   TA_CHECK_ARG(T >= 1 && T <= 256, "ta_attention_bwd: T = %d not supported in this build (T <= 256)", T);
-  TA_CHECK_ARG(dropout_p == 0.f, "ta_attention_bwd: attention dropout not implemented in this build");
+  TA_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "ta_attention_bwd: dropout_p must be in [0, 1)");
   TA_CHECK_ARG(ldo % 8 == 0 && o_gs % 8 == 0, "ta_attention_bwd: output strides must be multiples of 8");
   AttnBwdMaps maps;
   if (make_head_map(&maps.q, q, hs, H, T, B, G, 128)) return 1;
@@ -568,6 +583,10 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
   TA_CHECK_ARG(total < (1ll << 31), "attention grid too large");
   p.total_work = (int)total;
   { const char* e = getenv("TA_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
+  p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  p.drop_seed = seed;
+  p.drop_step = dropout_step_counter();
   { const char* e = getenv("TA_ATTN_TRACE"); p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   p.d_o = (const __nv_bfloat16*)do_bf16;
   p.o = (const __nv_bfloat16*)o_bf16;

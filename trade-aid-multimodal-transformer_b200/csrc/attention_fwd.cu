@@ -21,6 +21,7 @@
 
 #include "../../include/tradeaid_b200.h"
 #include "common.cuh"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ta {
@@ -42,6 +43,10 @@ struct AttnMaps {
 struct AttnFwdParams {
   int T, B, H, G, hs, n_src, n_qtiles, total_work;
   int debug;   // TA_ATTN_DEBUG (dev only): 16 = no TMEM source sum, 32 = no output staging / stores
+  uint32_t drop_thresh;            // dropout on the probabilities (model.py:69, 151): 16-bit lane threshold, 0 = off
+  float drop_scale;                // 1 / (1 - p)
+  unsigned long long drop_seed;
+  const unsigned long long* drop_step;
   float scale_log2;
   __nv_bfloat16* o;       // [G][B*T][ldo], head h at column h*hs
   long long ldo, o_gs;
@@ -401,7 +406,27 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
 #pragma unroll
         for (int e = 0; e < 16; ++e) pk[e] = 0u;
       }
-      l_run = l_run * alpha + psum;
+      l_run = l_run * alpha + psum;      // the softmax denominator is taken BEFORE dropout (model.py:68-69)
+      if (p.drop_thresh && need) {
+        // inverted dropout on the probabilities: the keep mask is a function of (seed, source / group / batch / head
+        // plane, query row, key column), regenerated by the backward kernel
+        const unsigned long long sd = p.drop_seed + (p.drop_step ? *p.drop_step * 0x9E3779B97F4A7C15ull : 0ull);
+        int w = it.work;
+        const uint32_t plane = (uint32_t)it.s * (uint32_t)total + (uint32_t)w;   // ((s*G + g)*B + b)*H + h
+        const __nv_bfloat162 sc2 = __floats2bfloat162_rn(p.drop_scale, p.drop_scale);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t m = dropout_keep8(sd, 1u, plane, (uint32_t)row, (uint32_t)(col_base >> 3) + i, p.drop_thresh);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 v2 = *reinterpret_cast<__nv_bfloat162*>(&pk[4 * i + e]);
+            v2 = __hmul2(v2, sc2);
+            uint32_t u = *reinterpret_cast<uint32_t*>(&v2);
+            u &= ((m >> (2 * e)) & 1u ? 0x0000FFFFu : 0u) | ((m >> (2 * e + 1)) & 1u ? 0xFFFF0000u : 0u);
+            pk[4 * i + e] = u;
+          }
+        }
+      }
       if (pend) epilogue();                  // previous segment: its last P V has had the exponentials above to finish
       // P -> smem (A operand of P V); the P V that last read this buffer (pair n - 2) must be complete
       mbar_wait(&p_empty[pb], ((it.n >> 1) & 1) ^ 1);
@@ -502,13 +527,12 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
                                     int32_t n_src, void* o_bf16, int64_t ldo, int64_t o_gs, void* o_src_bf16,
                                     int64_t o_src_stride, float* lse, int32_t G, int32_t B, int32_t T, int32_t H,
                                     int32_t hs, float dropout_p, uint64_t seed, void* stream) {
-  (void)seed;
   TA_CHECK_ARG(q && k && v && o_bf16 && lse, "ta_attention_fwd: null pointer");
   TA_CHECK_ARG(n_src >= 1 && n_src <= ATT_MAX_SRC, "ta_attention_fwd: n_src must be in [1, %d]", ATT_MAX_SRC);
   TA_CHECK_ARG(hs >= 8 && hs <= 64 && hs % 8 == 0, "ta_attention_fwd: head_size %d not supported (8..64, multiple of 8)", hs);
   TA_CHECK_ARG(G > 0 && B > 0 && T > 0 && H > 0, "ta_attention_fwd: non-positive size");
   TA_CHECK_ARG(ldo % 8 == 0 && o_gs % 8 == 0 && (reinterpret_cast<uintptr_t>(o_bf16) & 15) == 0, "ta_attention_fwd: output alignment");
-  TA_CHECK_ARG(dropout_p == 0.f, "ta_attention_fwd: attention dropout not implemented in this build");
+  TA_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "ta_attention_fwd: dropout_p must be in [0, 1)");
   AttnMaps maps;
   if (make_head_map(&maps.q, q, hs, H, T, B, G, 128)) return 1;
   for (int s = 0; s < n_src; ++s) {
@@ -529,6 +553,10 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
   p.n_qtiles = (T + 127) / 128;
   p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)hs));
   { const char* e = getenv("TA_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
+  p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  p.drop_seed = seed;
+  p.drop_step = dropout_step_counter();
   p.o = (__nv_bfloat16*)o_bf16; p.ldo = ldo; p.o_gs = o_gs;
   p.o_src = (__nv_bfloat16*)o_src_bf16; p.o_src_stride = o_src_stride;
   p.lse = lse;

@@ -10,6 +10,7 @@ namespace ta {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static const unsigned long long* g_dropout_step = nullptr;   // device counter mixed into every dropout seed
 
 char* err_buf() { return g_err; }
 
@@ -22,6 +23,8 @@ int set_err(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+const unsigned long long* dropout_step_counter() { return g_dropout_step; }
 
 int num_sms() {
   static int cached[64] = {0};
@@ -40,6 +43,11 @@ int num_sms() {
 extern "C" {
 const char* ta_last_error(void) { return ta::err_buf(); }
 int32_t ta_abi_version(void) { return TA_ABI_VERSION; }
+
+int32_t ta_dropout_set_step_counter(const uint64_t* device_counter) {
+  ta::g_dropout_step = reinterpret_cast<const unsigned long long*>(device_counter);
+  return 0;
+}
 int64_t ta_launch_count(void) { return ta::g_launches.load(std::memory_order_relaxed); }
 void ta_reset_launch_count(void) { ta::g_launches.store(0, std::memory_order_relaxed); }
 }

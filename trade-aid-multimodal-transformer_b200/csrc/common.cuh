@@ -32,6 +32,7 @@ void count_launch(int n = 1);
   } while (0)
 
 int num_sms();
+const unsigned long long* dropout_step_counter();   // see ta_dropout_set_step_counter
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -15,6 +15,7 @@
 
 #include "../../include/tradeaid_b200.h"
 #include "common.cuh"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ta {
@@ -58,6 +59,10 @@ struct GemmParams {
   int bf16_direct;     // tma_epi with both outputs: bf16 goes out with row-per-thread stores
   int epi_warp_bytes;
   int m_major;         // tile order, see decode_tile
+  uint32_t drop_thresh;     // 16-bit lane threshold of the epilogue dropout (0 = off), see philox.cuh
+  float drop_scale;         // 1 / (1 - p)
+  unsigned long long drop_seed;
+  const unsigned long long* drop_step;
   int debug;           // TA_GEMM_DEBUG (dev only): 1 = skip global stores, 2 = skip the epilogue math and stores
 };
 
@@ -219,6 +224,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             }
+            if (p.drop_thresh) {   // inverted dropout on act(acc + bias), before the residual add (model.py:91, 116, 171)
+              const unsigned long long sd = p.drop_seed + (p.drop_step ? *p.drop_step * 0x9E3779B97F4A7C15ull : 0ull);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t m = dropout_keep8(sd, 0u, (uint32_t)g, (uint32_t)row, (uint32_t)(col0 >> 3) + i, p.drop_thresh);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[8 * i + e] = (m >> e) & 1u ? f[8 * i + e] * p.drop_scale : 0.f;
+              }
+            }
             if (has_load) {
               mbar_wait(&epi_bar[ep][lb], (lphase >> lb) & 1);
               lphase ^= 1u << lb;
@@ -361,6 +375,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
           } else if (p.act == TA_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (p.drop_thresh) {   // inverted dropout on act(acc + bias), before the residual add (model.py:91, 116, 171)
+            const unsigned long long sd = p.drop_seed + (p.drop_step ? *p.drop_step * 0x9E3779B97F4A7C15ull : 0ull);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t m = dropout_keep8(sd, 0u, (uint32_t)g, (uint32_t)row, (uint32_t)(col0 >> 3) + i, p.drop_thresh);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[8 * i + e] = (m >> e) & 1u ? f[8 * i + e] * p.drop_scale : 0.f;
+            }
           }
           if (aux) {
             if (full && p.vec_aux) {
@@ -878,7 +901,7 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   TA_CHECK_ARG(M > 0 && N > 0 && K > 0 && G0 > 0 && G1 > 0, "ta_gemm_bf16: non-positive shape");
   TA_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "ta_gemm_bf16: shape too large");
   TA_CHECK_ARG(ep->out_f32 || ep->out_bf16, "ta_gemm_bf16: no output");
-  TA_CHECK_ARG(ep->dropout_p == 0.f, "ta_gemm_bf16: epilogue dropout not implemented in this build");
+  TA_CHECK_ARG(ep->dropout_p >= 0.f && ep->dropout_p < 1.f, "ta_gemm_bf16: dropout_p must be in [0, 1)");
   TA_CHECK_ARG(!ep->aux || ep->aux_mode != TA_AUX_NONE, "ta_gemm_bf16: aux given without aux_mode");
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.G0 = G0; p.G1 = G1;
@@ -900,6 +923,10 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   p.vec_aux = al(p.aux, p.ld_aux, p.aux_gs0, p.aux_gs1, 8, 16);
   p.vec_bias = al(p.bias, 4, p.bias_gs0, p.bias_gs1, 4, 16);
   { static const int dbg = env_int("TA_GEMM_DEBUG", 0); p.debug = dbg; }
+  p.drop_thresh = ep->dropout_p > 0.f ? dropout_thresh16(ep->dropout_p) : 0u;
+  p.drop_scale = ep->dropout_p > 0.f ? 1.f / (1.f - ep->dropout_p) : 1.f;
+  p.drop_seed = ep->dropout_seed;
+  p.drop_step = dropout_step_counter();
   {
     static const int force_mm = env_int("TA_GEMM_M_MAJOR", -1);
     p.m_major = force_mm >= 0 ? force_mm : ((long long)G0 * G1 >= 16 && p.k_blocks == 1 && p.m_blocks > 1);

@@ -6,6 +6,7 @@
 
 #include "../../include/tradeaid_b200.h"
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace ta {
 
@@ -515,6 +516,44 @@ static int grid_for(long long work_items, int per_block, int max_blocks_per_sm =
   return (int)b;
 }
 
+
+// ------------------------------------------------------------------------------------------------ dropout helpers
+// dst[g, r, c] = keep(seed; plane g, row r, col c) ? src[g, r, c] / (1 - p) : 0 — the mask of the GEMM epilogue with the
+// same seed, applied to the upstream gradient in backward (model.py:91, 116, 171). One thread per 8 columns.
+__global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, long long gs_src,
+                                    __nv_bfloat16* __restrict__ dst, long long ld_dst, long long gs_dst, long long rows, int cols,
+                                    unsigned thresh, float scale, unsigned long long seed, const unsigned long long* step) {
+  const int c8n = (cols + 7) >> 3;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (idx >= rows * c8n) return;
+  const long long row = idx / c8n;
+  const int c8 = (int)(idx - row * c8n);
+  const unsigned long long sd = seed + (step ? *step * 0x9E3779B97F4A7C15ull : 0ull);
+  const unsigned m = dropout_keep8(sd, 0u, (unsigned)g, (unsigned)row, (unsigned)c8, thresh);
+  const __nv_bfloat16* s = src + (long long)g * gs_src + row * ld_src + c8 * 8;
+  __nv_bfloat16* d = dst + (long long)g * gs_dst + row * ld_dst + c8 * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (c8 * 8 + e < cols) d[e] = (m >> e) & 1u ? __float2bfloat16_rn(__bfloat162float(s[e]) * scale) : __float2bfloat16_rn(0.f);
+}
+
+// attention keep mask as bytes [n_src][G][B][H][T][T] (tests): plane = ((s*G + g)*B + b)*H + h, kind 1
+__global__ void dropout_attn_mask_kernel(uint8_t* __restrict__ mask, long long planes, int T, unsigned thresh, unsigned long long seed,
+                                         const unsigned long long* step) {
+  const int c8n = (T + 7) >> 3;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= planes * T * c8n) return;
+  const int c8 = (int)(idx % c8n);
+  const long long pr = idx / c8n;
+  const int row = (int)(pr % T);
+  const long long plane = pr / T;
+  const unsigned long long sd = seed + (step ? *step * 0x9E3779B97F4A7C15ull : 0ull);
+  const unsigned m = dropout_keep8(sd, 1u, (unsigned)plane, (unsigned)row, (unsigned)c8, thresh);
+  for (int e = 0; e < 8; ++e)
+    if (c8 * 8 + e < T) mask[(plane * T + row) * T + c8 * 8 + e] = (m >> e) & 1u;
+}
+
 }  // namespace ta
 
 using namespace ta;
@@ -551,6 +590,30 @@ int32_t ta_embed_bwd(const int64_t* idx, const float* dx, const int64_t* voff, i
   dim3 grid(max_vocab, M);
   embed_bwd_tok_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)idx, dx, (const long long*)voff, dtok,
                                                                (long long)B * T, C);
+  TA_CHECK_LAUNCH();
+  return 0;
+}
+
+int32_t ta_dropout_bf16(const void* src, int64_t ld_src, int64_t gs_src, void* dst, int64_t ld_dst, int64_t gs_dst, int32_t G,
+                        int64_t rows, int32_t cols, float p, uint64_t seed, void* stream) {
+  TA_CHECK_ARG(src && dst && G > 0 && rows > 0 && cols > 0, "ta_dropout_bf16: bad arguments");
+  TA_CHECK_ARG(p >= 0.f && p < 1.f, "ta_dropout_bf16: p must be in [0, 1)");
+  const long long n = rows * ((cols + 7) / 8);
+  dim3 grid((unsigned)ceil_div(n, 256), (unsigned)G);
+  dropout_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, ld_src, gs_src, (__nv_bfloat16*)dst, ld_dst,
+                                                            gs_dst, rows, cols, dropout_thresh16(p), 1.f / (1.f - p), seed,
+                                                            dropout_step_counter());
+  TA_CHECK_LAUNCH();
+  return 0;
+}
+
+int32_t ta_dropout_attn_mask(uint8_t* mask, int32_t n_src, int32_t G, int32_t B, int32_t H, int32_t T, float p, uint64_t seed,
+                             void* stream) {
+  TA_CHECK_ARG(mask && n_src > 0 && G > 0 && B > 0 && H > 0 && T > 0, "ta_dropout_attn_mask: bad arguments");
+  const long long planes = (long long)n_src * G * B * H;
+  const long long n = planes * T * ((T + 7) / 8);
+  dropout_attn_mask_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, planes, T, dropout_thresh16(p), seed,
+                                                                                         dropout_step_counter());
   TA_CHECK_LAUNCH();
   return 0;
 }

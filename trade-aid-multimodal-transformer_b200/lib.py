@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtradeaid_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class TaOperand(C.Structure):
@@ -108,7 +108,7 @@ def _operand(t, major):
 
 
 def gemm(A, B, *, a_major=0, b_major=0, out_f32=None, out_bf16=None, bias=None, act=ACT_NONE, aux=None,
-         aux_mode=AUX_NONE, residual=None, alpha=1.0):
+         aux_mode=AUX_NONE, residual=None, alpha=1.0, dropout_p=0.0, dropout_seed=0):
     """D[g] = epi(alpha * A[g] @ B[g]^T). Tensors are [..groups.., rows, cols] views (up to two group dims, inner
     stride 1). For a_major/b_major = 1 the stored matrix is [K, M] / [K, N]."""
     K = A.shape[-1] if a_major == 0 else A.shape[-2]
@@ -121,6 +121,8 @@ def gemm(A, B, *, a_major=0, b_major=0, out_f32=None, out_bf16=None, bias=None, 
     ep = TaEpilogue()
     ep.alpha = alpha
     ep.act = act
+    ep.dropout_p = float(dropout_p)
+    ep.dropout_seed = int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
     if bias is not None:
         assert bias.dtype.is_floating_point and bias.element_size() == 4 and bias.shape[-1] == N
         s0, s1, g0, g1 = _grp(bias, 1)
@@ -168,7 +170,8 @@ def _attn_tensor(t, head_stride):
     return TaAttnTensor(t.data_ptr(), t.stride(-2), head_stride, gs)
 
 
-def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None, o_src=None):
+def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None, o_src=None, dropout_p=0.0,
+                  dropout_seed=0):
     """q: [G, B*T, *]; ks/vs: lists (one per source) of [G, B*T, *] views; o: [G, B*T, H*hs] bf16;
     lse: fp32 [n_src, G, B, H, T]; o_src: optional [n_src, G, B*T, H*hs] bf16."""
     n_src = len(ks)
@@ -183,8 +186,8 @@ def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_st
     if o_src is not None:
         assert o_src.stride(-2) == o.stride(-2) and (o.dim() < 3 or o_src.stride(1) == o.stride(0))
     _check(_lib.ta_attention_fwd(qa, ka, va, n_src, _ptr(o), o.stride(-2), o_gs, _ptr(o_src),
-                                 o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, 0.0, 0,
-                                 _stream()))
+                                 o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, float(dropout_p),
+                                 int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
 
 
 # ---------------------------------------------------------------------------------------------------- row ops
@@ -210,6 +213,31 @@ _unpad = _sig("ta_unpad_f32", _P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I32, 
 _cast = _sig("ta_cast_bf16", _P, _P, _I64, _P)
 _adamw_tick = _sig("ta_adamw_tick", _P, _P, _F64, _F64, _F64, _F64, _P)
 _adamw_step = _sig("ta_adamw_step", _P, _P, _P, _P, _P, _I64, _P, _F32, _F32, _F32, _F32, _P)
+
+
+_drop_set = _sig("ta_dropout_set_step_counter", _P)
+_drop_bf16 = _sig("ta_dropout_bf16", _P, _I64, _I64, _P, _I64, _I64, _I32, _I64, _I32, _F32, _U64, _P)
+_drop_attn_mask = _sig("ta_dropout_attn_mask", _P, _I32, _I32, _I32, _I32, _I32, _F32, _U64, _P)
+
+
+def dropout_set_step_counter(counter):
+    """counter: int64/uint64 device tensor with one element (or None): its value is mixed into every dropout seed when the
+    kernels RUN, so CUDA-graph replays draw fresh masks as long as the graph increments it."""
+    _check(_drop_set(_ptr(counter)))
+
+
+def dropout_bf16(src, dst, p, seed):
+    """dst = keep ? src / (1 - p) : 0 with the GEMM-epilogue mask of `seed`; src/dst bf16 [G, rows, cols] views."""
+    assert src.dim() == 3 and dst.shape == src.shape and src.stride(-1) == 1 and dst.stride(-1) == 1
+    G, rows, cols = src.shape
+    _check(_drop_bf16(_ptr(src), src.stride(1), src.stride(0), _ptr(dst), dst.stride(1), dst.stride(0), G, rows, cols, float(p),
+                      int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
+
+
+def dropout_attn_mask(mask, n_src, G, B, H, T, p, seed):
+    """mask: uint8 [n_src, G, B, H, T, T] contiguous; the keep mask the attention kernels use for `seed` (tests)."""
+    assert mask.is_contiguous() and mask.numel() == n_src * G * B * H * T * T
+    _check(_drop_attn_mask(_ptr(mask), n_src, G, B, H, T, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
 
 
 def gather_batch(store, ix, T, xb, yb):
@@ -322,7 +350,7 @@ _lib.ta_attention_bwd.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTenso
 
 
 def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None,
-                  o_src=None):
+                  o_src=None, dropout_p=0.0, dropout_seed=0):
     """Gradients of attention_fwd. d_o has the layout of o; dq of q; dks[s]/dvs[s] of ks[s]/vs[s] (bf16)."""
     n_src = len(ks)
     G = q.shape[0] if q.dim() == 3 else 1
@@ -338,5 +366,5 @@ def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_str
     o_gs = o.stride(0) if o.dim() == 3 else 0
     assert o.dim() < 3 or d_o.stride(0) == o.stride(0)
     _check(_lib.ta_attention_bwd(qa, ka, va, n_src, _ptr(o), _ptr(o_src), o_src.stride(0) if o_src is not None else 0,
-                                 _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), dqa, dka, dva, G, B, T, H, hs, 0.0, 0,
-                                 _stream()))
+                                 _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), dqa, dka, dva, G, B, T, H, hs, float(dropout_p),
+                                 int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
