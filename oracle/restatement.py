@@ -80,13 +80,18 @@ def pack_cross_attention(sd, cfg, l, i, dtype=torch.float32):
 
 
 # --------------------------------------------------------------------------------------------- forward
-def _causal_attention(q, k, v):
-    """softmax(mask(q k^T * hs^-0.5)) v for [B, H, T, hs] tensors (model.py:65-72 and :147-154)."""
+def _causal_attention(q, k, v, drop=None):
+    """softmax(mask(q k^T * hs^-0.5)) v for [B, H, T, hs] tensors (model.py:65-72 and :147-154). `drop`: optional
+    [B, H, T, T] multiplier (keep / (1 - p)) applied to the probabilities, i.e. nn.Dropout with a given mask
+    (model.py:69, 151)."""
     T = q.shape[-2]
     aff = q @ k.transpose(-2, -1) * (k.shape[-1] ** -0.5)
     mask = torch.ones(T, T, dtype=torch.bool, device=q.device).tril()
     aff = aff.masked_fill(~mask, float("-inf"))
-    return F.softmax(aff, dim=-1) @ v
+    wei = F.softmax(aff, dim=-1)
+    if drop is not None:
+        wei = wei * drop
+    return wei @ v
 
 
 def _ln(x, sd, key):
@@ -99,8 +104,10 @@ def _proj_mlp(o, sd, p, dtype):
     return h @ sd[f"{p}.proj.2.weight"].to(dtype).T + sd[f"{p}.proj.2.bias"].to(dtype)
 
 
-def forward(sd, cfg: Cfg, idx_list, targets_list=None, dtype=torch.float32, return_hidden=False):
-    """Restates MultimodalTransformer.forward (model.py:380-402) with dropout = 0 (eval mode / p = 0).
+def forward(sd, cfg: Cfg, idx_list, targets_list=None, dtype=torch.float32, return_hidden=False, masks=None):
+    """Restates MultimodalTransformer.forward (model.py:380-402). Dropout: off (eval mode / p = 0) unless `masks` gives the
+    multipliers keep / (1 - p) of the five nn.Dropout sites explicitly (the reference draws them from torch's RNG stream):
+    ("sa_attn", l, i) and ("ca_attn", l, i, s): [B, H, T, T]; ("sa_proj", l, i), ("ffn", l, i), ("ca_proj", l, i): [B, T, C].
 
     sd: state dict with the reference's keys. Returns (logits_list, losses_list | None)."""
     M, C, H, hs, h2 = cfg.M, cfg.n_embd, cfg.n_head, cfg.hs, cfg.h2
@@ -119,11 +126,14 @@ def forward(sd, cfg: Cfg, idx_list, targets_list=None, dtype=torch.float32, retu
             W1, b1, W2 = pack_self_attention(sd, cfg, l, i, dtype)
             hid = torch.tanh(_ln(x, sd, f"blocks.{l}.ln1_layers.{i}") @ W1.T + b1).view(B, T, 3, H, h2)
             qkv = torch.einsum("btnhr,nhdr->nbhtd", hid, W2)  # [3, B, H, T, hs]
-            o = _causal_attention(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(B, T, C)  # head-major concat
-            x = x + _proj_mlp(o, sd, f"blocks.{l}.sa_layers.{i}", dtype)
+            mk = masks or {}
+            o = _causal_attention(qkv[0], qkv[1], qkv[2], mk.get(("sa_attn", l, i))).transpose(1, 2).reshape(B, T, C)  # head-major concat
+            pr = _proj_mlp(o, sd, f"blocks.{l}.sa_layers.{i}", dtype)
+            x = x + (pr * mk[("sa_proj", l, i)] if ("sa_proj", l, i) in mk else pr)
             p = f"blocks.{l}.ffwd_layers.{i}.net"
             hdn = torch.relu(_ln(x, sd, f"blocks.{l}.ln2_layers.{i}") @ sd[f"{p}.0.weight"].to(dtype).T + sd[f"{p}.0.bias"].to(dtype))
-            x = x + hdn @ sd[f"{p}.2.weight"].to(dtype).T + sd[f"{p}.2.bias"].to(dtype)
+            ff = hdn @ sd[f"{p}.2.weight"].to(dtype).T + sd[f"{p}.2.bias"].to(dtype)
+            x = x + (ff * mk[("ffn", l, i)] if ("ffn", l, i) in mk else ff)
             att.append(x)
         new = []
         for i in range(M):
@@ -135,9 +145,10 @@ def forward(sd, cfg: Cfg, idx_list, targets_list=None, dtype=torch.float32, retu
                 o = 0
                 for s, j in enumerate(cfg.others(i)):
                     kv = torch.einsum("btc,hdc->bhtd", att[j], Wkv[s])  # un-normalised stream of source j
-                    o = o + _causal_attention(q, kv[..., :hs], kv[..., hs:])
+                    o = o + _causal_attention(q, kv[..., :hs], kv[..., hs:], (masks or {}).get(("ca_attn", l, i, s)))
                 o = o.transpose(1, 2).reshape(B, T, C)
-                x = x + _proj_mlp(o, sd, f"blocks.{l}.cross_attention_layers.{i}", dtype)
+                pr = _proj_mlp(o, sd, f"blocks.{l}.cross_attention_layers.{i}", dtype)
+                x = x + (pr * masks[("ca_proj", l, i)] if masks and ("ca_proj", l, i) in masks else pr)
             new.append(x)
         xs = new
     logits_list = []
@@ -156,10 +167,10 @@ def forward(sd, cfg: Cfg, idx_list, targets_list=None, dtype=torch.float32, retu
     return logits_list, losses
 
 
-def forward_backward(sd, cfg, idx_list, targets_list, dtype=torch.float32):
+def forward_backward(sd, cfg, idx_list, targets_list, dtype=torch.float32, masks=None):
     """Forward + autograd backward of sum(losses) (main.py:646-649). Returns (logits, losses, grads by key)."""
     params = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items() if not k.endswith(".tril")}
-    logits, losses = forward(params, cfg, idx_list, targets_list, dtype)
+    logits, losses = forward(params, cfg, idx_list, targets_list, dtype, masks=masks)
     sum(losses).backward()
     # parameters the forward never touches keep grad None (e.g. cross-attention modules of a single-modality model,
     # model.py:235-238) and torch.optim.AdamW skips them entirely — no weight decay either.

@@ -28,6 +28,14 @@ def _tick(n=1):
     _launches += n
 
 
+def dropout_set_step_counter(counter):
+    pass
+
+
+def dropout_bf16(src, dst, p, seed):
+    raise NotImplementedError("the CPU emulation covers dropout = 0 only (masks come from the CUDA Philox kernels)")
+
+
 def gemm(A, B, *, a_major=0, b_major=0, out_f32=None, out_bf16=None, bias=None, act=ACT_NONE, aux=None,
          aux_mode=AUX_NONE, residual=None, alpha=1.0):
     _tick()

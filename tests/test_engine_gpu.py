@@ -92,3 +92,82 @@ def test_against_oracle(M, cross, V, B, T, C, H, L):
     emu.backward()
     for a, b in zip(logits, elog):
         assert ((a.cpu() - b).norm() / b.norm()).item() <= 5e-3   # same rounding points, different summation order
+
+
+def _dropout_masks(eng, B, T, p):
+    """The keep / (1 - p) multipliers the engine's kernels used in its LAST training forward, read back through the mask
+    kernels (same seeds, same device step counter) and keyed like oracle.restatement.forward(masks=...)."""
+    from tradeaid_b200 import lib
+    d = eng.d
+    M, C, H, L = d.M, d.n_embd, d.n_head, d.n_layer
+    BT = B * T
+    masks = {}
+    ones = torch.ones(M, BT, C, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty_like(ones)
+    for l in range(L):
+        for site, key in ((eng.SITE_SA_PROJ, "sa_proj"), (eng.SITE_FFN, "ffn")):
+            lib.dropout_bf16(ones, out, p, eng._seed(site, l))
+            for i in range(M):
+                masks[(key, l, i)] = ((out[i] > 0).float() / (1 - p)).view(B, T, C).cpu()
+        am = torch.empty(1, M, B, H, T, T, device="cuda", dtype=torch.uint8)
+        lib.dropout_attn_mask(am, 1, M, B, H, T, p, eng._seed(eng.SITE_SA_ATTN, l))
+        for i in range(M):
+            masks[("sa_attn", l, i)] = (am[0, i].float() / (1 - p)).cpu()
+        if d.Xc:
+            K = M - 1
+            for xi, i in enumerate(d.xc):
+                cm = torch.empty(K, 1, B, H, T, T, device="cuda", dtype=torch.uint8)
+                lib.dropout_attn_mask(cm, K, 1, B, H, T, p, eng._seed(eng.SITE_CA_ATTN, l, xi))
+                for s in range(K):
+                    masks[("ca_attn", l, i, s)] = (cm[s, 0].float() / (1 - p)).cpu()
+            for view, pos in eng._sub(ones, d.xc):      # one GEMM launch per contiguous run of enabled modalities
+                n = view.shape[0]
+                lib.dropout_bf16(ones[:n], out[:n], p, eng._seed(eng.SITE_CA_PROJ, l, pos[0]))
+                for k, pp in enumerate(pos):
+                    masks[("ca_proj", l, d.xc[pp])] = ((out[k] > 0).float() / (1 - p)).view(B, T, C).cpu()
+    return masks
+
+
+@pytest.mark.parametrize("M,cross,V,B,T,C,H,L", [
+    (3, [True, False, True], [100, 64, 80], 2, 64, 128, 4, 2),
+    (2, [True, True], [120, 90], 1, 256, 128, 2, 1),
+])
+def test_training_step_with_dropout_against_oracle(M, cross, V, B, T, C, H, L):
+    """Dropout at the reference's five sites (model.py:69, 91, 116, 151, 171): the engine's forward/backward with p = 0.2
+    against the oracle given the SAME masks. (torch's own Philox stream cannot be reproduced, see csrc/philox.cuh.)"""
+    from oracle import restatement as R
+    from tradeaid_b200.engine import Engine
+    from tradeaid_b200.params import Dims
+    p = 0.2
+    cfg = R.Cfg(T, C, H, L, V, cross)
+    sd = R.random_state_dict(cfg, seed=4)
+    g = torch.Generator().manual_seed(6)
+    idx = [torch.randint(0, V[i], (B, T), generator=g) for i in range(M)]
+    tgt = [torch.randint(0, V[i], (B, T), generator=g) for i in range(M)]
+    eng = Engine(Dims(V, cross, T, C, H, L, dropout=p), "cuda")
+    nv = eng.layout.named_views(eng.master)
+    for k, v in sd.items():
+        nv[k].copy_(v)
+    logits, losses = eng.forward(torch.stack(idx).cuda(), torch.stack(tgt).cuda(), save=True, train=True)
+    eng.backward()
+    masks = _dropout_masks(eng, B, T, p)
+    ref_logits, ref_losses, ref_grads = R.forward_backward(sd, cfg, idx, tgt, masks=masks)
+    for a, b in zip(logits, ref_logits):
+        rel = (a.cpu() - b).norm() / b.norm()
+        assert rel <= 2e-2, rel
+    for a, b in zip(losses.cpu(), ref_losses):
+        assert abs(float(a) - float(b)) <= 3e-3 * abs(float(b))
+    gv = eng.layout.named_views(eng.grad)
+    num = den = 0.0
+    for k, ref in ref_grads.items():
+        num += float((gv[k].cpu() - ref).pow(2).sum())
+        den += float(ref.pow(2).sum())
+    assert (num / den) ** 0.5 <= 6e-2, (num / den) ** 0.5
+    # a second training forward draws different masks (device step counter), eval mode none at all
+    l1 = [x.clone() for x in logits]
+    logits2, _ = eng.forward(torch.stack(idx).cuda(), torch.stack(tgt).cuda(), save=True, train=True)
+    assert not torch.equal(logits2[0], l1[0])
+    e1, _ = eng.forward(torch.stack(idx).cuda(), None, save=False)
+    e1 = [x.clone() for x in e1]
+    e2, _ = eng.forward(torch.stack(idx).cuda(), None, save=False)
+    assert all(torch.equal(a, b) for a, b in zip(e1, e2))

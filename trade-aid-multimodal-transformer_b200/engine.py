@@ -60,6 +60,10 @@ class Engine:
         self._voff = torch.tensor(dims.voff, dtype=torch.int64, device=self.device)
         self._saved = None
         self.shadows_stale = True
+        # dropout (model.py:69, 91, 116, 151, 171): masks are a function of (seed, coordinates); `seed` is fixed per
+        # (site, layer), a device step counter mixed in by the kernels makes every step (and graph replay) different
+        self.dropout_base_seed = 0x5DEECE66D
+        self._drop_step = None
 
     # ------------------------------------------------------------------------------------------ weights
     def _make_padded(self):
@@ -118,11 +122,34 @@ class Engine:
         self._bufs.clear()
         self._saved = None
 
+    # ------------------------------------------------------------------------------------------ dropout
+    SITE_SA_ATTN, SITE_SA_PROJ, SITE_FFN, SITE_CA_ATTN, SITE_CA_PROJ = range(5)
+
+    def _seed(self, site, layer, sub=0):
+        """64-bit seed of one dropout site of one layer (splitmix64 of the coordinates)."""
+        z = (self.dropout_base_seed + 0x9E3779B97F4A7C15 * (1 + site + 8 * (layer + 1024 * sub))) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+    def next_dropout_step(self):
+        """Advance the device step counter the kernels mix into every dropout seed (call once per training forward;
+        a plain device op, so it can be captured in a CUDA graph)."""
+        if self._drop_step is None:
+            self._drop_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self.ops.dropout_set_step_counter(self._drop_step)
+        self._drop_step.add_(1)
+
     # ------------------------------------------------------------------------------------------ forward
-    def forward(self, idx, targets=None, save=True):
+    def forward(self, idx, targets=None, save=True, train=False):
         """idx, targets: int64 [M, B, T'] on the device (T' <= block_size). Returns (logits list of fp32 [B, T', V_i],
-        losses fp32 [M] or None). With save=True the activations needed by backward() are kept."""
+        losses fp32 [M] or None). With save=True the activations needed by backward() are kept. train=True applies
+        dropout (p = dims.dropout) at the reference's five sites; eval / p = 0 is the deterministic path."""
         d, ops, P = self.d, self.ops, self.P
+        pd = float(d.dropout) if train else 0.0
+        if pd > 0.0:
+            self.next_dropout_step()
+        S_ = self._seed
         if self.shadows_stale:
             self.refresh_shadows()
         M, C, H, hs, L = d.M, d.n_embd, d.n_head, d.hs, d.n_layer
@@ -133,7 +160,7 @@ class Engine:
             raise ValueError(f"sequence length {T} exceeds block_size {d.block_size}")
         BT = B * T
         bf, f32 = self.act_dtype, torch.float32
-        S = {"B": B, "T": T, "layers": [], "idx": idx}
+        S = {"B": B, "T": T, "layers": [], "idx": idx, "pd": pd}
 
         def nb(name, l, shape, dtype):
             return self.buf(f"{name}.{l}" if save else name, shape, dtype)
@@ -156,12 +183,14 @@ class Engine:
                      out_bf16=self._qkv_groups(qkv, BT))
             o = nb("o", l, (M, BT, C), bf)
             lse = nb("lse", l, (1, M, B, H, T), f32)
-            ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs)
+            ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
+                              **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l)} if pd > 0.0 else {}))
             # projection MLP + residual   model.py:82-91, 224
             p1 = nb("p1", l, (M, BT, C // 2), bf)
             ops.gemm(o, self.W("sa_pw1")[l], bias=P["sa_pb1"][l], act=ACT_TANH, out_bf16=p1)
             x1 = nb("x1", l, (M, BT, C), f32)
-            ops.gemm(p1, self.W("sa_pw2")[l], bias=P["sa_pb2"][l], residual=x, out_f32=x1)
+            ops.gemm(p1, self.W("sa_pw2")[l], bias=P["sa_pb2"][l], residual=x, out_f32=x1,
+                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_PROJ, l)} if pd > 0.0 else {}))
             # feed-forward + residual   model.py:167-172, 225
             hh = nb("h2", l, (M, BT, C), bf)
             st2 = nb("st2", l, (2, M * BT), f32)
@@ -170,12 +199,13 @@ class Engine:
             ops.gemm(hh, self.W("ff_w1")[l], bias=P["ff_b1"][l], act=ACT_RELU, out_bf16=ffh)
             x2 = nb("x2", l, (M, BT, C), f32)
             a_bf = nb("a_bf", l, (M, BT, C), bf) if d.Xc else None
-            ops.gemm(ffh, self.W("ff_w2")[l], bias=P["ff_b2"][l], residual=x1, out_f32=x2, out_bf16=a_bf)
+            ops.gemm(ffh, self.W("ff_w2")[l], bias=P["ff_b2"][l], residual=x1, out_f32=x2, out_bf16=a_bf,
+                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_FFN, l)} if pd > 0.0 else {}))
             Sl.update(h1=h1, st1=st1, hid=hid, qkv=qkv, o=o, lse=lse, p1=p1, x1=x1, h2=hh, st2=st2, ffh=ffh, x2=x2,
                       a_bf=a_bf)
             x = x2
             if d.Xc:
-                x = self._cross_forward(l, Sl, x2, a_bf, B, T, nb)
+                x = self._cross_forward(l, Sl, x2, a_bf, B, T, nb, pd)
             S["layers"].append(Sl)
         # output heads   model.py:339-352
         hf = nb("hf", 0, (M, BT, C), bf)
@@ -226,7 +256,7 @@ class Engine:
             pos += n
         return out
 
-    def _cross_forward(self, l, Sl, x2, a_bf, B, T, nb):
+    def _cross_forward(self, l, Sl, x2, a_bf, B, T, nb, pd=0.0):
         """Selective cross-attention of layer l (model.py:136-159, 229-242). Every enabled modality queries the SAME
         snapshot x2 of all other modalities, so all K/V projections are issued before any residual update."""
         d, ops, P = self.d, self.ops, self.P
@@ -258,13 +288,15 @@ class Engine:
         for xi, i in enumerate(d.xc):
             ks, vs = self._kv_views(kvs, i)
             ops.attention_fwd(qc[xi:xi + 1], ks, vs, oc[xi:xi + 1], lsec[xi], B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
-                              o_src=ocs[xi] if ocs is not None else None)
+                              o_src=ocs[xi] if ocs is not None else None,
+                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi)} if pd > 0.0 else {}))
         pc1 = nb("pc1", l, (Xc, BT, C // 2), bf)
         ops.gemm(oc, self.W("ca_pw1")[l], bias=P["ca_pb1"][l], act=ACT_TANH, out_bf16=pc1)
         x3 = nb("x3", l, (M, BT, C), f32)
         for (xv, pos), (ov, _) in zip(self._sub(x2, d.xc), self._sub(x3, d.xc)):
             p0, p1 = pos[0], pos[-1] + 1
-            ops.gemm(pc1[p0:p1], self.W("ca_pw2")[l][p0:p1], bias=P["ca_pb2"][l][p0:p1], residual=xv, out_f32=ov)
+            ops.gemm(pc1[p0:p1], self.W("ca_pw2")[l][p0:p1], bias=P["ca_pb2"][l][p0:p1], residual=xv, out_f32=ov,
+                     **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_PROJ, l, p0)} if pd > 0.0 else {}))
         for i in range(M):
             if i not in d.xc:
                 x3[i].copy_(x2[i])
@@ -295,6 +327,17 @@ class Engine:
         B, T = S["B"], S["T"]
         BT = B * T
         bf, f32 = self.act_dtype, torch.float32
+        pd = S.get("pd", 0.0)
+        # upstream gradient of a dropout site = stream gradient o keep / (1 - p), same mask as the forward epilogue
+        dxm = self.buf("dxm", (M, BT, C), bf) if pd > 0.0 else None
+
+        def masked(t, site, sub=0):
+            if pd == 0.0:
+                return t
+            out = dxm[:t.shape[0]]
+            ops.dropout_bf16(t, out, pd, self._seed(site, l, sub))
+            return out
+
         cs_ws = self.buf("cs_ws", (max(ops.colsum_workspace(BT, 4 * C, M), ops.colsum_workspace(BT, max(d.vocab_sizes), 1),
                                        ops.colsum_workspace(BT, 3 * H * h2p, M)),), f32)
         # the workspace depends on the launch shape: grouped launches (all modalities) and the per-modality launches
@@ -327,12 +370,13 @@ class Engine:
         for l in reversed(range(L)):
             Sl = S["layers"][l]
             if d.Xc:
-                self._cross_backward(l, Sl, dx, dxb, B, T, cs_ws, ln_ws)
+                self._cross_backward(l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd, dxm)
             # feed-forward
-            ops.gemm(dxb, Sl["ffh"], a_major=1, b_major=1, out_f32=G["ff_w2"][l])
-            ops.colsum(dxb, G["ff_b2"][l], cs_ws)
+            dy = masked(dxb, self.SITE_FFN)
+            ops.gemm(dy, Sl["ffh"], a_major=1, b_major=1, out_f32=G["ff_w2"][l])
+            ops.colsum(dy, G["ff_b2"][l], cs_ws)
             dffh = self.buf("dffh", (M, BT, 4 * C), bf)
-            ops.gemm(dxb, self.W("ff_w2")[l], b_major=1, aux=Sl["ffh"], aux_mode=AUX_RELU_BWD, out_bf16=dffh)
+            ops.gemm(dy, self.W("ff_w2")[l], b_major=1, aux=Sl["ffh"], aux_mode=AUX_RELU_BWD, out_bf16=dffh)
             ops.gemm(dffh, Sl["h2"], a_major=1, b_major=1, out_f32=G["ff_w1"][l])
             ops.colsum(dffh, G["ff_b1"][l], cs_ws)
             dh = self.buf("dh", (M, BT, C), bf)
@@ -340,10 +384,11 @@ class Engine:
             ops.layernorm_bwd(dh, Sl["x1"], self.P["ln2_w"][l], Sl["st2"][0], Sl["st2"][1], dx, dx, dxb, G["ln2_w"][l],
                               G["ln2_b"][l], ln_ws)
             # self-attention projection MLP
-            ops.gemm(dxb, Sl["p1"], a_major=1, b_major=1, out_f32=G["sa_pw2"][l])
-            ops.colsum(dxb, G["sa_pb2"][l], cs_ws)
+            dy = masked(dxb, self.SITE_SA_PROJ)
+            ops.gemm(dy, Sl["p1"], a_major=1, b_major=1, out_f32=G["sa_pw2"][l])
+            ops.colsum(dy, G["sa_pb2"][l], cs_ws)
             dp1 = self.buf("dp1", (M, BT, C // 2), bf)
-            ops.gemm(dxb, self.W("sa_pw2")[l], b_major=1, aux=Sl["p1"], aux_mode=AUX_TANH_BWD, out_bf16=dp1)
+            ops.gemm(dy, self.W("sa_pw2")[l], b_major=1, aux=Sl["p1"], aux_mode=AUX_TANH_BWD, out_bf16=dp1)
             ops.gemm(dp1, Sl["o"], a_major=1, b_major=1, out_f32=G["sa_pw1"][l])
             ops.colsum(dp1, G["sa_pb1"][l], cs_ws)
             do = self.buf("do", (M, BT, C), bf)
@@ -352,7 +397,8 @@ class Engine:
             qkv = Sl["qkv"]
             dqkv = self.buf("dqkv", (M, BT, 3 * C), bf)
             ops.attention_bwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], Sl["o"], do, Sl["lse"],
-                              dqkv[..., 0:C], [dqkv[..., C:2 * C]], [dqkv[..., 2 * C:3 * C]], B=B, T=T, H=H, hs=hs)
+                              dqkv[..., 0:C], [dqkv[..., C:2 * C]], [dqkv[..., 2 * C:3 * C]], B=B, T=T, H=H, hs=hs,
+                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_SA_ATTN, l)} if pd > 0.0 else {}))
             # q/k/v MLP stage 2 (block diagonal) and stage 1
             hidg, dqkvg = self._hid_groups(Sl["hid"], BT), self._qkv_groups(dqkv, BT)
             ops.gemm(dqkvg, hidg, a_major=1, b_major=1, out_f32=G["sa_w2"][l].reshape(M, 3 * H, hs, d.h2))
@@ -376,7 +422,7 @@ class Engine:
         if T < d.block_size:
             G["pos"][T:].zero_()
 
-    def _cross_backward(self, l, Sl, dx, dxb, B, T, cs_ws, ln_ws):
+    def _cross_backward(self, l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd=0.0, dxm=None):
         d, ops, G = self.d, self.ops, self.G
         M, C, H, hs, Xc = d.M, d.n_embd, d.n_head, d.hs, d.Xc
         BT = B * T
@@ -386,6 +432,10 @@ class Engine:
         dpc1 = self.buf("dpc1", (Xc, BT, C // 2), bf)
         for dv, pos in self._sub(dxb, d.xc):
             p0, p1 = pos[0], pos[-1] + 1
+            if pd > 0.0:   # same mask as the forward epilogue of this launch (seed keyed by layer and first position)
+                dvm = dxm[:dv.shape[0]]
+                ops.dropout_bf16(dv, dvm, pd, self._seed(self.SITE_CA_PROJ, l, p0))
+                dv = dvm
             ops.gemm(dv, Sl["pc1"][p0:p1], a_major=1, b_major=1, out_f32=G["ca_pw2"][l][p0:p1])
             ops.colsum(dv, G["ca_pb2"][l][p0:p1], cs_ws)
             ops.gemm(dv, self.W("ca_pw2")[l][p0:p1], b_major=1, aux=Sl["pc1"][p0:p1], aux_mode=AUX_TANH_BWD,
@@ -401,7 +451,8 @@ class Engine:
             dks, dvs = self._kv_views(dkvs, i)
             ops.attention_bwd(Sl["qc"][xi:xi + 1], ks, vs, Sl["oc"][xi:xi + 1], doc[xi:xi + 1], Sl["lsec"][xi],
                               dqc[xi:xi + 1], dks, dvs, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
-                              o_src=Sl["ocs"][xi] if Sl["ocs"] is not None else None)
+                              o_src=Sl["ocs"][xi] if Sl["ocs"] is not None else None,
+                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi)} if pd > 0.0 else {}))
         # query projection and its LayerNorm (input: the snapshot x2 of the querying modality)
         ops.gemm(dqc, Sl["hc"], a_major=1, b_major=1, out_f32=G["ca_wq"][l].reshape(Xc, C, C))
         dhc = self.buf("dhc", (Xc, BT, C), bf)

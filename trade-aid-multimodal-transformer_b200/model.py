@@ -53,7 +53,7 @@ class _Node(nn.Module):
 class _Bridge(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, model, idx, tgt):
-        logits, losses = model._engine.forward(idx, tgt, save=True)
+        logits, losses = model._engine.forward(idx, tgt, save=True, train=model.training)
         ctx.model = model
         return losses.clone()
 
@@ -179,10 +179,6 @@ class MultimodalTransformer(nn.Module):
 
     def forward(self, idx_list, targets_list=None):
         eng = self._require_engine()
-        if self.training and self._dims.dropout > 0.0 and os.environ.get("TRADEAID_B200_IGNORE_DROPOUT") != "1":
-            raise NotImplementedError(
-                f"dropout={self._dims.dropout} in training mode is not implemented by the sm_100a kernels of this build; "
-                "set dropout: 0.0 (or TRADEAID_B200_IGNORE_DROPOUT=1 to train without dropout)")
         M = self.num_modalities
         idx = torch.stack([t.to(eng.device, torch.int64) for t in idx_list[:M]]).contiguous()
         if self.training or getattr(self, "_dirty", True):
@@ -190,7 +186,7 @@ class MultimodalTransformer(nn.Module):
             self._dirty = False
         B, T = idx.shape[1], idx.shape[2]
         if targets_list is None:
-            logits, _ = eng.forward(idx, None, save=False)
+            logits, _ = eng.forward(idx, None, save=False, train=self.training)
             return [l.clone() for l in logits], None
         tgt = torch.stack([t.to(eng.device, torch.int64) for t in targets_list[:M]]).contiguous()
         if torch.is_grad_enabled():
@@ -198,7 +194,7 @@ class MultimodalTransformer(nn.Module):
             losses = _Bridge.apply(self._anchor, self, idx, tgt)
             logits = [l.view(B, T, -1).clone() for l in eng._saved["logits"]]
         else:
-            logits, losses = eng.forward(idx, tgt, save=False)
+            logits, losses = eng.forward(idx, tgt, save=False, train=self.training)
             logits, losses = [l.clone() for l in logits], losses.clone()
         return logits, [losses[i] for i in range(M)]
 

@@ -34,7 +34,7 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------ pieces
     def forward_backward(self, idx, tgt):
-        logits, losses = self.eng.forward(idx, tgt, save=True)
+        logits, losses = self.eng.forward(idx, tgt, save=True, train=True)
         self.eng.backward()
         return losses
 
