@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--config", default=os.environ.get("TRADEAID_BENCH_CONFIG", "c4"))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--rows", type=int, default=0, help="synthetic rows override")
+    ap.add_argument("--dropout", type=float, default=0.0, help="dropout probability of the training step (default 0: the parity configuration)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -117,7 +118,7 @@ def workload_config(args, cfg, batch, world):
     return {"workload": f"{args.config}: {cfg['note']}", "modalities": len(cfg["vocab"]), "cross_attention": cfg["cross"],
             "vocab": cfg["vocab"], "rows": args.rows or cfg["rows"], "n_embd": cfg["n_embd"], "n_head": cfg["n_head"],
             "n_layer": cfg["n_layer"], "block_size": cfg["block_size"], "batch_per_gpu": batch,
-            "global_batch": batch * world, "parallelism": f"dp{world}", "dropout": 0.0,
+            "global_batch": batch * world, "parallelism": f"dp{world}", "dropout": float(getattr(args, "dropout", 0.0)),
             "l2": "working set per step (activations + weights) exceeds the 126 MB L2 many times over"
                   if args.config in ("c3", "c4", "c5") else "inputs smaller than L2; a 256 MB buffer is written between steps"}
 
@@ -247,7 +248,7 @@ def run_ours(args, cfg):
     rows = args.rows or cfg["rows"]
 
     # ---- model, data, trainer
-    dims = Dims(V, cfg["cross"], T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"])
+    dims = Dims(V, cfg["cross"], T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"], dropout=args.dropout)
     eng = Engine(dims, dev)
     eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))   # same weights on every rank
     tr = Trainer(eng, lr=3e-4, process_group=pg, world_size=world)

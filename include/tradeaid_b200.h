@@ -77,8 +77,9 @@ typedef struct ta_epilogue {
 
 /* Dropout (model.py:69, 91, 116, 151, 171). Masks are a pure function of (seed, coordinates): Philox4x32-7 keyed by the
  * 64-bit seed of the call, one draw per 8 consecutive columns of a row (csrc/philox.cuh), so backward regenerates them.
- * ta_dropout_set_step_counter registers a device counter whose value is mixed into every seed at kernel run time: a
- * captured CUDA graph then draws fresh masks on every replay (the trainer increments the counter inside the graph).
+ * ta_dropout_set_step_counter registers a device counter (or NULL) that the FOLLOWING launches of the calling process
+ * capture in their parameters: its value is mixed into the seed when the kernel RUNS, so a captured CUDA graph draws
+ * fresh masks on every replay as long as the graph increments the counter. Bindings set it around each launch.
  * ta_dropout_bf16: dst = keep ? src / (1 - p) : 0 with the GEMM-epilogue mask of the same seed (backward of the three
  * projection / feed-forward dropout sites). ta_dropout_attn_mask: the attention keep mask as bytes, for tests. */
 int32_t ta_dropout_set_step_counter(const uint64_t* device_counter);

@@ -28,11 +28,7 @@ def _tick(n=1):
     _launches += n
 
 
-def dropout_set_step_counter(counter):
-    pass
-
-
-def dropout_bf16(src, dst, p, seed):
+def dropout_bf16(src, dst, p, seed, dropout_step=None):
     raise NotImplementedError("the CPU emulation covers dropout = 0 only (masks come from the CUDA Philox kernels)")
 
 

@@ -106,23 +106,23 @@ def _dropout_masks(eng, B, T, p):
     out = torch.empty_like(ones)
     for l in range(L):
         for site, key in ((eng.SITE_SA_PROJ, "sa_proj"), (eng.SITE_FFN, "ffn")):
-            lib.dropout_bf16(ones, out, p, eng._seed(site, l))
+            lib.dropout_bf16(ones, out, p, eng._seed(site, l), eng._drop_step)
             for i in range(M):
                 masks[(key, l, i)] = ((out[i] > 0).float() / (1 - p)).view(B, T, C).cpu()
         am = torch.empty(1, M, B, H, T, T, device="cuda", dtype=torch.uint8)
-        lib.dropout_attn_mask(am, 1, M, B, H, T, p, eng._seed(eng.SITE_SA_ATTN, l))
+        lib.dropout_attn_mask(am, 1, M, B, H, T, p, eng._seed(eng.SITE_SA_ATTN, l), eng._drop_step)
         for i in range(M):
             masks[("sa_attn", l, i)] = (am[0, i].float() / (1 - p)).cpu()
         if d.Xc:
             K = M - 1
             for xi, i in enumerate(d.xc):
                 cm = torch.empty(K, 1, B, H, T, T, device="cuda", dtype=torch.uint8)
-                lib.dropout_attn_mask(cm, K, 1, B, H, T, p, eng._seed(eng.SITE_CA_ATTN, l, xi))
+                lib.dropout_attn_mask(cm, K, 1, B, H, T, p, eng._seed(eng.SITE_CA_ATTN, l, xi), eng._drop_step)
                 for s in range(K):
                     masks[("ca_attn", l, i, s)] = (cm[s, 0].float() / (1 - p)).cpu()
             for view, pos in eng._sub(ones, d.xc):      # one GEMM launch per contiguous run of enabled modalities
                 n = view.shape[0]
-                lib.dropout_bf16(ones[:n], out[:n], p, eng._seed(eng.SITE_CA_PROJ, l, pos[0]))
+                lib.dropout_bf16(ones[:n], out[:n], p, eng._seed(eng.SITE_CA_PROJ, l, pos[0]), eng._drop_step)
                 for k, pp in enumerate(pos):
                     masks[("ca_proj", l, d.xc[pp])] = ((out[k] > 0).float() / (1 - p)).view(B, T, C).cpu()
     return masks

@@ -33,7 +33,12 @@ template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // TMEM accumulator ring: all 512 columns (1 CTA per SM), up to 8 tiles deep for the narrow tiles so that the issuer
+  // runs ahead of the epilogue round trip; two epilogue warps per lane quarter where the smem budget allows it
+  static constexpr int NACC = 512 / BLOCK_N > 8 ? 8 : 512 / BLOCK_N;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int NW = BLOCK_N <= 128 ? 8 : 4;
+  static constexpr int THREADS = (2 + NW) * 32;
 };
 
 struct GemmParams {
@@ -100,7 +105,7 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int t
 //   tmem_empty0 address of tmem_empty_bar[0] of the CTA whose issuer warp waits on it: the own CTA's (m_off == 0, plain
 //               shared address) or the leader's through the cluster window (PAIR peer, m_off != 0)
 //   m_off       row offset of this CTA inside the tile (PAIR: rank * 128)
-template <int BLOCK_N, bool PAIR, int NW>
+template <int BLOCK_N, bool PAIR, int NW, int NACC>
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps& em, uint32_t epi_smem, uint64_t* tmem_full_bar,
                                               uint32_t tmem_empty0, uint64_t (*epi_bar)[3], uint32_t tmem_base, int warp, int lane,
                                               int first_tile, int tile_stride, int total_tiles, int tiles_per_group, int m_off) {
@@ -131,8 +136,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
       decode_tile(p, tile, tiles_per_group, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M, g, m0, n0);
       m0 += m_off;
       const int g0 = g % p.G0, g1 = g / p.G0;
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
+      const int acc = local % NACC;
+      const uint32_t acc_phase = (local / NACC) & 1;
       const int row0 = m0 + quarter * 32;
       constexpr int NCH = BLOCK_N / 32;
       int nch = (p.N - n0 + 31) / 32;
@@ -317,8 +322,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
     decode_tile(p, tile, tiles_per_group, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M, g, m0, n0);
       m0 += m_off;
     const int g0 = g % p.G0, g1 = g / p.G0;
-    const int acc = local & 1;
-    const uint32_t acc_phase = (local >> 1) & 1;
+    const int acc = local % NACC;
+    const uint32_t acc_phase = (local / NACC) & 1;
     mbar_wait(&tmem_full_bar[acc], acc_phase);
     tc_fence_after();
     const int row = m0 + quarter * 32 + lane;
@@ -462,7 +467,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ EpiMaps em, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -470,9 +475,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ __align__(8) uint64_t epi_bar[4][3];
+  constexpr int NACC = Cfg::NACC;
+  __shared__ __align__(8) uint64_t tmem_full_bar[NACC];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[NACC];
+  __shared__ __align__(8) uint64_t epi_bar[Cfg::NW][3];
   __shared__ uint32_t tmem_base_smem;
 
   // the shuffle tells the compiler that `warp` is warp-uniform: producer and issuer then keep their TMA / UMMA operands
@@ -488,11 +494,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);
+      mbar_init(&tmem_empty_bar[s], Cfg::NW);
     }
-    for (int s = 0; s < 12; ++s) mbar_init(&epi_bar[0][0] + s, 1);
+    for (int s = 0; s < 3 * Cfg::NW; ++s) mbar_init(&epi_bar[0][0] + s, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -558,8 +564,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
+      const int acc = local % NACC;
+      const uint32_t acc_phase = (local / NACC) & 1;
       mbar_wait_a(tempty0 + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -578,7 +584,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    gemm_epilogue<BLOCK_N, false, 4>(p, em, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES, tmem_full_bar, smem_u32(&tmem_empty_bar[0]),
+    gemm_epilogue<BLOCK_N, false, Cfg::NW, NACC>(p, em, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES, tmem_full_bar, smem_u32(&tmem_empty_bar[0]),
                                   epi_bar, tmem_base, warp, lane, blockIdx.x, gridDim.x, total_tiles, tiles_per_group, 0);
   }
 
@@ -719,7 +725,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, their own 128 rows)
     // the leader's warps arrive on their own barrier (CTA scope), the peer's through the cluster window
-    gemm_epilogue<G2_BLOCK_N, true, 8>(p, em, smem_u32(smem) + STAGES * G2_STAGE_BYTES, tmem_full_bar,
+    gemm_epilogue<G2_BLOCK_N, true, 8, 2>(p, em, smem_u32(smem) + STAGES * G2_STAGE_BYTES, tmem_full_bar,
                                     rank == 0 ? smem_u32(&tmem_empty_bar[0]) : mapa_u32(smem_u32(&tmem_empty_bar[0]), 0), epi_bar, tmem_base, warp, lane, first_tile,
                                     tile_stride, total_tiles, tiles_per_group, rank * BLOCK_M);
   }
@@ -853,9 +859,9 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, BLOCK_N)) return 1;
   p.n_blocks = (int)ceil_div(p.N, BLOCK_N);
   EpiMaps em;
-  plan_epilogue(p, em, Cfg::STAGE_BYTES, 4);
+  plan_epilogue(p, em, Cfg::STAGE_BYTES, Cfg::NW);
   const int stages = p.stages;
-  const int smem_bytes = stages * Cfg::STAGE_BYTES + 4 * p.epi_warp_bytes + 1024;
+  const int smem_bytes = stages * Cfg::STAGE_BYTES + Cfg::NW * p.epi_warp_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     TA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -864,7 +870,7 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   }
   const long long total = (long long)p.m_blocks * p.n_blocks * p.G0 * p.G1;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  gemm_bf16_kernel<BLOCK_N><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
+  gemm_bf16_kernel<BLOCK_N><<<grid, Cfg::THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
   TA_CHECK_LAUNCH();
   return 0;
 }

@@ -137,7 +137,6 @@ class Engine:
         a plain device op, so it can be captured in a CUDA graph)."""
         if self._drop_step is None:
             self._drop_step = torch.zeros(1, dtype=torch.int64, device=self.device)
-            self.ops.dropout_set_step_counter(self._drop_step)
         self._drop_step.add_(1)
 
     # ------------------------------------------------------------------------------------------ forward
@@ -184,13 +183,13 @@ class Engine:
             o = nb("o", l, (M, BT, C), bf)
             lse = nb("lse", l, (1, M, B, H, T), f32)
             ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
-                              **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l)} if pd > 0.0 else {}))
+                              **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
             # projection MLP + residual   model.py:82-91, 224
             p1 = nb("p1", l, (M, BT, C // 2), bf)
             ops.gemm(o, self.W("sa_pw1")[l], bias=P["sa_pb1"][l], act=ACT_TANH, out_bf16=p1)
             x1 = nb("x1", l, (M, BT, C), f32)
             ops.gemm(p1, self.W("sa_pw2")[l], bias=P["sa_pb2"][l], residual=x, out_f32=x1,
-                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_PROJ, l)} if pd > 0.0 else {}))
+                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_PROJ, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
             # feed-forward + residual   model.py:167-172, 225
             hh = nb("h2", l, (M, BT, C), bf)
             st2 = nb("st2", l, (2, M * BT), f32)
@@ -200,7 +199,7 @@ class Engine:
             x2 = nb("x2", l, (M, BT, C), f32)
             a_bf = nb("a_bf", l, (M, BT, C), bf) if d.Xc else None
             ops.gemm(ffh, self.W("ff_w2")[l], bias=P["ff_b2"][l], residual=x1, out_f32=x2, out_bf16=a_bf,
-                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_FFN, l)} if pd > 0.0 else {}))
+                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_FFN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
             Sl.update(h1=h1, st1=st1, hid=hid, qkv=qkv, o=o, lse=lse, p1=p1, x1=x1, h2=hh, st2=st2, ffh=ffh, x2=x2,
                       a_bf=a_bf)
             x = x2
@@ -289,14 +288,14 @@ class Engine:
             ks, vs = self._kv_views(kvs, i)
             ops.attention_fwd(qc[xi:xi + 1], ks, vs, oc[xi:xi + 1], lsec[xi], B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
                               o_src=ocs[xi] if ocs is not None else None,
-                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi)} if pd > 0.0 else {}))
+                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi), "dropout_step": self._drop_step} if pd > 0.0 else {}))
         pc1 = nb("pc1", l, (Xc, BT, C // 2), bf)
         ops.gemm(oc, self.W("ca_pw1")[l], bias=P["ca_pb1"][l], act=ACT_TANH, out_bf16=pc1)
         x3 = nb("x3", l, (M, BT, C), f32)
         for (xv, pos), (ov, _) in zip(self._sub(x2, d.xc), self._sub(x3, d.xc)):
             p0, p1 = pos[0], pos[-1] + 1
             ops.gemm(pc1[p0:p1], self.W("ca_pw2")[l][p0:p1], bias=P["ca_pb2"][l][p0:p1], residual=xv, out_f32=ov,
-                     **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_PROJ, l, p0)} if pd > 0.0 else {}))
+                     **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_PROJ, l, p0), "dropout_step": self._drop_step} if pd > 0.0 else {}))
         for i in range(M):
             if i not in d.xc:
                 x3[i].copy_(x2[i])
@@ -335,7 +334,7 @@ class Engine:
             if pd == 0.0:
                 return t
             out = dxm[:t.shape[0]]
-            ops.dropout_bf16(t, out, pd, self._seed(site, l, sub))
+            ops.dropout_bf16(t, out, pd, self._seed(site, l, sub), self._drop_step)
             return out
 
         cs_ws = self.buf("cs_ws", (max(ops.colsum_workspace(BT, 4 * C, M), ops.colsum_workspace(BT, max(d.vocab_sizes), 1),
@@ -398,7 +397,7 @@ class Engine:
             dqkv = self.buf("dqkv", (M, BT, 3 * C), bf)
             ops.attention_bwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], Sl["o"], do, Sl["lse"],
                               dqkv[..., 0:C], [dqkv[..., C:2 * C]], [dqkv[..., 2 * C:3 * C]], B=B, T=T, H=H, hs=hs,
-                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_SA_ATTN, l)} if pd > 0.0 else {}))
+                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_SA_ATTN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
             # q/k/v MLP stage 2 (block diagonal) and stage 1
             hidg, dqkvg = self._hid_groups(Sl["hid"], BT), self._qkv_groups(dqkv, BT)
             ops.gemm(dqkvg, hidg, a_major=1, b_major=1, out_f32=G["sa_w2"][l].reshape(M, 3 * H, hs, d.h2))
@@ -434,7 +433,7 @@ class Engine:
             p0, p1 = pos[0], pos[-1] + 1
             if pd > 0.0:   # same mask as the forward epilogue of this launch (seed keyed by layer and first position)
                 dvm = dxm[:dv.shape[0]]
-                ops.dropout_bf16(dv, dvm, pd, self._seed(self.SITE_CA_PROJ, l, p0))
+                ops.dropout_bf16(dv, dvm, pd, self._seed(self.SITE_CA_PROJ, l, p0), self._drop_step)
                 dv = dvm
             ops.gemm(dv, Sl["pc1"][p0:p1], a_major=1, b_major=1, out_f32=G["ca_pw2"][l][p0:p1])
             ops.colsum(dv, G["ca_pb2"][l][p0:p1], cs_ws)
@@ -452,7 +451,7 @@ class Engine:
             ops.attention_bwd(Sl["qc"][xi:xi + 1], ks, vs, Sl["oc"][xi:xi + 1], doc[xi:xi + 1], Sl["lsec"][xi],
                               dqc[xi:xi + 1], dks, dvs, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
                               o_src=Sl["ocs"][xi] if Sl["ocs"] is not None else None,
-                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi)} if pd > 0.0 else {}))
+                              **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi), "dropout_step": self._drop_step} if pd > 0.0 else {}))
         # query projection and its LayerNorm (input: the snapshot x2 of the querying modality)
         ops.gemm(dqc, Sl["hc"], a_major=1, b_major=1, out_f32=G["ca_wq"][l].reshape(Xc, C, C))
         dhc = self.buf("dhc", (Xc, BT, C), bf)

@@ -108,7 +108,7 @@ def _operand(t, major):
 
 
 def gemm(A, B, *, a_major=0, b_major=0, out_f32=None, out_bf16=None, bias=None, act=ACT_NONE, aux=None,
-         aux_mode=AUX_NONE, residual=None, alpha=1.0, dropout_p=0.0, dropout_seed=0):
+         aux_mode=AUX_NONE, residual=None, alpha=1.0, dropout_p=0.0, dropout_seed=0, dropout_step=None):
     """D[g] = epi(alpha * A[g] @ B[g]^T). Tensors are [..groups.., rows, cols] views (up to two group dims, inner
     stride 1). For a_major/b_major = 1 the stored matrix is [K, M] / [K, N]."""
     K = A.shape[-1] if a_major == 0 else A.shape[-2]
@@ -149,7 +149,8 @@ def gemm(A, B, *, a_major=0, b_major=0, out_f32=None, out_bf16=None, bias=None, 
         assert (g0, g1) == (G0, G1)
         ep.out_bf16, ep.ld_bf16, ep.bf16_gs0, ep.bf16_gs1 = out_bf16.data_ptr(), out_bf16.stride(-2), s0, s1
     a, b = _operand(A, a_major), _operand(B, b_major)
-    _check(_lib.ta_gemm_bf16(C.byref(a), C.byref(b), M, N, K, G0, G1, C.byref(ep), _stream()))
+    with _step_counter(dropout_step if dropout_p > 0 else None):
+        _check(_lib.ta_gemm_bf16(C.byref(a), C.byref(b), M, N, K, G0, G1, C.byref(ep), _stream()))
 
 
 # ---------------------------------------------------------------------------------------------------- attention
@@ -171,7 +172,7 @@ def _attn_tensor(t, head_stride):
 
 
 def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None, o_src=None, dropout_p=0.0,
-                  dropout_seed=0):
+                  dropout_seed=0, dropout_step=None):
     """q: [G, B*T, *]; ks/vs: lists (one per source) of [G, B*T, *] views; o: [G, B*T, H*hs] bf16;
     lse: fp32 [n_src, G, B, H, T]; o_src: optional [n_src, G, B*T, H*hs] bf16."""
     n_src = len(ks)
@@ -185,9 +186,10 @@ def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_st
     o_gs = o.stride(0) if o.dim() == 3 else 0
     if o_src is not None:
         assert o_src.stride(-2) == o.stride(-2) and (o.dim() < 3 or o_src.stride(1) == o.stride(0))
-    _check(_lib.ta_attention_fwd(qa, ka, va, n_src, _ptr(o), o.stride(-2), o_gs, _ptr(o_src),
-                                 o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, float(dropout_p),
-                                 int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
+    with _step_counter(dropout_step if dropout_p > 0 else None):
+        _check(_lib.ta_attention_fwd(qa, ka, va, n_src, _ptr(o), o.stride(-2), o_gs, _ptr(o_src),
+                                     o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, float(dropout_p),
+                                     int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
 
 
 # ---------------------------------------------------------------------------------------------------- row ops
@@ -220,24 +222,38 @@ _drop_bf16 = _sig("ta_dropout_bf16", _P, _I64, _I64, _P, _I64, _I64, _I32, _I64,
 _drop_attn_mask = _sig("ta_dropout_attn_mask", _P, _I32, _I32, _I32, _I32, _I32, _F32, _U64, _P)
 
 
-def dropout_set_step_counter(counter):
-    """counter: int64/uint64 device tensor with one element (or None): its value is mixed into every dropout seed when the
-    kernels RUN, so CUDA-graph replays draw fresh masks as long as the graph increments it."""
-    _check(_drop_set(_ptr(counter)))
+class _step_counter:
+    """Scope in which launches pick up `counter` (int64 device tensor with one element, or None) as the dropout step
+    counter: its value is mixed into every dropout seed when the kernels RUN, so CUDA-graph replays draw fresh masks as
+    long as the graph increments it. The library reads the registration at launch time only, on the calling thread."""
+
+    def __init__(self, counter):
+        self.counter = counter
+
+    def __enter__(self):
+        if self.counter is not None:
+            _check(_drop_set(_ptr(self.counter)))
+
+    def __exit__(self, *exc):
+        if self.counter is not None:
+            _check(_drop_set(C.c_void_p(0)))
+        return False
 
 
-def dropout_bf16(src, dst, p, seed):
+def dropout_bf16(src, dst, p, seed, dropout_step=None):
     """dst = keep ? src / (1 - p) : 0 with the GEMM-epilogue mask of `seed`; src/dst bf16 [G, rows, cols] views."""
     assert src.dim() == 3 and dst.shape == src.shape and src.stride(-1) == 1 and dst.stride(-1) == 1
     G, rows, cols = src.shape
-    _check(_drop_bf16(_ptr(src), src.stride(1), src.stride(0), _ptr(dst), dst.stride(1), dst.stride(0), G, rows, cols, float(p),
-                      int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
+    with _step_counter(dropout_step):
+        _check(_drop_bf16(_ptr(src), src.stride(1), src.stride(0), _ptr(dst), dst.stride(1), dst.stride(0), G, rows, cols,
+                          float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
 
 
-def dropout_attn_mask(mask, n_src, G, B, H, T, p, seed):
+def dropout_attn_mask(mask, n_src, G, B, H, T, p, seed, dropout_step=None):
     """mask: uint8 [n_src, G, B, H, T, T] contiguous; the keep mask the attention kernels use for `seed` (tests)."""
     assert mask.is_contiguous() and mask.numel() == n_src * G * B * H * T * T
-    _check(_drop_attn_mask(_ptr(mask), n_src, G, B, H, T, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
+    with _step_counter(dropout_step):
+        _check(_drop_attn_mask(_ptr(mask), n_src, G, B, H, T, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
 
 
 def gather_batch(store, ix, T, xb, yb):
@@ -350,7 +366,7 @@ _lib.ta_attention_bwd.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTenso
 
 
 def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None,
-                  o_src=None, dropout_p=0.0, dropout_seed=0):
+                  o_src=None, dropout_p=0.0, dropout_seed=0, dropout_step=None):
     """Gradients of attention_fwd. d_o has the layout of o; dq of q; dks[s]/dvs[s] of ks[s]/vs[s] (bf16)."""
     n_src = len(ks)
     G = q.shape[0] if q.dim() == 3 else 1
@@ -365,6 +381,7 @@ def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_str
     assert o.stride(-1) == 1 and d_o.stride(-1) == 1 and d_o.stride(-2) == o.stride(-2)
     o_gs = o.stride(0) if o.dim() == 3 else 0
     assert o.dim() < 3 or d_o.stride(0) == o.stride(0)
-    _check(_lib.ta_attention_bwd(qa, ka, va, n_src, _ptr(o), _ptr(o_src), o_src.stride(0) if o_src is not None else 0,
-                                 _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), dqa, dka, dva, G, B, T, H, hs, float(dropout_p),
-                                 int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
+    with _step_counter(dropout_step if dropout_p > 0 else None):
+        _check(_lib.ta_attention_bwd(qa, ka, va, n_src, _ptr(o), _ptr(o_src), o_src.stride(0) if o_src is not None else 0,
+                                     _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), dqa, dka, dva, G, B, T, H, hs, float(dropout_p),
+                                     int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
