@@ -28,6 +28,10 @@ class Trainer:
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
         self.pg = process_group
         self.world = int(world_size)
+        if self.world > 1:   # every rank draws its own dropout masks (its own batch shard, model.py:69 semantics per sample)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                engine.dropout_base_seed += 0x632BE59BD9B4E019 * (dist.get_rank(process_group) + 1)
         self.grad_chunks = max(1, int(grad_chunks))
         self._graphs = None
         self.launches_per_step = None
