@@ -39,6 +39,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the bounded CPU sample")
+    ap.add_argument("--no-overlap", action="store_true", help="DP: whole-buffer all-reduce after backward instead of "
+                    "bucketed all-reduces overlapped with backward")
+    ap.add_argument("--buckets", type=int, default=12, help="DP: gradient buckets (runs of consecutive layers)")
+    ap.add_argument("--sm-margin", type=int, default=16, help="DP overlap: SMs the persistent kernels leave to NCCL "
+                    "(also the cap on NCCL's CTAs)")
     return ap.parse_args()
 
 
@@ -239,7 +244,13 @@ def run_ours(args, cfg):
     pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if not args.no_overlap and args.sm_margin > 0:
+            # the collective runs beside backward: bound its CTAs by the SMs the persistent kernels leave free
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = args.sm_margin
+            opts.config.min_ctas = min(args.sm_margin, 8)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
         pg = dist.group.WORLD
     pk = peaks()
     B = args.batch or cfg["batch"]
@@ -251,7 +262,8 @@ def run_ours(args, cfg):
     dims = Dims(V, cfg["cross"], T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"], dropout=args.dropout)
     eng = Engine(dims, dev)
     eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))   # same weights on every rank
-    tr = Trainer(eng, lr=3e-4, process_group=pg, world_size=world)
+    tr = Trainer(eng, lr=3e-4, process_group=pg, world_size=world, overlap=not args.no_overlap,
+                 grad_buckets=args.buckets, sm_margin=args.sm_margin)
     streams = syn.make_streams(cfg, dev, rows)
     n_train = int(rows * 0.9)
     store = TokenStore([s[:n_train] for s in streams], dev)
@@ -396,6 +408,10 @@ def run_ours(args, cfg):
         line = {"metric": "training tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, B, world),
+                "exchange": None if world == 1 else (
+                    {"kind": "bucketed fp32 all-reduce overlapped with backward", "buckets": len(tr._buckets),
+                     "bucket_bytes": tr.bucket_bytes(), "sm_margin": tr.sm_margin} if tr.overlap else
+                    {"kind": "whole-buffer fp32 all-reduce after backward", "chunks": tr.grad_chunks}),
                 "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "breakdown_eager_step": breakdown, "cuda_graph": use_graph,
                 "loss_sum_last_step": loss_now, "positions_per_s": value / M,

@@ -29,6 +29,12 @@ int32_t ta_abi_version(void);
 /* Number of kernels this library has launched since load (or since ta_reset_launch_count). */
 int64_t ta_launch_count(void);
 void ta_reset_launch_count(void);
+/* Persistent kernels (GEMM, attention, LayerNorm backward) size their grids from the SM count. While a collective
+ * (the NCCL gradient all-reduce of the data-parallel step, main.py:646-650 under DP) runs on a side stream, its CTAs
+ * hold SMs; a persistent grid of one CTA per SM would then run its displaced CTAs as a second wave. The margin (SMs,
+ * rounded to whole SM pairs) is subtracted from the grid of every FOLLOWING launch of the process; 0 restores full grids. */
+int32_t ta_set_sm_margin(int32_t sms);
+int32_t ta_get_sm_margin(void);
 
 /* ------------------------------------------------------------------------------------------------ K2: GEMM
  * D[g] = epilogue( alpha * A[g] (M x K) * B[g]^T (N x K) ), bf16 operands, fp32 accumulation in TMEM (tcgen05.mma),

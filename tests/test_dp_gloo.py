@@ -18,31 +18,32 @@ def _setup_paths():
             sys.path.insert(0, p)
 
 
-def _build(world, pg):
+def _build(world, pg, overlap=False):
     _setup_paths()
     import emu_ops
     from oracle import restatement as R
     from tradeaid_b200.engine import Engine
     from tradeaid_b200.params import Dims
     from tradeaid_b200.trainer import Trainer
-    V, cross, T, C, H, L = [24, 10, 20], [True, False, True], 8, 32, 2, 1
+    V, cross, T, C, H, L = [24, 10, 20], [True, False, True], 8, 32, 2, 3
     sd = R.random_state_dict(R.Cfg(T, C, H, L, V, cross), seed=4)
     eng = Engine(Dims(V, cross, T, C, H, L), "cpu", ops=emu_ops, act_dtype=torch.float32)
     nv = eng.layout.named_views(eng.master)
     for k, v in sd.items():
         nv[k].copy_(v)
-    tr = Trainer(eng, lr=1e-2, process_group=pg, world_size=world, grad_chunks=3)
+    tr = Trainer(eng, lr=1e-2, process_group=pg, world_size=world, grad_chunks=3, overlap=overlap, grad_buckets=2)
     g = torch.Generator().manual_seed(9)
     idx = torch.stack([torch.randint(0, v, (4, T), generator=g) for v in V])
     tgt = torch.stack([torch.randint(0, v, (4, T), generator=g) for v in V])
     return eng, tr, idx, tgt
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, overlap):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    eng, tr, idx, tgt = _build(world, dist.group.WORLD)
+    eng, tr, idx, tgt = _build(world, dist.group.WORLD, overlap)
+    assert tr.overlap == overlap and (len(tr._buckets) == 2 if overlap else not tr._buckets)
     half = idx.shape[1] // world
     sl = slice(rank * half, (rank + 1) * half)
     for _ in range(3):
@@ -55,12 +56,44 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_dp_equals_single_process(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("overlap", [False, True], ids=["whole-buffer", "bucketed-overlap"])
+def test_two_rank_dp_equals_single_process(tmp_path, overlap):
     out = str(tmp_path / "dp_master.pt")
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29500 + (os.getpid() + 7 * overlap) % 2000
+    mp.spawn(_worker, args=(2, port, out, overlap), nprocs=2, join=True)
     dp_master = torch.load(out)
     eng, tr, idx, tgt = _build(1, None)
     for _ in range(3):
         tr.step(idx, tgt)
     assert (dp_master - eng.master).abs().max().item() <= 2e-5   # fp32 summation order (mean of halves vs whole) through 3 Adam steps of lr 1e-2
+
+
+def test_gradient_buckets_partition_the_active_parameters():
+    """Every element of every active parameter kind is in exactly one bucket (trainer.py: _make_buckets)."""
+    _setup_paths()
+    import emu_ops
+    from tradeaid_b200.engine import Engine
+    from tradeaid_b200.params import Dims
+    from tradeaid_b200.trainer import Trainer
+    for cross, L, nb in (([True, False, True], 5, 3), ([False, False], 2, 6), ([True, True, True, False], 12, 6)):
+        V = [24, 10, 20, 8][:len(cross)]
+        eng = Engine(Dims(V, cross, 8, 32, 2, L), "cpu", ops=emu_ops, act_dtype=torch.float32)
+        tr = Trainer(eng, lr=1e-3, world_size=2, overlap=True, grad_buckets=nb)
+        assert [b[0] for b in tr._buckets][-1] == "embed" and len(tr._buckets) == min(nb, L)
+        cover = torch.zeros(eng.layout.total, dtype=torch.int32)
+        base = eng.grad.data_ptr()
+        for _, views in tr._buckets:
+            for v in views:
+                a = (v.data_ptr() - base) // 4
+                cover[a:a + v.numel()] += 1
+        want = torch.zeros_like(cover)
+        for kind, (off, shape) in eng.layout.kinds.items():
+            n = 1
+            for s_ in shape:
+                n *= s_
+            if off < eng.layout.n_active:
+                want[off:off + n] = 1
+        assert torch.equal(cover, want)

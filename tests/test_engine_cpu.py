@@ -76,3 +76,29 @@ def test_runs_helper():
     assert _runs([1]) == [(1, 1, 1)]
     assert _runs([0, 1, 3, 7]) == [(0, 1, 2), (3, 4, 2)]
     assert _runs([0, 2, 4, 5]) == [(0, 2, 3), (5, 1, 1)]
+
+
+def test_stage2_blockdiag_equals_per_head_groups(monkeypatch):
+    """engine.py: stage 2 of the q/k/v MLPs as block-diagonal problems of gsz heads (the packing the CUDA path uses for
+    hs in {32, 64}) must give exactly what one problem per (q|k|v, head) gives — the padding is exact zeros."""
+    from oracle import restatement as R
+    V, cross, T, C, H, L, B = [24, 10, 20], [True, False, True], 8, 256, 8, 2, 2
+    sd = R.random_state_dict(R.Cfg(T, C, H, L, V, cross), seed=4)
+    g = torch.Generator().manual_seed(9)
+    idx = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V])
+    tgt = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V])
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TRADEAID_STAGE2_BLOCKDIAG", flag)
+        eng = Engine(Dims(V, cross, T, C, H, L), "cpu", ops=emu_ops, act_dtype=torch.float32)
+        assert (eng._bd is not None) == (flag == "1")
+        nv = eng.layout.named_views(eng.master)
+        for k, v in sd.items():
+            nv[k].copy_(v)
+        logits, losses = eng.forward(idx, tgt, save=True)
+        eng.backward()
+        outs[flag] = (torch.cat([x.flatten() for x in logits]).clone(), eng.grad.clone())
+    assert torch.equal(outs["1"][0], outs["0"][0]) and torch.equal(outs["1"][1], outs["0"][1])
+    # and against the reference restatement
+    ref_logits, _, ref_grads = R.forward_backward(sd, R.Cfg(T, C, H, L, V, cross), list(idx), list(tgt))
+    assert (outs["1"][0] - torch.cat([x.flatten() for x in ref_logits])).abs().max().item() <= 2e-5

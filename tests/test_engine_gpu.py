@@ -171,3 +171,27 @@ def test_training_step_with_dropout_against_oracle(M, cross, V, B, T, C, H, L):
     e1 = [x.clone() for x in e1]
     e2, _ = eng.forward(torch.stack(idx).cuda(), None, save=False)
     assert all(torch.equal(a, b) for a, b in zip(e1, e2))
+
+
+@pytest.mark.parametrize("C,H", [(256, 8), (256, 4)])
+def test_stage2_blockdiag_is_bit_identical_to_per_head_groups(C, H, monkeypatch):
+    """engine.py: q/k/v stage 2 packed gsz heads per block-diagonal problem vs one grouped problem per (q|k|v, head):
+    the extra operands are exact zeros, so logits, losses and every gradient must be bit-identical."""
+    from tradeaid_b200.engine import Engine
+    from tradeaid_b200.params import Dims
+    V, cross, T, L, B = [100, 64, 80], [True, False, True], 64, 2, 4
+    g = torch.Generator().manual_seed(8)
+    idx = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V]).cuda()
+    tgt = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V]).cuda()
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TRADEAID_STAGE2_BLOCKDIAG", flag)
+        eng = Engine(Dims(V, cross, T, C, H, L), "cuda")
+        assert (eng._bd is not None) == (flag == "1")
+        eng.layout.init_(eng.master, generator=torch.Generator(device="cuda").manual_seed(0))
+        logits, losses = eng.forward(idx, tgt, save=True)
+        eng.backward()
+        out[flag] = ([x.clone() for x in logits], losses.clone(), eng.grad.clone())
+    assert all(torch.equal(a, b) for a, b in zip(out["1"][0], out["0"][0]))
+    assert torch.equal(out["1"][1], out["0"][1])
+    assert torch.equal(out["1"][2], out["0"][2])

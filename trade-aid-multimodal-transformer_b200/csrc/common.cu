@@ -11,6 +11,7 @@ namespace ta {
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 static const unsigned long long* g_dropout_step = nullptr;   // device counter mixed into every dropout seed
+static std::atomic<int> g_sm_margin{0};                       // SMs left free for a concurrent kernel (ta_set_sm_margin)
 
 char* err_buf() { return g_err; }
 
@@ -35,7 +36,10 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
   }
-  return cached[dev];
+  // persistent grids leave `margin` SMs (whole SM pairs, so CTA-pair clusters still fit) to whatever runs beside them
+  const int margin = g_sm_margin.load(std::memory_order_relaxed);
+  const int n = (cached[dev] - margin) & ~1;
+  return n < 2 ? 2 : n;
 }
 
 }  // namespace ta
@@ -48,6 +52,12 @@ int32_t ta_dropout_set_step_counter(const uint64_t* device_counter) {
   ta::g_dropout_step = reinterpret_cast<const unsigned long long*>(device_counter);
   return 0;
 }
+int32_t ta_set_sm_margin(int32_t sms) {
+  TA_CHECK_ARG(sms >= 0 && sms <= 128, "ta_set_sm_margin: margin %d out of range [0, 128]", (int)sms);
+  ta::g_sm_margin.store(sms, std::memory_order_relaxed);
+  return 0;
+}
+int32_t ta_get_sm_margin(void) { return ta::g_sm_margin.load(std::memory_order_relaxed); }
 int64_t ta_launch_count(void) { return ta::g_launches.load(std::memory_order_relaxed); }
 void ta_reset_launch_count(void) { ta::g_launches.store(0, std::memory_order_relaxed); }
 }

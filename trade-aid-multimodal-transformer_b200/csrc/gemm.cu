@@ -82,8 +82,8 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 
 // tile index -> (group, m0, n0). Default order: group-major (tiles of a group are neighbours: its operands stay hot in
-// L2). m_major: row-block-major, for the block-diagonal q/k/v stage-2 problems (hundreds of groups that are column
-// slices of the SAME rows, K <= 64): concurrently running tiles then read / write adjacent segments of the same rows.
+// L2). m_major: row-block-major, for the block-diagonal q/k/v stage-2 problems (tens to hundreds of groups that are
+// column slices of the SAME rows, K <= 256): concurrently running tiles then read / write adjacent segments of the same rows.
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int tiles_per_group, int block_n, int block_m, int& g,
                                             int& m0, int& n0) {
   if (p.m_major) {
@@ -935,7 +935,7 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   p.drop_step = dropout_step_counter();
   {
     static const int force_mm = env_int("TA_GEMM_M_MAJOR", -1);
-    p.m_major = force_mm >= 0 ? force_mm : ((long long)G0 * G1 >= 16 && p.k_blocks == 1 && p.m_blocks > 1);
+    p.m_major = force_mm >= 0 ? force_mm : ((long long)G0 * G1 >= 16 && p.k_blocks <= 4 && p.m_blocks > 1);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tile width: the widest UMMA N that still yields about a wave of tiles

@@ -10,6 +10,8 @@ CPU emulation of the same ops to check this host logic without a GPU; the engine
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .params import Dims, Layout, r8
@@ -56,6 +58,18 @@ class Engine:
         self.S = self.layout.views(self.shadow)
         self._padded = {}      # kind -> zero-padded bf16 (or fp32 for biases) copy when the direct view is not TMA-able
         self._make_padded()
+        # q/k/v stage 2 (model.py:36-50: Linear(hs/2 -> hs) per head and projection) is block diagonal: 3H blocks of
+        # [hs x hs/2]. As 3H grouped problems with K = hs/2 the GEMM is bound by per-tile latency (c4: 49 152 tiles of
+        # 128 x 64 x 32 per launch, 2.4x the HBM time). Packing `gsz` neighbouring blocks on the diagonal of one
+        # [gsz*hs x gsz*hs/2] matrix (zeros elsewhere) turns it into 3H/gsz problems with full 256-wide tiles; the
+        # zeros add exact zeros to the fp32 accumulators, so the results are bit-identical.
+        self._bd = None
+        gsz = 256 // dims.hs if dims.hs > 0 else 0
+        if (os.environ.get("TRADEAID_STAGE2_BLOCKDIAG", "1") != "0" and dims.h2p == dims.h2 and gsz > 1
+                and (3 * dims.n_head) % gsz == 0):
+            ng = 3 * dims.n_head // gsz
+            self._bd = (gsz, ng, torch.zeros(dims.n_layer, dims.M, ng, gsz * dims.hs, gsz * dims.h2, dtype=act_dtype,
+                                             device=self.device))
         self._bufs = {}
         self._voff = torch.tensor(dims.voff, dtype=torch.int64, device=self.device)
         self._saved = None
@@ -96,6 +110,15 @@ class Engine:
                 ops.unpad(src.reshape(-1, 1, d.h2), dst.view(-1, 1, d.h2p)[..., :d.h2])
             else:
                 ops.cast_pad(src.reshape(-1, src.shape[-2], src.shape[-1]), dst.view(-1, dst.shape[-2], dst.shape[-1]))
+        if self._bd is not None:
+            gsz, ng, w2bd = self._bd
+            hs, h2 = d.hs, d.h2
+            n = d.n_layer * d.M * ng
+            src = self.P["sa_w2"].reshape(n, gsz, hs, h2)
+            R, Cc = gsz * hs, gsz * h2
+            for k in range(gsz):     # block k of every group -> rows [k*hs, (k+1)*hs), columns [k*h2, (k+1)*h2)
+                dst = w2bd.as_strided((n, hs, h2), (R * Cc, Cc, 1), w2bd.storage_offset() + k * (hs * Cc + h2))
+                ops.cast_pad(src[:, k], dst)
         self.shadows_stale = False
 
     def W(self, kind):
@@ -178,8 +201,11 @@ class Engine:
             ops.gemm(h1, self.W("sa_w1")[l].reshape(M, 3 * H * h2p, C), bias=b1, act=ACT_TANH, out_bf16=hid)
             # stage 2: block-diagonal [hs x h2] per (q|k|v, head): grouped GEMM, groups (3H within the row, modality)
             qkv = nb("qkv", l, (M, BT, 3 * C), bf)
-            ops.gemm(self._hid_groups(hid, BT), self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1),
-                     out_bf16=self._qkv_groups(qkv, BT))
+            if self._bd is not None:
+                ops.gemm(self._hid_groups(hid, BT, self._bd[0]), self._bd[2][l], out_bf16=self._qkv_groups(qkv, BT, self._bd[0]))
+            else:
+                ops.gemm(self._hid_groups(hid, BT), self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1),
+                         out_bf16=self._qkv_groups(qkv, BT))
             o = nb("o", l, (M, BT, C), bf)
             lse = nb("lse", l, (1, M, B, H, T), f32)
             ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
@@ -237,15 +263,19 @@ class Engine:
         self._saved = S if save else None
         return [lg.view(B, T, -1) for lg in logits], losses
 
-    def _hid_groups(self, hid, BT):
+    def _hid_groups(self, hid, BT, gsz=1):
+        """[M, BT, 3H*h2p] -> [M, 3H/gsz, BT, gsz*h2]: column slices of gsz neighbouring (q|k|v, head) blocks."""
         d = self.d
         M, H, h2, h2p = d.M, d.n_head, d.h2, d.h2p
+        if gsz > 1:
+            return hid.as_strided((M, 3 * H // gsz, BT, gsz * h2), (BT * 3 * H * h2, gsz * h2, 3 * H * h2, 1),
+                                  hid.storage_offset())
         return hid.as_strided((M, 3 * H, BT, h2), (BT * 3 * H * h2p, h2p, 3 * H * h2p, 1))
 
-    def _qkv_groups(self, qkv, BT):
+    def _qkv_groups(self, qkv, BT, gsz=1):
         d = self.d
         M, H, hs, C = d.M, d.n_head, d.hs, d.n_embd
-        return qkv.as_strided((M, 3 * H, BT, hs), (BT * 3 * C, hs, 3 * C, 1))
+        return qkv.as_strided((M, 3 * H // gsz, BT, gsz * hs), (BT * 3 * C, gsz * hs, 3 * C, 1), qkv.storage_offset())
 
     def _sub(self, t, idxs):
         """Views of t[idxs] (first dim) as a list of (view, positions-in-idxs) with arithmetic-progression strides."""
@@ -271,16 +301,15 @@ class Engine:
                                   stc[0][p * BT:(p + 1) * BT], stc[1][p * BT:(p + 1) * BT])
         qc = nb("qc", l, (Xc, BT, C), bf)
         ops.gemm(hc, self.W("ca_wq")[l].reshape(Xc, C, C), out_bf16=qc)
-        kvs = []
+        kvs = [None] * M
         Wkv = self.W("ca_wkv")[l]  # [sum_j nq_j, H, 2hs, C]
-        for j in range(M):
-            nq = len(d.queriers[j])
-            if nq == 0:
-                kvs.append(None)
-                continue
-            kv = nb(f"kv{j}", l, (BT, nq * 2 * C), bf)
-            ops.gemm(a_bf[j], Wkv[d.qoff[j]:d.qoff[j + 1]].reshape(nq * 2 * C, C), out_bf16=kv)
-            kvs.append(kv)
+        for j0, j1, nq in self._kv_runs():
+            # sources j0..j1-1 have the same number of queriers: one grouped launch (more tiles per launch = fewer
+            # partly filled waves of the persistent grid)
+            kv = nb(f"kv{j0}", l, (j1 - j0, BT, nq * 2 * C), bf)
+            ops.gemm(a_bf[j0:j1], Wkv[d.qoff[j0]:d.qoff[j1]].reshape(j1 - j0, nq * 2 * C, C), out_bf16=kv)
+            for j in range(j0, j1):
+                kvs[j] = kv[j - j0]
         oc = nb("oc", l, (Xc, BT, C), bf)
         ocs = nb("ocs", l, (Xc, K, 1, BT, C), bf) if K > 1 else None
         lsec = nb("lsec", l, (Xc, K, 1, B, H, T), f32)
@@ -302,6 +331,20 @@ class Engine:
         Sl.update(hc=hc, stc=stc, qc=qc, kvs=kvs, oc=oc, ocs=ocs, lsec=lsec, pc1=pc1, x3=x3)
         return x3
 
+    def _kv_runs(self):
+        """Maximal runs [j0, j1) of consecutive source modalities with the same non-zero number of queriers -> (j0, j1, nq):
+        their K/V projections (and the backward of those) have one shape and go out as one grouped launch."""
+        d, out, j = self.d, [], 0
+        while j < d.M:
+            nq = len(d.queriers[j])
+            k = j + 1
+            while k < d.M and len(d.queriers[k]) == nq:
+                k += 1
+            if nq > 0:
+                out.append((j, k, nq))
+            j = k
+        return out
+
     def _kv_views(self, kvs, i, grads=False):
         """K and V column views (head 0, dim 0) of querier i inside each source's stacked K/V buffer."""
         d = self.d
@@ -315,8 +358,11 @@ class Engine:
         return ks, vs
 
     # ------------------------------------------------------------------------------------------ backward
-    def backward(self, loss_weights=None):
-        """Gradients of sum_i w_i * loss_i (w_i = 1: main.py:646) into self.grad; needs forward(..., save=True)."""
+    def backward(self, loss_weights=None, stage_hook=None):
+        """Gradients of sum_i w_i * loss_i (w_i = 1: main.py:646) into self.grad; needs forward(..., save=True).
+        `stage_hook(stage)` is called when every gradient of a stage has been enqueued: "heads" (output heads + final
+        LayerNorm), then each layer index from n_layer-1 down to 0, then "embed" — the data-parallel trainer starts the
+        all-reduce of a gradient bucket there while the kernels of the earlier layers are still to run."""
         S = self._saved
         if S is None or "dlogits" not in S:
             raise RuntimeError("backward() needs a preceding forward(idx, targets, save=True)")
@@ -365,6 +411,8 @@ class Engine:
             ops.gemm(dhd, self.W(f"hd_w1_{i}"), b_major=1, out_bf16=dhf[i])
         ops.layernorm_bwd(dhf, S["x_final"], self.P["lnf_w"], S["stf"][0], S["stf"][1], None, dx, dxb, G["lnf_w"],
                           G["lnf_b"], ln_ws)
+        if stage_hook is not None:
+            stage_hook("heads")
         # ---- layers, last to first
         for l in reversed(range(L)):
             Sl = S["layers"][l]
@@ -402,8 +450,13 @@ class Engine:
             hidg, dqkvg = self._hid_groups(Sl["hid"], BT), self._qkv_groups(dqkv, BT)
             ops.gemm(dqkvg, hidg, a_major=1, b_major=1, out_f32=G["sa_w2"][l].reshape(M, 3 * H, hs, d.h2))
             dhid = self.buf("dhid", (M, BT, 3 * H * h2p), bf)
-            ops.gemm(dqkvg, self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1), b_major=1, aux=hidg, aux_mode=AUX_TANH_BWD,
-                     out_bf16=self._hid_groups(dhid, BT))
+            if self._bd is not None:
+                gsz = self._bd[0]
+                ops.gemm(self._qkv_groups(dqkv, BT, gsz), self._bd[2][l], b_major=1, aux=self._hid_groups(Sl["hid"], BT, gsz),
+                         aux_mode=AUX_TANH_BWD, out_bf16=self._hid_groups(dhid, BT, gsz))
+            else:
+                ops.gemm(dqkvg, self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1), b_major=1, aux=hidg, aux_mode=AUX_TANH_BWD,
+                         out_bf16=self._hid_groups(dhid, BT))
             if h2p == d.h2:
                 ops.gemm(dhid, Sl["h1"], a_major=1, b_major=1, out_f32=G["sa_w1"][l].reshape(M, 3 * H * h2p, C))
                 ops.colsum(dhid, G["sa_b1"][l].reshape(M, 3 * H * h2p), cs_ws)
@@ -417,9 +470,13 @@ class Engine:
             ops.gemm(dhid, self.W("sa_w1")[l].reshape(M, 3 * H * h2p, C), b_major=1, out_bf16=dh)
             ops.layernorm_bwd(dh, Sl["x0"], self.P["ln1_w"][l], Sl["st1"][0], Sl["st1"][1], dx, dx, dxb, G["ln1_w"][l],
                               G["ln1_b"][l], ln_ws)
+            if stage_hook is not None:
+                stage_hook(l)
         ops.embed_bwd(S["idx"].view(M, BT), dx, self._voff, max(d.vocab_sizes), G["tok"], G["pos"][:T], B, T)
         if T < d.block_size:
             G["pos"][T:].zero_()
+        if stage_hook is not None:
+            stage_hook("embed")
 
     def _cross_backward(self, l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd=0.0, dxm=None):
         d, ops, G = self.d, self.ops, self.G
@@ -444,7 +501,12 @@ class Engine:
         doc = self.buf("doc", (Xc, BT, C), bf)
         ops.gemm(dpc1, self.W("ca_pw1")[l], b_major=1, out_bf16=doc)
         dqc = self.buf("dqc", (Xc, BT, C), bf)
-        dkvs = [self.buf(f"dkv{j}", Sl["kvs"][j].shape, bf) if Sl["kvs"][j] is not None else None for j in range(M)]
+        dkvs, dkv_runs = [None] * M, []
+        for j0, j1, nq in self._kv_runs():
+            t = self.buf(f"dkv{j0}", (j1 - j0, BT, nq * 2 * C), bf)
+            dkv_runs.append(t)
+            for j in range(j0, j1):
+                dkvs[j] = t[j - j0]
         for xi, i in enumerate(d.xc):
             ks, vs = self._kv_views(Sl["kvs"], i)
             dks, dvs = self._kv_views(dkvs, i)
@@ -462,13 +524,11 @@ class Engine:
                               dx[i:i + 1], dxb[i:i + 1], G["lnc_w"][l][xi:xi + 1], G["lnc_b"][l][xi:xi + 1], ln_ws)
         # key/value projections: gradients land on the (un-normalised) stream of every SOURCE modality
         Wkv, Gkv = self.W("ca_wkv")[l], G["ca_wkv"][l]
-        for j in range(M):
-            nq = len(d.queriers[j])
-            if nq == 0:
-                continue
-            sl = slice(d.qoff[j], d.qoff[j + 1])
-            ops.gemm(dkvs[j], Sl["a_bf"][j], a_major=1, b_major=1, out_f32=Gkv[sl].reshape(nq * 2 * C, C))
-            ops.gemm(dkvs[j], Wkv[sl].reshape(nq * 2 * C, C), b_major=1, residual=dx[j], out_f32=dx[j], out_bf16=dxb[j])
+        for (j0, j1, nq), dkv in zip(self._kv_runs(), dkv_runs):
+            sl, n = slice(d.qoff[j0], d.qoff[j1]), j1 - j0
+            ops.gemm(dkv, Sl["a_bf"][j0:j1], a_major=1, b_major=1, out_f32=Gkv[sl].reshape(n, nq * 2 * C, C))
+            ops.gemm(dkv, Wkv[sl].reshape(n, nq * 2 * C, C), b_major=1, residual=dx[j0:j1], out_f32=dx[j0:j1],
+                     out_bf16=dxb[j0:j1])
 
     # ------------------------------------------------------------------------------------------ bookkeeping
     def zero_grad(self):

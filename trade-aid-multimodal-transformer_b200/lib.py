@@ -67,6 +67,20 @@ def reset_launch_count():
     _lib.ta_reset_launch_count()
 
 
+_lib.ta_set_sm_margin.restype = C.c_int32
+_lib.ta_set_sm_margin.argtypes = [C.c_int32]
+_lib.ta_get_sm_margin.restype = C.c_int32
+
+
+def set_sm_margin(sms):
+    """SMs the persistent kernels of the following launches leave free (for a concurrent NCCL kernel); 0 = none."""
+    _check(_lib.ta_set_sm_margin(int(sms)))
+
+
+def get_sm_margin():
+    return int(_lib.ta_get_sm_margin())
+
+
 def raw():
     """The ctypes CDLL handle (symbol table checks in tests)."""
     return _lib

@@ -186,6 +186,39 @@ class Layout:
             out[name] = t
         return out
 
+    GLOBAL_HEAD_PREFIXES = ("lnf_", "hd_")     # output heads + final LayerNorm: first gradients backward produces
+    GLOBAL_EMBED_KINDS = ("tok", "pos")        # embedding tables: the last
+
+    def grad_ranges(self, stage, layers=()):
+        """Element ranges [(start, stop), ...] of the flat gradient buffer (below n_active) written by a backward stage:
+        'heads' (output heads + final LayerNorm), 'embed' (token + position tables) or 'layers' with `layers` = a run of
+        consecutive layer indices — every per-layer kind is laid out [L, ...], so the run is one slice per kind."""
+        out = []
+        for kind, (off, shape) in self.kinds.items():
+            if off >= self.n_active:
+                continue
+            n = 1
+            for s_ in shape:
+                n *= s_
+            is_head = kind.startswith(self.GLOBAL_HEAD_PREFIXES)
+            is_embed = kind in self.GLOBAL_EMBED_KINDS
+            if stage == "heads" and is_head or stage == "embed" and is_embed:
+                out.append((off, off + n))
+            elif stage == "layers" and not is_head and not is_embed and n:
+                per = n // self.d.n_layer
+                lo, hi = min(layers), max(layers) + 1
+                assert list(range(lo, hi)) == sorted(layers), "layers must be consecutive"
+                out.append((off + lo * per, off + hi * per))
+        out = [r for r in out if r[1] > r[0]]
+        out.sort()
+        merged = []
+        for a, b in out:
+            if merged and merged[-1][1] == a:
+                merged[-1] = (merged[-1][0], b)
+            else:
+                merged.append((a, b))
+        return merged
+
     def is_active(self, name):
         kind, _ = self.names[name]
         return self.kinds[kind][0] < self.n_active

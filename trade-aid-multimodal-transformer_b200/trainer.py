@@ -4,18 +4,25 @@ fused AdamW, optionally replayed as CUDA graphs. Semantics of one step are those
 torch defaults.
 
 Data parallelism (BASELINE.json: 1/2/4/8 B200): one process per GPU, full replica each, per-rank batch shard, one
-exchange step per iteration — an all-reduce (sum) of the flat fp32 gradient buffer over NCCL, with the 1/R mean folded
-into the AdamW kernel's grad_scale. The all-reduce of the per-layer gradient ranges is issued on a side stream as soon as
-the backward kernels of that layer are enqueued, so it overlaps the rest of backward.
+exchange per iteration — an all-reduce (sum) of the flat fp32 gradient buffer over NCCL, with the 1/R mean folded into
+the AdamW kernel's grad_scale. The exchange is BUCKETED in the order backward produces gradients (output heads and the
+last layers first, the embedding tables last): as soon as the kernels of a bucket's layers are enqueued, the all-reduce
+of that bucket's gradient ranges is issued asynchronously (one coalesced NCCL call on the process group's own stream,
+which waits for exactly the work enqueued so far), so it runs beside the backward of the earlier layers. While a
+collective can be in flight, the persistent kernels leave `sm_margin` SMs free for its CTAs (ta_set_sm_margin) — a
+one-CTA-per-SM grid would otherwise run its displaced CTAs as a second wave. `overlap=False` keeps the plain form
+(backward, then the whole-buffer all-reduce in `grad_chunks` pieces).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
 
 class Trainer:
     def __init__(self, engine, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None, world_size=1,
-                 grad_chunks=8):
+                 grad_chunks=8, overlap=None, grad_buckets=None, sm_margin=None):
         self.eng = engine
         self.ops = engine.ops
         self.lr, self.betas, self.eps, self.wd = float(lr), betas, float(eps), float(weight_decay)
@@ -33,13 +40,63 @@ class Trainer:
             if dist.is_available() and dist.is_initialized():
                 engine.dropout_base_seed += 0x632BE59BD9B4E019 * (dist.get_rank(process_group) + 1)
         self.grad_chunks = max(1, int(grad_chunks))
+        if overlap is None:
+            overlap = os.environ.get("TRADEAID_DP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap) and self.world > 1
+        L = engine.d.n_layer
+        if grad_buckets is None:
+            grad_buckets = int(os.environ.get("TRADEAID_DP_BUCKETS", "12"))
+        self.grad_buckets = max(1, min(int(grad_buckets), L))
+        if sm_margin is None:
+            sm_margin = int(os.environ.get("TRADEAID_DP_SM_MARGIN", "16"))
+        self.sm_margin = int(sm_margin) if (self.overlap and hasattr(self.ops, "set_sm_margin")) else 0
+        self._buckets = self._make_buckets() if self.overlap else []
+        self._works = []
         self._graphs = None
         self.launches_per_step = None
 
+    # ------------------------------------------------------------------------------------------ buckets
+    def _make_buckets(self):
+        """[(closing stage, [gradient views])]: bucket b is complete when backward reports `closing stage`. Layers are
+        split into grad_buckets runs of consecutive layers, last layers first; the head gradients ride with the first
+        bucket, the embedding tables with the last one (which closes at 'embed')."""
+        lay, g = self.eng.layout, self.eng.grad
+        L, nb = self.eng.d.n_layer, self.grad_buckets
+        bounds = [round(L * k / nb) for k in range(nb + 1)]          # ascending layer boundaries
+        runs = [list(range(bounds[k], bounds[k + 1])) for k in range(nb) if bounds[k + 1] > bounds[k]]
+        runs.reverse()                                               # backward order: last layers first
+        buckets = []
+        for b, run in enumerate(runs):
+            ranges = lay.grad_ranges("layers", run)
+            if b == 0:
+                ranges = lay.grad_ranges("heads") + ranges
+            last = b == len(runs) - 1
+            if last:
+                ranges = ranges + lay.grad_ranges("embed")
+            buckets.append(("embed" if last else run[0], [g[a:e] for a, e in ranges]))
+        return buckets
+
+    def bucket_bytes(self):
+        return [sum(t.numel() * 4 for t in views) for _, views in self._buckets]
+
+    def _issue_bucket(self, views):
+        """One coalesced asynchronous all-reduce(sum) of a bucket's gradient ranges. The process group's stream waits
+        for the work enqueued on the current stream so far; the current stream is not blocked."""
+        import torch.distributed as dist
+        with dist._coalescing_manager(group=self.pg, async_ops=True) as cm:
+            for t in views:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+        self._works.append(cm)
+
+    def _wait_buckets(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+
     # ------------------------------------------------------------------------------------------ pieces
-    def forward_backward(self, idx, tgt):
+    def forward_backward(self, idx, tgt, stage_hook=None):
         logits, losses = self.eng.forward(idx, tgt, save=True, train=True)
-        self.eng.backward()
+        self.eng.backward(stage_hook=stage_hook)
         return losses
 
     def allreduce_grads(self):
@@ -62,11 +119,31 @@ class Trainer:
                        self.scalars, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
         eng.refresh_shadows(flat_cast=False)
 
+    def _set_margin(self, sms):
+        if self.sm_margin:
+            self.ops.set_sm_margin(sms)
+
     # ------------------------------------------------------------------------------------------ eager step
     def step(self, idx, tgt):
         """One training step on device-resident int64 [M, B, T] batches. Returns the per-modality losses [M] (device)."""
-        losses = self.forward_backward(idx, tgt)
-        self.allreduce_grads()
+        if not self.overlap:
+            losses = self.forward_backward(idx, tgt)
+            self.allreduce_grads()
+            self.optimizer_step()
+            return losses
+        closing = {stage: views for stage, views in self._buckets}
+
+        def hook(stage):
+            views = closing.get(stage)
+            if views is not None:
+                self._issue_bucket(views)
+                self._set_margin(self.sm_margin)     # from here on a collective may be running beside the kernels
+
+        try:
+            losses = self.forward_backward(idx, tgt, stage_hook=hook)
+        finally:
+            self._set_margin(0)
+        self._wait_buckets()
         self.optimizer_step()
         return losses
 
@@ -74,8 +151,9 @@ class Trainer:
     def capture(self, idx_static, tgt_static):
         """Capture the step into CUDA graphs over STATIC batch buffers (the feeder writes them with
         TokenStore.gather(ix, T, out=(idx_static, tgt_static)) before each replay). Single GPU: one graph holds forward,
-        backward and the optimizer. Data parallel: forward+backward and the optimizer are two graphs with the NCCL
-        all-reduce between them."""
+        backward and the optimizer. Data parallel: the optimizer is its own graph after the exchange; with overlap the
+        forward+backward program is cut into one graph per gradient bucket, and the bucket's all-reduce is issued
+        between the replays."""
         eng = self.eng
         if eng.shadows_stale:
             eng.refresh_shadows()
@@ -88,25 +166,64 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.ops.reset_launch_count()
-        g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_fb):
-            self._losses_static = self.forward_backward(idx_static, tgt_static)
-            if self.world <= 1:
-                self.optimizer_step()
+        segments = []          # [(graph, gradient views to all-reduce after it | None)]
+        if not self.overlap:
+            g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fb):
+                self._losses_static = self.forward_backward(idx_static, tgt_static)
+                if self.world <= 1:
+                    self.optimizer_step()
+            segments.append((g_fb, None))
+        else:
+            closing = {stage: views for stage, views in self._buckets}
+            pool = torch.cuda.graph_pool_handle()
+            cap = torch.cuda.Stream()
+            cap.wait_stream(torch.cuda.current_stream())
+            state = {"g": None}
+
+            def begin():
+                state["g"] = torch.cuda.CUDAGraph()
+                state["g"].capture_begin(pool=pool)
+
+            def hook(stage):
+                views = closing.get(stage)
+                if views is None:
+                    return
+                state["g"].capture_end()
+                segments.append((state["g"], views))
+                state["g"] = None
+                self._set_margin(self.sm_margin)
+                if stage != "embed":
+                    begin()
+
+            try:
+                with torch.cuda.stream(cap):
+                    begin()
+                    self._losses_static = self.forward_backward(idx_static, tgt_static, stage_hook=hook)
+                    assert state["g"] is None, "the last bucket must close at the end of backward"
+            finally:
+                self._set_margin(0)
+            torch.cuda.current_stream().wait_stream(cap)
         g_opt = None
         if self.world > 1:
             g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_opt):
                 self.optimizer_step()
         self.launches_per_step = self.ops.launch_count()
-        self._graphs = (g_fb, g_opt)
+        self._graphs = (segments, g_opt)
         return self._losses_static
 
     def replay(self):
-        g_fb, g_opt = self._graphs
-        g_fb.replay()
+        segments, g_opt = self._graphs
+        for g, views in segments:
+            g.replay()
+            if views is not None:
+                self._issue_bucket(views)
         if g_opt is not None:
-            self.allreduce_grads()
+            if self.overlap:
+                self._wait_buckets()
+            else:
+                self.allreduce_grads()
             g_opt.replay()
         return self._losses_static
 
