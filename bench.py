@@ -421,12 +421,94 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ inference (c5)
+def run_inference(args, cfg):
+    """`--config c5` (BASELINE.json: long-context inference, forward/generate on 1xB200): tokens/s of the full forward over
+    [M, B, T] windows, and of generate() in its growing phase (prompt T/2, K/V cache, one new position per step).
+    A parity-test configuration, not the headline line; replicas only for --gpus > 1 (no exchange in inference)."""
+    from tradeaid_b200 import lib, synthetic as syn
+    from tradeaid_b200.engine import Engine, KVCache
+    from tradeaid_b200.params import Dims
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch or cfg["batch"]
+    T, V = cfg["block_size"], cfg["vocab"]
+    M = len(V)
+    dims = Dims(V, cfg["cross"], T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"])
+    eng = Engine(dims, dev)
+    eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))
+    rows = min(args.rows or cfg["rows"], 1_000_000)
+    streams = syn.make_streams(cfg, dev, rows)
+    g = torch.Generator().manual_seed(1 + rank)
+    ix = torch.randint(0, rows - T - 1, (B,), generator=g).to(dev)
+    idx = torch.stack([s[ix[:, None] + torch.arange(T, device=dev)] for s in streams]).contiguous()
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    for _ in range(max(args.warmup, 3)):
+        eng.forward(idx, None, save=False)
+    torch.cuda.synchronize()
+    lib.reset_launch_count()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        logits, _ = eng.forward(idx, None, save=False)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.launch_count()
+    fwd_ms = e0.elapsed_time(e1) / args.steps
+    fwd_tps = M * B * T / (fwd_ms * 1e-3)
+    flops = syn.train_flops_per_step(cfg, B) / 3
+    # generate, growing phase: prompt of T/2 positions, then one position per step against the K/V cache
+    n0, n_dec = T // 2, min(64, T // 2)
+    cache = KVCache(eng, B, T)
+    p0, p1 = ev(), ev()
+    p0.record()
+    eng.forward(idx[:, :, :n0].contiguous(), None, save=False, cache=cache)
+    p1.record()
+    new = idx[:, :, n0:n0 + 1].contiguous()
+    eng.forward(new, None, save=False, cache=cache)          # allocates the one-row buffers
+    d0, d1 = ev(), ev()
+    d0.record()
+    for k in range(1, n_dec):
+        eng.forward(idx[:, :, n0 + k:n0 + k + 1].contiguous(), None, save=False, cache=cache)
+    d1.record()
+    torch.cuda.synchronize()
+    dec_ms = d0.elapsed_time(d1) / (n_dec - 1)
+    # the same n_dec positions the way the reference generates them: a full forward over the window per new token
+    r0, r1 = ev(), ev()
+    r0.record()
+    for k in range(2):
+        eng.forward(idx[:, :, :n0 + n_dec // 2].contiguous(), None, save=False)
+    r1.record()
+    torch.cuda.synchronize()
+    recompute_ms = r0.elapsed_time(r1) / 2
+    if rank == 0:
+        pk = peaks()
+        line = {"metric": "inference tokens/s (forward)", "value": fwd_tps * world, "unit": "tokens/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": fwd_ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(args, cfg, B, world), "gpu_launches": launches,
+                "forward": {"ms": fwd_ms, "algorithmic_tflop": flops / 1e12, "tflops": flops / (fwd_ms * 1e-3) / 1e12,
+                            "frac_of_measured_sustained": flops / (fwd_ms * 1e-3) / 1e12 / pk["tc_sustained"]},
+                "generate": {"prompt": n0, "prefill_ms": p0.elapsed_time(p1), "decode_ms_per_position": dec_ms,
+                             "decode_tokens_per_s": M * B / (dec_ms * 1e-3), "kv_cache_bytes": cache.bytes(),
+                             "kv_cache_GBs_read": cache.bytes() * (n0 + n_dec / 2) / T / (dec_ms * 1e-3) / 1e9,
+                             "recompute_ms_per_position": recompute_ms,
+                             "speedup_vs_recompute": recompute_ms / dec_ms},
+                "hbm_bytes_allocated": torch.cuda.max_memory_allocated(dev)}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     from tradeaid_b200 import synthetic as syn
     cfg = syn.CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.config == "c5":
+        run_inference(args, cfg)
     else:
         run_ours(args, cfg)
 

@@ -119,6 +119,17 @@ int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const
                          int32_t G, int32_t B, int32_t T, int32_t H, int32_t hs, float dropout_p, uint64_t seed,
                          void* stream);
 
+/* Decode step of `generate` (model.py:404-446) while the sequence still fits block_size: ONE new query row per
+ * (group, batch) against the first `len` rows of a key/value cache — the reference recomputes the whole window for
+ * every new token; with causal masks and absolute positions the earlier rows do not change, so their keys / values are
+ * cached. q: bf16 [G][B][ld] (ta_attn_tensor.ld = elements between batch rows). k[s], v[s]: caches [G][B][capacity][ld]
+ * (ld = elements between cached positions, kv_batch_stride[s] = elements between batches; k and v of a source share
+ * strides). Per source an independent softmax over positions [0, len), outputs summed; o: bf16 [G][B][ldo], head h at
+ * columns [h*hs, (h+1)*hs). n_src <= 16, hs in {8, 16, 32, 64}. */
+int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v,
+                            const int64_t* kv_batch_stride, int32_t n_src, void* o_bf16, int64_t ldo, int64_t o_gs,
+                            int32_t G, int32_t B, int32_t len, int32_t H, int32_t hs, void* stream);
+
 /* Backward of the above (recompute): given dO (layout of o) produces dq (layout of q), and per source dk, dv (layouts
  * of k[s], v[s]); all bf16. T <= 256 in this build. */
 int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v, int32_t n_src,

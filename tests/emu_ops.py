@@ -109,6 +109,22 @@ def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_st
     _scatter_heads(o, tot, B, T, H, hs, hs)
 
 
+def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None):
+    """One new query row per (group, batch) against cache rows [0, length) of every source (csrc/attention_decode.cu)."""
+    _tick()
+    hq = head_stride_q or hs
+    hkv = head_stride_kv or hs
+    G, B = q.shape[0], q.shape[1]
+    qh = torch.stack([q[..., h * hq:h * hq + hs] for h in range(H)], 2).float()            # [G, B, H, hs]
+    tot = 0
+    for k, v in zip(ks, vs):
+        kh = torch.stack([k[:, :, :length, h * hkv:h * hkv + hs] for h in range(H)], 2).float()   # [G, B, H, len, hs]
+        vh = torch.stack([v[:, :, :length, h * hkv:h * hkv + hs] for h in range(H)], 2).float()
+        sc = torch.einsum("gbhd,gbhtd->gbht", qh, kh) * hs ** -0.5
+        tot = tot + torch.einsum("gbht,gbhtd->gbhd", torch.softmax(sc, -1), vh)
+    o.copy_(tot.reshape(G, B, H * hs).to(o.dtype))
+
+
 def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None,
                   o_src=None):
     _tick()

@@ -102,3 +102,34 @@ def test_stage2_blockdiag_equals_per_head_groups(monkeypatch):
     # and against the reference restatement
     ref_logits, _, ref_grads = R.forward_backward(sd, R.Cfg(T, C, H, L, V, cross), list(idx), list(tgt))
     assert (outs["1"][0] - torch.cat([x.flatten() for x in ref_logits])).abs().max().item() <= 2e-5
+
+
+def test_kv_cache_decode_equals_full_forward():
+    """engine.KVCache host logic (prompt fill, per-position decode, cross-attention caches per source run) in fp32: every
+    step must reproduce the full forward's logits at that position to round-off."""
+    from oracle import restatement as R
+    from tradeaid_b200.engine import KVCache
+    V, cross, T, C, H, L, B = [24, 10, 20, 12], [True, False, True, False], 12, 32, 2, 2, 3
+    eng = Engine(Dims(V, cross, T, C, H, L), "cpu", ops=emu_ops, act_dtype=torch.float32)
+    sd = R.random_state_dict(R.Cfg(T, C, H, L, V, cross), seed=4)
+    nv = eng.layout.named_views(eng.master)
+    for k, v in sd.items():
+        nv[k].copy_(v)
+    g = torch.Generator().manual_seed(9)
+    idx = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V])
+    ref_logits, _ = R.forward(sd, R.Cfg(T, C, H, L, V, cross), list(idx), None) if hasattr(R, "forward") else (None, None)
+    full, _ = eng.forward(idx, None, save=False)
+    full = [x.clone() for x in full]
+    if ref_logits is not None:
+        for a, b in zip(full, ref_logits):
+            assert (a - b).abs().max().item() <= 2e-5
+    cache = KVCache(eng, B)
+    n0 = 5
+    lg, _ = eng.forward(idx[:, :, :n0].contiguous(), None, save=False, cache=cache)
+    assert max((a - b[:, :n0]).abs().max().item() for a, b in zip(lg, full)) <= 1e-6
+    for t in range(n0, T):
+        lg, _ = eng.forward(idx[:, :, t:t + 1].contiguous(), None, save=False, cache=cache)
+        assert cache.length == t + 1
+        assert max((a[:, 0] - b[:, t]).abs().max().item() for a, b in zip(lg, full)) <= 1e-6
+    with pytest.raises(ValueError):
+        eng.forward(idx[:, :, :1].contiguous(), None, save=False, cache=cache)      # cache is full

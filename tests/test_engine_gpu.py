@@ -195,3 +195,36 @@ def test_stage2_blockdiag_is_bit_identical_to_per_head_groups(C, H, monkeypatch)
     assert all(torch.equal(a, b) for a, b in zip(out["1"][0], out["0"][0]))
     assert torch.equal(out["1"][1], out["0"][1])
     assert torch.equal(out["1"][2], out["0"][2])
+
+
+@pytest.mark.parametrize("M,cross,V,B,T,C,H,L,n0", [
+    (3, [True, False, True], [100, 64, 80], 3, 48, 128, 4, 2, 17),
+    (4, [True, False, False, True], [64, 64, 64, 64], 2, 300, 768, 12, 1, 290),      # c5 widths (C=768, H=12), two query tiles
+    (1, [False], [50], 2, 16, 64, 2, 2, 1),
+])
+def test_kv_cache_decode_matches_full_forward(M, cross, V, B, T, C, H, L, n0):
+    """engine.KVCache: prompt of n0 positions through the normal forward, then one position at a time against the cache;
+    every step's logits must match the full forward over the whole sequence (same weights, same bf16 rounding points up
+    to the attention kernel's summation order)."""
+    from tradeaid_b200.engine import Engine, KVCache
+    from tradeaid_b200.params import Dims
+    eng = Engine(Dims(V, cross, T, C, H, L), "cuda")
+    eng.layout.init_(eng.master, generator=torch.Generator(device="cuda").manual_seed(2))
+    eng.master.mul_(3.0)        # sharper attention than N(0, 0.02) init gives
+    g = torch.Generator().manual_seed(3)
+    idx = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V]).cuda()
+    full, _ = eng.forward(idx, None, save=False)
+    full = [x.clone() for x in full]
+    cache = KVCache(eng, B)
+    lg, _ = eng.forward(idx[:, :, :n0].contiguous(), None, save=False, cache=cache)
+    for a, b in zip(lg, full):
+        assert ((a - b[:, :n0]).norm() / b[:, :n0].norm()).item() <= 1e-3
+    steps = list(range(n0, min(T, n0 + 12)))
+    for t in steps:
+        lg, _ = eng.forward(idx[:, :, t:t + 1].contiguous(), None, save=False, cache=cache)
+        assert cache.length == t + 1
+        for a, b in zip(lg, full):
+            rel = ((a[:, 0] - b[:, t]).norm() / b[:, t].norm()).item()
+            assert rel <= 1e-2, (t, rel)
+    with pytest.raises(ValueError):
+        eng.forward(idx[:, :, :2].contiguous(), None, save=False, cache=cache)      # decode takes one position at a time

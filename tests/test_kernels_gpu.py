@@ -473,3 +473,27 @@ def test_attention_dropout_fwd_bwd(lib, G, B, T, H, hs, S):
     for s in range(S):
         ref = kvf[s].grad.view(G, B * T, 2 * C)
         assert (dkv[s].float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("G,B,H,hs,cap,length,S", [(2, 3, 4, 64, 40, 33, 1), (1, 5, 2, 32, 64, 64, 3), (3, 2, 3, 16, 10, 1, 2),
+                                                   (1, 4, 12, 64, 1024, 1000, 3), (2, 2, 4, 8, 7, 5, 1)])
+def test_attention_decode(lib, G, B, H, hs, cap, length, S):
+    """ta_attention_decode (one new query row against a K/V cache, generate's growing phase) vs fp32 torch: per source an
+    independent softmax over the cached positions [0, length), outputs summed (model.py:60-73, 136-159, last row)."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    C = H * hs
+    q = torch.randn(G, B, 3 * C, device="cuda", generator=g).to(torch.bfloat16)              # packed q|k|v row, q first
+    caches = [torch.randn(G, B, cap, 2 * C, device="cuda", generator=g).to(torch.bfloat16) for _ in range(S)]   # per head [k|v]
+    o = torch.zeros(G, B, C, device="cuda", dtype=torch.bfloat16)
+    ks = [c for c in caches]
+    vs = [c[..., hs:] for c in caches]
+    lib.attention_decode(q[..., :C], ks, vs, o, length=length, H=H, hs=hs, head_stride_kv=2 * hs)
+    qh = q[..., :C].float().view(G, B, H, hs)
+    ref = 0
+    for c in caches:
+        kv = c[:, :, :length].float().view(G, B, length, H, 2 * hs)
+        sc = torch.einsum("gbhd,gbthd->gbht", qh, kv[..., :hs]) * hs ** -0.5
+        ref = ref + torch.einsum("gbht,gbthd->gbhd", torch.softmax(sc, -1), kv[..., hs:])
+    ref = ref.reshape(G, B, C)
+    assert (o.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert ((o.float() - ref).norm() / ref.norm()).item() <= 5e-3      # bf16 rounding of the output only

@@ -77,6 +77,26 @@ def test_generate_bookkeeping():
     assert torch.equal(out[2][:, :5], idx[2]) and int(out[2].max()) < g["cfg"]["V"][2]
 
 
+def test_generate_with_kv_cache_matches_recompute():
+    """generate(): the K/V-cache path (growing phase) against the reference's recompute-everything form with the same
+    torch seed — the sampled tokens agree (logits equal up to bf16 summation order; a rare flip of a near-tie sample is
+    tolerated), and past block_size both fall back to the sliding-window full forward."""
+    g, m = _model("m3")
+    m.eval()
+    T = g["cfg"]["T"]          # block_size 8
+    idx = [t[:, :3].cuda() for t in g["idx"]]
+    torch.manual_seed(5)
+    a = m.generate(idx, max_new_tokens=9, modality_to_generate=0, use_cache=True)      # 3 -> 12 > block_size: slides at the end
+    torch.manual_seed(5)
+    b = m.generate(idx, max_new_tokens=9, modality_to_generate=0, use_cache=False)
+    assert [x.shape for x in a] == [x.shape for x in b]
+    same = (a[0] == b[0]).float().mean().item()
+    assert same >= 0.9, same
+    for i in (1, 2):
+        assert torch.equal(a[i], b[i])
+    assert T == 8
+
+
 def test_trainer_matches_golden_curve_and_graph_replay_is_identical():
     from tradeaid_b200.engine import Engine
     from tradeaid_b200.params import Dims

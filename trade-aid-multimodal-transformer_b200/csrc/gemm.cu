@@ -61,6 +61,7 @@ struct GemmParams {
   int stages;          // depth of the A/B smem ring
   int tma_epi;         // 1: TMA-staged epilogue (maps below are valid)
   int nbf, nbb;        // staging buffers per epilogue warp: fp32 chunks / bf16 chunks
+  int nst;             // rotation depth of the store-only buffers (2, or 4 for short-K problems bound by the store path)
   int bf16_direct;     // tma_epi with both outputs: bf16 goes out with row-per-thread stores
   int epi_warp_bytes;
   int m_major;         // tile order, see decode_tile
@@ -121,7 +122,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
                has_bf = p.out_bf16 != nullptr;
     const bool has_load = has_res || has_aux;
     const int nl = has_res ? p.nbf : p.nbb;          // rotation depth of the loaded buffer family
-    const int dbg = p.debug, act = p.act;
+    const int dbg = p.debug, act = p.act, nst = p.nst;
     const float alpha = p.alpha;
     const bool aux_tanh = p.aux_mode == TA_AUX_TANH_BWD;
     const uint32_t wbase = epi_smem + ep * p.epi_warp_bytes;
@@ -203,8 +204,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
             __syncwarp();
             if (lane == 0) { if (PAIR && m_off != 0) mbar_arrive_cluster(tmem_empty0 + 8 * acc); else mbar_arrive_a(tmem_empty0 + 8 * acc); }
           }
-          const uint32_t fbuf = fbuf0 + (has_res ? lb : (int)(sc & 1)) * EPI_F32_BYTES;
-          const uint32_t bbuf = bbuf0 + (has_aux ? lb : (int)(sc & 1)) * EPI_BF16_BYTES;
+          const uint32_t fbuf = fbuf0 + (has_res ? lb : (int)(sc & (uint32_t)(nst - 1))) * EPI_F32_BYTES;
+          const uint32_t bbuf = bbuf0 + (has_aux ? lb : (int)(sc & (uint32_t)(nst - 1))) * EPI_BF16_BYTES;
           if (dbg != 2) {
             if (vb) {
 #pragma unroll
@@ -304,7 +305,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
               if (has_bf && !p.bf16_direct) tma_store_4d(&em.bf16, bbuf, col0, row0, g0, g1);
             }
             bulk_commit_group();
-            bulk_wait_read<1>();      // the store of the previous chunk has drained its buffer
+            // the buffer the next chunk writes has been drained by its store (nst - 1 younger stores may be in flight)
+            if (nst == 4) bulk_wait_read<3>(); else bulk_wait_read<1>();
             if (has_load)
               for (; next_load < c1 && next_load <= c + nl - 1; ++next_load) issue_load(next_load);
           }
@@ -830,9 +832,14 @@ static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes, int ep_wa
     tma_ok = make_epi_map(&em.bf16, p.out_bf16, p.ld_bf16, p.bf16_gs0, p.bf16_gs1, p.M, p.N, p.G0, p.G1, false);
   p.tma_epi = tma_ok ? 1 : 0;
   p.nbf = p.nbb = 0;
+  p.nst = 2;
   if (tma_ok) {
+    // short K, bf16 store only (q/k/v stage 2 forward): the tile's math is a few hundred cycles, the kernel runs at the
+    // rate its TMA stores drain - four 2 KB chunk buffers per warp keep three stores in flight instead of one
+    static const int force_nst = env_int("TA_GEMM_NST", 0);
+    if (!need_f && need_b && !p.aux && ((force_nst == 0 && p.k_blocks <= 4) || force_nst == 4)) p.nst = 4;
     if (need_f) p.nbf = p.res ? 3 : 2;
-    else if (need_b) p.nbb = p.aux ? 3 : 2;
+    else if (need_b) p.nbb = p.aux ? 3 : p.nst;
     if (force_nl == 2 || force_nl == 3) { if (p.res) p.nbf = force_nl; if (p.aux) p.nbb = force_nl; }
     auto epi_bytes = [&]() { return ep_warps * (p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES); };
     // long K: the epilogue has slack, the A/B ring does not - two buffers (no residual prefetch distance of 2) are enough
@@ -950,7 +957,8 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   if (bn == 128 && N > 64 && tiles(128) < num_sms() / 2 && tiles(64) > tiles(128)) bn = 64;
   // CTA pairs (256 x 256 tiles, B split across the pair) for the large problems: a third less L2 -> smem traffic
   static const int use_2cta = env_int("TA_GEMM_2CTA", 1);
-  if (use_2cta && bn == 256 && M >= 256 && N >= 256 && K >= 256 &&
+  static const int min_k_2cta = env_int("TA_GEMM_2CTA_MINK", 128);
+  if (use_2cta && bn == 256 && M >= 256 && N >= 256 && K >= min_k_2cta &&
       groups * ceil_div(M, 2 * BLOCK_M) * ceil_div(N, 256) >= num_sms() / 4)
     return launch_gemm2(A, B, p, st);
   if (bn == 256) return launch_gemm<256>(A, B, p, st);

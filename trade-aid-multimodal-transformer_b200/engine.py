@@ -36,6 +36,30 @@ def _runs(idxs):
     return out
 
 
+class KVCache:
+    """Keys / values of every layer at positions [0, length), for `generate` in the growing phase (model.py:404-446 re-runs
+    the whole window for every new token; while the sequence still fits block_size the earlier positions are unchanged —
+    causal masks, absolute position embeddings — so only the new position is computed against this cache).
+    self_kv[l]: [M, B, capacity, 2C] (K | V of the modality's own stream); cross_kv[l][r]: [n_r, B, capacity, nq_r*2C] per
+    run r of source modalities (engine._kv_runs), laid out like the K/V projection buffers of the forward."""
+
+    def __init__(self, eng, B, capacity=None):
+        d = eng.d
+        self.B = int(B)
+        self.capacity = int(capacity or d.block_size)
+        if self.capacity > d.block_size:
+            raise ValueError("cache capacity exceeds block_size: beyond it the window slides and every position changes")
+        self.length = 0
+        C, dt, dev = d.n_embd, eng.act_dtype, eng.device
+        self.self_kv = [torch.zeros(d.M, self.B, self.capacity, 2 * C, dtype=dt, device=dev) for _ in range(d.n_layer)]
+        self.cross_kv = [[torch.zeros(j1 - j0, self.B, self.capacity, nq * 2 * C, dtype=dt, device=dev)
+                          for j0, j1, nq in eng._kv_runs()] if d.Xc else [] for _ in range(d.n_layer)]
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.self_kv) + \
+            sum(t.numel() * t.element_size() for r in self.cross_kv for t in r)
+
+
 class Engine:
     def __init__(self, dims: Dims, device, ops=None, act_dtype=torch.bfloat16):
         self.d = dims
@@ -163,10 +187,13 @@ class Engine:
         self._drop_step.add_(1)
 
     # ------------------------------------------------------------------------------------------ forward
-    def forward(self, idx, targets=None, save=True, train=False):
+    def forward(self, idx, targets=None, save=True, train=False, cache=None):
         """idx, targets: int64 [M, B, T'] on the device (T' <= block_size). Returns (logits list of fp32 [B, T', V_i],
         losses fp32 [M] or None). With save=True the activations needed by backward() are kept. train=True applies
-        dropout (p = dims.dropout) at the reference's five sites; eval / p = 0 is the deterministic path."""
+        dropout (p = dims.dropout) at the reference's five sites; eval / p = 0 is the deterministic path.
+        cache (a KVCache, inference only): idx holds the positions [cache.length, cache.length + T'). An empty cache is
+        filled by a normal forward over the prompt; afterwards T' must be 1 and the new row attends to the cached keys /
+        values (ta_attention_decode)."""
         d, ops, P = self.d, self.ops, self.P
         pd = float(d.dropout) if train else 0.0
         if pd > 0.0:
@@ -183,12 +210,22 @@ class Engine:
         BT = B * T
         bf, f32 = self.act_dtype, torch.float32
         S = {"B": B, "T": T, "layers": [], "idx": idx, "pd": pd}
+        t0 = 0
+        if cache is not None:
+            if save or train or targets is not None:
+                raise ValueError("the K/V cache is an inference path: save=False, train=False, no targets")
+            t0 = cache.length
+            if cache.B != B or t0 + T > cache.capacity:
+                raise ValueError(f"cache holds {t0} of {cache.capacity} positions for batch {cache.B}; got batch {B}, {T} new")
+            if t0 > 0 and T != 1:
+                raise ValueError("decode steps take one new position at a time")
+        decode = cache is not None and t0 > 0
 
         def nb(name, l, shape, dtype):
             return self.buf(f"{name}.{l}" if save else name, shape, dtype)
 
         x = nb("x0", 0, (M, BT, C), f32)
-        ops.embed_fwd(idx.view(M, BT), P["tok"], self._voff, P["pos"], x, T)
+        ops.embed_fwd(idx.view(M, BT), P["tok"], self._voff, P["pos"][t0:t0 + T] if cache is not None else P["pos"], x, T)
         for l in range(L):
             Sl = {}
             Sl["x0"] = x
@@ -208,8 +245,15 @@ class Engine:
                          out_bf16=self._qkv_groups(qkv, BT))
             o = nb("o", l, (M, BT, C), bf)
             lse = nb("lse", l, (1, M, B, H, T), f32)
-            ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
-                              **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
+            if cache is not None:
+                cache.self_kv[l][:, :, t0:t0 + T].copy_(qkv.view(M, B, T, 3 * C)[..., C:])
+            if decode:
+                kc = cache.self_kv[l]
+                ops.attention_decode(qkv.view(M, B, 3 * C)[..., 0:C], [kc[..., 0:C]], [kc[..., C:2 * C]], o.view(M, B, C),
+                                     length=t0 + 1, H=H, hs=hs)
+            else:
+                ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
+                                  **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
             # projection MLP + residual   model.py:82-91, 224
             p1 = nb("p1", l, (M, BT, C // 2), bf)
             ops.gemm(o, self.W("sa_pw1")[l], bias=P["sa_pb1"][l], act=ACT_TANH, out_bf16=p1)
@@ -230,7 +274,7 @@ class Engine:
                       a_bf=a_bf)
             x = x2
             if d.Xc:
-                x = self._cross_forward(l, Sl, x2, a_bf, B, T, nb, pd)
+                x = self._cross_forward(l, Sl, x2, a_bf, B, T, nb, pd, cache, t0)
             S["layers"].append(Sl)
         # output heads   model.py:339-352
         hf = nb("hf", 0, (M, BT, C), bf)
@@ -261,6 +305,8 @@ class Engine:
                 dls.append(dl)
             S["dlogits"] = dls
         self._saved = S if save else None
+        if cache is not None:
+            cache.length = t0 + T
         return [lg.view(B, T, -1) for lg in logits], losses
 
     def _hid_groups(self, hid, BT, gsz=1):
@@ -285,7 +331,7 @@ class Engine:
             pos += n
         return out
 
-    def _cross_forward(self, l, Sl, x2, a_bf, B, T, nb, pd=0.0):
+    def _cross_forward(self, l, Sl, x2, a_bf, B, T, nb, pd=0.0, cache=None, t0=0):
         """Selective cross-attention of layer l (model.py:136-159, 229-242). Every enabled modality queries the SAME
         snapshot x2 of all other modalities, so all K/V projections are issued before any residual update."""
         d, ops, P = self.d, self.ops, self.P
@@ -301,19 +347,29 @@ class Engine:
                                   stc[0][p * BT:(p + 1) * BT], stc[1][p * BT:(p + 1) * BT])
         qc = nb("qc", l, (Xc, BT, C), bf)
         ops.gemm(hc, self.W("ca_wq")[l].reshape(Xc, C, C), out_bf16=qc)
-        kvs = [None] * M
+        kvs, kv_runs = [None] * M, []
         Wkv = self.W("ca_wkv")[l]  # [sum_j nq_j, H, 2hs, C]
         for j0, j1, nq in self._kv_runs():
             # sources j0..j1-1 have the same number of queriers: one grouped launch (more tiles per launch = fewer
             # partly filled waves of the persistent grid)
             kv = nb(f"kv{j0}", l, (j1 - j0, BT, nq * 2 * C), bf)
             ops.gemm(a_bf[j0:j1], Wkv[d.qoff[j0]:d.qoff[j1]].reshape(j1 - j0, nq * 2 * C, C), out_bf16=kv)
+            kv_runs.append(kv)
             for j in range(j0, j1):
                 kvs[j] = kv[j - j0]
+        decode = cache is not None and t0 > 0
+        if cache is not None:
+            for r, kv in enumerate(kv_runs):
+                cache.cross_kv[l][r][:, :, t0:t0 + T].copy_(kv.view(kv.shape[0], B, T, kv.shape[-1]))
         oc = nb("oc", l, (Xc, BT, C), bf)
         ocs = nb("ocs", l, (Xc, K, 1, BT, C), bf) if K > 1 else None
         lsec = nb("lsec", l, (Xc, K, 1, B, H, T), f32)
         for xi, i in enumerate(d.xc):
+            if decode:     # the new row of querier i against the cached K/V of every other modality
+                ks, vs = self._kv_cache_views(cache.cross_kv[l], i)
+                ops.attention_decode(qc[xi:xi + 1].view(1, B, C), ks, vs, oc[xi:xi + 1].view(1, B, C), length=t0 + 1, H=H,
+                                     hs=hs, head_stride_kv=2 * hs)
+                continue
             ks, vs = self._kv_views(kvs, i)
             ops.attention_fwd(qc[xi:xi + 1], ks, vs, oc[xi:xi + 1], lsec[xi], B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
                               o_src=ocs[xi] if ocs is not None else None,
@@ -344,6 +400,20 @@ class Engine:
                 out.append((j, k, nq))
             j = k
         return out
+
+    def _kv_cache_views(self, run_caches, i):
+        """K and V views [1, B, capacity, *] of querier i inside the cached K/V of each of its sources."""
+        d = self.d
+        C, hs = d.n_embd, d.hs
+        ks, vs = [], []
+        runs = self._kv_runs()
+        for j in d.others(i):
+            r = next(k for k, (j0, j1, _) in enumerate(runs) if j0 <= j < j1)
+            p = d.queriers[j].index(i)
+            blk = run_caches[r][j - runs[r][0]:j - runs[r][0] + 1, :, :, p * 2 * C:(p + 1) * 2 * C]
+            ks.append(blk)
+            vs.append(blk[..., hs:])
+        return ks, vs
 
     def _kv_views(self, kvs, i, grads=False):
         """K and V column views (head 0, dim 0) of querier i inside each source's stacked K/V buffer."""

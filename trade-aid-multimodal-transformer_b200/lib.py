@@ -206,6 +206,24 @@ def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_st
                                      int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
 
 
+def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None):
+    """q: bf16 [G, B, *] (one new row per batch); ks/vs: lists (one per source) of cache views [G, B, capacity, *] whose
+    column 0 is head 0 / dim 0; o: bf16 [G, B, H*hs]. Attends to cached positions [0, length)."""
+    n_src = len(ks)
+    G, B = q.shape[0], q.shape[1]
+    hq = head_stride_q if head_stride_q is not None else hs
+    hkv = head_stride_kv if head_stride_kv is not None else hs
+    assert q.dim() == 3 and o.dim() == 3 and o.stride(-1) == 1 and q.stride(-1) == 1
+    qa = (TaAttnTensor * 1)(TaAttnTensor(q.data_ptr(), q.stride(1), hq, q.stride(0)))
+    for t in list(ks) + list(vs):
+        assert t.dim() == 4 and t.shape[0] == G and t.shape[1] == B and t.shape[2] >= length and t.stride(-1) == 1
+    ka = (TaAttnTensor * n_src)(*[TaAttnTensor(k.data_ptr(), k.stride(2), hkv, k.stride(0)) for k in ks])
+    va = (TaAttnTensor * n_src)(*[TaAttnTensor(v.data_ptr(), v.stride(2), hkv, v.stride(0)) for v in vs])
+    bs = (C.c_int64 * n_src)(*[k.stride(1) for k in ks])
+    _check(_lib.ta_attention_decode(qa, ka, va, bs, n_src, _ptr(o), o.stride(1), o.stride(0), G, B, int(length), H, hs,
+                                    _stream()))
+
+
 # ---------------------------------------------------------------------------------------------------- row ops
 def _sig(name, *argtypes, restype=C.c_int32):
     fn = getattr(_lib, name)

@@ -181,9 +181,7 @@ class MultimodalTransformer(nn.Module):
         eng = self._require_engine()
         M = self.num_modalities
         idx = torch.stack([t.to(eng.device, torch.int64) for t in idx_list[:M]]).contiguous()
-        if self.training or getattr(self, "_dirty", True):
-            eng.shadows_stale = True     # a stock optimizer updates the fp32 views in place between forwards
-            self._dirty = False
+        self._sync_shadows(eng)
         B, T = idx.shape[1], idx.shape[2]
         if targets_list is None:
             logits, _ = eng.forward(idx, None, save=False, train=self.training)
@@ -199,23 +197,52 @@ class MultimodalTransformer(nn.Module):
         return logits, [losses[i] for i in range(M)]
 
     @torch.no_grad()
-    def generate(self, idx_list, max_new_tokens=1, modality_to_generate=0):
-        """Same sequence bookkeeping as the reference (model.py:404-446): crop to block_size, full forward, sample the
-        last position of the target modality, append; other modalities are padded with their last token or cropped."""
+    def generate(self, idx_list, max_new_tokens=1, modality_to_generate=0, use_cache=True):
+        """Same sequence bookkeeping and sampling as the reference (model.py:404-446): crop to block_size, logits of the
+        last position of the target modality, softmax + torch.multinomial, append; other modalities are padded with their
+        last token or cropped. The reference runs the full forward over the window for every new token. Here, while the
+        sequences still fit block_size (no cropping: earlier positions keep their activations), the first step fills a
+        K/V cache and every later step computes only the new position against it (engine.KVCache, ta_attention_decode);
+        once the window starts to slide, positions shift and the full forward is used, as in the reference.
+        use_cache=False forces the reference's recompute-everything form."""
         T = self._dims.block_size
+        mg = modality_to_generate
         seqs = [idx.clone() for idx in idx_list]
+        eng = self._require_engine()
+        use_cache = use_cache and not (self.training and self._dims.dropout > 0.0)   # dropout draws need the full pass
+        cache = None
         for _ in range(max_new_tokens):
-            cond = [s[:, -T:] for s in seqs]
-            logits_list, _ = self(cond)
-            probs = F.softmax(logits_list[modality_to_generate][:, -1, :], dim=-1)
+            n = seqs[mg].shape[1]
+            M = self.num_modalities
+            fits = use_cache and n <= T and all(s.shape[1] == n and s.shape[0] == seqs[mg].shape[0] for s in seqs[:M])
+            if fits and (cache is None or cache.length == n - 1):
+                from .engine import KVCache
+                self._sync_shadows(eng)
+                if cache is None:
+                    cache = KVCache(eng, seqs[mg].shape[0], T)
+                    new = torch.stack([s.to(eng.device, torch.int64) for s in seqs[:M]]).contiguous()
+                else:
+                    new = torch.stack([s[:, -1:].to(eng.device, torch.int64) for s in seqs[:M]]).contiguous()
+                logits, _ = eng.forward(new, None, save=False, train=False, cache=cache)
+                last = logits[mg][:, -1, :]
+            else:
+                cache = None
+                logits_list, _ = self([s[:, -T:] for s in seqs])
+                last = logits_list[mg][:, -1, :]
+            probs = F.softmax(last, dim=-1)
             nxt = torch.multinomial(probs, num_samples=1)
-            seqs[modality_to_generate] = torch.cat((seqs[modality_to_generate], nxt.to(seqs[modality_to_generate].device)), dim=1)
-            tl = seqs[modality_to_generate].shape[1]
+            seqs[mg] = torch.cat((seqs[mg], nxt.to(seqs[mg].device)), dim=1)
+            tl = seqs[mg].shape[1]
             for i in range(self.num_modalities):
-                if i == modality_to_generate:
+                if i == mg:
                     continue
                 if seqs[i].shape[1] < tl:
                     seqs[i] = torch.cat((seqs[i], seqs[i][:, -1:]), dim=1)
                 elif seqs[i].shape[1] > tl:
                     seqs[i] = seqs[i][:, :tl]
         return seqs
+
+    def _sync_shadows(self, eng):
+        if self.training or getattr(self, "_dirty", True):
+            eng.shadows_stale = True     # a stock optimizer updates the fp32 views in place between forwards
+            self._dirty = False
