@@ -5,9 +5,11 @@
 // Same math as model.py:60-73 / 136-159 for the last row: per source an independent softmax(q k^T * hs^-0.5) v over
 // positions [0, len), outputs of the sources summed.
 //
-// HBM-bound (every cached K and V row is read once per step): one warp per (group, batch, head); a lane scores one
-// cached position per 32-position chunk (its K row is 2*hs contiguous bytes), online softmax with warp-shuffle
-// reductions, then the lanes split the head dimension and walk the chunk's V rows (coalesced 2*hs-byte rows).
+// HBM-bound (every cached K and V row is read once per step): one warp per (group, batch, head); a lane owns one cached
+// position per 32-position chunk - it scores its K row (2*hs contiguous bytes), the online softmax runs on warp-shuffle
+// reductions, and it accumulates p * (its V row) privately; the lanes are summed once per source by recursive halving.
+// All 16-byte loads of a chunk are independent (a first version that walked the V rows one after the other ran at
+// 0.9 TB/s on c5 - one dependent load per step of the chain).
 #include <cuda_bf16.h>
 
 #include "../../include/tradeaid_b200.h"
@@ -29,6 +31,32 @@ struct AttnDecodeParams {
   int n_src, G, B, H, hs, len;
   float scale_log2;     // hs^-0.5 * log2(e)
 };
+
+// Sum over the 32 lanes of a per-lane array acc[HS] by recursive halving: at each step a lane keeps one half of its
+// live elements and hands the other half to its partner, so the whole reduction costs HS - 1 (+ a few) shuffles instead
+// of 5 * HS. Afterwards acc[0] (and acc[1] for HS = 64) hold complete sums: HS = 64 -> dims 2*lane, 2*lane + 1;
+// HS = 32 -> dim lane; HS = 16 -> dim lane >> 1; HS = 8 -> dim lane >> 2 (duplicated over the lanes that share a dim).
+template <int HS>
+__device__ __forceinline__ void lane_reduce(float (&acc)[HS], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int mask = 16 >> s;
+    const int nb = (HS >> s) > 1 ? (HS >> s) : 1;     // live elements before this step (compile time after unrolling)
+    if (nb > (HS == 64 ? 2 : 1)) {
+      const int half = nb / 2;
+      const bool up = (lane & mask) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float send = up ? acc[i] : acc[i + half];
+        const float keep = up ? acc[i + half] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+      }
+    } else {
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], mask);
+      if (HS == 64) acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], mask);
+    }
+  }
+}
 
 template <int HS>
 __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid_constant__ AttnDecodeParams p) {
@@ -56,33 +84,46 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
       }
     }
   }
-  constexpr int DPL = HS > 32 ? 2 : 1;          // head dims per lane in the P.V phase
-  const bool d_ok = lane * DPL < HS;
   float out0 = 0.f, out1 = 0.f;
   for (int s = 0; s < p.n_src; ++s) {
-    const __nv_bfloat16* kb = p.k[s] + g * p.kv_gs[s] + (long long)b * p.kv_bs[s] + (long long)h * p.kv_hs[s];
-    const __nv_bfloat16* vb = p.v[s] + g * p.kv_gs[s] + (long long)b * p.kv_bs[s] + (long long)h * p.kv_hs[s];
+    const long long base = g * p.kv_gs[s] + (long long)b * p.kv_bs[s] + (long long)h * p.kv_hs[s];
+    const __nv_bfloat16* kb = p.k[s] + base;
+    const __nv_bfloat16* vb = p.v[s] + base;
     const long long ld = p.kv_ld[s];
-    float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+    // A lane owns one cached position per 32-position chunk in BOTH phases: it scores its K row and accumulates
+    // p * (its V row) into a private acc[HS]; the lanes are summed once per source. Every load of a chunk (2 * HS / 8
+    // 16-byte loads per lane) is independent and in flight together.
+    float m = -INFINITY, l = 0.f;
+    float acc[HS];
+#pragma unroll
+    for (int i = 0; i < HS; ++i) acc[i] = 0.f;
     for (int p0 = 0; p0 < p.len; p0 += 32) {
       const int pos = p0 + lane;
-      float sc = -INFINITY;
-      if (pos < p.len) {
-        const __nv_bfloat16* kr = kb + (long long)pos * ld;
-        float acc = 0.f;
+      const bool ok = pos < p.len;
+      uint4 ku[HS / 8], vu[HS / 8];
+      if (ok) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)pos * ld);
+        const uint4* vr = reinterpret_cast<const uint4*>(vb + (long long)pos * ld);
 #pragma unroll
-        for (int i = 0; i < HS / 8; ++i) {
-          const uint4 u = *reinterpret_cast<const uint4*>(kr + 8 * i);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+        for (int i = 0; i < HS / 8; ++i) ku[i] = __ldg(kr + i);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h2[j]);
-            acc = fmaf(q[8 * i + 2 * j], f.x, acc);
-            acc = fmaf(q[8 * i + 2 * j + 1], f.y, acc);
-          }
-        }
-        sc = acc;
+        for (int i = 0; i < HS / 8; ++i) vu[i] = __ldg(vr + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < HS / 8; ++i) ku[i] = vu[i] = make_uint4(0, 0, 0, 0);
       }
+      float sc = 0.f;
+#pragma unroll
+      for (int i = 0; i < HS / 8; ++i) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&ku[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          sc = fmaf(q[8 * i + 2 * j], f.x, sc);
+          sc = fmaf(q[8 * i + 2 * j + 1], f.y, sc);
+        }
+      }
+      if (!ok) sc = -INFINITY;
       float cm = sc;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
@@ -93,31 +134,32 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
       l = l * corr + ps;
-      a0 *= corr; a1 *= corr;
       m = m_new;
-      const int n = p.len - p0 < 32 ? p.len - p0 : 32;
-      const __nv_bfloat16* vr = vb + (long long)p0 * ld + lane * DPL;
-      for (int j = 0; j < n; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, pr, j);
-        if (d_ok) {
-          if (DPL == 2) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vr + (long long)j * ld));
-            a0 = fmaf(pj, f.x, a0);
-            a1 = fmaf(pj, f.y, a1);
-          } else {
-            a0 = fmaf(pj, __bfloat162float(vr[(long long)j * ld]), a0);
-          }
+#pragma unroll
+      for (int i = 0; i < HS / 8; ++i) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vu[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          acc[8 * i + 2 * j] = fmaf(pr, f.x, acc[8 * i + 2 * j] * corr);
+          acc[8 * i + 2 * j + 1] = fmaf(pr, f.y, acc[8 * i + 2 * j + 1] * corr);
         }
       }
     }
+    lane_reduce<HS>(acc, lane);
     const float inv = 1.f / l;
-    out0 += a0 * inv;
-    out1 += a1 * inv;
+    out0 += acc[0] * inv;
+    if (HS == 64) out1 += acc[1] * inv;
   }
-  if (d_ok) {
-    __nv_bfloat16* op = p.o + g * p.o_gs + (long long)b * p.o_ld + (long long)h * HS + lane * DPL;
-    if (DPL == 2) *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(out0, out1);
-    else *op = __float2bfloat16_rn(out0);
+  __nv_bfloat16* op = p.o + g * p.o_gs + (long long)b * p.o_ld + (long long)h * HS;
+  if (HS == 64) {
+    *reinterpret_cast<__nv_bfloat162*>(op + 2 * lane) = __floats2bfloat162_rn(out0, out1);
+  } else if (HS == 32) {
+    op[lane] = __float2bfloat16_rn(out0);
+  } else if (HS == 16) {
+    if ((lane & 1) == 0) op[lane >> 1] = __float2bfloat16_rn(out0);
+  } else {
+    if ((lane & 3) == 0) op[lane >> 2] = __float2bfloat16_rn(out0);
   }
 }
 
@@ -143,7 +185,7 @@ extern "C" int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_te
                  "ta_attention_decode: k cache of source %d must be 16-byte aligned (ptr, strides)", s);
     TA_CHECK_ARG(k[s].ld == v[s].ld && k[s].head_stride == v[s].head_stride && k[s].gs == v[s].gs,
                  "ta_attention_decode: k and v of a source must share strides");
-    TA_CHECK_ARG((reinterpret_cast<uintptr_t>(v[s].ptr) & 3) == 0, "ta_attention_decode: v cache misaligned");
+    TA_CHECK_ARG((reinterpret_cast<uintptr_t>(v[s].ptr) & 15) == 0, "ta_attention_decode: v cache must be 16-byte aligned");
     p.k[s] = static_cast<const __nv_bfloat16*>(k[s].ptr);
     p.v[s] = static_cast<const __nv_bfloat16*>(v[s].ptr);
     p.kv_ld[s] = k[s].ld; p.kv_hs[s] = k[s].head_stride; p.kv_gs[s] = k[s].gs; p.kv_bs[s] = kv_batch_stride[s];

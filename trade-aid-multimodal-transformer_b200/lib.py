@@ -178,6 +178,12 @@ _lib.ta_attention_fwd.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTenso
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_void_p]
 
 
+_lib.ta_attention_decode.restype = C.c_int32
+_lib.ta_attention_decode.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor),
+                                     C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+
+
 def _attn_tensor(t, head_stride):
     """t: bf16 view [G, B*T, >=H*hs] (or [B*T, ...] for G = 1) whose column 0 is head 0 / dim 0."""
     assert t.element_size() == 2 and t.stride(-1) == 1
