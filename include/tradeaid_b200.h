@@ -174,6 +174,17 @@ int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, cons
 int32_t ta_cross_entropy(const float* logits, int64_t ldl, const int64_t* targets, float* row_loss, float* loss_mean,
                          void* dlogits_bf16, int64_t ldd, int64_t rows, int32_t V, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ K8: evaluation metrics
+ * Directional metrics of one modality for one batch (training_utils.py:183-330, calculate_evaluation_metrics): from the
+ * LAST-position logits (fp32, row r at last_logits + r*ld) the arg-max token's value, its direction sign and the actual
+ * next value's sign against the previous input value (vocab_values[prev_tokens[r*prev_stride]]; against 0 when
+ * is_percentage, prev_tokens may then be NULL), and the softmax mass on the tokens of the predicted direction.
+ * counts[0] += wins, counts[1] += losses, certainty[0] += sum of masses (device accumulators: estimate_loss adds
+ * eval_iters batches and reads once). vocab_values: fp64 [V], the numeric vocabulary (python floats are doubles). */
+int32_t ta_directional_metrics(const float* last_logits, int64_t ld, const double* vocab_values, const int64_t* prev_tokens,
+                               int64_t prev_stride, const int64_t* actual_tokens, int64_t actual_stride, int32_t rows,
+                               int32_t V, int32_t is_percentage, int64_t* counts, double* certainty, void* stream);
+
 /* bias gradients: out[g, c] = sum_r dy[g, r, c] (dy bf16 [G][rows][ld]); deterministic two-stage reduction. */
 int64_t ta_colsum_workspace_floats(int64_t rows, int32_t N, int32_t G);
 int32_t ta_colsum_bf16(const void* dy_bf16, int64_t ld, int64_t gs, float* out, int64_t out_gs, float* workspace,

@@ -262,3 +262,16 @@ def adamw_step(p, g, m, v, shadow, scalars_dev, beta1=0.9, beta2=0.999, eps=1e-8
     p.sub_(step_size * (m / (v.sqrt() / bc2s + eps)))
     if shadow is not None:
         shadow.copy_(p.to(shadow.dtype))
+
+
+def directional_metrics(last_logits, vocab_values, prev_tokens, actual_tokens, is_percentage, counts, certainty):
+    """csrc/metrics.cu on CPU tensors."""
+    _tick()
+    x = last_logits.float()
+    ref = torch.zeros(x.shape[0], dtype=torch.float64) if is_percentage else vocab_values[prev_tokens]
+    ps = torch.sign(vocab_values[x.argmax(-1)] - ref)
+    as_ = torch.sign(vocab_values[actual_tokens] - ref)
+    counts[0] += int((ps == as_).sum())
+    counts[1] += int((ps != as_).sum())
+    probs = torch.softmax(x, -1).double()
+    certainty[0] += float((probs * (torch.sign(vocab_values[None, :] - ref[:, None]) == ps[:, None])).sum())

@@ -106,7 +106,13 @@ def test_get_batch_bit_exact_through_module_globals():
 def test_directional_metrics_match_reference():
     from tradeaid_b200 import training_utils as tu
     g = load_golden("metrics.pt")
-    w, l, c, p = tu.calculate_evaluation_metrics(g["logits"], g["xb"], g["yb"], 3, g["vocabs"], g["params"], None)
+    with pytest.raises(RuntimeError):       # CPU tensors and no kernel namespace: the product refuses, it has no CPU path
+        tu.calculate_evaluation_metrics(g["logits"], g["xb"], g["yb"], 3, g["vocabs"], g["params"], None)
+    tu._ops_override = emu_ops              # host logic (eligibility rules, accumulators) over the CPU emulation of the kernel
+    try:
+        w, l, c, p = tu.calculate_evaluation_metrics(g["logits"], g["xb"], g["yb"], 3, g["vocabs"], g["params"], None)
+    finally:
+        tu._ops_override = None
     rw, rl, rc, rp = g["result"]
     assert w == rw and l == rl and p == rp
     for a, b in zip(c, rc):

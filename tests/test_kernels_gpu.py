@@ -497,3 +497,34 @@ def test_attention_decode(lib, G, B, H, hs, cap, length, S):
     ref = ref.reshape(G, B, C)
     assert (o.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
     assert ((o.float() - ref).norm() / ref.norm()).item() <= 5e-3      # bf16 rounding of the output only
+
+
+def test_directional_metrics_kernel_matches_reference_golden(lib):
+    """ta_directional_metrics against the reference's own calculate_evaluation_metrics (tests/golden/metrics.pt, made by
+    /root/reference/training_utils.py:215-330): value data, percentage data, a non-numeric vocabulary; plus accumulation
+    over several calls and a batch larger than one shared-memory pass."""
+    from conftest import load_golden
+    from tradeaid_b200 import training_utils as tu
+    g = load_golden("metrics.pt")
+    cu = lambda ts: [t.cuda() for t in ts]  # noqa: E731
+    w, l, c, p = tu.calculate_evaluation_metrics(cu(g["logits"]), cu(g["xb"]), cu(g["yb"]), 3, g["vocabs"], g["params"], None)
+    rw, rl, rc, rp = g["result"]
+    assert w == rw and l == rl and p == rp
+    for a, b in zip(c, rc):
+        assert abs(a - b) <= 1e-5
+    # large batch (3 passes of 1024 samples) against the torch formulation, accumulated twice
+    gen = torch.Generator().manual_seed(4)
+    B, V = 2500, 333
+    logits = torch.randn(B, 3, V, generator=gen)
+    vals = torch.randn(V, generator=gen, dtype=torch.float64).round(decimals=1)       # ties in value -> zero directions
+    xb, yb = torch.randint(0, V, (B, 5), generator=gen), torch.randint(0, V, (B, 5), generator=gen)
+    counts = torch.zeros(2, dtype=torch.int64, device="cuda")
+    cert = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        lib.directional_metrics(logits.cuda()[:, -1, :], vals.cuda(), xb.cuda()[:, -1], yb.cuda()[:, -1], False, counts, cert)
+    last = logits[:, -1, :]
+    ref = vals[xb[:, -1]]
+    ps, as_ = torch.sign(vals[last.argmax(-1)] - ref), torch.sign(vals[yb[:, -1]] - ref)
+    mass = (torch.softmax(last, -1).double() * (torch.sign(vals[None, :] - ref[:, None]) == ps[:, None])).sum()
+    assert counts.tolist() == [2 * int((ps == as_).sum()), 2 * int((ps != as_).sum())]
+    assert abs(float(cert) - 2 * float(mass)) <= 1e-6 * B

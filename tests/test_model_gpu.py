@@ -147,6 +147,59 @@ def test_feeder_bit_exact_on_device():
     tu._stores.clear()
 
 
+def test_estimate_loss_matches_oracle(capsys):
+    """training_utils.estimate_loss (training_utils.py:387-520) on the device: mean summed loss and directional counts of
+    eval_iters batches per split, against the oracle restatement fed the same batches (same torch seed -> same indices)."""
+    from oracle import restatement as R
+    from tradeaid_b200 import model as tm, training_utils as tu
+    g, m = _model("m3")
+    c = g["cfg"]
+    V, T, B, iters = c["V"], c["T"], 5, 3
+    gen = torch.Generator().manual_seed(12)
+    full = [torch.randint(0, v, (400,), generator=gen) for v in V]
+    n_val = 80
+    tu.configure(device="cuda", batch_size=B, block_size=T, eval_iters=iters)
+    tu._stores.clear()
+    tu.all_train_sets = [d[:-n_val].tolist() for d in full]
+    tu.all_val_sets = [d[-n_val:].clone() for d in full]
+    tu.all_vocabularies = [[0.25 * k - 3.0 for k in range(V[0])], [float(k - 1) for k in range(V[1])], [f"s{k}" for k in range(V[2])]]
+    tu.all_modality_params = [["s", i, None, i == 1, None, None, None, None, c["cross"][i], f"m{i}"] for i in range(3)]
+    tu.file_lengths = [400]
+    tu.num_modalities = 3
+    tu.is_percents = False
+    tu.m = m
+    m.train()
+    torch.manual_seed(21)
+    out = tu.estimate_loss(7, 100)
+    assert m.training                                   # estimate_loss restores train mode (training_utils.py:519)
+    printed = capsys.readouterr().out
+    # the oracle on the same batches
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items() if not k.endswith(".tril")}
+    cfg = R.Cfg(T, c["C"], c["H"], c["L"], V, c["cross"])
+    torch.manual_seed(21)
+    for split, data in (("train", [d[:-n_val] for d in full]), ("val", [d[-n_val:] for d in full])):
+        tot, wins, losses = [], [0, 0, 0], [0, 0, 0]
+        for _ in range(iters):
+            ix = R.batch_starting_indices(len(data[0]), T, B, split, [400], False)
+            xb, yb = R.gather_batch(data, ix, T)
+            logits, ls = R.forward(sd, cfg, xb, yb)
+            tot.append(float(sum(ls)))
+            w, l, _, _ = R.directional_metrics(logits, xb, yb, tu.all_vocabularies, tu.all_modality_params)
+            wins = [a + b for a, b in zip(wins, w)]
+            losses = [a + b for a, b in zip(losses, l)]
+        assert abs(out[split] - sum(tot) / iters) <= 2e-3 * abs(sum(tot) / iters)
+        disp = "Train Set" if split == "train" else "Val Set"
+        block = printed.split(f"DIRECTIONAL METRICS - {disp}")[1]
+        for i in (0, 1):      # arg-max of bf16-path logits vs fp32 logits can flip on a near-tie: allow one sample
+            import re
+            mm = re.search(rf"m{i}\s+(\d+)/(\d+)", block)
+            assert mm and int(mm.group(2)) == wins[i] + losses[i] == iters * B
+            assert abs(int(mm.group(1)) - wins[i]) <= 1
+        assert "m2: No data processed (non-numeric)" in block
+    tu._stores.clear()
+    tu.m = None
+
+
 def test_200_step_loss_curve_vs_oracle():
     """North-star criterion: the 200-step loss curve matches the fp32 reference within 1e-2 absolute (identical
     batches, identical initial weights, lr 1e-3)."""

@@ -364,6 +364,23 @@ def colsum(dy, out, workspace):
                    _stream()))
 
 
+_dir_metrics = _sig("ta_directional_metrics", _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _P)
+
+
+def directional_metrics(last_logits, vocab_values, prev_tokens, actual_tokens, is_percentage, counts, certainty):
+    """last_logits fp32 [B, V] view (last position; any row stride); vocab_values fp64 [V]; prev_tokens / actual_tokens
+    int64 [B] views (any stride; prev may be None for percentage data); counts int64 [2] and certainty fp64 [1] are
+    device accumulators (+=)."""
+    import torch
+    Bn, V = last_logits.shape
+    assert last_logits.dtype == torch.float32 and last_logits.stride(1) == 1 and vocab_values.dtype == torch.float64
+    assert vocab_values.is_contiguous() and vocab_values.numel() == V
+    assert actual_tokens.dtype == torch.int64 and counts.dtype == torch.int64 and certainty.dtype == torch.float64
+    _check(_dir_metrics(_ptr(last_logits), last_logits.stride(0), _ptr(vocab_values), _ptr(prev_tokens),
+                        prev_tokens.stride(0) if prev_tokens is not None else 0, _ptr(actual_tokens), actual_tokens.stride(0),
+                        Bn, V, 1 if is_percentage else 0, _ptr(counts), _ptr(certainty), _stream()))
+
+
 def cast_pad(src, dst):
     """src fp32 [G, R, Cs] (inner stride 1), dst bf16 [G, Rd, Cd] with Rd >= R, Cd >= Cs: zero padded cast."""
     G, R, Cs = src.shape

@@ -83,48 +83,68 @@ def get_batch(split, is_training):
 
 
 # ------------------------------------------------------------------------------------------------ metrics
-def _direction_table(vocab, is_percentage_data, device):
-    """values of a numeric vocabulary as a device tensor (float64 keeps python-float comparisons exact)."""
-    return torch.tensor([float(v) for v in vocab], dtype=torch.float64, device=device)
+_vocab_tables = {}
 
 
-def calculate_evaluation_metrics(logits_list, xb_list, yb_list, num_modalities, all_vocabularies, all_modality_params,
-                                 all_file_info):
-    """training_utils.py:215-330, vectorised over the batch: directional wins / losses of the arg-max prediction at the
-    last position against the actual next value, and the probability mass on the predicted direction."""
-    wins = [0] * num_modalities
-    losses = [0] * num_modalities
-    cert = [0.0] * num_modalities
-    processed = [0] * num_modalities
+def _vocab_table(vocab, device):
+    """Values of a numeric vocabulary as a device fp64 tensor (python floats are doubles: the comparisons of
+    training_utils.py:198-211 stay exact). Cached per vocabulary object."""
+    key = (id(vocab), len(vocab), str(device))
+    ent = _vocab_tables.get(key)
+    if ent is None or ent[0] is not vocab:
+        ent = (vocab, torch.tensor([float(v) for v in vocab], dtype=torch.float64, device=device))
+        _vocab_tables[key] = ent
+    return ent[1]
+
+
+def _metric_ops(device):
+    if _ops_override is not None:
+        return _ops_override
+    if torch.device(device).type != 'cuda':
+        raise RuntimeError("tradeaid_b200.training_utils computes the directional metrics with a CUDA kernel "
+                           "(ta_directional_metrics); logits must live on the GPU - there is no CPU path")
+    from . import lib
+    return lib
+
+
+def _accumulate_metrics(logits_list, xb_list, yb_list, num_modalities, all_vocabularies, all_modality_params, counts, cert,
+                        processed):
+    """One ta_directional_metrics launch per numeric modality: counts int64 [M, 2] (wins, losses) and cert fp64 [M] are
+    device accumulators; processed (host list) counts the batches that took part (training_utils.py:262)."""
     for i in range(num_modalities):
         if not (len(logits_list) > i and len(yb_list) > i):
             continue
         vocab = all_vocabularies[i]
-        is_pct = all_modality_params[i][3]
+        is_pct = bool(all_modality_params[i][3])
         numeric = all(isinstance(v, numbers.Number) for v in vocab)
         y = yb_list[i]
         if not (numeric and y.ndim >= 2 and y.shape[1] >= (1 if is_pct else 2) and y.shape[0] > 0):
             continue
-        processed[i] = 1
-        last = logits_list[i][:, -1, :].float()
+        processed[i] += 1
+        if not is_pct and xb_list[i].shape[1] < 1:
+            continue  # no previous value: direction undefined for every sample (training_utils.py:278-287)
+        last = logits_list[i][:, -1, :]
+        if last.dtype != torch.float32:
+            last = last.float()
         dev = last.device
-        vals = _direction_table(vocab, is_pct, dev)
-        pred_v = vals[last.argmax(-1)]
-        act_v = vals[y[:, -1].to(dev)]
-        if is_pct:
-            ref = torch.zeros_like(pred_v)
-            tok_sign = torch.sign(vals)[None, :].expand(last.shape[0], -1)
-        else:
-            if xb_list[i].shape[1] < 1:
-                continue  # no previous value: direction undefined for every sample (training_utils.py:278-287)
-            ref = vals[xb_list[i][:, -1].to(dev)]
-            tok_sign = torch.sign(vals[None, :] - ref[:, None])
-        ps, as_ = torch.sign(pred_v - ref), torch.sign(act_v - ref)
-        wins[i] = int((ps == as_).sum())
-        losses[i] = int((ps != as_).sum())
-        probs = F.softmax(last, dim=-1).double()
-        cert[i] = float((probs * (tok_sign == ps[:, None])).sum())
-    return wins, losses, cert, processed
+        ops = _metric_ops(dev)
+        prev = None if is_pct else xb_list[i][:, -1].to(dev)
+        ops.directional_metrics(last, _vocab_table(vocab, dev), prev, y[:, -1].to(dev), is_pct, counts[i], cert[i:i + 1])
+
+
+def calculate_evaluation_metrics(logits_list, xb_list, yb_list, num_modalities, all_vocabularies, all_modality_params,
+                                 all_file_info):
+    """training_utils.py:215-330 on the device: directional wins / losses of the arg-max prediction at the last position
+    against the actual next value, and the probability mass on the predicted direction — one kernel per modality and
+    ONE read-back per call (the reference does batch x vocabulary .item() calls)."""
+    dev = logits_list[0].device if len(logits_list) else 'cpu'
+    counts = torch.zeros(num_modalities, 2, dtype=torch.int64, device=dev)
+    cert = torch.zeros(num_modalities, dtype=torch.float64, device=dev)
+    processed = [0] * num_modalities
+    _accumulate_metrics(logits_list, xb_list, yb_list, num_modalities, all_vocabularies, all_modality_params, counts, cert,
+                        processed)
+    c, ce = counts.tolist(), cert.tolist()
+    return [r[0] for r in c], [r[1] for r in c], [float(x) for x in ce], [min(p, 1) for p in processed]
 
 
 def estimate_loss(current_step=None, max_steps=None):
@@ -139,22 +159,26 @@ def estimate_loss(current_step=None, max_steps=None):
         batch_calc = f' * {batch_size} batches = {eval_iters * batch_size} samples'
         print(f'Evaluation: {step_info}{state.title()} set ({eval_iters} iterations{batch_calc}) | {current_time}')
         tot_proc = [0] * num_modalities
-        tot_ok = [0] * num_modalities
-        tot_bad = [0] * num_modalities
-        tot_cert = [0.0] * num_modalities
+        counts = cert = None
         total_losses = []
         for k in range(eval_iters):
             xb_list, yb_list = get_batch(state, 0)
             with torch.no_grad():
                 logits_list, losses_list = m(xb_list, yb_list)
             if losses_list and all(l is not None for l in losses_list):
-                total_losses.append(sum(losses_list).item())
+                total_losses.append(sum(losses_list).detach())
             else:
                 print(f"Warning: Iteration {k} losses not calculated, skipping")
-            ok, bad, cert, proc = calculate_evaluation_metrics(logits_list, xb_list, yb_list, num_modalities,
-                                                               all_vocabularies, all_modality_params, all_file_info)
-            for i in range(num_modalities):
-                tot_ok[i] += ok[i]; tot_bad[i] += bad[i]; tot_cert[i] += cert[i]; tot_proc[i] += proc[i]
+            if counts is None:   # device accumulators: one read-back per split instead of B*V .item() calls per batch
+                dev = logits_list[0].device
+                counts = torch.zeros(num_modalities, 2, dtype=torch.int64, device=dev)
+                cert = torch.zeros(num_modalities, dtype=torch.float64, device=dev)
+            _accumulate_metrics(logits_list, xb_list, yb_list, num_modalities, all_vocabularies, all_modality_params,
+                                counts, cert, tot_proc)
+        total_losses = torch.stack(total_losses).tolist() if total_losses else []
+        c = counts.tolist() if counts is not None else [[0, 0]] * num_modalities
+        tot_ok, tot_bad = [r[0] for r in c], [r[1] for r in c]
+        tot_cert = cert.tolist() if cert is not None else [0.0] * num_modalities  # noqa: F841 (reference keeps it too)
         out[state] = sum(total_losses) / len(total_losses) if total_losses else float('nan')
         disp = 'Train Set' if state == 'train' else 'Val Set'
         print(f"\nDIRECTIONAL METRICS - {disp} (Correct/Total)")
