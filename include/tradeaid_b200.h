@@ -174,6 +174,18 @@ int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, cons
 int32_t ta_cross_entropy(const float* logits, int64_t ldl, const int64_t* targets, float* row_loss, float* loss_mean,
                          void* dlogits_bf16, int64_t ldd, int64_t rows, int32_t V, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ K7b: augmentation
+ * data_utils.add_rand_to_data_points (data_utils.py:293-358; the `[2]` quirk of get_batch, training_utils.py:353-360) on
+ * one modality of the device-resident token store, bit-exact to the host loop INCLUDING the consumption of Python's
+ * Mersenne-Twister stream: words = the next W 32-bit outputs of the generator (pre-drawn by the host); every eligible
+ * token (rand_size < v < vocab_size - rand_size), in index order, takes the next word whose top bit_length(2*rand_size+1)
+ * bits are < 2*rand_size+1 (CPython's _randbelow rejection) and adds [0, 1, -1, 2, -2, 3, -3][that value].
+ * stats[0] = eligible tokens E, stats[1] = accepted words A among the W given, stats[2] = words consumed (index of the
+ * E-th accepted word + 1; 0 if E = 0). If A < E nothing is modified: call again with more words. */
+int64_t ta_augment_workspace_bytes(int64_t N, int64_t W);
+int32_t ta_augment_tokens(int32_t* tokens, int64_t N, const uint32_t* words, int64_t W, int32_t rand_size, int32_t vocab_size,
+                          void* workspace, int64_t* stats, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ K8: evaluation metrics
  * Directional metrics of one modality for one batch (training_utils.py:183-330, calculate_evaluation_metrics): from the
  * LAST-position logits (fp32, row r at last_logits + r*ld) the arg-max token's value, its direction sign and the actual

@@ -255,6 +255,38 @@ def gather_batch(data_list, ix, block_size):
     return xs, ys
 
 
+# --------------------------------------------------------------------------------------------- augmentation
+def add_rand_to_data_points(numeric_data, rand_size, vocab_size, rng=None):
+    """Restates data_utils.add_rand_to_data_points (data_utils.py:293-358) for a list of ints: every element v with
+    max_r < v < vocab_size - max_r (max_r = rand_size) gets `random.choice([0, 1, -1, ..., rand_size, -rand_size])`
+    added, IN PLACE and in index order; elements outside that band consume no random number. `rng` is a
+    random.Random (default: the module-level generator the reference uses). get_batch passes all_modality_params[r][2]
+    as rand_size (training_utils.py:353), i.e. the has_header bool of the legacy list: True acts as 1, False fails the
+    range check below exactly like the reference (bool is an int)."""
+    import random as _random
+    rng = rng or _random
+    if not isinstance(numeric_data, list):
+        raise TypeError("numeric_data must be a list or a tensor.")
+    if not numeric_data:
+        raise ValueError("numeric_data cannot be empty.")
+    if not isinstance(rand_size, (int, type(None))):
+        raise TypeError("rand_size must be an integer or null.")
+    if rand_size is not None and (rand_size < 1 or rand_size > 3):
+        raise ValueError("rand_size must be an integer between 1 and 3, or null.")
+    if not isinstance(vocab_size, int) or vocab_size <= 0:
+        raise TypeError("vocab_size must be a positive integer.")
+    if rand_size is None:
+        return numeric_data
+    rand_list = [0]
+    for r in range(rand_size):
+        rand_list.extend([r + 1, -(r + 1)])
+    hi = max(rand_list)
+    for n in range(len(numeric_data)):
+        if hi < numeric_data[n] < vocab_size - hi:
+            numeric_data[n] += rng.choice(rand_list)
+    return numeric_data
+
+
 # --------------------------------------------------------------------------------------------- metrics
 def _sign(cur, prev, is_pct):
     """_get_direction_sign (training_utils.py:184-212)."""

@@ -275,3 +275,24 @@ def directional_metrics(last_logits, vocab_values, prev_tokens, actual_tokens, i
     counts[1] += int((ps != as_).sum())
     probs = torch.softmax(x, -1).double()
     certainty[0] += float((probs * (torch.sign(vocab_values[None, :] - ref[:, None]) == ps[:, None])).sum())
+
+
+def augment_workspace_bytes(N, W):
+    return 64
+
+
+def augment_tokens(tokens, words, rand_size, vocab_size, workspace, stats):
+    """csrc/augment.cu with torch ops: j-th accepted word <-> j-th eligible token."""
+    _tick()
+    n = 2 * rand_size + 1
+    k = 2 if rand_size == 1 else 3
+    w = words.to(torch.int64) & 0xFFFFFFFF
+    r = w >> (32 - k)
+    acc = (r < n).nonzero().flatten()
+    elig = ((tokens > rand_size) & (tokens < vocab_size - rand_size)).nonzero().flatten()
+    E, A = elig.numel(), acc.numel()
+    stats[0], stats[1], stats[2] = E, A, (int(acc[E - 1]) + 1 if 0 < E <= A else 0)
+    if A < E or E == 0:
+        return
+    delta = torch.tensor([0, 1, -1, 2, -2, 3, -3], dtype=torch.int32)
+    tokens[elig] += delta[r[acc[:E]]]

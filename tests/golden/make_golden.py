@@ -144,6 +144,38 @@ def metrics_case():
     print("metrics:", res)
 
 
+def augmentation_case():
+    """data_utils.add_rand_to_data_points (the `[2]` quirk of get_batch, training_utils.py:353-360) on seeded lists:
+    outputs after one and after three cumulative applications, and the next outputs of Python's `random` (pins how many
+    Mersenne-Twister words the function consumed)."""
+    from data_utils import add_rand_to_data_points
+    cases = []
+    for name, N, V, size, seed in (("s1", 1000, 50, 1, 11), ("s1_true", 777, 9, True, 12), ("s2", 500, 12, 2, 13),
+                                   ("s3", 2000, 300, 3, 14), ("edge_band", 64, 3, 1, 15), ("tiny", 1, 10, 1, 16)):
+        g = torch.Generator().manual_seed(seed)
+        data = torch.randint(0, V, (N,), generator=g).tolist()
+        random.seed(seed)
+        work = list(data)
+        after1 = list(add_rand_to_data_points(work, size, V))
+        tail1 = [random.getrandbits(32) for _ in range(4)]
+        random.seed(seed)
+        work = list(data)
+        for _ in range(3):
+            work = add_rand_to_data_points(work, size, V)
+        tail3 = [random.getrandbits(32) for _ in range(4)]
+        cases.append(dict(name=name, data=data, V=V, size=size, seed=seed, after1=after1, tail1=tail1, after3=list(work),
+                          tail3=tail3))
+    errors = []
+    for size in (False, 0, 4, 1.5):
+        try:
+            add_rand_to_data_points([1, 2, 3], size, 10)
+            errors.append((size, None, None))
+        except (TypeError, ValueError) as e:
+            errors.append((size, type(e).__name__, str(e)))
+    torch.save(dict(cases=cases, errors=errors), os.path.join(OUT, "augmentation.pt"))
+    print("augmentation:", len(cases), "cases", errors)
+
+
 if __name__ == "__main__":
     random.seed(0)
     model_case("demo", M=2, V=[57, 3], cross=[True, False], B=4, T=4, C=32, H=4, L=2)
@@ -154,3 +186,4 @@ if __name__ == "__main__":
     index_cases()
     get_batch_case()
     metrics_case()
+    augmentation_case()

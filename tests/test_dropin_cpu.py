@@ -132,3 +132,64 @@ def test_library_exports_every_declared_symbol():
     lib.ta_abi_version.restype = ctypes.c_int32
     m = re.search(r"#define TA_ABI_VERSION (\d+)", hdr)
     assert lib.ta_abi_version() == int(m.group(1))
+
+
+def test_device_augmentation_host_logic_matches_reference():
+    """TokenStore.augment_modality (word pre-draw from Python's `random`, eligible/accepted matching, generator
+    re-positioning) over the CPU emulation of ta_augment_tokens, against the reference's own outputs."""
+    import random
+    from tradeaid_b200.feeder import TokenStore
+    g = load_golden("augmentation.pt")
+    for c in g["cases"]:
+        for rounds, key_out, key_tail in ((1, "after1", "tail1"), (3, "after3", "tail3")):
+            store = TokenStore([c["data"], c["data"]], "cpu", ops=emu_ops)
+            random.seed(c["seed"])
+            for _ in range(rounds):
+                store.augment_modality(1, c["size"], c["V"])
+            assert store.store[1].tolist() == c[key_out], (c["name"], rounds)
+            assert store.store[0].tolist() == c["data"]
+            assert [random.getrandbits(32) for _ in range(4)] == c[key_tail]
+    store = TokenStore([[1, 2, 3]], "cpu", ops=emu_ops)
+    for size, exc, msg in g["errors"]:
+        with pytest.raises({"TypeError": TypeError, "ValueError": ValueError}[exc]) as ei:
+            store.augment_modality(0, size, 10)
+        assert str(ei.value) == msg
+    store.augment_modality(0, None, 10)
+    assert store.store[0].tolist() == [1, 2, 3]
+
+
+def test_get_batch_with_the_has_header_quirk_matches_oracle():
+    """get_batch as shipped (all_modality_params[r][2] = has_header = True -> rand_size 1, training_utils.py:353-360):
+    three training calls against the oracle's in-place host walk + gather with the same `random` / torch seeds."""
+    import random
+    from oracle import restatement as R
+    from tradeaid_b200 import training_utils as tu
+    gen = torch.Generator().manual_seed(5)
+    M, N, V, T, B = 2, 300, 40, 8, 6
+    data = [torch.randint(0, V, (N,), generator=gen).tolist() for _ in range(M)]
+    tu.configure(device="cpu", batch_size=B, block_size=T, eval_iters=1)
+    tu._ops_override = emu_ops
+    tu._stores.clear()
+    try:
+        tu.all_train_sets = [list(d) for d in data]
+        tu.all_val_sets = [torch.tensor(d[:50]) for d in data]
+        tu.all_vocabularies = [[float(k) for k in range(V)]] * M
+        tu.all_modality_params = [["s", i, True if i == 0 else None, False, None, None, None, None, False, f"m{i}"] for i in range(M)]
+        tu.file_lengths = [N]
+        tu.num_modalities = M
+        tu.is_percents = False
+        ref = [list(d) for d in data]
+        random.seed(3); torch.manual_seed(4)
+        ours = [tu.get_batch("train", 1) for _ in range(3)]
+        tail = random.getrandbits(32)
+        random.seed(3); torch.manual_seed(4)
+        for xb, yb in ours:
+            ref[0] = R.add_rand_to_data_points(ref[0], True, V)
+            ix = R.batch_starting_indices(N, T, B, "train", [N], False)
+            rx, ry = R.gather_batch([torch.tensor(d) for d in ref], ix, T)
+            assert all(torch.equal(a, b) for a, b in zip(xb, rx)) and all(torch.equal(a, b) for a, b in zip(yb, ry))
+        assert tail == random.getrandbits(32)
+        assert ref[0] != data[0]
+    finally:
+        tu._ops_override = None
+        tu._stores.clear()

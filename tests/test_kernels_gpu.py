@@ -528,3 +528,34 @@ def test_directional_metrics_kernel_matches_reference_golden(lib):
     mass = (torch.softmax(last, -1).double() * (torch.sign(vals[None, :] - ref[:, None]) == ps[:, None])).sum()
     assert counts.tolist() == [2 * int((ps == as_).sum()), 2 * int((ps != as_).sum())]
     assert abs(float(cert) - 2 * float(mass)) <= 1e-6 * B
+
+
+def test_augment_tokens_matches_reference_golden():
+    """ta_augment_tokens through TokenStore.augment_modality on the GPU against the reference's own outputs
+    (tests/golden/augmentation.pt: values after 1 and 3 cumulative applications, position of Python's `random` stream),
+    plus a multi-tile case (several 2048-item tiles, rejection sampling for rand_size 2) against the oracle loop."""
+    import random
+    from conftest import load_golden
+    from oracle import restatement as R
+    from tradeaid_b200.feeder import TokenStore
+    g = load_golden("augmentation.pt")
+    for c in g["cases"]:
+        for rounds, key_out, key_tail in ((1, "after1", "tail1"), (3, "after3", "tail3")):
+            store = TokenStore([c["data"], c["data"]], "cuda")
+            random.seed(c["seed"])
+            for _ in range(rounds):
+                store.augment_modality(1, c["size"], c["V"])
+            assert store.store[1].tolist() == c[key_out], (c["name"], rounds)
+            assert store.store[0].tolist() == c["data"]
+            assert [random.getrandbits(32) for _ in range(4)] == c[key_tail]
+    gen = torch.Generator().manual_seed(6)
+    for size, V, N in ((2, 64, 100_003), (1, 1024, 50_000), (3, 9, 20_000)):
+        data = torch.randint(0, V, (N,), generator=gen).tolist()
+        store = TokenStore([data], "cuda")
+        random.seed(77)
+        store.augment_modality(0, size, V)
+        store.augment_modality(0, size, V)
+        tail = random.getrandbits(32)
+        random.seed(77)
+        ref = R.add_rand_to_data_points(R.add_rand_to_data_points(list(data), size, V), size, V)
+        assert store.store[0].tolist() == ref and tail == random.getrandbits(32)

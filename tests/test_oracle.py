@@ -112,3 +112,24 @@ def test_directional_metrics_match_reference():
     assert w == rw and l == rl and p == rp
     for a, b in zip(c, rc):
         assert abs(a - b) <= 1e-5
+
+
+def test_augmentation_matches_reference():
+    """oracle add_rand_to_data_points vs outputs of data_utils.add_rand_to_data_points (tests/golden/augmentation.pt):
+    values after one and three cumulative applications, the position of Python's `random` stream afterwards, errors."""
+    import random
+    g = load_golden("augmentation.pt")
+    for c in g["cases"]:
+        random.seed(c["seed"])
+        work = list(c["data"])
+        assert R.add_rand_to_data_points(work, c["size"], c["V"]) == c["after1"], c["name"]
+        assert [random.getrandbits(32) for _ in range(4)] == c["tail1"]
+        random.seed(c["seed"])
+        work = list(c["data"])
+        for _ in range(3):
+            work = R.add_rand_to_data_points(work, c["size"], c["V"])
+        assert work == c["after3"] and [random.getrandbits(32) for _ in range(4)] == c["tail3"]
+    for size, exc, msg in g["errors"]:
+        with pytest.raises({"TypeError": TypeError, "ValueError": ValueError}[exc]) as ei:
+            R.add_rand_to_data_points([1, 2, 3], size, 10)
+        assert str(ei.value) == msg

@@ -87,6 +87,44 @@ class TokenStore:
         t = data if torch.is_tensor(data) else torch.tensor(data, dtype=torch.long)
         self.store[r].copy_(t.to(torch.int32))
 
+    def augment_modality(self, r, rand_size, vocab_size):
+        """data_utils.add_rand_to_data_points (data_utils.py:293-358) applied IN PLACE to modality r of the resident
+        store, bit-exact to the reference's host loop and to its use of Python's module-level `random` generator:
+        the Mersenne-Twister words the loop would draw are pre-drawn in bulk (random.getrandbits(32 * W): its 32-bit
+        limbs are the successive outputs), matched on the device with the eligible tokens (ta_augment_tokens), and the
+        generator is then re-positioned to exactly the number of words the reference would have consumed.
+        Same argument checks and messages as the reference (rand_size comes from all_modality_params[r][2])."""
+        import random
+        if not isinstance(rand_size, (int, type(None))):
+            raise TypeError("rand_size must be an integer or null.")
+        if rand_size is not None and (rand_size < 1 or rand_size > 3):
+            raise ValueError("rand_size must be an integer between 1 and 3, or null.")
+        if not isinstance(vocab_size, int) or vocab_size <= 0:
+            raise TypeError("vocab_size must be a positive integer.")
+        if rand_size is None:
+            return
+        if self.N == 0:
+            raise ValueError("numeric_data cannot be empty.")
+        s = int(rand_size)
+        n = 2 * s + 1
+        k = n.bit_length()
+        state0 = random.getstate()
+        W = int(self.N * (2 ** k / n) * 1.03) + 4096       # expected words if every token were eligible, + slack
+        stats = torch.zeros(3, dtype=torch.int64, device=self.device)
+        while True:
+            random.setstate(state0)
+            big = random.getrandbits(32 * W)
+            words = torch.frombuffer(bytearray(big.to_bytes(4 * W, "little")), dtype=torch.int32).to(self.device)
+            ws = torch.empty(self.ops.augment_workspace_bytes(self.N, W), dtype=torch.uint8, device=self.device)
+            self.ops.augment_tokens(self.store[r], words, s, int(vocab_size), ws, stats)
+            eligible, accepted, consumed = stats.tolist()
+            if accepted >= eligible:
+                break
+            W *= 2                                           # (astronomically unlikely) not enough accepted draws: redo
+        random.setstate(state0)
+        if consumed:
+            random.getrandbits(32 * consumed)                # leave the generator where the reference's loop leaves it
+
     RING = 4  # pinned index staging buffers: the host may run this many steps ahead of the device
 
     def gather(self, ix, block_size, out=None):

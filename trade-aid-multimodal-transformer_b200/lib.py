@@ -364,6 +364,25 @@ def colsum(dy, out, workspace):
                    _stream()))
 
 
+_aug_ws = _sig("ta_augment_workspace_bytes", _I64, _I64, restype=_I64)
+_aug = _sig("ta_augment_tokens", _P, _I64, _P, _I64, _I32, _I32, _P, _P, _P)
+
+
+def augment_workspace_bytes(N, W):
+    return int(_aug_ws(N, W))
+
+
+def augment_tokens(tokens, words, rand_size, vocab_size, workspace, stats):
+    """tokens int32 [N] (contiguous row of the token store, modified in place); words int32/uint32 bits [W]: the next W
+    outputs of Python's Mersenne Twister; workspace uint8 [>= augment_workspace_bytes(N, W)]; stats int64 [3]."""
+    import torch
+    assert tokens.dtype == torch.int32 and tokens.is_contiguous() and words.is_contiguous() and words.element_size() == 4
+    assert stats.dtype == torch.int64 and stats.numel() >= 3
+    assert workspace.numel() * workspace.element_size() >= augment_workspace_bytes(tokens.numel(), words.numel())
+    _check(_aug(_ptr(tokens), tokens.numel(), _ptr(words), words.numel(), int(rand_size), int(vocab_size), _ptr(workspace),
+                _ptr(stats), _stream()))
+
+
 _dir_metrics = _sig("ta_directional_metrics", _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _P)
 
 

@@ -67,14 +67,12 @@ def get_batch(split, is_training):
         this_rand_size = all_modality_params[r][2]
         if this_rand_size is not None and is_training == 1:
             # The reference reads the augmentation size from index 2 of the legacy list, which holds `has_header`
-            # (training_utils.py:353; schema.py:213-248): with a truthy value it applies a +-1 random walk to the whole
-            # training list in place, on the host, every call. Kept verbatim by delegating to the reference's own
-            # function; the mutated modality is re-uploaded. O(N) per step by construction — see INTEGRATION.md.
-            from data_utils import add_rand_to_data_points
-            all_train_sets[r] = add_rand_to_data_points(all_train_sets[r], this_rand_size, len(all_vocabularies[r]))
-            train_store.update_modality(r, all_train_sets[r])
-            _stores['train'] = ((('train', id(all_train_sets), tuple(id(s) for s in all_train_sets), str(_get('device')))),
-                                train_store)
+            # (training_utils.py:353; schema.py:213-248): True acts as rand_size 1 - a +-1 random walk applied to the whole
+            # training list in place, cumulatively, on every call; False fails add_rand_to_data_points' range check.
+            # Kept as shipped, but on the device-resident store (TokenStore.augment_modality: same values, same
+            # consumption of Python's `random` stream, same errors); the host lists are not rewritten - the reference
+            # reads them nowhere else.
+            train_store.augment_modality(r, this_rand_size, len(all_vocabularies[r]))
     store = train_store if split == 'train' else _store('val')
     T, B = _get('block_size'), _get('batch_size')
     ix = generate_batch_starting_indices(store.N, T, B, split, file_lengths, is_percents)
