@@ -3,7 +3,7 @@
 # list of one eager step, ncu --set full of the HBM kernels.   usage: tools/gpu_round.sh <tag>   (outputs: gpurun_out/<tag>_*)
 tag=${1:-rXX}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${tag}_gpu_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/${tag}_gpu_tests.log
+if [ -z "$SKIP_TESTS" ]; then timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${tag}_gpu_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/${tag}_gpu_tests.log; fi
 TRADEAID_BENCH_DETAIL=gpurun_out/${tag}_gemm_detail_c4.txt timeout 900 python bench.py > gpurun_out/${tag}_bench_c4.json 2> gpurun_out/${tag}_bench_c4.err; echo "bench rc=$?"
 tail -c 1200 gpurun_out/${tag}_bench_c4.json; echo
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_c4_reference.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"
@@ -15,6 +15,10 @@ L=$(python -c "import json; d=json.loads(open('gpurun_out/${tag}_bench_c4.json')
 timeout 300 python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((4 * L)) -c $L --csv --log-file gpurun_out/${tag}_launches_c4.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_launches.log 2>&1
 echo "ncu launches rc=$? (L=$L)"
+# the .ncu-rep stays on the box (gpurun_out/ is capped at 64 MiB): only its csv pages and the one-screen summary come back
 HBM_ONCE=1 timeout 300 python tools/hbm_kernels.py > /dev/null 2>&1 && \
-HBM_ONCE=1 timeout 900 ncu --set full --clock-control none --import-source on -c 60 -o gpurun_out/${tag}_prof_hbm_kernels -f python tools/hbm_kernels.py > gpurun_out/${tag}_ncu_hbm.log 2>&1
+HBM_ONCE=1 timeout 900 ncu --set full --clock-control none -c 40 -o /tmp/${tag}_prof_hbm_kernels -f python tools/hbm_kernels.py > gpurun_out/${tag}_ncu_hbm.log 2>&1
 echo "ncu hbm rc=$?"
+python tools/ncu_summary.py /tmp/${tag}_prof_hbm_kernels.ncu-rep > gpurun_out/${tag}_prof_hbm_kernels_ncu_full.txt 2> /dev/null
+ncu -i /tmp/${tag}_prof_hbm_kernels.ncu-rep --page raw --csv > gpurun_out/${tag}_prof_hbm_kernels_raw.csv 2> /dev/null
+ls -la gpurun_out | tail -20; du -sh gpurun_out

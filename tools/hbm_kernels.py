@@ -1,7 +1,7 @@
 """The HBM-bound kernels of the path at c4 sizes (and the decode attention at c5 sizes), each timed alone with CUDA
 events: achieved GB/s = ALGORITHMIC bytes / launch time, next to the measured copy bandwidth of
-MEASURED_PEAKS.json. Also the ncu target for these kernels:  HBM_ONCE=1 runs every kernel twice (warm + one) so that
-`ncu --set full -c 60` captures one launch of each.   usage: hbm_kernels.py [out.json]"""
+MEASURED_PEAKS.json. Also the ncu target for these kernels:  HBM_ONCE=1 runs every kernel once so that
+`ncu --set full -c 40` captures one launch of each.   usage: hbm_kernels.py [out.json]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,7 +15,7 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
 def timeit(fn, n=10):
     if ONCE:
-        fn(); fn(); torch.cuda.synchronize()
+        fn(); torch.cuda.synchronize()
         return float("nan")
     for _ in range(3):
         fn()
@@ -71,8 +71,8 @@ dyw = torch.randn(M, rows, 4 * C, device=dev).to(torch.bfloat16); cs = torch.emp
 cw = torch.empty(lib.colsum_workspace(rows, 4 * C, M), device=dev)
 report("colsum_partial_kernel (+reduce)", f"G={M} rows={rows} N={4 * C}", M * rows * 4 * C * 2, timeit(lambda: lib.colsum(dyw, cs, cw)))
 del dyw, x, dx, dy, dxb, y
-# K6 AdamW: c4 has 1.89e9 parameters (30 B each); HBM_ONCE (ncu replays with save/restore) uses a quarter
-n = 472_000_000 if ONCE else 1_890_000_000
+# K6 AdamW: c4 has 1.89e9 parameters (30 B each); HBM_ONCE (ncu replays with save/restore) uses an eighth
+n = 236_000_000 if ONCE else 1_890_000_000
 p = torch.randn(n, device=dev); gr = torch.randn(n, device=dev); m1 = torch.zeros(n, device=dev); v1 = torch.zeros(n, device=dev)
 sh = torch.empty(n, device=dev, dtype=torch.bfloat16)
 step = torch.zeros(1, dtype=torch.int64, device=dev); sc = torch.zeros(4, device=dev)

@@ -342,9 +342,14 @@ class Engine:
         hc = nb("hc", l, (Xc, BT, C), bf)
         stc = nb("stc", l, (2, Xc * BT), f32)
         for xv, pos in self._sub(x2, d.xc):
-            for k, p in enumerate(pos):  # LayerNorm wants a dense [G, rows, C] block: one launch per enabled modality
-                ops.layernorm_fwd(xv[k:k + 1], P["lnc_w"][l][p:p + 1], P["lnc_b"][l][p:p + 1], hc[p:p + 1],
-                                  stc[0][p * BT:(p + 1) * BT], stc[1][p * BT:(p + 1) * BT])
+            # LayerNorm wants a dense [G, rows, C] block: neighbouring enabled modalities go out as one grouped launch,
+            # a strided run (every other modality, ...) as one launch per modality
+            dense = xv.is_contiguous()
+            for k0 in ([0] if dense else range(len(pos))):
+                k1 = len(pos) if dense else k0 + 1
+                p0, p1 = pos[k0], pos[k1 - 1] + 1
+                ops.layernorm_fwd(xv[k0:k1], P["lnc_w"][l][p0:p1], P["lnc_b"][l][p0:p1], hc[p0:p1],
+                                  stc[0][p0 * BT:p1 * BT], stc[1][p0 * BT:p1 * BT])
         qc = nb("qc", l, (Xc, BT, C), bf)
         ops.gemm(hc, self.W("ca_wq")[l].reshape(Xc, C, C), out_bf16=qc)
         kvs, kv_runs = [None] * M, []
@@ -457,7 +462,8 @@ class Engine:
                                        ops.colsum_workspace(BT, 3 * H * h2p, M)),), f32)
         # the workspace depends on the launch shape: grouped launches (all modalities) and the per-modality launches
         # of the cross-attention LayerNorm share one buffer
-        ln_ws = self.buf("ln_ws", (max(ops.layernorm_bwd_workspace(M, BT, C), ops.layernorm_bwd_workspace(1, BT, C)),), f32)
+        ln_ws = self.buf("ln_ws", (max([ops.layernorm_bwd_workspace(M, BT, C)] +
+                                       [ops.layernorm_bwd_workspace(k, BT, C) for k in range(1, max(d.Xc, 1) + 1)]),), f32)
         dx = self.buf("dx", (M, BT, C), f32)
         dxb = self.buf("dxb", (M, BT, C), bf)
         # ---- output heads
@@ -588,10 +594,15 @@ class Engine:
         ops.gemm(dqc, Sl["hc"], a_major=1, b_major=1, out_f32=G["ca_wq"][l].reshape(Xc, C, C))
         dhc = self.buf("dhc", (Xc, BT, C), bf)
         ops.gemm(dqc, self.W("ca_wq")[l].reshape(Xc, C, C), b_major=1, out_bf16=dhc)
-        for xi, i in enumerate(d.xc):
-            ops.layernorm_bwd(dhc[xi:xi + 1], Sl["x2"][i:i + 1], self.P["lnc_w"][l][xi:xi + 1],
-                              Sl["stc"][0][xi * BT:(xi + 1) * BT], Sl["stc"][1][xi * BT:(xi + 1) * BT], dx[i:i + 1],
-                              dx[i:i + 1], dxb[i:i + 1], G["lnc_w"][l][xi:xi + 1], G["lnc_b"][l][xi:xi + 1], ln_ws)
+        for xv, pos in self._sub(Sl["x2"], d.xc):
+            dense = xv.is_contiguous()
+            for k0 in ([0] if dense else range(len(pos))):
+                k1 = len(pos) if dense else k0 + 1
+                p0, p1 = pos[k0], pos[k1 - 1] + 1
+                i0, i1 = d.xc[p0], d.xc[p1 - 1] + 1
+                ops.layernorm_bwd(dhc[p0:p1], Sl["x2"][i0:i1], self.P["lnc_w"][l][p0:p1], Sl["stc"][0][p0 * BT:p1 * BT],
+                                  Sl["stc"][1][p0 * BT:p1 * BT], dx[i0:i1], dx[i0:i1], dxb[i0:i1], G["lnc_w"][l][p0:p1],
+                                  G["lnc_b"][l][p0:p1], ln_ws)
         # key/value projections: gradients land on the (un-normalised) stream of every SOURCE modality
         Wkv, Gkv = self.W("ca_wkv")[l], G["ca_wkv"][l]
         for (j0, j1, nq), dkv in zip(self._kv_runs(), dkv_runs):
