@@ -5,11 +5,10 @@
 // Same math as model.py:60-73 / 136-159 for the last row: per source an independent softmax(q k^T * hs^-0.5) v over
 // positions [0, len), outputs of the sources summed.
 //
-// HBM-bound (every cached K and V row is read once per step): one warp per (group, batch, head); a lane owns one cached
-// position per 32-position chunk - it scores its K row (2*hs contiguous bytes), the online softmax runs on warp-shuffle
-// reductions, and it accumulates p * (its V row) privately; the lanes are summed once per source by recursive halving.
-// All 16-byte loads of a chunk are independent (a first version that walked the V rows one after the other ran at
-// 0.9 TB/s on c5 - one dependent load per step of the chain).
+// HBM-bound (every cached K and V row is read once per step): one warp per (group, batch, head); hs/8 neighbouring
+// lanes share a cached row (16 bytes each), partial dot products are completed with warp shuffles, the online softmax
+// runs on shuffle reductions, p * V is accumulated per lane for its 8 head dims and summed over the row groups once per
+// source. All 16-byte loads of a chunk are independent and the next chunk's loads are issued as soon as registers free up.
 #include <cuda_bf16.h>
 
 #include "../../include/tradeaid_b200.h"
@@ -32,34 +31,17 @@ struct AttnDecodeParams {
   float scale_log2;     // hs^-0.5 * log2(e)
 };
 
-// Sum over the 32 lanes of a per-lane array acc[HS] by recursive halving: at each step a lane keeps one half of its
-// live elements and hands the other half to its partner, so the whole reduction costs HS - 1 (+ a few) shuffles instead
-// of 5 * HS. Afterwards acc[0] (and acc[1] for HS = 64) hold complete sums: HS = 64 -> dims 2*lane, 2*lane + 1;
-// HS = 32 -> dim lane; HS = 16 -> dim lane >> 1; HS = 8 -> dim lane >> 2 (duplicated over the lanes that share a dim).
-template <int HS>
-__device__ __forceinline__ void lane_reduce(float (&acc)[HS], int lane) {
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    const int mask = 16 >> s;
-    const int nb = (HS >> s) > 1 ? (HS >> s) : 1;     // live elements before this step (compile time after unrolling)
-    if (nb > (HS == 64 ? 2 : 1)) {
-      const int half = nb / 2;
-      const bool up = (lane & mask) != 0;
-#pragma unroll
-      for (int i = 0; i < half; ++i) {
-        const float send = up ? acc[i] : acc[i + half];
-        const float keep = up ? acc[i + half] : acc[i];
-        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-      }
-    } else {
-      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], mask);
-      if (HS == 64) acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], mask);
-    }
-  }
-}
+// Work split inside a warp: LPR = HS / 8 neighbouring lanes share one cached row (each owns 16 bytes = 8 head dims of
+// it), so one warp-wide 16-byte load touches 32 / LPR whole rows (HS = 64: four full 128-byte lines) instead of 32
+// different lines - the first version of this kernel, one row per lane, was bound by L1 tag lookups (0.6 of the HBM
+// rate). A lane takes AD_U rows per chunk: rows p0 + u * RPI + lane / LPR.
+constexpr int AD_U = 8;
 
 template <int HS>
 __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid_constant__ AttnDecodeParams p) {
+  constexpr int LPR = HS / 8;            // lanes per row
+  constexpr int RPI = 32 / LPR;          // rows per warp-wide load instruction
+  constexpr int CHUNK = RPI * AD_U;      // rows per chunk
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * AD_WARPS + (threadIdx.x >> 5);
   const long long total = (long long)p.G * p.B * p.H;
@@ -67,99 +49,116 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
   const int h = (int)(w % p.H);
   const long long gb = w / p.H;
   const int b = (int)(gb % p.B), g = (int)(gb / p.B);
+  const int piece = lane % LPR, rg = lane / LPR;
 
-  // the query row of this head, pre-scaled, in every lane
-  float q[HS];
+  // this lane's 8 dims of the query row, pre-scaled
+  float q[8];
   {
-    const __nv_bfloat16* qp = p.q + g * p.q_gs + (long long)b * p.q_ld + (long long)h * p.q_hs;
+    const __nv_bfloat16* qp = p.q + g * p.q_gs + (long long)b * p.q_ld + (long long)h * p.q_hs + 8 * piece;
+    const uint4 u = *reinterpret_cast<const uint4*>(qp);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-    for (int i = 0; i < HS / 8; ++i) {
-      const uint4 u = *reinterpret_cast<const uint4*>(qp + 8 * i);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h2[j]);
-        q[8 * i + 2 * j] = f.x * p.scale_log2;
-        q[8 * i + 2 * j + 1] = f.y * p.scale_log2;
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h2[j]);
+      q[2 * j] = f.x * p.scale_log2;
+      q[2 * j + 1] = f.y * p.scale_log2;
     }
   }
-  float out0 = 0.f, out1 = 0.f;
+  float out[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) out[d] = 0.f;
   for (int s = 0; s < p.n_src; ++s) {
-    const long long base = g * p.kv_gs[s] + (long long)b * p.kv_bs[s] + (long long)h * p.kv_hs[s];
+    const long long base = g * p.kv_gs[s] + (long long)b * p.kv_bs[s] + (long long)h * p.kv_hs[s] + 8 * piece;
     const __nv_bfloat16* kb = p.k[s] + base;
     const __nv_bfloat16* vb = p.v[s] + base;
     const long long ld = p.kv_ld[s];
-    // A lane owns one cached position per 32-position chunk in BOTH phases: it scores its K row and accumulates
-    // p * (its V row) into a private acc[HS]; the lanes are summed once per source. Every load of a chunk (2 * HS / 8
-    // 16-byte loads per lane) is independent and in flight together.
     float m = -INFINITY, l = 0.f;
-    float acc[HS];
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < HS; ++i) acc[i] = 0.f;
-    for (int p0 = 0; p0 < p.len; p0 += 32) {
-      const int pos = p0 + lane;
-      const bool ok = pos < p.len;
-      uint4 ku[HS / 8], vu[HS / 8];
-      if (ok) {
-        const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)pos * ld);
-        const uint4* vr = reinterpret_cast<const uint4*>(vb + (long long)pos * ld);
+    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+    uint4 ku[AD_U], vu[AD_U];
+    auto load_rows = [&](uint4 (&dst)[AD_U], const __nv_bfloat16* base_ptr, int p0) {
 #pragma unroll
-        for (int i = 0; i < HS / 8; ++i) ku[i] = __ldg(kr + i);
-#pragma unroll
-        for (int i = 0; i < HS / 8; ++i) vu[i] = __ldg(vr + i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < HS / 8; ++i) ku[i] = vu[i] = make_uint4(0, 0, 0, 0);
+      for (int u = 0; u < AD_U; ++u) {
+        const int pos = p0 + u * RPI + rg;
+        dst[u] = pos < p.len ? __ldg(reinterpret_cast<const uint4*>(base_ptr + (long long)pos * ld)) : make_uint4(0, 0, 0, 0);
       }
-      float sc = 0.f;
+    };
+    // software pipeline without extra registers: the K registers are dead once the scores are formed, the V registers
+    // once the accumulators are updated - the next chunk's rows are requested right there
+    load_rows(ku, kb, 0);
+    load_rows(vu, vb, 0);
+    for (int p0 = 0; p0 < p.len; p0 += CHUNK) {
+      float sc[AD_U];
 #pragma unroll
-      for (int i = 0; i < HS / 8; ++i) {
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&ku[i]);
+      for (int u = 0; u < AD_U; ++u) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&ku[u]);
+        float a = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __bfloat1622float2(h2[j]);
-          sc = fmaf(q[8 * i + 2 * j], f.x, sc);
-          sc = fmaf(q[8 * i + 2 * j + 1], f.y, sc);
+          a = fmaf(q[2 * j], f.x, a);
+          a = fmaf(q[2 * j + 1], f.y, a);
         }
+        sc[u] = a;
       }
-      if (!ok) sc = -INFINITY;
-      float cm = sc;
+      if (p0 + CHUNK < p.len) load_rows(ku, kb, p0 + CHUNK);
+      // complete the dot products over the LPR lanes of a row; afterwards every lane of the row holds the score
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < AD_U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+      }
+      float cm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < AD_U; ++u) {
+        if (p0 + u * RPI + rg >= p.len) sc[u] = -INFINITY;
+        cm = fmaxf(cm, sc[u]);
+      }
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
       const float m_new = fmaxf(m, cm);                 // finite: position p0 is always valid
       const float corr = exp2f(m - m_new);              // exp2f(-inf) = 0 on the first chunk
-      const float pr = exp2f(sc - m_new);               // 0 for masked lanes
-      float ps = pr;
+      float ps = 0.f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      for (int u = 0; u < AD_U; ++u) {
+        sc[u] = exp2f(sc[u] - m_new);                   // 0 for masked rows
+        ps += sc[u];
+      }
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
       l = l * corr + ps;
       m = m_new;
 #pragma unroll
-      for (int i = 0; i < HS / 8; ++i) {
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vu[i]);
+      for (int d = 0; d < 8; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int u = 0; u < AD_U; ++u) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vu[u]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __bfloat1622float2(h2[j]);
-          acc[8 * i + 2 * j] = fmaf(pr, f.x, acc[8 * i + 2 * j] * corr);
-          acc[8 * i + 2 * j + 1] = fmaf(pr, f.y, acc[8 * i + 2 * j + 1] * corr);
+          acc[2 * j] = fmaf(sc[u], f.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(sc[u], f.y, acc[2 * j + 1]);
         }
       }
+      if (p0 + CHUNK < p.len) load_rows(vu, vb, p0 + CHUNK);
     }
-    lane_reduce<HS>(acc, lane);
+    // sum the row groups (lanes with the same piece); every lane ends with the full sum of its 8 dims
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+    }
     const float inv = 1.f / l;
-    out0 += acc[0] * inv;
-    if (HS == 64) out1 += acc[1] * inv;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) out[d] += acc[d] * inv;
   }
-  __nv_bfloat16* op = p.o + g * p.o_gs + (long long)b * p.o_ld + (long long)h * HS;
-  if (HS == 64) {
-    *reinterpret_cast<__nv_bfloat162*>(op + 2 * lane) = __floats2bfloat162_rn(out0, out1);
-  } else if (HS == 32) {
-    op[lane] = __float2bfloat16_rn(out0);
-  } else if (HS == 16) {
-    if ((lane & 1) == 0) op[lane >> 1] = __float2bfloat16_rn(out0);
-  } else {
-    if ((lane & 3) == 0) op[lane >> 2] = __float2bfloat16_rn(out0);
+  if (rg == 0) {
+    uint4 u;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(out[2 * j], out[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p.o + g * p.o_gs + (long long)b * p.o_ld + (long long)h * HS + 8 * piece) = u;
   }
 }
 
@@ -191,7 +190,7 @@ extern "C" int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_te
     p.kv_ld[s] = k[s].ld; p.kv_hs[s] = k[s].head_stride; p.kv_gs[s] = k[s].gs; p.kv_bs[s] = kv_batch_stride[s];
   }
   p.o = static_cast<__nv_bfloat16*>(o_bf16); p.o_ld = ldo; p.o_gs = o_gs;
-  TA_CHECK_ARG((reinterpret_cast<uintptr_t>(o_bf16) & 3) == 0 && ldo % 2 == 0 && o_gs % 2 == 0, "ta_attention_decode: o misaligned");
+  TA_CHECK_ARG((reinterpret_cast<uintptr_t>(o_bf16) & 15) == 0 && ldo % 8 == 0 && o_gs % 8 == 0, "ta_attention_decode: o must be 16-byte aligned (ptr, strides)");
   p.n_src = n_src; p.G = G; p.B = B; p.H = H; p.hs = hs; p.len = len;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)hs);
   const long long total = (long long)G * B * H;
