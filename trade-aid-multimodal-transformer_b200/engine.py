@@ -437,7 +437,9 @@ class Engine:
         """Gradients of sum_i w_i * loss_i (w_i = 1: main.py:646) into self.grad; needs forward(..., save=True).
         `stage_hook(stage)` is called when every gradient of a stage has been enqueued: "heads" (output heads + final
         LayerNorm), then each layer index from n_layer-1 down to 0, then "embed" — the data-parallel trainer starts the
-        all-reduce of a gradient bucket there while the kernels of the earlier layers are still to run."""
+        all-reduce of a gradient bucket there while the kernels of the earlier layers are still to run. ("part", l) is
+        reported once the first part of layer l's backward is enqueued (its cross-attention, or its feed-forward when
+        there is none): the window in which the previous bucket's collective runs beside the kernels."""
         S = self._saved
         if S is None or "dlogits" not in S:
             raise RuntimeError("backward() needs a preceding forward(idx, targets, save=True)")
@@ -493,7 +495,7 @@ class Engine:
         for l in reversed(range(L)):
             Sl = S["layers"][l]
             if d.Xc:
-                self._cross_backward(l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd, dxm)
+                self._cross_backward(l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd, dxm, stage_hook)
             # feed-forward
             dy = masked(dxb, self.SITE_FFN)
             ops.gemm(dy, Sl["ffh"], a_major=1, b_major=1, out_f32=G["ff_w2"][l])
@@ -506,6 +508,8 @@ class Engine:
             ops.gemm(dffh, self.W("ff_w1")[l], b_major=1, out_bf16=dh)
             ops.layernorm_bwd(dh, Sl["x1"], self.P["ln2_w"][l], Sl["st2"][0], Sl["st2"][1], dx, dx, dxb, G["ln2_w"][l],
                               G["ln2_b"][l], ln_ws)
+            if stage_hook is not None and not d.Xc:
+                stage_hook(("part", l))
             # self-attention projection MLP
             dy = masked(dxb, self.SITE_SA_PROJ)
             ops.gemm(dy, Sl["p1"], a_major=1, b_major=1, out_f32=G["sa_pw2"][l])
@@ -554,7 +558,7 @@ class Engine:
         if stage_hook is not None:
             stage_hook("embed")
 
-    def _cross_backward(self, l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd=0.0, dxm=None):
+    def _cross_backward(self, l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd=0.0, dxm=None, stage_hook=None):
         d, ops, G = self.d, self.ops, self.G
         M, C, H, hs, Xc = d.M, d.n_embd, d.n_head, d.hs, d.Xc
         BT = B * T
@@ -590,6 +594,8 @@ class Engine:
                               dqc[xi:xi + 1], dks, dvs, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
                               o_src=Sl["ocs"][xi] if Sl["ocs"] is not None else None,
                               **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi), "dropout_step": self._drop_step} if pd > 0.0 else {}))
+        if stage_hook is not None and os.environ.get("TRADEAID_DP_WINDOW", "cross") == "attn":
+            stage_hook(("part", l))      # the first few milliseconds of this layer's backward are enqueued
         # query projection and its LayerNorm (input: the snapshot x2 of the querying modality)
         ops.gemm(dqc, Sl["hc"], a_major=1, b_major=1, out_f32=G["ca_wq"][l].reshape(Xc, C, C))
         dhc = self.buf("dhc", (Xc, BT, C), bf)
@@ -610,6 +616,8 @@ class Engine:
             ops.gemm(dkv, Sl["a_bf"][j0:j1], a_major=1, b_major=1, out_f32=Gkv[sl].reshape(n, nq * 2 * C, C))
             ops.gemm(dkv, Wkv[sl].reshape(n, nq * 2 * C, C), b_major=1, residual=dx[j0:j1], out_f32=dx[j0:j1],
                      out_bf16=dxb[j0:j1])
+        if stage_hook is not None and os.environ.get("TRADEAID_DP_WINDOW", "cross") != "attn":
+            stage_hook(("part", l))
 
     # ------------------------------------------------------------------------------------------ bookkeeping
     def zero_grad(self):

@@ -8,9 +8,11 @@ exchange per iteration — an all-reduce (sum) of the flat fp32 gradient buffer 
 the AdamW kernel's grad_scale. The exchange is BUCKETED in the order backward produces gradients (output heads and the
 last layers first, the embedding tables last): as soon as the kernels of a bucket's layers are enqueued, the all-reduce
 of that bucket's gradient ranges is issued asynchronously (one coalesced NCCL call on the process group's own stream,
-which waits for exactly the work enqueued so far), so it runs beside the backward of the earlier layers. While a
-collective can be in flight, the persistent kernels leave `sm_margin` SMs free for its CTAs (ta_set_sm_margin) — a
-one-CTA-per-SM grid would otherwise run its displaced CTAs as a second wave. `overlap=False` keeps the plain form
+which waits for exactly the work enqueued so far), so it runs beside the backward of the earlier layers. In the window
+in which that collective runs (the first part of the next layer's backward: a few milliseconds, the collective of a
+one-layer bucket takes ~2) the persistent kernels leave `sm_margin` SMs free for its CTAs (ta_set_sm_margin) — a
+one-CTA-per-SM grid would otherwise run its displaced CTAs as a second wave; the rest of the layer runs full grids
+(a margin over the whole backward costs the GEMMs 11 % of their SMs all the time: measured +18 ms per step on c4). `overlap=False` keeps the plain form
 (backward, then the whole-buffer all-reduce in `grad_chunks` pieces).
 """
 from __future__ import annotations
@@ -134,10 +136,13 @@ class Trainer:
         closing = {stage: views for stage, views in self._buckets}
 
         def hook(stage):
+            if isinstance(stage, tuple):             # ("part", l): the previous bucket's collective is over by now
+                self._set_margin(0)
+                return
             views = closing.get(stage)
             if views is not None:
                 self._issue_bucket(views)
-                self._set_margin(self.sm_margin)     # from here on a collective may be running beside the kernels
+                self._set_margin(self.sm_margin)     # a collective now runs beside the next kernels
 
         try:
             losses = self.forward_backward(idx, tgt, stage_hook=hook)
@@ -186,6 +191,9 @@ class Trainer:
                 state["g"].capture_begin(pool=pool)
 
             def hook(stage):
+                if isinstance(stage, tuple):         # ("part", l): full grids again for the rest of the layer
+                    self._set_margin(0)
+                    return
                 views = closing.get(stage)
                 if views is None:
                     return
