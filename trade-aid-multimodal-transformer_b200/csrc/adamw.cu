@@ -20,6 +20,7 @@ struct AdamScalars {  // device-resident, written by tick
 };
 
 __global__ void adamw_tick_kernel(long long* step, AdamScalars* sc, double lr, double beta1, double beta2, double wd) {
+  pdl_prologue();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const long long t = *step + 1;
     *step = t;
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, long long n, const AdamScalars* __restrict__ sc, float beta1, float beta2,
              float eps, float grad_scale) {
+  pdl_prologue();
   const AdamScalars s = *sc;
   const float b1w = 1.f - beta1, b2w = 1.f - beta2;
   const long long nv = n / 4;
@@ -86,7 +88,7 @@ extern "C" {
 int32_t ta_adamw_tick(int64_t* step_dev, float* scalars_dev, double lr, double beta1, double beta2, double weight_decay,
                       void* stream) {
   TA_CHECK_ARG(step_dev && scalars_dev, "ta_adamw_tick: null pointer");
-  adamw_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long*)step_dev, (AdamScalars*)scalars_dev, lr, beta1, beta2,
+  launch_kernel(adamw_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (long long*)step_dev, (AdamScalars*)scalars_dev, lr, beta1, beta2,
                                                        weight_decay);
   TA_CHECK_LAUNCH();
   return 0;
@@ -101,7 +103,7 @@ int32_t ta_adamw_step(float* p, const float* g, float* m, float* v, void* shadow
   long long blocks = ceil_div(n / 4 + 1, 256);
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)shadow_bf16, n,
+  launch_kernel(adamw_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)shadow_bf16, n,
                                                              (const AdamScalars*)scalars_dev, beta1, beta2, eps, grad_scale);
   TA_CHECK_LAUNCH();
   return 0;

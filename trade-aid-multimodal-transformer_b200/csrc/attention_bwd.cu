@@ -142,6 +142,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_launch_dependents();       // PDL: on-chip set-up done; wait for the previous kernel before touching global memory
+  pdl_wait();
   // TMEM columns: S halves [0,128) dP halves [128,256) dV [256,320) dK [320,384) dQ_0 [384,448) dQ_1 [448,512)
   const int n_qt = p.n_qt, n_src = p.n_src, stride = gridDim.x, total = p.total_work;
   AbIter it;
@@ -532,7 +534,7 @@ static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cuda
     attr = true;
   }
   const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
-  attn_bwd_kernel<DP><<<grid, AB_THREADS, SMEM, st>>>(maps, p);
+  launch_kernel(attn_bwd_kernel<DP>, dim3(grid), dim3(AB_THREADS), SMEM, st, maps, p);
   TA_CHECK_LAUNCH();
   return 0;
 }

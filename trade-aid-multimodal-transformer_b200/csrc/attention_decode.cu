@@ -39,6 +39,7 @@ constexpr int AD_U = 8;
 
 template <int HS>
 __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid_constant__ AttnDecodeParams p) {
+  pdl_prologue();
   constexpr int LPR = HS / 8;            // lanes per row
   constexpr int RPI = 32 / LPR;          // rows per warp-wide load instruction
   constexpr int CHUNK = RPI * AD_U;      // rows per chunk
@@ -197,10 +198,10 @@ extern "C" int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_te
   const unsigned grid = (unsigned)ceil_div(total, AD_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (hs) {
-    case 64: attn_decode_kernel<64><<<grid, AD_WARPS * 32, 0, st>>>(p); break;
-    case 32: attn_decode_kernel<32><<<grid, AD_WARPS * 32, 0, st>>>(p); break;
-    case 16: attn_decode_kernel<16><<<grid, AD_WARPS * 32, 0, st>>>(p); break;
-    default: attn_decode_kernel<8><<<grid, AD_WARPS * 32, 0, st>>>(p); break;
+    case 64: launch_kernel(attn_decode_kernel<64>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
+    case 32: launch_kernel(attn_decode_kernel<32>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
+    case 16: launch_kernel(attn_decode_kernel<16>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
+    default: launch_kernel(attn_decode_kernel<8>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
   }
   TA_CHECK_LAUNCH();
   return 0;

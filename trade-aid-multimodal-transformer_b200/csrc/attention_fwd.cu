@@ -123,6 +123,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_launch_dependents();       // PDL: on-chip set-up done; wait for the previous kernel before touching global memory
+  pdl_wait();
   // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+DP) O1 [320,320+DP) sum over sources [384,384+DP)
   AfIter it;
   it.init(blockIdx.x);
@@ -514,7 +516,7 @@ static int launch_attn_fwd(const AttnMaps& maps, const AttnFwdParams& p, cudaStr
     attr = true;
   }
   const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
-  attn_fwd_kernel<DP, MULTI><<<grid, AF_THREADS, SMEM, st>>>(maps, p);
+  launch_kernel(attn_fwd_kernel<DP, MULTI>, dim3(grid), dim3(AF_THREADS), SMEM, st, maps, p);
   TA_CHECK_LAUNCH();
   return 0;
 }

@@ -69,6 +69,7 @@ __device__ __forceinline__ unsigned block_exclusive(unsigned v, unsigned& total)
 }
 
 __global__ void __launch_bounds__(AUG_THREADS) aug_count_kernel(const AugParams p) {
+  pdl_prologue();
   const bool is_w = (int)blockIdx.x < p.tiles_w;
   const long long tile = is_w ? blockIdx.x : blockIdx.x - p.tiles_w;
   const long long i0 = tile * AUG_TILE + (long long)threadIdx.x * AUG_PER;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(AUG_THREADS) aug_count_kernel(const AugParams 
 }
 
 __global__ void __launch_bounds__(1024) aug_scan_kernel(const AugParams p) {
+  pdl_prologue();
   // one block: exclusive scan of counts_w and counts_e in place, totals to stats
   __shared__ unsigned long long carry_s;
   __shared__ unsigned warp_sums[32];
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(1024) aug_scan_kernel(const AugParams p) {
 }
 
 __global__ void __launch_bounds__(AUG_THREADS) aug_compact_kernel(const AugParams p) {
+  pdl_prologue();
   const long long E = p.stats[0];
   const long long i0 = (long long)blockIdx.x * AUG_TILE + (long long)threadIdx.x * AUG_PER;
   unsigned flags = 0, c = 0;
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(AUG_THREADS) aug_compact_kernel(const AugParam
 }
 
 __global__ void __launch_bounds__(AUG_THREADS) aug_apply_kernel(const AugParams p) {
+  pdl_prologue();
   if (p.stats[1] < p.stats[0]) return;        // too few accepted words for the eligible elements: leave the tokens alone
   const long long i0 = (long long)blockIdx.x * AUG_TILE + (long long)threadIdx.x * AUG_PER;
   unsigned flags = 0, c = 0;
@@ -188,13 +192,13 @@ int32_t ta_augment_tokens(int32_t* tokens, int64_t N, const uint32_t* words, int
   p.draws = reinterpret_cast<unsigned char*>(p.counts_e + p.tiles_e);
   p.stats = reinterpret_cast<long long*>(stats);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  aug_count_kernel<<<p.tiles_w + p.tiles_e, AUG_THREADS, 0, st>>>(p);
+  launch_kernel(aug_count_kernel, dim3(p.tiles_w + p.tiles_e), dim3(AUG_THREADS), 0, st, p);
   TA_CHECK_LAUNCH();
-  aug_scan_kernel<<<1, 1024, 0, st>>>(p);
+  launch_kernel(aug_scan_kernel, dim3(1), dim3(1024), 0, st, p);
   TA_CHECK_LAUNCH();
-  aug_compact_kernel<<<p.tiles_w, AUG_THREADS, 0, st>>>(p);
+  launch_kernel(aug_compact_kernel, dim3(p.tiles_w), dim3(AUG_THREADS), 0, st, p);
   TA_CHECK_LAUNCH();
-  aug_apply_kernel<<<p.tiles_e, AUG_THREADS, 0, st>>>(p);
+  launch_kernel(aug_apply_kernel, dim3(p.tiles_e), dim3(AUG_THREADS), 0, st, p);
   TA_CHECK_LAUNCH();
   return 0;
 }

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/tradeaid_b200.h"
@@ -21,6 +22,11 @@ int set_err(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return 1;
+}
+
+bool pdl_enabled() {
+  static const int on = [] { const char* e = getenv("TA_PDL"); return e ? atoi(e) : 0; }();
+  return on != 0;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -511,6 +511,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // PDL: everything above is on-chip set-up (barriers, TMEM, descriptor prefetch); from here on the kernel reads what
+  // the previous kernel of the stream wrote
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_per_group = p.m_blocks * p.n_blocks;
   const int total_tiles = tiles_per_group * p.G0 * p.G1;
@@ -650,6 +654,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();            // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();       // PDL: on-chip set-up done; wait for the previous kernel before touching global memory
+  pdl_wait();
 
   const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int tiles_per_group = m_pairs * p.n_blocks;
@@ -877,7 +883,7 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   }
   const long long total = (long long)p.m_blocks * p.n_blocks * p.G0 * p.G1;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  gemm_bf16_kernel<BLOCK_N><<<grid, Cfg::THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
+  launch_kernel(gemm_bf16_kernel<BLOCK_N>, dim3(grid), dim3(Cfg::THREADS), smem_bytes, stream, tmA, tmB, em, p);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -900,7 +906,7 @@ static int launch_gemm2(const ta_operand* A, const ta_operand* B, GemmParams& p,
   const long long total = m_pairs * p.n_blocks * p.G0 * p.G1;
   const long long max_clusters = num_sms() / 2;
   const int clusters = (int)(total < max_clusters ? total : max_clusters);
-  gemm2_bf16_kernel<<<2 * clusters, GEMM2_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
+  launch_kernel(gemm2_bf16_kernel, dim3(2 * clusters), dim3(GEMM2_THREADS), smem_bytes, stream, tmA, tmB, em, p);
   TA_CHECK_LAUNCH();
   return 0;
 }

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(DM_THREADS) directional_metrics_kernel(
     const float* __restrict__ logits, long long ld, const double* __restrict__ vals, const long long* __restrict__ prev,
     long long prev_stride, const long long* __restrict__ actual, long long actual_stride, int rows, int V, int is_pct,
     long long* __restrict__ counts, double* __restrict__ certainty) {
+  pdl_prologue();
   __shared__ int s_win[DM_ROWS];
   __shared__ double s_cert[DM_ROWS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,7 +90,7 @@ extern "C" int32_t ta_directional_metrics(const float* last_logits, int64_t ld, 
   TA_CHECK_ARG(last_logits && vocab_values && actual_tokens && counts && certainty, "ta_directional_metrics: null pointer");
   TA_CHECK_ARG(is_percentage || prev_tokens, "ta_directional_metrics: value data needs the previous input tokens");
   TA_CHECK_ARG(rows > 0 && V > 0, "ta_directional_metrics: bad sizes");
-  directional_metrics_kernel<<<1, DM_THREADS, 0, (cudaStream_t)stream>>>(
+  launch_kernel(directional_metrics_kernel, dim3(1), dim3(DM_THREADS), 0, (cudaStream_t)stream, 
       last_logits, ld, vocab_values, (const long long*)prev_tokens, prev_stride, (const long long*)actual_tokens,
       actual_stride, rows, V, is_percentage ? 1 : 0, (long long*)counts, certainty);
   TA_CHECK_LAUNCH();

@@ -26,6 +26,7 @@ __device__ __forceinline__ float warp_max(float v) {
 __global__ void gather_batch_kernel(const int32_t* __restrict__ store, long long store_stride, int M,
                                     const long long* __restrict__ ix, int B, int T, long long* __restrict__ xb,
                                     long long* __restrict__ yb) {
+  pdl_prologue();
   const long long total = (long long)M * B * (T + 1);
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(e % (T + 1));
@@ -43,6 +44,7 @@ __global__ void gather_batch_kernel(const int32_t* __restrict__ store, long long
 __global__ void embed_fwd_kernel(const long long* __restrict__ idx, const float* __restrict__ tok,
                                  const long long* __restrict__ voff, const float* __restrict__ pos, float* __restrict__ x,
                                  int M, long long rows, int T, int C) {
+  pdl_prologue();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = (long long)M * rows;
@@ -67,6 +69,7 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ idx, const float*
 
 // dP[t, c] = sum_m sum_b dx[m, b*T + t, c]   (position table shared by all modalities, model.py:298,313)
 __global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int M, int B, int T, int C) {
+  pdl_prologue();
   const int t = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
@@ -80,6 +83,7 @@ __global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __rest
 // (deterministic). One block per (m, v): scan the modality's indices in chunks, compact matches, accumulate.
 __global__ void embed_bwd_tok_kernel(const long long* __restrict__ idx, const float* __restrict__ dx,
                                      const long long* __restrict__ voff, float* __restrict__ dtok, long long rows, int C) {
+  pdl_prologue();
   constexpr int CHUNK = 1024;
   __shared__ int match[CHUNK];
   __shared__ int warp_cnt[32];
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               long long rows_total, long long rows_per_group, int C, float eps) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows_total) return;
@@ -219,6 +224,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
               const float* __restrict__ dstream_in, float* __restrict__ dstream_out, __nv_bfloat16* __restrict__ dstream_bf16,
               long long ld_dbf, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, long long rows_per_group,
               int C) {
+  pdl_prologue();
   constexpr int SLOTS = 256 / TPR;
   constexpr int WPR = TPR / 32;                 // warps per row
   __shared__ float red[2][2 * R][SLOTS][WPR > 1 ? WPR : 1];
@@ -368,6 +374,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float*
 // out[g, c] = sum_{p < parts_per_group} part[g*parts_per_group + p, c]
 __global__ void partial_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int parts_per_group, int C,
                                       long long out_gs) {
+  pdl_prologue();
   const int g = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -384,6 +391,7 @@ __global__ void __launch_bounds__(256)
 ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ldl, const long long* __restrict__ targets,
                   float* __restrict__ row_loss, __nv_bfloat16* __restrict__ dlogits, long long ldd, long long rows, int V,
                   float scale) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -410,6 +418,7 @@ ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ldl, const long lo
 
 // out[g] = mean over rows of in[g, :rows]; one block per group, fixed summation tree => deterministic.
 __global__ void row_mean_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows) {
+  pdl_prologue();
   __shared__ float sh[32];
   const float* p = in + (long long)blockIdx.x * rows;
   float a = 0.f;
@@ -429,6 +438,7 @@ __global__ void row_mean_kernel(const float* __restrict__ in, float* __restrict_
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, long long gs, float* __restrict__ part,
                       long long rows, int N, int splits) {
+  pdl_prologue();
   __shared__ float sh[8][64];
   const int g = blockIdx.z, split = blockIdx.y;
   const int c0 = blockIdx.x * 64;
@@ -466,6 +476,7 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, long l
 // dst[g, r, c] (bf16, zero padded) = src[g, r, c] (fp32) for r < R, c < Cs
 __global__ void cast_pad_kernel(const float* __restrict__ src, long long sg, long long sr, __nv_bfloat16* __restrict__ dst,
                                 long long dg, long long dr, int G, int R, int Cs, int Rd, int Cd) {
+  pdl_prologue();
   const long long total = (long long)G * Rd * Cd;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e % Cd);
@@ -480,6 +491,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long sg, lon
 // dst (fp32, ld = dr) = src (fp32 padded, ld = sr) unpadded copy: dst[g, r, c] = src[g, r, c], r < R, c < Cn
 __global__ void unpad_f32_kernel(const float* __restrict__ src, long long sg, long long sr, float* __restrict__ dst,
                                  long long dg, long long dr, int G, int R, int Cn) {
+  pdl_prologue();
   const long long total = (long long)G * R * Cn;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e % Cn);
@@ -492,6 +504,7 @@ __global__ void unpad_f32_kernel(const float* __restrict__ src, long long sg, lo
 
 // contiguous fp32 -> bf16 cast, 8 elements per thread (n % 8 == 0 handled by the vector body, tail scalar)
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_prologue();
   const long long nv = n / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
@@ -523,6 +536,7 @@ static int grid_for(long long work_items, int per_block, int max_blocks_per_sm =
 __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, long long gs_src,
                                     __nv_bfloat16* __restrict__ dst, long long ld_dst, long long gs_dst, long long rows, int cols,
                                     unsigned thresh, float scale, unsigned long long seed, const unsigned long long* step) {
+  pdl_prologue();
   const int c8n = (cols + 7) >> 3;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = blockIdx.y;
@@ -541,6 +555,7 @@ __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ src, long 
 // attention keep mask as bytes [n_src][G][B][H][T][T] (tests): plane = ((s*G + g)*B + b)*H + h, kind 1
 __global__ void dropout_attn_mask_kernel(uint8_t* __restrict__ mask, long long planes, int T, unsigned thresh, unsigned long long seed,
                                          const unsigned long long* step) {
+  pdl_prologue();
   const int c8n = (T + 7) >> 3;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= planes * T * c8n) return;
@@ -565,7 +580,7 @@ int32_t ta_gather_batch(const int32_t* store, int64_t store_stride, int32_t M, c
   TA_CHECK_ARG(store && ix && xb && yb, "ta_gather_batch: null pointer");
   TA_CHECK_ARG(M > 0 && B > 0 && T > 0, "ta_gather_batch: non-positive size");
   const long long total = (long long)M * B * (T + 1);
-  gather_batch_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_kernel(gather_batch_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       store, store_stride, M, (const long long*)ix, B, T, (long long*)xb, (long long*)yb);
   TA_CHECK_LAUNCH();
   return 0;
@@ -575,7 +590,7 @@ int32_t ta_embed_fwd(const int64_t* idx, const float* tok, const int64_t* voff, 
                      int64_t rows, int32_t T, int32_t C, void* stream) {
   TA_CHECK_ARG(idx && tok && voff && pos && x, "ta_embed_fwd: null pointer");
   TA_CHECK_ARG(M > 0 && rows > 0 && T > 0 && C > 0 && rows % T == 0, "ta_embed_fwd: bad sizes");
-  embed_fwd_kernel<<<grid_for((long long)M * rows, 8), 256, 0, (cudaStream_t)stream>>>(
+  launch_kernel(embed_fwd_kernel, dim3(grid_for((long long)M * rows, 8)), dim3(256), 0, (cudaStream_t)stream, 
       (const long long*)idx, tok, (const long long*)voff, pos, x, M, rows, T, C);
   TA_CHECK_LAUNCH();
   return 0;
@@ -585,10 +600,10 @@ int32_t ta_embed_bwd(const int64_t* idx, const float* dx, const int64_t* voff, i
                      float* dpos, int32_t M, int32_t B, int32_t T, int32_t C, void* stream) {
   TA_CHECK_ARG(idx && dx && voff && dtok && dpos, "ta_embed_bwd: null pointer");
   TA_CHECK_ARG(C <= 8 * 256, "ta_embed_bwd: n_embd > 2048 not supported");
-  embed_bwd_pos_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(dx, dpos, M, B, T, C);
+  launch_kernel(embed_bwd_pos_kernel, dim3(T), dim3(256), 0, (cudaStream_t)stream, dx, dpos, M, B, T, C);
   TA_CHECK_LAUNCH();
   dim3 grid(max_vocab, M);
-  embed_bwd_tok_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)idx, dx, (const long long*)voff, dtok,
+  launch_kernel(embed_bwd_tok_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const long long*)idx, dx, (const long long*)voff, dtok,
                                                                (long long)B * T, C);
   TA_CHECK_LAUNCH();
   return 0;
@@ -600,7 +615,7 @@ int32_t ta_dropout_bf16(const void* src, int64_t ld_src, int64_t gs_src, void* d
   TA_CHECK_ARG(p >= 0.f && p < 1.f, "ta_dropout_bf16: p must be in [0, 1)");
   const long long n = rows * ((cols + 7) / 8);
   dim3 grid((unsigned)ceil_div(n, 256), (unsigned)G);
-  dropout_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, ld_src, gs_src, (__nv_bfloat16*)dst, ld_dst,
+  launch_kernel(dropout_bf16_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, ld_src, gs_src, (__nv_bfloat16*)dst, ld_dst,
                                                             gs_dst, rows, cols, dropout_thresh16(p), 1.f / (1.f - p), seed,
                                                             dropout_step_counter());
   TA_CHECK_LAUNCH();
@@ -612,7 +627,7 @@ int32_t ta_dropout_attn_mask(uint8_t* mask, int32_t n_src, int32_t G, int32_t B,
   TA_CHECK_ARG(mask && n_src > 0 && G > 0 && B > 0 && H > 0 && T > 0, "ta_dropout_attn_mask: bad arguments");
   const long long planes = (long long)n_src * G * B * H;
   const long long n = planes * T * ((T + 7) / 8);
-  dropout_attn_mask_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, planes, T, dropout_thresh16(p), seed,
+  launch_kernel(dropout_attn_mask_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, mask, planes, T, dropout_thresh16(p), seed,
                                                                                          dropout_step_counter());
   TA_CHECK_LAUNCH();
   return 0;
@@ -626,7 +641,7 @@ int32_t ta_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
   const int grid = (int)ceil_div(rows_total, 8);
   auto st = (cudaStream_t)stream;
   auto* y = (__nv_bfloat16*)y_bf16;
-#define TA_LN_FWD(NV) ln_fwd_kernel<NV><<<grid, 256, 0, st>>>(x, gamma, beta, y, ldy, mean, rstd, rows_total, rows_per_group, C, eps)
+#define TA_LN_FWD(NV) launch_kernel(ln_fwd_kernel<NV>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, ldy, mean, rstd, rows_total, rows_per_group, C, eps)
   if (C <= 128) TA_LN_FWD(1);
   else if (C <= 256) TA_LN_FWD(2);
   else if (C <= 512) TA_LN_FWD(4);
@@ -673,7 +688,7 @@ int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, cons
   auto st = (cudaStream_t)stream;
   dim3 grid((unsigned)gx, (unsigned)G);
 #define TA_LN_BWD(TPR, NV)                                                                                             \
-  ln_bwd_kernel<TPR, NV, 4><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy_bf16, lddy, x, gamma, mean, rstd, dstream_in, \
+  launch_kernel(ln_bwd_kernel<TPR, NV, 4>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dy_bf16, lddy, x, gamma, mean, rstd, dstream_in, \
                                                   dstream_out, (__nv_bfloat16*)dstream_bf16, ld_dbf, pg, pb,            \
                                                   rows_per_group, C)
   if (tpr == 32) TA_LN_BWD(32, 1);
@@ -684,9 +699,9 @@ int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, cons
 #undef TA_LN_BWD
   TA_CHECK_LAUNCH();
   dim3 rg((unsigned)ceil_div(C, 256), G);
-  partial_reduce_kernel<<<rg, 256, 0, st>>>(pg, dgamma, gx, C, C);
+  launch_kernel(partial_reduce_kernel, dim3(rg), dim3(256), 0, st, pg, dgamma, gx, C, C);
   TA_CHECK_LAUNCH();
-  partial_reduce_kernel<<<rg, 256, 0, st>>>(pb, dbeta, gx, C, C);
+  launch_kernel(partial_reduce_kernel, dim3(rg), dim3(256), 0, st, pb, dbeta, gx, C, C);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -696,11 +711,11 @@ int32_t ta_cross_entropy(const float* logits, int64_t ldl, const int64_t* target
   TA_CHECK_ARG(logits && targets && row_loss && loss_mean, "ta_cross_entropy: null pointer");
   TA_CHECK_ARG(rows > 0 && V > 0, "ta_cross_entropy: bad sizes");
   auto st = (cudaStream_t)stream;
-  ce_fwd_bwd_kernel<<<(int)ceil_div(rows, 8), 256, 0, st>>>(logits, ldl, (const long long*)targets, row_loss,
+  launch_kernel(ce_fwd_bwd_kernel, dim3((int)ceil_div(rows, 8)), dim3(256), 0, st, logits, ldl, (const long long*)targets, row_loss,
                                                           (__nv_bfloat16*)dlogits_bf16, ldd, rows, V,
                                                           grad_scale / (float)rows);
   TA_CHECK_LAUNCH();
-  row_mean_kernel<<<1, 1024, 0, st>>>(row_loss, loss_mean, rows);
+  launch_kernel(row_mean_kernel, dim3(1), dim3(1024), 0, st, row_loss, loss_mean, rows);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -716,10 +731,10 @@ int32_t ta_colsum_bf16(const void* dy_bf16, int64_t ld, int64_t gs, float* out, 
   const int splits = (int)(rows >= 4096 ? 16 : (rows >= 512 ? 4 : 1));
   auto st = (cudaStream_t)stream;
   dim3 grid((unsigned)ceil_div(N, 64), splits, G);
-  colsum_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy_bf16, ld, gs, workspace, rows, N, splits);
+  launch_kernel(colsum_partial_kernel, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dy_bf16, ld, gs, workspace, rows, N, splits);
   TA_CHECK_LAUNCH();
   dim3 rg((unsigned)ceil_div(N, 256), G);
-  partial_reduce_kernel<<<rg, 256, 0, st>>>(workspace, out, splits, N, out_gs);
+  launch_kernel(partial_reduce_kernel, dim3(rg), dim3(256), 0, st, workspace, out, splits, N, out_gs);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -729,7 +744,7 @@ int32_t ta_cast_pad_bf16(const float* src, int64_t sg, int64_t sr, void* dst_bf1
   TA_CHECK_ARG(src && dst_bf16, "ta_cast_pad_bf16: null pointer");
   const long long total = (long long)G * Rd * Cd;
   if (total == 0) return 0;
-  cast_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, sg, sr, (__nv_bfloat16*)dst_bf16, dg, dr,
+  launch_kernel(cast_pad_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, sg, sr, (__nv_bfloat16*)dst_bf16, dg, dr,
                                                                          G, R, Cs, Rd, Cd);
   TA_CHECK_LAUNCH();
   return 0;
@@ -740,7 +755,7 @@ int32_t ta_unpad_f32(const float* src, int64_t sg, int64_t sr, float* dst, int64
   TA_CHECK_ARG(src && dst, "ta_unpad_f32: null pointer");
   const long long total = (long long)G * R * Cn;
   if (total == 0) return 0;
-  unpad_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, sg, sr, dst, dg, dr, G, R, Cn);
+  launch_kernel(unpad_f32_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, sg, sr, dst, dg, dr, G, R, Cn);
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -749,7 +764,7 @@ int32_t ta_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) 
   TA_CHECK_ARG(src && dst_bf16, "ta_cast_bf16: null pointer");
   TA_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst_bf16 & 15) == 0, "ta_cast_bf16: pointers must be 16-byte aligned");
   if (n == 0) return 0;
-  cast_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst_bf16, n);
+  launch_kernel(cast_bf16_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst_bf16, n);
   TA_CHECK_LAUNCH();
   return 0;
 }

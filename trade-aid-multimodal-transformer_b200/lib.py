@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtradeaid_b200.so")
+LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
 ABI_VERSION = 2
 
 
