@@ -964,9 +964,15 @@ extern "C" int32_t ta_gemm_bf16(const ta_operand* A, const ta_operand* B, int64_
   // CTA pairs (256 x 256 tiles, B split across the pair) for the large problems: a third less L2 -> smem traffic
   static const int use_2cta = env_int("TA_GEMM_2CTA", 1);
   static const int min_k_2cta = env_int("TA_GEMM_2CTA_MINK", 128);
-  if (use_2cta && bn == 256 && M >= 256 && N >= 256 && K >= min_k_2cta &&
-      groups * ceil_div(M, 2 * BLOCK_M) * ceil_div(N, 256) >= num_sms() / 4)
-    return launch_gemm2(A, B, p, st);
+  const long long pair_tiles = groups * ceil_div(M, 2 * BLOCK_M) * ceil_div(N, 256);
+  if (use_2cta && M >= 256 && N >= 256 && K >= min_k_2cta && pair_tiles >= num_sms() / 4) {
+    if (bn == 256) return launch_gemm2(A, B, p, st);
+    // 128-wide tiles were picked only to fill a wave (fewer than one 256-wide tile per SM): if the CTA pairs need no
+    // more time - waves of pair tiles x 2 <= waves of 128 x 128 tiles - take them, they move a third less L2 -> smem
+    // traffic per flop (the 1-CTA kernel ran the small dW problems, M, N ~ 1024, K = 16384, at 0.62 tensor-pipe activity)
+    if (!force_bn && bn == 128 && 2 * ceil_div(pair_tiles, num_sms() / 2) <= ceil_div(tiles(128), num_sms()))
+      return launch_gemm2(A, B, p, st);
+  }
   if (bn == 256) return launch_gemm<256>(A, B, p, st);
   if (bn == 128) return launch_gemm<128>(A, B, p, st);
   return launch_gemm<64>(A, B, p, st);
