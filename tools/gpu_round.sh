@@ -16,9 +16,10 @@ timeout 300 python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((4 * L)) -c $L --csv --log-file gpurun_out/${tag}_launches_c4.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ncu_launches.log 2>&1
 echo "ncu launches rc=$? (L=$L)"
 # the .ncu-rep stays on the box (gpurun_out/ is capped at 64 MiB): only its csv pages and the one-screen summary come back
+if [ -z "$SKIP_HBM_NCU" ]; then
 HBM_ONCE=1 timeout 300 python tools/hbm_kernels.py > /dev/null 2>&1 && \
-HBM_ONCE=1 timeout 900 ncu --set full --clock-control none -c 40 -o /tmp/${tag}_prof_hbm_kernels -f python tools/hbm_kernels.py > gpurun_out/${tag}_ncu_hbm.log 2>&1
+HBM_ONCE=1 timeout 900 ncu --set full --clock-control none -k regex:"ta::|attn_|gemm" -c 40 -o /tmp/${tag}_prof_hbm_kernels -f python tools/hbm_kernels.py > gpurun_out/${tag}_ncu_hbm.log 2>&1
 echo "ncu hbm rc=$?"
 python tools/ncu_summary.py /tmp/${tag}_prof_hbm_kernels.ncu-rep > gpurun_out/${tag}_prof_hbm_kernels_ncu_full.txt 2> /dev/null
-ncu -i /tmp/${tag}_prof_hbm_kernels.ncu-rep --page raw --csv > gpurun_out/${tag}_prof_hbm_kernels_raw.csv 2> /dev/null
+fi
 ls -la gpurun_out | tail -20; du -sh gpurun_out
