@@ -117,12 +117,11 @@ def test_kv_cache_decode_equals_full_forward():
         nv[k].copy_(v)
     g = torch.Generator().manual_seed(9)
     idx = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V])
-    ref_logits, _ = R.forward(sd, R.Cfg(T, C, H, L, V, cross), list(idx), None) if hasattr(R, "forward") else (None, None)
+    ref_logits, _ = R.forward(sd, R.Cfg(T, C, H, L, V, cross), list(idx), None)
     full, _ = eng.forward(idx, None, save=False)
     full = [x.clone() for x in full]
-    if ref_logits is not None:
-        for a, b in zip(full, ref_logits):
-            assert (a - b).abs().max().item() <= 2e-5
+    for a, b in zip(full, ref_logits):
+        assert (a - b).abs().max().item() <= 2e-5
     cache = KVCache(eng, B)
     n0 = 5
     lg, _ = eng.forward(idx[:, :, :n0].contiguous(), None, save=False, cache=cache)
@@ -133,3 +132,35 @@ def test_kv_cache_decode_equals_full_forward():
         assert max((a[:, 0] - b[:, t]).abs().max().item() for a, b in zip(lg, full)) <= 1e-6
     with pytest.raises(ValueError):
         eng.forward(idx[:, :, :1].contiguous(), None, save=False, cache=cache)      # cache is full
+
+
+def test_grouped_output_heads_equal_per_modality_heads(monkeypatch):
+    """engine.py: with one vocabulary size for every modality the output-head kinds are a constant stride apart in the
+    flat buffer and go through one grouped launch per GEMM; logits, losses and gradients must equal the per-modality form
+    (and the reference restatement)."""
+    from oracle import restatement as R
+    V, cross, T, C, H, L, B = [32, 32, 32], [True, False, True], 8, 32, 2, 2, 3
+    cfg = R.Cfg(T, C, H, L, V, cross)
+    sd = R.random_state_dict(cfg, seed=4)
+    g = torch.Generator().manual_seed(9)
+    idx = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V])
+    tgt = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V])
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TRADEAID_GROUPED_HEADS", flag)
+        eng = Engine(Dims(V, cross, T, C, H, L), "cpu", ops=emu_ops, act_dtype=torch.float32)
+        assert (eng._heads_grouped is not None) == (flag == "1")
+        nv = eng.layout.named_views(eng.master)
+        for k, v in sd.items():
+            nv[k].copy_(v)
+        logits, losses = eng.forward(idx, tgt, save=True)
+        eng.backward()
+        outs[flag] = (torch.cat([x.flatten() for x in logits]).clone(), losses.clone(), eng.grad.clone())
+        eng.backward([1.0, 0.5, 2.0])      # weighted losses take the per-modality path in both forms
+        outs[flag + "w"] = eng.grad.clone()
+    assert all(torch.equal(a, b) for a, b in zip(outs["1"], outs["0"])) and torch.equal(outs["1w"], outs["0w"])
+    ref_logits, _, ref_grads = R.forward_backward(sd, cfg, list(idx), list(tgt))
+    assert (outs["1"][0] - torch.cat([x.flatten() for x in ref_logits])).abs().max().item() <= 2e-5
+    # vocabularies of different sizes (or odd hidden widths) keep the per-modality launches
+    assert Engine(Dims([32, 40], [False, False], T, C, H, 1), "cpu", ops=emu_ops)._heads_grouped is None
+    assert Engine(Dims([30, 30], [False, False], T, C, H, 1), "cpu", ops=emu_ops)._heads_grouped is None

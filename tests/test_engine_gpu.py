@@ -232,3 +232,24 @@ def test_kv_cache_decode_matches_full_forward(M, cross, V, B, T, C, H, L, n0, sc
             assert rel <= 1e-2, (t, rel)
     with pytest.raises(ValueError):
         eng.forward(idx[:, :, :2].contiguous(), None, save=False, cache=cache)      # decode takes one position at a time
+
+
+def test_grouped_output_heads_are_bit_identical(monkeypatch):
+    """Output heads of all modalities in one grouped launch per GEMM (equal vocabulary sizes) vs one launch per modality."""
+    from tradeaid_b200.engine import Engine
+    from tradeaid_b200.params import Dims
+    V, cross, T, C, H, L, B = [256, 256, 256], [True, False, True], 64, 128, 4, 1, 4
+    g = torch.Generator().manual_seed(8)
+    idx = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V]).cuda()
+    tgt = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in V]).cuda()
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TRADEAID_GROUPED_HEADS", flag)
+        eng = Engine(Dims(V, cross, T, C, H, L), "cuda")
+        assert (eng._heads_grouped is not None) == (flag == "1")
+        eng.layout.init_(eng.master, generator=torch.Generator(device="cuda").manual_seed(0))
+        logits, losses = eng.forward(idx, tgt, save=True)
+        eng.backward()
+        out[flag] = ([x.clone() for x in logits], losses.clone(), eng.grad.clone())
+    assert all(torch.equal(a, b) for a, b in zip(out["1"][0], out["0"][0]))
+    assert torch.equal(out["1"][1], out["0"][1]) and torch.equal(out["1"][2], out["0"][2])

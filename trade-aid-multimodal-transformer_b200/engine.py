@@ -95,6 +95,23 @@ class Engine:
             self._bd = (gsz, ng, torch.zeros(dims.n_layer, dims.M, ng, gsz * dims.hs, gsz * dims.h2, dtype=act_dtype,
                                              device=self.device))
         self._bufs = {}
+        # output heads (model.py:339-352): with one vocabulary size for every modality (and TMA-able widths) the per-modality
+        # weight kinds hd_w1_i, hd_b1_i, hd_w2_i, hd_b2_i sit a constant stride apart in the flat buffer, so all
+        # modalities go through one grouped launch per GEMM instead of M launches of a few dozen tiles each
+        self._heads_grouped = None
+        Vs = dims.vocab_sizes
+        if (os.environ.get("TRADEAID_GROUPED_HEADS", "1") != "0" and dims.M > 1 and len(set(Vs)) == 1
+                and (Vs[0] // 2) % 8 == 0 and Vs[0] // 2 > 0):
+            off = [self.layout.kinds[f"hd_w1_{i}"][0] for i in range(dims.M)]
+            stride = off[1] - off[0]
+            if all(off[i + 1] - off[i] == stride for i in range(dims.M - 1)):
+                V, V2, C, M = Vs[0], Vs[0] // 2, dims.n_embd, dims.M
+                o = {k: self.layout.kinds[f"hd_{k}_0"][0] for k in ("w1", "b1", "w2", "b2")}
+                shapes = {"w1": ((M, V2, C), (stride, C, 1)), "b1": ((M, V2), (stride, 1)),
+                          "w2": ((M, V, V2), (stride, V2, 1)), "b2": ((M, V), (stride, 1))}
+                view = lambda flat, k: flat.as_strided(shapes[k][0], shapes[k][1], o[k])  # noqa: E731
+                self._heads_grouped = {"P": {k: view(self.master, k) for k in shapes}, "G": {k: view(self.grad, k) for k in shapes},
+                                       "S": {k: view(self.shadow, k) for k in ("w1", "w2")}}
         self._voff = torch.tensor(dims.voff, dtype=torch.int64, device=self.device)
         self._saved = None
         self.shadows_stale = True
@@ -102,6 +119,9 @@ class Engine:
         # (site, layer), a device step counter mixed in by the kernels makes every step (and graph replay) different
         self.dropout_base_seed = 0x5DEECE66D
         self._drop_step = None
+        # where backward reports ("part", l) to its stage hook (trainer.py: the SM-margin window of the data-parallel
+        # exchange): after the whole cross-attention backward of the layer ("cross") or after its attention kernels ("attn")
+        self._dp_window = os.environ.get("TRADEAID_DP_WINDOW", "cross")
 
     # ------------------------------------------------------------------------------------------ weights
     def _make_padded(self):
@@ -281,7 +301,16 @@ class Engine:
         stf = nb("stf", 0, (2, M * BT), f32)
         ops.layernorm_fwd(x, P["lnf_w"], P["lnf_b"], hf, stf[0], stf[1])
         logits, hhs = [], []
-        for i, V in enumerate(d.vocab_sizes):
+        hg = self._heads_grouped
+        if hg is not None:
+            V = d.vocab_sizes[0]
+            hd_all = nb("hd_all", 0, (M, BT, V // 2), bf)
+            lg_all = nb("logits_all", 0, (M, BT, V), f32)
+            ops.gemm(hf, hg["S"]["w1"], bias=hg["P"]["b1"], act=ACT_TANH, out_bf16=hd_all)
+            ops.gemm(hd_all, hg["S"]["w2"], bias=hg["P"]["b2"], out_f32=lg_all)
+            logits, hhs = [lg_all[i] for i in range(M)], [hd_all[i] for i in range(M)]
+            S.update(hd_all=hd_all)
+        for i, V in enumerate(d.vocab_sizes if hg is None else []):
             V2 = V // 2
             hd = nb(f"hd{i}", 0, (BT, r8(max(V2, 1))), bf)[:, :V2]
             lg = nb(f"logits{i}", 0, (BT, V), f32)
@@ -298,9 +327,14 @@ class Engine:
             assert targets.shape == idx.shape and targets.dtype == torch.int64 and targets.is_contiguous()
             losses = nb("losses", 0, (M,), f32)
             dls = []
+            dl_all = nb("dlogits_all", 0, (M, BT, d.vocab_sizes[0]), bf) if (save and hg is not None) else None
+            S.update(dl_all=dl_all)
             for i, V in enumerate(d.vocab_sizes):
                 row_loss = nb(f"rowloss{i}", 0, (BT,), f32)
-                dl = nb(f"dlogits{i}", 0, (BT, r8(V)), bf)[:, :V] if save else None
+                if dl_all is not None:
+                    dl = dl_all[i]
+                else:
+                    dl = nb(f"dlogits{i}", 0, (BT, r8(V)), bf)[:, :V] if save else None
                 ops.cross_entropy(logits[i], targets[i].view(BT), row_loss, losses[i:i + 1], dl, 1.0)
                 dls.append(dl)
             S["dlogits"] = dls
@@ -460,7 +494,7 @@ class Engine:
             ops.dropout_bf16(t, out, pd, self._seed(site, l, sub), self._drop_step)
             return out
 
-        cs_ws = self.buf("cs_ws", (max(ops.colsum_workspace(BT, 4 * C, M), ops.colsum_workspace(BT, max(d.vocab_sizes), 1),
+        cs_ws = self.buf("cs_ws", (max(ops.colsum_workspace(BT, 4 * C, M), ops.colsum_workspace(BT, max(d.vocab_sizes), M),
                                        ops.colsum_workspace(BT, 3 * H * h2p, M)),), f32)
         # the workspace depends on the launch shape: grouped launches (all modalities) and the per-modality launches
         # of the cross-attention LayerNorm share one buffer
@@ -470,7 +504,17 @@ class Engine:
         dxb = self.buf("dxb", (M, BT, C), bf)
         # ---- output heads
         dhf = self.buf("dhf", (M, BT, C), bf)
-        for i, V in enumerate(d.vocab_sizes):
+        hg = self._heads_grouped if (loss_weights is None and S.get("dl_all") is not None) else None
+        if hg is not None:     # every modality in one grouped launch per op
+            dl_all, hd_all = S["dl_all"], S["hd_all"]
+            ops.colsum(dl_all, hg["G"]["b2"], cs_ws)
+            ops.gemm(dl_all, hd_all, a_major=1, b_major=1, out_f32=hg["G"]["w2"])
+            dhd_all = self.buf("dhd_all", hd_all.shape, bf)
+            ops.gemm(dl_all, hg["S"]["w2"], b_major=1, aux=hd_all, aux_mode=AUX_TANH_BWD, out_bf16=dhd_all)
+            ops.gemm(dhd_all, S["hf"], a_major=1, b_major=1, out_f32=hg["G"]["w1"])
+            ops.colsum(dhd_all, hg["G"]["b1"], cs_ws)
+            ops.gemm(dhd_all, hg["S"]["w1"], b_major=1, out_bf16=dhf)
+        for i, V in enumerate(d.vocab_sizes if hg is None else []):
             V2 = V // 2
             dl = S["dlogits"][i]
             w = 1.0 if loss_weights is None else float(loss_weights[i])
@@ -594,7 +638,7 @@ class Engine:
                               dqc[xi:xi + 1], dks, dvs, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,
                               o_src=Sl["ocs"][xi] if Sl["ocs"] is not None else None,
                               **({"dropout_p": pd, "dropout_seed": self._seed(self.SITE_CA_ATTN, l, xi), "dropout_step": self._drop_step} if pd > 0.0 else {}))
-        if stage_hook is not None and os.environ.get("TRADEAID_DP_WINDOW", "cross") == "attn":
+        if stage_hook is not None and self._dp_window == "attn":
             stage_hook(("part", l))      # the first few milliseconds of this layer's backward are enqueued
         # query projection and its LayerNorm (input: the snapshot x2 of the querying modality)
         ops.gemm(dqc, Sl["hc"], a_major=1, b_major=1, out_f32=G["ca_wq"][l].reshape(Xc, C, C))
@@ -616,7 +660,7 @@ class Engine:
             ops.gemm(dkv, Sl["a_bf"][j0:j1], a_major=1, b_major=1, out_f32=Gkv[sl].reshape(n, nq * 2 * C, C))
             ops.gemm(dkv, Wkv[sl].reshape(n, nq * 2 * C, C), b_major=1, residual=dx[j0:j1], out_f32=dx[j0:j1],
                      out_bf16=dxb[j0:j1])
-        if stage_hook is not None and os.environ.get("TRADEAID_DP_WINDOW", "cross") != "attn":
+        if stage_hook is not None and self._dp_window != "attn":
             stage_hook(("part", l))
 
     # ------------------------------------------------------------------------------------------ bookkeeping
