@@ -265,7 +265,7 @@ class Engine:
                          out_bf16=self._qkv_groups(qkv, BT))
             o = nb("o", l, (M, BT, C), bf)
             lse = nb("lse", l, (1, M, B, H, T), f32)
-            if cache is not None:
+            if cache is not None:      # append this call's keys / values (a strided device copy: cache bookkeeping, not math)
                 cache.self_kv[l][:, :, t0:t0 + T].copy_(qkv.view(M, B, T, 3 * C)[..., C:])
             if decode:
                 kc = cache.self_kv[l]

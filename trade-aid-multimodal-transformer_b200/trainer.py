@@ -85,7 +85,12 @@ class Trainer:
         """One coalesced asynchronous all-reduce(sum) of a bucket's gradient ranges. The process group's stream waits
         for the work enqueued on the current stream so far; the current stream is not blocked."""
         import torch.distributed as dist
-        with dist._coalescing_manager(group=self.pg, async_ops=True) as cm:
+        cmgr = getattr(dist, "_coalescing_manager", None)
+        if cmgr is None:       # no coalescing support in this torch: one asynchronous all-reduce per range
+            for t in views:
+                self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            return
+        with cmgr(group=self.pg, async_ops=True) as cm:
             for t in views:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
         self._works.append(cm)
