@@ -144,6 +144,53 @@ def metrics_case():
     print("metrics:", res)
 
 
+def curve200_case():
+    """North-star criterion "the 200-step loss curve matches within 1e-2 absolute": the UNMODIFIED reference trained for
+    200 AdamW steps (lr 1e-3, main.py:646-650 loop body) through its own get_batch on SURVEY appendix-E streams; stores
+    the summed loss of every step. Initial weights = oracle.restatement.random_state_dict(seed 0) with the second
+    q/k/v matrices at a reference-like scale, loaded into the reference model (so the fixture needs no weights)."""
+    sys.path.append(os.path.dirname(os.path.dirname(OUT)))      # repo root (for oracle/), after the reference on the path
+    from oracle import restatement as R
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("syn", os.path.join(os.path.dirname(os.path.dirname(OUT)),
+                                                                     "trade-aid-multimodal-transformer_b200", "synthetic.py"))
+    syn = importlib.util.module_from_spec(spec); spec.loader.exec_module(syn)
+    import training_utils as tu
+    V, cross, T, C, H, L, B, N, steps, lr = [64, 64], [True, False], 32, 128, 4, 2, 16, 4096, 200, 1e-3
+    set_cfg(T, C, H, L, B)
+    import model as ref_model
+    m = ref_model.MultimodalTransformer(2, V, params_list(cross))
+    sd = R.random_state_dict(R.Cfg(T, C, H, L, V, cross), seed=0)
+    for k in list(sd):
+        if ".heads." in k and k.endswith(".2.weight") and "sa_layers" in k:
+            sd[k] = sd[k] / 10
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith(".tril") for k in missing), (missing, unexpected)
+    data = [syn.token_stream("price", N, 64, 1000), syn.token_stream("indicator", N, 64, 1001)]
+    tu.all_train_sets = [d.tolist() for d in data]
+    tu.all_val_sets = [d[:64].clone() for d in data]
+    tu.all_vocabularies = [[float(k) for k in range(64)]] * 2
+    tu.all_modality_params = params_list(cross)
+    tu.file_lengths = [N]
+    tu.num_modalities = 2
+    tu.is_percents = False
+    opt = torch.optim.AdamW(m.parameters(), lr=lr)
+    m.train()
+    torch.manual_seed(2)
+    curve = []
+    for _ in range(steps):
+        xb, yb = tu.get_batch("train", 1)
+        _, losses = m(xb, yb)
+        tot = sum(losses)
+        opt.zero_grad(set_to_none=True)
+        tot.backward()
+        opt.step()
+        curve.append(float(tot))
+    torch.save(dict(cfg=dict(V=V, cross=cross, T=T, C=C, H=H, L=L, B=B, N=N, steps=steps, lr=lr, seed=2), curve=curve),
+               os.path.join(OUT, "curve200.pt"))
+    print("curve200:", [round(c, 4) for c in curve[::25]], round(curve[-1], 4))
+
+
 def augmentation_case():
     """data_utils.add_rand_to_data_points (the `[2]` quirk of get_batch, training_utils.py:353-360) on seeded lists:
     outputs after one and after three cumulative applications, and the next outputs of Python's `random` (pins how many
@@ -187,3 +234,4 @@ if __name__ == "__main__":
     get_batch_case()
     metrics_case()
     augmentation_case()
+    curve200_case()

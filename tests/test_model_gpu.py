@@ -200,6 +200,37 @@ def test_estimate_loss_matches_oracle(capsys):
     tu.m = None
 
 
+def test_200_step_loss_curve_vs_reference_golden():
+    """North-star criterion against the reference itself: tests/golden/curve200.pt holds the 200 losses of the UNMODIFIED
+    reference (its own get_batch, model, torch AdamW; lr 1e-3). The engine's trainer fed the same index stream (same
+    torch seed) must stay within 1e-2 absolute over the whole curve."""
+    from oracle import restatement as R
+    from tradeaid_b200 import synthetic as syn
+    from tradeaid_b200.engine import Engine
+    from tradeaid_b200.feeder import TokenStore, generate_batch_starting_indices
+    from tradeaid_b200.params import Dims
+    from tradeaid_b200.trainer import Trainer
+    g = load_golden("curve200.pt")
+    c = g["cfg"]
+    sd = R.random_state_dict(R.Cfg(c["T"], c["C"], c["H"], c["L"], c["V"], c["cross"]), seed=0)
+    for k in list(sd):
+        if ".heads." in k and k.endswith(".2.weight") and "sa_layers" in k:
+            sd[k] = sd[k] / 10
+    eng = Engine(Dims(c["V"], c["cross"], c["T"], c["C"], c["H"], c["L"]), "cuda")
+    nv = eng.layout.named_views(eng.master)
+    for k, v in sd.items():
+        nv[k].copy_(v)
+    tr = Trainer(eng, lr=c["lr"])
+    store = TokenStore([syn.token_stream("price", c["N"], 64, 1000), syn.token_stream("indicator", c["N"], 64, 1001)], "cuda")
+    torch.manual_seed(c["seed"])
+    worst = 0.0
+    for step in range(c["steps"]):
+        ix = generate_batch_starting_indices(c["N"], c["T"], c["B"], "train", [c["N"]], False)
+        xb, yb = store.gather(ix, c["T"])
+        worst = max(worst, abs(float(tr.step(xb, yb).sum()) - g["curve"][step]))
+    assert worst <= 1e-2, worst
+
+
 def test_200_step_loss_curve_vs_oracle():
     """North-star criterion: the 200-step loss curve matches the fp32 reference within 1e-2 absolute (identical
     batches, identical initial weights, lr 1e-3)."""

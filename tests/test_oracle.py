@@ -133,3 +133,27 @@ def test_augmentation_matches_reference():
         with pytest.raises({"TypeError": TypeError, "ValueError": ValueError}[exc]) as ei:
             R.add_rand_to_data_points([1, 2, 3], size, 10)
         assert str(ei.value) == msg
+
+
+def test_loss_curve_prefix_matches_reference_training_run():
+    """tests/golden/curve200.pt: the unmodified reference trained for 200 AdamW steps through its own get_batch. The
+    oracle (index draw, gather, forward/backward, AdamW restatements chained) reproduces the first 40 losses to fp32
+    round-off; the CUDA engine is held to the whole curve in tests/test_model_gpu.py."""
+    from tradeaid_b200 import synthetic as syn
+    g = load_golden("curve200.pt")
+    c = g["cfg"]
+    cfg = R.Cfg(c["T"], c["C"], c["H"], c["L"], c["V"], c["cross"])
+    sd = R.random_state_dict(cfg, seed=0)
+    for k in list(sd):
+        if ".heads." in k and k.endswith(".2.weight") and "sa_layers" in k:
+            sd[k] = sd[k] / 10
+    data = [syn.token_stream("price", c["N"], 64, 1000), syn.token_stream("indicator", c["N"], 64, 1001)]
+    m1 = {k: torch.zeros_like(v) for k, v in sd.items()}
+    m2 = {k: torch.zeros_like(v) for k, v in sd.items()}
+    torch.manual_seed(c["seed"])
+    for step in range(1, 41):
+        ix = R.batch_starting_indices(c["N"], c["T"], c["B"], "train", [c["N"]], False)
+        xb, yb = R.gather_batch(data, ix, c["T"])
+        _, losses, grads = R.forward_backward(sd, cfg, xb, yb)
+        R.adamw_step(sd, grads, m1, m2, step, c["lr"])
+        assert abs(float(sum(losses)) - g["curve"][step - 1]) <= 2e-4, (step, float(sum(losses)), g["curve"][step - 1])
