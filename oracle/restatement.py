@@ -112,6 +112,7 @@ def forward(sd, cfg: Cfg, idx_list, targets_list=None, dtype=torch.float32, retu
     sd: state dict with the reference's keys. Returns (logits_list, losses_list | None)."""
     M, C, H, hs, h2 = cfg.M, cfg.n_embd, cfg.n_head, cfg.hs, cfg.h2
     xs = []
+    per_layer = []      # return_hidden="layers": the M residual streams after every block (model.py:214-244)
     for i in range(M):  # model.py:300-319
         idx = idx_list[i]
         B, T = idx.shape
@@ -151,11 +152,15 @@ def forward(sd, cfg: Cfg, idx_list, targets_list=None, dtype=torch.float32, retu
                 x = x + (pr * masks[("ca_proj", l, i)] if masks and ("ca_proj", l, i) in masks else pr)
             new.append(x)
         xs = new
+        if return_hidden == "layers":
+            per_layer.append(list(xs))
     logits_list = []
     for i in range(M):  # model.py:339-352
         p = f"post_block.soft_score_layers.{i}"
         h = torch.tanh(_ln(xs[i], sd, f"post_block.fin_norm_layers.{i}") @ sd[f"{p}.0.weight"].to(dtype).T + sd[f"{p}.0.bias"].to(dtype))
         logits_list.append(h @ sd[f"{p}.2.weight"].to(dtype).T + sd[f"{p}.2.bias"].to(dtype))
+    if return_hidden == "layers":
+        return logits_list, per_layer
     if return_hidden:
         return logits_list, xs
     if targets_list is None:

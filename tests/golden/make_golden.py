@@ -191,6 +191,32 @@ def curve200_case():
     print("curve200:", [round(c, 4) for c in curve[::25]], round(curve[-1], 4))
 
 
+def layer_activations_case():
+    """Per-block activations of the reference (forward hooks on m.blocks[l]: the list of M residual streams each
+    MultimodalBlock returns, model.py:214-244) for the weights and inputs of model_m3.pt / model_m3_short.pt — localises a
+    parity failure to a layer."""
+    import model as ref_model
+    out = {}
+    for name in ("m3", "m3_short"):
+        g = torch.load(os.path.join(OUT, f"model_{name}.pt"))
+        c = g["cfg"]
+        set_cfg(c["T"], c["C"], c["H"], c["L"], c["B"])
+        m = ref_model.MultimodalTransformer(c["M"], c["V"], params_list(c["cross"]))
+        missing, unexpected = m.load_state_dict(g["state_dict"], strict=False)
+        assert not unexpected and all(k.endswith(".tril") for k in missing)
+        m.eval()
+        acts = []
+        hooks = [blk.register_forward_hook(lambda mod, inp, res: acts.append([t.detach().clone() for t in res])) for blk in m.blocks]
+        with torch.no_grad():
+            logits, _ = m(g["idx"])
+        for h in hooks:
+            h.remove()
+        assert all((a - b).abs().max() == 0 for a, b in zip(logits, g["logits"]))     # same run as the stored logits
+        out[name] = acts
+    torch.save(out, os.path.join(OUT, "layer_activations.pt"))
+    print("layer activations:", {k: (len(v), len(v[0]), tuple(v[0][0].shape)) for k, v in out.items()})
+
+
 def augmentation_case():
     """data_utils.add_rand_to_data_points (the `[2]` quirk of get_batch, training_utils.py:353-360) on seeded lists:
     outputs after one and after three cumulative applications, and the next outputs of Python's `random` (pins how many
@@ -235,3 +261,4 @@ if __name__ == "__main__":
     metrics_case()
     augmentation_case()
     curve200_case()
+    layer_activations_case()

@@ -164,3 +164,18 @@ def test_grouped_output_heads_equal_per_modality_heads(monkeypatch):
     # vocabularies of different sizes (or odd hidden widths) keep the per-modality launches
     assert Engine(Dims([32, 40], [False, False], T, C, H, 1), "cpu", ops=emu_ops)._heads_grouped is None
     assert Engine(Dims([30, 30], [False, False], T, C, H, 1), "cpu", ops=emu_ops)._heads_grouped is None
+
+
+@pytest.mark.parametrize("name", ["m3", "m3_short"])
+def test_per_layer_streams_match_reference(name):
+    """The engine's residual stream after every block (saved for backward as x3 / x2) against forward hooks on the
+    reference's blocks (tests/golden/layer_activations.pt), fp32 activations."""
+    g, eng = build(name, torch.float32)
+    acts = load_golden("layer_activations.pt")[name]
+    idx, tgt = torch.stack(g["idx"]), torch.stack(g["tgt"])
+    eng.forward(idx, tgt, save=True)
+    B, T = idx.shape[1], idx.shape[2]
+    for l, Sl in enumerate(eng._saved["layers"]):
+        x = Sl["x3"] if eng.d.Xc else Sl["x2"]
+        for i in range(eng.d.M):
+            assert (x[i].view(B, T, -1) - acts[l][i]).abs().max().item() <= 2e-5, (l, i)

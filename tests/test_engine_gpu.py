@@ -253,3 +253,20 @@ def test_grouped_output_heads_are_bit_identical(monkeypatch):
         out[flag] = ([x.clone() for x in logits], losses.clone(), eng.grad.clone())
     assert all(torch.equal(a, b) for a, b in zip(out["1"][0], out["0"][0]))
     assert torch.equal(out["1"][1], out["0"][1]) and torch.equal(out["1"][2], out["0"][2])
+
+
+@pytest.mark.parametrize("name", ["m3", "m3_short"])
+def test_per_layer_streams_match_reference(name):
+    """The CUDA engine's residual stream after every block against forward hooks on the reference's blocks
+    (tests/golden/layer_activations.pt): bf16 GEMM operands, fp32 stream — normwise within the bf16 budget per layer."""
+    g, eng = build(name)
+    acts = load_golden("layer_activations.pt")[name]
+    idx, tgt = torch.stack(g["idx"]).cuda(), torch.stack(g["tgt"]).cuda()
+    eng.forward(idx, tgt, save=True)
+    B, T = idx.shape[1], idx.shape[2]
+    for l, Sl in enumerate(eng._saved["layers"]):
+        x = Sl["x3"] if eng.d.Xc else Sl["x2"]
+        for i in range(eng.d.M):
+            ref = acts[l][i]
+            rel = ((x[i].view(B, T, -1).cpu() - ref).norm() / ref.norm()).item()
+            assert rel <= 1e-2, (l, i, rel)

@@ -157,3 +157,18 @@ def test_loss_curve_prefix_matches_reference_training_run():
         _, losses, grads = R.forward_backward(sd, cfg, xb, yb)
         R.adamw_step(sd, grads, m1, m2, step, c["lr"])
         assert abs(float(sum(losses)) - g["curve"][step - 1]) <= 2e-4, (step, float(sum(losses)), g["curve"][step - 1])
+
+
+@pytest.mark.parametrize("name", ["m3", "m3_short"])
+def test_per_layer_activations_match_reference(name):
+    """tests/golden/layer_activations.pt: forward hooks on the reference's blocks — the restatement must agree after
+    every block, not only at the logits."""
+    g = load_golden(f"model_{name}.pt")
+    acts = load_golden("layer_activations.pt")[name]
+    c = g["cfg"]
+    cfg = R.Cfg(c["T"], c["C"], c["H"], c["L"], c["V"], c["cross"])
+    _, per_layer = R.forward(g["state_dict"], cfg, g["idx"], None, return_hidden="layers")
+    assert len(per_layer) == len(acts) == c["L"]
+    for l in range(c["L"]):
+        for a, b in zip(per_layer[l], acts[l]):
+            assert (a - b).abs().max().item() <= 5e-6, (l, (a - b).abs().max().item())
