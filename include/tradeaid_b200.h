@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 2
+#define TA_ABI_VERSION 3
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -196,6 +196,71 @@ int32_t ta_augment_tokens(int32_t* tokens, int64_t N, const uint32_t* words, int
 int32_t ta_directional_metrics(const float* last_logits, int64_t ld, const double* vocab_values, const int64_t* prev_tokens,
                                int64_t prev_stride, const int64_t* actual_tokens, int64_t actual_stride, int32_t rows,
                                int32_t V, int32_t is_percentage, int64_t* counts, double* certainty, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ K9: data preparation
+ * One-shot preparation of one modality's column on the device. The column is float64 [N] in device
+ * memory (python floats are doubles); every step is bit-exact to the reference's Python arithmetic, including CPython's
+ * round(x, ndigits) (exact decimal rounding, half to even) — see csrc/dataprep_math.cuh.
+ * status: int64 [TA_PREP_STATUS_WORDS] device array, reset with ta_prep_status_reset; word w holds the FIRST row for which
+ * condition w occurred (INT64_MAX = never). The kernels do not fail on bad rows; the host wrapper reads status and raises
+ * what the reference raises. */
+#define TA_PREP_STATUS_WORDS 4
+#define TA_PREP_STATUS_NONFINITE 0   /* NaN / inf element */
+#define TA_PREP_STATUS_ZERO_PREV 1   /* percent change with a zero previous value (row of that previous value) */
+#define TA_PREP_STATUS_OVERFLOW 2    /* ranged value not finite (10**k factor beyond DBL_MAX) */
+#define TA_PREP_STATUS_TABLE_FULL 3  /* vocabulary hash table too small: retry with a larger capacity */
+#define TA_PREP_MAX_RANKS 4
+#define TA_PREP_MAX_GROUPS 8192
+int32_t ta_prep_status_reset(int64_t* status, void* stream);
+
+/* convert_to_percent_changes (data_utils.py:612-662; file_cache.py:329-385 is the same arithmetic):
+ * out[i] = round(((x[i] - x[i-1]) / x[i-1]) * 100, decimals), 0.0 for the first row of every file (file_starts: ascending
+ * int64 [n_files] device array of first rows, file_starts[0] = 0). A zero previous value gives 0.0 and is recorded in
+ * status[ZERO_PREV]: data_utils raises ZeroDivisionError for it (:652), file_cache keeps the 0.0 (:366-372).
+ * Not in place. 0 <= decimals <= 22. */
+int32_t ta_prep_percent_changes(const double* x, double* out, int64_t N, const int64_t* file_starts, int32_t n_files,
+                                int32_t decimals, int64_t* status, void* stream);
+
+/* range_numeric_data (data_utils.py:361-470) with decimal_places given: per element
+ * round(x * 10**(nwd-1 - floor(log10|x|)), decimals), then the magnitude clamps of :440-455 (lower = 10**(nwd-1),
+ * upper = 10**nwd, upper_clamp = what a value >= upper becomes). has_whole_digits = 0: only the rounding (:434).
+ * thresholds / factors: fp64 [633] device tables over the decades -324..308 — thresholds[k] = the smallest double whose
+ * floor(math.log10(.)) is >= k-324 under the host's libm, factors[k] = float(10**(nwd-1-(k-324))) (inf if not
+ * representable); both built by the host wrapper with Python's own expressions. May run in place. */
+int32_t ta_prep_range(const double* x, double* out, int64_t N, int32_t has_whole_digits, int32_t decimals, double lower,
+                      double upper, double upper_clamp, const double* thresholds, const double* factors, int64_t* status,
+                      void* stream);
+
+/* Order statistics for np.percentile (data_utils.py:503-504): out[r] = the ranks[r]-th smallest element (0-based) of x,
+ * n_ranks <= TA_PREP_MAX_RANKS, by an 8-pass radix select (no sort, x is not modified). ranks / out are device arrays. */
+int64_t ta_prep_select_workspace_bytes(void);
+int32_t ta_prep_order_statistics(const double* x, int64_t N, const int64_t* ranks_dev, int32_t n_ranks, double* out,
+                                 void* workspace, int64_t* status, void* stream);
+
+/* Outlier filter of bin_numeric_data (:505-512): out3 = {min, max, count} over the rows with lo <= x <= hi. */
+int64_t ta_prep_minmax_workspace_bytes(int64_t N);
+int32_t ta_prep_filtered_minmax(const double* x, int64_t N, double lo, double hi, double* out3, void* workspace,
+                                void* stream);
+
+/* Group assignment of bin_numeric_data (:527-557): pos_bounds = [0, b_1 .. b_G], neg_bounds = [-b_G .. -b_1, 0] (fp64
+ * [G+1] device arrays built by the host with the reference's expressions); out[i] = the group number as a double
+ * (-G .. G). May run in place. */
+int32_t ta_prep_bin_assign(const double* x, double* out, int64_t N, const double* pos_bounds, const double* neg_bounds,
+                           int32_t num_groups, void* stream);
+
+/* numerical_representation (data_utils.py:212-225): vocabulary = sorted(set(x)), token = index in it.
+ * insert: distinct values of x into an open-addressing table (uint64 [capacity], capacity a power of two; cleared here);
+ *   counters[0] = number of distinct values. The caller retries with a larger table if status[TABLE_FULL] is set or the
+ *   load exceeds 1/2.
+ * build: ranks the n_distinct values by counting (O(V^2) compares, V is a vocabulary size): vocabulary fp64 [n_distinct]
+ *   ascending, token_of_slot int32 [capacity]; keys_ws uint64 [n_distinct], slots_ws int32 [n_distinct].
+ * lookup: tokens[i] = token of x[i] (int32: a row of the token store the feeder gathers from). */
+int32_t ta_prep_vocab_insert(const double* x, int64_t N, uint64_t* table, int64_t capacity, int64_t* counters,
+                             int64_t* status, void* stream);
+int32_t ta_prep_vocab_build(const uint64_t* table, int64_t capacity, int64_t n_distinct, uint64_t* keys_ws, int32_t* slots_ws,
+                            double* vocabulary, int32_t* token_of_slot, int64_t* counters, void* stream);
+int32_t ta_prep_vocab_lookup(const double* x, int64_t N, const uint64_t* table, int64_t capacity, const int32_t* token_of_slot,
+                             int32_t* tokens, void* stream);
 
 /* bias gradients: out[g, c] = sum_r dy[g, r, c] (dy bf16 [G][rows][ld]); deterministic two-stage reduction. */
 int64_t ta_colsum_workspace_floats(int64_t rows, int32_t N, int32_t G);

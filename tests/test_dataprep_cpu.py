@@ -1,0 +1,287 @@
+"""Row f-4 (one-shot data preparation) without a GPU:
+  * the oracle restatement (oracle/dataprep.py) against the fixtures made by the reference's data_utils
+    (tests/golden/dataprep.pt, generator tests/golden/make_golden_dataprep.py) — bit for bit;
+  * the element arithmetic the CUDA kernels run (csrc/dataprep_math.cuh), compiled for the host with g++
+    (tests/host_harness/dataprep_host.cpp), against CPython and the same fixtures — bit for bit;
+  * the host scalars of tradeaid_b200.data_utils (libm decade thresholds, 10**k factors, numpy's percentile
+    interpolation, group boundaries) and the argument validation / error messages of the drop-in functions."""
+import ctypes
+import math
+import os
+import random
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import dataprep as oracle
+
+P = ctypes.c_void_p
+
+
+def bits(values):
+    return np.ascontiguousarray(values, dtype=np.float64).view(np.uint64)
+
+
+def same_bits(a, b):
+    """Equal as doubles bit for bit (the sign of zero included)."""
+    return np.array_equal(bits(a), bits(b))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return load_golden("dataprep.pt")
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    """The device arithmetic built for the host."""
+    out = str(tmp_path_factory.mktemp("dph") / "libdataprep_host.so")
+    src = os.path.join(ROOT, "tests", "host_harness", "dataprep_host.cpp")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src], check=True)
+    return ctypes.CDLL(out)
+
+
+def col(g, case):
+    return g["columns"][case["x"]].tolist()
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs reference
+def test_oracle_percent_changes(golden):
+    for c in golden["percent"]:
+        x = col(golden, c)
+        if "file_lengths" in c:
+            y = oracle.percent_changes_by_file(x, c["file_lengths"], c["decimals"])
+        else:
+            y = oracle.percent_changes(x, c["decimals"], c.get("on_zero", "raise"))
+        assert same_bits(y, c["y"].numpy()), c["name"]
+    e = golden["errors"]["zero_prev"]
+    with pytest.raises(ZeroDivisionError) as info:
+        oracle.percent_changes(col(golden, e), 2)
+    assert str(info.value) == e["message"]
+
+
+def test_oracle_range(golden):
+    for c in golden["range"]:
+        y = oracle.range_values(col(golden, c), c["whole_digits"], c["decimals"])
+        assert same_bits([float(v) for v in y], c["y"].numpy()), (c["name"], c["whole_digits"], c["decimals"])
+
+
+def test_oracle_bins(golden):
+    for c in golden["bin"]:
+        y = oracle.bin_groups(col(golden, c), c["num_groups"], c["outlier"], c["exponent"])
+        assert y == c["y"].tolist(), (c["name"], c["num_groups"], c["outlier"], c["exponent"])
+    e = golden["errors"]["all_filtered"]
+    with pytest.raises(ValueError) as info:
+        oracle.bin_groups(col(golden, e), e["num_groups"], e["outlier"], e["exponent"])
+    assert str(info.value) == e["message"]
+
+
+def test_oracle_vocabulary_and_chain(golden):
+    for c in golden["vocab"]:
+        tok, voc = oracle.vocabulary_tokens(col(golden, c))
+        assert tok == c["tokens"].tolist() and voc == c["vocabulary"].tolist(), c["name"]
+    for c in golden["chain"]:
+        tok, voc = oracle.prepare_modality(col(golden, c), c["params"], c["file_lengths"])
+        assert tok == c["tokens"].tolist(), c["name"]
+        assert [float(v) for v in voc] == c["vocabulary"].tolist(), c["name"]
+        assert all(isinstance(v, int) for v in voc) == c["integer_vocabulary"]
+
+
+# ------------------------------------------------------------------------------------------------ device arithmetic on the host
+def h_round(host, xs, nd):
+    x = np.ascontiguousarray(xs, dtype=np.float64)
+    o = np.empty_like(x)
+    host.h_py_round(P(x.ctypes.data), ctypes.c_longlong(x.size), ctypes.c_int(nd), P(o.ctypes.data))
+    return o
+
+
+def test_device_round_is_cpython_round(host):
+    rng = random.Random(7)
+    for nd in range(0, 23):
+        xs = [0.0, -0.0, 0.5, 1.5, 2.5, -0.5, 0.125, 0.375, 2.675, 1.005, 1e15 + 0.5, 4503599627370495.5, 5e-324, 1e22, 0.1,
+              -2.5e-3, 2 ** 52 + 0.0, 2 ** 53 + 2.0, 1e300, -1e-300]
+        for _ in range(3000):
+            c = rng.random()
+            if c < 0.3:
+                xs.append(rng.uniform(-1000, 1000))
+            elif c < 0.5:
+                xs.append(rng.randint(-10 ** 7, 10 ** 7) / 2 ** rng.randint(0, 30))          # exact ties
+            elif c < 0.6:
+                xs.append((rng.randint(-10 ** 6, 10 ** 6) + 0.5) / 10 ** rng.randint(0, 8))
+            elif c < 0.75:
+                xs.append(rng.uniform(-1, 1) * 10 ** rng.randint(-30, 15))
+            elif c < 0.85:
+                v = struct.unpack("d", struct.pack("Q", rng.getrandbits(64)))[0]
+                if v == v and abs(v) != math.inf:
+                    xs.append(v)
+            else:
+                xs.append(round(rng.uniform(-100, 100), rng.randint(0, 6)))
+        want = []
+        keep = []
+        for v in xs:
+            try:
+                want.append(round(v, nd))
+                keep.append(v)
+            except OverflowError:      # CPython refuses results beyond DBL_MAX; the data path never gets there
+                pass
+        assert same_bits(h_round(host, keep, nd), want), nd
+
+
+def thresholds_and_factors(nwd):
+    from tradeaid_b200 import data_utils as du
+    return (np.array(du._log10_thresholds(), dtype=np.float64),
+            np.array(du._decade_factors(nwd if nwd is not None else 1), dtype=np.float64))
+
+
+def test_decade_thresholds_follow_libm(host):
+    from tradeaid_b200 import data_utils as du
+    thr = du._log10_thresholds()
+    assert len(thr) == 633 and all(a < b for a, b in zip(thr, thr[1:]))
+    rng = random.Random(3)
+    xs = []
+    for k, t in enumerate(thr):
+        p = k - 324
+        assert math.floor(math.log10(t)) >= p
+        if t > 5e-324:
+            assert math.floor(math.log10(math.nextafter(t, -math.inf))) < p
+        v = t
+        for _ in range(24):             # a neighbourhood of every decade boundary, both sides
+            xs.append(v)
+            v = math.nextafter(v, math.inf)
+        v = t
+        for _ in range(24):
+            v = math.nextafter(v, -math.inf)
+            if v > 0:
+                xs.append(v)
+    xs += [rng.uniform(0, 1) * 10 ** rng.randint(-300, 300) for _ in range(20000)]
+    xs = [v for v in xs if v > 0]
+    x = np.array(xs, dtype=np.float64)
+    t = np.array(thr, dtype=np.float64)
+    out = np.empty(len(xs), dtype=np.int32)
+    host.h_floor_log10(P(x.ctypes.data), ctypes.c_longlong(x.size), P(t.ctypes.data), P(out.ctypes.data))
+    assert out.tolist() == [int(math.floor(math.log10(v))) for v in xs]
+
+
+def test_device_range_against_reference(host, golden):
+    from tradeaid_b200 import data_utils as du
+    for c in golden["range"]:
+        nwd, dp = c["whole_digits"], c["decimals"]
+        x = np.ascontiguousarray(golden["columns"][c["x"]].numpy())
+        thr, fac = thresholds_and_factors(nwd)
+        lower = upper = clamp = 0.0
+        if nwd is not None:
+            lower, upper = float(10 ** (nwd - 1)), float(10 ** nwd)
+            clamp = float(10 ** nwd - (10 ** (-dp))) if dp > 0 else float(10 ** nwd - 1)
+        out = np.empty_like(x)
+        host.h_range(P(x.ctypes.data), ctypes.c_longlong(x.size), ctypes.c_int(nwd is not None), ctypes.c_int(dp),
+                     ctypes.c_double(lower), ctypes.c_double(upper), ctypes.c_double(clamp), P(thr.ctypes.data),
+                     P(fac.ctypes.data), P(out.ctypes.data))
+        want = c["y"].numpy()
+        assert same_bits(out, want), (c["name"], nwd, dp)
+    assert du._decade_factors(1)[324] == 1.0 and du._decade_factors(3)[324 + 5] == 10.0 ** -3
+
+
+def test_device_percent_and_bins_against_reference(host, golden):
+    for c in golden["percent"]:
+        if "file_lengths" in c:
+            continue
+        x = np.ascontiguousarray(golden["columns"][c["x"]].numpy())
+        if c.get("on_zero") != "keep" and (x[:-1] == 0).any():
+            continue
+        out = np.empty_like(x)
+        host.h_percent(P(x.ctypes.data), ctypes.c_longlong(x.size), ctypes.c_int(2 if c["decimals"] is None else c["decimals"]),
+                       P(out.ctypes.data))
+        assert same_bits(out, c["y"].numpy()), (c["name"], c["decimals"])
+    for c in golden["bin"]:
+        x = np.ascontiguousarray(golden["columns"][c["x"]].numpy())
+        lo, hi = np.percentile(x, c["outlier"]), np.percentile(x, 100 - c["outlier"])
+        kept = x[(x >= lo) & (x <= hi)]
+        pos, neg = oracle.group_boundaries(c["num_groups"], c["exponent"], max(abs(kept.min()), abs(kept.max())))
+        pos, neg = np.array(pos), np.array(neg)
+        out = np.empty(x.size, dtype=np.int32)
+        host.h_bin(P(x.ctypes.data), ctypes.c_longlong(x.size), P(pos.ctypes.data), P(neg.ctypes.data),
+                   ctypes.c_int(c["num_groups"]), P(out.ctypes.data))
+        assert out.tolist() == c["y"].tolist(), (c["name"], c["num_groups"])
+
+
+def test_order_key_is_monotone_and_invertible(host):
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.standard_normal(5000) * 10.0 ** rng.integers(-20, 20, 5000), [0.0, -0.0, 5e-324, -5e-324, 1e308, -1e308]])
+    keys = np.empty(x.size, dtype=np.uint64)
+    back = np.empty_like(x)
+    host.h_order_key(P(x.ctypes.data), ctypes.c_longlong(x.size), P(keys.ctypes.data), P(back.ctypes.data))
+    assert same_bits(back, x)
+    order = np.argsort(keys, kind="stable")
+    assert np.all(np.diff(x[order]) >= 0)
+
+
+# ------------------------------------------------------------------------------------------------ host scalars
+def test_percentile_plan_is_numpys():
+    from tradeaid_b200 import data_utils as du
+    rng = np.random.default_rng(11)
+    for n in [1, 2, 3, 4, 5, 10, 11, 97, 1000, 1501]:
+        a = np.sort(rng.standard_normal(n) * 100)
+        shuffled = rng.permutation(a)
+        for q in [0, 0.1, 1, 5, 12.5, 25, 45, 50, 55, 75, 87.5, 95, 99, 99.9, 100, 100 - 0.1, 100 - 12.5]:
+            prev, nxt, gamma = du._percentile_plan(n, q)
+            got = du._lerp(float(a[prev]), float(a[nxt]), gamma)
+            want = float(np.percentile(list(shuffled), q))
+            assert struct.pack("d", got) == struct.pack("d", want), (n, q)
+
+
+def test_group_boundaries_match_oracle():
+    from tradeaid_b200 import data_utils as du
+    for G, ex, m in [(5, 2.0, 3.7), (10, 2.2, 0.123), (64, 1, 1e6), (3, 3.0, 0.0)]:
+        assert du._group_boundaries(G, ex, m) == oracle.group_boundaries(G, ex, m)
+
+
+def test_validation_matches_reference_messages():
+    """Argument checks run before anything touches the device: same exception types and texts as data_utils.py."""
+    from tradeaid_b200 import data_utils as du
+    with pytest.raises(ValueError, match="'data' must be a non-empty list."):
+        du.convert_to_percent_changes([], 2)
+    with pytest.raises(ValueError, match="Element at index 1 is str: 'a'"):
+        du.convert_to_percent_changes([1.0, "a"], 2)
+    with pytest.raises(ValueError, match="'decimal_places' must be a non-negative integer or null."):
+        du.convert_to_percent_changes([1.0, 2.0], -1)
+    with pytest.raises(TypeError, match="'numeric_data' must be a list."):
+        du.range_numeric_data((1.0, 2.0), 1, 2)
+    with pytest.raises(TypeError, match="'numeric_data' must be a non-empty list."):
+        du.range_numeric_data([], 1, 2)
+    with pytest.raises(IndexError, match="Element at index 0 in 'numeric_data' is not a number."):
+        du.range_numeric_data(["x"], 1, 2)
+    with pytest.raises(TypeError, match="'num_whole_digits' must be an integer or None."):
+        du.range_numeric_data([1.0], 1.5, 2)
+    with pytest.raises(ValueError, match="'decimal_places' must be greater than or equal to 0."):
+        du.range_numeric_data([1.0], 1, -2)
+    with pytest.raises(NotImplementedError):
+        du.range_numeric_data([1.0], 1, None)
+    with pytest.raises(ValueError, match="'num_groups' must be a positive integer."):
+        du.bin_numeric_data([1.0], 0)
+    with pytest.raises(ValueError, match="'outlier_percentile' must be a number between 0 and 50."):
+        du.bin_numeric_data([1.0], 3, 60)
+    with pytest.raises(ValueError, match="'exponent' must be a number >= 1."):
+        du.bin_numeric_data([1.0], 3, 5, 0.5)
+    with pytest.raises(TypeError, match="'file_lengths' must be a list of positive integers."):
+        du.create_train_val_datasets(torch.zeros(4, dtype=torch.int32), 0.1, 0, [4, 0])
+    with pytest.raises(ValueError, match="'val_size' must be a float between 0 and 1"):
+        du.create_train_val_datasets(torch.zeros(4, dtype=torch.int32), 1.5, 0, [4])
+    tr, va = du.create_train_val_datasets(torch.arange(10, dtype=torch.int32), 0.1, 0, [4, 6])
+    assert tr.tolist() == list(range(9)) and va.tolist() == [9]          # int(10 * (1 - 0.1)) = 9 (data_utils.py:276)
+    tr, va = du.create_train_val_datasets(torch.arange(10, dtype=torch.int32), 0.1, 1, [4, 6])
+    assert tr.numel() == 4 and va.numel() == 6
+
+
+def test_no_cpu_path():
+    """The drop-in functions never compute on the host: without a CUDA device they raise."""
+    from tradeaid_b200 import data_utils as du
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    for call in (lambda: du.convert_to_percent_changes([1.0, 2.0], 2), lambda: du.range_numeric_data([1.0, 2.0], 1, 2),
+                 lambda: du.bin_numeric_data([1.0, 2.0], 3), lambda: du.numerical_representation([1.0, 2.0])):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            call()

@@ -1,0 +1,436 @@
+"""One-shot data preparation on the device: the reference's `data_utils` processing functions
+with the same names, arguments, validation and error behaviour, computed by the K9 kernels (csrc/dataprep.cu) on a
+float64 column resident in HBM.
+
+    convert_to_percent_changes   /root/reference/data_utils.py:612-662  (file_cache.py:329-385 with on_zero="keep")
+    range_numeric_data           /root/reference/data_utils.py:361-470
+    bin_numeric_data             /root/reference/data_utils.py:473-609
+    numerical_representation     /root/reference/data_utils.py:212-225
+    create_train_val_datasets    /root/reference/data_utils.py:228-290   (slicing only: host)
+
+Every function takes what the reference takes — a Python list — and then returns what the reference returns (lists), or
+a float64 CUDA tensor [N], and then returns device tensors: that is the form `prepare_modality` chains, so that a column
+goes from raw values to a row of the feeder's token store without a per-element Python loop or a host copy.
+Results are BIT-exact to the reference's Python floats (tests/test_dataprep_*.py): equal values share a vocabulary entry
+and the entry's index is the token id, so "close" is not good enough. What the host contributes is scalar work done with
+Python's own expressions — decade tables from this machine's `math.log10` and `10**k`, `np.percentile`'s interpolation of
+four order statistics, the group boundaries — everything proportional to N runs in the kernels.
+There is no CPU fallback: without a CUDA device or the library these functions raise.
+
+Not covered (raises NotImplementedError, use the reference's function): `range_numeric_data` with
+`decimal_places=None`, which sizes the rounding of every element by the length of its `str()` (data_utils.py:431);
+non-numeric (string) modalities in `numerical_representation`.
+"""
+from __future__ import annotations
+
+import math
+import numbers
+
+import numpy as np
+import torch
+
+# ---------------------------------------------------------------------------------------------------- host scalars
+_DECADE_MIN, _DECADE_MAX = -324, 308
+_thresholds_cache = None
+
+
+def _prev_double(x):
+    return math.nextafter(x, -math.inf)
+
+
+def _log10_thresholds():
+    """thresholds[k] = the smallest positive double t with floor(math.log10(t)) >= k + _DECADE_MIN, found with THIS
+    machine's libm — the reference calls math.log10 (data_utils.py:429) and glibc rounds arguments a few ulps below a
+    power of ten up to the integer, so the decade boundary is not the power of ten itself."""
+    global _thresholds_cache
+    if _thresholds_cache is None:
+        out = []
+        for p in range(_DECADE_MIN, _DECADE_MAX + 1):
+            t = float(f"1e{p}") if p > -324 else 5e-324
+            while t > 5e-324 and math.floor(math.log10(_prev_double(t))) >= p:
+                t = _prev_double(t)
+            while math.floor(math.log10(t)) < p:
+                t = math.nextafter(t, math.inf)
+            out.append(t)
+        _thresholds_cache = out
+    return _thresholds_cache
+
+
+def _decade_factors(num_whole_digits):
+    """factors[k] = what `element * 10**(desired_power - power)` multiplies a FLOAT element with (data_utils.py:436-440):
+    an int power converted to double for exponents >= 0, Python's float power below; inf where not representable."""
+    out = []
+    for p in range(_DECADE_MIN, _DECADE_MAX + 1):
+        try:
+            out.append(float(10 ** ((num_whole_digits - 1) - p)))
+        except OverflowError:
+            out.append(math.inf)
+    return out
+
+
+def _percentile_plan(n, q):
+    """np.percentile(a, q) for 1-d `a` of length n, method 'linear' (numpy/lib/_function_base_impl.py `_quantile`):
+    returns (previous_index, next_index, gamma) in terms of the ascending order statistics."""
+    quantile = np.true_divide(q, np.float64(100))
+    virtual = (n - 1) * quantile
+    prev = int(np.floor(virtual))
+    nxt = prev + 1
+    gamma = virtual - np.floor(virtual)
+    if virtual >= n - 1:                    # at or above the last index: numpy takes the maximum for both neighbours
+        gamma = virtual - (-1)
+        prev = nxt = n - 1
+    if virtual < 0:
+        prev = nxt = 0
+    return prev, nxt, float(gamma)
+
+
+def _lerp(a, b, t):
+    """numpy's `_lerp`: a + (b - a) * t, evaluated from the other end for t >= 0.5."""
+    diff = b - a
+    return b - diff * (1 - t) if t >= 0.5 else a + diff * t
+
+
+def _group_boundaries(num_groups, exponent, max_abs_value):
+    """data_utils.py:514-524, verbatim arithmetic."""
+    pos = [0.0]
+    for i in range(1, num_groups + 1):
+        normalized_i = i / num_groups
+        scaled_position = normalized_i ** exponent
+        pos.append(scaled_position * max_abs_value)
+    neg = [-b for b in reversed(pos[1:])] + [0.0]
+    return pos, neg
+
+
+# ---------------------------------------------------------------------------------------------------- device plumbing
+def _ops():
+    from . import lib
+    return lib
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("tradeaid_b200.data_utils runs on a CUDA device (sm_100a); there is no CPU path — "
+                           "use the reference's data_utils on a machine without one.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _first_non_number(data):
+    for i, item in enumerate(data):
+        if not isinstance(item, numbers.Number):
+            return i
+    return -1
+
+
+def _upload(data):
+    """Python list of numbers -> float64 device column (floats are doubles; ints are exact up to 2^53)."""
+    arr = np.asarray(data, dtype=np.float64)
+    if arr.ndim != 1:
+        raise ValueError("data must be one-dimensional")
+    return torch.from_numpy(arr).to(_device())
+
+
+class _Status:
+    """The device status words of a step (first offending row per condition), read back once."""
+
+    def __init__(self, ops, device):
+        self.ops = ops
+        self.words = torch.empty(ops.PREP_STATUS_WORDS, dtype=torch.int64, device=device)
+        ops.prep_status_reset(self.words)
+
+    def read(self):
+        return [None if w == self.ops.PREP_NO_ROW else w for w in self.words.tolist()]
+
+    def raise_nonfinite(self, row, x):
+        if row is not None:
+            raise ValueError(f"cannot process non-finite value {float(x[row])!r} at index {row}")
+
+
+def _is_column(x):
+    return torch.is_tensor(x)
+
+
+def _check_column(x, name):
+    if x.dtype != torch.float64 or x.dim() != 1 or not x.is_cuda:
+        raise TypeError(f"'{name}' as a tensor must be a float64 CUDA tensor of shape [N]")
+    if x.numel() == 0:
+        raise ValueError(f"'{name}' must be non-empty.")
+    return x.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------- percent changes
+def convert_to_percent_changes(data, decimal_places=2, file_lengths=None, on_zero="raise"):
+    """data_utils.convert_to_percent_changes (data_utils.py:612-662). `file_lengths` (extension, default one file): the
+    reference converts file by file (data_utils.py:148, file_cache.py:312-320), so the first row of every file is 0.0.
+    on_zero="raise": ZeroDivisionError with the reference's message (data_utils.py:652); "keep": file_cache's variant,
+    0.0 for that row (file_cache.py:366-372)."""
+    as_list = not _is_column(data)
+    if as_list:
+        if not isinstance(data, list) or not data:
+            raise ValueError("'data' must be a non-empty list.")
+        i = _first_non_number(data)
+        if i >= 0:
+            raise ValueError(f"All elements in 'data' must be numeric. Element at index {i} is "
+                             f"{type(data[i]).__name__}: '{data[i]}'.")
+    if decimal_places is not None:
+        if not isinstance(decimal_places, int) or decimal_places < 0:
+            raise ValueError("'decimal_places' must be a non-negative integer or null.")
+    else:
+        decimal_places = 2
+    if on_zero not in ("raise", "keep"):
+        raise ValueError("on_zero must be 'raise' or 'keep'")
+    ops = _ops()
+    if decimal_places > ops.PREP_MAX_DECIMALS:
+        raise NotImplementedError(f"decimal_places > {ops.PREP_MAX_DECIMALS} is not supported on the device")
+    x = _upload(data) if as_list else _check_column(data, "data")
+    n = x.numel()
+    lengths = [n] if file_lengths is None else [int(v) for v in file_lengths]
+    if sum(lengths) != n or any(v <= 0 for v in lengths):
+        raise ValueError(f"Sum of file_lengths ({sum(lengths)}) does not match length of data ({n}).")
+    starts = torch.tensor(np.concatenate(([0], np.cumsum(lengths[:-1]))).astype(np.int64), device=x.device)
+    st = _Status(ops, x.device)
+    out = torch.empty_like(x)
+    ops.prep_percent_changes(x, out, starts, decimal_places, st.words)
+    nonfinite, zero_prev, _, _ = st.read()
+    st.raise_nonfinite(nonfinite, x)
+    if zero_prev is not None and on_zero == "raise":
+        raise ZeroDivisionError(f"Cannot calculate percentage change: previous value is zero at index {zero_prev}.")
+    return out.tolist() if as_list else out
+
+
+# ---------------------------------------------------------------------------------------------------- ranging
+def range_numeric_data(numeric_data, num_whole_digits, decimal_places, out=None):
+    """data_utils.range_numeric_data (data_utils.py:361-470). Tensor input: `out` may be the input itself (in place)."""
+    as_list = not _is_column(numeric_data)
+    if as_list:
+        if not isinstance(numeric_data, list):
+            raise TypeError("'numeric_data' must be a list.")
+        if not numeric_data:
+            raise TypeError("'numeric_data' must be a non-empty list.")
+        i = _first_non_number(numeric_data)
+        if i >= 0:
+            raise IndexError(f"Element at index {i} in 'numeric_data' is not a number.")
+    if num_whole_digits is not None and not isinstance(num_whole_digits, int):
+        raise TypeError("'num_whole_digits' must be an integer or None.")
+    if decimal_places is not None and not isinstance(decimal_places, int):
+        raise TypeError("'decimal_places' must be an integer or None.")
+    if decimal_places is not None and decimal_places < 0:
+        raise ValueError("'decimal_places' must be greater than or equal to 0.")
+    if decimal_places is None:
+        raise NotImplementedError("range_numeric_data with decimal_places=None rounds every element to the length of its "
+                                  "str() (data_utils.py:431); that form is not built on the device")
+    ops = _ops()
+    if decimal_places > ops.PREP_MAX_DECIMALS:
+        raise NotImplementedError(f"decimal_places > {ops.PREP_MAX_DECIMALS} is not supported on the device")
+    x = _upload(numeric_data) if as_list else _check_column(numeric_data, "numeric_data")
+    lower = upper = upper_clamp = 0.0
+    thresholds = factors = None
+    if num_whole_digits is not None:
+        try:
+            lower = float(10 ** (num_whole_digits - 1))
+            upper = float(10 ** num_whole_digits)
+            if decimal_places > 0:
+                upper_clamp = float(10 ** num_whole_digits - (10 ** (-decimal_places)))
+            else:
+                upper_clamp = float(10 ** num_whole_digits - 1)
+        except OverflowError as e:
+            raise NotImplementedError(f"num_whole_digits={num_whole_digits} is outside the double range") from e
+        thresholds = torch.tensor(_log10_thresholds(), dtype=torch.float64, device=x.device)
+        factors = torch.tensor(_decade_factors(num_whole_digits), dtype=torch.float64, device=x.device)
+    st = _Status(ops, x.device)
+    res = torch.empty_like(x) if out is None else out
+    ops.prep_range(x, res, num_whole_digits is not None, decimal_places, lower, upper, upper_clamp, thresholds, factors,
+                   st.words)
+    nonfinite, _, overflow, _ = st.read()
+    st.raise_nonfinite(nonfinite, x)
+    if overflow is not None:
+        raise OverflowError(f"int too large to convert to float (scaling factor of element {overflow})")
+    return res.tolist() if as_list else res
+
+
+# ---------------------------------------------------------------------------------------------------- binning
+def _order_statistics(ops, x, ranks, st):
+    r = torch.tensor(ranks, dtype=torch.int64, device=x.device)
+    out = torch.empty(len(ranks), dtype=torch.float64, device=x.device)
+    ws = torch.empty(ops.prep_select_workspace_bytes(), dtype=torch.uint8, device=x.device)
+    ops.prep_order_statistics(x, r, out, ws, st.words)
+    return out.tolist()
+
+
+def percentiles(x, qs):
+    """np.percentile(x, q) for each q (linear interpolation) of a float64 device column: the neighbouring order
+    statistics come from one radix-select pass set, the interpolation is numpy's."""
+    ops = _ops()
+    x = _check_column(x, "x")
+    st = _Status(ops, x.device)
+    n = x.numel()
+    plans = [_percentile_plan(n, q) for q in qs]
+    out = []
+    for k in range(0, len(plans), 2):                      # two percentiles (four ranks) per select
+        chunk = plans[k:k + 2]
+        ranks = [i for p in chunk for i in (p[0], p[1])]
+        vals = _order_statistics(ops, x, ranks, st)
+        for j, p in enumerate(chunk):
+            out.append(_lerp(vals[2 * j], vals[2 * j + 1], p[2]))
+    nonfinite = st.read()[0]
+    st.raise_nonfinite(nonfinite, x)
+    return out
+
+
+def bin_numeric_data(data, num_groups, outlier_percentile=5, exponent=2.0, out=None, verbose=True, as_float=False):
+    """data_utils.bin_numeric_data (data_utils.py:473-609): groups -num_groups..num_groups with power-law boundaries
+    up to the largest magnitude inside the [p, 100-p] percentile band. List input returns a list of ints like the
+    reference; tensor input returns int64 groups on the device (float64 with as_float=True: the form
+    numerical_representation takes). Prints the reference's breakdown unless verbose=False."""
+    as_list = not _is_column(data)
+    if as_list:
+        if not isinstance(data, list) or not data:
+            raise ValueError("'data' must be a non-empty list.")
+        i = _first_non_number(data)
+        if i >= 0:
+            raise ValueError(f"All elements in 'data' must be numeric. Element at index {i} is "
+                             f"{type(data[i]).__name__}: '{data[i]}'.")
+    if not isinstance(num_groups, int) or num_groups <= 0:
+        raise ValueError("'num_groups' must be a positive integer.")
+    if not isinstance(outlier_percentile, (int, float)) or not (0 <= outlier_percentile <= 50):
+        raise ValueError("'outlier_percentile' must be a number between 0 and 50.")
+    if not isinstance(exponent, (int, float)) or exponent < 1:
+        raise ValueError("'exponent' must be a number >= 1.")
+    ops = _ops()
+    if num_groups > ops.PREP_MAX_GROUPS:
+        raise NotImplementedError(f"num_groups > {ops.PREP_MAX_GROUPS} is not supported on the device")
+    x = _upload(data) if as_list else _check_column(data, "data")
+    lower_percentile, upper_percentile = percentiles(x, [outlier_percentile, 100 - outlier_percentile])
+    mm = torch.empty(3, dtype=torch.float64, device=x.device)
+    ws = torch.empty(ops.prep_minmax_workspace_bytes(x.numel()), dtype=torch.uint8, device=x.device)
+    ops.prep_filtered_minmax(x, lower_percentile, upper_percentile, mm, ws)
+    fmin, fmax, count = mm.tolist()
+    if count == 0:
+        raise ValueError("All data points were filtered out as outliers.")
+    max_abs_value = max(abs(fmin), abs(fmax))
+    pos, neg = _group_boundaries(num_groups, exponent, max_abs_value)
+    res = torch.empty_like(x) if out is None else out
+    ops.prep_bin_assign(x, res, torch.tensor(pos, dtype=torch.float64, device=x.device),
+                        torch.tensor(neg, dtype=torch.float64, device=x.device))
+    if verbose:
+        counts = torch.bincount((res + num_groups).to(torch.int64), minlength=2 * num_groups + 1).tolist()
+        _print_bin_breakdown(counts, num_groups, pos, neg, x.numel())
+    if as_list:
+        return [int(v) for v in res.tolist()]
+    return res if as_float else res.to(torch.int64)
+
+
+def _print_bin_breakdown(counts, num_groups, pos, neg, n):
+    """The report of data_utils.py:566-607 (same text), from the per-group counts."""
+    print("    -> Binning breakdown (only populated bins showing):")
+    for i in range(-num_groups, 0):
+        c = counts[i + num_groups]
+        if c:
+            j = num_groups + i
+            if i == -num_groups:
+                print(f"      Bin {i}: (-inf, {neg[j + 1]:.3f}) - {c} elements")
+            else:
+                print(f"      Bin {i}: [{neg[j]:.3f}, {neg[j + 1]:.3f}) - {c} elements")
+    if counts[num_groups]:
+        print(f"      Bin  0: [0.000, 0.000] - {counts[num_groups]} elements")
+    for i in range(1, num_groups + 1):
+        c = counts[i + num_groups]
+        if c:
+            if i == num_groups:
+                print(f"      Bin {i:2d}: [{pos[i - 1]:.3f}, +inf) - {c} elements")
+            else:
+                print(f"      Bin {i:2d}: [{pos[i - 1]:.3f}, {pos[i]:.3f}) - {c} elements")
+    print(f"      All {n} elements successfully assigned to bins")
+
+
+# ---------------------------------------------------------------------------------------------------- vocabulary
+def numerical_representation(data_points, tokens_out=None, integer_vocabulary=False):
+    """data_utils.numerical_representation (data_utils.py:212-225): vocabulary = sorted(set(data)), token = index.
+    List input: (list of int tokens, vocabulary list). Tensor input: (int32 device tokens — written into `tokens_out`, e.g.
+    a row of the feeder's TokenStore — and the vocabulary as a Python list: it is what training_utils' metrics index).
+    integer_vocabulary: the column holds group numbers (output of bin_numeric_data): vocabulary entries are ints."""
+    as_list = not _is_column(data_points)
+    if as_list:
+        if not isinstance(data_points, list):
+            raise TypeError("'data_points' must be a list.")
+        if not data_points:
+            return [], []
+        if _first_non_number(data_points) >= 0:
+            raise NotImplementedError("non-numeric modalities are not tokenised on the device")
+        integer_vocabulary = integer_vocabulary or all(isinstance(v, int) for v in data_points)
+    ops = _ops()
+    x = _upload(data_points) if as_list else _check_column(data_points, "data_points")
+    n = x.numel()
+    dev = x.device
+    st = _Status(ops, dev)
+    counters = torch.empty(2, dtype=torch.int64, device=dev)
+    capacity = 1 << 17
+    limit = 1 << max(18, (2 * n - 1).bit_length())
+    while True:
+        table = torch.empty(capacity, dtype=torch.int64, device=dev)
+        ops.prep_vocab_insert(x, table, counters, st.words)
+        nonfinite, _, _, full = st.read()
+        st.raise_nonfinite(nonfinite, x)
+        distinct = int(counters[0])
+        if full is None and 2 * distinct <= capacity:
+            break
+        if capacity >= limit:
+            raise RuntimeError("vocabulary hash table did not converge")   # cannot happen: limit holds 2N slots
+        capacity = min(limit, capacity * 16)
+        ops.prep_status_reset(st.words)
+    keys = torch.empty(distinct, dtype=torch.int64, device=dev)
+    slots = torch.empty(distinct, dtype=torch.int32, device=dev)
+    vocabulary = torch.empty(distinct, dtype=torch.float64, device=dev)
+    token_of_slot = torch.empty(capacity, dtype=torch.int32, device=dev)
+    ops.prep_vocab_build(table, distinct, keys, slots, vocabulary, token_of_slot, counters)
+    tokens = torch.empty(n, dtype=torch.int32, device=dev) if tokens_out is None else tokens_out
+    ops.prep_vocab_lookup(x, table, token_of_slot, tokens)
+    vocab = vocabulary.tolist()
+    if integer_vocabulary:
+        vocab = [int(v) for v in vocab]
+    return (tokens.tolist(), vocab) if as_list else (tokens, vocab)
+
+
+def create_train_val_datasets(numeric_rep_data, val_size, num_val_files, file_lengths):
+    """data_utils.create_train_val_datasets (data_utils.py:228-290) for a device token row: returns two VIEWS of it
+    (train, val) — same split arithmetic, same errors; no list is built."""
+    if not torch.is_tensor(numeric_rep_data):
+        raise TypeError("'numeric_rep_data' must be a device token tensor here (the reference's list form is unchanged).")
+    if not isinstance(num_val_files, int) or num_val_files < 0:
+        raise TypeError("'num_val_files' must be a non-negative integer.")
+    if not isinstance(file_lengths, list) or not all(isinstance(v, int) and v > 0 for v in file_lengths):
+        raise TypeError("'file_lengths' must be a list of positive integers.")
+    n = int(numeric_rep_data.numel())
+    if sum(file_lengths) != n:
+        raise ValueError(f"Sum of file_lengths ({sum(file_lengths)}) does not match length of numeric_rep_data ({n}).")
+    if num_val_files > 0:
+        if num_val_files > len(file_lengths):
+            raise ValueError(f"'num_val_files' ({num_val_files}) cannot exceed the number of loaded files "
+                             f"({len(file_lengths)}).")
+        train_num_elements = n - sum(file_lengths[-num_val_files:])
+    else:
+        if not isinstance(val_size, (int, float)) or not (0 < val_size < 1):
+            raise ValueError("'val_size' must be a float between 0 and 1 (exclusive).")
+        train_num_elements = int(n * (1 - val_size))
+    return numeric_rep_data[:train_num_elements], numeric_rep_data[train_num_elements:]
+
+
+# ---------------------------------------------------------------------------------------------------- the chain
+def prepare_modality(column, modality_params, file_lengths=None, tokens_out=None, verbose=False):
+    """Raw column -> tokens, the steps main.py applies to one modality (main.py:100-210, 278) in the reference's order:
+    percent changes (params[3]; per file, data_utils.py:148), ranging (params[4], params[5]), binning (params[6];
+    outlier percentile params[10] default 0.1, exponent params[11] default 2.2, main.py:170-175), vocabulary.
+    column: list of numbers or float64 CUDA tensor [N]. modality_params: the reference's legacy list (schema.py:213-248).
+    Returns (int32 device tokens [N], vocabulary list). Intermediate columns stay in HBM."""
+    x = _upload(column) if not _is_column(column) else _check_column(column, "column")
+    p = list(modality_params) + [None] * (12 - len(modality_params))
+    is_percent, whole_digits, dec_places, num_bins = p[3], p[4], p[5], p[6]
+    if is_percent is True:
+        x = convert_to_percent_changes(x, dec_places if dec_places else 2, file_lengths=file_lengths)
+    if whole_digits is not None or dec_places is not None:
+        x = range_numeric_data(x, whole_digits, dec_places)
+    binned = num_bins is not None
+    if binned:
+        outlier = p[10] if p[10] is not None else 0.1
+        exponent = p[11] if p[11] is not None else 2.2
+        x = bin_numeric_data(x, num_bins, outlier, exponent, verbose=verbose, as_float=True)
+    return numerical_representation(x, tokens_out=tokens_out, integer_vocabulary=binned)

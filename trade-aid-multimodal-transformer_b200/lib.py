@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class TaOperand(C.Structure):
@@ -459,3 +459,109 @@ def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_str
         _check(_lib.ta_attention_bwd(qa, ka, va, n_src, _ptr(o), _ptr(o_src), o_src.stride(0) if o_src is not None else 0,
                                      _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), dqa, dka, dva, G, B, T, H, hs, float(dropout_p),
                                      int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
+
+
+# ---------------------------------------------------------------------------------------------------- K9: data preparation
+PREP_STATUS_WORDS = 4
+PREP_NONFINITE, PREP_ZERO_PREV, PREP_OVERFLOW, PREP_TABLE_FULL = 0, 1, 2, 3
+PREP_NO_ROW = 2 ** 63 - 1
+PREP_MAX_RANKS = 4
+PREP_MAX_GROUPS = 8192
+PREP_DECADES = 633            # decades -324 .. 308 of the threshold / factor tables
+PREP_DECADE_MIN = -324
+PREP_MAX_DECIMALS = 22
+
+_prep_reset = _sig("ta_prep_status_reset", _P, _P)
+_prep_pct = _sig("ta_prep_percent_changes", _P, _P, _I64, _P, _I32, _I32, _P, _P)
+_prep_range = _sig("ta_prep_range", _P, _P, _I64, _I32, _I32, _F64, _F64, _F64, _P, _P, _P, _P)
+_prep_sel_ws = _sig("ta_prep_select_workspace_bytes", restype=_I64)
+_prep_sel = _sig("ta_prep_order_statistics", _P, _I64, _P, _I32, _P, _P, _P, _P)
+_prep_mm_ws = _sig("ta_prep_minmax_workspace_bytes", _I64, restype=_I64)
+_prep_mm = _sig("ta_prep_filtered_minmax", _P, _I64, _F64, _F64, _P, _P, _P)
+_prep_bin = _sig("ta_prep_bin_assign", _P, _P, _I64, _P, _P, _I32, _P)
+_prep_vins = _sig("ta_prep_vocab_insert", _P, _I64, _P, _I64, _P, _P, _P)
+_prep_vbuild = _sig("ta_prep_vocab_build", _P, _I64, _I64, _P, _P, _P, _P, _P, _P)
+_prep_vlook = _sig("ta_prep_vocab_lookup", _P, _I64, _P, _I64, _P, _P, _P)
+
+
+def _f64(t):
+    import torch
+    assert t.dtype == torch.float64 and t.is_contiguous() and t.dim() == 1, "data columns are contiguous float64 [N]"
+    return t
+
+
+def prep_status_reset(status):
+    import torch
+    assert status.dtype == torch.int64 and status.numel() >= PREP_STATUS_WORDS
+    _check(_prep_reset(_ptr(status), _stream()))
+
+
+def prep_percent_changes(x, out, file_starts, decimals, status):
+    """x, out float64 [N] (distinct); file_starts int64 [F] device (first row of every file, [0] = 0)."""
+    import torch
+    assert file_starts.dtype == torch.int64 and file_starts.is_contiguous() and out.numel() == x.numel()
+    _check(_prep_pct(_ptr(_f64(x)), _ptr(_f64(out)), x.numel(), _ptr(file_starts), file_starts.numel(), int(decimals),
+                     _ptr(status), _stream()))
+
+
+def prep_range(x, out, has_whole_digits, decimals, lower, upper, upper_clamp, thresholds, factors, status):
+    """x, out float64 [N] (may alias); thresholds / factors float64 [633] device tables (None without whole digits)."""
+    assert out.numel() == x.numel()
+    if has_whole_digits:
+        assert thresholds.numel() == PREP_DECADES and factors.numel() == PREP_DECADES
+        _f64(thresholds), _f64(factors)
+    _check(_prep_range(_ptr(_f64(x)), _ptr(_f64(out)), x.numel(), 1 if has_whole_digits else 0, int(decimals), float(lower),
+                       float(upper), float(upper_clamp), _ptr(thresholds), _ptr(factors), _ptr(status), _stream()))
+
+
+def prep_select_workspace_bytes():
+    return int(_prep_sel_ws())
+
+
+def prep_order_statistics(x, ranks, out, workspace, status):
+    """out[r] = the ranks[r]-th smallest (0-based) element of x; ranks int64 [R <= 4] and out float64 [R] on the device."""
+    import torch
+    assert ranks.dtype == torch.int64 and out.dtype == torch.float64 and 1 <= ranks.numel() <= PREP_MAX_RANKS
+    assert out.numel() >= ranks.numel() and workspace.numel() * workspace.element_size() >= prep_select_workspace_bytes()
+    _check(_prep_sel(_ptr(_f64(x)), x.numel(), _ptr(ranks), ranks.numel(), _ptr(out), _ptr(workspace), _ptr(status), _stream()))
+
+
+def prep_minmax_workspace_bytes(N):
+    return int(_prep_mm_ws(int(N)))
+
+
+def prep_filtered_minmax(x, lo, hi, out3, workspace):
+    """out3 float64 [3] = {min, max, count} over the rows with lo <= x <= hi."""
+    import torch
+    assert out3.dtype == torch.float64 and out3.numel() >= 3
+    assert workspace.numel() * workspace.element_size() >= prep_minmax_workspace_bytes(x.numel())
+    _check(_prep_mm(_ptr(_f64(x)), x.numel(), float(lo), float(hi), _ptr(out3), _ptr(workspace), _stream()))
+
+
+def prep_bin_assign(x, out, pos_bounds, neg_bounds):
+    """out[i] = group of x[i] as a double; pos_bounds / neg_bounds float64 [G+1] on the device."""
+    G = pos_bounds.numel() - 1
+    assert neg_bounds.numel() == G + 1 and out.numel() == x.numel()
+    _check(_prep_bin(_ptr(_f64(x)), _ptr(_f64(out)), x.numel(), _ptr(_f64(pos_bounds)), _ptr(_f64(neg_bounds)), G, _stream()))
+
+
+def prep_vocab_insert(x, table, counters, status):
+    """table int64/uint64 bits [capacity = 2^k] (cleared here); counters int64 [2] (cleared here; [0] = distinct values)."""
+    import torch
+    assert table.element_size() == 8 and table.is_contiguous() and counters.dtype == torch.int64 and counters.numel() >= 2
+    _check(_prep_vins(_ptr(_f64(x)), x.numel(), _ptr(table), table.numel(), _ptr(counters), _ptr(status), _stream()))
+
+
+def prep_vocab_build(table, n_distinct, keys_ws, slots_ws, vocabulary, token_of_slot, counters):
+    import torch
+    assert keys_ws.element_size() == 8 and keys_ws.numel() >= n_distinct and slots_ws.dtype == torch.int32
+    assert slots_ws.numel() >= n_distinct and vocabulary.dtype == torch.float64 and vocabulary.numel() >= n_distinct
+    assert token_of_slot.dtype == torch.int32 and token_of_slot.numel() >= table.numel()
+    _check(_prep_vbuild(_ptr(table), table.numel(), int(n_distinct), _ptr(keys_ws), _ptr(slots_ws), _ptr(vocabulary),
+                        _ptr(token_of_slot), _ptr(counters), _stream()))
+
+
+def prep_vocab_lookup(x, table, token_of_slot, tokens):
+    import torch
+    assert tokens.dtype == torch.int32 and tokens.is_contiguous() and tokens.numel() == x.numel()
+    _check(_prep_vlook(_ptr(_f64(x)), x.numel(), _ptr(table), table.numel(), _ptr(token_of_slot), _ptr(tokens), _stream()))
