@@ -244,9 +244,10 @@ int32_t ta_prep_filtered_minmax(const double* x, int64_t N, double lo, double hi
 
 /* Group assignment of bin_numeric_data (:527-557): pos_bounds = [0, b_1 .. b_G], neg_bounds = [-b_G .. -b_1, 0] (fp64
  * [G+1] device arrays built by the host with the reference's expressions); out[i] = the group number as a double
- * (-G .. G). May run in place. */
+ * (-G .. G). bounds_sorted != 0: the caller has checked that both arrays are non-decreasing, the reference's linear walk
+ * (:531-536, :548-553) is then done as a bisection with the same result; 0 keeps the walk. May run in place. */
 int32_t ta_prep_bin_assign(const double* x, double* out, int64_t N, const double* pos_bounds, const double* neg_bounds,
-                           int32_t num_groups, void* stream);
+                           int32_t num_groups, int32_t bounds_sorted, void* stream);
 
 /* numerical_representation (data_utils.py:212-225): vocabulary = sorted(set(x)), token = index in it.
  * insert: distinct values of x into an open-addressing table (uint64 [capacity], capacity a power of two; cleared here);

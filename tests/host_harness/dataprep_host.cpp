@@ -45,8 +45,8 @@ void h_percent(const double* x, long long n, int nd, double* out) {
   for (long long i = 1; i < n; ++i) out[i] = x[i - 1] == 0.0 ? 0.0 : percent_change(x[i], x[i - 1], P);
 }
 
-void h_bin(const double* x, long long n, const double* pos, const double* neg, int G, int* out) {
-  for (long long i = 0; i < n; ++i) out[i] = bin_of(x[i], pos, neg, G);
+void h_bin(const double* x, long long n, const double* pos, const double* neg, int G, int sorted, int* out) {
+  for (long long i = 0; i < n; ++i) out[i] = bin_of(x[i], pos, neg, G, sorted != 0);
 }
 
 void h_order_key(const double* x, long long n, unsigned long long* keys, double* back) {

@@ -202,10 +202,22 @@ def test_device_percent_and_bins_against_reference(host, golden):
         kept = x[(x >= lo) & (x <= hi)]
         pos, neg = oracle.group_boundaries(c["num_groups"], c["exponent"], max(abs(kept.min()), abs(kept.max())))
         pos, neg = np.array(pos), np.array(neg)
-        out = np.empty(x.size, dtype=np.int32)
-        host.h_bin(P(x.ctypes.data), ctypes.c_longlong(x.size), P(pos.ctypes.data), P(neg.ctypes.data),
-                   ctypes.c_int(c["num_groups"]), P(out.ctypes.data))
-        assert out.tolist() == c["y"].tolist(), (c["name"], c["num_groups"])
+        assert np.all(np.diff(pos) >= 0) and np.all(np.diff(neg) >= 0)
+        for is_sorted in (0, 1):                                  # the reference's linear walk and the bisection
+            out = np.empty(x.size, dtype=np.int32)
+            host.h_bin(P(x.ctypes.data), ctypes.c_longlong(x.size), P(pos.ctypes.data), P(neg.ctypes.data),
+                       ctypes.c_int(c["num_groups"]), ctypes.c_int(is_sorted), P(out.ctypes.data))
+            assert out.tolist() == c["y"].tolist(), (c["name"], c["num_groups"], is_sorted)
+    # boundaries with repeats (empty groups): both searches agree on every side of every boundary
+    pos = np.array([0.0, 1.0, 1.0, 2.0, 2.0, 2.0, 5.0]); neg = -pos[::-1].copy(); neg[-1] = 0.0
+    xs = np.array(sorted({s * (b + d) for b in pos for d in (-0.5, -1e-9, 0.0, 1e-9, 0.5) for s in (1, -1)} | {7.0, -7.0}))
+    outs = []
+    for is_sorted in (0, 1):
+        out = np.empty(xs.size, dtype=np.int32)
+        host.h_bin(P(xs.ctypes.data), ctypes.c_longlong(xs.size), P(pos.ctypes.data), P(neg.ctypes.data), ctypes.c_int(6),
+                   ctypes.c_int(is_sorted), P(out.ctypes.data))
+        outs.append(out.tolist())
+    assert outs[0] == outs[1]
 
 
 def test_order_key_is_monotone_and_invertible(host):

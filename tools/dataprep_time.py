@@ -65,7 +65,7 @@ report("prep_minmax_partial_kernel (+final)", N * 8, timeit(lambda: lib.prep_fil
 pos, neg = du._group_boundaries(10, 2.2, max(abs(mm[0].item()), abs(mm[1].item())))
 pos_d, neg_d = torch.tensor(pos, dtype=torch.float64, device=dev), torch.tensor(neg, dtype=torch.float64, device=dev)
 groups = torch.empty_like(pct)
-report("prep_bin_kernel", N * 16, timeit(lambda: lib.prep_bin_assign(pct, groups, pos_d, neg_d)), "10 groups per sign")
+report("prep_bin_kernel", N * 16, timeit(lambda: lib.prep_bin_assign(pct, groups, pos_d, neg_d, True)), "10 groups per sign")
 cap = 1 << 17
 table = torch.empty(cap, dtype=torch.int64, device=dev); counters = torch.empty(2, dtype=torch.int64, device=dev)
 report("prep_vocab_insert_kernel", N * 8, timeit(lambda: lib.prep_vocab_insert(rng_out, table, counters, st)))

@@ -21,9 +21,22 @@ using namespace prep;
 constexpr int DP_THREADS = 256;
 constexpr long long NO_ROW = 0x7fffffffffffffffll;
 
-static inline int dp_grid(int64_t n, int per_thread = 4) {
-  const int64_t want = ceil_div(n, (int64_t)DP_THREADS * per_thread);
-  const int64_t cap = (int64_t)num_sms() * 8;
+// Grid of a grid-stride kernel: every CTA resident at once (SMs x the kernel's own occupancy), so that there is no
+// partial second wave - a fixed 8 CTAs per SM left the 36-42 register kernels with a quarter-filled tail wave (ncu:
+// 55 % achieved warps) - and never more CTAs than the rows need (`rows_per_thread` rows per thread).
+template <typename Kernel>
+static int dp_grid(Kernel kernel, int64_t n, int rows_per_thread = 2, size_t dyn_smem = 0) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DP_THREADS, dyn_smem) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 4;
+  }
+  const int64_t want = ceil_div(n, (int64_t)DP_THREADS * rows_per_thread);
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+static inline int dp_parts(int64_t n) {   // partial results of the two-stage min/max: sized without a device query
+  const int64_t want = ceil_div(n, (int64_t)DP_THREADS * 2), cap = (int64_t)num_sms() * 8;
   return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
@@ -184,33 +197,40 @@ __global__ void __launch_bounds__(DP_THREADS) prep_select_hist_kernel(const doub
   }
 }
 
-__global__ void prep_select_pick_kernel(int R, int shift, u64* __restrict__ state, u64* __restrict__ hist,
-                                        double* __restrict__ out) {
+// One CTA of 256 threads = one thread per bin: block-wide prefix sum of the leader's histogram, the bin that holds the
+// rank extends the prefix. (A serial walk over the 256 bins cost 19 us per pass, a quarter of a pass over 20 M rows.)
+__global__ void __launch_bounds__(256) prep_select_pick_kernel(int R, int shift, u64* __restrict__ state,
+                                                               u64* __restrict__ hist, double* __restrict__ out) {
   pdl_prologue();
-  __shared__ u64 s_prefix[TA_PREP_MAX_RANKS];
+  __shared__ u64 s_prefix[TA_PREP_MAX_RANKS], s_k[TA_PREP_MAX_RANKS];
   __shared__ int s_leader[TA_PREP_MAX_RANKS];
-  if (threadIdx.x == 0) {
-    for (int r = 0; r < R; ++r) s_prefix[r] = state[2 * r];
+  __shared__ u64 s_c[256];
+  const int t = threadIdx.x;
+  if (t == 0) {
+    for (int r = 0; r < R; ++r) { s_prefix[r] = state[2 * r]; s_k[r] = state[2 * r + 1]; }
     select_leaders(s_prefix, R, shift, s_leader);
   }
   __syncthreads();
-  const int r = threadIdx.x;
-  if (r < R) {
-    const u64* h = hist + s_leader[r] * 256;
-    u64 k = state[2 * r + 1], cum = 0;
-    int b = 0;
-    for (; b < 255; ++b) {
-      const u64 c = h[b];
-      if (cum + c > k) break;
-      cum += c;
+  for (int r = 0; r < R; ++r) {
+    const u64 c = hist[s_leader[r] * 256 + t];
+    s_c[t] = c;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+      const u64 v = t >= off ? s_c[t - off] : 0;
+      __syncthreads();
+      s_c[t] += v;
+      __syncthreads();
     }
-    const u64 prefix = s_prefix[r] | ((u64)b << shift);
-    state[2 * r] = prefix;
-    state[2 * r + 1] = k - cum;
-    if (shift == 0) out[r] = order_value(prefix);
+    const u64 incl = s_c[t], excl = incl - c, k = s_k[r];
+    if ((excl <= k && k < incl) || (t == 255 && k >= incl)) {
+      const u64 prefix = s_prefix[r] | ((u64)t << shift);
+      state[2 * r] = prefix;
+      state[2 * r + 1] = k - excl;
+      if (shift == 0) out[r] = order_value(prefix);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < R * 256; k += blockDim.x) hist[k] = 0;
+  for (int k = t; k < R * 256; k += 256) hist[k] = 0;
 }
 
 __global__ void prep_select_init_kernel(int R, const long long* __restrict__ ranks, u64* __restrict__ state,
@@ -274,7 +294,7 @@ __global__ void __launch_bounds__(DP_THREADS) prep_minmax_final_kernel(const dou
 // ------------------------------------------------------------------------------------------------ bin assignment
 __global__ void __launch_bounds__(DP_THREADS) prep_bin_kernel(const double* __restrict__ x, double* __restrict__ out,
                                                                 long long N, const double* __restrict__ pos,
-                                                                const double* __restrict__ neg, int G) {
+                                                                const double* __restrict__ neg, int G, int sorted) {
   pdl_prologue();
   extern __shared__ double s_bounds[];
   double* s_pos = s_bounds;
@@ -287,8 +307,8 @@ __global__ void __launch_bounds__(DP_THREADS) prep_bin_kernel(const double* __re
     const bool two = i1 < N;
     const double v0 = x[i0];
     const double v1 = two ? x[i1] : 0.0;
-    out[i0] = (double)bin_of(v0, s_pos, s_neg, G);
-    if (two) out[i1] = (double)bin_of(v1, s_pos, s_neg, G);
+    out[i0] = (double)bin_of(v0, s_pos, s_neg, G, sorted != 0);
+    if (two) out[i1] = (double)bin_of(v1, s_pos, s_neg, G, sorted != 0);
   }
 }
 
@@ -402,7 +422,7 @@ int32_t ta_prep_percent_changes(const double* x, double* out, int64_t N, const i
   TA_CHECK_ARG(N > 0 && n_files >= 1, "ta_prep_percent_changes: N=%lld n_files=%d", (long long)N, n_files);
   TA_CHECK_ARG(decimals >= 0 && decimals <= MAX_DECIMALS, "ta_prep_percent_changes: decimals %d outside [0, %d]", decimals,
                MAX_DECIMALS);
-  TA_CHECK_CUDA(launch_kernel(prep_percent_kernel, dim3(dp_grid(N)), dim3(DP_THREADS), 0, (cudaStream_t)stream, x, out,
+  TA_CHECK_CUDA(launch_kernel(prep_percent_kernel, dim3(dp_grid(prep_percent_kernel, N)), dim3(DP_THREADS), 0, (cudaStream_t)stream, x, out,
                               (long long)N, (const long long*)file_starts, (int)n_files, host_pow10(decimals),
                               (long long*)status));
   TA_CHECK_LAUNCH();
@@ -423,7 +443,7 @@ int32_t ta_prep_range(const double* x, double* out, int64_t N, int32_t has_whole
   rp.lower = lower;
   rp.upper = upper;
   rp.upper_clamp = upper_clamp;
-  TA_CHECK_CUDA(launch_kernel(prep_range_kernel, dim3(dp_grid(N)), dim3(DP_THREADS), 0, (cudaStream_t)stream, x, out,
+  TA_CHECK_CUDA(launch_kernel(prep_range_kernel, dim3(dp_grid(prep_range_kernel, N)), dim3(DP_THREADS), 0, (cudaStream_t)stream, x, out,
                               (long long)N, rp, thresholds, factors, (long long*)status));
   TA_CHECK_LAUNCH();
   return 0;
@@ -442,7 +462,7 @@ int32_t ta_prep_order_statistics(const double* x, int64_t N, const int64_t* rank
   TA_CHECK_CUDA(launch_kernel(prep_select_init_kernel, dim3(1), dim3(256), 0, st, (int)n_ranks, (const long long*)ranks_dev,
                               state, hist));
   TA_CHECK_LAUNCH();
-  const int grid = dp_grid(N, 8);
+  const int grid = dp_grid(prep_select_hist_kernel, N);
   for (int shift = 56; shift >= 0; shift -= 8) {
     TA_CHECK_CUDA(launch_kernel(prep_select_hist_kernel, dim3(grid), dim3(DP_THREADS), 0, st, x, (long long)N, (int)n_ranks,
                                 shift, (const u64*)state, hist, (long long*)status));
@@ -453,13 +473,13 @@ int32_t ta_prep_order_statistics(const double* x, int64_t N, const int64_t* rank
   return 0;
 }
 
-int64_t ta_prep_minmax_workspace_bytes(int64_t N) { return (int64_t)dp_grid(N) * 24; }
+int64_t ta_prep_minmax_workspace_bytes(int64_t N) { return (int64_t)dp_parts(N) * 24; }
 
 int32_t ta_prep_filtered_minmax(const double* x, int64_t N, double lo, double hi, double* out3, void* workspace,
                                 void* stream) {
   TA_CHECK_ARG(x && out3 && workspace, "ta_prep_filtered_minmax: null pointer");
   TA_CHECK_ARG(N > 0, "ta_prep_filtered_minmax: N=%lld", (long long)N);
-  const int grid = dp_grid(N);
+  const int grid = dp_parts(N);
   double* pmin = (double*)workspace;
   double* pmax = pmin + grid;
   long long* pcnt = (long long*)(pmax + grid);
@@ -474,7 +494,7 @@ int32_t ta_prep_filtered_minmax(const double* x, int64_t N, double lo, double hi
 }
 
 int32_t ta_prep_bin_assign(const double* x, double* out, int64_t N, const double* pos_bounds, const double* neg_bounds,
-                           int32_t num_groups, void* stream) {
+                           int32_t num_groups, int32_t bounds_sorted, void* stream) {
   TA_CHECK_ARG(x && out && pos_bounds && neg_bounds, "ta_prep_bin_assign: null pointer");
   TA_CHECK_ARG(N > 0, "ta_prep_bin_assign: N=%lld", (long long)N);
   TA_CHECK_ARG(num_groups >= 1 && num_groups <= TA_PREP_MAX_GROUPS, "ta_prep_bin_assign: num_groups %d outside [1, %d]",
@@ -482,8 +502,8 @@ int32_t ta_prep_bin_assign(const double* x, double* out, int64_t N, const double
   const size_t smem = (size_t)2 * (num_groups + 1) * sizeof(double);
   if (smem > 48 * 1024)
     TA_CHECK_CUDA(cudaFuncSetAttribute(prep_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TA_CHECK_CUDA(launch_kernel(prep_bin_kernel, dim3(dp_grid(N)), dim3(DP_THREADS), smem, (cudaStream_t)stream, x, out,
-                              (long long)N, pos_bounds, neg_bounds, (int)num_groups));
+  TA_CHECK_CUDA(launch_kernel(prep_bin_kernel, dim3(dp_grid(prep_bin_kernel, N, 2, smem)), dim3(DP_THREADS), smem, (cudaStream_t)stream, x, out,
+                              (long long)N, pos_bounds, neg_bounds, (int)num_groups, (int)(bounds_sorted != 0)));
   TA_CHECK_LAUNCH();
   return 0;
 }
@@ -497,7 +517,7 @@ int32_t ta_prep_vocab_insert(const double* x, int64_t N, uint64_t* table, int64_
   cudaStream_t st = (cudaStream_t)stream;
   TA_CHECK_CUDA(cudaMemsetAsync(table, 0xff, (size_t)capacity * 8, st));
   TA_CHECK_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(int64_t), st));
-  TA_CHECK_CUDA(launch_kernel(prep_vocab_insert_kernel, dim3(dp_grid(N)), dim3(DP_THREADS), 0, st, x, (long long)N,
+  TA_CHECK_CUDA(launch_kernel(prep_vocab_insert_kernel, dim3(dp_grid(prep_vocab_insert_kernel, N, 1)), dim3(DP_THREADS), 0, st, x, (long long)N,
                               (u64*)table, (long long)(capacity - 1), (long long*)counters, (long long*)status));
   TA_CHECK_LAUNCH();
   return 0;
@@ -509,7 +529,7 @@ int32_t ta_prep_vocab_build(const uint64_t* table, int64_t capacity, int64_t n_d
   TA_CHECK_ARG(n_distinct >= 1 && n_distinct <= capacity && n_distinct < (1ll << 31), "ta_prep_vocab_build: n_distinct=%lld",
                (long long)n_distinct);
   cudaStream_t st = (cudaStream_t)stream;
-  TA_CHECK_CUDA(launch_kernel(prep_vocab_compact_kernel, dim3(dp_grid(capacity)), dim3(DP_THREADS), 0, st, (const u64*)table,
+  TA_CHECK_CUDA(launch_kernel(prep_vocab_compact_kernel, dim3(dp_grid(prep_vocab_compact_kernel, capacity, 1)), dim3(DP_THREADS), 0, st, (const u64*)table,
                               (long long)capacity, (u64*)keys_ws, (int*)slots_ws, (long long*)counters));
   TA_CHECK_LAUNCH();
   TA_CHECK_CUDA(launch_kernel(prep_vocab_rank_kernel, dim3((unsigned)ceil_div(n_distinct, DP_THREADS)), dim3(DP_THREADS), 0, st,
@@ -523,7 +543,7 @@ int32_t ta_prep_vocab_lookup(const double* x, int64_t N, const uint64_t* table, 
   TA_CHECK_ARG(x && table && token_of_slot && tokens, "ta_prep_vocab_lookup: null pointer");
   TA_CHECK_ARG(N > 0 && capacity >= 2 && (capacity & (capacity - 1)) == 0, "ta_prep_vocab_lookup: N=%lld capacity=%lld",
                (long long)N, (long long)capacity);
-  TA_CHECK_CUDA(launch_kernel(prep_vocab_lookup_kernel, dim3(dp_grid(N)), dim3(DP_THREADS), 0, (cudaStream_t)stream, x,
+  TA_CHECK_CUDA(launch_kernel(prep_vocab_lookup_kernel, dim3(dp_grid(prep_vocab_lookup_kernel, N, 1)), dim3(DP_THREADS), 0, (cudaStream_t)stream, x,
                               (long long)N, (const u64*)table, (long long)(capacity - 1), (const int*)token_of_slot,
                               (int*)tokens));
   TA_CHECK_LAUNCH();

@@ -159,15 +159,22 @@ TA_HD double py_round(double x, Pow10 P) {
   return double_of(bits_of(r) | sign);
 }
 
-// floor(math.log10(ax)) for a finite ax > 0 through the host-built threshold table (ascending, P10_COUNT entries):
-// the number of thresholds <= ax, minus one, plus P10_MIN.
+// floor(math.log10(ax)) for a finite ax > 0 through the host-built threshold table (ascending, P10_COUNT entries;
+// thresholds[k] = smallest double whose floor(log10) is >= k + P10_MIN). A binade [2^e, 2^(e+1)) meets at most two
+// decades, floor(e * log10(2)) and the next one, so the binary exponent gives the candidate and two comparisons with the
+// table settle it (the table, not the arithmetic, carries libm's rounding near the powers of ten).
 TA_HD int floor_log10(double ax, const double* __restrict__ thresholds) {
-  int lo = 0, hi = P10_COUNT;                // first index with thresholds[i] > ax
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (thresholds[mid] <= ax) lo = mid + 1; else hi = mid;
+  const u64 b = bits_of(ax);
+  int e = (int)(b >> 52) - 1023;
+  if (e == -1023) {                          // subnormal: exponent of the leading fraction bit
+    int lead = 51;
+    while (!((b >> lead) & 1)) --lead;
+    e = lead - 1074;
   }
-  return lo - 1 + P10_MIN;
+  int p = (e * 78913) >> 18;                 // floor(e * log10(2)) for |e| <= 1650
+  if (p < P10_MAX && ax >= thresholds[p + 1 - P10_MIN]) ++p;
+  else if (ax < thresholds[p - P10_MIN]) --p;
+  return p;
 }
 
 struct RangeParams {
@@ -206,7 +213,7 @@ TA_HD double percent_change(double cur, double prev, Pow10 P) {
 
 // Group of one value in bin_numeric_data (data_utils.py:527-557): pos = [0, b_1 .. b_G], neg = [-b_G .. -b_1, 0].
 // The reference's linear search for the first j with bound[j] <= v < bound[j+1], with its for/else edge groups.
-TA_HD int bin_of(double v, const double* pos, const double* neg, int G) {
+TA_HD int bin_of_linear(double v, const double* pos, const double* neg, int G) {
   if (v > 0.0) {
     for (int j = 0; j < G; ++j)
       if (v >= pos[j] && v < pos[j + 1]) return j + 1;
@@ -216,6 +223,33 @@ TA_HD int bin_of(double v, const double* pos, const double* neg, int G) {
   for (int j = 0; j < G; ++j)
     if (v >= neg[j] && v < neg[j + 1]) return -(G - j);
   return -G;
+}
+
+// count of bounds[0..n) that are <= v (bounds non-decreasing)
+TA_HD int count_le(const double* bounds, int n, double v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (bounds[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// The same group when the boundaries are non-decreasing (the host checks; they are whenever pow() is monotone): the
+// first interval that holds v is the one after the last boundary <= v, so the search is a bisection.
+TA_HD int bin_of_sorted(double v, const double* pos, const double* neg, int G) {
+  if (v > 0.0) {
+    const int j = count_le(pos + 1, G, v);          // v > 0 = pos[0]
+    return j < G ? j + 1 : G;
+  }
+  if (v == 0.0) return 0;
+  if (!(v >= neg[0])) return -G;                      // below the most negative boundary (or NaN)
+  const int j = count_le(neg, G + 1, v) - 1;          // v < 0 = neg[G]  =>  j <= G - 1
+  return -(G - j);
+}
+
+TA_HD int bin_of(double v, const double* pos, const double* neg, int G, bool sorted) {
+  return sorted ? bin_of_sorted(v, pos, neg, G) : bin_of_linear(v, pos, neg, G);
 }
 
 // Order-preserving map of finite doubles to unsigned integers (for the radix select) and back.

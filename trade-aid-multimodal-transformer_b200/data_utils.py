@@ -309,8 +309,9 @@ def bin_numeric_data(data, num_groups, outlier_percentile=5, exponent=2.0, out=N
     max_abs_value = max(abs(fmin), abs(fmax))
     pos, neg = _group_boundaries(num_groups, exponent, max_abs_value)
     res = torch.empty_like(x) if out is None else out
+    monotone = all(a <= b for a, b in zip(pos, pos[1:])) and all(a <= b for a, b in zip(neg, neg[1:]))
     ops.prep_bin_assign(x, res, torch.tensor(pos, dtype=torch.float64, device=x.device),
-                        torch.tensor(neg, dtype=torch.float64, device=x.device))
+                        torch.tensor(neg, dtype=torch.float64, device=x.device), bounds_sorted=monotone)
     if verbose:
         counts = torch.bincount((res + num_groups).to(torch.int64), minlength=2 * num_groups + 1).tolist()
         _print_bin_breakdown(counts, num_groups, pos, neg, x.numel())

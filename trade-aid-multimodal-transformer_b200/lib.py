@@ -478,7 +478,7 @@ _prep_sel_ws = _sig("ta_prep_select_workspace_bytes", restype=_I64)
 _prep_sel = _sig("ta_prep_order_statistics", _P, _I64, _P, _I32, _P, _P, _P, _P)
 _prep_mm_ws = _sig("ta_prep_minmax_workspace_bytes", _I64, restype=_I64)
 _prep_mm = _sig("ta_prep_filtered_minmax", _P, _I64, _F64, _F64, _P, _P, _P)
-_prep_bin = _sig("ta_prep_bin_assign", _P, _P, _I64, _P, _P, _I32, _P)
+_prep_bin = _sig("ta_prep_bin_assign", _P, _P, _I64, _P, _P, _I32, _I32, _P)
 _prep_vins = _sig("ta_prep_vocab_insert", _P, _I64, _P, _I64, _P, _P, _P)
 _prep_vbuild = _sig("ta_prep_vocab_build", _P, _I64, _I64, _P, _P, _P, _P, _P, _P)
 _prep_vlook = _sig("ta_prep_vocab_lookup", _P, _I64, _P, _I64, _P, _P, _P)
@@ -538,11 +538,13 @@ def prep_filtered_minmax(x, lo, hi, out3, workspace):
     _check(_prep_mm(_ptr(_f64(x)), x.numel(), float(lo), float(hi), _ptr(out3), _ptr(workspace), _stream()))
 
 
-def prep_bin_assign(x, out, pos_bounds, neg_bounds):
-    """out[i] = group of x[i] as a double; pos_bounds / neg_bounds float64 [G+1] on the device."""
+def prep_bin_assign(x, out, pos_bounds, neg_bounds, bounds_sorted=False):
+    """out[i] = group of x[i] as a double; pos_bounds / neg_bounds float64 [G+1] on the device; bounds_sorted: the caller
+    checked that both are non-decreasing (bisection instead of the reference's linear walk, same groups)."""
     G = pos_bounds.numel() - 1
     assert neg_bounds.numel() == G + 1 and out.numel() == x.numel()
-    _check(_prep_bin(_ptr(_f64(x)), _ptr(_f64(out)), x.numel(), _ptr(_f64(pos_bounds)), _ptr(_f64(neg_bounds)), G, _stream()))
+    _check(_prep_bin(_ptr(_f64(x)), _ptr(_f64(out)), x.numel(), _ptr(_f64(pos_bounds)), _ptr(_f64(neg_bounds)), G,
+                     1 if bounds_sorted else 0, _stream()))
 
 
 def prep_vocab_insert(x, table, counters, status):
