@@ -215,3 +215,48 @@ def test_vocabulary_table_growth(du):
     tok, voc = du.numerical_representation(x)
     assert len(voc) == n and voc[0] == -1000.0 and voc[-1] == (n - 1) * 0.5 - 1000.0
     assert torch.equal(tok.long(), ((x + 1000.0) * 2).long())
+
+
+def test_prepared_dataset_feeds_get_batch(du):
+    """Raw columns -> prepare_dataset -> training_utils.get_batch: the batches equal the ones drawn from the reference-style
+    python lists built by the oracle chain (same seed), so prepared device rows are a drop-in for all_train_sets/val_sets."""
+    from oracle import dataprep as oracle
+    from tradeaid_b200 import training_utils as tu
+    rng = random.Random(4)
+    n, lens = 3000, [1000, 1200, 800]
+    price = []
+    p = 50.0
+    for _ in range(n):
+        p = max(1.0, p * (1 + rng.gauss(0, 0.01)))
+        price.append(round(p, 2))
+    volume = [float(rng.randint(1, 10 ** 5)) for _ in range(n)]
+    params = [["p.csv", 1, None, True, None, 2, 8, None, False, "price pct", 0.5, 2.0],
+              ["p.csv", 2, None, False, 2, 1, None, None, True, "volume", None, None]]
+    train, val, vocabs = du.prepare_dataset([price, volume], params, lens, validation_size=0.1)
+    want = [oracle.prepare_modality(c, q, lens) for c, q in zip([price, volume], params)]
+    cut = int(n * (1 - 0.1))
+    for i in range(2):
+        assert train[i].is_cuda and train[i].dtype == torch.int32
+        assert train[i].cpu().tolist() == want[i][0][:cut] and val[i].cpu().tolist() == want[i][0][cut:]
+        assert [float(v) for v in vocabs[i]] == [float(v) for v in want[i][1]]
+
+    def batches(train_sets, val_sets):
+        tu.configure(device="cuda", batch_size=8, block_size=16, eval_iters=1)
+        tu.all_train_sets, tu.all_val_sets = train_sets, val_sets
+        tu.all_vocabularies = vocabs
+        tu.all_modality_params = params
+        tu.file_lengths = lens
+        tu.num_modalities = 2
+        tu.is_percents = True
+        torch.manual_seed(123)
+        out = []
+        for split in ("train", "val", "train"):
+            xb, yb = tu.get_batch(split, 0)
+            out.append([t.cpu() for t in xb + yb])
+        return out
+
+    got = batches(train, val)
+    ref = batches([w[0][:cut] for w in want], [torch.tensor(w[0][cut:], dtype=torch.long) for w in want])
+    for a, b in zip(got, ref):
+        for s, t in zip(a, b):
+            assert torch.equal(s, t)

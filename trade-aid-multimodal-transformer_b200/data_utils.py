@@ -435,3 +435,30 @@ def prepare_modality(column, modality_params, file_lengths=None, tokens_out=None
         exponent = p[11] if p[11] is not None else 2.2
         x = bin_numeric_data(x, num_bins, outlier, exponent, verbose=verbose, as_float=True)
     return numerical_representation(x, tokens_out=tokens_out, integer_vocabulary=binned)
+
+
+def prepare_dataset(columns, all_modality_params, file_lengths, validation_size=0.1, num_validation_files=0, verbose=False):
+    """All modalities of a run: what main.py builds between loading and training (main.py:100-210, 270-396), with the
+    tokens kept in ONE int32 [M, N] device matrix — the layout of the feeder's TokenStore.
+    columns: per modality a list of numbers or a float64 CUDA tensor [N] (raw values, files concatenated in order).
+    Returns (all_train_sets, all_val_sets, all_vocabularies): per modality VIEWS of the matrix rows split as
+    create_train_val_datasets splits them, and the vocabularies as Python lists — assign them to
+    tradeaid_b200.training_utils' globals of the same names; get_batch then gathers straight from HBM."""
+    M = len(columns)
+    if M == 0 or len(all_modality_params) != M:
+        raise ValueError("columns and all_modality_params must list the same, non-zero number of modalities")
+    lengths = {len(c) if not _is_column(c) else int(c.numel()) for c in columns}
+    if len(lengths) != 1:
+        raise ValueError(f"All modalities must have the same length for proper training, got {sorted(lengths)}.")
+    n = lengths.pop()
+    tokens = torch.empty(M, n, dtype=torch.int32, device=_device())
+    vocabularies = []
+    for i in range(M):
+        _, vocab = prepare_modality(columns[i], all_modality_params[i], file_lengths, tokens_out=tokens[i], verbose=verbose)
+        vocabularies.append(vocab)
+    train, val = [], []
+    for i in range(M):
+        tr, va = create_train_val_datasets(tokens[i], validation_size, num_validation_files, list(file_lengths))
+        train.append(tr)
+        val.append(va)
+    return train, val, vocabularies
