@@ -5,22 +5,30 @@
 
 using namespace ta::prep;
 
-static Pow10 pow10_of(int nd) {
-  u128 p = 1;
-  double d = 1.0;
-  for (int i = 0; i < nd; ++i) { p *= 10; d *= 10.0; }   // exact up to 10^22
-  Pow10 P;
-  P.lo = (u64)p;
-  P.hi = (u64)(p >> 64);
-  P.d = d;
-  return P;
-}
+static Pow10 pow10_of(int nd) { return make_pow10(nd); }
 
 extern "C" {
 
 void h_py_round(const double* x, long long n, int nd, double* out) {
   const Pow10 P = pow10_of(nd);
   for (long long i = 0; i < n; ++i) out[i] = py_round(x[i], P);
+}
+
+// number of k in a pseudo-random sample (plus the edges) for which the division-free quotient differs from IEEE k / 10^nd
+long long h_div_pow10_mismatches(int nd, long long samples, unsigned long long seed) {
+  const Pow10 P = pow10_of(nd);
+  long long bad = 0;
+  unsigned long long st = seed;
+  for (long long i = 0; i < samples; ++i) {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    const int bits = 1 + (int)((st >> 58) % 53);
+    unsigned long long k = (hash64(st) >> (64 - bits)) | (1ull << (bits - 1));
+    if (i < 4096) k = (unsigned long long)i + 1;
+    else if (i < 8192) k = (1ull << 53) - (unsigned long long)(i - 4096);
+    const double a = (double)k;
+    if (bits_of(div_pow10(a, P)) != bits_of(a / P.d)) ++bad;
+  }
+  return bad;
 }
 
 void h_floor_log10(const double* ax, long long n, const double* thresholds, int* out) {

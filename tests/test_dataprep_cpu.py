@@ -131,6 +131,14 @@ def test_device_round_is_cpython_round(host):
         assert same_bits(h_round(host, keep, nd), want), nd
 
 
+def test_division_free_quotient_is_ieee_division(host):
+    """k / 10^nd by Markstein's correction with a host-made reciprocal (csrc/dataprep_math.cuh div_pow10) equals the IEEE
+    quotient for every sampled integer k <= 2^53 (all bit lengths, the smallest and the largest 4096 values)."""
+    host.h_div_pow10_mismatches.restype = ctypes.c_longlong
+    for nd in range(0, 23):
+        assert host.h_div_pow10_mismatches(ctypes.c_int(nd), ctypes.c_longlong(2_000_000), ctypes.c_ulonglong(1234 + nd)) == 0, nd
+
+
 def thresholds_and_factors(nwd):
     from tradeaid_b200 import data_utils as du
     return (np.array(du._log10_thresholds(), dtype=np.float64),

@@ -44,16 +44,7 @@ __device__ __forceinline__ void note_row(long long* slot, long long row) {
   atomicMin(reinterpret_cast<long long*>(slot), row);
 }
 
-static Pow10 host_pow10(int nd) {
-  u128 p = 1;
-  double d = 1.0;
-  for (int i = 0; i < nd; ++i) { p *= 10; d *= 10.0; }
-  Pow10 P;
-  P.lo = (u64)p;
-  P.hi = (u64)(p >> 64);
-  P.d = d;
-  return P;
-}
+static Pow10 host_pow10(int nd) { return make_pow10(nd); }
 
 // ------------------------------------------------------------------------------------------------ status
 __global__ void prep_status_reset_kernel(long long* status) {
@@ -83,7 +74,7 @@ __device__ __forceinline__ double percent_row(long long i, double cur, double pr
 }
 
 // Every thread takes two rows a grid stride apart per iteration: four independent 8-byte loads in flight.
-__global__ void __launch_bounds__(DP_THREADS) prep_percent_kernel(const double* __restrict__ x, double* __restrict__ out,
+__global__ void __launch_bounds__(DP_THREADS, 8) prep_percent_kernel(const double* __restrict__ x, double* __restrict__ out,
                                                                     long long N, const long long* __restrict__ file_starts,
                                                                     int F, Pow10 P, long long* __restrict__ status) {
   pdl_prologue();
@@ -109,7 +100,7 @@ __device__ __forceinline__ double range_row(long long i, double v, const RangePa
   return r;
 }
 
-__global__ void __launch_bounds__(DP_THREADS) prep_range_kernel(const double* __restrict__ x, double* __restrict__ out,
+__global__ void __launch_bounds__(DP_THREADS, 8) prep_range_kernel(const double* __restrict__ x, double* __restrict__ out,
                                                                   long long N, RangeParams rp,
                                                                   const double* __restrict__ thresholds,
                                                                   const double* __restrict__ factors,
@@ -144,7 +135,7 @@ __device__ __forceinline__ void select_leaders(const u64* prefix, int R, int shi
   }
 }
 
-__global__ void __launch_bounds__(DP_THREADS) prep_select_hist_kernel(const double* __restrict__ x, long long N, int R,
+__global__ void __launch_bounds__(DP_THREADS, 8) prep_select_hist_kernel(const double* __restrict__ x, long long N, int R,
                                                                         int shift, const u64* __restrict__ state,
                                                                         u64* __restrict__ hist,
                                                                         long long* __restrict__ status) {

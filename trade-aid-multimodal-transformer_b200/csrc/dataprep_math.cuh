@@ -78,11 +78,42 @@ TA_HD double div_rn(double a, double b) {
 TA_HD bool is_finite(double x) { return ((bits_of(x) >> 52) & 0x7ff) != 0x7ff; }
 TA_HD double abs_of(double x) { return double_of(bits_of(x) & 0x7fffffffffffffffull); }
 
-// 10^nd as an exact 128-bit integer (nd <= 22: < 2^74) and as the (exact) double.
+TA_HD double fma_rn(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
+
+// 10^nd as an exact 128-bit integer (nd <= 22: < 2^74), as the (exact) double, and its correctly rounded reciprocal.
 struct Pow10 {
   u64 lo, hi;
   double d;
+  double inv;
 };
+
+TA_HD Pow10 make_pow10(int nd) {
+  u128 p = 1;
+  double d = 1.0;
+  for (int i = 0; i < nd; ++i) { p *= 10; d *= 10.0; }   // exact up to 10^22
+  Pow10 P;
+  P.lo = (u64)p;
+  P.hi = (u64)(p >> 64);
+  P.d = d;
+  P.inv = div_rn(1.0, d);
+  return P;
+}
+
+// RN(k / 10^nd) for an integer-valued 0 < k <= 2^53 without a division: Markstein's correction. With y = RN(1/b) and a
+// faithful quotient q, r = a - b*q is exact in one FMA and RN(q + r*y) is the correctly rounded a/b (Markstein 1990; the
+// one exception, a divisor whose significand is all ones, is not a power of ten). The first q = RN(a*y) can be 2 ulps off,
+// so the correction runs twice. tests/test_dataprep_cpu.py holds this to IEEE division on 10^7 random k per nd.
+TA_HD double div_pow10(double k, const Pow10& P) {
+  double q = mul_rn(k, P.inv);
+  q = fma_rn(fma_rn(-q, P.d, k), P.inv, q);
+  return fma_rn(fma_rn(-q, P.d, k), P.inv, q);
+}
 
 // m * 2^e (m < 2^54, result normal): exact scaling by a power of two without ldexp.
 TA_HD double scale_pow2(u64 m, int e) { return mul_rn((double)m, double_of((u64)(e + 1023) << 52)); }
@@ -101,38 +132,9 @@ TA_HD u64 mul_hi64(u64 a, u64 b) {
 #define TA_HD_COLD inline
 #endif
 
-// General form of py_round: |x| = m / 2^s (m < 2^53, 1 <= s <= 1074), any 10^nd <= 10^22. Kept out of line on the device
-// (128-bit shifts and divisions): the kernels' loops only carry the 64-bit form below.
-TA_HD_COLD double py_round_wide(u64 m, int s, Pow10 P) {
-  const u128 p = ((u128)P.hi << 64) | P.lo;
-  const u128 prod = (u128)m * p;             // < 2^53 * 2^74
-  u128 k = 0;
-  if (s < 128) {                             // s >= 128: prod < 2^127 <= 2^(s-1), the value is below one half
-    k = prod >> s;
-    const u128 rem = prod - (k << s);
-    const u128 half = (u128)1 << (s - 1);
-    if (rem > half || (rem == half && ((u64)k & 1))) k += 1;
-  }
-  if (k == 0) return 0.0;
-  if (k < ((u128)1 << 53)) return div_rn((double)(u64)k, P.d);
-  // correctly rounded k / 10^nd for k >= 2^53 (only when |x| * 10^nd >= 2^53): binary long division to 55 bits
-  u128 q = k / p, rem = k % p;               // q <= 2^53
-  int t = 0;
-  while (q < ((u128)1 << 54)) {
-    rem <<= 1;
-    q <<= 1;
-    if (rem >= p) { rem -= p; q |= 1; }
-    ++t;
-  }
-  const u64 q64 = (u64)q;                    // 55 bits: 53 + guard + first sticky
-  u64 mant = q64 >> 2;
-  const bool guard = (q64 >> 1) & 1, sticky = (q64 & 1) || rem != 0;
-  if (guard && (sticky || (mant & 1))) mant += 1;
-  return scale_pow2(mant, 2 - t);
-}
-
-// CPython round(x, nd), 0 <= nd <= 22.
-TA_HD double py_round(double x, Pow10 P) {
+// General form of py_round: any finite or non-finite x, any 10^nd <= 10^22. Kept out of line on the device (128-bit
+// shifts and divisions): the kernels' loops only carry the 64-bit form below.
+TA_HD_COLD double py_round_wide(double x, Pow10 P) {
   const u64 b = bits_of(x);
   const int be = (int)((b >> 52) & 0x7ff);
   const u64 frac = b & ((1ull << 52) - 1);
@@ -143,20 +145,59 @@ TA_HD double py_round(double x, Pow10 P) {
   if (be == 0) { m = frac; s = 1074; } else { m = frac | (1ull << 52); s = 1075 - be; }
   if (m == 0) return x;                      // +-0.0
   const u64 sign = b & 0x8000000000000000ull;
+  const u128 p = ((u128)P.hi << 64) | P.lo;
+  const u128 prod = (u128)m * p;             // < 2^53 * 2^74
+  u128 k = 0;
+  if (s < 128) {                             // s >= 128: prod < 2^127 <= 2^(s-1), the value is below one half
+    k = prod >> s;
+    const u128 rem = prod - (k << s);
+    const u128 half = (u128)1 << (s - 1);
+    if (rem > half || (rem == half && ((u64)k & 1))) k += 1;
+  }
   double r;
-  bool done = false;
-  if (P.hi == 0 && s < 64 && mul_hi64(m, P.lo) == 0) {      // m * 10^nd fits 64 bits (nd <= 3 always does)
-    const u64 prod = m * P.lo;
-    u64 k = prod >> s;
-    const u64 rem = prod & ((1ull << s) - 1), half = 1ull << (s - 1);
-    if (rem > half || (rem == half && (k & 1))) k += 1;
-    if (k < (1ull << 53)) {
-      r = k ? div_rn((double)k, P.d) : 0.0;  // both exact doubles: IEEE division = correctly rounded k / 10^nd
-      done = true;
+  if (k == 0) {
+    r = 0.0;
+  } else if (k < ((u128)1 << 53)) {
+    r = div_rn((double)(u64)k, P.d);         // both exact doubles: IEEE division = correctly rounded k / 10^nd
+  } else {
+    // correctly rounded k / 10^nd for k >= 2^53 (only when |x| * 10^nd >= 2^53): binary long division to 55 bits
+    u128 q = k / p, rem = k % p;             // q <= 2^53
+    int t = 0;
+    while (q < ((u128)1 << 54)) {
+      rem <<= 1;
+      q <<= 1;
+      if (rem >= p) { rem -= p; q |= 1; }
+      ++t;
+    }
+    const u64 q64 = (u64)q;                  // 55 bits: 53 + guard + first sticky
+    u64 mant = q64 >> 2;
+    const bool guard = (q64 >> 1) & 1, sticky = (q64 & 1) || rem != 0;
+    if (guard && (sticky || (mant & 1))) mant += 1;
+    r = scale_pow2(mant, 2 - t);
+  }
+  return double_of(bits_of(r) | sign);
+}
+
+// CPython round(x, nd), 0 <= nd <= 22. Inline form: 2^-11 <= |x| < 2^42 (so that 11 <= s <= 63: the scaled value
+// m*10^nd / 2^s needs no 128-bit shift and k <= 2^53) with m * 10^nd < 2^64 (always for nd <= 3, |x| < 2^42); everything
+// else - zeros, tiny, huge and non-finite values, many decimals - takes the general form.
+TA_HD double py_round(double x, const Pow10& P) {
+  const u64 b = bits_of(x);
+  const unsigned be = (unsigned)(b >> 52) & 0x7ffu;
+  if ((b << 1) == 0) return x;               // +-0.0 (unchanged prices: common in percent data)
+  if (be - 1012u <= 52u && P.hi == 0) {
+    const u64 m = (b & ((1ull << 52) - 1)) | (1ull << 52);
+    if (mul_hi64(m, P.lo) == 0) {
+      const int s = 1075 - (int)be;
+      const u64 prod = m * P.lo;
+      u64 k = prod >> s;
+      const u64 rem = prod & ((1ull << s) - 1), half = 1ull << (s - 1);
+      k += (rem > half) | ((rem == half) & (k & 1));
+      const double r = k ? div_pow10((double)k, P) : 0.0;
+      return double_of(bits_of(r) | (b & 0x8000000000000000ull));
     }
   }
-  if (!done) r = py_round_wide(m, s, P);
-  return double_of(bits_of(r) | sign);
+  return py_round_wide(x, P);
 }
 
 // floor(math.log10(ax)) for a finite ax > 0 through the host-built threshold table (ascending, P10_COUNT entries;
@@ -207,7 +248,7 @@ TA_HD double range_element(double x, const RangeParams& rp, const double* __rest
 }
 
 // One element of convert_to_percent_changes (data_utils.py:649-657 / file_cache.py:362-377); prev != 0.
-TA_HD double percent_change(double cur, double prev, Pow10 P) {
+TA_HD double percent_change(double cur, double prev, const Pow10& P) {
   return py_round(mul_rn(div_rn(sub_rn(cur, prev), prev), 100.0), P);
 }
 
