@@ -501,9 +501,153 @@ def run_inference(args, cfg):
         print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ data preparation (row f-4)
+def run_dataprep(args):
+    """`--config prep` (not the headline line): the one-shot data preparation of c4's raw columns —
+    8 modalities x 50 M float64 rows (--rows overrides) — through tradeaid_b200.data_utils. A "step" prepares every
+    modality once: percent changes -> rounding -> 10+10+1 groups for the odd modalities, 2 whole digits / 1 decimal for
+    the even ones, then vocabulary + int32 tokens into the [M, N] token store. `value`: rows/s with the raw columns
+    resident in HBM (CUDA events); `e2e`: the same through prepare_dataset from pinned HOST columns (H2D inside the timed
+    region, vocabularies read back); `roofline`: the radix-select histogram passes (the largest share of the step) against
+    the measured copy bandwidth; `cpu_baseline`: the oracle's pure-Python port of the reference chain on a bounded
+    sample. Each column (400 MB) exceeds the 126 MB L2. Replicas only for --gpus > 1 (every rank prepares its own data)."""
+    import torch.distributed as dist
+    from tradeaid_b200 import lib, data_utils as du
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    M, N = 8, args.rows or 50_000_000
+    params = [["synthetic.csv", i + 1, None, True, None, 2, 10, None, False, f"pct{i}", 0.1, 2.2] if i % 2 else
+              ["synthetic.csv", i + 1, None, False, 2, 1, None, None, False, f"ranged{i}", None, None] for i in range(M)]
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    cols = []
+    for i in range(M):
+        steps = torch.randn(N, dtype=torch.float64, device=dev, generator=g) * (2.0 / N ** 0.5)
+        cols.append((100.0 * (i + 1) * torch.exp(torch.cumsum(steps, 0))).mul(100).round().div(100))
+        del steps
+    tokens = torch.empty(M, N, dtype=torch.int32, device=dev)
+
+    def step():
+        return [du.prepare_modality(cols[i], params[i], tokens_out=tokens[i])[1] for i in range(M)]
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        vocabs = step()
+    lib.reset_launch_count()
+    step()
+    launches_per_step = lib.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = M * N * world / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel: the 8 histogram passes of one radix select (4 order statistics = 2 percentiles)
+    st = torch.empty(lib.PREP_STATUS_WORDS, dtype=torch.int64, device=dev)
+    lib.prep_status_reset(st)
+    ranks = torch.tensor([N // 1000, N // 1000 + 1, N - N // 1000 - 2, N - N // 1000 - 1], dtype=torch.int64, device=dev)
+    osv = torch.empty(4, dtype=torch.float64, device=dev)
+    ws = torch.empty(lib.prep_select_workspace_bytes(), dtype=torch.uint8, device=dev)
+    n_sel = 5
+    for _ in range(2):
+        lib.prep_order_statistics(cols[1], ranks, osv, ws, st)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(n_sel):
+        lib.prep_order_statistics(cols[1], ranks, osv, ws, st)
+    s1.record()
+    torch.cuda.synchronize()
+    sel_ms = s0.elapsed_time(s1) / n_sel
+    sel_gbs = N * 8 * 8 / (sel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "prep_select_hist_kernel x8 + prep_select_pick_kernel x8 (one radix select)",
+                "achieved": sel_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": sel_gbs / pk["hbm"], "traffic": None,
+                "algorithmic_bytes": N * 8 * 8, "ms": sel_ms, "peak_source": f"{pk['source']} (MEASURED_PEAKS.json hbm_gbs)",
+                "note": "8 B/row per pass x 8 passes; ncu of one pass (profiles/r01_prof_dataprep_v3_ncu_full.txt): DRAM read = "
+                        "algorithmic (64.0 MB per 8 M rows); instruction-bound, DESIGN.md section 7"}
+
+    S = min(N, 400_000)
+    sample = [cols[i][:S].cpu().tolist() for i in (0, 1)]       # bounded sample for the CPU baseline
+
+    # end to end from pinned host columns through the drop-in API
+    e2e = None
+    if not args.no_e2e:
+        host_cols = [c.cpu().pin_memory() for c in cols]
+        del cols
+
+        def e2e_step():
+            dcols = [h.to(dev, non_blocking=True) for h in host_cols]
+            tr, va, vo = du.prepare_dataset(dcols, params, [N], validation_size=0.1)
+            return sum(len(v) for v in vo)
+
+        e2e_step()
+        torch.cuda.synchronize()
+        n_e2e = max(2, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": M * N * world * n_e2e / dt, "unit": "rows/s", "h2d_bytes_per_step": M * N * 8,
+               "d2h_bytes_per_step": 8 * sum(len(v) for v in vocabs), "steps": n_e2e,
+               "api": "data_utils.prepare_dataset(pinned host float64 columns -> cudaMemcpyAsync -> K9 kernels -> int32 "
+                      "[M, N] token store, vocabularies read back as python lists)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import dataprep as oracle
+        t0 = time.perf_counter()
+        for i in (0, 1):
+            oracle.prepare_modality(sample[i], params[i])
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": 2 * S / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                        "sample": f"oracle port (oracle/dataprep.py, pure Python like the reference) of both chains on the first "
+                                  f"{S} rows of two modalities ({dt:.1f} s)"}
+    if rank == 0:
+        line = {"metric": "data preparation rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+                "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"prep: raw columns of c4 ({M} modalities x {N} float64 rows), odd modalities percent(2) -> "
+                                       "10 groups per sign (0.1 % band, exponent 2.2), even modalities 2 whole digits / 1 decimal, "
+                                       "then vocabulary -> int32 token store", "modalities": M, "rows": N,
+                           "l2": "every column (8 B/row) is larger than the 126 MB L2", "parallelism": f"replicas x{world}"},
+                "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "vocabulary_sizes": [len(v) for v in vocabs],
+                "hbm_bytes_allocated": torch.cuda.max_memory_allocated(dev)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     from tradeaid_b200 import synthetic as syn
+    if args.config == "prep":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "--config prep is an extra row; its CPU baseline is in the "
+                                                                   "cpu_baseline key of the default arm"}), flush=True)
+            return
+        return run_dataprep(args)
     cfg = syn.CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
