@@ -204,6 +204,11 @@ def test_device_percent_and_bins_against_reference(host, golden):
         host.h_percent(P(x.ctypes.data), ctypes.c_longlong(x.size), ctypes.c_int(2 if c["decimals"] is None else c["decimals"]),
                        P(out.ctypes.data))
         assert same_bits(out, c["y"].numpy()), (c["name"], c["decimals"])
+    # unchanged values (answered without a division): zero of the previous value's sign, like Python's 0.0 / prev
+    x = np.array([3.0, 3.0, -2.0, -2.0, 7.5, 7.5, -1e-300, -1e-300, 4.0], dtype=np.float64)
+    out = np.empty_like(x)
+    host.h_percent(P(x.ctypes.data), ctypes.c_longlong(x.size), ctypes.c_int(2), P(out.ctypes.data))
+    assert same_bits(out, oracle.percent_changes(x.tolist(), 2))
     for c in golden["bin"]:
         x = np.ascontiguousarray(golden["columns"][c["x"]].numpy())
         lo, hi = np.percentile(x, c["outlier"]), np.percentile(x, 100 - c["outlier"])

@@ -248,8 +248,13 @@ TA_HD double range_element(double x, const RangeParams& rp, const double* __rest
 }
 
 // One element of convert_to_percent_changes (data_utils.py:649-657 / file_cache.py:362-377); prev != 0.
+// An unchanged value is common (prices quoted in cents) and a zero numerator sends the device's division down its slow
+// path for the whole warp (ncu: 59 of 177 instructions per row), so it is answered directly: (0.0 / prev) * 100 is a zero
+// of prev's sign, and round() keeps it.
 TA_HD double percent_change(double cur, double prev, const Pow10& P) {
-  return py_round(mul_rn(div_rn(sub_rn(cur, prev), prev), 100.0), P);
+  const double d = sub_rn(cur, prev);
+  if (d == 0.0) return double_of(bits_of(prev) & 0x8000000000000000ull);
+  return py_round(mul_rn(div_rn(d, prev), 100.0), P);
 }
 
 // Group of one value in bin_numeric_data (data_utils.py:527-557): pos = [0, b_1 .. b_G], neg = [-b_G .. -b_1, 0].
