@@ -310,3 +310,85 @@ def test_no_cpu_path():
                  lambda: du.bin_numeric_data([1.0, 2.0], 3), lambda: du.numerical_representation([1.0, 2.0])):
         with pytest.raises(RuntimeError, match="no CPU path"):
             call()
+
+
+# ------------------------------------------------------------------------------------------------ host logic over the CPU emulation
+@pytest.fixture()
+def du_emu():
+    """tradeaid_b200.data_utils with the K9 kernel namespace replaced by tests/emu_prep.py (the kernels' own element
+    arithmetic built for the host + numpy data movement): everything data_utils does on the host runs for real."""
+    import emu_prep
+    from tradeaid_b200 import data_utils as du
+    du._ops_override = emu_prep
+    try:
+        yield du
+    finally:
+        du._ops_override = None
+
+
+def test_host_logic_percent_range_bins_golden(du_emu, golden, capsys):
+    du = du_emu
+    for c in golden["percent"]:
+        x = golden["columns"][c["x"]]
+        y = du.convert_to_percent_changes(x.clone(), c["decimals"], file_lengths=c.get("file_lengths"),
+                                          on_zero=c.get("on_zero", "raise"))
+        assert same_bits(y.numpy(), c["y"].numpy()), (c["name"], c["decimals"])
+    e = golden["errors"]["zero_prev"]
+    with pytest.raises(ZeroDivisionError) as info:
+        du.convert_to_percent_changes(golden["columns"][e["x"]].tolist(), 2)
+    assert str(info.value) == e["message"]
+    for c in golden["range"]:
+        y = du.range_numeric_data(golden["columns"][c["x"]].tolist(), c["whole_digits"], c["decimals"])
+        assert isinstance(y, list) and same_bits(y, c["y"].numpy()), (c["name"], c["whole_digits"], c["decimals"])
+    e = golden["errors"]["range_overflow"]
+    with pytest.raises(OverflowError):
+        du.range_numeric_data(golden["columns"][e["x"]].tolist(), e["whole_digits"], e["decimals"])
+    with pytest.raises(ValueError, match="non-finite value nan at index 1"):
+        du.range_numeric_data([1.0, float("nan"), 2.0], 1, 2)
+    for c in golden["bin"]:
+        y = du.bin_numeric_data(golden["columns"][c["x"]].clone(), c["num_groups"], c["outlier"], c["exponent"], verbose=False)
+        assert y.dtype == torch.int64 and y.tolist() == c["y"].tolist(), (c["name"], c["num_groups"], c["outlier"])
+    e = golden["errors"]["all_filtered"]
+    with pytest.raises(ValueError) as info:
+        du.bin_numeric_data(golden["columns"][e["x"]].tolist(), e["num_groups"], e["outlier"], e["exponent"])
+    assert str(info.value) == e["message"]
+    capsys.readouterr()
+    c = golden["bin"][0]
+    du.bin_numeric_data(golden["columns"][c["x"]].tolist(), c["num_groups"], c["outlier"], c["exponent"])
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip().startswith("Bin")]
+    assert len(lines) == len(set(c["y"].tolist()))
+
+
+def test_host_logic_vocabulary_chain_and_split(du_emu, golden):
+    import emu_prep
+    du = du_emu
+    for c in golden["vocab"]:
+        tok, voc = du.numerical_representation(golden["columns"][c["x"]].clone())
+        assert tok.dtype == torch.int32 and tok.tolist() == c["tokens"].tolist() and voc == c["vocabulary"].tolist(), c["name"]
+    assert du.numerical_representation([3, 1, 2, 3, 1]) == ([2, 0, 1, 2, 0], [1, 2, 3])
+    for c in golden["chain"]:
+        x = golden["columns"][c["x"]]
+        row = torch.full((x.numel(),), -7, dtype=torch.int32)
+        tok, voc = du.prepare_modality(x.tolist(), c["params"], c["file_lengths"], tokens_out=row)
+        assert tok is row and row.tolist() == c["tokens"].tolist(), c["name"]
+        assert [float(v) for v in voc] == c["vocabulary"].tolist()
+        assert all(isinstance(v, int) for v in voc) == c["integer_vocabulary"]
+    # more distinct values than half the first table: one retry with a larger table, same result
+    before = emu_prep.stats["vocab_inserts"]
+    n = 70_000
+    x = torch.from_numpy(np.random.default_rng(0).permutation(n).astype(np.float64) * 0.25 - 100.0)
+    tok, voc = du.numerical_representation(x)
+    assert emu_prep.stats["vocab_inserts"] - before == 2
+    assert len(voc) == n and voc[0] == -100.0 and torch.equal(tok.long(), ((x + 100.0) * 4).long())
+    # all modalities into one [M, N] matrix + the reference's split arithmetic
+    a, b = golden["chain"][0], golden["chain"][3]
+    cols = [golden["columns"][a["x"]].tolist(), golden["columns"][b["x"]].clone()]
+    n = len(cols[0])
+    train, val, vocabs = du.prepare_dataset(cols, [a["params"], b["params"]], [n], validation_size=0.2)
+    cut = int(n * (1 - 0.2))
+    for i, c in enumerate((a, b)):
+        assert train[i].tolist() == c["tokens"].tolist()[:cut] and val[i].tolist() == c["tokens"].tolist()[cut:]
+        assert [float(v) for v in vocabs[i]] == c["vocabulary"].tolist()
+    assert train[0].data_ptr() + 4 * n == train[1].data_ptr()          # rows of one matrix
+    with pytest.raises(ValueError, match="same length"):
+        du.prepare_dataset([[1.0, 2.0], [1.0]], [a["params"], b["params"]], [2])

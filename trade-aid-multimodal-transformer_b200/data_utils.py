@@ -102,12 +102,19 @@ def _group_boundaries(num_groups, exponent, max_abs_value):
 
 
 # ---------------------------------------------------------------------------------------------------- device plumbing
+_ops_override = None   # tests inject a CPU emulation of the kernel namespace (tests/emu_prep.py); the product leaves this None
+
+
 def _ops():
+    if _ops_override is not None:
+        return _ops_override
     from . import lib
     return lib
 
 
 def _device():
+    if _ops_override is not None:
+        return torch.device("cpu")
     if not torch.cuda.is_available():
         raise RuntimeError("tradeaid_b200.data_utils runs on a CUDA device (sm_100a); there is no CPU path — "
                            "use the reference's data_utils on a machine without one.")
@@ -150,7 +157,7 @@ def _is_column(x):
 
 
 def _check_column(x, name):
-    if x.dtype != torch.float64 or x.dim() != 1 or not x.is_cuda:
+    if x.dtype != torch.float64 or x.dim() != 1 or not (x.is_cuda or _ops_override is not None):
         raise TypeError(f"'{name}' as a tensor must be a float64 CUDA tensor of shape [N]")
     if x.numel() == 0:
         raise ValueError(f"'{name}' must be non-empty.")
