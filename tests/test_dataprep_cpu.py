@@ -392,3 +392,16 @@ def test_host_logic_vocabulary_chain_and_split(du_emu, golden):
     assert train[0].data_ptr() + 4 * n == train[1].data_ptr()          # rows of one matrix
     with pytest.raises(ValueError, match="same length"):
         du.prepare_dataset([[1.0, 2.0], [1.0]], [a["params"], b["params"]], [2])
+
+
+def test_reference_demo_columns(du_emu):
+    """BASELINE.json configs[0]: the reference's own demo schemas on its demo_stock.csv (tests/golden/demo_prep.pt, made by
+    the reference's loader + processing functions in main.py's order): vocabulary sizes [57, 3], tokens and vocabularies
+    reproduced by the oracle and by data_utils' host logic over the kernels' arithmetic."""
+    g = load_golden("demo_prep.pt")
+    assert [v.numel() for v in g["vocabulary"]] == [57, 3]
+    for raw, params, tokens, vocabulary in zip(g["raw"], g["params"], g["tokens"], g["vocabulary"]):
+        tok, voc = oracle.prepare_modality(raw.tolist(), params, g["file_lengths"])
+        assert tok == tokens.tolist() and [float(v) for v in voc] == vocabulary.tolist()
+        tok, voc = du_emu.prepare_modality(raw.tolist(), params, g["file_lengths"])
+        assert tok.tolist() == tokens.tolist() and [float(v) for v in voc] == vocabulary.tolist()
