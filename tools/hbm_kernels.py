@@ -87,5 +87,24 @@ kv = torch.randn(G, Bc, cap, 2 * Cc, device=dev).to(torch.bfloat16)
 o = torch.empty(G, Bc, Cc, device=dev, dtype=torch.bfloat16)
 report("attn_decode_kernel<64>", f"G={G} B={Bc} H={H} len={ln}", G * Bc * ln * 2 * Cc * 2,
        timeit(lambda: lib.attention_decode(q[..., :Cc], [kv[..., :Cc]], [kv[..., Cc:]], o, length=ln, H=H, hs=hs)))
+del q, kv, o
+# f-2: the [2]-quirk augmentation of one modality of the resident token store (c4: 45 M training tokens, rand_size 1:
+# 3 candidates -> 2 bits per draw, 4/3 words per accepted draw + slack). Added at the end of round 1: first measured in round 2.
+Nt = 45_000_000 if not ONCE else 8_000_000
+tokens = torch.randint(0, V, (Nt,), device=dev, generator=g, dtype=torch.int32)
+Wn = int(Nt * (4 / 3) * 1.03) + 4096
+words = torch.randint(-2 ** 31, 2 ** 31 - 1, (Wn,), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+aws = torch.empty(lib.augment_workspace_bytes(Nt, Wn), dtype=torch.uint8, device=dev)
+astats = torch.zeros(3, dtype=torch.int64, device=dev)
+report("aug_count/scan/compact/apply (ta_augment_tokens)", f"N={Nt} W={Wn}", 2 * (4 * Wn + 4 * Nt) + 4 * Nt + Wn,
+       timeit(lambda: lib.augment_tokens(tokens, words, 1, V, aws, astats), n=5))
+del tokens, words, aws
+# f-1: directional metrics of one evaluation batch (B = 64 last-position rows x V logits): launch-latency sized
+Bm = 64
+lg = torch.randn(Bm, V, device=dev); vv = torch.linspace(-5, 5, V, dtype=torch.float64, device=dev)
+pt = torch.randint(0, V, (Bm,), device=dev, generator=g); at = torch.randint(0, V, (Bm,), device=dev, generator=g)
+cnt = torch.zeros(2, dtype=torch.int64, device=dev); cert = torch.zeros(1, dtype=torch.float64, device=dev)
+report("directional_metrics_kernel", f"B={Bm} V={V}", Bm * V * 4 + V * 8 + Bm * 16,
+       timeit(lambda: lib.directional_metrics(lg, vv, pt, at, False, cnt, cert)))
 if len(sys.argv) > 1:
     json.dump(out, open(sys.argv[1], "w"), indent=1)
