@@ -97,3 +97,89 @@ def test_gradient_buckets_partition_the_active_parameters():
             if off < eng.layout.n_active:
                 want[off:off + n] = 1
         assert torch.equal(cover, want)
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel evaluation
+class _OracleModel:
+    """Stand-in for the nn.Module in training_utils.m: the oracle forward on CPU (estimate_loss only calls it, eval(), train())."""
+
+    def __init__(self):
+        from oracle import restatement as R
+        self.R = R
+        self.cfg = R.Cfg(8, 32, 2, 2, [24, 10, 20], [True, False, True])
+        self.sd = R.random_state_dict(self.cfg, seed=5)
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    def train(self):
+        self.training = True
+
+    def __call__(self, xb, yb):
+        return self.R.forward(self.sd, self.cfg, xb, yb)
+
+
+def _eval_setup(pg):
+    _setup_paths()
+    import emu_ops
+    from tradeaid_b200 import training_utils as tu
+    gen = torch.Generator().manual_seed(31)
+    V = [24, 10, 20]
+    full = [torch.randint(0, v, (300,), generator=gen) for v in V]
+    tu.configure(device="cpu", batch_size=4, block_size=8, eval_iters=5)
+    tu._ops_override = emu_ops
+    tu._stores.clear()
+    tu.all_train_sets = [d[:-60].tolist() for d in full]
+    tu.all_val_sets = [d[-60:].clone() for d in full]
+    tu.all_vocabularies = [[0.5 * k - 4.0 for k in range(V[0])], [float(k - 2) for k in range(V[1])], [f"s{k}" for k in range(V[2])]]
+    tu.all_modality_params = [["s", i, None, i == 1, None, None, None, None, False, f"m{i}"] for i in range(3)]
+    tu.file_lengths = [300]
+    tu.num_modalities = 3
+    tu.is_percents = False
+    tu.m = _OracleModel()
+    tu.eval_process_group = pg
+    torch.manual_seed(77)            # every rank: the same host index stream (SURVEY.md 8e, parity mode)
+    return tu
+
+
+def _eval_worker(rank, world, port, out_dir):
+    import contextlib
+    import io
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tu = _eval_setup(dist.group.WORLD)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = tu.estimate_loss(3, 10)
+    after = int(torch.randint(0, 2 ** 31 - 1, (1,)))          # position of the host RNG stream after the evaluation
+    torch.save({"out": out, "printed": buf.getvalue(), "rng_after": after, "training": tu.m.training},
+               os.path.join(out_dir, f"eval_{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_evaluation_equals_single_process(tmp_path, capsys):
+    """estimate_loss with eval_process_group: iterations dealt round-robin, one all-reduce of the totals — same directional
+    counts, same mean loss (float64 sum order), same host RNG position as the single-process evaluation; rank 0 alone prints."""
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_eval_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [torch.load(str(tmp_path / f"eval_{r}.pt")) for r in range(2)]
+    tu = _eval_setup(None)
+    try:
+        want = tu.estimate_loss(3, 10)
+        want_after = int(torch.randint(0, 2 ** 31 - 1, (1,)))
+        printed = capsys.readouterr().out
+    finally:
+        tu._ops_override = None
+        tu._stores.clear()
+        tu.m = None
+        tu.eval_process_group = None
+    strip = lambda text: [ln for ln in text.splitlines() if not ln.startswith("Evaluation:")]     # (the header has a clock)
+    assert strip(got[0]["printed"]) == strip(printed) and "DIRECTIONAL METRICS - Val Set" in printed
+    assert got[1]["printed"] == ""
+    for r in range(2):
+        assert got[r]["rng_after"] == want_after and got[r]["training"]
+        for split in ("train", "val"):
+            assert abs(got[r]["out"][split] - want[split]) <= 1e-12 * abs(want[split])
+    assert got[0]["out"] == got[1]["out"]

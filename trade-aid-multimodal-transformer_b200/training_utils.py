@@ -145,28 +145,62 @@ def calculate_evaluation_metrics(logits_list, xb_list, yb_list, num_modalities, 
     return [r[0] for r in c], [r[1] for r in c], [float(x) for x in ce], [min(p, 1) for p in processed]
 
 
+eval_process_group = None   # data-parallel runs set this (torch.distributed group): see estimate_loss
+
+
+def _all_reduce_eval(pg, dev, loss_sum, n_losses, counts, cert, tot_proc):
+    """Sum of the per-rank evaluation totals: ONE all-reduce of 2 + 4M float64 scalars (loss sum, number of losses; per
+    modality wins, losses, certainty mass, batches processed) - SURVEY.md 8e. Counts are exact in float64 (< 2^53)."""
+    import torch.distributed as dist
+    M = num_modalities
+    pack = torch.zeros(2 + 4 * M, dtype=torch.float64, device=dev)
+    pack[0], pack[1] = loss_sum, n_losses
+    if counts is not None:
+        pack[2:2 + 2 * M] = counts.to(torch.float64).reshape(-1)
+        pack[2 + 2 * M:2 + 3 * M] = cert
+    pack[2 + 3 * M:] = torch.tensor(tot_proc, dtype=torch.float64)
+    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=pg)
+    host = pack.tolist()
+    counts_h = [[int(host[2 + 2 * i]), int(host[3 + 2 * i])] for i in range(M)]
+    return host[0], int(host[1]), counts_h, host[2 + 2 * M:2 + 3 * M], [int(v) for v in host[2 + 3 * M:]]
+
+
 def estimate_loss(current_step=None, max_steps=None):
     """training_utils.py:387-520: eval_iters batches of each split through the model in eval mode; mean summed loss,
-    directional metrics, same console and log-file lines."""
+    directional metrics, same console and log-file lines.
+    Data parallel (`eval_process_group` set): the eval_iters iterations are dealt round-robin to the ranks.
+    EVERY rank still draws every batch (get_batch is a host index draw + one gather launch), so the identically seeded host
+    RNG streams stay in step and the union of the evaluated batches is exactly the single-process set; the forward and the
+    metrics run only on the owner. The totals are summed with one all-reduce per split: counts are identical to the
+    single-process run, the mean loss up to the order of a float64 sum. Rank 0 prints and writes the log lines."""
     out = {}
     m.eval()
     eval_iters, batch_size = _get('eval_iters'), _get('batch_size')
+    pg = eval_process_group
+    if pg is not None:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+    else:
+        world, rank = 1, 0
+    say = print if rank == 0 else (lambda *a, **k: None)
     for state in ['train', 'val']:
         current_time = datetime.now().strftime("%H:%M:%S")
         step_info = f'Step {current_step}/{max_steps} | ' if current_step is not None else ''
         batch_calc = f' * {batch_size} batches = {eval_iters * batch_size} samples'
-        print(f'Evaluation: {step_info}{state.title()} set ({eval_iters} iterations{batch_calc}) | {current_time}')
+        say(f'Evaluation: {step_info}{state.title()} set ({eval_iters} iterations{batch_calc}) | {current_time}')
         tot_proc = [0] * num_modalities
         counts = cert = None
         total_losses = []
         for k in range(eval_iters):
             xb_list, yb_list = get_batch(state, 0)
+            if k % world != rank:
+                continue
             with torch.no_grad():
                 logits_list, losses_list = m(xb_list, yb_list)
             if losses_list and all(l is not None for l in losses_list):
                 total_losses.append(sum(losses_list).detach())
             else:
-                print(f"Warning: Iteration {k} losses not calculated, skipping")
+                say(f"Warning: Iteration {k} losses not calculated, skipping")
             if counts is None:   # device accumulators: one read-back per split instead of B*V .item() calls per batch
                 dev = logits_list[0].device
                 counts = torch.zeros(num_modalities, 2, dtype=torch.int64, device=dev)
@@ -174,11 +208,19 @@ def estimate_loss(current_step=None, max_steps=None):
             _accumulate_metrics(logits_list, xb_list, yb_list, num_modalities, all_vocabularies, all_modality_params,
                                 counts, cert, tot_proc)
         total_losses = torch.stack(total_losses).tolist() if total_losses else []
-        c = counts.tolist() if counts is not None else [[0, 0]] * num_modalities
+        if world > 1:
+            dev = torch.device(_get('device'))
+            loss_sum, n_losses, c, tot_cert, tot_proc = _all_reduce_eval(pg, dev, sum(total_losses), len(total_losses), counts,
+                                                                         cert, tot_proc)
+            out[state] = loss_sum / n_losses if n_losses else float('nan')
+        else:
+            c = counts.tolist() if counts is not None else [[0, 0]] * num_modalities
+            tot_cert = cert.tolist() if cert is not None else [0.0] * num_modalities  # noqa: F841 (reference keeps it too)
+            out[state] = sum(total_losses) / len(total_losses) if total_losses else float('nan')
         tot_ok, tot_bad = [r[0] for r in c], [r[1] for r in c]
-        tot_cert = cert.tolist() if cert is not None else [0.0] * num_modalities  # noqa: F841 (reference keeps it too)
-        out[state] = sum(total_losses) / len(total_losses) if total_losses else float('nan')
         disp = 'Train Set' if state == 'train' else 'Val Set'
+        if rank != 0:
+            continue
         print(f"\nDIRECTIONAL METRICS - {disp} (Correct/Total)")
         for i in range(num_modalities):
             name = all_modality_params[i][9] if all_modality_params[i][9] else f"Modality {i+1}"
