@@ -103,6 +103,49 @@ def test_get_batch_bit_exact_through_module_globals():
         tu._stores.clear()
 
 
+def test_get_batch_parity_mode_shards_concatenate_to_the_reference_batch():
+    """Data-parallel parity mode: with batch_shard = (rank, world) every rank draws the SAME indices as the
+    single-process reference (same RNG consumption) and gathers its slice of the rows; the slices concatenate to the
+    reference's batch (the golden get_batch trace) for every world size that divides the batch."""
+    from tradeaid_b200 import training_utils as tu
+    g = load_golden("get_batch.pt")
+    full, n_val, B = g["full"], g["n_val"], g["batch_size"]
+    tu.configure(device="cpu", batch_size=B, block_size=g["block_size"], eval_iters=2)
+    tu._ops_override = emu_ops
+    tu.all_train_sets = [d[:-n_val].tolist() for d in full]
+    tu.all_val_sets = [d[-n_val:].clone() for d in full]
+    tu.all_vocabularies = [[float(k) for k in range(50)]] * 3
+    tu.all_modality_params = [["s", i, None, False, None, None, None, None, False, f"m{i}"] for i in range(3)]
+    tu.file_lengths = g["file_lengths"]
+    tu.num_modalities = 3
+    tu.is_percents = False
+    try:
+        worlds = [w for w in (1, 2, 4) if B % w == 0]
+        assert len(worlds) >= 2
+        for world in worlds:
+            parts = []
+            for rank in range(world):
+                tu._stores.clear()
+                tu.batch_shard = (rank, world)
+                torch.manual_seed(g["seed"])
+                parts.append([tu.get_batch(call["split"], 1) for call in g["calls"]])
+                after = int(torch.randint(0, 2 ** 31 - 1, (1,)))
+                if rank == 0:
+                    first_after = after
+                assert after == first_after                       # every rank leaves the host generator at the same place
+            for c, call in enumerate(g["calls"]):
+                for i in range(3):
+                    assert torch.equal(torch.cat([parts[r][c][0][i] for r in range(world)]), call["xb"][i])
+                    assert torch.equal(torch.cat([parts[r][c][1][i] for r in range(world)]), call["yb"][i])
+        tu.batch_shard = (0, B + 1)
+        with pytest.raises(ValueError, match="must be divisible"):
+            tu.get_batch("train", 0)
+    finally:
+        tu.batch_shard = None
+        tu._ops_override = None
+        tu._stores.clear()
+
+
 def test_directional_metrics_match_reference():
     from tradeaid_b200 import training_utils as tu
     g = load_golden("metrics.pt")

@@ -60,8 +60,15 @@ def _store(split):
     return ent[1]
 
 
+batch_shard = None   # (rank, world) in data-parallel PARITY mode; None: every process draws its own batches
+
+
 def get_batch(split, is_training):
-    """training_utils.py:333-384. Returns (xb_list, yb_list): per modality int64 [batch_size, block_size] on `device`."""
+    """training_utils.py:333-384. Returns (xb_list, yb_list): per modality int64 [batch_size, block_size] on `device`.
+    With `batch_shard = (rank, world)` (data-parallel parity mode, fixed GLOBAL batch_size): every rank draws the same
+    batch_size indices from its identically seeded host generator - the CPU RNG stream stays bit-identical to the
+    single-process reference - and gathers only rows [rank*B/world, (rank+1)*B/world); the shards of all ranks
+    concatenate to the single-process batch."""
     train_store = _store('train')
     for r in range(num_modalities):
         this_rand_size = all_modality_params[r][2]
@@ -76,6 +83,11 @@ def get_batch(split, is_training):
     store = train_store if split == 'train' else _store('val')
     T, B = _get('block_size'), _get('batch_size')
     ix = generate_batch_starting_indices(store.N, T, B, split, file_lengths, is_percents)
+    if batch_shard is not None:
+        rank, world = batch_shard
+        if B % world != 0:
+            raise ValueError(f"batch_size ({B}) must be divisible by the number of data-parallel ranks ({world})")
+        ix = ix[rank * (B // world):(rank + 1) * (B // world)]
     xb, yb = store.gather(ix, T)
     return [xb[r] for r in range(num_modalities)], [yb[r] for r in range(num_modalities)]
 
