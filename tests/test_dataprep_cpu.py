@@ -405,3 +405,36 @@ def test_reference_demo_columns(du_emu):
         assert tok == tokens.tolist() and [float(v) for v in voc] == vocabulary.tolist()
         tok, voc = du_emu.prepare_modality(raw.tolist(), params, g["file_lengths"])
         assert tok.tolist() == tokens.tolist() and [float(v) for v in voc] == vocabulary.tolist()
+
+
+def test_token_store_cache_round_trip(tmp_path):
+    """save_token_store / load_token_store (row f-4's binary cache): tokens, vocabularies (doubles bit for bit, group
+    numbers as ints, strings), parameters and file lengths come back unchanged; corruption and truncation are detected."""
+    from tradeaid_b200 import data_utils as du
+    g = torch.Generator().manual_seed(2)
+    tokens = torch.randint(0, 1000, (3, 5000), generator=g, dtype=torch.int32)
+    vocabs = [[0.1 * k - 3.0 for k in range(1000)] + [-0.0, 1e-300, 123456789.125], list(range(-8, 9)), [f"sym{k}" for k in range(5)]]
+    params = [["a.csv", 1, True, True, None, 2, 8, None, False, "pct", 0.1, 2.2], ["a.csv", 2, True, False, 2, 1, None, None, True, "rng", None, None],
+              ["a.csv", 3, True, False, None, None, None, None, False, "sym", None, None]]
+    path = str(tmp_path / "store.tatok")
+    du.save_token_store(path, tokens, vocabs, params, [2000, 3000])
+    tok, voc, prm, lens = du.load_token_store(path, device="cpu")
+    assert tok.dtype == torch.int32 and torch.equal(tok, tokens) and prm == params and lens == [2000, 3000]
+    assert voc[1] == vocabs[1] and all(isinstance(v, int) for v in voc[1]) and voc[2] == vocabs[2]
+    assert same_bits(voc[0], vocabs[0])
+    du.save_token_store(path, [tokens[i] for i in range(3)], vocabs, params, [5000])        # rows instead of the matrix
+    assert torch.equal(du.load_token_store(path, device="cpu")[0], tokens)
+    with pytest.raises(ValueError, match="Sum of file_lengths"):
+        du.save_token_store(path, tokens, vocabs, params, [1, 2])
+    raw = bytearray(open(path, "rb").read())
+    raw[-5] ^= 0x40
+    open(path, "wb").write(raw)
+    with pytest.raises(ValueError, match="checksum"):
+        du.load_token_store(path, device="cpu")
+    assert du.load_token_store(path, device="cpu", verify=False)[0].shape == (3, 5000)
+    open(path, "wb").write(raw[:-8])
+    with pytest.raises(ValueError, match="truncated"):
+        du.load_token_store(path, device="cpu")
+    open(path, "wb").write(b"not a cache file at all")
+    with pytest.raises(ValueError, match="not a tradeaid_b200"):
+        du.load_token_store(path, device="cpu")

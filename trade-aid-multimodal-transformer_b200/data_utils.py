@@ -469,3 +469,68 @@ def prepare_dataset(columns, all_modality_params, file_lengths, validation_size=
         train.append(tr)
         val.append(va)
     return train, val, vocabularies
+
+
+# ---------------------------------------------------------------------------------------------------- token-store cache
+# SURVEY.md 8 row f-4, second half: a prepared dataset is written once and mapped back on later runs, so that a 50 M-row
+# run neither repeats the preparation nor builds Python lists. Layout (little endian):
+#   bytes 0..7    magic  b"TATOKEN1"
+#   bytes 8..15   uint64 length H of the JSON header
+#   bytes 16..    JSON header: modalities M, rows N, file_lengths, all_modality_params, vocabularies (Python's float repr
+#                 round-trips doubles exactly; group numbers stay ints), crc32 of the payload
+#   then zero padding to a multiple of 4096 and the payload: int32 [M, N] row-major - the TokenStore matrix itself.
+_TOKEN_MAGIC = b"TATOKEN1"
+_TOKEN_ALIGN = 4096
+
+
+def save_token_store(path, tokens, vocabularies, all_modality_params, file_lengths):
+    """tokens: int32 [M, N] tensor (any device) or the list of its rows (e.g. prepare_dataset's train + val views are NOT
+    the full rows - pass the matrix or full rows); vocabularies / all_modality_params / file_lengths as main.py holds them."""
+    import json
+    import zlib
+    if not torch.is_tensor(tokens):
+        tokens = torch.stack([t if torch.is_tensor(t) else torch.tensor(t, dtype=torch.int32) for t in tokens])
+    if tokens.dim() != 2 or tokens.dtype != torch.int32:
+        raise TypeError("tokens must be an int32 [M, N] matrix")
+    if len(vocabularies) != tokens.shape[0] or len(all_modality_params) != tokens.shape[0]:
+        raise ValueError("one vocabulary and one parameter list per modality")
+    if sum(file_lengths) != tokens.shape[1]:
+        raise ValueError(f"Sum of file_lengths ({sum(file_lengths)}) does not match the number of rows ({tokens.shape[1]}).")
+    payload = tokens.contiguous().cpu().numpy().astype("<i4", copy=False)
+    header = json.dumps({"modalities": int(tokens.shape[0]), "rows": int(tokens.shape[1]),
+                         "file_lengths": [int(v) for v in file_lengths], "all_modality_params": [list(p) for p in all_modality_params],
+                         "vocabularies": [list(v) for v in vocabularies], "crc32": zlib.crc32(payload.tobytes()) & 0xFFFFFFFF},
+                        allow_nan=False).encode("utf-8")
+    start = -(-(16 + len(header)) // _TOKEN_ALIGN) * _TOKEN_ALIGN
+    tmp = f"{path}.tmp"
+    with open(tmp, "wb") as f:
+        f.write(_TOKEN_MAGIC)
+        f.write(len(header).to_bytes(8, "little"))
+        f.write(header)
+        f.write(b"\0" * (start - 16 - len(header)))
+        payload.tofile(f)
+    import os
+    os.replace(tmp, path)          # a reader never sees a half-written cache
+
+
+def load_token_store(path, device=None, verify=True):
+    """Returns (tokens int32 [M, N] on `device` (default: the current CUDA device), vocabularies, all_modality_params,
+    file_lengths). The payload is memory-mapped and copied to the device in one transfer; verify=True checks its crc32."""
+    import json
+    import zlib
+    with open(path, "rb") as f:
+        if f.read(8) != _TOKEN_MAGIC:
+            raise ValueError(f"{path} is not a tradeaid_b200 token-store cache")
+        hlen = int.from_bytes(f.read(8), "little")
+        header = json.loads(f.read(hlen).decode("utf-8"))
+    M, N = header["modalities"], header["rows"]
+    start = -(-(16 + hlen) // _TOKEN_ALIGN) * _TOKEN_ALIGN
+    import os
+    if os.path.getsize(path) != start + 4 * M * N:
+        raise ValueError(f"{path}: truncated or oversized payload (expected {start + 4 * M * N} bytes)")
+    payload = np.memmap(path, dtype="<i4", mode="r", offset=start, shape=(M, N))
+    if verify and (zlib.crc32(payload.tobytes()) & 0xFFFFFFFF) != header["crc32"]:
+        raise ValueError(f"{path}: payload checksum mismatch")
+    dev = torch.device(device) if device is not None else _device()
+    tokens = torch.from_numpy(np.array(payload, dtype=np.int32)).to(dev)     # (a private copy: the mapping is read-only)
+    return tokens, header["vocabularies"], header["all_modality_params"], header["file_lengths"]
