@@ -390,6 +390,8 @@ def test_host_logic_vocabulary_chain_and_split(du_emu, golden):
         assert train[i].tolist() == c["tokens"].tolist()[:cut] and val[i].tolist() == c["tokens"].tolist()[cut:]
         assert [float(v) for v in vocabs[i]] == c["vocabulary"].tolist()
     assert train[0].data_ptr() + 4 * n == train[1].data_ptr()          # rows of one matrix
+    matrix = du.prepare_dataset(cols, [a["params"], b["params"]], [n], validation_size=0.2, return_matrix=True)[3]
+    assert matrix.shape == (2, n) and matrix[0].tolist() == a["tokens"].tolist() and matrix[1].tolist() == b["tokens"].tolist()
     with pytest.raises(ValueError, match="same length"):
         du.prepare_dataset([[1.0, 2.0], [1.0]], [a["params"], b["params"]], [2])
 

@@ -444,13 +444,15 @@ def prepare_modality(column, modality_params, file_lengths=None, tokens_out=None
     return numerical_representation(x, tokens_out=tokens_out, integer_vocabulary=binned)
 
 
-def prepare_dataset(columns, all_modality_params, file_lengths, validation_size=0.1, num_validation_files=0, verbose=False):
+def prepare_dataset(columns, all_modality_params, file_lengths, validation_size=0.1, num_validation_files=0, verbose=False,
+                    return_matrix=False):
     """All modalities of a run: what main.py builds between loading and training (main.py:100-210, 270-396), with the
     tokens kept in ONE int32 [M, N] device matrix — the layout of the feeder's TokenStore.
     columns: per modality a list of numbers or a float64 CUDA tensor [N] (raw values, files concatenated in order).
     Returns (all_train_sets, all_val_sets, all_vocabularies): per modality VIEWS of the matrix rows split as
     create_train_val_datasets splits them, and the vocabularies as Python lists — assign them to
-    tradeaid_b200.training_utils' globals of the same names; get_batch then gathers straight from HBM."""
+    tradeaid_b200.training_utils' globals of the same names; get_batch then gathers straight from HBM.
+    return_matrix=True appends the [M, N] matrix itself (what save_token_store takes)."""
     M = len(columns)
     if M == 0 or len(all_modality_params) != M:
         raise ValueError("columns and all_modality_params must list the same, non-zero number of modalities")
@@ -468,7 +470,7 @@ def prepare_dataset(columns, all_modality_params, file_lengths, validation_size=
         tr, va = create_train_val_datasets(tokens[i], validation_size, num_validation_files, list(file_lengths))
         train.append(tr)
         val.append(va)
-    return train, val, vocabularies
+    return (train, val, vocabularies, tokens) if return_matrix else (train, val, vocabularies)
 
 
 # ---------------------------------------------------------------------------------------------------- token-store cache
