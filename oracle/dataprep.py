@@ -97,12 +97,13 @@ def vocabulary_tokens(data):
     return [index[v] for v in data], vocabulary
 
 
-def prepare_modality(column, params, file_lengths=None):
-    """The per-modality chain of main.py:100-210 + :278 on the legacy parameter list (schema.py:213-248)."""
+def prepare_modality(column, params, file_lengths=None, on_zero="keep"):
+    """The per-modality chain of main.py:100-210 + :278 on the legacy parameter list (schema.py:213-248). main.py loads
+    through file_cache.load_file_data_cached, whose percent conversion keeps 0.0 after a zero (on_zero='keep')."""
     p = list(params) + [None] * (12 - len(params))
     x = list(column)
     if p[3] is True:
-        x = percent_changes_by_file(x, file_lengths or [len(x)], p[5] if p[5] else 2)
+        x = percent_changes_by_file(x, file_lengths or [len(x)], p[5] if p[5] else 2, on_zero)
     if p[4] is not None or p[5] is not None:
         x = range_values(x, p[4], p[5])
     if p[6] is not None:

@@ -373,6 +373,14 @@ def test_host_logic_vocabulary_chain_and_split(du_emu, golden):
         assert tok is row and row.tolist() == c["tokens"].tolist(), c["name"]
         assert [float(v) for v in voc] == c["vocabulary"].tolist()
         assert all(isinstance(v, int) for v in voc) == c["integer_vocabulary"]
+    # a zero inside a percent modality: main.py's loader keeps 0.0 (default), data_utils' loader raises
+    zc = [5.0, 0.0, 3.0, 3.3, 0.0, 0.0, 1.0]
+    zp = ["f", 1, None, True, None, 2, None, None, False, "z", None, None]
+    tok, voc = du.prepare_modality(zc, zp)
+    want_tok, want_voc = oracle.prepare_modality(zc, zp)
+    assert tok.tolist() == want_tok and voc == want_voc and 0.0 in voc
+    with pytest.raises(ZeroDivisionError, match="previous value is zero at index 1"):
+        du.prepare_modality(zc, zp, on_zero="raise")
     # more distinct values than half the first table: one retry with a larger table, same result
     before = emu_prep.stats["vocab_inserts"]
     n = 70_000

@@ -199,8 +199,11 @@ def convert_to_percent_changes(data, decimal_places=2, file_lengths=None, on_zer
     ops.prep_percent_changes(x, out, starts, decimal_places, st.words)
     nonfinite, zero_prev, _, _ = st.read()
     st.raise_nonfinite(nonfinite, x)
-    if zero_prev is not None and on_zero == "raise":
-        raise ZeroDivisionError(f"Cannot calculate percentage change: previous value is zero at index {zero_prev}.")
+    if zero_prev is not None:
+        if on_zero == "raise":
+            raise ZeroDivisionError(f"Cannot calculate percentage change: previous value is zero at index {zero_prev}.")
+        print(f"Warning: Zero value found (first at index {zero_prev}) causes division by zero. "
+              f"Using 0.0% change for the rows that follow a zero.")       # file_cache.py:367-370 prints one line per row
     return out.tolist() if as_list else out
 
 
@@ -423,17 +426,20 @@ def create_train_val_datasets(numeric_rep_data, val_size, num_val_files, file_le
 
 
 # ---------------------------------------------------------------------------------------------------- the chain
-def prepare_modality(column, modality_params, file_lengths=None, tokens_out=None, verbose=False):
+def prepare_modality(column, modality_params, file_lengths=None, tokens_out=None, verbose=False, on_zero="keep"):
     """Raw column -> tokens, the steps main.py applies to one modality (main.py:100-210, 278) in the reference's order:
     percent changes (params[3]; per file, data_utils.py:148), ranging (params[4], params[5]), binning (params[6];
     outlier percentile params[10] default 0.1, exponent params[11] default 2.2, main.py:170-175), vocabulary.
     column: list of numbers or float64 CUDA tensor [N]. modality_params: the reference's legacy list (schema.py:213-248).
+    on_zero: what a zero previous value does to the percent change - "keep" (default) is main.py's own loader,
+    file_cache.load_file_data_cached (file_cache.py:366-372: 0.0 and a warning); "raise" is data_utils.load_file_data's
+    ZeroDivisionError (data_utils.py:148-153).
     Returns (int32 device tokens [N], vocabulary list). Intermediate columns stay in HBM."""
     x = _upload(column) if not _is_column(column) else _check_column(column, "column")
     p = list(modality_params) + [None] * (12 - len(modality_params))
     is_percent, whole_digits, dec_places, num_bins = p[3], p[4], p[5], p[6]
     if is_percent is True:
-        x = convert_to_percent_changes(x, dec_places if dec_places else 2, file_lengths=file_lengths)
+        x = convert_to_percent_changes(x, dec_places if dec_places else 2, file_lengths=file_lengths, on_zero=on_zero)
     if whole_digits is not None or dec_places is not None:
         x = range_numeric_data(x, whole_digits, dec_places)
     binned = num_bins is not None
