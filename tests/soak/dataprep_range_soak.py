@@ -1,8 +1,8 @@
 """Offline soak of the kernels' ranging arithmetic (range_element, built for the host) against the oracle restatement of
 range_numeric_data: 2.7 M values per seed over 9 (whole digits, decimals) settings. Same harness as dataprep_round_soak.py.
-usage: dataprep_range_soak.py <seed>      (round 1: seeds 5-6, 5.4e6 values, 0 mismatches)"""
+usage: tests/soak/dataprep_range_soak.py <seed>      (round 1: seeds 5-6, 5.4e6 values, 0 mismatches)"""
 import ctypes, sys, numpy as np
-import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import dataprep as O
 from tradeaid_b200 import data_utils as du
 L = ctypes.CDLL("/tmp/t/libdph.so"); P = ctypes.c_void_p

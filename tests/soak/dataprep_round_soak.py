@@ -1,7 +1,7 @@
 """Offline soak of the kernels' exact round (csrc/dataprep_math.cuh py_round, built for the host) against CPython round():
 18 M values per seed over ndigits 0..12 (uniform, exact binary ties, decimal half-way cases, 24 decades). Build the harness
 first:  g++ -O2 -ffp-contract=off -shared -fPIC -o /tmp/t/libdph.so tests/host_harness/dataprep_host.cpp
-usage: dataprep_round_soak.py <seed>      (round 1: seeds 1-3, 5.4e7 values, 0 mismatches)"""
+usage: tests/soak/dataprep_round_soak.py <seed>      (round 1: seeds 1-3, 5.4e7 values, 0 mismatches)"""
 import ctypes, random, struct, numpy as np, sys
 L = ctypes.CDLL("/tmp/t/libdph.so"); P = ctypes.c_void_p
 rng = np.random.default_rng(int(sys.argv[1]))

@@ -1,5 +1,7 @@
 import sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from tradeaid_b200.engine import Engine, KVCache
 from tradeaid_b200.params import Dims
 from oracle import restatement as R

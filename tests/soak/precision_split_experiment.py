@@ -2,10 +2,10 @@
 (2 modalities with cross-attention, C=256, H=8, L=4, T=64, B=8, random init): bf16 everywhere vs fp32 GEMM operands with bf16
 attention vs split (hi+lo bf16) GEMM operands in the K-concatenated 3-term form the existing tcgen05 kernel can run.
 Round-1 result: 5.3e-3 / 2.7e-4 / A-only 3.7e-3, B-only 3.8e-3, both 2.7e-4 (normwise, vs the fp32 oracle).
-usage: python tools/precision_split_experiment.py"""
+usage: python tests/soak/precision_split_experiment.py      (test infrastructure: imports the oracle)"""
 import os
 import sys, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import emu_ops
 from oracle import restatement as R

@@ -200,7 +200,7 @@ def test_stage2_blockdiag_is_bit_identical_to_per_head_groups(C, H, monkeypatch)
 @pytest.mark.parametrize("M,cross,V,B,T,C,H,L,n0,scale", [
     (3, [True, False, True], [100, 64, 80], 3, 48, 128, 4, 2, 17, 3.0),
     # c5 widths (C=768, H=12), three query tiles. Weights at their init scale: at 3x both the decode path and the full
-    # forward sit 2-5e-2 from the fp32 oracle (bf16 noise amplified; tools/kv_diag.py), so they are 2-4e-2 apart
+    # forward sit 2-5e-2 from the fp32 oracle (bf16 noise amplified; tests/soak/kv_diag.py), so they are 2-4e-2 apart
     (4, [True, False, False, True], [64, 64, 64, 64], 2, 300, 768, 12, 1, 290, 1.0),
     (1, [False], [50], 2, 16, 64, 2, 2, 1, 3.0),
 ])

@@ -1,8 +1,8 @@
 """Row f-4 (one-shot data preparation): every K9 kernel timed alone with CUDA events on a column of c4's size
 (50 M float64 rows = 400 MB, larger than the 126 MB L2, so successive launches read from HBM), achieved GB/s =
 ALGORITHMIC bytes / launch time next to the measured copy bandwidth (MEASURED_PEAKS.json); then the whole chain
-(percent -> range -> bin -> vocabulary -> tokens) end to end from a HOST column (H2D inside the timed region), and the
-CPU baseline: the oracle's pure-Python restatement of the reference chain on a bounded sample of the same column.
+(percent -> range -> bin -> vocabulary -> tokens) end to end from a HOST column (H2D inside the timed region). The CPU
+baseline beside it is bench.py --config prep's cpu_baseline (round-1 artefacts r01_dataprep_v1..v6 still carry one).
 DATAPREP_ONCE=1 runs each kernel once (ncu target).          usage: dataprep_time.py [out.json] [rows]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -91,18 +91,9 @@ if not ONCE:
     chain(); torch.cuda.synchronize()
     t0 = time.perf_counter(); tok, vocab = chain(); torch.cuda.synchronize(); t1 = time.perf_counter()
     e2e_s = t1 - t0
-    # CPU baseline: oracle (pure-Python port of the reference chain) on a bounded sample of the same column
-    sys.path.insert(0, ROOT)
-    from oracle import dataprep as oracle
-    S = min(N, 400_000)
-    sample = host_col[:S].tolist()
-    t0 = time.perf_counter(); otok, ovoc = oracle.prepare_modality(sample, params); t1 = time.perf_counter()
-    cpu_rows_s = S / (t1 - t0)
     summary = dict(chain="percent(2) -> bin(10 groups, 0.1 %, 2.2) -> vocabulary -> int32 tokens", rows=N,
                    e2e_seconds=round(e2e_s, 4), e2e_rows_per_s=round(N / e2e_s), h2d_bytes=N * 8, vocabulary_size=len(vocab),
-                   cpu_baseline=dict(kind="port", cores=1, sample=f"first {S} rows of the same column", rows_per_s=round(cpu_rows_s),
-                                     seconds=round(t1 - t0, 2)))
-    # the sample is a prefix: its percentile band differs from the full column's, so only the first steps are comparable
+                   cpu_baseline="see bench.py --config prep (the oracle is imported by tests/, smoke() and bench.py only)")
     print(json.dumps(summary), flush=True)
     out.append(summary)
 if len(sys.argv) > 1:
