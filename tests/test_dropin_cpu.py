@@ -76,6 +76,34 @@ def test_indices_bit_exact_product_side():
         generate_batch_starting_indices(20, 8, 4, "train", [5, 5, 5, 5], False)
 
 
+def test_indices_randomised_against_oracle():
+    """600 random configurations (files, split, is_percents, sizes down to the error cases): the product feeder and the
+    oracle restatement give the same indices, leave the torch CPU generator at the same position and raise the same
+    errors. (tests/soak/index_soak_vs_reference.py runs the same comparison against the reference itself, offline.)"""
+    import random
+    from oracle import restatement as R
+    from tradeaid_b200.feeder import generate_batch_starting_indices as ours
+    rng = random.Random(5)
+    seen = {"ok": 0, "err": 0}
+    for trial in range(600):
+        lens = [rng.randint(5, 400) for _ in range(rng.choice([1, 1, 2, 3, 5, 8]))]
+        split = rng.choice(["train", "val"])
+        frac = rng.uniform(0.05, 0.95)
+        data_size = max(2, int(sum(lens) * (frac if split == "train" else 1 - frac)))
+        T, B, pct, seed = rng.choice([2, 4, 8, 16, 64]), rng.choice([1, 3, 16]), rng.random() < 0.5, rng.randint(0, 10 ** 6)
+        res = []
+        for fn in (ours, R.batch_starting_indices):
+            torch.manual_seed(seed)
+            try:
+                out = torch.as_tensor(fn(data_size, T, B, split, lens, pct)).tolist()
+                res.append(("ok", out, int(torch.randint(0, 2 ** 31 - 1, (1,)))))
+            except (ValueError, TypeError, RuntimeError) as e:
+                res.append(("err", type(e).__name__, str(e)))
+        assert res[0] == res[1], (trial, data_size, T, B, split, lens, pct, res)
+        seen[res[0][0]] += 1
+    assert seen["ok"] > 400 and seen["err"] > 10
+
+
 def test_get_batch_bit_exact_through_module_globals():
     from tradeaid_b200 import training_utils as tu
     g = load_golden("get_batch.pt")
