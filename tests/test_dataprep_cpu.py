@@ -381,6 +381,12 @@ def test_host_logic_vocabulary_chain_and_split(du_emu, golden):
     assert tok.tolist() == want_tok and voc == want_voc and 0.0 in voc
     with pytest.raises(ZeroDivisionError, match="previous value is zero at index 1"):
         du.prepare_modality(zc, zp, on_zero="raise")
+    # ... and the reference converts file by file, so its message carries the index inside the file
+    with pytest.raises(ZeroDivisionError) as info:
+        du.convert_to_percent_changes([1.0, 2.0, 3.0, 4.0, 0.0, 6.0, 0.0, 1.0], 2, file_lengths=[3, 5])
+    with pytest.raises(ZeroDivisionError) as want:
+        oracle.percent_changes_by_file([1.0, 2.0, 3.0, 4.0, 0.0, 6.0, 0.0, 1.0], [3, 5], 2)
+    assert str(info.value) == str(want.value) == "Cannot calculate percentage change: previous value is zero at index 1."
     # more distinct values than half the first table: one retry with a larger table, same result
     before = emu_prep.stats["vocab_inserts"]
     n = 70_000

@@ -201,7 +201,8 @@ def convert_to_percent_changes(data, decimal_places=2, file_lengths=None, on_zer
     st.raise_nonfinite(nonfinite, x)
     if zero_prev is not None:
         if on_zero == "raise":
-            raise ZeroDivisionError(f"Cannot calculate percentage change: previous value is zero at index {zero_prev}.")
+            local = zero_prev - max(int(v) for v in starts.tolist() if v <= zero_prev)   # the reference converts file by file
+            raise ZeroDivisionError(f"Cannot calculate percentage change: previous value is zero at index {local}.")
         print(f"Warning: Zero value found (first at index {zero_prev}) causes division by zero. "
               f"Using 0.0% change for the rows that follow a zero.")       # file_cache.py:367-370 prints one line per row
     return out.tolist() if as_list else out
