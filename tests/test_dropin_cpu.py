@@ -56,6 +56,18 @@ def test_init_statistics():
     assert float(sd["blocks.0.ln1_layers.0.bias"].abs().max()) == 0.0
 
 
+def test_unsupported_shapes_are_refused_at_construction():
+    """Shapes the kernels cannot take are refused with a ValueError when the dimensions are declared, not by a TMA descriptor
+    error in the middle of a step: head sizes outside {8, 16, ..., 64}, n_embd not divisible by n_head or by 16 (the
+    projection MLP's hidden width n_embd/2 is a bf16 row pitch; found by tests/soak/engine_soak_vs_reference.py)."""
+    from tradeaid_b200.params import Dims
+    for C, H in ((24, 3), (40, 5), (8, 1), (30, 4), (32, 8), (256, 2)):
+        with pytest.raises(ValueError):
+            Dims([16, 16], [True, False], 8, C, H, 1)
+    for C, H in ((16, 2), (48, 3), (64, 1), (1024, 16)):
+        Dims([16, 16], [True, False], 8, C, H, 1)
+
+
 def test_cpu_forward_fails_loudly():
     _, m = _model("demo")
     with pytest.raises(RuntimeError, match="CUDA"):

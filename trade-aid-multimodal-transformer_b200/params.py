@@ -45,8 +45,9 @@ class Dims:
         self.hs = C // H
         self.h2 = self.hs // 2
         self.h2p = r8(self.h2)
-        if C % 8 != 0:
-            raise ValueError("tradeaid_b200 requires n_embd % 8 == 0 (TMA 16-byte row pitch)")
+        if C % 16 != 0:
+            raise ValueError("tradeaid_b200 requires n_embd % 16 == 0 (the projection MLP's hidden width n_embd/2 is a bf16 "
+                             "row pitch: TMA needs 16 bytes)")
         if self.hs % 8 != 0 or self.hs > 64:
             raise ValueError(f"tradeaid_b200 supports head_size in {{8,16,...,64}}, got {self.hs}")
         # modalities whose cross-attention modules exist in the state dict (model.py:194-212)
