@@ -3,7 +3,8 @@
 against the reference model.py itself on RANDOM configurations - 1..4 modalities with random cross-attention flags, odd
 vocabularies (down to 2 and 3: hidden width 1), heads 1..8, head sizes 8..64, 1..3 layers, windows shorter than block_size,
 batch 1..3. Logits, losses and every parameter gradient (autograd of the reference) must agree to float32 round-off;
-inactive parameters (single modality with the cross flag) must stay zero.
+inactive parameters (single modality with the cross flag) must stay zero; then three AdamW steps of the
+reference loop (torch.optim.AdamW) against the engine-owned Trainer (fused AdamW): loss curve and parameters.
 usage: cd /tmp && python /root/repo/tests/soak/engine_soak_vs_reference.py [trials] [seed]"""
 import os
 import random
@@ -78,8 +79,10 @@ for trial in range(trials):
         assert d <= 5e-6 * max(1.0, abs(float(b))), (trial, cfg_s, "loss", d)
     eng.backward()
     gv = eng.layout.named_views(eng.grad)
+    grad_scale = {}
     for k, p in m.named_parameters():
         ref_g = p.grad if p.grad is not None else torch.zeros_like(p)
+        grad_scale[k] = ref_g.abs().max().item()
         if not eng.layout.is_active(k):
             assert gv[k].abs().max().item() == 0.0 and ref_g.abs().max().item() == 0.0, (trial, cfg_s, k)
             continue
@@ -87,5 +90,28 @@ for trial in range(trials):
         d = (gv[k] - ref_g).abs().max().item() / sc
         worst["grad"] = max(worst["grad"], d)
         assert d <= 3e-4 + 1e-6 / sc, (trial, cfg_s, k, d)
+    # three AdamW steps: the reference loop of main.py:641-650 with torch.optim.AdamW against the engine-owned Trainer
+    from tradeaid_b200.trainer import Trainer
+    lr = rng.choice([1e-3, 3e-3])
+    opt = torch.optim.AdamW(m.parameters(), lr=lr)
+    tr = Trainer(eng, lr=lr)
+    for _ in range(3):
+        lg, ls = m(idx, tgt)
+        opt.zero_grad(set_to_none=True)
+        sum(ls).backward()
+        opt.step()
+        e_ls = tr.step(torch.stack(idx), torch.stack(tgt))
+        d = max(abs(float(a) - float(b)) for a, b in zip(e_ls, ls))
+        worst["curve"] = max(worst.get("curve", 0.0), d)
+        assert d <= 2e-5, (trial, cfg_s, "loss curve", d)
+    # Adam's m / sqrt(v) turns float32 round-off of near-zero gradient elements (dead ReLU units ...) into O(lr) differences
+    # of single elements, so the UPDATE of every tensor is compared normwise
+    after = dict(m.named_parameters())
+    for k, v in nv.items():
+        if eng.layout.is_active(k) and grad_scale[k] > 1e-7:     # (a 1-position window: q/k gradients are pure round-off)
+            upd_ref = after[k].detach() - sd[k]
+            d = float((v - after[k].detach()).norm() / (upd_ref.norm() + 1e-12))
+            worst["param"] = max(worst.get("param", 0.0), d)
+            assert d <= 2e-2, (trial, cfg_s, k, d)
 print(f"engine soak: {trials} random configurations agree with the reference (max abs logits {worst['logits']:.1e}, loss {worst['loss']:.1e}, "
-      f"max relative gradient {worst['grad']:.1e}; oracle logits {worst['oracle']:.1e})")
+      f"max relative gradient {worst['grad']:.1e}; oracle logits {worst['oracle']:.1e}; 3 AdamW steps: losses {worst.get('curve', 0):.1e}, parameter updates {worst.get('param', 0):.1e} normwise)")
