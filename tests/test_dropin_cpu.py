@@ -68,6 +68,50 @@ def test_unsupported_shapes_are_refused_at_construction():
         Dims([16, 16], [True, False], 8, C, H, 1)
 
 
+def test_module_under_the_stock_loop_on_the_emulation():
+    """The nn.Module's host logic without a GPU (model._ops_override = the CPU emulation): forward through the autograd
+    bridge, `sum(losses).backward()` deposits the oracle's gradients into `.grad`, a stock torch AdamW step moves the flat
+    buffer, and generate() gives the same tokens with and without the K/V cache. (tests/soak/stock_loop_soak_vs_reference.py
+    runs the same loop against the reference model itself, offline.)"""
+    from oracle import restatement as R
+    from tradeaid_b200 import model as tm
+    g = load_golden("model_m3.pt")
+    c = g["cfg"]
+    tm.configure(block_size=c["T"], n_embd=c["C"], n_head=c["H"], n_layer=c["L"], dropout=0.0)
+    params = [["s", i + 1, None, False, None, None, None, None, c["cross"][i], f"m{i}"] for i in range(c["M"])]
+    tm._ops_override = emu_ops
+    try:
+        m = tm.MultimodalTransformer(c["M"], c["V"], params)
+        m.load_state_dict({k: v for k, v in g["state_dict"].items()}, strict=False)
+        m = m.to("cpu")
+        logits, losses = m(g["idx"], g["tgt"])
+        for a, b in zip(logits, g["logits"]):
+            assert (a - b).abs().max().item() <= 2e-5
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+        opt.zero_grad(set_to_none=True)
+        sum(losses).backward()
+        for k, p in m.named_parameters():
+            ref = g["grads"][k]
+            if p.grad is None:
+                assert ref.abs().max().item() == 0.0, k
+            else:
+                assert (p.grad - ref).abs().max().item() <= 1e-4 * (ref.abs().max().item() + 1e-8) + 1e-7, k
+        before = m._flat.clone()
+        opt.step()
+        assert not torch.equal(before, m._flat)                       # the stock optimizer updated the engine's flat buffer
+        lg2, _ = m(g["idx"], g["tgt"])
+        assert (lg2[0] - logits[0]).abs().max().item() > 0            # ... and the next forward sees the new weights
+        m.eval()
+        prompt = [t[:, :2].clone() for t in g["idx"]]
+        outs = []
+        for use_cache in (True, False):
+            torch.manual_seed(5)
+            outs.append(m.generate([p.clone() for p in prompt], max_new_tokens=c["T"] + 2, modality_to_generate=1, use_cache=use_cache))
+        assert all(torch.equal(a, b) for a, b in zip(*outs)) and outs[0][1].shape[1] == 2 + c["T"] + 2
+    finally:
+        tm._ops_override = None
+
+
 def test_cpu_forward_fails_loudly():
     _, m = _model("demo")
     with pytest.raises(RuntimeError, match="CUDA"):

@@ -66,6 +66,9 @@ class _Bridge(torch.autograd.Function):
         return None, None, None, None
 
 
+_ops_override = None   # tests inject a CPU emulation of the kernel namespace (tests/emu_ops.py); the product leaves this None
+
+
 class MultimodalTransformer(nn.Module):
     def __init__(self, num_modalities, vocab_sizes, all_modality_params):
         super().__init__()
@@ -139,6 +142,10 @@ class MultimodalTransformer(nn.Module):
         if dev.type == "cuda":
             from .engine import Engine
             eng = Engine(self._dims, dev)
+            flat = eng.master
+        elif _ops_override is not None:      # tests only: the host program over the CPU emulation of the kernel namespace
+            from .engine import Engine
+            eng = Engine(self._dims, dev, ops=_ops_override, act_dtype=torch.float32)
             flat = eng.master
         else:
             eng, flat = None, torch.zeros(self._layout.total, dtype=torch.float32, device=dev)
