@@ -1,0 +1,115 @@
+"""Offline whole-program soak (BUILD CONTAINER ONLY: copies and runs /root/reference): the reference's own `main.py` on its
+demo (config.yaml = the demo: 2 modalities of demo_stock.csv, 50 steps, evaluation at steps 0 / 25 / 49, the [2]-quirk
+augmentation active because has_header is true) twice in a writable copy -
+  (1) unmodified;
+  (2) with the two shim modules of INTEGRATION.md section 1 ahead on sys.path (model.py -> tradeaid_b200.model,
+      training_utils.py -> tradeaid_b200.training_utils), the engine's host program running over the CPU emulation of the
+      kernels (there is no GPU in the build container) -
+and compares every console line (clocks masked; exact) and the training log file (its six-decimal losses to 2e-6). Both runs start from the same seeded checkpoint
+(create_new_model: 0 - the engine initialises its flat buffer with its own draws) with the generators
+re-seeded after model construction, and dropout 0.0 (torch's dropout stream cannot be reproduced outside torch).
+Round 1: 109 console lines and 78 log-file lines, 0 differences - after this soak exposed evaluation running one optimizer step behind (model.py
+_sync_shadows; fixed, regression test in tests/test_dropin_cpu.py).
+usage: python tests/soak/main_py_soak_vs_reference.py"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+work = tempfile.mkdtemp(prefix="mainpy_soak_")
+run = os.path.join(work, "ref_run")
+shims = os.path.join(work, "shims")
+shutil.copytree(REF, run)
+for d, _, files in os.walk(run):
+    os.chmod(d, 0o755)
+    for f in files:
+        os.chmod(os.path.join(d, f), 0o644)
+cfg = open(os.path.join(run, "config.yaml")).read()
+cfg = cfg.replace("dropout: 0.1", "dropout: 0.0").replace("create_new_model: 1", "create_new_model: 0")
+open(os.path.join(run, "config.yaml"), "w").write(cfg)
+os.makedirs(os.path.join(run, "output"))
+os.makedirs(os.path.join(run, "examples", "output"), exist_ok=True)
+os.makedirs(shims)
+open(os.path.join(shims, "model.py"), "w").write("from tradeaid_b200.model import MultimodalTransformer  # noqa: F401\n")
+open(os.path.join(shims, "training_utils.py"), "w").write(
+    "from tradeaid_b200.training_utils import *  # noqa: F401,F403\n"
+    "import tradeaid_b200.training_utils as _impl, sys\n"
+    "sys.modules[__name__] = _impl\n")
+
+CHECKPOINT = f"""
+import os, sys, torch
+os.chdir({run!r}); sys.path.insert(0, {run!r})
+import config_utils
+config_utils._config_cache = dict(device="cpu", batch_size=4, block_size=4, eval_iters=40, n_embd=32, n_head=4, n_layer=2,
+                                  dropout=0.0, fixed_values=[], output_file_name="", project_file_path="./examples/")
+import model
+torch.manual_seed(42)
+params = [["p", 13, True, False, 2, 1, None, None, True, "Demo Prices", None, None],
+          ["p", 13, True, True, None, 2, 3, None, False, "Demo Changes (%)", 0.1, None]]
+torch.save(model.MultimodalTransformer(2, [57, 3], params).state_dict(), "output/demo_model.pth")
+"""
+RESEED = """
+_orig = {mod}.MultimodalTransformer.__init__
+def _init(self, *a, **k):
+    _orig(self, *a, **k)
+    torch.manual_seed(123); random.seed(123)          # the same generator positions after construction on both sides
+{mod}.MultimodalTransformer.__init__ = _init
+sys.argv = ["main.py"]
+exec(compile(open("main.py").read(), "main.py", "exec"))
+"""
+RUN_REF = f"import os, random, sys, torch\nos.chdir({run!r}); sys.path.insert(0, {run!r})\nimport model\n" + RESEED.format(mod="model")
+RUN_OURS = (f"import os, random, sys, torch\nos.chdir({run!r}); sys.path.insert(0, {run!r})\n"
+            f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r}); sys.path.insert(0, {shims!r})\n"
+            "import emu_ops\nfrom tradeaid_b200 import model as _m, training_utils as _t\n"
+            "_m._ops_override = emu_ops; _t._ops_override = emu_ops\n" + RESEED.format(mod="_m"))
+
+
+def go(code, tag):
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, (tag, r.stdout[-1500:], r.stderr[-1500:])
+    log = os.path.join(run, "examples", "output", "demo_training_log.txt")
+    text = open(log).read() if os.path.exists(log) else ""
+    if os.path.exists(log):
+        os.remove(log)
+    return r.stdout, text
+
+
+def mask(text):
+    return [re.sub(r"\d\d:\d\d:\d\d", "<clock>", re.sub(r"\d{4}-\d\d-\d\d", "<date>", ln)) for ln in text.splitlines()]
+
+
+go(CHECKPOINT, "checkpoint")
+out_ref, log_ref = go(RUN_REF, "reference")
+out_ours, log_ours = go(RUN_OURS, "shimmed")
+assert "Model: Loaded successfully" in out_ref and "Model: Loaded successfully" in out_ours
+assert "TRAINING COMPLETED SUCCESSFULLY" in out_ref and "TRAINING COMPLETED SUCCESSFULLY" in out_ours
+
+
+def differing(a, b, tol):
+    """Lines that differ in text - or, with tol, in any number by more than tol (the log file prints six decimals: the
+    float32 round-off between torch's kernels and the emulation shows in the last one)."""
+    if len(a) != len(b):
+        return [f"{len(a)} lines vs {len(b)}"]
+    out = []
+    num = re.compile(r"-?\d+\.\d+")
+    for x, y in zip(a, b):
+        if x == y:
+            continue
+        nx, ny = num.findall(x), num.findall(y)
+        if tol and num.sub("#", x) == num.sub("#", y) and all(abs(float(p) - float(q)) <= tol for p, q in zip(nx, ny)):
+            continue
+        out += ["-" + x, "+" + y]
+    return out
+
+
+d_out = differing(mask(out_ref), mask(out_ours), 0)
+d_log = differing(mask(log_ref), mask(log_ours), 2e-6)
+print("\n".join(ln for ln in mask(out_ours) if "LOSS METRICS" in ln))
+print(f"main.py soak: {len(mask(out_ref))} console lines, {len(d_out)} differing; {len(mask(log_ref))} log-file lines, {len(d_log)} differing")
+print("\n".join((d_out + d_log)[:40]))
+shutil.rmtree(work)
+assert not d_out and not d_log

@@ -99,8 +99,19 @@ def test_module_under_the_stock_loop_on_the_emulation():
         before = m._flat.clone()
         opt.step()
         assert not torch.equal(before, m._flat)                       # the stock optimizer updated the engine's flat buffer
+        # ... and the next forward sees the new weights - in EVAL mode too (estimate_loss right after optimizer.step();
+        # the operand copies used to be refreshed only by training-mode forwards: evaluation ran one step behind)
+        m.eval()
+        with torch.no_grad():
+            lg_eval, _ = m(g["idx"], g["tgt"])
+        sd_now = {k: v.detach().clone() for k, v in m.state_dict().items() if not k.endswith(".tril")}
+        want, _ = R.forward(sd_now, R.Cfg(c["T"], c["C"], c["H"], c["L"], c["V"], c["cross"]), g["idx"], g["tgt"])
+        for a, b in zip(lg_eval, want):
+            assert (a - b).abs().max().item() <= 2e-5
+        assert (lg_eval[0] - logits[0]).abs().max().item() > 1e-4
+        m.train()
         lg2, _ = m(g["idx"], g["tgt"])
-        assert (lg2[0] - logits[0]).abs().max().item() > 0            # ... and the next forward sees the new weights
+        assert (lg2[0] - lg_eval[0]).abs().max().item() <= 2e-5
         m.eval()
         prompt = [t[:, :2].clone() for t in g["idx"]]
         outs = []

@@ -160,6 +160,7 @@ class MultimodalTransformer(nn.Module):
         self._dirty = True
 
     def _deposit_grads(self):
+        self._dirty = True               # gradients were produced: the parameters are about to change
         gviews = self._grad_views
         for name, par in self._param_list:
             if not self._layout.is_active(name):
@@ -252,4 +253,7 @@ class MultimodalTransformer(nn.Module):
     def _sync_shadows(self, eng):
         if self.training or getattr(self, "_dirty", True):
             eng.shadows_stale = True     # a stock optimizer updates the fp32 views in place between forwards
-            self._dirty = False
+        # After a training-mode forward an optimizer step may follow, so the NEXT forward must refresh the operand copies
+        # even in eval mode (estimate_loss right after optimizer.step(), main.py:603/650); consecutive eval-mode forwards
+        # (eval_iters of them) refresh once. _deposit_grads marks the same for a backward taken in eval mode.
+        self._dirty = bool(self.training)
