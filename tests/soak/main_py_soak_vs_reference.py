@@ -5,6 +5,8 @@ augmentation active because has_header is true) twice in a writable copy -
   (2) with the two shim modules of INTEGRATION.md section 1 ahead on sys.path (model.py -> tradeaid_b200.model,
       training_utils.py -> tradeaid_b200.training_utils), the engine's host program running over the CPU emulation of the
       kernels (there is no GPU in the build container) -
+  (3) as (2) plus a data_utils shim that routes range_numeric_data / bin_numeric_data / numerical_representation /
+      convert_to_percent_changes to tradeaid_b200.data_utils (lists in - lists out) -
 and compares every console line (clocks masked; exact) and the training log file (its six-decimal losses to 2e-6). Both runs start from the same seeded checkpoint
 (create_new_model: 0 - the engine initialises its flat buffer with its own draws) with the generators
 re-seeded after model construction, and dropout 0.0 (torch's dropout stream cannot be reproduced outside torch).
@@ -75,6 +77,8 @@ def go(code, tag):
     text = open(log).read() if os.path.exists(log) else ""
     if os.path.exists(log):
         os.remove(log)
+    if tag == "shimmed + data_utils":     # the shimmed functions really ran: one vocabulary build per modality
+        assert "K9_VOCAB_BUILDS 2" in r.stderr, r.stderr[-500:]
     return r.stdout, text
 
 
@@ -82,9 +86,28 @@ def mask(text):
     return [re.sub(r"\d\d:\d\d:\d\d", "<clock>", re.sub(r"\d{4}-\d\d-\d\d", "<date>", ln)) for ln in text.splitlines()]
 
 
+# (3) additionally the data-preparation functions of row f-4 (form (a): lists in, lists out) through
+# a data_utils shim: everything of the reference's data_utils except the four processing functions
+shims3 = os.path.join(work, "shims3")
+shutil.copytree(shims, shims3)
+open(os.path.join(shims3, "data_utils.py"), "w").write(
+    "import importlib.util as _u\n"
+    f"_spec = _u.spec_from_file_location('_reference_data_utils', {os.path.join(run, 'data_utils.py')!r})\n"
+    "_ref = _u.module_from_spec(_spec); _spec.loader.exec_module(_ref)\n"
+    "globals().update({k: getattr(_ref, k) for k in dir(_ref) if not k.startswith('__')})\n"
+    "from tradeaid_b200.data_utils import (range_numeric_data, bin_numeric_data, numerical_representation,  # noqa: E402,F401\n"
+    "                                      convert_to_percent_changes)\n")
+RUN_OURS3 = (RUN_OURS.replace(repr(shims), repr(shims3)).replace('exec(compile(open("main.py").read(), "main.py", "exec"))',
+                              'exec(compile(open("main.py").read(), "main.py", "exec"))\n'
+                              'print("K9_VOCAB_BUILDS", emu_prep.stats["vocab_inserts"], file=sys.stderr)')
+             .replace("_m._ops_override = emu_ops; _t._ops_override = emu_ops\n",
+                      "_m._ops_override = emu_ops; _t._ops_override = emu_ops\n"
+                      "import emu_prep\nfrom tradeaid_b200 import data_utils as _d\n_d._ops_override = emu_prep\n"))
+
 go(CHECKPOINT, "checkpoint")
 out_ref, log_ref = go(RUN_REF, "reference")
 out_ours, log_ours = go(RUN_OURS, "shimmed")
+out_ours3, log_ours3 = go(RUN_OURS3, "shimmed + data_utils")
 assert "Model: Loaded successfully" in out_ref and "Model: Loaded successfully" in out_ours
 assert "TRAINING COMPLETED SUCCESSFULLY" in out_ref and "TRAINING COMPLETED SUCCESSFULLY" in out_ours
 
@@ -111,5 +134,9 @@ d_log = differing(mask(log_ref), mask(log_ours), 2e-6)
 print("\n".join(ln for ln in mask(out_ours) if "LOSS METRICS" in ln))
 print(f"main.py soak: {len(mask(out_ref))} console lines, {len(d_out)} differing; {len(mask(log_ref))} log-file lines, {len(d_log)} differing")
 print("\n".join((d_out + d_log)[:40]))
+d_out3 = differing(mask(out_ref), mask(out_ours3), 0)
+d_log3 = differing(mask(log_ref), mask(log_ours3), 2e-6)
+print(f"with the data_utils shim as well: {len(d_out3)} console lines and {len(d_log3)} log-file lines differing")
+print("\n".join((d_out3 + d_log3)[:40]))
 shutil.rmtree(work)
-assert not d_out and not d_log
+assert not d_out and not d_log and not d_out3 and not d_log3
