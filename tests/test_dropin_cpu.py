@@ -96,6 +96,21 @@ def test_module_under_the_stock_loop_on_the_emulation():
                 assert ref.abs().max().item() == 0.0, k
             else:
                 assert (p.grad - ref).abs().max().item() <= 1e-4 * (ref.abs().max().item() + 1e-8) + 1e-7, k
+        # gradient accumulation: a second backward without zero_grad adds to .grad, as torch does
+        first = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        _, losses_b = m(g["idx"], g["tgt"])
+        (2.0 * losses_b[0] + sum(losses_b[1:])).backward()
+        sd_here = {k: v.detach().clone() for k, v in m.state_dict().items() if not k.endswith(".tril")}
+        ocfg = R.Cfg(c["T"], c["C"], c["H"], c["L"], c["V"], c["cross"])
+        _, ref_losses = R.forward({k: v.requires_grad_(True) for k, v in sd_here.items()}, ocfg, g["idx"], g["tgt"])
+        (2.0 * ref_losses[0] + sum(ref_losses[1:])).backward()
+        for k, p in m.named_parameters():
+            if k in first:
+                want_g = first[k] + (sd_here[k].grad if sd_here[k].grad is not None else 0)
+                assert (p.grad - want_g).abs().max().item() <= 2e-4 * (want_g.abs().max().item() + 1e-8) + 1e-7, k
+        opt.zero_grad(set_to_none=True)
+        _, losses_c = m(g["idx"], g["tgt"])
+        sum(losses_c).backward()                                        # back to one step's gradients for the optimizer
         before = m._flat.clone()
         opt.step()
         assert not torch.equal(before, m._flat)                       # the stock optimizer updated the engine's flat buffer

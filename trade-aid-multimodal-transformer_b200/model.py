@@ -61,7 +61,14 @@ class _Bridge(torch.autograd.Function):
     def backward(ctx, dlosses):
         model = ctx.model
         w = dlosses.tolist()
+        # torch accumulates into an existing .grad. The .grad tensors ARE views of the engine's gradient buffer, which the
+        # backward program overwrites, so gradients still held by the parameters (a second backward without zero_grad: gradient
+        # accumulation) are set aside first and added back. main.py calls optimizer.zero_grad(set_to_none=True) before every
+        # backward (main.py:648): nothing is held then and nothing is copied.
+        held = model._held_grads()
         model._engine.backward(None if all(x == 1.0 for x in w) else w)
+        for view, old in held:
+            view.add_(old)
         model._deposit_grads()
         return None, None, None, None
 
@@ -158,6 +165,18 @@ class MultimodalTransformer(nn.Module):
         self._flat, self._engine = flat, eng
         self._anchor = torch.zeros(1, device=dev, requires_grad=True) if eng is not None else None
         self._dirty = True
+
+    def _held_grads(self):
+        """[(gradient-buffer view, copy of its current content)] for the parameters whose .grad is such a view."""
+        gviews = self._grad_views
+        names = [name for name, par in self._param_list
+                 if par.grad is not None and self._layout.is_active(name) and par.grad.data_ptr() == gviews[name].data_ptr()]
+        if not names:
+            return []
+        if len(names) == sum(1 for name, _ in self._param_list if self._layout.is_active(name)):
+            whole = self._engine.grad[:self._layout.n_active]          # every parameter holds one: one copy of the flat buffer
+            return [(whole, whole.clone())]
+        return [(gviews[name], gviews[name].clone()) for name in names]
 
     def _deposit_grads(self):
         self._dirty = True               # gradients were produced: the parameters are about to change
