@@ -168,6 +168,8 @@ class MultimodalTransformer(nn.Module):
 
     def _held_grads(self):
         """[(gradient-buffer view, copy of its current content)] for the parameters whose .grad is such a view."""
+        if all(par.grad is None for _, par in self._param_list):       # main.py's loop: nothing to look at
+            return []
         gviews = self._grad_views
         names = [name for name, par in self._param_list
                  if par.grad is not None and self._layout.is_active(name) and par.grad.data_ptr() == gviews[name].data_ptr()]
