@@ -12,7 +12,8 @@ and compares every console line (clocks masked; exact) and the training log file
 re-seeded after model construction, and dropout 0.0 (torch's dropout stream cannot be reproduced outside torch).
 Round 1: 109 console lines and 78 log-file lines, 0 differences - after this soak exposed evaluation running one optimizer step behind (model.py
 _sync_shadows; fixed, regression test in tests/test_dropin_cpu.py).
-usage: python tests/soak/main_py_soak_vs_reference.py"""
+usage: python tests/soak/main_py_soak_vs_reference.py [demo|folder]
+("folder": three csv files in a folder, four modalities incl. a string one, file-based validation split, block_size 8)"""
 import os
 import re
 import shutil
@@ -33,6 +34,81 @@ for d, _, files in os.walk(run):
 cfg = open(os.path.join(run, "config.yaml")).read()
 cfg = cfg.replace("dropout: 0.1", "dropout: 0.0").replace("create_new_model: 1", "create_new_model: 0")
 open(os.path.join(run, "config.yaml"), "w").write(cfg)
+SCENARIO = sys.argv[1] if len(sys.argv) > 1 else "demo"
+MODEL_ARGS = ('2, [57, 3], [["p", 13, True, False, 2, 1, None, None, True, "Demo Prices", None, None], '
+              '["p", 13, True, True, None, 2, 3, None, False, "Demo Changes (%)", 0.1, None]]')
+DIMS = dict(batch_size=4, block_size=4, n_embd=32, n_head=4, n_layer=2)
+VOCAB_BUILDS = 2
+if SCENARIO == "folder":
+    # a harder set-up: a FOLDER of three csv files (multi-file index generation, per-file percent changes), four modalities -
+    # ranged prices, binned percent changes, a STRING modality (time of day: non-numeric vocabulary, no directional metrics)
+    # and ranged volumes - three of them with cross-attention, the last file as the validation set, block_size 8
+    import random as _r
+    rng = _r.Random(3)
+    src = open(os.path.join(run, "examples", "demo_data", "demo_stock.csv")).read().splitlines()
+    folder = os.path.join(run, "examples", "demo_data", "multi")
+    os.makedirs(folder)
+    for k, n_rows in enumerate((70, 100, 55)):
+        rows = [src[0]]
+        price = 60.0 + 25 * k
+        for j in range(n_rows):
+            f = src[1 + (j + 13 * k) % (len(src) - 1)].split(",")
+            price = max(5.0, price * (1 + rng.gauss(0, 0.01)))
+            f[12] = f"{price:.2f}"
+            f[13] = str(rng.randint(900, 2500) * 1000)
+            rows.append(",".join(f))
+        open(os.path.join(folder, f"part_{k}.csv"), "w").write("\n".join(rows) + "\n")
+    open(os.path.join(run, "input_schemas.yaml"), "w").write("""modalities:
+  - modality_name: "Prices"
+    path: "./examples/demo_data/multi"
+    column_number: 13
+    has_header: true
+    processing_steps:
+      - function: range_numeric_data
+        args: {num_whole_digits: 2, decimal_places: 1}
+        enabled: true
+    cross_attention: true
+    randomness_size: null
+  - modality_name: "Changes (%)"
+    path: "./examples/demo_data/multi"
+    column_number: 13
+    has_header: true
+    processing_steps:
+      - function: convert_to_percent_changes
+        args: {decimal_places: 2}
+        enabled: true
+      - function: bin_numeric_data
+        args: {num_bins: 4, outlier_percentile: 1, exponent: 2.0}
+        enabled: true
+    cross_attention: false
+    randomness_size: null
+  - modality_name: "Time of day"
+    path: "./examples/demo_data/multi"
+    column_number: 9
+    has_header: true
+    processing_steps: []
+    cross_attention: true
+    randomness_size: null
+  - modality_name: "Volume"
+    path: "./examples/demo_data/multi"
+    column_number: 14
+    has_header: true
+    processing_steps:
+      - function: range_numeric_data
+        args: {num_whole_digits: 1, decimal_places: 1}
+        enabled: true
+    cross_attention: true
+    randomness_size: null
+""")
+    cfg = open(os.path.join(run, "config.yaml")).read()
+    for a, b in (("num_validation_files: 0", "num_validation_files: 1"), ("block_size: 4", "block_size: 8"),
+                 ("max_iters: 50", "max_iters: 30"), ("eval_interval: 25", "eval_interval: 10")):
+        assert a in cfg, a
+        cfg = cfg.replace(a, b)
+    open(os.path.join(run, "config.yaml"), "w").write(cfg)
+    MODEL_ARGS = None          # vocabulary sizes are read from a first, unmodified run (below)
+    DIMS = dict(batch_size=4, block_size=8, n_embd=32, n_head=4, n_layer=2)
+    VOCAB_BUILDS = 3           # the string modality goes to the reference's function (NotImplementedError in the product)
 os.makedirs(os.path.join(run, "output"))
 os.makedirs(os.path.join(run, "examples", "output"), exist_ok=True)
 os.makedirs(shims)
@@ -42,18 +118,21 @@ open(os.path.join(shims, "training_utils.py"), "w").write(
     "import tradeaid_b200.training_utils as _impl, sys\n"
     "sys.modules[__name__] = _impl\n")
 
-CHECKPOINT = f"""
+
+
+def checkpoint_code(model_args):
+    return f"""
 import os, sys, torch
 os.chdir({run!r}); sys.path.insert(0, {run!r})
 import config_utils
-config_utils._config_cache = dict(device="cpu", batch_size=4, block_size=4, eval_iters=40, n_embd=32, n_head=4, n_layer=2,
-                                  dropout=0.0, fixed_values=[], output_file_name="", project_file_path="./examples/")
+config_utils._config_cache = dict(device="cpu", eval_iters=40, dropout=0.0, fixed_values=[], output_file_name="",
+                                  project_file_path="./examples/", **{DIMS!r})
 import model
 torch.manual_seed(42)
-params = [["p", 13, True, False, 2, 1, None, None, True, "Demo Prices", None, None],
-          ["p", 13, True, True, None, 2, 3, None, False, "Demo Changes (%)", 0.1, None]]
-torch.save(model.MultimodalTransformer(2, [57, 3], params).state_dict(), "output/demo_model.pth")
+torch.save(model.MultimodalTransformer({model_args}).state_dict(), "output/demo_model.pth")
 """
+
+
 RESEED = """
 _orig = {mod}.MultimodalTransformer.__init__
 def _init(self, *a, **k):
@@ -78,7 +157,7 @@ def go(code, tag):
     if os.path.exists(log):
         os.remove(log)
     if tag == "shimmed + data_utils":     # the shimmed functions really ran: one vocabulary build per modality
-        assert "K9_VOCAB_BUILDS 2" in r.stderr, r.stderr[-500:]
+        assert f"K9_VOCAB_BUILDS {VOCAB_BUILDS}" in r.stderr, r.stderr[-500:]
     return r.stdout, text
 
 
@@ -95,8 +174,13 @@ open(os.path.join(shims3, "data_utils.py"), "w").write(
     f"_spec = _u.spec_from_file_location('_reference_data_utils', {os.path.join(run, 'data_utils.py')!r})\n"
     "_ref = _u.module_from_spec(_spec); _spec.loader.exec_module(_ref)\n"
     "globals().update({k: getattr(_ref, k) for k in dir(_ref) if not k.startswith('__')})\n"
-    "from tradeaid_b200.data_utils import (range_numeric_data, bin_numeric_data, numerical_representation,  # noqa: E402,F401\n"
-    "                                      convert_to_percent_changes)\n")
+    "from tradeaid_b200.data_utils import (range_numeric_data, bin_numeric_data, convert_to_percent_changes)  # noqa: E402,F401\n"
+    "from tradeaid_b200 import data_utils as _ours\n"
+    "def numerical_representation(data_points):\n"
+    "    try:\n"
+    "        return _ours.numerical_representation(data_points)\n"
+    "    except NotImplementedError:          # string modalities stay with the reference's function (INTEGRATION.md 1a)\n"
+    "        return _ref.numerical_representation(data_points)\n")
 RUN_OURS3 = (RUN_OURS.replace(repr(shims), repr(shims3)).replace('exec(compile(open("main.py").read(), "main.py", "exec"))',
                               'exec(compile(open("main.py").read(), "main.py", "exec"))\n'
                               'print("K9_VOCAB_BUILDS", emu_prep.stats["vocab_inserts"], file=sys.stderr)')
@@ -104,7 +188,17 @@ RUN_OURS3 = (RUN_OURS.replace(repr(shims), repr(shims3)).replace('exec(compile(o
                       "_m._ops_override = emu_ops; _t._ops_override = emu_ops\n"
                       "import emu_prep\nfrom tradeaid_b200 import data_utils as _d\n_d._ops_override = emu_prep\n"))
 
-go(CHECKPOINT, "checkpoint")
+if MODEL_ARGS is None:
+    probe = cfg_text = open(os.path.join(run, "config.yaml")).read()
+    open(os.path.join(run, "config.yaml"), "w").write(cfg_text.replace("create_new_model: 0", "create_new_model: 1")
+                                                      .replace("max_iters: 30", "max_iters: 1"))
+    out_probe, _ = go(RUN_REF, "probe")
+    open(os.path.join(run, "config.yaml"), "w").write(cfg_text)
+    sizes = [int(v) for v in re.search(r"Vocabulary sizes: \[([^\]]*)\]", out_probe).group(1).split(",")]
+    flags = [True, False, True, True]
+    MODEL_ARGS = f"{len(sizes)}, {sizes}, [['p', 1, True, False, None, None, None, None, {flags}[i], 'm', None, None] for i in range({len(sizes)})]"
+    print("folder scenario: vocabulary sizes", sizes)
+go(checkpoint_code(MODEL_ARGS), "checkpoint")
 out_ref, log_ref = go(RUN_REF, "reference")
 out_ours, log_ours = go(RUN_OURS, "shimmed")
 out_ours3, log_ours3 = go(RUN_OURS3, "shimmed + data_utils")
