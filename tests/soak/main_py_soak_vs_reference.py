@@ -101,7 +101,7 @@ if SCENARIO == "folder":
     randomness_size: null
 """)
     cfg = open(os.path.join(run, "config.yaml")).read()
-    for a, b in (("num_validation_files: 0", "num_validation_files: 1"), ("block_size: 4", "block_size: 8"),
+    for a, b in (("num_validation_files: 0", "num_validation_files: 1"), ("block_size: 4", "block_size: 8"), ("save_model: 0", "save_model: 1"),
                  ("max_iters: 50", "max_iters: 30"), ("eval_interval: 25", "eval_interval: 10")):
         assert a in cfg, a
         cfg = cfg.replace(a, b)
@@ -149,8 +149,21 @@ RUN_OURS = (f"import os, random, sys, torch\nos.chdir({run!r}); sys.path.insert(
             "_m._ops_override = emu_ops; _t._ops_override = emu_ops\n" + RESEED.format(mod="_m"))
 
 
+saved = {}
+
+
 def go(code, tag):
+    ckpt, init = os.path.join(run, "output", "demo_model.pth"), os.path.join(work, "init.pth")
+    if tag == "checkpoint":
+        pass
+    elif os.path.exists(init):
+        shutil.copyfile(init, ckpt)          # every run starts from the same checkpoint (save_model: 1 overwrites it)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1200)
+    if tag == "checkpoint":
+        shutil.copyfile(ckpt, init)
+    elif os.path.exists(ckpt):
+        saved[tag] = os.path.join(work, f"saved_{len(saved)}.pth")
+        shutil.copyfile(ckpt, saved[tag])
     assert r.returncode == 0, (tag, r.stdout[-1500:], r.stderr[-1500:])
     log = os.path.join(run, "examples", "output", "demo_training_log.txt")
     text = open(log).read() if os.path.exists(log) else ""
@@ -162,7 +175,16 @@ def go(code, tag):
 
 
 def mask(text):
-    return [re.sub(r"\d\d:\d\d:\d\d", "<clock>", re.sub(r"\d{4}-\d\d-\d\d", "<date>", ln)) for ln in text.splitlines()]
+    # clocks and dates; and the size of the checkpoint FILE: the engine's parameters are views of one flat storage and its
+    # per-head tril buffers one tensor, so torch.save writes fewer zip records (0.71 vs 0.85 MB here) - same keys, shapes and
+    # values, loadable in both directions (compared below and in module_soak_vs_reference.py)
+    out = []
+    for ln in text.splitlines():
+        ln = re.sub(r"\d\d:\d\d:\d\d", "<clock>", re.sub(r"\d{4}-\d\d-\d\d", "<date>", ln))
+        if ln.startswith(("Saved: Model checkpoint (", "Final Save: ")):
+            ln = re.sub(r"\d+\.\d+ MB", "<size> MB", ln)
+        out.append(ln)
+    return out
 
 
 # (3) additionally the data-preparation functions of row f-4 (form (a): lists in, lists out) through
@@ -232,5 +254,16 @@ d_out3 = differing(mask(out_ref), mask(out_ours3), 0)
 d_log3 = differing(mask(log_ref), mask(log_ours3), 2e-6)
 print(f"with the data_utils shim as well: {len(d_out3)} console lines and {len(d_log3)} log-file lines differing")
 print("\n".join((d_out3 + d_log3)[:40]))
+if SCENARIO == "folder":                 # save_model: 1 - the checkpoints main.py wrote at the end of the runs
+    import torch
+    a = torch.load(saved["reference"], weights_only=True)
+    for tag in ("shimmed", "shimmed + data_utils"):
+        b = torch.load(saved[tag], weights_only=True)
+        assert list(a.keys()) == list(b.keys())
+        init_sd = torch.load(os.path.join(work, "init.pth"), weights_only=True)
+        worst = max(float((a[k] - b[k]).norm() / ((a[k] - init_sd[k]).norm() + 1e-12)) for k in a
+                    if not k.endswith(".tril") and float((a[k] - init_sd[k]).abs().max()) > 0)
+        print(f"saved checkpoint ({tag}): same keys in the same order; parameter updates within {worst:.1e} normwise of the reference's")
+        assert worst <= 5e-2
 shutil.rmtree(work)
 assert not d_out and not d_log and not d_out3 and not d_log3
