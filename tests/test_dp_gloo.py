@@ -183,3 +183,71 @@ def test_two_rank_evaluation_equals_single_process(tmp_path, capsys):
         for split in ("train", "val"):
             assert abs(got[r]["out"][split] - want[split]) <= 1e-12 * abs(want[split])
     assert got[0]["out"] == got[1]["out"]
+
+
+# ------------------------------------------------------------------------------------------------ the pieces together
+class _EngineModel:
+    """training_utils.m for the engine-owned tier: forward through the engine (evaluation never needs backward)."""
+
+    def __init__(self, eng):
+        self.eng, self.training = eng, True
+
+    def eval(self):
+        self.training = False
+
+    def train(self):
+        self.training = True
+
+    def __call__(self, xb, yb):
+        logits, losses = self.eng.forward(torch.stack(xb), torch.stack(yb), save=False)
+        return logits, [losses[i] for i in range(len(xb))]
+
+
+def _parity_run(world, pg, rank):
+    """Three training steps + one evaluation in data-parallel PARITY mode: get_batch with batch_shard (every rank draws the
+    global batch's indices, gathers its rows), Trainer with the gradient exchange, estimate_loss over eval_process_group."""
+    eng, tr, _, _ = _build(world, pg)
+    tu = _eval_setup(pg if world > 1 else None)
+    tu.configure(device="cpu", batch_size=4, block_size=8, eval_iters=4)
+    tu.m = _EngineModel(eng)
+    tu.batch_shard = (rank, world) if world > 1 else None
+    torch.manual_seed(5)
+    try:
+        for _ in range(3):
+            xb, yb = tu.get_batch("train", 0)
+            tr.step(torch.stack(xb), torch.stack(yb))
+        tu.batch_shard = None                     # evaluation batches are whole; the iterations are what is dealt out
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = tu.estimate_loss()
+    finally:
+        tu.batch_shard = None
+        tu.eval_process_group = None
+        tu._ops_override = None
+        tu._stores.clear()
+        tu.m = None
+    return eng.master.clone(), out
+
+
+def _parity_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    master, out = _parity_run(world, dist.group.WORLD, rank)
+    torch.save({"master": master, "out": out}, os.path.join(out_dir, f"parity_{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_parity_mode_training_and_evaluation_equal_single_process(tmp_path):
+    """SURVEY.md 8e end to end on CPU: fixed global batch, sharded get_batch, gradient exchange, sharded evaluation - the
+    parameters after three steps and the evaluation losses equal the single-process run on the same index stream."""
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_parity_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [torch.load(str(tmp_path / f"parity_{r}.pt")) for r in range(2)]
+    master, out = _parity_run(1, None, 0)
+    assert torch.equal(got[0]["master"], got[1]["master"])
+    assert (got[0]["master"] - master).abs().max().item() <= 2e-5
+    for split in ("train", "val"):
+        assert got[0]["out"][split] == got[1]["out"][split]
+        assert abs(got[0]["out"][split] - out[split]) <= 1e-5 * abs(out[split])
