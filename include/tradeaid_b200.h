@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 3
+#define TA_ABI_VERSION 4
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -32,7 +32,8 @@ void ta_reset_launch_count(void);
 /* Persistent kernels (GEMM, attention, LayerNorm backward) size their grids from the SM count. While a collective
  * (the NCCL gradient all-reduce of the data-parallel step, main.py:646-650 under DP) runs on a side stream, its CTAs
  * hold SMs; a persistent grid of one CTA per SM would then run its displaced CTAs as a second wave. The margin (SMs,
- * rounded to whole SM pairs) is subtracted from the grid of every FOLLOWING launch of the process; 0 restores full grids. */
+ * rounded to whole SM pairs) is subtracted from the grid of every FOLLOWING launch made by the CALLING THREAD (two engines
+ * driven from two threads do not see each other's margin); 0 restores full grids. */
 int32_t ta_set_sm_margin(int32_t sms);
 int32_t ta_get_sm_margin(void);
 
@@ -83,7 +84,7 @@ typedef struct ta_epilogue {
 
 /* Dropout (model.py:69, 91, 116, 151, 171). Masks are a pure function of (seed, coordinates): Philox4x32-7 keyed by the
  * 64-bit seed of the call, one draw per 8 consecutive columns of a row (csrc/philox.cuh), so backward regenerates them.
- * ta_dropout_set_step_counter registers a device counter (or NULL) that the FOLLOWING launches of the calling process
+ * ta_dropout_set_step_counter registers a device counter (or NULL) that the FOLLOWING launches of the calling THREAD
  * capture in their parameters: its value is mixed into the seed when the kernel RUNS, so a captured CUDA graph draws
  * fresh masks on every replay as long as the graph increments the counter. Bindings set it around each launch.
  * ta_dropout_bf16: dst = keep ? src / (1 - p) : 0 with the GEMM-epilogue mask of the same seed (backward of the three
@@ -125,7 +126,7 @@ int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const
  * cached. q: bf16 [G][B][ld] (ta_attn_tensor.ld = elements between batch rows). k[s], v[s]: caches [G][B][capacity][ld]
  * (ld = elements between cached positions, kv_batch_stride[s] = elements between batches; k and v of a source share
  * strides). Per source an independent softmax over positions [0, len), outputs summed; o: bf16 [G][B][ldo], head h at
- * columns [h*hs, (h+1)*hs). n_src <= 16, hs in {8, 16, 32, 64}. */
+ * columns [h*hs, (h+1)*hs). n_src <= 16, hs a multiple of 8 up to 64 (as the forward / backward kernels). */
 int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v,
                             const int64_t* kv_batch_stride, int32_t n_src, void* o_bf16, int64_t ldo, int64_t o_gs,
                             int32_t G, int32_t B, int32_t len, int32_t H, int32_t hs, void* stream);
@@ -161,6 +162,9 @@ int32_t ta_embed_bwd(const int64_t* idx, const float* dx, const int64_t* voff, i
  */
 int32_t ta_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t ldy, float* mean,
                          float* rstd, int64_t rows_total, int64_t rows_per_group, int32_t C, float eps, void* stream);
+/* same, fp32 output (the bf16x3 precision mode splits it into hi + lo operands next: ta_split_bf16) */
+int32_t ta_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y_f32, int64_t ldy, float* mean,
+                             float* rstd, int64_t rows_total, int64_t rows_per_group, int32_t C, float eps, void* stream);
 int64_t ta_layernorm_bwd_workspace_floats(int64_t rows_total, int64_t rows_per_group, int32_t C);
 int32_t ta_layernorm_bwd(const void* dy_bf16, int64_t lddy, const float* x, const float* gamma, const float* mean,
                          const float* rstd, const float* dstream_in, float* dstream_out, void* dstream_bf16,
@@ -274,6 +278,20 @@ int32_t ta_cast_pad_bf16(const float* src, int64_t sg, int64_t sr, void* dst_bf1
 int32_t ta_unpad_f32(const float* src, int64_t sg, int64_t sr, float* dst, int64_t dg, int64_t dr, int32_t G, int32_t R,
                      int32_t Cn, void* stream);
 int32_t ta_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ bf16x3 precision mode
+ * The north star holds logits to 2e-3 of the reference's fp32 forward (model.py:380-402); single-pass bf16 operands give
+ * ~5e-3. An fp32 value is written as hi + lo (hi = bf16(x), lo = bf16(x - hi)) and a product of two such values as
+ * a_hi*b_hi + a_lo*b_hi + a_hi*b_lo: ONE ta_gemm_bf16 launch over K-concatenated operands [A_hi|A_lo|A_hi] x [B_hi|B_hi|B_lo].
+ * ta_split_bf16 writes `terms` slots of a [G1][G0][R][C] fp32 view (unit inner stride; g1/g0/r element strides) side by
+ * side along the columns (concat_rows = 0: slot k at columns [k*C, (k+1)*C)) or stacked along the rows (concat_rows = 1:
+ * slot k at rows [k*R, (k+1)*R), for MN-major operands); bit k of lo_mask selects lo for slot k (A: 0b010, B: 0b100).
+ * ta_convert: strided fp32 <-> bf16 conversion / copy of such a view (the attention kernels keep bf16 I/O in every mode). */
+int32_t ta_split_bf16(const float* src, int64_t s_g1, int64_t s_g0, int64_t s_r, void* dst_bf16, int64_t d_g1, int64_t d_g0,
+                      int64_t d_r, int32_t G1, int32_t G0, int32_t R, int32_t C, int32_t terms, int32_t lo_mask,
+                      int32_t concat_rows, void* stream);
+int32_t ta_convert(const void* src, int32_t src_is_bf16, int64_t s_g1, int64_t s_g0, int64_t s_r, void* dst, int32_t dst_is_bf16,
+                   int64_t d_g1, int64_t d_g0, int64_t d_r, int32_t G1, int32_t G0, int32_t R, int32_t C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ K6: AdamW
  * torch.optim.AdamW defaults (main.py:464, 650): betas (0.9, 0.999), eps 1e-8, decoupled weight_decay 0.01, on the flat

@@ -184,6 +184,32 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
     y.copy_((((x - mu.unsqueeze(-1)) * rs.unsqueeze(-1)) * gamma.unsqueeze(1) + beta.unsqueeze(1)).to(y.dtype))
 
 
+def layernorm_fwd_f32(x, gamma, beta, y, mean, rstd, eps=1e-5):
+    assert y.dtype == torch.float32
+    layernorm_fwd(x, gamma, beta, y, mean, rstd, eps)
+
+
+def split_bf16(src, dst, lo_mask, terms=3, concat_rows=False):
+    """csrc/split.cu: slot k of dst = lo (bit k of lo_mask) or hi of src."""
+    _tick()
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16
+    hi = src.to(torch.bfloat16)
+    lo = (src - hi.float()).to(torch.bfloat16)
+    R, C = src.shape[-2], src.shape[-1]
+    for k in range(terms):
+        v = lo if (lo_mask >> k) & 1 else hi
+        if concat_rows:
+            dst[..., k * R:(k + 1) * R, :].copy_(v)
+        else:
+            dst[..., k * C:(k + 1) * C].copy_(v)
+
+
+def convert(src, dst):
+    _tick()
+    assert src.shape == dst.shape and src.stride(-1) == 1 and dst.stride(-1) == 1 and src.dim() <= 4
+    dst.copy_(src.to(dst.dtype))
+
+
 def layernorm_bwd_workspace(G, rows, C):
     return 1
 

@@ -216,7 +216,8 @@ def _parity_run(world, pg, rank):
         for _ in range(3):
             xb, yb = tu.get_batch("train", 0)
             tr.step(torch.stack(xb), torch.stack(yb))
-        tu.batch_shard = None                     # evaluation batches are whole; the iterations are what is dealt out
+        # batch_shard AND eval_process_group both stay set (the natural parity set-up): estimate_loss itself draws whole
+        # evaluation batches and deals the iterations to the ranks (it used to evaluate 1/world of each batch)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):

@@ -476,7 +476,8 @@ def test_attention_dropout_fwd_bwd(lib, G, B, T, H, hs, S):
 
 
 @pytest.mark.parametrize("G,B,H,hs,cap,length,S", [(2, 3, 4, 64, 40, 33, 1), (1, 5, 2, 32, 64, 64, 3), (3, 2, 3, 16, 10, 1, 2),
-                                                   (1, 4, 12, 64, 1024, 1000, 3), (2, 2, 4, 8, 7, 5, 1)])
+                                                   (1, 4, 12, 64, 1024, 1000, 3), (2, 2, 4, 8, 7, 5, 1),
+                                                   (1, 2, 2, 48, 20, 17, 2), (2, 2, 3, 24, 9, 9, 1), (1, 3, 2, 56, 70, 70, 1), (1, 2, 4, 40, 33, 32, 3)])
 def test_attention_decode(lib, G, B, H, hs, cap, length, S):
     """ta_attention_decode (one new query row against a K/V cache, generate's growing phase) vs fp32 torch: per source an
     independent softmax over the cached positions [0, length), outputs summed (model.py:60-73, 136-159, last row)."""

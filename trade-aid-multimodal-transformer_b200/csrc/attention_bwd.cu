@@ -528,11 +528,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
 template <int DP>
 static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t st) {
   constexpr int SMEM = 12 * AB_TILE + AB_NBARS * 8 + 16 + 2 * ATTB_MAX_SRC * 256 * 4 + 64;
-  static bool attr = false;
-  if (!attr) {
-    TA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
-  }
+  static bool attr[TA_MAX_DEVICES] = {};
+  TA_CHECK_CUDA(ensure_dynamic_smem(attn_bwd_kernel<DP>, SMEM, attr));
   const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
   launch_kernel(attn_bwd_kernel<DP>, dim3(grid), dim3(AB_THREADS), SMEM, st, maps, p);
   TA_CHECK_LAUNCH();

@@ -51,10 +51,15 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
   const long long gb = w / p.H;
   const int b = (int)(gb % p.B), g = (int)(gb / p.B);
   const int piece = lane % LPR, rg = lane / LPR;
+  // HS is the head size rounded up to a power of two (lane layout); lanes whose 8 dims lie beyond the real head size
+  // (hs = 24, 40, 48, 56) load nothing and contribute zeros
+  const bool act = 8 * piece < p.hs;
 
   // this lane's 8 dims of the query row, pre-scaled
   float q[8];
-  {
+#pragma unroll
+  for (int d = 0; d < 8; ++d) q[d] = 0.f;
+  if (act) {
     const __nv_bfloat16* qp = p.q + g * p.q_gs + (long long)b * p.q_ld + (long long)h * p.q_hs + 8 * piece;
     const uint4 u = *reinterpret_cast<const uint4*>(qp);
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
 #pragma unroll
       for (int u = 0; u < AD_U; ++u) {
         const int pos = p0 + u * RPI + rg;
-        dst[u] = pos < p.len ? __ldg(reinterpret_cast<const uint4*>(base_ptr + (long long)pos * ld)) : make_uint4(0, 0, 0, 0);
+        dst[u] = (pos < p.len && act) ? __ldg(reinterpret_cast<const uint4*>(base_ptr + (long long)pos * ld)) : make_uint4(0, 0, 0, 0);
       }
     };
     // software pipeline without extra registers: the K registers are dead once the scores are formed, the V registers
@@ -154,12 +159,12 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
 #pragma unroll
     for (int d = 0; d < 8; ++d) out[d] += acc[d] * inv;
   }
-  if (rg == 0) {
+  if (rg == 0 && act) {
     uint4 u;
     __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
     for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(out[2 * j], out[2 * j + 1]);
-    *reinterpret_cast<uint4*>(p.o + g * p.o_gs + (long long)b * p.o_ld + (long long)h * HS + 8 * piece) = u;
+    *reinterpret_cast<uint4*>(p.o + g * p.o_gs + (long long)b * p.o_ld + (long long)h * p.hs + 8 * piece) = u;
   }
 }
 
@@ -172,7 +177,7 @@ extern "C" int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_te
   TA_CHECK_ARG(q && k && v && kv_batch_stride && o_bf16, "ta_attention_decode: null argument");
   TA_CHECK_ARG(n_src >= 1 && n_src <= AD_MAX_SRC, "ta_attention_decode: n_src %d not in [1, %d]", (int)n_src, AD_MAX_SRC);
   TA_CHECK_ARG(G > 0 && B > 0 && H > 0 && len > 0, "ta_attention_decode: non-positive shape");
-  TA_CHECK_ARG(hs == 8 || hs == 16 || hs == 32 || hs == 64, "ta_attention_decode: head size %d not in {8, 16, 32, 64}", (int)hs);
+  TA_CHECK_ARG(hs >= 8 && hs <= 64 && hs % 8 == 0, "ta_attention_decode: head size %d not supported (8..64, multiple of 8)", (int)hs);
   auto al16 = [](const void* ptr, int64_t a, int64_t b2, int64_t c) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && a % 8 == 0 && b2 % 8 == 0 && c % 8 == 0;
   };
@@ -197,12 +202,11 @@ extern "C" int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_te
   const long long total = (long long)G * B * H;
   const unsigned grid = (unsigned)ceil_div(total, AD_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (hs) {
-    case 64: launch_kernel(attn_decode_kernel<64>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
-    case 32: launch_kernel(attn_decode_kernel<32>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
-    case 16: launch_kernel(attn_decode_kernel<16>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
-    default: launch_kernel(attn_decode_kernel<8>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p); break;
-  }
+  // lane layout of the next power of two: 24 -> 32, 40 / 48 / 56 -> 64
+  if (hs > 32) launch_kernel(attn_decode_kernel<64>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p);
+  else if (hs > 16) launch_kernel(attn_decode_kernel<32>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p);
+  else if (hs > 8) launch_kernel(attn_decode_kernel<16>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p);
+  else launch_kernel(attn_decode_kernel<8>, dim3(grid), dim3(AD_WARPS * 32), 0, st, p);
   TA_CHECK_LAUNCH();
   return 0;
 }

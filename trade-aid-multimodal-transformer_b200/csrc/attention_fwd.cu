@@ -510,11 +510,8 @@ int make_head_map(CUtensorMap* out, const ta_attn_tensor* t, int hs, int H, int 
 template <int DP, bool MULTI>
 static int launch_attn_fwd(const AttnMaps& maps, const AttnFwdParams& p, cudaStream_t st) {
   constexpr int SMEM = (2 + 2 * AF_KV_STAGES + 4 + 1) * AF_TILE + 256 + 8192 + 64;
-  static bool attr = false;
-  if (!attr) {
-    TA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DP, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
-  }
+  static bool attr[TA_MAX_DEVICES] = {};
+  TA_CHECK_CUDA(ensure_dynamic_smem(attn_fwd_kernel<DP, MULTI>, SMEM, attr));
   const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
   launch_kernel(attn_fwd_kernel<DP, MULTI>, dim3(grid), dim3(AF_THREADS), SMEM, st, maps, p);
   TA_CHECK_LAUNCH();

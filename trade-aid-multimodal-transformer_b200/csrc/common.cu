@@ -11,8 +11,8 @@ namespace ta {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-static const unsigned long long* g_dropout_step = nullptr;   // device counter mixed into every dropout seed
-static std::atomic<int> g_sm_margin{0};                       // SMs left free for a concurrent kernel (ta_set_sm_margin)
+static thread_local const unsigned long long* g_dropout_step = nullptr;   // device counter mixed into every dropout seed; per calling thread
+static thread_local int g_sm_margin = 0;                      // SMs left free for a concurrent kernel (ta_set_sm_margin); per calling thread
 
 char* err_buf() { return g_err; }
 
@@ -43,7 +43,7 @@ int num_sms() {
     cached[dev] = n;
   }
   // persistent grids leave `margin` SMs (whole SM pairs, so CTA-pair clusters still fit) to whatever runs beside them
-  const int margin = g_sm_margin.load(std::memory_order_relaxed);
+  const int margin = g_sm_margin;
   const int n = (cached[dev] - margin) & ~1;
   return n < 2 ? 2 : n;
 }
@@ -60,10 +60,10 @@ int32_t ta_dropout_set_step_counter(const uint64_t* device_counter) {
 }
 int32_t ta_set_sm_margin(int32_t sms) {
   TA_CHECK_ARG(sms >= 0 && sms <= 128, "ta_set_sm_margin: margin %d out of range [0, 128]", (int)sms);
-  ta::g_sm_margin.store(sms, std::memory_order_relaxed);
+  ta::g_sm_margin = sms;
   return 0;
 }
-int32_t ta_get_sm_margin(void) { return ta::g_sm_margin.load(std::memory_order_relaxed); }
+int32_t ta_get_sm_margin(void) { return ta::g_sm_margin; }
 int64_t ta_launch_count(void) { return ta::g_launches.load(std::memory_order_relaxed); }
 void ta_reset_launch_count(void) { ta::g_launches.store(0, std::memory_order_relaxed); }
 }

@@ -36,6 +36,20 @@ const unsigned long long* dropout_step_counter();   // see ta_dropout_set_step_c
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE setting: a process that drives a second GPU after the first
+// must opt in there too. `done` is the launcher's own static flag array (one per kernel instantiation), indexed by device.
+constexpr int TA_MAX_DEVICES = 64;
+template <typename Kernel>
+static inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, bool (&done)[TA_MAX_DEVICES]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < TA_MAX_DEVICES && done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < TA_MAX_DEVICES) done[dev] = true;
+  return e;
+}
+
 // Programmatic dependent launch (PDL), opt-in with TA_PDL=1: every kernel of the library can be launched with the
 // programmatic-stream-serialization attribute and starts with pdl_prologue() - `griddepcontrol.launch_dependents` lets the
 // NEXT kernel of the stream be scheduled as soon as all CTAs of this one have started (its CTAs become resident as SMs

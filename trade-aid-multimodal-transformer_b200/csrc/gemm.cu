@@ -875,12 +875,8 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   plan_epilogue(p, em, Cfg::STAGE_BYTES, Cfg::NW);
   const int stages = p.stages;
   const int smem_bytes = stages * Cfg::STAGE_BYTES + Cfg::NW * p.epi_warp_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_LIMIT + 1024));
-    attr_set = true;
-  }
+  static bool attr_set[TA_MAX_DEVICES] = {};
+  TA_CHECK_CUDA(ensure_dynamic_smem(gemm_bf16_kernel<BLOCK_N>, SMEM_LIMIT + 1024, attr_set));
   const long long total = (long long)p.m_blocks * p.n_blocks * p.G0 * p.G1;
   const int grid = (int)(total < num_sms() ? total : num_sms());
   launch_kernel(gemm_bf16_kernel<BLOCK_N>, dim3(grid), dim3(Cfg::THREADS), smem_bytes, stream, tmA, tmB, em, p);
@@ -897,11 +893,8 @@ static int launch_gemm2(const ta_operand* A, const ta_operand* B, GemmParams& p,
   EpiMaps em;
   plan_epilogue(p, em, G2_STAGE_BYTES, 8);
   const int smem_bytes = p.stages * G2_STAGE_BYTES + 8 * p.epi_warp_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TA_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));
-    attr_set = true;
-  }
+  static bool attr_set[TA_MAX_DEVICES] = {};
+  TA_CHECK_CUDA(ensure_dynamic_smem(gemm2_bf16_kernel, SMEM_LIMIT + 1024, attr_set));
   const long long m_pairs = ceil_div(p.M, 2 * BLOCK_M);
   const long long total = m_pairs * p.n_blocks * p.G0 * p.G1;
   const long long max_clusters = num_sms() / 2;

@@ -15,6 +15,10 @@ constexpr int DM_THREADS = 256;
 constexpr int DM_ROWS = 1024;      // samples per pass through shared memory
 
 __device__ __forceinline__ int sign_of(double x) { return (x > 0.0) - (x < 0.0); }
+// ordering in which NaN is the largest value (torch.argmax / torch.max semantics)
+__device__ __forceinline__ bool nan_max_gt(float a, float b) { return a > b || (a != a && b == b); }
+__device__ __forceinline__ bool nan_max_eq(float a, float b) { return a == b || (a != a && b != b); }
+__device__ __forceinline__ long long clamp_token(long long t, int V) { return t < 0 ? 0 : (t >= V ? V - 1 : t); }
 
 __global__ void __launch_bounds__(DM_THREADS) directional_metrics_kernel(
     const float* __restrict__ logits, long long ld, const double* __restrict__ vals, const long long* __restrict__ prev,
@@ -30,22 +34,24 @@ __global__ void __launch_bounds__(DM_THREADS) directional_metrics_kernel(
     const int n = rows - r0 < DM_ROWS ? rows - r0 : DM_ROWS;
     for (int r = warp; r < n; r += DM_THREADS / 32) {
       const float* x = logits + (long long)(r0 + r) * ld;
-      // arg-max (lowest index among equal maxima, as torch.argmax)
-      float best = -INFINITY;
-      int arg = 0x7fffffff;
+      // arg-max as torch.argmax: lowest index among equal maxima, a NaN counts as the maximum (first NaN wins). The
+      // reference survives NaN logits (main.py:606-614 warns and goes on), so a row of NaNs must not index out of range:
+      // `arg` is always a valid column, and the token ids read from the batch are clamped into the vocabulary.
+      float best = x[0];
+      int arg = 0;
       for (int c = lane; c < V; c += 32) {
         const float v = x[c];
-        if (v > best) { best = v; arg = c; }
+        if (nan_max_gt(v, best) || (nan_max_eq(v, best) && c < arg)) { best = v; arg = c; }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
         const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        if (nan_max_gt(ob, best) || (nan_max_eq(ob, best) && oa < arg)) { best = ob; arg = oa; }
       }
-      const double ref = is_pct ? 0.0 : vals[prev[(long long)(r0 + r) * prev_stride]];
+      const double ref = is_pct ? 0.0 : vals[clamp_token(prev[(long long)(r0 + r) * prev_stride], V)];
       const int ps = sign_of(vals[arg] - ref);
-      const int as = sign_of(vals[actual[(long long)(r0 + r) * actual_stride]] - ref);
+      const int as = sign_of(vals[clamp_token(actual[(long long)(r0 + r) * actual_stride], V)] - ref);
       // softmax mass on the tokens whose direction equals the predicted one
       float tot = 0.f, dir = 0.f;
       for (int c = lane; c < V; c += 32) {

@@ -156,11 +156,12 @@ __global__ void embed_bwd_tok_kernel(const long long* __restrict__ idx, const fl
 // ------------------------------------------------------------------------------------------------ K4 LayerNorm
 // y = (x - mean) * rstd * gamma + beta, eps inside the sqrt (torch.nn.LayerNorm, model.py:189-190, 210, 330).
 // One warp per row; the row is held in registers (C <= 32*4*NV) so x is read from HBM exactly once.
+// y32 != nullptr: the output is written in fp32 instead (bf16x3 precision mode: it is split into hi + lo operands next).
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              long long rows_total, long long rows_per_group, int C, float eps) {
+              __nv_bfloat16* __restrict__ y, float* __restrict__ y32, long long ldy, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, long long rows_total, long long rows_per_group, int C, float eps) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -199,6 +200,12 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
     if (c < C) {
       const float4 gg = *reinterpret_cast<const float4*>(gm + c);
       const float4 bb = *reinterpret_cast<const float4*>(bt + c);
+      if (y32 != nullptr) {
+        *reinterpret_cast<float4*>(y32 + row * ldy + c) =
+            make_float4((v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y,
+                        (v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w);
+        continue;
+      }
       __nv_bfloat162 lo = __floats2bfloat162_rn((v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y);
       __nv_bfloat162 hi = __floats2bfloat162_rn((v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w);
       uint2 u;
@@ -633,15 +640,17 @@ int32_t ta_dropout_attn_mask(uint8_t* mask, int32_t n_src, int32_t G, int32_t B,
   return 0;
 }
 
-int32_t ta_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t ldy, float* mean,
-                         float* rstd, int64_t rows_total, int64_t rows_per_group, int32_t C, float eps, void* stream) {
-  TA_CHECK_ARG(x && gamma && beta && y_bf16 && mean && rstd, "ta_layernorm_fwd: null pointer");
+static int32_t layernorm_fwd_any(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y32, int64_t ldy,
+                                 float* mean, float* rstd, int64_t rows_total, int64_t rows_per_group, int32_t C, float eps,
+                                 void* stream) {
+  TA_CHECK_ARG(x && gamma && beta && (y_bf16 || y32) && mean && rstd, "ta_layernorm_fwd: null pointer");
   TA_CHECK_ARG(C % 4 == 0 && C <= 4096 && ldy % 4 == 0, "ta_layernorm_fwd: n_embd must be a multiple of 4 and <= 4096");
   TA_CHECK_ARG(rows_total > 0 && rows_per_group > 0 && rows_total % rows_per_group == 0, "ta_layernorm_fwd: bad rows");
+  TA_CHECK_ARG(!y32 || (reinterpret_cast<uintptr_t>(y32) & 15) == 0, "ta_layernorm_fwd_f32: y must be 16-byte aligned");
   const int grid = (int)ceil_div(rows_total, 8);
   auto st = (cudaStream_t)stream;
   auto* y = (__nv_bfloat16*)y_bf16;
-#define TA_LN_FWD(NV) launch_kernel(ln_fwd_kernel<NV>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, ldy, mean, rstd, rows_total, rows_per_group, C, eps)
+#define TA_LN_FWD(NV) launch_kernel(ln_fwd_kernel<NV>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, y32, ldy, mean, rstd, rows_total, rows_per_group, C, eps)
   if (C <= 128) TA_LN_FWD(1);
   else if (C <= 256) TA_LN_FWD(2);
   else if (C <= 512) TA_LN_FWD(4);
@@ -651,6 +660,18 @@ int32_t ta_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 #undef TA_LN_FWD
   TA_CHECK_LAUNCH();
   return 0;
+}
+
+int32_t ta_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t ldy, float* mean,
+                         float* rstd, int64_t rows_total, int64_t rows_per_group, int32_t C, float eps, void* stream) {
+  TA_CHECK_ARG(y_bf16, "ta_layernorm_fwd: null pointer");
+  return layernorm_fwd_any(x, gamma, beta, y_bf16, nullptr, ldy, mean, rstd, rows_total, rows_per_group, C, eps, stream);
+}
+
+int32_t ta_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y_f32, int64_t ldy, float* mean,
+                             float* rstd, int64_t rows_total, int64_t rows_per_group, int32_t C, float eps, void* stream) {
+  TA_CHECK_ARG(y_f32, "ta_layernorm_fwd_f32: null pointer");
+  return layernorm_fwd_any(x, gamma, beta, nullptr, y_f32, ldy, mean, rstd, rows_total, rows_per_group, C, eps, stream);
 }
 
 // launch shape of ln_bwd_kernel: TPR threads per row, R row sets per pass, grid.x blocks per group

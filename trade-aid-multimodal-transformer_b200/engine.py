@@ -61,17 +61,32 @@ class KVCache:
 
 
 class Engine:
-    def __init__(self, dims: Dims, device, ops=None, act_dtype=torch.bfloat16):
+    PRECISIONS = ("bf16", "bf16x3")
+
+    def __init__(self, dims: Dims, device, ops=None, act_dtype=None, precision=None):
         self.d = dims
-        # storage type of GEMM operands / saved activations. bf16 in the product (the CUDA kernels accept nothing
-        # else); the CPU test-suite also runs the host logic with float32 to check the backward wiring exactly.
-        self.act_dtype = act_dtype
         self.layout = Layout(dims)
         self.device = torch.device(device)
         if ops is None:
             if self.device.type != "cuda":
                 raise RuntimeError("tradeaid_b200 runs on CUDA (sm_100a) only; there is no CPU path")
             from . import lib as ops  # raises ImportError if libtradeaid_b200.so is missing
+        # precision: "bf16" = one bf16 rounding per GEMM operand (throughput mode, ~5e-3 normwise on the logits, like
+        # torch.autocast on the reference); "bf16x3" = fp32 activations and three-term split GEMM operands on the same
+        # kernels (precision.py: the north star's 2e-3 logits bound against the fp32 reference, 3x the GEMM FLOPs)
+        if precision is None:
+            precision = os.environ.get("TRADEAID_PRECISION", "bf16")
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {self.PRECISIONS}, got {precision!r}")
+        self.precision = precision
+        if precision == "bf16x3":
+            from .precision import SplitPrecisionOps
+            ops, act_dtype = SplitPrecisionOps(ops), torch.float32
+        # storage type of GEMM operands / saved activations. bf16 in the throughput mode (the CUDA GEMM / attention
+        # kernels accept nothing else); fp32 in the bf16x3 mode; the CPU test-suite also runs the host logic with float32
+        # over the plain emulation to check the backward wiring exactly.
+        self.act_dtype = act_dtype if act_dtype is not None else torch.bfloat16
+        act_dtype = self.act_dtype
         self.ops = ops
         n = self.layout.total
         self.master = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -94,6 +109,9 @@ class Engine:
             ng = 3 * dims.n_head // gsz
             self._bd = (gsz, ng, torch.zeros(dims.n_layer, dims.M, ng, gsz * dims.hs, gsz * dims.h2, dtype=act_dtype,
                                              device=self.device))
+        if hasattr(ops, "register_weight_storage"):      # bf16x3: splits of weight operands are kept between launches
+            for t in [self.shadow, *self._padded.values()] + ([self._bd[2]] if self._bd is not None else []):
+                ops.register_weight_storage(t)
         self._bufs = {}
         # output heads (model.py:339-352): with one vocabulary size for every modality (and TMA-able widths) the per-modality
         # weight kinds hd_w1_i, hd_b1_i, hd_w2_i, hd_b2_i sit a constant stride apart in the flat buffer, so all
@@ -119,6 +137,8 @@ class Engine:
         # (site, layer), a device step counter mixed in by the kernels makes every step (and graph replay) different
         self.dropout_base_seed = 0x5DEECE66D
         self._drop_step = None
+        self._drop_step_host = 0      # host mirror of the device counter (value the NEXT launches will read)
+        self._fwd_gen = 0             # generation stamp of the saved activations (model._Bridge checks it in backward)
         # where backward reports ("part", l) to its stage hook (trainer.py: the SM-margin window of the data-parallel
         # exchange): after the whole cross-attention backward of the layer ("cross") or after its attention kernels ("attn")
         self._dp_window = os.environ.get("TRADEAID_DP_WINDOW", "cross")
@@ -163,6 +183,8 @@ class Engine:
             for k in range(gsz):     # block k of every group -> rows [k*hs, (k+1)*hs), columns [k*h2, (k+1)*h2)
                 dst = w2bd.as_strided((n, hs, h2), (R * Cc, Cc, 1), w2bd.storage_offset() + k * (hs * Cc + h2))
                 ops.cast_pad(src[:, k], dst)
+        if hasattr(ops, "refresh_weight_splits"):
+            ops.refresh_weight_splits()
         self.shadows_stale = False
 
     def W(self, kind):
@@ -205,6 +227,7 @@ class Engine:
         if self._drop_step is None:
             self._drop_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._drop_step.add_(1)
+        self._drop_step_host += 1
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, idx, targets=None, save=True, train=False, cache=None):
@@ -229,7 +252,7 @@ class Engine:
             raise ValueError(f"sequence length {T} exceeds block_size {d.block_size}")
         BT = B * T
         bf, f32 = self.act_dtype, torch.float32
-        S = {"B": B, "T": T, "layers": [], "idx": idx, "pd": pd}
+        S = {"B": B, "T": T, "layers": [], "idx": idx, "pd": pd, "drop_step": self._drop_step_host}
         t0 = 0
         if cache is not None:
             if save or train or targets is not None:
@@ -338,7 +361,10 @@ class Engine:
                 ops.cross_entropy(logits[i], targets[i].view(BT), row_loss, losses[i:i + 1], dl, 1.0)
                 dls.append(dl)
             S["dlogits"] = dls
-        self._saved = S if save else None
+        if save:       # a forward that does not save uses its own (unsuffixed) buffers and leaves the saved set alone, so
+            self._fwd_gen += 1          # forward(save) -> evaluation forward -> backward() works as with torch's autograd
+            S["gen"] = self._fwd_gen
+            self._saved = S
         if cache is not None:
             cache.length = t0 + T
         return [lg.view(B, T, -1) for lg in logits], losses
@@ -484,6 +510,11 @@ class Engine:
         BT = B * T
         bf, f32 = self.act_dtype, torch.float32
         pd = S.get("pd", 0.0)
+        restore_step = None
+        if pd > 0.0 and S.get("drop_step", self._drop_step_host) != self._drop_step_host:
+            # a later training-mode forward advanced the device counter: regenerate THIS forward's masks
+            restore_step = self._drop_step_host
+            self._drop_step.fill_(S["drop_step"])
         # upstream gradient of a dropout site = stream gradient o keep / (1 - p), same mask as the forward epilogue
         dxm = self.buf("dxm", (M, BT, C), bf) if pd > 0.0 else None
 
@@ -599,6 +630,8 @@ class Engine:
         ops.embed_bwd(S["idx"].view(M, BT), dx, self._voff, max(d.vocab_sizes), G["tok"], G["pos"][:T], B, T)
         if T < d.block_size:
             G["pos"][T:].zero_()
+        if restore_step is not None:
+            self._drop_step.fill_(restore_step)
         if stage_hook is not None:
             stage_hook("embed")
 

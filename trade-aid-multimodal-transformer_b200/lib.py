@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class TaOperand(C.Structure):
@@ -243,6 +243,9 @@ _gather_batch = _sig("ta_gather_batch", _P, _I64, _I32, _P, _I32, _I32, _P, _P, 
 _embed_fwd = _sig("ta_embed_fwd", _P, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _P)
 _embed_bwd = _sig("ta_embed_bwd", _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _P)
 _ln_fwd = _sig("ta_layernorm_fwd", _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _F32, _P)
+_ln_fwd_f32 = _sig("ta_layernorm_fwd_f32", _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _F32, _P)
+_split = _sig("ta_split_bf16", _P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P)
+_convert = _sig("ta_convert", _P, _I32, _I64, _I64, _I64, _P, _I32, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _P)
 _ln_bwd_ws = _sig("ta_layernorm_bwd_workspace_floats", _I64, _I64, _I32, restype=_I64)
 _ln_bwd = _sig("ta_layernorm_bwd", _P, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _P)
 _ce = _sig("ta_cross_entropy", _P, _I64, _P, _P, _P, _P, _I64, _I64, _I32, _F32, _P)
@@ -323,6 +326,49 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
     assert y.stride(0) == rows * y.stride(1)
     _check(_ln_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), y.stride(1), _ptr(mean), _ptr(rstd), G * rows, rows, Cc,
                    eps, _stream()))
+
+
+def layernorm_fwd_f32(x, gamma, beta, y, mean, rstd, eps=1e-5):
+    """layernorm_fwd with an fp32 output y [G, rows, ldy] (bf16x3 precision mode)."""
+    import torch
+    G, rows, Cc = x.shape
+    assert x.is_contiguous() and gamma.is_contiguous() and beta.is_contiguous() and y.stride(-1) == 1
+    assert y.dtype == torch.float32 and y.stride(0) == rows * y.stride(1)
+    _check(_ln_fwd_f32(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), y.stride(1), _ptr(mean), _ptr(rstd), G * rows, rows, Cc,
+                       eps, _stream()))
+
+
+def _view4(t):
+    """(g1 stride, g0 stride, row stride, G1, G0, R, C) of a [..<=2 group dims.., R, C] view with unit inner stride."""
+    assert t.dim() >= 2 and t.dim() <= 4 and t.stride(-1) == 1
+    gs0, gs1, G0, G1 = _grp(t, 2)
+    return gs1, gs0, t.stride(-2), G1, G0, t.shape[-2], t.shape[-1]
+
+
+SPLIT_A, SPLIT_B = 0b010, 0b100      # lo slot of the three K-concatenated terms: [hi|lo|hi] x [hi|hi|lo]
+
+
+def split_bf16(src, dst, lo_mask, terms=3, concat_rows=False):
+    """src fp32 [.., R, C] -> dst bf16 [.., R, terms*C] (or [.., terms*R, C] with concat_rows): slot k holds lo = bf16(x - hi)
+    where bit k of lo_mask is set, hi = bf16(x) elsewhere."""
+    import torch
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.dim() == dst.dim()
+    s1, s0, sr, G1, G0, R, Cc = _view4(src)
+    d1, d0, dr, H1, H0, Rd, Cd = _view4(dst)
+    assert (G1, G0) == (H1, H0) and (Rd, Cd) == ((terms * R, Cc) if concat_rows else (R, terms * Cc))
+    _check(_split(_ptr(src), s1, s0, sr, _ptr(dst), d1, d0, dr, G1, G0, R, Cc, terms, lo_mask, 1 if concat_rows else 0,
+                  _stream()))
+
+
+def convert(src, dst):
+    """dst[...] = src[...] between fp32 and bf16 (either direction, or a same-type strided copy); [..<=2 group dims.., R, C]
+    views of equal shape with unit inner stride."""
+    import torch
+    assert src.shape == dst.shape and src.dtype in (torch.float32, torch.bfloat16) and dst.dtype in (torch.float32, torch.bfloat16)
+    s1, s0, sr, G1, G0, R, Cc = _view4(src)
+    d1, d0, dr, _, _, _, _ = _view4(dst)
+    _check(_convert(_ptr(src), 1 if src.dtype == torch.bfloat16 else 0, s1, s0, sr, _ptr(dst),
+                    1 if dst.dtype == torch.bfloat16 else 0, d1, d0, dr, G1, G0, R, Cc, _stream()))
 
 
 def layernorm_bwd_workspace(G, rows, Cc):

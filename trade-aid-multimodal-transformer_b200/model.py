@@ -25,6 +25,18 @@ import torch.nn.functional as F
 from .params import Dims, Layout
 
 _explicit_cfg = None
+_precision = None      # None: the TRADEAID_PRECISION environment variable, default "bf16" (engine.Engine.PRECISIONS)
+
+
+def set_precision(precision):
+    """"bf16": single-pass bf16 GEMM operands (throughput mode). "bf16x3": fp32 activations and three-term split operands on
+    the same kernels — logits within 2e-3 of the reference's fp32 forward (precision.py). Applies to models moved to the
+    device afterwards."""
+    global _precision
+    from .engine import Engine
+    if precision is not None and precision not in Engine.PRECISIONS:
+        raise ValueError(f"precision must be one of {Engine.PRECISIONS}")
+    _precision = precision
 
 
 def configure(block_size, n_embd, n_head, n_layer, dropout=0.0):
@@ -55,18 +67,26 @@ class _Bridge(torch.autograd.Function):
     def forward(ctx, anchor, model, idx, tgt):
         logits, losses = model._engine.forward(idx, tgt, save=True, train=model.training)
         ctx.model = model
+        ctx.gen = model._engine._fwd_gen       # the engine keeps ONE set of saved activations: stamp it
         return losses.clone()
 
     @staticmethod
     def backward(ctx, dlosses):
         model = ctx.model
-        w = dlosses.tolist()
+        eng = model._engine
+        if eng is None or eng._saved is None or eng._saved.get("gen") != ctx.gen:
+            raise RuntimeError("tradeaid_b200: backward() of a forward whose saved activations are gone - the engine keeps the "
+                               "activations of the LATEST grad-enabled forward only (another forward(idx, targets) with "
+                               "gradients enabled ran in between); call backward() before the next training forward")
+        ones = model._ones_like(dlosses)
+        # sum(losses).backward() (main.py:646) hands in exact ones: compared on the device, no read-back on that path
+        w = None if (dlosses is ones or bool(torch.equal(dlosses, ones))) else dlosses.tolist()
         # torch accumulates into an existing .grad. The .grad tensors ARE views of the engine's gradient buffer, which the
         # backward program overwrites, so gradients still held by the parameters (a second backward without zero_grad: gradient
         # accumulation) are set aside first and added back. main.py calls optimizer.zero_grad(set_to_none=True) before every
         # backward (main.py:648): nothing is held then and nothing is copied.
         held = model._held_grads()
-        model._engine.backward(None if all(x == 1.0 for x in w) else w)
+        eng.backward(w)
         for view, old in held:
             view.add_(old)
         model._deposit_grads()
@@ -148,11 +168,12 @@ class MultimodalTransformer(nn.Module):
             raise TypeError("tradeaid_b200 keeps fp32 master parameters (bf16 operand copies are internal)")
         if dev.type == "cuda":
             from .engine import Engine
-            eng = Engine(self._dims, dev)
+            eng = Engine(self._dims, dev, precision=_precision)
             flat = eng.master
         elif _ops_override is not None:      # tests only: the host program over the CPU emulation of the kernel namespace
             from .engine import Engine
-            eng = Engine(self._dims, dev, ops=_ops_override, act_dtype=torch.float32)
+            eng = Engine(self._dims, dev, ops=_ops_override, act_dtype=None if _precision == "bf16x3" else torch.float32,
+                         precision=_precision)
             flat = eng.master
         else:
             eng, flat = None, torch.zeros(self._layout.total, dtype=torch.float32, device=dev)
@@ -165,6 +186,12 @@ class MultimodalTransformer(nn.Module):
         self._flat, self._engine = flat, eng
         self._anchor = torch.zeros(1, device=dev, requires_grad=True) if eng is not None else None
         self._dirty = True
+
+    def _ones_like(self, t):
+        o = getattr(self, "_ones", None)
+        if o is None or o.shape != t.shape or o.device != t.device or o.dtype != t.dtype:
+            o = self._ones = torch.ones_like(t)
+        return o
 
     def _held_grads(self):
         """[(gradient-buffer view, copy of its current content)] for the parameters whose .grad is such a view."""
@@ -217,7 +244,6 @@ class MultimodalTransformer(nn.Module):
             return [l.clone() for l in logits], None
         tgt = torch.stack([t.to(eng.device, torch.int64) for t in targets_list[:M]]).contiguous()
         if torch.is_grad_enabled():
-            par_grads = [p.grad for _, p in self._param_list[:1]]  # noqa: F841 (keeps alias semantics explicit)
             losses = _Bridge.apply(self._anchor, self, idx, tgt)
             logits = [l.view(B, T, -1).clone() for l in eng._saved["logits"]]
         else:

@@ -63,12 +63,13 @@ def _store(split):
 batch_shard = None   # (rank, world) in data-parallel PARITY mode; None: every process draws its own batches
 
 
-def get_batch(split, is_training):
+def get_batch(split, is_training, shard=True):
     """training_utils.py:333-384. Returns (xb_list, yb_list): per modality int64 [batch_size, block_size] on `device`.
     With `batch_shard = (rank, world)` (data-parallel parity mode, fixed GLOBAL batch_size): every rank draws the same
     batch_size indices from its identically seeded host generator - the CPU RNG stream stays bit-identical to the
     single-process reference - and gathers only rows [rank*B/world, (rank+1)*B/world); the shards of all ranks
-    concatenate to the single-process batch."""
+    concatenate to the single-process batch. `shard=False` returns the whole batch regardless (estimate_loss: an
+    evaluation batch is never split by rows - its iterations are dealt to the ranks instead)."""
     train_store = _store('train')
     for r in range(num_modalities):
         this_rand_size = all_modality_params[r][2]
@@ -83,7 +84,7 @@ def get_batch(split, is_training):
     store = train_store if split == 'train' else _store('val')
     T, B = _get('block_size'), _get('batch_size')
     ix = generate_batch_starting_indices(store.N, T, B, split, file_lengths, is_percents)
-    if batch_shard is not None:
+    if batch_shard is not None and shard:
         rank, world = batch_shard
         if B % world != 0:
             raise ValueError(f"batch_size ({B}) must be divisible by the number of data-parallel ranks ({world})")
@@ -204,7 +205,9 @@ def estimate_loss(current_step=None, max_steps=None):
         counts = cert = None
         total_losses = []
         for k in range(eval_iters):
-            xb_list, yb_list = get_batch(state, 0)
+            # whole batches even in data-parallel parity mode (`batch_shard`): the owner of iteration k evaluates all
+            # batch_size samples of it, so the totals are those of the single-process run
+            xb_list, yb_list = get_batch(state, 0, shard=False)
             if k % world != rank:
                 continue
             with torch.no_grad():
