@@ -6,8 +6,12 @@
 A step = one pass of the hot path over one batch of synthetic input: get_batch (host torch.randint -> index upload ->
 device window gather) -> forward -> backward -> [gradient all-reduce] -> fused AdamW. One JSON line on stdout (rank 0).
 Metric (BASELINE.json): training tokens/s (tokens = modalities x batch x block_size per step, whole job).
-`--impl reference` times the reference's algorithm on the host CPU cores: the oracle port (oracle/restatement.py) —
-the reference is pure Python and /root/reference does not exist on the GPU box.
+`--impl reference` times the reference's own CPU implementation on the host cores: the UNMODIFIED reference from oracle/_ref
+(model.MultimodalTransformer + training_utils.get_batch + torch.optim.AdamW, main.py:641-650; oracle/make_ref.py copies it in
+the build container and it travels with the snapshot), falling back to the oracle port (oracle/restatement.py) when that copy
+is absent. `--impl reference-eager` is the extra comparator of BASELINE.md section 3: the same unmodified reference on the
+B200 in torch eager (`--ref-mode fp32|tf32|autocast`). `--tier compat` measures the drop-in the way main.py drives it
+(m(xb, yb); sum(losses).backward(); stock torch.optim.AdamW) instead of the engine-owned Trainer step.
 """
 import argparse
 import json
@@ -30,7 +34,11 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-eager"])
+    ap.add_argument("--ref-mode", default="fp32", choices=["fp32", "tf32", "autocast"], help="reference-eager: matmul precision")
+    ap.add_argument("--tier", default="engine", choices=["engine", "compat"], help="compat: the reference's own loop body "
+                    "(nn.Module forward, autograd bridge, torch.optim.AdamW) over the kernels")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--config", default=os.environ.get("TRADEAID_BENCH_CONFIG", "c4"))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--rows", type=int, default=0, help="synthetic rows override")
@@ -99,24 +107,85 @@ def cpu_oracle_run(cfg, batch, steps, warmup, lr=3e-4):
     return M * batch * T / sec, sec, torch.get_num_threads()
 
 
+CPU_SAMPLE_BATCH = {"c1": 4, "c2": 16, "c3": 4, "c4": 1, "c5": 1}     # bounded CPU sample: batch of the timed reference step
+
+
+def cpu_reference_run(cfg, batch, steps, warmup, lr=3e-4):
+    """The UNMODIFIED reference (oracle/_ref) on the host cores through its own loop body (main.py:641-650). Returns
+    (tokens_per_s, seconds_per_step, threads) or None when oracle/_ref is absent."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    run = ref_runner.ReferenceRun(cfg, batch, "cpu", min(cfg["rows"], 200_000), lr=lr)
+    sec, _ = run.timed(steps, warmup)
+    return len(cfg["vocab"]) * batch * cfg["block_size"] / sec, sec, torch.get_num_threads()
+
+
+def cpu_baseline_of(cfg, config_name, batch, steps, warmup):
+    """cpu_baseline object: oracle/_ref ("reference") when it is there, else the oracle port ("port")."""
+    r = cpu_reference_run(cfg, batch, steps, warmup)
+    if r is not None:
+        tps, sec, threads = r
+        return tps, sec, {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "reference",
+                          "sample": f"unmodified reference (oracle/_ref: model.MultimodalTransformer + training_utils.get_batch + "
+                                    f"torch.optim.AdamW, main.py:641-650) on the host CPU, fp32, full model, batch {batch} of "
+                                    f"{cfg['batch']}, 200 k synthetic rows, {steps} timed steps ({sec:.2f} s/step)"}
+    tps, sec, threads = cpu_oracle_run(cfg, batch, steps, warmup)
+    return tps, sec, {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                      "sample": f"oracle port (oracle/restatement.py) of model.py fwd+bwd + AdamW + get_batch on CPU (oracle/_ref "
+                                f"absent), full model, batch {batch} of {cfg['batch']}, {steps} timed steps ({sec:.2f} s/step)"}
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.cpu_batch or max(1, min(cfg["batch"], {"c1": 4, "c2": 16, "c3": 2, "c4": 1, "c5": 1}.get(args.config, 1)))
-    tps, sec, threads = cpu_oracle_run(cfg, B, args.steps, args.warmup)
+    B = args.cpu_batch or max(1, min(cfg["batch"], CPU_SAMPLE_BATCH.get(args.config, 1)))
+    # bounded: a c4 step of the unmodified reference is ~45 s on 8 host cores (plus ~60 s to build the 1.89 G-parameter model)
+    heavy = args.config in ("c4", "c5")
+    steps, warmup = max(1, min(args.steps, 2 if heavy else 5)), min(args.warmup, 1)
+    tps, sec, cb = cpu_baseline_of(cfg, args.config, B, steps, warmup)
     line = {
         "impl": "reference", "metric": "training tokens/s", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "timed_steps": steps, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, B, 1),
-        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle port (oracle/restatement.py) of model.py fwd+bwd + AdamW + get_batch on CPU, "
-                                   f"full model, batch {B} of {cfg['batch']} per step"},
+        "config": workload_config(args, cfg, B, 1), "cpu_baseline": cb,
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_reference_eager(args, cfg):
+    """BASELINE.md section 3, "GPU comparator": the unmodified reference with device='cuda' in torch eager — fp32, TF32 matmuls,
+    or torch.autocast(bf16). Not the driver's reference arm (that one is the CPU path); an extra line for profiles/."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        print(json.dumps({"impl": "reference-eager", "unavailable": "oracle/_ref is missing"}), flush=True)
+        return
+    torch.cuda.set_device(0)
+    B = args.batch or cfg["batch"]
+    sampler = ClockSampler(0)
+    run = ref_runner.ReferenceRun(cfg, B, "cuda", min(args.rows or cfg["rows"], 200_000), mode=args.ref_mode)
+    for _ in range(max(1, args.warmup)):
+        run.step()
+    torch.cuda.synchronize()
+    sampler.start()
+    sec, loss = run.timed(args.steps, 0)
+    clocks = sampler.stop()
+    M, T = len(cfg["vocab"]), cfg["block_size"]
+    tps = M * B * T / sec
+    from tradeaid_b200 import synthetic as syn
+    fl = syn.train_flops_per_step(cfg, B)
+    print(json.dumps({"impl": "reference-eager", "ref_mode": args.ref_mode, "metric": "training tokens/s", "value": tps,
+                      "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": {"fp32": "f32", "tf32": "tf32", "autocast": "bf16 (torch.autocast)"}[args.ref_mode],
+                      "data": "synthetic", "config": workload_config(args, cfg, B, 1), "clocks": clocks,
+                      "achieved_tflops": fl / sec / 1e12, "loss_sum_last_step": loss,
+                      "hbm_bytes_allocated": torch.cuda.max_memory_allocated(),
+                      "note": "unmodified reference (oracle/_ref) through its own loop body, torch eager on the B200"}), flush=True)
 
 
 def workload_config(args, cfg, batch, world):
@@ -179,10 +248,14 @@ class ClockSampler:
 class TimedOps:
     """Proxy of the kernel namespace that brackets every call with CUDA events on the launching stream."""
 
-    def __init__(self, ops):
+    def __init__(self, ops, blockdiag=None):
         self._ops = ops
         self.records = []   # (name, start_event, end_event, flops)
         self.detail = {}
+        # (storage pointer of the packed block-diagonal stage-2 weights, blocks per group): those launches multiply exact
+        # zeros off the diagonal - only 1/gsz of the launched FLOPs are algorithmic (model.py:36-50)
+        self._bd = blockdiag
+        self.launched_flops = 0.0
 
     def __getattr__(self, name):
         fn = getattr(self._ops, name)
@@ -202,6 +275,9 @@ class TimedOps:
                 for s in A.shape[:-2]:
                     G *= s
                 flops = 2.0 * Mm * N * K * G
+                self.launched_flops += flops
+                if self._bd is not None and B.untyped_storage().data_ptr() == self._bd[0]:
+                    flops /= self._bd[1]
                 name_key = f"gemm M={Mm} N={N} K={K} G={G} maj={am}{bm} act={kw.get('act', 0)} aux={kw.get('aux_mode', 0)} " \
                            f"res={int(kw.get('residual') is not None)} f32={int(kw.get('out_f32') is not None)} " \
                            f"bf16={int(kw.get('out_bf16') is not None)}"
@@ -260,7 +336,7 @@ def run_ours(args, cfg):
 
     # ---- model, data, trainer
     dims = Dims(V, cfg["cross"], T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"], dropout=args.dropout)
-    eng = Engine(dims, dev)
+    eng = Engine(dims, dev, precision=args.precision)
     eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))   # same weights on every rank
     tr = Trainer(eng, lr=3e-4, process_group=pg, world_size=world, overlap=not args.no_overlap,
                  grad_buckets=args.buckets, sm_margin=args.sm_margin)
@@ -362,13 +438,14 @@ def run_ours(args, cfg):
                       "Trainer step (fwd+bwd+AdamW) -> per-modality losses copied back and read on the host every step"}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM), from one instrumented eager step
-    timed = TimedOps(lib)
+    base_ops = eng.ops
+    timed = TimedOps(base_ops, (eng._bd[2].untyped_storage().data_ptr(), eng._bd[0]) if eng._bd is not None else None)
     eng.ops = tr.ops = timed
     tr.step(idx, tgt)          # un-timed settle
     timed.records.clear()
     tr.step(idx, tgt)
     agg = timed.summary()
-    eng.ops = tr.ops = lib
+    eng.ops = tr.ops = base_ops
     if rank == 0 and os.environ.get("TRADEAID_BENCH_DETAIL"):
         rows = []
         for k, evs in timed.detail.items():
@@ -391,7 +468,9 @@ def run_ours(args, cfg):
                 "traffic_detail": traffic_of_dominant_launch(),
                 "peak_source": f"{pk['source']} (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": gm[1], "gemm_ms_per_step": round(gm[0], 3), "gemm_share_of_step": round(gm[0] / tot_ms, 4),
-                "algorithmic_flops_per_step_gemm": gm[2],
+                "algorithmic_flops_per_step_gemm": gm[2], "launched_flops_per_step_gemm": timed.launched_flops / 2,
+                "achieved_note": "algorithmic FLOPs (the exact zeros of the block-diagonal stage-2 packing are not counted) / "
+                                 "CUDA-event time of the GEMM launches of one eager step",
                 "step_mfu": {"algorithmic_train_tflop_per_step": flops_step / 1e12,
                              "achieved_tflops_per_gpu": flops_step / (ms_per_step * 1e-3) / 1e12,
                              "frac_of_measured_sustained": flops_step / (ms_per_step * 1e-3) / 1e12 / pk["tc_sustained"],
@@ -399,15 +478,14 @@ def run_ours(args, cfg):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = args.cpu_batch or {"c1": 4, "c2": 16, "c3": 2, "c4": 1, "c5": 1}.get(args.config, 1)
-        tps, sec, threads = cpu_oracle_run(cfg, cb, 2, 1)
-        cpu_baseline = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                        "sample": f"oracle port of the reference step (get_batch + fwd + bwd + AdamW, fp32) on the host CPU, "
-                                  f"full model, batch {cb} of {B}, 2 timed steps ({sec:.2f} s/step)"}
+        cb = args.cpu_batch or CPU_SAMPLE_BATCH.get(args.config, 1)
+        heavy = args.config in ("c4", "c5")        # ~45 s per step of the unmodified reference on 8 cores: one timed step
+        _, _, cpu_baseline = cpu_baseline_of(cfg, args.config, cb, 1 if heavy else 2, 0 if heavy else 1)
     if rank == 0:
         line = {"metric": "training tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, B, world),
+                "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split bf16 operands, fp32 activations)",
+                "data": "synthetic", "config": workload_config(args, cfg, B, world), "precision": args.precision, "tier": "engine",
                 "exchange": None if world == 1 else (
                     {"kind": "bucketed fp32 all-reduce overlapped with backward", "buckets": len(tr._buckets),
                      "bucket_bytes": tr.bucket_bytes(), "sm_margin": tr.sm_margin} if tr.overlap else
@@ -419,6 +497,82 @@ def run_ours(args, cfg):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ compat tier
+def run_compat(args, cfg):
+    """`--tier compat`: the step the way the reference's main.py drives it (main.py:641-650) over the drop-in nn.Module —
+    `logits, losses = m(xb_list, yb_list)`, `sum(losses).backward()` through the autograd bridge into the engine's backward
+    program, stock `torch.optim.AdamW(m.parameters(), lr)`; no CUDA graph, the operand copies of the weights are re-cast
+    after every optimizer step. One GPU (the reference has no data parallelism of its own)."""
+    from tradeaid_b200 import lib, model as tmodel, synthetic as syn
+    from tradeaid_b200.feeder import TokenStore, generate_batch_starting_indices
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    T, V = cfg["block_size"], cfg["vocab"]
+    M = len(V)
+    rows = args.rows or cfg["rows"]
+    tmodel.configure(T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"], dropout=args.dropout)
+    tmodel.set_precision(args.precision)
+    torch.manual_seed(0)
+    m = tmodel.MultimodalTransformer(M, list(V), syn.modality_params(cfg)).to(dev)
+    opt = torch.optim.AdamW(m.parameters(), lr=3e-4)
+    streams = syn.make_streams(cfg, dev, rows)
+    n_train = int(rows * 0.9)
+    store = TokenStore([s[:n_train] for s in streams], dev)
+    del streams
+    torch.manual_seed(1)
+    B = args.batch or cfg["batch"]
+
+    def step(B):
+        ix = generate_batch_starting_indices(n_train, T, B, "train", [n_train], False)
+        xb, yb = store.gather(ix, T)
+        logits_list, losses_list = m([xb[i] for i in range(M)], [yb[i] for i in range(M)])
+        total_loss = sum(losses_list)
+        opt.zero_grad(set_to_none=True)
+        total_loss.backward()
+        opt.step()
+        return total_loss
+
+    while True:
+        try:
+            for _ in range(max(args.warmup, 3)):
+                step(B)
+            break
+        except torch.OutOfMemoryError:
+            opt.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
+            if B == 1:
+                raise
+            B //= 2                 # torch.optim.AdamW's foreach temporaries on top of the engine's buffers
+    torch.cuda.synchronize()
+    lib.reset_launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(B)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    value = M * B * T / (ms_per_step * 1e-3)
+    pk = peaks()
+    fl = syn.train_flops_per_step(cfg, B)
+    print(json.dumps({"metric": "training tokens/s", "value": value, "unit": "tokens/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "data": "synthetic",
+                      "config": workload_config(args, cfg, B, 1), "tier": "compat", "precision": args.precision,
+                      "api": "tradeaid_b200.model.MultimodalTransformer: m(xb, yb) -> sum(losses).backward() -> torch.optim.AdamW.step() "
+                             "(main.py:641-650), device-side get_batch gather",
+                      "wall_ms_per_step": wall / args.steps * 1e3, "gpu_launches": lib.launch_count(), "clocks": clocks,
+                      "step_mfu": {"achieved_tflops_per_gpu": fl / (ms_per_step * 1e-3) / 1e12,
+                                   "frac_of_measured_sustained": fl / (ms_per_step * 1e-3) / 1e12 / pk["tc_sustained"]},
+                      "loss_sum_last_step": float(loss.detach()), "hbm_bytes_allocated": torch.cuda.max_memory_allocated(dev)}),
+          flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ inference (c5)
@@ -651,8 +805,12 @@ def main():
     cfg = syn.CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.impl == "reference-eager":
+        run_reference_eager(args, cfg)
     elif args.config == "c5":
         run_inference(args, cfg)
+    elif args.tier == "compat":
+        run_compat(args, cfg)
     else:
         run_ours(args, cfg)
 

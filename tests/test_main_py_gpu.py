@@ -1,0 +1,72 @@
+"""The drop-in, run for real on the GPU: the UNMODIFIED reference program from oracle/_ref
+(made by oracle/make_ref.py in the build container; it travels with the snapshot) against the same program with the
+INTEGRATION.md shims, both on cuda — main.py on the demo (BASELINE.json configs[0]: console text, losses, directional
+metrics, checkpoints) and `generate` token by token. The heavy lifting is in tests/main_py_dropin_run.py and
+tests/generate_vs_reference_run.py (subprocesses: the reference's module names `model`, `training_utils`, `config_utils` must
+not leak into this test process)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(ROOT, "oracle", "_ref")
+needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "main.py")),
+                               reason="oracle/_ref is missing: run `python oracle/make_ref.py` in the build container")
+
+
+def _record(**kw):
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "parity_r02.jsonl"), "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+@needs_ref
+@pytest.mark.parametrize("precision,loss_tol,count_tol,weight_tol", [("bf16", 1e-2, 8, 2e-2), ("bf16x3", 2e-3, 3, 5e-3)])
+def test_reference_main_py_unmodified_vs_shimmed_on_cuda(precision, loss_tol, count_tol, weight_tol):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "main_py_dropin_run.py"), "--ref", REF, "--device", "cuda",
+                        "--precision", precision, "--loss-tol", str(loss_tol), "--count-tol", str(count_tol),
+                        "--weight-tol", str(weight_tol)], capture_output=True, text=True, timeout=1700)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert line, (r.stdout[-2000:], r.stderr[-2000:])
+    res = json.loads(line[-1])
+    _record(test="main_py_dropin_cuda", **res)
+    assert res["ok"], res
+    assert res["console_text_diffs"] == 0 and res["log_text_diffs"] == 0 and res["checkpoint_keys_equal"]
+    assert res["kernel_launches"] > 1000          # the shimmed run really went through libtradeaid_b200.so
+
+
+@needs_ref
+def test_generate_tokens_equal_the_reference_on_cuda():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "generate_vs_reference_run.py"), REF, "cuda"],
+                       capture_output=True, text=True, timeout=900)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and line, (r.stdout[-2000:], r.stderr[-3000:])
+    res = json.loads(line[-1])
+    _record(test="generate_vs_reference_cuda", **res)
+    for case in res["cases"]:
+        frac = case["identical"] / case["tokens"]
+        if case["precision"] == "bf16x3":
+            assert frac >= 0.98 and case["first_step_max_prob_diff"] <= 2e-4, case
+        else:
+            assert frac >= 0.9 and case["first_step_max_prob_diff"] <= 5e-3, case
+
+
+@needs_ref
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda-graph"])
+def test_launcher_on_one_gpu_reproduces_the_reference_main_py(graph):
+    """Row x-1: `python -m tradeaid_b200.launch` (main.py's preamble unchanged, its loop over Trainer.step: fused AdamW, the
+    engine's own backward) against the unmodified main.py, both on cuda."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "main_py_dropin_run.py"), "--ref", REF, "--device", "cuda", "--launcher", "1",
+           "--loss-tol", "1e-2", "--count-tol", "8", "--weight-tol", "2e-2"] + (["--graph"] if graph else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1700)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert line, (r.stdout[-2000:], r.stderr[-2000:])
+    res = json.loads(line[-1])
+    _record(test="launcher_1gpu_vs_reference_main_py", graph=graph, **res)
+    assert res["ok"], res
