@@ -20,40 +20,16 @@
 #include <cuda_bf16.h>
 
 #include "../../include/tradeaid_b200.h"
+#include "attention_fwd.cuh"
 #include "common.cuh"
 #include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ta {
 
-constexpr int ATT_MAX_SRC = 8;
 constexpr int AF_MATH_WARPS = 16;
 constexpr int AF_THREADS = (AF_MATH_WARPS + 4) * 32;   // warps 0-15 math, 16 loader, 17 issuer, 18-19 idle (whole warpgroup for setmaxnreg)
 constexpr int AF_KV_STAGES = 3;
-constexpr int AF_TILE = 16384;   // 128 rows x 128 bytes
-
-struct AttnMaps {
-  CUtensorMap q;
-  CUtensorMap k[ATT_MAX_SRC];
-  CUtensorMap v[ATT_MAX_SRC];
-  CUtensorMap o;                     // TMA store targets
-  CUtensorMap o_src[ATT_MAX_SRC];
-};
-
-struct AttnFwdParams {
-  int T, B, H, G, hs, n_src, n_qtiles, total_work;
-  int debug;   // TA_ATTN_DEBUG (dev only): 16 = no TMEM source sum, 32 = no output staging / stores
-  uint32_t drop_thresh;            // dropout on the probabilities (model.py:69, 151): 16-bit lane threshold, 0 = off
-  float drop_scale;                // 1 / (1 - p)
-  unsigned long long drop_seed;
-  const unsigned long long* drop_step;
-  float scale_log2;
-  __nv_bfloat16* o;       // [G][B*T][ldo], head h at column h*hs
-  long long ldo, o_gs;
-  __nv_bfloat16* o_src;   // optional per-source outputs [n_src][G][B*T][ldo] (needed by backward when n_src > 1)
-  long long o_src_stride;
-  float* lse;             // [n_src][G][B][H][T], natural log
-};
 
 // The (work, i, s, j) schedule; every warp role walks the same sequence with its own copy.
 struct AfIter {
@@ -563,6 +539,10 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
   TA_CHECK_ARG(total < (1ll << 31), "attention grid too large");
   p.total_work = (int)total;
   auto st = (cudaStream_t)stream;
+  // TA_ATTN_FWD=1 keeps the first-generation kernel of this file (one tile at a time on 16 math warps); default: the
+  // two-stream kernel of attention_fwd2.cu
+  static const int version = [] { const char* e = getenv("TA_ATTN_FWD"); return e ? atoi(e) : 2; }();
+  if (version != 1) return launch_attn_fwd2(maps, p, st);
   if (n_src > 1) {
     if (hs <= 16) return launch_attn_fwd<16, true>(maps, p, st);
     if (hs <= 32) return launch_attn_fwd<32, true>(maps, p, st);

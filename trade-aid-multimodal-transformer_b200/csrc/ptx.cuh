@@ -202,6 +202,18 @@ __device__ __forceinline__ void umma_bf16_ws(uint32_t tmem_d, uint64_t desc_a, u
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand in TENSOR MEMORY (the "TS" form): A[128 x 16] bf16 of one k-step lives in 8 consecutive 32-bit columns of
+// lanes 0..127 (row r = lane r, elements 2c / 2c+1 in the low / high half of column c); B through an smem descriptor.
+__device__ __forceinline__ void umma_bf16_ts_ws(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_ws(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
