@@ -454,3 +454,30 @@ def test_token_store_cache_round_trip(tmp_path):
     open(path, "wb").write(b"not a cache file at all")
     with pytest.raises(ValueError, match="not a tradeaid_b200"):
         du.load_token_store(path, device="cpu")
+
+
+def test_string_modalities_are_tokenised_like_the_reference(du_emu):
+    """numerical_representation on non-numeric data (data_utils.py:212-225: vocabulary = sorted(set(data)), token = index) —
+    the case that used to raise NotImplementedError: same vocabulary order (Python's / code-point order), same tokens, same
+    TypeError for values that do not compare; through prepare_modality the ids land in the token-store row."""
+    import random
+    du = du_emu
+    rng = random.Random(5)
+    words = ["09:30", "09:35", "10:00", "close", "Open", "open", "é", "zz", "10:0", "", " "]
+    data = [rng.choice(words) for _ in range(500)]
+    tokens, vocab = du.numerical_representation(data)
+    want_vocab = sorted(list(set(data)))
+    mapping = {e: i for i, e in enumerate(want_vocab)}
+    assert vocab == want_vocab and tokens == [mapping[e] for e in data]
+    mixed = [("a", 1), ("a", 0), ("b", 2)] * 3                      # tuples: hashable and orderable, not str
+    t2, v2 = du.numerical_representation(mixed)
+    assert v2 == sorted(set(mixed)) and t2 == [v2.index(e) for e in mixed]
+    with pytest.raises(TypeError):                                  # sorted() of str and None, as in the reference
+        du.numerical_representation(["a", None, "b"])
+    row = torch.full((len(data),), -1, dtype=torch.int32)
+    params = ["t.csv", 9, True, False, None, None, None, None, True, "Time of day", None, None]
+    tok, voc = du.prepare_modality(data, params, tokens_out=row)
+    assert tok is row and voc == want_vocab and row.tolist() == tokens
+    tr, va, vo = du.prepare_dataset([data, [float(len(w)) for w in data]], [params, ["t.csv", 1, None, False, None, None, None, None,
+                                                                                       False, "len", None, None]], [500], 0.2)
+    assert vo[0] == want_vocab and torch.cat([tr[0], va[0]]).tolist() == tokens

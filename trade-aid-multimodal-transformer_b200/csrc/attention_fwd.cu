@@ -508,6 +508,10 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
   TA_CHECK_ARG(G > 0 && B > 0 && T > 0 && H > 0, "ta_attention_fwd: non-positive size");
   TA_CHECK_ARG(ldo % 8 == 0 && o_gs % 8 == 0 && (reinterpret_cast<uintptr_t>(o_bf16) & 15) == 0, "ta_attention_fwd: output alignment");
   TA_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "ta_attention_fwd: dropout_p must be in [0, 1)");
+  // TA_ATTN_FWD=1 keeps the first-generation kernel of this file (one tile at a time on 16 math warps, 128-row output
+  // stores); default: the two-stream kernel of attention_fwd2.cu, whose math warps store 32 rows each
+  static const int version = [] { const char* e = getenv("TA_ATTN_FWD"); return e ? atoi(e) : 2; }();
+  const int store_rows = version == 1 ? 128 : 32;
   AttnMaps maps;
   if (make_head_map(&maps.q, q, hs, H, T, B, G, 128)) return 1;
   for (int s = 0; s < n_src; ++s) {
@@ -516,11 +520,11 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
   }
   {
     ta_attn_tensor ot{o_bf16, ldo, hs, o_gs};
-    if (make_head_map(&maps.o, &ot, hs, H, T, B, G, 128)) return 1;
+    if (make_head_map(&maps.o, &ot, hs, H, T, B, G, store_rows)) return 1;
     if (o_src_bf16)
       for (int s = 0; s < n_src; ++s) {
         ta_attn_tensor st{static_cast<const __nv_bfloat16*>(o_src_bf16) + (long long)s * o_src_stride, ldo, hs, o_gs};
-        if (make_head_map(&maps.o_src[s], &st, hs, H, T, B, G, 128)) return 1;
+        if (make_head_map(&maps.o_src[s], &st, hs, H, T, B, G, store_rows)) return 1;
       }
   }
   AttnFwdParams p{};
@@ -539,9 +543,6 @@ extern "C" int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tenso
   TA_CHECK_ARG(total < (1ll << 31), "attention grid too large");
   p.total_work = (int)total;
   auto st = (cudaStream_t)stream;
-  // TA_ATTN_FWD=1 keeps the first-generation kernel of this file (one tile at a time on 16 math warps); default: the
-  // two-stream kernel of attention_fwd2.cu
-  static const int version = [] { const char* e = getenv("TA_ATTN_FWD"); return e ? atoi(e) : 2; }();
   if (version != 1) return launch_attn_fwd2(maps, p, st);
   if (n_src > 1) {
     if (hs <= 16) return launch_attn_fwd<16, true>(maps, p, st);

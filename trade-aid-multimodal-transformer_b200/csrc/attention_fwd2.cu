@@ -20,8 +20,8 @@
 //     runs under the exponentials of the current tile (the first version of this file aliased P over S, which chained
 //     S(n+1) behind P V(n): ncu showed the math warps waiting on mbarriers half of the time, 305 us per c4 launch);
 //   * the sum over the cross-attention sources lives in 64 registers of the row's thread (tensor memory is full: per stream
-//     S [0, 128), P [128, 192), O [192, 256)), and the output tiles are stored by TMA from a staging tile by one elected math
-//     thread - no storer warp, so the CTA is 12 warps and a math thread may hold 232 registers.
+//     S [0, 128), P [128, 192), O [192, 256)), and every math warp stores its own 32 output rows by TMA from its part of a
+//     staging tile - no storer warp and no barrier between warps, so the CTA is 12 warps and a math thread may hold 240 registers.
 // Per stream smem: Q 2 slots, K/V 2 stages, one staging tile. Nothing of size T x T touches HBM. head_size <= 64.
 #include <cmath>
 #include <cstdlib>
@@ -198,10 +198,8 @@ attn_fwd2_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
     const int wq = warp & 3, lane = tid & 31;
     const int r = wq * 32 + lane;                                  // row of the tile = TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-    const bool elected = r == 0;                                   // issues this stream's TMA stores
-    const int bar_id = 1 + stream;
+    const uint32_t aStageW = aStage + wq * 4096;                    // this warp's 32 rows of the staging tile
     float m_run = -INFINITY, l_run = 0.f;
-    int uh = 0, ub = 0, ug = 0;                                    // head / batch / group of the current unit
     float sum[MULTI ? DP : 1];                                     // running sum over the sources of this row's output
     // deferred segment epilogue: the last P V of a segment completes while the NEXT tile's scores are loaded and exponentiated,
     // so its result is picked up after that tile's P has been written - the math warps never sit waiting for the tensor pipe
@@ -221,17 +219,20 @@ attn_fwd2_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
         sts128(aStage + r * 128 + (((((c >> 3) + hlf)) ^ (r & 7)) << 4), u);
       }
     };
-    // the staging tile may be rewritten once the previous store has read it: the elected thread knows, a barrier tells the rest
+    // Every warp stores its own 32 rows (the store maps have 32-row boxes): lane 0 issues the TMA store and knows when the
+    // previous one has read the warp's part of the staging tile - no barrier between the warps of a stream (with 128-row
+    // stores two named barriers per segment cost 9 % of the cross-attention kernel, mostly waiting for the warp with the
+    // most unmasked columns)
     auto staging_acquire = [&]() {
-      if (elected) bulk_wait_read<0>();
-      named_bar_sync(bar_id, 128);
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
     };
     auto staging_store = [&](const CUtensorMap* m0, const CUtensorMap* m1) {
       fence_proxy_async_smem();
-      named_bar_sync(bar_id, 128);
-      if (elected) {
-        tma_store_5d(m0, aStage, 0, pe_h, pe_i * 128, pe_b, pe_g);
-        if (m1) tma_store_5d(m1, aStage, 0, pe_h, pe_i * 128, pe_b, pe_g);
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_5d(m0, aStageW, 0, pe_h, pe_i * 128 + wq * 32, pe_b, pe_g);
+        if (m1) tma_store_5d(m1, aStageW, 0, pe_h, pe_i * 128 + wq * 32, pe_b, pe_g);
         bulk_commit_group();
       }
     };
@@ -282,12 +283,6 @@ attn_fwd2_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
 
     for (; !it.done(); it.next()) {
       const bool diag = it.j == it.i;
-      if (it.new_unit()) {
-        int w = it.work;
-        uh = w % p.H; w /= p.H;
-        ub = w % p.B;
-        ug = w / p.B;
-      }
       if (it.first_in_seg()) { m_run = -INFINITY; l_run = 0.f; }
       // 32-column chunks this warp needs: all four below the diagonal tile, else those that reach its last row (warp-uniform)
       const int nch = diag ? wq + 1 : 4;
@@ -392,12 +387,16 @@ attn_fwd2_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
       mbar_arrive_a(b_p_full);
       if (it.last_in_seg()) {
         pend = true;
-        pe_i = it.i; pe_s = it.s; pe_k = it.k; pe_h = uh; pe_b = ub; pe_g = ug;
+        int w = it.work;
+        pe_h = w % p.H; w /= p.H;
+        pe_b = w % p.B;
+        pe_g = w / p.B;
+        pe_i = it.i; pe_s = it.s; pe_k = it.k;
         pe_m = m_run; pe_l = l_run;
       }
     }
     if (pend) epilogue();
-    if (elected) bulk_wait_all<0>();
+    if (lane == 0) bulk_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();

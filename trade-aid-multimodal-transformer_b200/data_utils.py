@@ -17,6 +17,8 @@ Python's own expressions — decade tables from this machine's `math.log10` and 
 four order statistics, the group boundaries — everything proportional to N runs in the kernels.
 There is no CPU fallback: without a CUDA device or the library these functions raise.
 
+Non-numeric (string) modalities are tokenised too: their vocabulary is host work by nature (_symbolic_representation), the
+token ids go to the device store like every other modality's.
 Not covered (raises NotImplementedError, use the reference's function): `range_numeric_data` with
 `decimal_places=None`, which sizes the rounding of every element by the length of its `str()` (data_utils.py:431);
 non-numeric (string) modalities in `numerical_representation`.
@@ -367,7 +369,7 @@ def numerical_representation(data_points, tokens_out=None, integer_vocabulary=Fa
         if not data_points:
             return [], []
         if _first_non_number(data_points) >= 0:
-            raise NotImplementedError("non-numeric modalities are not tokenised on the device")
+            return _symbolic_representation(data_points, tokens_out)
         integer_vocabulary = integer_vocabulary or all(isinstance(v, int) for v in data_points)
     ops = _ops()
     x = _upload(data_points) if as_list else _check_column(data_points, "data_points")
@@ -400,6 +402,30 @@ def numerical_representation(data_points, tokens_out=None, integer_vocabulary=Fa
     if integer_vocabulary:
         vocab = [int(v) for v in vocab]
     return (tokens.tolist(), vocab) if as_list else (tokens, vocab)
+
+
+def _symbolic_representation(data_points, tokens_out=None):
+    """Non-numeric modalities (strings: a time-of-day or a label column; data_utils.py:212-225 takes any hashable, orderable
+    values). The values exist only as host objects, so vocabulary = sorted(set(data)) is host work by nature and uses Python's
+    own expressions (same order, same TypeError on values that do not compare); for a list of str the token ids come from
+    numpy's sorted-unique inverse (code-point order, identical to Python's str ordering) instead of N dictionary look-ups.
+    With `tokens_out` (a row of the device token store) the ids are uploaded there and that row is returned."""
+    import numpy as np
+    vocabulary = sorted(list(set(data_points)))
+    if all(type(v) is str for v in data_points) and not any("\x00" in v for v in vocabulary):
+        arr = np.array(data_points)               # fixed-width unicode; trailing NULs would be stripped, hence the check
+        uniq, inverse = np.unique(arr, return_inverse=True)
+        assert uniq.tolist() == vocabulary
+        tokens = inverse.astype(np.int32)
+    else:
+        data_mapping = {element: index for index, element in enumerate(vocabulary)}
+        tokens = np.fromiter((data_mapping[element] for element in data_points), dtype=np.int32, count=len(data_points))
+    if tokens_out is None:
+        return tokens.tolist(), vocabulary
+    if tokens_out.numel() != tokens.size:
+        raise ValueError(f"tokens_out holds {tokens_out.numel()} tokens, the modality has {tokens.size}")
+    tokens_out.copy_(torch.from_numpy(tokens).to(tokens_out.device))
+    return tokens_out, vocabulary
 
 
 def create_train_val_datasets(numeric_rep_data, val_size, num_val_files, file_lengths):
@@ -436,9 +462,16 @@ def prepare_modality(column, modality_params, file_lengths=None, tokens_out=None
     file_cache.load_file_data_cached (file_cache.py:366-372: 0.0 and a warning); "raise" is data_utils.load_file_data's
     ZeroDivisionError (data_utils.py:148-153).
     Returns (int32 device tokens [N], vocabulary list). Intermediate columns stay in HBM."""
-    x = _upload(column) if not _is_column(column) else _check_column(column, "column")
     p = list(modality_params) + [None] * (12 - len(modality_params))
     is_percent, whole_digits, dec_places, num_bins = p[3], p[4], p[5], p[6]
+    if not _is_column(column) and isinstance(column, list) and column and _first_non_number(column) >= 0 and \
+            is_percent is not True and whole_digits is None and dec_places is None and num_bins is None:
+        # a non-numeric modality without numeric processing steps (main.py applies none to such a column): vocabulary on the
+        # host, token ids straight into the store row
+        if tokens_out is None:
+            tokens_out = torch.empty(len(column), dtype=torch.int32, device=_device())
+        return _symbolic_representation(column, tokens_out)
+    x = _upload(column) if not _is_column(column) else _check_column(column, "column")
     if is_percent is True:
         x = convert_to_percent_changes(x, dec_places if dec_places else 2, file_lengths=file_lengths, on_zero=on_zero)
     if whole_digits is not None or dec_places is not None:
