@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the bounded CPU sample")
     ap.add_argument("--no-overlap", action="store_true", help="DP: whole-buffer all-reduce after backward instead of "
                     "bucketed all-reduces overlapped with backward")
+    ap.add_argument("--grad-dtype", default="bf16", choices=["fp32", "bf16"], help="DP: what the gradient buckets travel as "
+                    "(bf16: half the NVLink bytes, consumed by AdamW as bf16; fp32: the exact exchange of the parity mode)")
     ap.add_argument("--buckets", type=int, default=12, help="DP: gradient buckets (runs of consecutive layers)")
     ap.add_argument("--sm-margin", type=int, default=16, help="DP overlap: SMs the persistent kernels leave to NCCL "
                     "(also the cap on NCCL's CTAs)")
@@ -339,7 +341,7 @@ def run_ours(args, cfg):
     eng = Engine(dims, dev, precision=args.precision)
     eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))   # same weights on every rank
     tr = Trainer(eng, lr=3e-4, process_group=pg, world_size=world, overlap=not args.no_overlap,
-                 grad_buckets=args.buckets, sm_margin=args.sm_margin)
+                 grad_buckets=args.buckets, sm_margin=args.sm_margin, grad_dtype=args.grad_dtype)
     streams = syn.make_streams(cfg, dev, rows)
     n_train = int(rows * 0.9)
     store = TokenStore([s[:n_train] for s in streams], dev)
@@ -395,6 +397,24 @@ def run_ours(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
+    # what the exchange costs: the same step with its collectives left out (measurement only), max over ranks
+    exposed_ms = None
+    if world > 1:
+        tr.skip_exchange = True
+        for _ in range(2):
+            one_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(max(3, args.steps // 2)):
+            one_step()
+        n1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([n0.elapsed_time(n1) / max(3, args.steps // 2)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exposed_ms = ms_per_step - float(t.item())
+        tr.skip_exchange = False
     tokens_per_step = M * B * T * world
     value = tokens_per_step / (ms_per_step * 1e-3)
     loss_now = float(losses.sum().item())
@@ -487,9 +507,13 @@ def run_ours(args, cfg):
                 "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split bf16 operands, fp32 activations)",
                 "data": "synthetic", "config": workload_config(args, cfg, B, world), "precision": args.precision, "tier": "engine",
                 "exchange": None if world == 1 else (
-                    {"kind": "bucketed fp32 all-reduce overlapped with backward", "buckets": len(tr._buckets),
-                     "bucket_bytes": tr.bucket_bytes(), "sm_margin": tr.sm_margin} if tr.overlap else
-                    {"kind": "whole-buffer fp32 all-reduce after backward", "chunks": tr.grad_chunks}),
+                    {"kind": f"bucketed {tr.grad_dtype} all-reduce overlapped with backward", "buckets": len(tr._buckets),
+                     "bucket_bytes": tr.bucket_bytes(), "bytes_per_step": sum(tr.bucket_bytes()), "sm_margin": tr.sm_margin,
+                     "exposed_ms_per_step": exposed_ms,
+                     "exposed_note": "ms_per_step minus the same step replayed without its collectives (max over ranks)"}
+                    if tr.overlap else
+                    {"kind": f"whole-buffer {tr.grad_dtype} all-reduce after backward", "chunks": tr.grad_chunks,
+                     "exposed_ms_per_step": exposed_ms}),
                 "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "breakdown_eager_step": breakdown, "cuda_graph": use_graph,
                 "loss_sum_last_step": loss_now, "positions_per_s": value / M,

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 4
+#define TA_ABI_VERSION 5
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -301,6 +301,10 @@ int32_t ta_adamw_tick(int64_t* step_dev, float* scalars_dev, double lr, double b
                       void* stream);
 int32_t ta_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* scalars_dev,
                       float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* same with the gradient read as bf16: the data-parallel step may exchange its gradient buckets in bf16 (half the NVLink
+ * bytes of the all-reduce that follows main.py:646 under DP); the reduced bf16 buckets are consumed here without a cast back. */
+int32_t ta_adamw_step_bf16g(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n,
+                            const float* scalars_dev, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

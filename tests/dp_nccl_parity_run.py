@@ -35,7 +35,8 @@ V, cross, T, C, H, L, B = [256, 100, 64, 300], [True, False, False, True], 64, 2
 cfg = dict(kinds=["price", "volume", "time", "indicator"], cross=cross, vocab=V, rows=20_000)
 eng = Engine(Dims(V, cross, T, C, H, L), dev)
 eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))
-tr = Trainer(eng, lr=1e-3, process_group=pg, world_size=world, overlap=True, grad_buckets=3)
+start = eng.master.clone()
+tr = Trainer(eng, lr=1e-3, process_group=pg, world_size=world, overlap=True, grad_buckets=3, grad_dtype="fp32")
 streams = syn.make_streams(cfg, "cpu", cfg["rows"])
 n_train = 18_000
 
@@ -89,7 +90,7 @@ if world > 1:
     dist.all_reduce(sl, op=dist.ReduceOp.SUM)
     step_losses = list(sl / world)
 if rank == 0:
-    torch.save({"master": eng.master.cpu(), "step_losses": torch.stack(step_losses).cpu(), "eval": ev,
+    torch.save({"master": eng.master.cpu(), "start": start.cpu(), "step_losses": torch.stack(step_losses).cpu(), "eval": ev,
                 "eval_text": buf.getvalue(), "world": world}, out_path)
 if world > 1:
     dist.barrier()

@@ -281,7 +281,7 @@ def adamw_tick(step_dev, scalars_dev, lr, beta1=0.9, beta2=0.999, weight_decay=0
 def adamw_step(p, g, m, v, shadow, scalars_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     _tick()
     step_size, bc2s, decay = (float(scalars_dev[k]) for k in range(3))
-    g = g * grad_scale
+    g = g.float() * grad_scale
     p.mul_(decay)
     m.add_((g - m) * (1.0 - beta1))
     v.mul_(beta2).add_((1.0 - beta2) * g * g)

@@ -150,7 +150,10 @@ def compare(a, b):
     """(lines whose text with numbers masked differs, max loss difference, max directional-count difference)"""
     a, b = mask_clock(a), mask_clock(b)
     if len(a) != len(b):
-        return [f"{len(a)} lines vs {len(b)}"], None, None
+        import difflib
+        d = [ln for ln in difflib.unified_diff([NUM.sub("#", x) for x in a], [NUM.sub("#", y) for y in b], lineterm="", n=0)
+             if not ln.startswith(("---", "+++", "@@"))]
+        return [f"{len(a)} lines vs {len(b)}"] + d[:10], None, None
     bad, dl, dc = [], 0.0, 0
     for x, y in zip(a, b):
         if x == y:

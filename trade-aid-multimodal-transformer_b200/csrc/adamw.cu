@@ -41,8 +41,10 @@ __device__ __forceinline__ void adam_one(float& p, float& m, float& v, float g, 
   p = p - s.step_size * (m / denom);
 }
 
+// GB16: the gradient is read as bf16 (the exchanged copy of a data-parallel step: trainer.py, grad_dtype = "bf16")
+template <bool GB16>
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adamw_kernel(float* __restrict__ p, const void* __restrict__ gv, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, long long n, const AdamScalars* __restrict__ sc, float beta1, float beta2,
              float eps, float grad_scale) {
   pdl_prologue();
@@ -51,7 +53,15 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   const long long nv = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 gg;
+    if constexpr (GB16) {
+      const uint2 u = reinterpret_cast<const uint2*>(gv)[i];
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      gg = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      gg = reinterpret_cast<const float4*>(gv)[i];
+    }
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     adam_one(pp.x, mm.x, vv.x, gg.x * grad_scale, s, b1w, beta2, b2w, eps);
@@ -72,7 +82,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   if (blockIdx.x == 0) {
     for (long long i = nv * 4 + threadIdx.x; i < n; i += blockDim.x) {
       float pp = p[i], mm = m[i], vv = v[i];
-      adam_one(pp, mm, vv, g[i] * grad_scale, s, b1w, beta2, b2w, eps);
+      const float gi = GB16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gv)[i]) : reinterpret_cast<const float*>(gv)[i];
+      adam_one(pp, mm, vv, gi * grad_scale, s, b1w, beta2, b2w, eps);
       p[i] = pp; m[i] = mm; v[i] = vv;
       if (shadow) shadow[i] = __float2bfloat16_rn(pp);
     }
@@ -94,19 +105,33 @@ int32_t ta_adamw_tick(int64_t* step_dev, float* scalars_dev, double lr, double b
   return 0;
 }
 
-int32_t ta_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* scalars_dev,
-                      float beta1, float beta2, float eps, float grad_scale, void* stream) {
+static int32_t adamw_step_any(float* p, const void* g, bool g_bf16, float* m, float* v, void* shadow_bf16, int64_t n,
+                              const float* scalars_dev, float beta1, float beta2, float eps, float grad_scale, void* stream) {
   TA_CHECK_ARG(p && g && m && v && scalars_dev, "ta_adamw_step: null pointer");
-  TA_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)shadow_bf16 & 7) == 0,
-               "ta_adamw_step: buffers must be 16-byte aligned");
+  TA_CHECK_ARG((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)g & (g_bf16 ? 7 : 15)) == 0 &&
+               ((uintptr_t)shadow_bf16 & 7) == 0, "ta_adamw_step: buffers must be 16-byte aligned (bf16 buffers 8-byte)");
   if (n == 0) return 0;
   long long blocks = ceil_div(n / 4 + 1, 256);
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  launch_kernel(adamw_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)shadow_bf16, n,
-                                                             (const AdamScalars*)scalars_dev, beta1, beta2, eps, grad_scale);
+  if (g_bf16)
+    launch_kernel(adamw_kernel<true>, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)shadow_bf16, n,
+                  (const AdamScalars*)scalars_dev, beta1, beta2, eps, grad_scale);
+  else
+    launch_kernel(adamw_kernel<false>, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)shadow_bf16, n,
+                  (const AdamScalars*)scalars_dev, beta1, beta2, eps, grad_scale);
   TA_CHECK_LAUNCH();
   return 0;
+}
+
+int32_t ta_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* scalars_dev,
+                      float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  return adamw_step_any(p, g, false, m, v, shadow_bf16, n, scalars_dev, beta1, beta2, eps, grad_scale, stream);
+}
+
+int32_t ta_adamw_step_bf16g(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n,
+                            const float* scalars_dev, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  return adamw_step_any(p, g_bf16, true, m, v, shadow_bf16, n, scalars_dev, beta1, beta2, eps, grad_scale, stream);
 }
 
 }  // extern "C"

@@ -46,6 +46,8 @@ def parse(argv=None):
     ap.add_argument("--precision", default=None, choices=["bf16", "bf16x3"])
     ap.add_argument("--buckets", type=int, default=None, help="gradient buckets of the overlapped exchange")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"], help="what the gradient buckets travel as; default: "
+                    "fp32 in parity mode (the run equals the single-process run), bf16 in throughput mode")
     return ap.parse_args(argv)
 
 
@@ -188,6 +190,7 @@ def main(argv=None):
     kw = {}
     if args.buckets is not None:
         kw["grad_buckets"] = args.buckets
+    kw["grad_dtype"] = args.grad_dtype or ("fp32" if args.mode == "parity" else "bf16")
     trainer = Trainer(eng, lr=ns["learning_rate"], process_group=pg, world_size=world, overlap=not args.no_overlap, **kw)
     # the same generator positions on every rank from here on in parity mode; own streams per rank in throughput mode
     seed = args.seed + 1 + (rank if args.mode == "throughput" else 0)

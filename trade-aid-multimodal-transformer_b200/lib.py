@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class TaOperand(C.Structure):
@@ -256,6 +256,7 @@ _unpad = _sig("ta_unpad_f32", _P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I32, 
 _cast = _sig("ta_cast_bf16", _P, _P, _I64, _P)
 _adamw_tick = _sig("ta_adamw_tick", _P, _P, _F64, _F64, _F64, _F64, _P)
 _adamw_step = _sig("ta_adamw_step", _P, _P, _P, _P, _P, _I64, _P, _F32, _F32, _F32, _F32, _P)
+_adamw_step_bf16g = _sig("ta_adamw_step_bf16g", _P, _P, _P, _P, _P, _I64, _P, _F32, _F32, _F32, _F32, _P)
 
 
 _drop_set = _sig("ta_dropout_set_step_counter", _P)
@@ -472,8 +473,13 @@ def adamw_tick(step_dev, scalars_dev, lr, beta1=0.9, beta2=0.999, weight_decay=0
 
 
 def adamw_step(p, g, m, v, shadow, scalars_dev, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    import torch
     n = p.numel()
     assert g.numel() == n and m.numel() == n and v.numel() == n and (shadow is None or shadow.numel() == n)
+    if g.dtype == torch.bfloat16:        # the exchanged bf16 copy of the gradient (data-parallel step)
+        _check(_adamw_step_bf16g(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), n, _ptr(scalars_dev), beta1, beta2, eps,
+                                 grad_scale, _stream()))
+        return
     _check(_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), n, _ptr(scalars_dev), beta1, beta2, eps,
                        grad_scale, _stream()))
 

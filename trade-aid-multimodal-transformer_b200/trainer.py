@@ -24,7 +24,7 @@ import torch
 
 class Trainer:
     def __init__(self, engine, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None, world_size=1,
-                 grad_chunks=8, overlap=None, grad_buckets=None, sm_margin=None):
+                 grad_chunks=8, overlap=None, grad_buckets=None, sm_margin=None, grad_dtype=None):
         self.eng = engine
         self.ops = engine.ops
         self.lr, self.betas, self.eps, self.wd = float(lr), betas, float(eps), float(weight_decay)
@@ -52,8 +52,18 @@ class Trainer:
         if sm_margin is None:
             sm_margin = int(os.environ.get("TRADEAID_DP_SM_MARGIN", "16"))
         self.sm_margin = int(sm_margin) if (self.overlap and hasattr(self.ops, "set_sm_margin")) else 0
+        # "bf16": every bucket is cast to bf16 (ta_cast_bf16, on the compute stream, right before its collective is issued),
+        # all-reduced in bf16 - half the NVLink bytes - and consumed by the AdamW kernel as bf16 (no cast back). "fp32" keeps
+        # the exchange exact: the data-parallel PARITY mode (DP == single process to fp32 summation order) uses it.
+        if grad_dtype is None:
+            grad_dtype = os.environ.get("TRADEAID_DP_GRAD_DTYPE", "fp32")
+        if grad_dtype not in ("fp32", "bf16"):
+            raise ValueError("grad_dtype must be 'fp32' or 'bf16'")
+        self.grad_dtype = grad_dtype if self.world > 1 else "fp32"
+        self.grad16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.grad_dtype == "bf16" else None
         self._buckets = self._make_buckets() if self.overlap else []
         self._works = []
+        self.skip_exchange = False       # measurement only (bench.py): run the data-parallel step without its collectives
         self._graphs = None
         self.launches_per_step = None
 
@@ -75,16 +85,36 @@ class Trainer:
             last = b == len(runs) - 1
             if last:
                 ranges = ranges + lay.grad_ranges("embed")
-            buckets.append(("embed" if last else run[0], [g[a:e] for a, e in ranges]))
+            # 8-element alignment of every range start keeps the bf16 copies 16-byte aligned (cast / AdamW vector accesses)
+            buckets.append(("embed" if last else run[0], [g[a:e] for a, e in ranges], ranges))
         return buckets
 
     def bucket_bytes(self):
-        return [sum(t.numel() * 4 for t in views) for _, views in self._buckets]
+        per = 2 if self.grad_dtype == "bf16" else 4
+        return [sum(t.numel() * per for t in b[1]) for b in self._buckets]
 
-    def _issue_bucket(self, views):
+    def _exchange_views(self, views, ranges):
+        """What goes on the wire for a bucket: the fp32 gradient ranges themselves, or their bf16 copies (cast here)."""
+        if self.grad16 is None:
+            return views
+        out = []
+        for t, (a, e) in zip(views, ranges):
+            dst = self.grad16[a:e]
+            if a % 8 == 0:
+                self.ops.cast_bf16(t, dst)
+            else:                                  # unaligned start: the strided conversion kernel has no alignment needs
+                self.ops.convert(t.view(1, -1), dst.view(1, -1))
+            out.append(dst)
+        return out
+
+    def _issue_bucket(self, views, ranges=None):
         """One coalesced asynchronous all-reduce(sum) of a bucket's gradient ranges. The process group's stream waits
         for the work enqueued on the current stream so far; the current stream is not blocked."""
         import torch.distributed as dist
+        if ranges is not None:
+            views = self._exchange_views(views, ranges)
+        if self.skip_exchange:
+            return
         cmgr = getattr(dist, "_coalescing_manager", None)
         if cmgr is None:       # no coalescing support in this torch: one asynchronous all-reduce per range
             for t in views:
@@ -110,7 +140,12 @@ class Trainer:
         if self.world <= 1:
             return
         import torch.distributed as dist
+        if self.skip_exchange:
+            return
         g = self.eng.grad[:self.n]
+        if self.grad16 is not None:
+            self.ops.cast_bf16(g, self.grad16)
+            g = self.grad16
         per = (self.n + self.grad_chunks - 1) // self.grad_chunks
         per = (per + 63) // 64 * 64
         works = []
@@ -122,7 +157,8 @@ class Trainer:
     def optimizer_step(self):
         eng, ops = self.eng, self.ops
         ops.adamw_tick(self.step_dev, self.scalars, self.lr, self.betas[0], self.betas[1], self.wd)
-        ops.adamw_step(eng.master[:self.n], eng.grad[:self.n], self.exp_avg, self.exp_avg_sq, eng.shadow[:self.n],
+        ops.adamw_step(eng.master[:self.n], self.grad16 if self.grad16 is not None else eng.grad[:self.n], self.exp_avg,
+                       self.exp_avg_sq, eng.shadow[:self.n],
                        self.scalars, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
         eng.refresh_shadows(flat_cast=False)
 
@@ -138,15 +174,15 @@ class Trainer:
             self.allreduce_grads()
             self.optimizer_step()
             return losses
-        closing = {stage: views for stage, views in self._buckets}
+        closing = {stage: (views, ranges) for stage, views, ranges in self._buckets}
 
         def hook(stage):
             if isinstance(stage, tuple):             # ("part", l): the previous bucket's collective is over by now
                 self._set_margin(0)
                 return
-            views = closing.get(stage)
-            if views is not None:
-                self._issue_bucket(views)
+            b = closing.get(stage)
+            if b is not None:
+                self._issue_bucket(*b)
                 self._set_margin(self.sm_margin)     # a collective now runs beside the next kernels
 
         try:
@@ -185,7 +221,7 @@ class Trainer:
                     self.optimizer_step()
             segments.append((g_fb, None))
         else:
-            closing = {stage: views for stage, views in self._buckets}
+            closing = {stage: (views, ranges) for stage, views, ranges in self._buckets}
             pool = torch.cuda.graph_pool_handle()
             cap = torch.cuda.Stream()
             cap.wait_stream(torch.cuda.current_stream())
@@ -199,11 +235,13 @@ class Trainer:
                 if isinstance(stage, tuple):         # ("part", l): full grids again for the rest of the layer
                     self._set_margin(0)
                     return
-                views = closing.get(stage)
-                if views is None:
+                b = closing.get(stage)
+                if b is None:
                     return
+                if self.grad16 is not None:          # the bf16 copy of the bucket is part of the captured segment
+                    b = (self._exchange_views(*b), None)
                 state["g"].capture_end()
-                segments.append((state["g"], views))
+                segments.append((state["g"], b))
                 state["g"] = None
                 self._set_margin(self.sm_margin)
                 if stage != "embed":
@@ -228,10 +266,10 @@ class Trainer:
 
     def replay(self):
         segments, g_opt = self._graphs
-        for g, views in segments:
+        for g, b in segments:
             g.replay()
-            if views is not None:
-                self._issue_bucket(views)
+            if b is not None:
+                self._issue_bucket(*b)
         if g_opt is not None:
             if self.overlap:
                 self._wait_buckets()
