@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--rows", type=int, default=0, help="synthetic rows override")
     ap.add_argument("--dropout", type=float, default=0.0, help="dropout probability of the training step (default 0: the parity configuration)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--all-cross", action="store_true", help="cross-attention on EVERY modality (SURVEY appendix E: 'also report "
+                    "all-T'); c4 then needs --batch 32 to fit 180 GB")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the bounded CPU sample")
@@ -628,12 +630,16 @@ def run_inference(args, cfg):
         eng.forward(idx, None, save=False)
     torch.cuda.synchronize()
     lib.reset_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.steps):
         logits, _ = eng.forward(idx, None, save=False)
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     launches = lib.launch_count()
     fwd_ms = e0.elapsed_time(e1) / args.steps
     fwd_tps = M * B * T / (fwd_ms * 1e-3)
@@ -667,7 +673,7 @@ def run_inference(args, cfg):
         line = {"metric": "inference tokens/s (forward)", "value": fwd_tps * world, "unit": "tokens/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": fwd_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(args, cfg, B, world), "gpu_launches": launches,
+                "config": workload_config(args, cfg, B, world), "gpu_launches": launches, "clocks": clocks,
                 "forward": {"ms": fwd_ms, "algorithmic_tflop": flops / 1e12, "tflops": flops / (fwd_ms * 1e-3) / 1e12,
                             "frac_of_measured_sustained": flops / (fwd_ms * 1e-3) / 1e12 / pk["tc_sustained"]},
                 "generate": {"prompt": n0, "prefill_ms": p0.elapsed_time(p1), "decode_ms_per_position": dec_ms,
@@ -826,7 +832,10 @@ def main():
                                                                    "cpu_baseline key of the default arm"}), flush=True)
             return
         return run_dataprep(args)
-    cfg = syn.CONFIGS[args.config]
+    cfg = dict(syn.CONFIGS[args.config])
+    if args.all_cross:
+        cfg["cross"] = [True] * len(cfg["vocab"])
+        cfg["note"] += " (cross-attention on every modality)"
     if args.impl == "reference":
         run_reference(args, cfg)
     elif args.impl == "reference-eager":

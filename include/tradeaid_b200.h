@@ -36,6 +36,12 @@ void ta_reset_launch_count(void);
  * driven from two threads do not see each other's margin); 0 restores full grids. */
 int32_t ta_set_sm_margin(int32_t sms);
 int32_t ta_get_sm_margin(void);
+/* Programmatic dependent launch for the FOLLOWING launches of the calling thread: 1 = every kernel is launched with the
+ * programmatic-stream-serialization attribute (its CTAs are scheduled while the previous kernel drains; griddepcontrol.wait
+ * keeps the data dependence), 0 = plain launches, -1 = follow the TA_PDL environment variable (default off). It pays where a
+ * step is a few hundred small launches (c2: -4.5 %) and costs a little where one persistent CTA per SM holds all of shared
+ * memory (c4: +1.8 %), so the engine switches it on for small problems only. Results are bit-identical either way. */
+int32_t ta_set_pdl(int32_t on);
 
 /* ------------------------------------------------------------------------------------------------ K2: GEMM
  * D[g] = epilogue( alpha * A[g] (M x K) * B[g]^T (N x K) ), bf16 operands, fp32 accumulation in TMEM (tcgen05.mma),

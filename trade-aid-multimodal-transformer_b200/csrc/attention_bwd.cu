@@ -66,6 +66,9 @@ struct AttnBwdParams {
 };
 
 // dev-only timeline: role 0 loader, 1 S/dP issuer, 2 math (warp 0), 3 gradient issuer; slot = running event index
+#ifndef TA_ATTN_TRACE_BUILD
+#define AB_TRACE(role, cnt, tag) do { (void)(cnt); } while (0)      // compiled out: -DTA_ATTN_TRACE_BUILD brings the timeline back
+#else
 #define AB_TRACE(role, cnt, tag)                                                                     \
   do {                                                                                               \
     if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (cnt) < 1024) {                     \
@@ -73,6 +76,7 @@ struct AttnBwdParams {
       ++(cnt);                                                                                       \
     }                                                                                                \
   } while (0)
+#endif
 
 constexpr int AB_MATH_WARPS = 16;
 constexpr int AB_MATH_THREADS = AB_MATH_WARPS * 32;
@@ -106,7 +110,9 @@ enum : uint32_t {
   AB_SKV_FULL = 20, AB_SQ_FULL = 21, AB_NBARS = 22
 };
 
-template <int DP>
+// DROPOUT is a template parameter: the mask code sat in the middle of the hot loop (two Philox draws and sixteen selects per
+// 16-column piece) and was executed-around on every pair of the common p = 0 case
+template <int DP, bool DROPOUT>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant__ AttnBwdParams p) {
   constexpr int TILE = AB_TILE;
@@ -464,7 +470,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
           // dropout (model.py:69, 151): O = (P o M / (1-p)) V, so dV takes the dropped P~ = P o M / (1-p) and
           // dS = P o (dP o M / (1-p) - D); the mask is regenerated from (seed, plane, row, column) as in the forward
           uint32_t keep = 0xFFFFu;
-          if (p.drop_thresh) {
+          if constexpr (DROPOUT) {
             const unsigned long long sd = p.drop_seed + (p.drop_step ? *p.drop_step * 0x9E3779B97F4A7C15ull : 0ull);
             const uint32_t plane = (uint32_t)it.s * (uint32_t)total + (uint32_t)it.work;
             keep = dropout_keep8(sd, 1u, plane, (uint32_t)row, (uint32_t)(col_base >> 3), p.drop_thresh) |
@@ -477,7 +483,11 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
             float p1 = ex2_approx(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
             p0 = e < nvalid ? p0 : 0.f;
             p1 = e + 1 < nvalid ? p1 : 0.f;
-            const float m0 = (keep >> e) & 1u ? dsc : 0.f, m1 = (keep >> (e + 1)) & 1u ? dsc : 0.f;
+            float m0 = 1.f, m1 = 1.f;
+            if constexpr (DROPOUT) {
+              m0 = (keep >> e) & 1u ? dsc : 0.f;
+              m1 = (keep >> (e + 1)) & 1u ? dsc : 0.f;
+            }
             const float d0 = p0 * (__uint_as_float(dv[e]) * m0 - Dr), d1 = p1 * (__uint_as_float(dv[e + 1]) * m1 - Dr);
             __nv_bfloat162 pv = __floats2bfloat162_rn(p0 * m0, p1 * m1), dh = __floats2bfloat162_rn(d0, d1);
             pp[e / 2] = *reinterpret_cast<uint32_t*>(&pv);
@@ -525,15 +535,20 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   if (warp == AB_MATH_WARPS + 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int DP>
-static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t st) {
+template <int DP, bool DROPOUT>
+static int launch_attn_bwd_d(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t st) {
   constexpr int SMEM = 12 * AB_TILE + AB_NBARS * 8 + 16 + 2 * ATTB_MAX_SRC * 256 * 4 + 64;
   static bool attr[TA_MAX_DEVICES] = {};
-  TA_CHECK_CUDA(ensure_dynamic_smem(attn_bwd_kernel<DP>, SMEM, attr));
+  TA_CHECK_CUDA(ensure_dynamic_smem(attn_bwd_kernel<DP, DROPOUT>, SMEM, attr));
   const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
-  launch_kernel(attn_bwd_kernel<DP>, dim3(grid), dim3(AB_THREADS), SMEM, st, maps, p);
+  launch_kernel(attn_bwd_kernel<DP, DROPOUT>, dim3(grid), dim3(AB_THREADS), SMEM, st, maps, p);
   TA_CHECK_LAUNCH();
   return 0;
+}
+
+template <int DP>
+static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t st) {
+  return p.drop_thresh ? launch_attn_bwd_d<DP, true>(maps, p, st) : launch_attn_bwd_d<DP, false>(maps, p, st);
 }
 
 static int grad_out(GradOut* o, const ta_attn_tensor* t, int G) {

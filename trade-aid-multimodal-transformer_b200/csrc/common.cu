@@ -24,9 +24,11 @@ int set_err(const char* fmt, ...) {
   return 1;
 }
 
+// -1: not set through ta_set_pdl -> the TA_PDL environment variable decides (default off)
+static thread_local int g_pdl = -1;
 bool pdl_enabled() {
-  static const int on = [] { const char* e = getenv("TA_PDL"); return e ? atoi(e) : 0; }();
-  return on != 0;
+  static const int env = [] { const char* e = getenv("TA_PDL"); return e ? atoi(e) : 0; }();
+  return (g_pdl >= 0 ? g_pdl : env) != 0;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -64,6 +66,10 @@ int32_t ta_set_sm_margin(int32_t sms) {
   return 0;
 }
 int32_t ta_get_sm_margin(void) { return ta::g_sm_margin; }
+int32_t ta_set_pdl(int32_t on) {
+  ta::g_pdl = on < 0 ? -1 : (on ? 1 : 0);
+  return 0;
+}
 int64_t ta_launch_count(void) { return ta::g_launches.load(std::memory_order_relaxed); }
 void ta_reset_launch_count(void) { ta::g_launches.store(0, std::memory_order_relaxed); }
 }

@@ -251,6 +251,10 @@ class Engine:
         if T > d.block_size:
             raise ValueError(f"sequence length {T} exceeds block_size {d.block_size}")
         BT = B * T
+        if hasattr(ops, "set_pdl") and "TA_PDL" not in os.environ:
+            # launch-latency territory (c2: 282 launches of a few microseconds each): let the next kernel's CTAs be scheduled
+            # while the previous one drains; large problems run one persistent CTA per SM and gain nothing (common.cuh)
+            ops.set_pdl(M * BT * C <= (8 << 20))
         bf, f32 = self.act_dtype, torch.float32
         S = {"B": B, "T": T, "layers": [], "idx": idx, "pd": pd, "drop_step": self._drop_step_host}
         t0 = 0

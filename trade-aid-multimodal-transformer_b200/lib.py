@@ -77,6 +77,15 @@ def set_sm_margin(sms):
     _check(_lib.ta_set_sm_margin(int(sms)))
 
 
+_lib.ta_set_pdl.restype = C.c_int32
+_lib.ta_set_pdl.argtypes = [C.c_int32]
+
+
+def set_pdl(on):
+    """Programmatic dependent launch for the following launches of this thread: True / False, or None = the TA_PDL variable."""
+    _check(_lib.ta_set_pdl(-1 if on is None else int(bool(on))))
+
+
 def get_sm_margin():
     return int(_lib.ta_get_sm_margin())
 
