@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 5
+#define TA_ABI_VERSION 6
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -125,6 +125,13 @@ int32_t ta_attention_fwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const
                          void* o_bf16, int64_t ldo, int64_t o_gs, void* o_src_bf16, int64_t o_src_stride, float* lse,
                          int32_t G, int32_t B, int32_t T, int32_t H, int32_t hs, float dropout_p, uint64_t seed,
                          void* stream);
+
+/* The same forward in plain fp32 (no tensor cores; q / k / v / o / o_src are FLOAT tensors, strides in elements): the exact
+ * attention of the bf16x3 precision mode, where the bf16 operands and output of the tensor-core kernels are all that is left
+ * of the logits error against the reference's fp32 forward. hs <= 64, T <= 1024, no dropout. */
+int32_t ta_attention_fwd_f32(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v, int32_t n_src,
+                             float* o, int64_t ldo, int64_t o_gs, float* o_src, int64_t o_src_stride, float* lse, int32_t G,
+                             int32_t B, int32_t T, int32_t H, int32_t hs, void* stream);
 
 /* Decode step of `generate` (model.py:404-446) while the sequence still fits block_size: ONE new query row per
  * (group, batch) against the first `len` rows of a key/value cache — the reference recomputes the whole window for

@@ -109,6 +109,11 @@ def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_st
     _scatter_heads(o, tot, B, T, H, hs, hs)
 
 
+def attention_fwd_f32(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None, o_src=None):
+    assert q.dtype == torch.float32 and o.dtype == torch.float32
+    attention_fwd(q, ks, vs, o, lse, B=B, T=T, H=H, hs=hs, head_stride_q=head_stride_q, head_stride_kv=head_stride_kv, o_src=o_src)
+
+
 def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None):
     """One new query row per (group, batch) against cache rows [0, length) of every source (csrc/attention_decode.cu)."""
     _tick()

@@ -23,7 +23,9 @@ GOLDEN_CASES = ["demo", "m3", "m3_short", "hs32", "nocross"]
 # bounds: logits normwise, loss relative, gradient normwise (all parameters together)
 # bf16 = measured on B200 in round 2 (logits 5.5e-3 c2 ... 7.6e-3 c4 at depth 12; gradients 4.5e-2 ... 6.9e-2, growing with
 # depth) plus a margin; torch.autocast(bf16) over the oracle, the control, gives 6.7-7.9e-3 on the logits of the same cases.
-BOUNDS = {"bf16": (9e-3, 2e-3, 7e-2), "bf16x3": (2e-3, 2e-4, 1e-2)}
+# bf16x3: the north star's 2e-3 on the logits with a wide margin (exact fp32 attention forward + split GEMM operands); its
+# gradients still pass through the bf16 tensor-core attention backward and bf16 LayerNorm / bias-gradient inputs.
+BOUNDS = {"bf16": (9e-3, 2e-3, 7e-2), "bf16x3": (5e-4, 2e-4, 4.5e-2)}
 
 
 def _record(**kw):
@@ -125,7 +127,7 @@ def test_both_precisions_against_oracle(shape):
     for precision, (lg, ls, gr) in out.items():
         lb, sb, gb = BOUNDS[precision]
         assert lg <= lb and ls <= sb and gr <= gb, (shape, precision, lg, ls, gr)
-    assert out["bf16x3"][0] < 0.2 * out["bf16"][0] and out["bf16x3"][2] < 0.3 * out["bf16"][2]
+    assert out["bf16x3"][0] < 0.1 * out["bf16"][0] and out["bf16x3"][2] < 0.7 * out["bf16"][2]
     # the single-pass bf16 mode is in the same class as torch's own autocast on the same model
     assert out["bf16"][0] <= 1.5 * control["logits"] + 1e-3, (out, control)
     assert out["bf16"][2] <= 2.0 * control["grads"] + 1e-2, (out, control)
@@ -185,6 +187,29 @@ def test_attention_seven_sources_sixteen_heads(G, B, T, H, hs, S):
     for s in range(S):
         ref = kvf[s].grad.view(G, B * T, 2 * C)
         assert (dkv[s].float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("G,B,T,H,hs,S", [(2, 2, 100, 3, 24, 1), (1, 2, 256, 4, 64, 3), (1, 1, 600, 2, 64, 2), (1, 3, 4, 4, 8, 1)])
+def test_attention_fwd_f32_is_exact(G, B, T, H, hs, S):
+    """ta_attention_fwd_f32 (the bf16x3 mode's attention) against fp32 torch: outputs, per-source outputs and log-sum-exps to
+    fp32 round-off, on strided views like the engine's packed q|k|v and [k|v]-per-head buffers."""
+    from tradeaid_b200 import lib
+    from test_kernels_gpu import _ref_attention
+    torch.manual_seed(12)
+    C = H * hs
+    qkv = torch.randn(G, B * T, 3 * C, device="cuda")
+    kv = [torch.randn(G, B * T, H, 2 * hs, device="cuda") for _ in range(S)]
+    q = qkv[..., :C]
+    o = torch.zeros(G, B * T, C, device="cuda")
+    o_src = torch.zeros(S, G, B * T, C, device="cuda")
+    lse = torch.zeros(S, G, B, H, T, device="cuda")
+    k_views = [t.view(G, B * T, 2 * C) for t in kv]
+    v_views = [t.view(G, B * T, 2 * C)[..., hs:] for t in kv]
+    lib.attention_fwd_f32(q, k_views, v_views, o, lse, B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs, o_src=o_src)
+    ro, ros, rl = _ref_attention(q.contiguous(), [t[..., :hs] for t in kv], [t[..., hs:] for t in kv], B, T, H, hs)
+    assert (o - ro).abs().max().item() <= 2e-5 * max(1.0, ro.abs().max().item())
+    assert (o_src - ros).abs().max().item() <= 2e-5 * max(1.0, ros.abs().max().item())
+    assert (lse - rl).abs().max().item() <= 2e-5
 
 
 @pytest.mark.parametrize("G,R,C,rows", [(3, 37, 40, False), (2, 64, 28, True), (1, 5, 1024, False)])

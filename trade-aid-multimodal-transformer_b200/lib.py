@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class TaOperand(C.Structure):
@@ -219,6 +219,36 @@ def attention_fwd(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_st
         _check(_lib.ta_attention_fwd(qa, ka, va, n_src, _ptr(o), o.stride(-2), o_gs, _ptr(o_src),
                                      o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, float(dropout_p),
                                      int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
+
+
+_lib.ta_attention_fwd_f32.restype = C.c_int32
+_lib.ta_attention_fwd_f32.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.c_int32,
+                                      C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+
+
+def attention_fwd_f32(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None, o_src=None):
+    """attention_fwd on fp32 tensors (plain fp32 arithmetic, the bf16x3 precision mode); same views and strides."""
+    import torch
+    n_src = len(ks)
+    G = q.shape[0] if q.dim() == 3 else 1
+    hq = head_stride_q if head_stride_q is not None else hs
+    hkv = head_stride_kv if head_stride_kv is not None else hs
+    for t in [q, o, *ks, *vs] + ([o_src] if o_src is not None else []):
+        assert t.dtype == torch.float32 and t.stride(-1) == 1
+
+    def at(t, hstride):
+        return TaAttnTensor(t.data_ptr(), t.stride(-2), hstride, t.stride(0) if t.dim() == 3 else 0)
+
+    qa = (TaAttnTensor * 1)(at(q, hq))
+    ka = (TaAttnTensor * n_src)(*[at(k, hkv) for k in ks])
+    va = (TaAttnTensor * n_src)(*[at(v, hkv) for v in vs])
+    assert lse.is_contiguous() and lse.numel() == n_src * G * B * H * T
+    o_gs = o.stride(0) if o.dim() == 3 else 0
+    if o_src is not None:
+        assert o_src.stride(-2) == o.stride(-2) and (o.dim() < 3 or o_src.stride(1) == o.stride(0))
+    _check(_lib.ta_attention_fwd_f32(qa, ka, va, n_src, _ptr(o), o.stride(-2), o_gs, _ptr(o_src),
+                                     o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, _stream()))
 
 
 def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None):

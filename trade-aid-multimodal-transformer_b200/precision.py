@@ -8,8 +8,10 @@ between kernels is fp32 and every GEMM runs as the three-term product
     A B^T ~= A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T,      x_hi = bf16(x), x_lo = bf16(x - x_hi)
 
 which is ONE launch of the unmodified tcgen05 kernel over K-concatenated operands [A_hi|A_lo|A_hi] x [B_hi|B_hi|B_lo]
-(ta_split_bf16 + ta_gemm_bf16: fp32 accumulation in TMEM, 3x the FLOPs). The attention kernels keep their bf16 operands
-(q, k, v, P) and bf16 output; LayerNorm writes fp32 (ta_layernorm_fwd_f32). The engine's host program is unchanged: it is
+(ta_split_bf16 + ta_gemm_bf16: fp32 accumulation in TMEM, 3x the FLOPs). The attention FORWARD is the plain fp32 kernel
+ta_attention_fwd_f32 (with the tensor-core kernel's bf16 q, k, v, P and output the logits error is 1.9e-3 at c4 widths instead of
+~1e-5); dropout and the attention backward stay on the tensor-core kernels through bf16 copies; LayerNorm writes fp32
+(ta_layernorm_fwd_f32). The engine's host program is unchanged: it is
 constructed with `act_dtype=torch.float32` over this namespace (Engine(..., precision="bf16x3")).
 
 This is a precision mode, not a fallback: every op still runs through libtradeaid_b200.so. The throughput mode stays
@@ -120,6 +122,11 @@ class SplitPrecisionOps:
         return out
 
     def attention_fwd(self, q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None, o_src=None, **kw):
+        if q.dtype == torch.float32 and not kw.get("dropout_p") and T <= 1024:
+            # exact attention: plain fp32 kernel (ta_attention_fwd_f32) straight on the engine's fp32 views. The bf16 operands
+            # and output of the tensor-core kernel would be all that is left of the logits error (1.9e-3 at c4 widths)
+            return self.inner.attention_fwd_f32(q, ks, vs, o, lse, B=B, T=T, H=H, hs=hs, head_stride_q=head_stride_q,
+                                                head_stride_kv=head_stride_kv, o_src=o_src)
         hq, hkv = head_stride_q or hs, head_stride_kv or hs
         qb = self._heads_bf16("af_q", q, H, hs, hq)
         kb = [self._heads_bf16(("af_k", s), k, H, hs, hkv) for s, k in enumerate(ks)]
