@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 6
+#define TA_ABI_VERSION 7
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -247,6 +247,19 @@ int32_t ta_prep_percent_changes(const double* x, double* out, int64_t N, const i
 int32_t ta_prep_range(const double* x, double* out, int64_t N, int32_t has_whole_digits, int32_t decimals, double lower,
                       double upper, double upper_clamp, const double* thresholds, const double* factors, int64_t* status,
                       void* stream);
+
+/* range_numeric_data with decimal_places = None (data_utils.py:431): every element is rounded to the length of the fraction its
+ * own str() shows - max(1, shortest round-tripping number of decimals) for a float in repr's positional range, 0 for a Python
+ * int (is_int: optional uint8 [N] mask). Elements repr() prints in exponent notation (|x| >= 1e16 or 0 < |x| < 1e-4) come back
+ * as NaN and are counted in n_flagged[0] (device int64, += ): the host wrapper patches those few with Python's own expression.
+ * params: ta_prep_range_auto_params fills a host block of ta_prep_range_auto_params_bytes() bytes (powers of ten, the clamps
+ * upper_clamps_host[d] = what a value >= 10**nwd becomes at d decimals, d = 0..22, built with Python's expressions); the caller
+ * copies it to the device. thresholds / factors as ta_prep_range (needed with whole digits). May run in place. */
+int64_t ta_prep_range_auto_params_bytes(void);
+int32_t ta_prep_range_auto_params(void* params_host, int32_t has_whole_digits, double lower, double upper,
+                                  const double* upper_clamps_host);
+int32_t ta_prep_range_auto(const double* x, const uint8_t* is_int, double* out, int64_t N, const void* params_dev,
+                           const double* thresholds, const double* factors, int64_t* status, int64_t* n_flagged, void* stream);
 
 /* Order statistics for np.percentile (data_utils.py:503-504): out[r] = the ranks[r]-th smallest element (0-based) of x,
  * n_ranks <= TA_PREP_MAX_RANKS, by an 8-pass radix select (no sort, x is not modified). ranks / out are device arrays. */

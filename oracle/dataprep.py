@@ -47,10 +47,13 @@ def percent_changes_by_file(data, file_lengths, decimals=2, on_zero="raise"):
 
 def range_values(data, whole_digits, decimals):
     """Scale every value into `whole_digits` digits before the point and round to `decimals` (data_utils.py:421-457).
-    `decimals` must be given (the str()-length form of :431 is outside the device path)."""
+    decimals=None: every element is rounded to the length of the fraction part of its own str() (:431)."""
     out = []
+    fixed = decimals
     for v in data:
         decade = 0 if v == 0 else int(math.floor(math.log10(abs(v))))          # :423-429
+        decimals = fixed if fixed is not None else (len(str(v).split('.')[-1]) if '.' in str(v) else 0)   # :431
+        decimals = max(0, decimals)
         factor = 1 if whole_digits is None else 10 ** ((whole_digits - 1) - decade)   # :436-440
         s = round(v * factor, decimals) if factor != 0 else 0.0                # :443
         if whole_digits is not None:                                           # :445-455

@@ -87,6 +87,29 @@ def prep_range(x, out, has_whole_digits, decimals, lower, upper, upper_clamp, th
     _np(out)[:] = res
 
 
+def prep_range_auto(x, is_int, out, has_whole_digits, lower, upper, upper_clamps, thresholds, factors, status, n_flagged):
+    """csrc/dataprep.cu prep_range_auto_kernel with the kernels' own element arithmetic built for the host."""
+    xa = np.ascontiguousarray(_np(x))
+    bad = np.flatnonzero(~np.isfinite(xa))
+    _note(status, PREP_NONFINITE, bad)
+    safe = xa.copy()
+    safe[bad] = 1.0
+    res = np.empty_like(safe)
+    flags = np.zeros(safe.size, dtype=np.int32)
+    thr = _np(thresholds) if has_whole_digits else np.zeros(PREP_DECADES)
+    fac = _np(factors) if has_whole_digits else np.ones(PREP_DECADES)
+    clamps = np.asarray([float(v) for v in upper_clamps], dtype=np.float64)
+    ints = np.ascontiguousarray(_np(is_int)) if is_int is not None else None
+    host().h_range_auto(P(safe.ctypes.data), P(ints.ctypes.data) if ints is not None else None, ctypes.c_longlong(safe.size),
+                        ctypes.c_int(1 if has_whole_digits else 0), ctypes.c_double(lower), ctypes.c_double(upper),
+                        P(clamps.ctypes.data), P(thr.ctypes.data), P(fac.ctypes.data), P(res.ctypes.data), P(flags.ctypes.data))
+    res[bad] = xa[bad]
+    flags[bad] = 0
+    _note(status, PREP_OVERFLOW, np.flatnonzero(~np.isfinite(res) & np.isfinite(xa) & (flags == 0)))
+    _np(out)[:] = res
+    n_flagged[0] += int(flags.sum())
+
+
 def prep_select_workspace_bytes():
     return (2 * PREP_MAX_RANKS + PREP_MAX_RANKS * 256) * 8
 

@@ -47,6 +47,26 @@ void h_range(const double* x, long long n, int has_nwd, int decimals, double low
   for (long long i = 0; i < n; ++i) out[i] = range_element(x[i], rp, thresholds, factors);
 }
 
+void h_repr_decimals(const double* x, long long n, int* out) {
+  Pow10 P[AUTO_MAX_DECIMALS + 1];
+  for (int d = 0; d <= AUTO_MAX_DECIMALS; ++d) P[d] = pow10_of(d);
+  for (long long i = 0; i < n; ++i) out[i] = repr_decimals(x[i], P);
+}
+
+// out[i] = NaN and flags[i] = 1 where the element is left to the host
+void h_range_auto(const double* x, const unsigned char* is_int, long long n, int has_nwd, double lower, double upper,
+                  const double* upper_clamps, const double* thresholds, const double* factors, double* out, int* flags) {
+  RangeAutoParams rp;
+  rp.has_whole_digits = has_nwd;
+  rp.lower = lower;
+  rp.upper = upper;
+  for (int d = 0; d <= AUTO_MAX_DECIMALS; ++d) { rp.P[d] = pow10_of(d); rp.upper_clamp[d] = upper_clamps[d]; }
+  for (long long i = 0; i < n; ++i) {
+    flags[i] = 0;
+    out[i] = range_element_auto(x[i], is_int && is_int[i], rp, thresholds, factors, &flags[i]);
+  }
+}
+
 void h_percent(const double* x, long long n, int nd, double* out) {
   const Pow10 P = pow10_of(nd);
   out[0] = 0.0;

@@ -284,7 +284,7 @@ def test_validation_matches_reference_messages():
     with pytest.raises(ValueError, match="'decimal_places' must be greater than or equal to 0."):
         du.range_numeric_data([1.0], 1, -2)
     with pytest.raises(NotImplementedError):
-        du.range_numeric_data([1.0], 1, None)
+        du.range_numeric_data([1.0], 1, 40)
     with pytest.raises(ValueError, match="'num_groups' must be a positive integer."):
         du.bin_numeric_data([1.0], 0)
     with pytest.raises(ValueError, match="'outlier_percentile' must be a number between 0 and 50."):
@@ -481,3 +481,62 @@ def test_string_modalities_are_tokenised_like_the_reference(du_emu):
     tr, va, vo = du.prepare_dataset([data, [float(len(w)) for w in data]], [params, ["t.csv", 1, None, False, None, None, None, None,
                                                                                        False, "len", None, None]], [500], 0.2)
     assert vo[0] == want_vocab and torch.cat([tr[0], va[0]]).tolist() == tokens
+
+
+def test_repr_decimals_is_the_length_of_str_fraction(host):
+    """The device's count of decimals for decimal_places=None (smallest d at which round() reproduces x, at least 1) against
+    Python's own len(str(x).split('.')[-1]) on prices, random doubles of every positional magnitude, and short decimals."""
+    import random
+    rng = random.Random(11)
+    vals = [0.0, -0.0, 1.0, 100.0, 0.1, 0.5, 12.5, 0.125, 1e-4, 9999999999999998.0, 123456789012345.6, 0.0001234, 5e-324 * 0 + 0.3,
+            1 / 3, 2 / 3, 1e15 + 0.5, 4.35, 2.675, 1.005, 0.30000000000000004]
+    for _ in range(60000):
+        k = rng.random()
+        if k < 0.3:
+            vals.append(round(rng.uniform(0.01, 5000.0), rng.randint(0, 6)))          # prices / quoted decimals
+        elif k < 0.6:
+            vals.append(rng.uniform(-1, 1) * 10.0 ** rng.randint(-4, 15))             # full-precision doubles
+        elif k < 0.8:
+            vals.append(rng.randint(-10 ** 6, 10 ** 6) / 10.0 ** rng.randint(0, 8))
+        else:
+            vals.append(float(rng.randint(-10 ** 15, 10 ** 15)))                       # integral floats: "x.0"
+    vals = [v for v in vals if v == 0.0 or 1e-4 <= abs(v) < 1e16]
+    x = np.asarray(vals, dtype=np.float64)
+    out = np.zeros(x.size, dtype=np.int32)
+    host.h_repr_decimals(ctypes.c_void_p(x.ctypes.data), ctypes.c_longlong(x.size), ctypes.c_void_p(out.ctypes.data))
+    want = [len(str(float(v)).split('.')[-1]) for v in x.tolist()]
+    assert all('e' not in str(float(v)) for v in x.tolist())
+    bad = [(v, int(o), w) for v, o, w in zip(x.tolist(), out.tolist(), want) if o != w]
+    assert not bad, bad[:5]
+    # exponent notation is left to the host
+    y = np.asarray([1e16, 1.5e-5, 1e-5, 2.5e22, -3e-7], dtype=np.float64)
+    o2 = np.zeros(y.size, dtype=np.int32)
+    host.h_repr_decimals(ctypes.c_void_p(y.ctypes.data), ctypes.c_longlong(y.size), ctypes.c_void_p(o2.ctypes.data))
+    assert o2.tolist() == [-1] * 5
+
+
+def test_range_with_decimal_places_none_matches_the_reference_algorithm(du_emu):
+    """range_numeric_data(decimal_places=None) through the host wrapper over the kernels' arithmetic == the oracle's restatement
+    of data_utils.py:421-457 (and the reference itself where its checkout exists), incl. ints, exponent-notation values."""
+    import random
+    from oracle import dataprep as O
+    du = du_emu
+    rng = random.Random(3)
+    data = [12.5, 0.125, 100.0, 7, -3, 0.0, 1.5e-5, 2e16, -0.00042, 99.999, 1234.5678, 0.30000000000000004, 5, 1e-4]
+    data += [round(rng.uniform(-3000, 3000), rng.randint(0, 5)) for _ in range(3000)]
+    data += [rng.uniform(-1, 1) * 10.0 ** rng.randint(-6, 17) for _ in range(500)]
+    for nwd in (None, 1, 2, 3):
+        got = du.range_numeric_data(list(data), nwd, None)
+        want = O.range_values(data, nwd, None)
+        assert len(got) == len(want)
+        bad = [(v, g, w) for v, g, w in zip(data, got, want) if g != w or math.copysign(1, g) != math.copysign(1, w)]
+        assert not bad, (nwd, bad[:5])
+    col = torch.tensor([v for v in data if isinstance(v, float)], dtype=torch.float64)
+    got = du.range_numeric_data(col, 2, None)
+    assert got.tolist() == O.range_values(col.tolist(), 2, None)
+    if os.path.isdir("/root/reference"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_du", "/root/reference/data_utils.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        assert ref.range_numeric_data(list(data), 2, None) == O.range_values(data, 2, None)

@@ -260,3 +260,26 @@ def test_prepared_dataset_feeds_get_batch(du):
     for a, b in zip(got, ref):
         for s, t in zip(a, b):
             assert torch.equal(s, t)
+
+
+def test_range_with_decimal_places_none_on_the_device(du):
+    """range_numeric_data(decimal_places=None) (data_utils.py:431: every element rounded to the fraction length of its own
+    str()) on the device against the oracle: list form with Python ints and exponent-notation values, and a float64 column of
+    100 k quoted prices / full-precision doubles, bit for bit."""
+    from oracle import dataprep as O
+    rng = random.Random(21)
+    data = [12.5, 0.125, 100.0, 7, -3, 0.0, 1.5e-5, 2e16, -0.00042, 99.999, 1234.5678, 0.30000000000000004, 5, 1e-4]
+    data += [round(rng.uniform(-3000, 3000), rng.randint(0, 5)) for _ in range(2000)]
+    for nwd in (None, 2):
+        got = du.range_numeric_data(list(data), nwd, None)
+        assert same_bits(got, O.range_values(data, nwd, None)), nwd
+    col = [round(rng.uniform(0.5, 900.0), rng.randint(1, 4)) for _ in range(60_000)]
+    col += [rng.uniform(-1, 1) * 10.0 ** rng.randint(-3, 12) for _ in range(40_000)]
+    x = dev(torch.tensor(col, dtype=torch.float64))
+    for nwd in (None, 1, 3):
+        got = du.range_numeric_data(x, nwd, None)
+        assert same_bits(got.cpu().numpy(), O.range_values(col, nwd, None)), nwd
+    # string modality through the chain: ids in the store row
+    words = [rng.choice(["a", "b", "09:30", "Zed", ""]) for _ in range(1000)]
+    tok, voc = du.prepare_modality(words, ["t.csv", 1, None, False, None, None, None, None, False, "label", None, None])
+    assert voc == sorted(set(words)) and tok.is_cuda and tok.cpu().tolist() == [voc.index(w) for w in words]

@@ -122,6 +122,42 @@ __global__ void __launch_bounds__(DP_THREADS, 8) prep_range_kernel(const double*
   }
 }
 
+// decimal_places = None: per-element decimals from the element's own shortest repr (dataprep_math.cuh). The parameter block
+// (23 powers of ten + clamps, ~1 KB) is read from global memory into shared memory once per CTA.
+__global__ void __launch_bounds__(DP_THREADS, 4) prep_range_auto_kernel(const double* __restrict__ x,
+                                                                       const unsigned char* __restrict__ is_int,
+                                                                       double* __restrict__ out, long long N,
+                                                                       const RangeAutoParams* __restrict__ rp_g,
+                                                                       const double* __restrict__ thresholds,
+                                                                       const double* __restrict__ factors,
+                                                                       long long* __restrict__ status,
+                                                                       long long* __restrict__ n_flagged) {
+  pdl_prologue();
+  __shared__ double s_thr[P10_COUNT];
+  __shared__ double s_fac[P10_COUNT];
+  __shared__ RangeAutoParams s_rp;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(rp_g);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_rp);
+    for (int k = threadIdx.x; k < (int)(sizeof(RangeAutoParams) / 4); k += DP_THREADS) dst[k] = src[k];
+  }
+  __syncthreads();
+  if (s_rp.has_whole_digits)
+    for (int k = threadIdx.x; k < P10_COUNT; k += DP_THREADS) { s_thr[k] = thresholds[k]; s_fac[k] = factors[k]; }
+  __syncthreads();
+  long long flagged = 0;
+  for (long long i = blockIdx.x * (long long)DP_THREADS + threadIdx.x; i < N; i += (long long)gridDim.x * DP_THREADS) {
+    const double v = x[i];
+    if (!is_finite(v)) { note_row(status + TA_PREP_STATUS_NONFINITE, i); out[i] = v; continue; }
+    int flag = 0;
+    const double r = range_element_auto(v, is_int && is_int[i], s_rp, s_thr, s_fac, &flag);
+    if (!flag && !is_finite(r)) note_row(status + TA_PREP_STATUS_OVERFLOW, i);
+    flagged += flag;
+    out[i] = r;
+  }
+  if (flagged) atomicAdd(reinterpret_cast<unsigned long long*>(n_flagged), (unsigned long long)flagged);
+}
+
 // ------------------------------------------------------------------------------------------------ order statistics
 // Radix select, most significant byte first, for up to TA_PREP_MAX_RANKS ranks at once. state: per rank {prefix, k}.
 // Ranks whose prefixes agree on the bytes decided so far see the same rows, so they share one histogram (the neighbouring
@@ -436,6 +472,33 @@ int32_t ta_prep_range(const double* x, double* out, int64_t N, int32_t has_whole
   rp.upper_clamp = upper_clamp;
   TA_CHECK_CUDA(launch_kernel(prep_range_kernel, dim3(dp_grid(prep_range_kernel, N)), dim3(DP_THREADS), 0, (cudaStream_t)stream, x, out,
                               (long long)N, rp, thresholds, factors, (long long*)status));
+  TA_CHECK_LAUNCH();
+  return 0;
+}
+
+int64_t ta_prep_range_auto_params_bytes(void) { return (int64_t)sizeof(RangeAutoParams); }
+
+int32_t ta_prep_range_auto_params(void* params_host, int32_t has_whole_digits, double lower, double upper,
+                                  const double* upper_clamps_host) {
+  TA_CHECK_ARG(params_host && upper_clamps_host, "ta_prep_range_auto_params: null pointer");
+  RangeAutoParams* rp = static_cast<RangeAutoParams*>(params_host);
+  rp->has_whole_digits = has_whole_digits ? 1 : 0;
+  rp->lower = lower;
+  rp->upper = upper;
+  for (int d = 0; d <= AUTO_MAX_DECIMALS; ++d) {
+    rp->P[d] = host_pow10(d);
+    rp->upper_clamp[d] = upper_clamps_host[d];
+  }
+  return 0;
+}
+
+int32_t ta_prep_range_auto(const double* x, const uint8_t* is_int, double* out, int64_t N, const void* params_dev,
+                           const double* thresholds, const double* factors, int64_t* status, int64_t* n_flagged, void* stream) {
+  TA_CHECK_ARG(x && out && params_dev && status && n_flagged, "ta_prep_range_auto: null pointer");
+  TA_CHECK_ARG(N > 0, "ta_prep_range_auto: N=%lld", (long long)N);
+  TA_CHECK_CUDA(launch_kernel(prep_range_auto_kernel, dim3(dp_grid(prep_range_auto_kernel, N)), dim3(DP_THREADS), 0,
+                              (cudaStream_t)stream, x, (const unsigned char*)is_int, out, (long long)N,
+                              (const RangeAutoParams*)params_dev, thresholds, factors, (long long*)status, (long long*)n_flagged));
   TA_CHECK_LAUNCH();
   return 0;
 }

@@ -247,6 +247,50 @@ TA_HD double range_element(double x, const RangeParams& rp, const double* __rest
   return scaled;
 }
 
+// ---- range_numeric_data with decimal_places = None (data_utils.py:431): every element is rounded to the number of characters
+// after the '.' of ITS OWN str(). For a float in repr's positional range (1e-4 <= |x| < 1e16, or zero) that is max(1, d) with
+// d the smallest number of decimals at which CPython's round() reproduces x: repr() prints the shortest digit string that
+// reads back as x, and the decimal nearest to x with d places reads back as x exactly when some d-place decimal does
+// (tests/test_dataprep_cpu.py holds this to str() on millions of values). A Python int prints without a '.', i.e. 0.
+// Values repr() prints in exponent notation are left to the caller (returns -1): "1.5e-05".split('.')[-1] is "5e-05".
+constexpr int AUTO_MAX_DECIMALS = 22;
+struct RangeAutoParams {
+  int has_whole_digits;
+  double lower, upper;
+  Pow10 P[AUTO_MAX_DECIMALS + 1];             // 10^d
+  double upper_clamp[AUTO_MAX_DECIMALS + 1];  // 10**nwd - 10**(-d) (d > 0), 10**nwd - 1 (d = 0): Python's own expressions
+};
+
+TA_HD int repr_decimals(double x, const Pow10* P) {
+  const double ax = abs_of(x);
+  if (ax == 0.0) return 1;                                  // "0.0", "-0.0"
+  if (!(ax >= 1e-4 && ax < 1e16)) return -1;                 // exponent notation (or not finite): the caller's business
+  for (int d = 0; d <= AUTO_MAX_DECIMALS; ++d)
+    if (bits_of(py_round(x, P[d])) == bits_of(x)) return d < 1 ? 1 : d;
+  return -1;
+}
+
+// One element with decimal_places = None. Returns NaN (and *flag = 1) where the element needs the host's str().
+TA_HD double range_element_auto(double x, bool is_int, const RangeAutoParams& rp, const double* __restrict__ thresholds,
+                                const double* __restrict__ factors, int* flag) {
+  const int d = is_int ? 0 : repr_decimals(x, rp.P);
+  if (d < 0) { *flag = 1; return double_of(0x7ff8000000000000ull); }
+  double f = 1.0;
+  if (rp.has_whole_digits) {
+    const int p = (x == 0.0) ? 0 : floor_log10(abs_of(x), thresholds);
+    f = factors[p - P10_MIN];
+    if (!is_finite(f)) return f;
+  }
+  double scaled = (f != 0.0) ? py_round(mul_rn(x, f), rp.P[d]) : 0.0;
+  if (rp.has_whole_digits) {
+    double a = abs_of(scaled);
+    if (a < rp.lower && a > 0.0) a = rp.lower;
+    if (a >= rp.upper) a = rp.upper_clamp[d];
+    scaled = (x < 0.0) ? -a : a;
+  }
+  return scaled;
+}
+
 // One element of convert_to_percent_changes (data_utils.py:649-657 / file_cache.py:362-377); prev != 0.
 // An unchanged value is common (prices quoted in cents) and a zero numerator sends the device's division down its slow
 // path for the whole warp (ncu: 59 of 177 instructions per row), so it is answered directly: (0.0 / prev) * 100 is a zero

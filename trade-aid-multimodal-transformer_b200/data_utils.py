@@ -19,9 +19,9 @@ There is no CPU fallback: without a CUDA device or the library these functions r
 
 Non-numeric (string) modalities are tokenised too: their vocabulary is host work by nature (_symbolic_representation), the
 token ids go to the device store like every other modality's.
-Not covered (raises NotImplementedError, use the reference's function): `range_numeric_data` with
-`decimal_places=None`, which sizes the rounding of every element by the length of its `str()` (data_utils.py:431);
-non-numeric (string) modalities in `numerical_representation`.
+`range_numeric_data(decimal_places=None)` - every element rounded to the length of the fraction its own `str()` shows
+(data_utils.py:431) - runs on the device too (_range_auto). What still raises NotImplementedError are parameter values outside
+the double / table range (decimal_places > 22, num_groups > 8192).
 """
 from __future__ import annotations
 
@@ -228,10 +228,9 @@ def range_numeric_data(numeric_data, num_whole_digits, decimal_places, out=None)
         raise TypeError("'decimal_places' must be an integer or None.")
     if decimal_places is not None and decimal_places < 0:
         raise ValueError("'decimal_places' must be greater than or equal to 0.")
-    if decimal_places is None:
-        raise NotImplementedError("range_numeric_data with decimal_places=None rounds every element to the length of its "
-                                  "str() (data_utils.py:431); that form is not built on the device")
     ops = _ops()
+    if decimal_places is None:
+        return _range_auto(ops, numeric_data, as_list, num_whole_digits, out)
     if decimal_places > ops.PREP_MAX_DECIMALS:
         raise NotImplementedError(f"decimal_places > {ops.PREP_MAX_DECIMALS} is not supported on the device")
     x = _upload(numeric_data) if as_list else _check_column(numeric_data, "numeric_data")
@@ -258,6 +257,71 @@ def range_numeric_data(numeric_data, num_whole_digits, decimal_places, out=None)
     if overflow is not None:
         raise OverflowError(f"int too large to convert to float (scaling factor of element {overflow})")
     return res.tolist() if as_list else res
+
+
+def _range_auto(ops, numeric_data, as_list, num_whole_digits, out):
+    """range_numeric_data with decimal_places=None (data_utils.py:431): every element is rounded to the number of characters
+    its own str() shows after the '.', so 12.5 keeps one decimal and 0.125 three. On the device that number is found as the
+    smallest count of decimals at which round() reproduces the value (what repr's shortest digit string amounts to in its
+    positional range; a Python int has none). The few values repr() prints in exponent notation come back flagged and are
+    finished here with the reference's own expression."""
+    x = _upload(numeric_data) if as_list else _check_column(numeric_data, "numeric_data")
+    dev = x.device
+    is_int = None
+    if as_list and any(isinstance(v, numbers.Integral) for v in numeric_data):
+        is_int = torch.from_numpy(np.fromiter((isinstance(v, numbers.Integral) for v in numeric_data), dtype=np.uint8,
+                                              count=len(numeric_data))).to(dev)
+    nd = ops.PREP_MAX_DECIMALS
+    lower = upper = 0.0
+    clamps = [0.0] * (nd + 1)
+    thresholds = factors = None
+    if num_whole_digits is not None:
+        try:
+            lower = float(10 ** (num_whole_digits - 1))
+            upper = float(10 ** num_whole_digits)
+            clamps = [float(10 ** num_whole_digits - (10 ** (-d))) if d > 0 else float(10 ** num_whole_digits - 1)
+                      for d in range(nd + 1)]
+        except OverflowError as e:
+            raise NotImplementedError(f"num_whole_digits={num_whole_digits} is outside the double range") from e
+        thresholds = torch.tensor(_log10_thresholds(), dtype=torch.float64, device=dev)
+        factors = torch.tensor(_decade_factors(num_whole_digits), dtype=torch.float64, device=dev)
+    st = _Status(ops, dev)
+    flagged = torch.zeros(1, dtype=torch.int64, device=dev)
+    res = torch.empty_like(x) if out is None else out
+    keep = ops.prep_range_auto(x, is_int, res, num_whole_digits is not None, lower, upper, clamps, thresholds, factors,
+                               st.words, flagged)
+    nonfinite, _, overflow, _ = st.read()
+    del keep
+    st.raise_nonfinite(nonfinite, x)
+    if overflow is not None:
+        raise OverflowError(f"int too large to convert to float (scaling factor of element {overflow})")
+    if int(flagged[0]) > 0:
+        # magnitudes repr() prints as 1.5e-05 / 1e+16: "5e-05" counts as five "decimals" in the reference. Python's own code.
+        rows = torch.nonzero(torch.isnan(res) & ~torch.isnan(x)).flatten().tolist()
+        src = numeric_data if as_list else None
+        for i in rows:
+            v = src[i] if src is not None else float(x[i])
+            res[i] = _range_one_by_str(v, num_whole_digits)
+    return res.tolist() if as_list else res
+
+
+def _range_one_by_str(element, num_whole_digits):
+    """One element of range_numeric_data(decimal_places=None), the reference's expressions (data_utils.py:421-457)."""
+    power_of_10 = 0 if element == 0 else int(math.floor(math.log10(abs(element))))
+    apply_dec_places = max(0, len(str(element).split('.')[-1]) if '.' in str(element) else 0)
+    scaling_factor = 1
+    if num_whole_digits is not None:
+        scaling_factor = 10 ** ((num_whole_digits - 1) - power_of_10)
+    scaled_value = round(element * scaling_factor, apply_dec_places) if scaling_factor != 0 else 0.0
+    if num_whole_digits is not None:
+        abs_scaled_value = abs(scaled_value)
+        if abs_scaled_value < 10 ** (num_whole_digits - 1) and abs_scaled_value > 0:
+            abs_scaled_value = 10 ** (num_whole_digits - 1)
+        if abs_scaled_value >= 10 ** num_whole_digits:
+            abs_scaled_value = 10 ** num_whole_digits - (10 ** (-apply_dec_places)) if apply_dec_places > 0 else \
+                10 ** num_whole_digits - 1
+        scaled_value = abs_scaled_value * (-1 if element < 0 else 1)
+    return float(scaled_value)
 
 
 # ---------------------------------------------------------------------------------------------------- binning

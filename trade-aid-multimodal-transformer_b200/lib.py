@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class TaOperand(C.Structure):
@@ -565,6 +565,9 @@ PREP_MAX_DECIMALS = 22
 _prep_reset = _sig("ta_prep_status_reset", _P, _P)
 _prep_pct = _sig("ta_prep_percent_changes", _P, _P, _I64, _P, _I32, _I32, _P, _P)
 _prep_range = _sig("ta_prep_range", _P, _P, _I64, _I32, _I32, _F64, _F64, _F64, _P, _P, _P, _P)
+_prep_range_auto_pb = _sig("ta_prep_range_auto_params_bytes", restype=_I64)
+_prep_range_auto_p = _sig("ta_prep_range_auto_params", _P, _I32, _F64, _F64, _P)
+_prep_range_auto = _sig("ta_prep_range_auto", _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P)
 _prep_sel_ws = _sig("ta_prep_select_workspace_bytes", restype=_I64)
 _prep_sel = _sig("ta_prep_order_statistics", _P, _I64, _P, _I32, _P, _P, _P, _P)
 _prep_mm_ws = _sig("ta_prep_minmax_workspace_bytes", _I64, restype=_I64)
@@ -603,6 +606,24 @@ def prep_range(x, out, has_whole_digits, decimals, lower, upper, upper_clamp, th
         _f64(thresholds), _f64(factors)
     _check(_prep_range(_ptr(_f64(x)), _ptr(_f64(out)), x.numel(), 1 if has_whole_digits else 0, int(decimals), float(lower),
                        float(upper), float(upper_clamp), _ptr(thresholds), _ptr(factors), _ptr(status), _stream()))
+
+
+def prep_range_auto(x, is_int, out, has_whole_digits, lower, upper, upper_clamps, thresholds, factors, status, n_flagged):
+    """range_numeric_data with decimal_places=None. is_int: uint8 [N] device mask or None; upper_clamps: 23 python floats;
+    n_flagged: int64 [1] device counter (+=) of the elements left as NaN for the host (exponent-notation magnitudes)."""
+    import torch
+    assert out.numel() == x.numel() and len(upper_clamps) == PREP_MAX_DECIMALS + 1 and n_flagged.dtype == torch.int64
+    host = (C.c_uint8 * int(_prep_range_auto_pb()))()
+    clamps = (C.c_double * (PREP_MAX_DECIMALS + 1))(*[float(v) for v in upper_clamps])
+    _check(_prep_range_auto_p(host, 1 if has_whole_digits else 0, float(lower), float(upper), clamps))
+    params = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(x.device)
+    if has_whole_digits:
+        _f64(thresholds), _f64(factors)
+    if is_int is not None:
+        assert is_int.dtype == torch.uint8 and is_int.is_contiguous() and is_int.numel() == x.numel()
+    _check(_prep_range_auto(_ptr(_f64(x)), _ptr(is_int), _ptr(_f64(out)), x.numel(), _ptr(params), _ptr(thresholds),
+                            _ptr(factors), _ptr(status), _ptr(n_flagged), _stream()))
+    return params       # keep alive until the launch has run (the caller synchronises when it reads the status)
 
 
 def prep_select_workspace_bytes():
