@@ -25,7 +25,8 @@ GOLDEN_CASES = ["demo", "m3", "m3_short", "hs32", "nocross"]
 # depth) plus a margin; torch.autocast(bf16) over the oracle, the control, gives 6.7-7.9e-3 on the logits of the same cases.
 # bf16x3: the north star's 2e-3 on the logits with a wide margin (exact fp32 attention forward + split GEMM operands); its
 # gradients still pass through the bf16 tensor-core attention backward and bf16 LayerNorm / bias-gradient inputs.
-BOUNDS = {"bf16": (9e-3, 2e-3, 7e-2), "bf16x3": (5e-4, 2e-4, 4.5e-2)}
+# measured in round 2 (profiles/r02_parity_v2.jsonl): logits 1.1e-5 (c2) ... 2.0e-5 (full c4), gradients 2.6e-3 ... 4.7e-3
+BOUNDS = {"bf16": (9e-3, 2e-3, 7e-2), "bf16x3": (2e-4, 2e-5, 1e-2)}
 
 
 def _record(**kw):
@@ -127,7 +128,7 @@ def test_both_precisions_against_oracle(shape):
     for precision, (lg, ls, gr) in out.items():
         lb, sb, gb = BOUNDS[precision]
         assert lg <= lb and ls <= sb and gr <= gb, (shape, precision, lg, ls, gr)
-    assert out["bf16x3"][0] < 0.1 * out["bf16"][0] and out["bf16x3"][2] < 0.7 * out["bf16"][2]
+    assert out["bf16x3"][0] < 0.02 * out["bf16"][0] and out["bf16x3"][2] < 0.2 * out["bf16"][2]
     # the single-pass bf16 mode is in the same class as torch's own autocast on the same model
     assert out["bf16"][0] <= 1.5 * control["logits"] + 1e-3, (out, control)
     assert out["bf16"][2] <= 2.0 * control["grads"] + 1e-2, (out, control)

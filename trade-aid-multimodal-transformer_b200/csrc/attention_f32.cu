@@ -38,7 +38,7 @@ struct AttnF32Params {
 
 __global__ void __launch_bounds__(AF32_WARPS * 32) attn_fwd_f32_kernel(const __grid_constant__ AttnF32Params p) {
   pdl_prologue();
-  __shared__ float s_q[AF32_WARPS][64];
+  __shared__ __align__(16) float s_q[AF32_WARPS][64];
   __shared__ float s_p[AF32_WARPS][AF32_MAX_T];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_per_block = AF32_WARPS;
@@ -59,10 +59,21 @@ __global__ void __launch_bounds__(AF32_WARPS * 32) attn_fwd_f32_kernel(const __g
     const float* kb = p.k[s] + g * p.kv_gs[s] + tok * p.kv_ld[s] + (long long)h * p.kv_hs[s];
     const float* vb = p.v[s] + g * p.kv_gs[s] + tok * p.kv_ld[s] + (long long)h * p.kv_hs[s];
     float mx = -INFINITY;
+    const bool vec = (p.hs & 3) == 0 && ((reinterpret_cast<uintptr_t>(kb) | (uintptr_t)(p.kv_ld[s] * 4)) & 15) == 0;
     for (int j = lane; j <= r; j += 32) {
       const float* kr = kb + (long long)j * p.kv_ld[s];
       float a = 0.f;
-      for (int d = 0; d < p.hs; ++d) a = fmaf(s_q[warp][d], kr[d], a);
+      if (vec) {              // 16-byte loads, four independent partial sums
+        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int d = 0; d < p.hs; d += 4) {
+          const float4 kk = *reinterpret_cast<const float4*>(kr + d);
+          const float4 qq = *reinterpret_cast<const float4*>(&s_q[warp][d]);
+          a = fmaf(qq.x, kk.x, a); a1 = fmaf(qq.y, kk.y, a1); a2 = fmaf(qq.z, kk.z, a2); a3 = fmaf(qq.w, kk.w, a3);
+        }
+        a = (a + a1) + (a2 + a3);
+      } else {
+        for (int d = 0; d < p.hs; ++d) a = fmaf(s_q[warp][d], kr[d], a);
+      }
       a *= p.scale;
       s_p[warp][j] = a;
       mx = fmaxf(mx, a);
@@ -80,11 +91,25 @@ __global__ void __launch_bounds__(AF32_WARPS * 32) attn_fwd_f32_kernel(const __g
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
     const bool d0 = lane < p.hs, d1 = lane + 32 < p.hs;
-    for (int j = 0; j <= r; ++j) {
-      const float pj = s_p[warp][j];
-      const float* vr = vb + (long long)j * p.kv_ld[s];
-      if (d0) o0 = fmaf(pj, vr[lane], o0);
-      if (d1) o1 = fmaf(pj, vr[lane + 32], o1);
+    {
+      // four key rows per iteration: eight independent loads in flight per lane
+      float p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f, r0 = 0.f, r1 = 0.f, t0 = 0.f, t1 = 0.f;
+      const long long ld = p.kv_ld[s];
+      int j = 0;
+      for (; j + 3 <= r; j += 4) {
+        const float* vr = vb + (long long)j * ld;
+        const float w0 = s_p[warp][j], w1 = s_p[warp][j + 1], w2 = s_p[warp][j + 2], w3 = s_p[warp][j + 3];
+        if (d0) { p0 = fmaf(w0, vr[lane], p0); q0 = fmaf(w1, vr[ld + lane], q0); r0 = fmaf(w2, vr[2 * ld + lane], r0); t0 = fmaf(w3, vr[3 * ld + lane], t0); }
+        if (d1) { p1 = fmaf(w0, vr[lane + 32], p1); q1 = fmaf(w1, vr[ld + lane + 32], q1); r1 = fmaf(w2, vr[2 * ld + lane + 32], r1); t1 = fmaf(w3, vr[3 * ld + lane + 32], t1); }
+      }
+      for (; j <= r; ++j) {
+        const float pj = s_p[warp][j];
+        const float* vr = vb + (long long)j * ld;
+        if (d0) p0 = fmaf(pj, vr[lane], p0);
+        if (d1) p1 = fmaf(pj, vr[lane + 32], p1);
+      }
+      o0 = (p0 + q0) + (r0 + t0);
+      o1 = (p1 + q1) + (r1 + t1);
     }
     const float inv = 1.f / l;
     o0 *= inv; o1 *= inv;
