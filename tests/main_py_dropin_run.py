@@ -139,6 +139,8 @@ NUM = re.compile(r"-?\d+(?:,\d{3})*(?:\.\d+)?")
 def mask_clock(text):
     out = []
     for ln in text.splitlines():
+        if ln.startswith("NCCL version "):        # torch's c10d prints it on stdout when the first communicator is made
+            continue
         ln = re.sub(r"\d\d:\d\d:\d\d", "<clock>", re.sub(r"\d{4}-\d\d-\d\d", "<date>", ln))
         if ln.startswith(("Saved: Model checkpoint (", "Final Save: ")):
             ln = re.sub(r"\d+\.\d+ MB", "<size> MB", ln)     # one flat storage: fewer zip records, same keys and values
