@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 7
+#define TA_ABI_VERSION 8
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -142,7 +142,15 @@ int32_t ta_attention_fwd_f32(const ta_attn_tensor* q, const ta_attn_tensor* k, c
  * columns [h*hs, (h+1)*hs). n_src <= 16, hs a multiple of 8 up to 64 (as the forward / backward kernels). */
 int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v,
                             const int64_t* kv_batch_stride, int32_t n_src, void* o_bf16, int64_t ldo, int64_t o_gs,
-                            int32_t G, int32_t B, int32_t len, int32_t H, int32_t hs, void* stream);
+                            int32_t G, int32_t B, int32_t len, const int32_t* len_dev, int32_t H, int32_t hs, void* stream);
+/* The decode step as a replayable CUDA graph keeps the number of cached positions in device memory: with len_dev != NULL the
+ * decode kernel attends to *len_dev + len positions; ta_embed_fwd_at embeds one new position per sequence at index *pos_dev
+ * (x[m, r, :] = tok[voff[m] + idx[m, r], :] + pos[*pos_dev, :]); ta_kv_append writes the new position's K/V rows (W_words
+ * 32-bit words per (group, batch), element strides in words) at row *pos_dev of a cache [G][B][capacity][...]. */
+int32_t ta_embed_fwd_at(const int64_t* idx, const float* tok, const int64_t* voff, const float* pos, float* x, int32_t M,
+                        int64_t rows, int32_t C, const int32_t* pos_dev, void* stream);
+int32_t ta_kv_append(const void* src, int64_t s_g, int64_t s_b, void* cache, int64_t c_g, int64_t c_b, int64_t c_t, int32_t G,
+                     int32_t B, int32_t W_words, const int32_t* pos_dev, void* stream);
 
 /* Backward of the above (recompute): given dO (layout of o) produces dq (layout of q), and per source dk, dv (layouts
  * of k[s], v[s]); all bf16. T <= 256 in this build. */

@@ -114,9 +114,23 @@ def attention_fwd_f32(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, hea
     attention_fwd(q, ks, vs, o, lse, B=B, T=T, H=H, hs=hs, head_stride_q=head_stride_q, head_stride_kv=head_stride_kv, o_src=o_src)
 
 
-def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None):
+def embed_fwd_at(idx, tok, voff, pos, x, pos_dev):
+    _tick()
+    M, rows = idx.shape
+    for m in range(M):
+        x[m].copy_(tok[voff[m] + idx[m]] + pos[int(pos_dev)])
+
+
+def kv_append(src, cache, pos_dev):
+    _tick()
+    cache[:, :, int(pos_dev), :src.shape[-1]].copy_(src)
+
+
+def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None, len_dev=None):
     """One new query row per (group, batch) against cache rows [0, length) of every source (csrc/attention_decode.cu)."""
     _tick()
+    if len_dev is not None:
+        length = length + int(len_dev)
     hq = head_stride_q or hs
     hkv = head_stride_kv or hs
     G, B = q.shape[0], q.shape[1]

@@ -179,3 +179,23 @@ def test_per_layer_streams_match_reference(name):
         x = Sl["x3"] if eng.d.Xc else Sl["x2"]
         for i in range(eng.d.M):
             assert (x[i].view(B, T, -1) - acts[l][i]).abs().max().item() <= 2e-5, (l, i)
+
+
+def test_decode_step_with_device_side_length_matches_the_full_forward(monkeypatch):
+    """The decode step in its graph-replayable form (positions-so-far read from cache.len_dev by the embedding, cache-append
+    and decode-attention ops) on the CPU emulation: every position's logits equal the full forward's."""
+    from tradeaid_b200.engine import KVCache
+    g, eng = build("m3", torch.float32)
+    monkeypatch.setenv("TRADEAID_DECODE_DYN", "1")
+    idx = torch.stack(g["idx"])
+    M, B, T = idx.shape
+    full, _ = eng.forward(idx, None, save=False)
+    full = [t.clone() for t in full]
+    cache = KVCache(eng, B, T)
+    eng.forward(idx[:, :, :3].contiguous(), None, save=False, cache=cache)
+    assert int(cache.len_dev) == 3
+    for t in range(3, T):
+        step = eng.decode_step(idx[:, :, t:t + 1].contiguous(), cache)
+        assert cache.length == t + 1 and int(cache.len_dev) == t + 1
+        for i in range(M):
+            assert (step[i][:, 0] - full[i][:, t]).abs().max().item() <= 2e-5

@@ -270,3 +270,29 @@ def test_per_layer_streams_match_reference(name):
             ref = acts[l][i]
             rel = ((x[i].view(B, T, -1).cpu() - ref).norm() / ref.norm()).item()
             assert rel <= 1e-2, (l, i, rel)
+
+
+def test_decode_step_graph_replay_is_bit_identical_to_plain_launches(monkeypatch):
+    """Engine.decode_step: eager first step, captured second step, replays afterwards (the cached length read from device
+    memory by the embedding / cache-append / decode-attention kernels) against the plain-launch decode path, bit for bit."""
+    from tradeaid_b200.engine import KVCache
+    g, eng = build("m3")
+    idx = torch.stack(g["idx"]).cuda()
+    M, B, T = idx.shape
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TRADEAID_DECODE_GRAPH", mode)
+        cache = KVCache(eng, B, T)
+        eng.forward(idx[:, :, :2].contiguous(), None, save=False, cache=cache)
+        got = []
+        for t in range(2, T):
+            step = eng.decode_step(idx[:, :, t:t + 1].contiguous(), cache)
+            got.append(torch.stack([s.clone() for s in step]) if len({s.shape for s in step}) == 1 else [s.clone() for s in step])
+        outs[mode] = got
+        assert cache.length == T and int(cache.len_dev) == T
+        assert (cache._graph is not None) == (mode == "1")
+    for a, b in zip(outs["0"], outs["1"]):
+        if isinstance(a, list):
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+        else:
+            assert torch.equal(a, b)

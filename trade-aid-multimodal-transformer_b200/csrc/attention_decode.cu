@@ -28,6 +28,7 @@ struct AttnDecodeParams {
   __nv_bfloat16* o;
   long long o_ld, o_gs;
   int n_src, G, B, H, hs, len;
+  const int* len_dev;   // optional: positions already cached, on the device (CUDA-graph replay); len = *len_dev + len then
   float scale_log2;     // hs^-0.5 * log2(e)
 };
 
@@ -38,8 +39,10 @@ struct AttnDecodeParams {
 constexpr int AD_U = 8;
 
 template <int HS>
-__global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid_constant__ AttnDecodeParams p) {
+__global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid_constant__ AttnDecodeParams pp) {
   pdl_prologue();
+  AttnDecodeParams p = pp;
+  if (p.len_dev) p.len += *p.len_dev;
   constexpr int LPR = HS / 8;            // lanes per row
   constexpr int RPI = 32 / LPR;          // rows per warp-wide load instruction
   constexpr int CHUNK = RPI * AD_U;      // rows per chunk
@@ -172,11 +175,12 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
 
 extern "C" int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v,
                                        const int64_t* kv_batch_stride, int32_t n_src, void* o_bf16, int64_t ldo, int64_t o_gs,
-                                       int32_t G, int32_t B, int32_t len, int32_t H, int32_t hs, void* stream) {
+                                       int32_t G, int32_t B, int32_t len, const int32_t* len_dev, int32_t H, int32_t hs,
+                                       void* stream) {
   using namespace ta;
   TA_CHECK_ARG(q && k && v && kv_batch_stride && o_bf16, "ta_attention_decode: null argument");
   TA_CHECK_ARG(n_src >= 1 && n_src <= AD_MAX_SRC, "ta_attention_decode: n_src %d not in [1, %d]", (int)n_src, AD_MAX_SRC);
-  TA_CHECK_ARG(G > 0 && B > 0 && H > 0 && len > 0, "ta_attention_decode: non-positive shape");
+  TA_CHECK_ARG(G > 0 && B > 0 && H > 0 && (len > 0 || (len_dev && len >= 0)), "ta_attention_decode: non-positive shape");
   TA_CHECK_ARG(hs >= 8 && hs <= 64 && hs % 8 == 0, "ta_attention_decode: head size %d not supported (8..64, multiple of 8)", (int)hs);
   auto al16 = [](const void* ptr, int64_t a, int64_t b2, int64_t c) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && a % 8 == 0 && b2 % 8 == 0 && c % 8 == 0;
@@ -197,7 +201,7 @@ extern "C" int32_t ta_attention_decode(const ta_attn_tensor* q, const ta_attn_te
   }
   p.o = static_cast<__nv_bfloat16*>(o_bf16); p.o_ld = ldo; p.o_gs = o_gs;
   TA_CHECK_ARG((reinterpret_cast<uintptr_t>(o_bf16) & 15) == 0 && ldo % 8 == 0 && o_gs % 8 == 0, "ta_attention_decode: o must be 16-byte aligned (ptr, strides)");
-  p.n_src = n_src; p.G = G; p.B = B; p.H = H; p.hs = hs; p.len = len;
+  p.n_src = n_src; p.G = G; p.B = B; p.H = H; p.hs = hs; p.len = len; p.len_dev = len_dev;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)hs);
   const long long total = (long long)G * B * H;
   const unsigned grid = (unsigned)ceil_div(total, AD_WARPS);

@@ -67,6 +67,40 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ idx, const float*
   }
 }
 
+// Decode step under a CUDA graph: one new position per sequence whose index lives on the device.
+// x[m, r, :] = E[voff[m] + idx[m, r], :] + P[*pos_dev, :]
+__global__ void embed_fwd_at_kernel(const long long* __restrict__ idx, const float* __restrict__ tok,
+                                    const long long* __restrict__ voff, const float* __restrict__ pos, float* __restrict__ x,
+                                    int M, long long rows, int C, const int* __restrict__ pos_dev) {
+  pdl_prologue();
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)M * rows;
+  const float* p = pos + (long long)(*pos_dev) * C;
+  for (long long r = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); r < total;
+       r += (long long)gridDim.x * warps_per_block) {
+    const int m = (int)(r / rows);
+    const float* e = tok + (voff[m] + idx[r]) * C;
+    float* o = x + r * C;
+    for (int c = lane; c < C; c += 32) o[c] = e[c] + p[c];
+  }
+}
+
+// cache[g, b, *pos_dev, 0:W) = src[g, b, 0:W)  (32-bit words; the K/V rows of the new position)
+__global__ void kv_append_kernel(const uint32_t* __restrict__ src, long long s_g, long long s_b, uint32_t* __restrict__ cache,
+                                 long long c_g, long long c_b, long long c_t, int G, int B, int W, const int* __restrict__ pos_dev) {
+  pdl_prologue();
+  const long long t = *pos_dev;
+  const long long total = (long long)G * B * W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(e % W);
+    const long long gb = e / W;
+    const int b = (int)(gb % B);
+    const long long g = gb / B;
+    cache[g * c_g + b * c_b + t * c_t + w] = src[g * s_g + b * s_b + w];
+  }
+}
+
 // dP[t, c] = sum_m sum_b dx[m, b*T + t, c]   (position table shared by all modalities, model.py:298,313)
 __global__ void embed_bwd_pos_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int M, int B, int T, int C) {
   pdl_prologue();
@@ -599,6 +633,30 @@ int32_t ta_embed_fwd(const int64_t* idx, const float* tok, const int64_t* voff, 
   TA_CHECK_ARG(M > 0 && rows > 0 && T > 0 && C > 0 && rows % T == 0, "ta_embed_fwd: bad sizes");
   launch_kernel(embed_fwd_kernel, dim3(grid_for((long long)M * rows, 8)), dim3(256), 0, (cudaStream_t)stream, 
       (const long long*)idx, tok, (const long long*)voff, pos, x, M, rows, T, C);
+  TA_CHECK_LAUNCH();
+  return 0;
+}
+
+int32_t ta_embed_fwd_at(const int64_t* idx, const float* tok, const int64_t* voff, const float* pos, float* x, int32_t M,
+                        int64_t rows, int32_t C, const int32_t* pos_dev, void* stream) {
+  TA_CHECK_ARG(idx && tok && voff && pos && x && pos_dev, "ta_embed_fwd_at: null pointer");
+  TA_CHECK_ARG(M > 0 && rows > 0 && C > 0, "ta_embed_fwd_at: bad sizes");
+  const long long total = (long long)M * rows;
+  launch_kernel(embed_fwd_at_kernel, dim3(grid_for(total, 8)), dim3(256), 0, (cudaStream_t)stream, (const long long*)idx, tok,
+                (const long long*)voff, pos, x, (int)M, (long long)rows, (int)C, (const int*)pos_dev);
+  TA_CHECK_LAUNCH();
+  return 0;
+}
+
+int32_t ta_kv_append(const void* src, int64_t s_g, int64_t s_b, void* cache, int64_t c_g, int64_t c_b, int64_t c_t, int32_t G,
+                     int32_t B, int32_t W_words, const int32_t* pos_dev, void* stream) {
+  TA_CHECK_ARG(src && cache && pos_dev, "ta_kv_append: null pointer");
+  TA_CHECK_ARG(G > 0 && B > 0 && W_words > 0, "ta_kv_append: bad sizes");
+  TA_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(cache)) & 3) == 0, "ta_kv_append: 4-byte alignment");
+  const long long total = (long long)G * B * W_words;
+  launch_kernel(kv_append_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint32_t*)src,
+                (long long)s_g, (long long)s_b, (uint32_t*)cache, (long long)c_g, (long long)c_b, (long long)c_t, (int)G, (int)B,
+                (int)W_words, (const int*)pos_dev);
   TA_CHECK_LAUNCH();
   return 0;
 }

@@ -50,6 +50,13 @@ class KVCache:
         if self.capacity > d.block_size:
             raise ValueError("cache capacity exceeds block_size: beyond it the window slides and every position changes")
         self.length = 0
+        # the same count on the device: the decode step replayed as a CUDA graph reads it there (Engine.decode_step)
+        self.len_dev = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        self.dyn = False                 # True while a decode step runs with the device-side length
+        self._graph = None
+        self._static_idx = None
+        self._static_logits = None
+        self._dyn_steps = 0
         C, dt, dev = d.n_embd, eng.act_dtype, eng.device
         self.self_kv = [torch.zeros(d.M, self.B, self.capacity, 2 * C, dtype=dt, device=dev) for _ in range(d.n_layer)]
         self.cross_kv = [[torch.zeros(j1 - j0, self.B, self.capacity, nq * 2 * C, dtype=dt, device=dev)
@@ -271,8 +278,12 @@ class Engine:
         def nb(name, l, shape, dtype):
             return self.buf(f"{name}.{l}" if save else name, shape, dtype)
 
+        dyn = decode and cache.dyn        # positions-so-far read from cache.len_dev by the kernels (graph replay)
         x = nb("x0", 0, (M, BT, C), f32)
-        ops.embed_fwd(idx.view(M, BT), P["tok"], self._voff, P["pos"][t0:t0 + T] if cache is not None else P["pos"], x, T)
+        if dyn:
+            ops.embed_fwd_at(idx.view(M, BT), P["tok"], self._voff, P["pos"], x, cache.len_dev)
+        else:
+            ops.embed_fwd(idx.view(M, BT), P["tok"], self._voff, P["pos"][t0:t0 + T] if cache is not None else P["pos"], x, T)
         for l in range(L):
             Sl = {}
             Sl["x0"] = x
@@ -292,12 +303,14 @@ class Engine:
                          out_bf16=self._qkv_groups(qkv, BT))
             o = nb("o", l, (M, BT, C), bf)
             lse = nb("lse", l, (1, M, B, H, T), f32)
-            if cache is not None:      # append this call's keys / values (a strided device copy: cache bookkeeping, not math)
+            if dyn:
+                ops.kv_append(qkv.view(M, B, 3 * C)[..., C:], cache.self_kv[l], cache.len_dev)
+            elif cache is not None:    # append this call's keys / values (a strided device copy: cache bookkeeping, not math)
                 cache.self_kv[l][:, :, t0:t0 + T].copy_(qkv.view(M, B, T, 3 * C)[..., C:])
             if decode:
                 kc = cache.self_kv[l]
                 ops.attention_decode(qkv.view(M, B, 3 * C)[..., 0:C], [kc[..., 0:C]], [kc[..., C:2 * C]], o.view(M, B, C),
-                                     length=t0 + 1, H=H, hs=hs)
+                                     length=1 if dyn else t0 + 1, H=H, hs=hs, **({"len_dev": cache.len_dev} if dyn else {}))
             else:
                 ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
                                   **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
@@ -389,7 +402,48 @@ class Engine:
             self._saved = S
         if cache is not None:
             cache.length = t0 + T
+            if dyn:
+                cache.len_dev.add_(1)        # part of the step (and of its graph): the next replay sees the new count
+            else:
+                cache.len_dev.fill_(cache.length)
         return [lg.view(B, T, -1) for lg in logits], losses
+
+    def decode_step(self, idx, cache):
+        """One new position per sequence against the K/V cache (generate's growing phase; idx int64 [M, B, 1]). On a CUDA
+        device in the bf16 mode the step is replayed as a CUDA graph: the number of cached positions lives in device memory
+        (cache.len_dev) and is read there by the position-embedding, cache-append and decode-attention kernels, so one
+        captured graph serves every position. The first decode step of a cache runs eagerly (it allocates the one-row
+        buffers), the second one is captured, later ones are replays. TRADEAID_DECODE_GRAPH=0 keeps plain launches."""
+        use_graph = (self.device.type == "cuda" and self.precision == "bf16" and hasattr(self.ops, "kv_append")
+                     and os.environ.get("TRADEAID_DECODE_GRAPH", "1") != "0")
+        if cache.length == 0 or idx.shape[2] != 1:
+            raise ValueError("decode_step takes one new position per sequence after the prompt has filled the cache")
+        if not use_graph and not os.environ.get("TRADEAID_DECODE_DYN"):
+            return self.forward(idx, None, save=False, train=False, cache=cache)[0]
+        if cache.length + 1 > cache.capacity:
+            raise ValueError(f"cache holds {cache.length} of {cache.capacity} positions")
+        cache.dyn = True
+        try:
+            if not use_graph or cache._dyn_steps == 0:
+                cache._dyn_steps += 1
+                return self.forward(idx, None, save=False, train=False, cache=cache)[0]
+            if cache._graph is None:
+                if self.shadows_stale:
+                    self.refresh_shadows()
+                cache._static_idx = idx.clone()
+                length = cache.length
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    cache._static_logits = self.forward(cache._static_idx, None, save=False, train=False, cache=cache)[0]
+                cache.length = length        # capture does not run the step: undo the host-side count
+                cache._graph = g
+            cache._static_idx.copy_(idx)
+            cache._graph.replay()
+            cache.length += 1
+            cache._dyn_steps += 1
+            return cache._static_logits
+        finally:
+            cache.dyn = False
 
     def _hid_groups(self, hid, BT, gsz=1):
         """[M, BT, 3H*h2p] -> [M, 3H/gsz, BT, gsz*h2]: column slices of gsz neighbouring (q|k|v, head) blocks."""
@@ -445,7 +499,11 @@ class Engine:
             for j in range(j0, j1):
                 kvs[j] = kv[j - j0]
         decode = cache is not None and t0 > 0
-        if cache is not None:
+        dyn = decode and cache.dyn
+        if dyn:
+            for r, kv in enumerate(kv_runs):
+                ops.kv_append(kv.view(kv.shape[0], B, kv.shape[-1]), cache.cross_kv[l][r], cache.len_dev)
+        elif cache is not None:
             for r, kv in enumerate(kv_runs):
                 cache.cross_kv[l][r][:, :, t0:t0 + T].copy_(kv.view(kv.shape[0], B, T, kv.shape[-1]))
         oc = nb("oc", l, (Xc, BT, C), bf)
@@ -454,8 +512,9 @@ class Engine:
         for xi, i in enumerate(d.xc):
             if decode:     # the new row of querier i against the cached K/V of every other modality
                 ks, vs = self._kv_cache_views(cache.cross_kv[l], i)
-                ops.attention_decode(qc[xi:xi + 1].view(1, B, C), ks, vs, oc[xi:xi + 1].view(1, B, C), length=t0 + 1, H=H,
-                                     hs=hs, head_stride_kv=2 * hs)
+                ops.attention_decode(qc[xi:xi + 1].view(1, B, C), ks, vs, oc[xi:xi + 1].view(1, B, C),
+                                     length=1 if dyn else t0 + 1, H=H, hs=hs, head_stride_kv=2 * hs,
+                                     **({"len_dev": cache.len_dev} if dyn else {}))
                 continue
             ks, vs = self._kv_views(kvs, i)
             ops.attention_fwd(qc[xi:xi + 1], ks, vs, oc[xi:xi + 1], lsec[xi], B=B, T=T, H=H, hs=hs, head_stride_kv=2 * hs,

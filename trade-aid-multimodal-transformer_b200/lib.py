@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class TaOperand(C.Structure):
@@ -190,7 +190,7 @@ _lib.ta_attention_fwd.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTenso
 _lib.ta_attention_decode.restype = C.c_int32
 _lib.ta_attention_decode.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor),
                                      C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
-                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
 
 
 def _attn_tensor(t, head_stride):
@@ -251,9 +251,10 @@ def attention_fwd_f32(q, ks, vs, o, lse, *, B, T, H, hs, head_stride_q=None, hea
                                      o_src.stride(0) if o_src is not None else 0, _ptr(lse), G, B, T, H, hs, _stream()))
 
 
-def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None):
+def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None, len_dev=None):
     """q: bf16 [G, B, *] (one new row per batch); ks/vs: lists (one per source) of cache views [G, B, capacity, *] whose
-    column 0 is head 0 / dim 0; o: bf16 [G, B, H*hs]. Attends to cached positions [0, length)."""
+    column 0 is head 0 / dim 0; o: bf16 [G, B, H*hs]. Attends to cached positions [0, length) - with len_dev (int32 [1] on the
+    device: CUDA-graph replay) to [0, *len_dev + length)."""
     n_src = len(ks)
     G, B = q.shape[0], q.shape[1]
     hq = head_stride_q if head_stride_q is not None else hs
@@ -262,11 +263,14 @@ def attention_decode(q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_st
     qa = (TaAttnTensor * 1)(TaAttnTensor(q.data_ptr(), q.stride(1), hq, q.stride(0)))
     for t in list(ks) + list(vs):
         assert t.dim() == 4 and t.shape[0] == G and t.shape[1] == B and t.shape[2] >= length and t.stride(-1) == 1
+    if len_dev is not None:
+        import torch
+        assert len_dev.dtype == torch.int32 and len_dev.numel() == 1
     ka = (TaAttnTensor * n_src)(*[TaAttnTensor(k.data_ptr(), k.stride(2), hkv, k.stride(0)) for k in ks])
     va = (TaAttnTensor * n_src)(*[TaAttnTensor(v.data_ptr(), v.stride(2), hkv, v.stride(0)) for v in vs])
     bs = (C.c_int64 * n_src)(*[k.stride(1) for k in ks])
-    _check(_lib.ta_attention_decode(qa, ka, va, bs, n_src, _ptr(o), o.stride(1), o.stride(0), G, B, int(length), H, hs,
-                                    _stream()))
+    _check(_lib.ta_attention_decode(qa, ka, va, bs, n_src, _ptr(o), o.stride(1), o.stride(0), G, B, int(length), _ptr(len_dev),
+                                    H, hs, _stream()))
 
 
 # ---------------------------------------------------------------------------------------------------- row ops
@@ -280,6 +284,8 @@ def _sig(name, *argtypes, restype=C.c_int32):
 _P, _I32, _I64, _F32, _F64, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_uint64
 _gather_batch = _sig("ta_gather_batch", _P, _I64, _I32, _P, _I32, _I32, _P, _P, _P)
 _embed_fwd = _sig("ta_embed_fwd", _P, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _P)
+_embed_fwd_at = _sig("ta_embed_fwd_at", _P, _P, _P, _P, _P, _I32, _I64, _I32, _P, _P)
+_kv_append = _sig("ta_kv_append", _P, _I64, _I64, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P, _P)
 _embed_bwd = _sig("ta_embed_bwd", _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _P)
 _ln_fwd = _sig("ta_layernorm_fwd", _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _F32, _P)
 _ln_fwd_f32 = _sig("ta_layernorm_fwd_f32", _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _F32, _P)
@@ -350,6 +356,30 @@ def embed_fwd(idx, tok, voff, pos, x, T):
     Cc = tok.shape[1]
     assert idx.is_contiguous() and tok.is_contiguous() and pos.is_contiguous() and x.is_contiguous()
     _check(_embed_fwd(_ptr(idx), _ptr(tok), _ptr(voff), _ptr(pos), _ptr(x), M, rows, T, Cc, _stream()))
+
+
+def embed_fwd_at(idx, tok, voff, pos, x, pos_dev):
+    """One new position per sequence at index *pos_dev (int32 [1] on the device): idx int64 [M, rows]; x fp32 [M, rows, C]."""
+    import torch
+    M, rows = idx.shape
+    assert idx.is_contiguous() and tok.is_contiguous() and pos.is_contiguous() and x.is_contiguous()
+    assert pos_dev.dtype == torch.int32 and pos_dev.numel() == 1
+    _check(_embed_fwd_at(_ptr(idx), _ptr(tok), _ptr(voff), _ptr(pos), _ptr(x), M, rows, tok.shape[1], _ptr(pos_dev), _stream()))
+
+
+def kv_append(src, cache, pos_dev):
+    """cache[g, b, *pos_dev, :W] = src[g, b, :W]; src [G, B, W] view (unit inner stride), cache [G, B, capacity, >= W] view of
+    the same dtype (bf16 or fp32; W * element size a multiple of 4)."""
+    import torch
+    G, Bn, W = src.shape
+    es = src.element_size()
+    assert cache.dim() == 4 and cache.shape[0] == G and cache.shape[1] == Bn and cache.dtype == src.dtype
+    assert src.stride(-1) == 1 and cache.stride(-1) == 1 and (W * es) % 4 == 0 and pos_dev.dtype == torch.int32
+    k = 4 // es
+    for st in (src.stride(0), src.stride(1), cache.stride(0), cache.stride(1), cache.stride(2)):
+        assert st % k == 0
+    _check(_kv_append(_ptr(src), src.stride(0) // k, src.stride(1) // k, _ptr(cache), cache.stride(0) // k, cache.stride(1) // k,
+                      cache.stride(2) // k, G, Bn, W // k, _ptr(pos_dev), _stream()))
 
 
 def embed_bwd(idx, dx, voff, max_vocab, dtok, dpos, B, T):

@@ -276,9 +276,10 @@ class MultimodalTransformer(nn.Module):
                 if cache is None:
                     cache = KVCache(eng, seqs[mg].shape[0], T)
                     new = torch.stack([s.to(eng.device, torch.int64) for s in seqs[:M]]).contiguous()
+                    logits, _ = eng.forward(new, None, save=False, train=False, cache=cache)
                 else:
                     new = torch.stack([s[:, -1:].to(eng.device, torch.int64) for s in seqs[:M]]).contiguous()
-                logits, _ = eng.forward(new, None, save=False, train=False, cache=cache)
+                    logits = eng.decode_step(new, cache)       # replayed as a CUDA graph from the second decode step on
                 last = logits[mg][:, -1, :]
             else:
                 cache = None

@@ -139,7 +139,8 @@ class SplitPrecisionOps:
         if o_src is not None:
             self.inner.convert(osb.reshape(-1, *osb.shape[-2:]), o_src.reshape(-1, *o_src.shape[-2:]))
 
-    def attention_decode(self, q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None):
+    def attention_decode(self, q, ks, vs, o, *, length, H, hs, head_stride_q=None, head_stride_kv=None, len_dev=None):
+        assert len_dev is None, "the bf16x3 mode does not replay the decode step as a graph"
         hq, hkv = head_stride_q or hs, head_stride_kv or hs
         G, Bn = q.shape[0], q.shape[1]
         qb = self._heads_bf16("ad_q", q, H, hs, hq)
