@@ -679,7 +679,8 @@ def run_inference(args, cfg):
                 "forward": {"ms": fwd_ms, "algorithmic_tflop": flops / 1e12, "tflops": flops / (fwd_ms * 1e-3) / 1e12,
                             "frac_of_measured_sustained": flops / (fwd_ms * 1e-3) / 1e12 / pk["tc_sustained"]},
                 "generate": {"prompt": n0, "prefill_ms": p0.elapsed_time(p1), "decode_ms_per_position": dec_ms,
-                             "decode_tokens_per_s": M * B / (dec_ms * 1e-3), "kv_cache_bytes": cache.bytes(),
+                             "decode_tokens_per_s": M * B / (dec_ms * 1e-3), "decode_as_cuda_graph": cache._graph is not None,
+                             "kv_cache_bytes": cache.bytes(),
                              "kv_cache_GBs_read": cache.bytes() * (n0 + n_dec / 2) / T / (dec_ms * 1e-3) / 1e9,
                              "recompute_ms_per_position": recompute_ms,
                              "speedup_vs_recompute": recompute_ms / dec_ms},

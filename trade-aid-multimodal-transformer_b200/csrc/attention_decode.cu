@@ -39,10 +39,9 @@ struct AttnDecodeParams {
 constexpr int AD_U = 8;
 
 template <int HS>
-__global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid_constant__ AttnDecodeParams pp) {
+__global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid_constant__ AttnDecodeParams p) {
   pdl_prologue();
-  AttnDecodeParams p = pp;
-  if (p.len_dev) p.len += *p.len_dev;
+  const int len = p.len + (p.len_dev ? *p.len_dev : 0);      // cached positions to attend to
   constexpr int LPR = HS / 8;            // lanes per row
   constexpr int RPI = 32 / LPR;          // rows per warp-wide load instruction
   constexpr int CHUNK = RPI * AD_U;      // rows per chunk
@@ -90,14 +89,14 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
 #pragma unroll
       for (int u = 0; u < AD_U; ++u) {
         const int pos = p0 + u * RPI + rg;
-        dst[u] = (pos < p.len && act) ? __ldg(reinterpret_cast<const uint4*>(base_ptr + (long long)pos * ld)) : make_uint4(0, 0, 0, 0);
+        dst[u] = (pos < len && act) ? __ldg(reinterpret_cast<const uint4*>(base_ptr + (long long)pos * ld)) : make_uint4(0, 0, 0, 0);
       }
     };
     // software pipeline without extra registers: the K registers are dead once the scores are formed, the V registers
     // once the accumulators are updated - the next chunk's rows are requested right there
     load_rows(ku, kb, 0);
     load_rows(vu, vb, 0);
-    for (int p0 = 0; p0 < p.len; p0 += CHUNK) {
+    for (int p0 = 0; p0 < len; p0 += CHUNK) {
       float sc[AD_U];
 #pragma unroll
       for (int u = 0; u < AD_U; ++u) {
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
         }
         sc[u] = a;
       }
-      if (p0 + CHUNK < p.len) load_rows(ku, kb, p0 + CHUNK);
+      if (p0 + CHUNK < len) load_rows(ku, kb, p0 + CHUNK);
       // complete the dot products over the LPR lanes of a row; afterwards every lane of the row holds the score
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) {
@@ -121,7 +120,7 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
       float cm = -INFINITY;
 #pragma unroll
       for (int u = 0; u < AD_U; ++u) {
-        if (p0 + u * RPI + rg >= p.len) sc[u] = -INFINITY;
+        if (p0 + u * RPI + rg >= len) sc[u] = -INFINITY;
         cm = fmaxf(cm, sc[u]);
       }
 #pragma unroll
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(AD_WARPS * 32) attn_decode_kernel(const __grid
           acc[2 * j + 1] = fmaf(sc[u], f.y, acc[2 * j + 1]);
         }
       }
-      if (p0 + CHUNK < p.len) load_rows(vu, vb, p0 + CHUNK);
+      if (p0 + CHUNK < len) load_rows(vu, vb, p0 + CHUNK);
     }
     // sum the row groups (lanes with the same piece); every lane ends with the full sum of its 8 dims
 #pragma unroll

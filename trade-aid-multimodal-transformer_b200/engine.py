@@ -261,7 +261,9 @@ class Engine:
         if hasattr(ops, "set_pdl") and "TA_PDL" not in os.environ:
             # launch-latency territory (c2: 282 launches of a few microseconds each): let the next kernel's CTAs be scheduled
             # while the previous one drains; large problems run one persistent CTA per SM and gain nothing (common.cuh)
-            ops.set_pdl(M * BT * C <= (8 << 20))
+            # (not on the cached decode path: there the early-scheduled CTAs of the next small kernel take SM slots from the
+            # HBM-bound decode-attention kernel - c5 decode 5.7 -> 7.1 ms per position with it)
+            ops.set_pdl(M * BT * C <= (8 << 20) and cache is None)
         bf, f32 = self.act_dtype, torch.float32
         S = {"B": B, "T": T, "layers": [], "idx": idx, "pd": pd, "drop_step": self._drop_step_host}
         t0 = 0
