@@ -259,7 +259,9 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 // in flight before the first reduction. The first version kept a whole row plus its dgamma/dbeta accumulators in one
 // warp (193 registers, 8 warps per SM) and reached 27% of the HBM roofline on c4.
 template <int TPR, int NV, int R>
-__global__ void __launch_bounds__(256, NV == 1 ? 3 : 1)
+// (three resident blocks cap a thread at 80 registers: fine for TPR = 256, where a thread owns one float4 per row; the
+// narrower rows keep SLOTS x R rows per thread block in flight and spilled 124-164 bytes at 80, so they run two blocks)
+__global__ void __launch_bounds__(256, NV == 1 ? (TPR == 256 ? 3 : 2) : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ dstream_in, float* __restrict__ dstream_out, __nv_bfloat16* __restrict__ dstream_bf16,
@@ -737,7 +739,8 @@ static void ln_bwd_shape(int64_t rows_per_group, int64_t G, int C, int* tpr, int
   *tpr = C <= 128 ? 32 : C <= 256 ? 64 : C <= 512 ? 128 : 256;
   *r = 4;
   const int64_t rpp = (int64_t)*r * (256 / *tpr);
-  int64_t want = ((int64_t)num_sms() * 3) / G;              // 3 resident blocks per SM over all groups, one wave
+  const int resident = C <= 512 ? 2 : 3;                    // the kernel's launch bounds
+  int64_t want = ((int64_t)num_sms() * resident) / G;       // every block resident, over all groups: one wave
   const int64_t passes = ceil_div(rows_per_group, rpp);
   if (want > passes) want = passes;
   if (want < 1) want = 1;
