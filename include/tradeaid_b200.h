@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 8
+#define TA_ABI_VERSION 9
 
 const char* ta_last_error(void);
 int32_t ta_abi_version(void);
@@ -153,10 +153,13 @@ int32_t ta_kv_append(const void* src, int64_t s_g, int64_t s_b, void* cache, int
                      int32_t B, int32_t W_words, const int32_t* pos_dev, void* stream);
 
 /* Backward of the above (recompute): given dO (layout of o) produces dq (layout of q), and per source dk, dv (layouts
- * of k[s], v[s]); all bf16. T <= 256 in this build. */
+ * of k[s], v[s]); all bf16. T <= 256 in this build. Two launches on `stream`: one pass over dO and the per-source outputs
+ * writes D = rowsum(dO * O_s) into `workspace` (ta_attention_bwd_workspace_bytes(n_src, G, B, T, H) bytes of device memory,
+ * fp32 [n_src][G][B][H][T], the layout of lse), then the tile kernel. */
+int64_t ta_attention_bwd_workspace_bytes(int32_t n_src, int32_t G, int32_t B, int32_t T, int32_t H);
 int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v, int32_t n_src,
                          const void* o_bf16, const void* o_src_bf16, int64_t o_src_stride, const void* do_bf16,
-                         int64_t ldo, int64_t o_gs, const float* lse, const ta_attn_tensor* dq,
+                         int64_t ldo, int64_t o_gs, const float* lse, void* workspace, const ta_attn_tensor* dq,
                          const ta_attn_tensor* dk, const ta_attn_tensor* dv, int32_t G, int32_t B, int32_t T, int32_t H,
                          int32_t hs, float dropout_p, uint64_t seed, void* stream);
 

@@ -323,6 +323,7 @@ ATTN_CASES = [
     (1, 1, 1024, 2, 64, 2),   # c5 long context
     (1, 2, 100, 2, 16, 2),    # ragged T
     (1, 3, 5, 2, 8, 1),       # T < block_size (generate)
+    (1, 2, 37, 3, 24, 2),     # odd T, head size that is no power of two
 ]
 
 

@@ -7,17 +7,25 @@
 //   dV_j, dK_j     2 x 64  columns   accumulated over the query tiles i >= j
 //   dQ_0, dQ_1     2 x 64  columns   accumulated over key/value tiles j <= i AND over all key/value sources
 //   warp 16  loader : TMA Q/dO tiles of the head, K/V tiles through a 2-stage ring (runs ahead)
-//   warp 17  issuer : S and dP of pair n+1 are issued as soon as the math warps have pulled S / dP of pair n out of
-//                     TMEM; the three gradient UMMAs of pair n run while the math warps work on pair n+1
-//   warps 0-15 math : thread (row r, column quarter) owns 32 columns: P = exp2(S*c - lse), dS = P * (dP - D) with
-//                     D = rowsum(dO * O_src) computed once per head straight from global memory; P and dS go to
+//   warp 17  issuer : S and dP of pair n+1 are issued as soon as the math warps have pulled S / dP of pair n out of TMEM
+//   warp 18  issuer : the three gradient UMMAs of pair n run while the math warps work on pair n+1; its commits hand
+//                     the K/V stage and the Q/dO slot back to the loader the moment their last reader has completed
+//   warp 19  storer : TMA stores of the dK/dV/dQ read-outs from two staging tiles of their own
+//   warps 0-15 math : thread (row r, column quarter) owns 32 columns: P = exp2(S*c - lse), dS = P * (dP - D); lse and
+//                     D = rowsum(dO * O_src) come from global tables (D: attn_bwd_dtab_kernel below, one HBM pass over dO
+//                     and the per-source outputs right before this kernel), loaded one pair ahead. P and dS go to
 //                     128B-swizzled smem once and are consumed by three UMMAs through two descriptor views of the same
 //                     bytes: K-major (dQ += dS K) and MN-major (dV += P^T dO, dK += dS^T Q). The dK/dV/dQ read-outs are
 //                     deferred behind the next pair's math so the gradient UMMAs never stall the math warps.
 // K_j, V_j, Q_i, dO_i are read straight from their TMA tiles as MN-major B operands. hs^-0.5 is applied to dQ / dK at
 // read-out. No T x T tensor and no atomics; dq/dk/dv are written once, in bf16.
-// The previous version ran S/dP -> math -> gradient UMMAs strictly one after another in a 9-warp CTA (tensor pipe 8%
-// active, 43% of the samples waiting on mbarriers: profiles/r01_ncu_attn_v2.txt).
+// History (CTA timelines: profiles/r02_attn_bwd_trace_*.txt). v1 ran S/dP -> math -> gradient UMMAs strictly one after
+// another in a 9-warp CTA (tensor pipe 8% active). v2 overlapped them but (a) computed D in a per-head prologue of the math
+// warps - 9 k of a 21 k-cycle head at the c4 self shape, 38 k of 116 k with 7 sources, every UMMA queue drained meanwhile -
+// and (b) staged the read-outs in the dead K/V and Q/dO tiles, so a tile could only be reloaded after its TMA store had
+// drained: the first pair of every source and the second pair of every head waited ~2500 cycles for operands. Storing the
+// read-outs straight from registers instead (64 contiguous bytes per thread) was worse: one L1 tag cycle per row and
+// instruction, 0.76 instead of 0.54 ms.
 #include <cmath>
 #include <cstdlib>
 #include <cuda_bf16.h>
@@ -41,11 +49,6 @@ struct AttnBwdMaps {
   CUtensorMap dv[ATTB_MAX_SRC];
 };
 
-struct GradOut {
-  __nv_bfloat16* ptr;
-  long long ld, head_stride, gs;
-};
-
 struct AttnBwdParams {
   int T, B, H, G, hs, n_src, n_qt, total_work;
   long long* trace;   // TA_ATTN_TRACE=<device address> (dev only): clock64 stamps of CTA 0, 4 roles x 1024 slots
@@ -53,16 +56,10 @@ struct AttnBwdParams {
   float drop_scale;                // 1 / (1 - p)
   unsigned long long drop_seed;
   const unsigned long long* drop_step;
-  int debug;   // TA_ATTN_DEBUG (dev only): 1 = no D/lse prologue loads, 2 = no read-out stores, 4 = no P/dS math
+  int debug;   // TA_ATTN_DEBUG (dev only): 1 = no D/lse loads, 2 = no read-out stores, 4 = no P/dS math
   float scale, scale_log2;
-  const __nv_bfloat16* d_o;    // [G][B*T][ldo]
-  const __nv_bfloat16* o;      // [G][B*T][ldo]
-  const __nv_bfloat16* o_src;  // [n_src] x same, or NULL when n_src == 1
-  long long ldo, o_gs, o_src_stride;
   const float* lse;            // [n_src][G][B][H][T]
-  GradOut dq;
-  GradOut dk[ATTB_MAX_SRC];
-  GradOut dv[ATTB_MAX_SRC];
+  const float* dtab;           // [n_src][G][B][H][T]  D = rowsum(dO * O_src)
 };
 
 // dev-only timeline: role 0 loader, 1 S/dP issuer, 2 math (warp 0), 3 gradient issuer; slot = running event index
@@ -80,7 +77,7 @@ struct AttnBwdParams {
 
 constexpr int AB_MATH_WARPS = 16;
 constexpr int AB_MATH_THREADS = AB_MATH_WARPS * 32;
-// warps 0-15 math, 16 loader, 17 S/dP issuer, 18 gradient issuer, 19 storer (TMA stores of dK/dV/dQ)
+// warps 0-15 math, 16 loader, 17 S/dP issuer, 18 gradient issuer, 19 storer (640 x 96 registers = 512 x 104 + 128 x 64)
 constexpr int AB_THREADS = (AB_MATH_WARPS + 4) * 32;
 constexpr int AB_TILE = 16384;                          // 128 rows x 128 B
 
@@ -107,8 +104,9 @@ struct AbIter {
 enum : uint32_t {
   AB_Q_FULL = 0, AB_Q_EMPTY = 2, AB_KV_FULL = 4, AB_KV_EMPTY = 6, AB_S_FULL = 8, AB_DP_FULL = 10, AB_S_EMPTY = 12,
   AB_DP_EMPTY = 14, AB_PDS_FULL = 16, AB_G_DONE = 17, AB_DKV_EMPTY = 18, AB_DQ_EMPTY = 19,
-  AB_SKV_FULL = 20, AB_SQ_FULL = 21, AB_NBARS = 22
+  AB_ST_FULL = 20, AB_ST_EMPTY = 21, AB_NBARS = 22
 };
+constexpr int AB_NTILES = 14;   // Q, dO: 2 slots each; K/V: 2 stages; P, dS: 2 column halves each; 2 read-out staging tiles
 
 // DROPOUT is a template parameter: the mask code sat in the middle of the hot loop (two Philox draws and sixteen selects per
 // 16-column piece) and was executed-around on every pair of the common p = 0 case
@@ -118,15 +116,14 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   constexpr int TILE = AB_TILE;
   constexpr int OC = DP / 2;   // gradient columns per math thread at read-out
   extern __shared__ __align__(1024) uint8_t smem[];
-  // [Q 2 slots][dO 2 slots][2 stages x (K, V)][P: 2 column halves][dS: 2 column halves][barriers][D][lse]
-  // Dead operand tiles double as the staging tiles of the gradient read-outs (TMA stores): dK_j / dV_j go into the
-  // K_j / V_j tiles of their own ring stage, dQ into the Q/dO slot of the head's last query tile; the STORER warp
-  // releases those tiles to the loader once the TMA store has drained them.
+  // [Q 2 slots][dO 2 slots][2 stages x (K, V)][P: 2 column halves][dS: 2 column halves][staging: 2 tiles][barriers]
+  // The staging tiles take the dK_j / dV_j read-out of a key/value tile, or the two dQ tiles of a head, for the storer's
+  // TMA stores; only the next read-out waits for them: dK/dV read-outs are at least a pair apart, and the dQ read-out of a
+  // head follows its last dK/dV read-out half a pair later (middle / end of the next head's first pair).
   const uint32_t sQ = smem_u32(smem), sdO = sQ + 2 * TILE, sKV = sQ + 4 * TILE, sP = sQ + 8 * TILE, sdS = sQ + 10 * TILE;
-  const uint32_t bb = sQ + 12 * TILE;                        // barrier i at bb + 8 * i
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + 12 * TILE + AB_NBARS * 8);
-  const uint32_t sD = bb + AB_NBARS * 8 + 16;                // fp32 [n_src][256] rowsum(dO * O_src)
-  const uint32_t sLse = sD + ATTB_MAX_SRC * 256 * 4;         // fp32 [n_src][256] lse * log2(e)
+  const uint32_t sSt = sQ + 12 * TILE;
+  const uint32_t bb = sQ + AB_NTILES * TILE;                 // barrier i at bb + 8 * i
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + AB_NTILES * TILE + AB_NBARS * 8);
   if ((sQ & 1023u) != 0) __trap();
 
   // the shuffle tells the compiler that `warp` is warp-uniform: the issuer branches then compute their descriptors in
@@ -135,7 +132,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   if (tid == 0) {
     for (uint32_t x = 0; x < AB_NBARS; ++x) {
       const bool wide = x == AB_S_EMPTY || x == AB_S_EMPTY + 1 || x == AB_DP_EMPTY || x == AB_DP_EMPTY + 1 ||
-                        x == AB_PDS_FULL || x == AB_DKV_EMPTY || x == AB_DQ_EMPTY || x == AB_SKV_FULL || x == AB_SQ_FULL;
+                        x == AB_PDS_FULL || x == AB_DKV_EMPTY || x == AB_DQ_EMPTY || x == AB_ST_FULL;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bb + 8 * x), "r"(wide ? AB_MATH_THREADS : 1));
     }
     fence_mbar_init();
@@ -157,7 +154,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
   // Q/dO smem slot of query tile ti: two tiles per head use slot = tile, one tile per head alternates between heads
   auto slot = [&](const AbIter& a, int ti) { return n_qt == 2 ? ti : (a.hc & 1); };
   auto slot_use = [&](const AbIter& a) { return n_qt == 2 ? a.hc : (a.hc >> 1); };
-  auto bar = [&](uint32_t i) { return reinterpret_cast<uint64_t*>(smem + 12 * TILE) + i; };
+  auto bar = [&](uint32_t i) { return reinterpret_cast<uint64_t*>(smem + AB_NTILES * TILE) + i; };
 
   if (warp >= AB_MATH_WARPS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -199,36 +196,35 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
       }
     } else if (warp == AB_MATH_WARPS + 3) {
       // ================================================================== storer (one lane): TMA stores of the read-outs
+      // jobs in the order the math warps produce them: dK_j / dV_j after the last pair of a key/value tile, then - after
+      // the last pair of a head - its dQ tiles
       if ((tid & 31) == 0) {
-        int ekv = 0, eq = 0;
+        uint32_t job = 0;
+        auto drain = [&]() {
+          bulk_commit_group();
+          bulk_wait_read<0>();
+          mbar_arrive_a(bb + 8 * AB_ST_EMPTY);      // the staging tiles may be overwritten
+          ++job;
+        };
         for (; it.work < total; it.next(n_qt, n_src, stride)) {
           if (it.i != n_qt - 1) continue;
           int w = it.work;
           const int h = w % p.H; w /= p.H;
           const int b = w % p.B;
           const int g = w / p.B;
-          // dK_j, dV_j of the key/value tile whose last pair this is: staged in the K/V tiles of its own stage
-          const int st = it.ks & 1;
-          mbar_wait_a(bb + 8 * AB_SKV_FULL, ekv & 1);
+          mbar_wait_a(bb + 8 * AB_ST_FULL, job & 1);
           if (!(p.debug & 2)) {
-            tma_store_5d(&maps.dk[it.s], sKV + st * 2 * TILE, 0, h, it.j * 128, b, g);
-            tma_store_5d(&maps.dv[it.s], sKV + st * 2 * TILE + TILE, 0, h, it.j * 128, b, g);
+            tma_store_5d(&maps.dk[it.s], sSt, 0, h, it.j * 128, b, g);
+            tma_store_5d(&maps.dv[it.s], sSt + TILE, 0, h, it.j * 128, b, g);
           }
-          bulk_commit_group();
-          bulk_wait_read<0>();
-          mbar_arrive_a(bb + 8 * (AB_KV_EMPTY + st));      // the loader may refill this stage
-          ++ekv;
-          if (it.j == n_qt - 1 && it.s == n_src - 1) {   // last pair of the head: dQ tiles, staged in the slot of tile n_qt - 1
-            const int sl = slot(it, n_qt - 1);
-            mbar_wait_a(bb + 8 * AB_SQ_FULL, eq & 1);
+          drain();
+          if (it.j == n_qt - 1 && it.s == n_src - 1) {   // last pair of the head
+            mbar_wait_a(bb + 8 * AB_ST_FULL, job & 1);
             if (!(p.debug & 2)) {
-              tma_store_5d(&maps.dq, sQ + sl * TILE, 0, h, 0, b, g);
-              if (n_qt > 1) tma_store_5d(&maps.dq, sdO + sl * TILE, 0, h, 128, b, g);
+              tma_store_5d(&maps.dq, sSt, 0, h, 0, b, g);
+              if (n_qt > 1) tma_store_5d(&maps.dq, sSt + TILE, 0, h, 128, b, g);
             }
-            bulk_commit_group();
-            bulk_wait_read<0>();
-            mbar_arrive_a(bb + 8 * (AB_Q_EMPTY + sl));     // the loader may refill this slot
-            ++eq;
+            drain();
           }
         }
         bulk_wait_all<0>();
@@ -299,9 +295,10 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
                          acc_q | (kk != 0));
           umma_commit_ws(bb + 8 * AB_G_DONE);
           AB_TRACE(3, tc, 5);   // grads issued
-          // last pair that reads query tile i < n_qt - 1: its slot goes back to the loader. (The K/V stage and the slot
-          // of the last query tile are released by the storer: they stage the dK/dV and dQ read-outs first.)
-          if (a.s == n_src - 1 && a.j == a.i && a.i != n_qt - 1) umma_commit_ws(bb + 8 * (AB_Q_EMPTY + sl));
+          // last pair that reads query tile i / key-value tile j: the slot / ring stage goes back to the loader when these
+          // UMMAs are complete (the S / dP UMMAs of the pair completed before the math warps could produce P / dS)
+          if (a.s == n_src - 1 && a.j == a.i) umma_commit_ws(bb + 8 * (AB_Q_EMPTY + sl));
+          if (a.i == n_qt - 1) umma_commit_ws(bb + 8 * (AB_KV_EMPTY + st));
         }
       }
     }
@@ -310,9 +307,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
     // ================================================================== math warps
     const int r = tid & 127, qd = tid >> 7, wq = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-    // deferred read-outs, packed: bit 0 dK/dV pending, bit 1 dQ pending, bit 2/3 their g_done parities,
-    // bit 4 ring stage of the pending key/value tile, bit 5 Q/dO slot that stages dQ
+    // deferred read-outs, packed: bit 0 dK/dV pending, bit 1 dQ pending, bit 2/3 their g_done parities
     uint32_t pend = 0;
+    uint32_t job = 0;          // read-outs staged so far (the storer counts the same sequence)
     // TMEM -> scale -> bf16 -> staging tile row r (128B-swizzled, the layout of the TMA store box), RC columns at a time
     constexpr int RC = OC < 16 ? OC : 16;
     auto read_stage = [&](uint32_t taddr, uint32_t stile, int col0, float mul, bool do_ld) {
@@ -334,120 +331,65 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
         }
       }
     };
-    // dK_j (quarters 2, 3) -> K tile, dV_j (quarters 0, 1) -> V tile of the stage the tile was loaded into (dead: every
-    // UMMA that reads it is complete); the storer warp issues the TMA stores and hands the stage back to the loader
+    // dK_j (quarters 2, 3) -> staging tile 0, dV_j (quarters 0, 1) -> staging tile 1: every UMMA that accumulates into
+    // them is complete at g_done, and the storer has drained the previous read-out from the staging tiles
     auto readout_kv = [&]() {
       mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 2) & 1);
+      mbar_wait_a(bb + 8 * AB_ST_EMPTY, (job & 1) ^ 1);
       tc_fence_after();
       const bool is_k = qd >= 2;
-      read_stage(tmem_base + (is_k ? 320 : 256) + lane_off, sKV + ((pend >> 4) & 1) * 2 * TILE + (is_k ? 0 : TILE), (qd & 1) * OC,
-                 is_k ? p.scale : 1.f, true);
+      read_stage(tmem_base + (is_k ? 320 : 256) + lane_off, sSt + (is_k ? 0 : TILE), (qd & 1) * OC, is_k ? p.scale : 1.f, true);
       tc_fence_before();
       mbar_arrive_a(bb + 8 * AB_DKV_EMPTY);
       fence_proxy_async_smem();
-      mbar_arrive_a(bb + 8 * AB_SKV_FULL);
-      pend &= ~0x15u;
+      mbar_arrive_a(bb + 8 * AB_ST_FULL);
+      ++job;
+      pend &= ~0x5u;
     };
-    // dQ_0 (quarters 0, 1) -> Q tile, dQ_1 (quarters 2, 3) -> dO tile of the slot of the head's last query tile
+    // dQ_0 (quarters 0, 1) -> staging tile 0, dQ_1 (quarters 2, 3) -> staging tile 1
     auto readout_q = [&]() {
       mbar_wait_a(bb + 8 * AB_G_DONE, (pend >> 3) & 1);
+      mbar_wait_a(bb + 8 * AB_ST_EMPTY, (job & 1) ^ 1);
       tc_fence_after();
       const int ti = qd >> 1;
-      read_stage(tmem_base + 384 + 64 * ti + lane_off, (ti ? sdO : sQ) + ((pend >> 5) & 1) * TILE, (qd & 1) * OC, p.scale, ti < n_qt);
+      read_stage(tmem_base + 384 + 64 * ti + lane_off, sSt + ti * TILE, (qd & 1) * OC, p.scale, ti < n_qt);
       tc_fence_before();
       mbar_arrive_a(bb + 8 * AB_DQ_EMPTY);
       fence_proxy_async_smem();
-      mbar_arrive_a(bb + 8 * AB_SQ_FULL);
-      pend &= ~0x2au;
+      mbar_arrive_a(bb + 8 * AB_ST_FULL);
+      ++job;
+      pend &= ~0xau;
     };
-    // per-thread piece of the D / lse prologue: row tid >> 1, 16-byte vectors 2v + (tid & 1) of the head's hs columns
-    const int drow = tid >> 1, dpart = tid & 1, nvec = p.hs >> 3;
-    int g2 = 0, b2 = 0, h2 = 0;
     int tc = 0;
     const bool ttr = warp == 0;
-    int g = 0, b = 0, h = 0;
+    // lse and D of this thread's row, loaded one pair ahead (an L2 round trip is as long as a fifth of a pair)
+    const long long src_stride = (long long)p.G * p.B * p.H * p.T;
+    auto table_base = [&](int work) {    // work = (g * B + b) * H + h
+      return (long long)work * p.T;
+    };
+    float Ln = 0.f, Dn = 0.f;
+    auto load_row = [&](const AbIter& a) {
+      const int row = a.i * 128 + r;
+      if (row < p.T && !(p.debug & 1)) {
+        const long long idx = a.s * src_stride + table_base(a.work) + row;
+        Ln = __ldg(p.lse + idx);
+        Dn = __ldg(p.dtab + idx);
+      } else {
+        Ln = Dn = 0.f;
+      }
+    };
+    if (it.work < total) load_row(it);
 
     for (; it.work < total; it.next(n_qt, n_src, stride)) {
-      if (it.first_of_head()) {
-        if (it.hc == 0) {
-          int w = it.work;
-          h = w % p.H; w /= p.H;
-          b = w % p.B;
-          g = w / p.B;
-        } else {
-          g = g2; b = b2; h = h2;      // decoded one head ahead (below)
-        }
-        // D[s][row] = rowsum(dO * O_s) and lse * log2(e) for the whole head, straight from global memory (two threads
-        // per row). The NEXT head's inputs are prefetched into L2 here, a whole head ahead of their use; this head's
-        // dO and first-source loads are issued before the pending read-outs so that their latency overlaps them.
-        // (Eight lanes per row - whole 128-byte lines per load instruction - measured slower: 0.61 vs 0.57 ms.)
-        if (ttr) AB_TRACE(2, tc, 7);            // prologue start
-        named_bar_sync(5, AB_MATH_THREADS);     // sD / sLse of the previous head are no longer read
-        if (ttr) AB_TRACE(2, tc, 8);            // first barrier passed
-        const bool rok = drow < p.T && !(p.debug & 1);
-        const long long roff = ((long long)b * p.T + drow) * p.ldo + h * p.hs;
-        if (it.work + stride < total) {
-          int w = it.work + stride;
-          h2 = w % p.H; w /= p.H;
-          b2 = w % p.B;
-          g2 = w / p.B;
-          if (rok && dpart == 0) {
-            const long long roff2 = ((long long)b2 * p.T + drow) * p.ldo + h2 * p.hs;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_o + (long long)g2 * p.o_gs + roff2));
-            for (int s = 0; s < n_src; ++s) {
-              const __nv_bfloat16* ob = p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o + (long long)g2 * p.o_gs;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(ob + roff2));
-              if ((drow & 31) == 0)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lse + ((((long long)s * p.G + g2) * p.B + b2) * p.H + h2) * p.T + drow));
-            }
-          }
-        }
-        if (ttr) AB_TRACE(2, tc, 14);           // prefetches issued
-        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        uint4 dvv[4], ov[4];
-        float lv;
-        auto load_src = [&](int s) {
-          const __nv_bfloat16* ob = p.o_src ? p.o_src + (long long)s * p.o_src_stride : p.o + (long long)g * p.o_gs;
-#pragma unroll
-          for (int v = 0; v < 4; ++v)
-            ov[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(ob + roff + (2 * v + dpart) * 8) : z4;
-          lv = (rok && dpart == 0) ? p.lse[((((long long)s * p.G + g) * p.B + b) * p.H + h) * p.T + drow] : 0.f;
-        };
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          dvv[v] = (rok && 2 * v + dpart < nvec) ? *reinterpret_cast<const uint4*>(p.d_o + (long long)g * p.o_gs + roff + (2 * v + dpart) * 8) : z4;
-        load_src(0);
-        if (ttr) AB_TRACE(2, tc, 11);           // loads issued
-        if (pend & 1) readout_kv();
-        if (ttr) AB_TRACE(2, tc, 13);           // kv read-out done
-        if (pend & 2) readout_q();
-        if (ttr) AB_TRACE(2, tc, 9);            // read-outs done
-        for (int s = 0; s < n_src; ++s) {
-          if (s > 0) load_src(s);
-          float acc = 0.f;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&dvv[v]);
-            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov[v]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              acc += __low2float(ah[e]) * __low2float(oh[e]) + __high2float(ah[e]) * __high2float(oh[e]);
-          }
-          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-          if (dpart == 0) {
-            sts_f32(sD + (s * 256 + drow) * 4, acc);
-            sts_f32(sLse + (s * 256 + drow) * 4, lv * 1.4426950408889634f);
-          }
-        }
-        if (ttr) AB_TRACE(2, tc, 10);           // D stored
-        named_bar_sync(5, AB_MATH_THREADS);
-        if (ttr) AB_TRACE(2, tc, 1);            // head prologue done
-      }
       const int row = it.i * 128 + r;
       const bool diag = it.i == it.j;
-      const float Lr = lds_f32(sLse + (it.s * 256 + row) * 4);
-      const float Dr = lds_f32(sD + (it.s * 256 + row) * 4);
-#pragma unroll
+      const float Lr = Ln * 1.4426950408889634f, Dr = Dn;
+      {
+        AbIter nx = it;
+        nx.next(n_qt, n_src, stride);
+        if (nx.work < total) load_row(nx);
+      }
+      #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int col_base = it.j * 128 + hh * 64 + qd * 16;
         // these 16 columns are needed unless they lie above the diagonal for every row of the warp (warp-uniform)
@@ -522,10 +464,13 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
       fence_proxy_async_smem();
       mbar_arrive_a(bb + 8 * AB_PDS_FULL);
       if (ttr) AB_TRACE(2, tc, 6);          // pds_full arrive
+      // dQ of the previous head, at the end of this head's first pair: its dK/dV read-out went into the staging tiles half
+      // a pair ago and has drained; the gradient UMMAs of this pair wait for it (AB_DQ_EMPTY)
+      if (pend & 2) readout_q();
       if (it.i == n_qt - 1)   // last pair of this key/value tile: dK/dV read-out after the next pair's first half
-        pend = (pend & ~0x14u) | 1u | ((it.n & 1u) << 2) | ((uint32_t)(it.ks & 1) << 4);
-      if (it.i == n_qt - 1 && it.j == n_qt - 1 && it.s == n_src - 1)   // last pair of the head
-        pend = (pend & ~0x28u) | 2u | ((it.n & 1u) << 3) | ((uint32_t)slot(it, n_qt - 1) << 5);
+        pend = (pend & ~0x4u) | 1u | ((it.n & 1u) << 2);
+      if (it.i == n_qt - 1 && it.j == n_qt - 1 && it.s == n_src - 1)   // last pair of the head: dQ right behind it
+        pend = (pend & ~0x8u) | 2u | ((it.n & 1u) << 3);
     }
     if (pend & 1) readout_kv();
     if (pend & 2) readout_q();
@@ -537,7 +482,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
 
 template <int DP, bool DROPOUT>
 static int launch_attn_bwd_d(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t st) {
-  constexpr int SMEM = 12 * AB_TILE + AB_NBARS * 8 + 16 + 2 * ATTB_MAX_SRC * 256 * 4 + 64;
+  constexpr int SMEM = AB_NTILES * AB_TILE + AB_NBARS * 8 + 16 + 64;
   static bool attr[TA_MAX_DEVICES] = {};
   TA_CHECK_CUDA(ensure_dynamic_smem(attn_bwd_kernel<DP, DROPOUT>, SMEM, attr));
   const int grid = p.total_work < num_sms() ? p.total_work : num_sms();
@@ -551,24 +496,79 @@ static int launch_attn_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, cuda
   return p.drop_thresh ? launch_attn_bwd_d<DP, true>(maps, p, st) : launch_attn_bwd_d<DP, false>(maps, p, st);
 }
 
-static int grad_out(GradOut* o, const ta_attn_tensor* t, int G) {
-  TA_CHECK_ARG(t && t->ptr && (reinterpret_cast<uintptr_t>(t->ptr) & 15) == 0, "attention gradient pointer must be 16-byte aligned");
-  TA_CHECK_ARG(t->ld % 8 == 0 && t->head_stride % 8 == 0 && (G == 1 || t->gs % 8 == 0), "attention gradient strides must be multiples of 8");
-  o->ptr = (__nv_bfloat16*)t->ptr; o->ld = t->ld; o->head_stride = t->head_stride; o->gs = t->gs;
-  return 0;
+// D[s][g][b][h][t] = sum_c dO[g][b*T+t][h*hs+c] * O_s[...][h*hs+c]. Eight lanes per (g, b, h, four consecutive rows t), one
+// 16-byte vector per row each (lanes beyond hs/8 idle); the dO vectors are reused for every source. One pass over dO and the
+// per-source outputs: HBM-bound, so every thread keeps four independent 16-byte loads in flight and the grid is sized to the
+// machine (one (row, head) per thread group and block launch ran at half the copy bandwidth).
+__global__ void __launch_bounds__(256, 3)
+attn_bwd_dtab_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ o_src,
+                     long long ldo, long long o_gs, long long o_src_stride, float* __restrict__ dtab, int n_src, int G, int B, int T,
+                     int H, int hs, int items) {      // items = G * B * ceil(T / 4) * H
+  pdl_prologue();
+  const int v = threadIdx.x & 7;
+  const int TQ = (T + 3) >> 2;
+  const long long table = (long long)G * B * H * T;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int item = blockIdx.x * 32 + (threadIdx.x >> 3); item < items; item += gridDim.x * 32) {
+    const int h = item % H, r1 = item / H;
+    const int t0 = (r1 % TQ) * 4, r2 = r1 / TQ;
+    const int b = r2 % B, g = r2 / B;
+    const bool okv = v * 8 < hs;
+    const long long ro = ((long long)b * T + t0) * ldo + h * hs + v * 8;
+    const long long dst = (((long long)g * B + b) * H + h) * T + t0;
+    uint4 dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dv[u] = okv && t0 + u < T ? *reinterpret_cast<const uint4*>(d_o + g * o_gs + ro + u * ldo) : z4;
+    for (int s = 0; s < n_src; ++s) {
+      const __nv_bfloat16* ob = o_src ? o_src + (long long)s * o_src_stride : o + g * o_gs;
+      uint4 ov[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ov[u] = okv && t0 + u < T ? *reinterpret_cast<const uint4*>(ob + ro + u * ldo) : z4;
+      float acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&dv[u]);
+        const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov[u]);
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a += __low2float(ah[e]) * __low2float(oh[e]) + __high2float(ah[e]) * __high2float(oh[e]);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        acc[u] = a;
+      }
+      if (v == 0) {
+        float* d = dtab + s * table + dst;
+        if ((T & 3) == 0) {
+          *reinterpret_cast<float4*>(d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (t0 + u < T) d[u] = acc[u];
+        }
+      }
+    }
+  }
 }
 
 }  // namespace ta
 
 using namespace ta;
 
+extern "C" int64_t ta_attention_bwd_workspace_bytes(int32_t n_src, int32_t G, int32_t B, int32_t T, int32_t H) {
+  return (int64_t)n_src * G * B * H * T * (int64_t)sizeof(float);
+}
+
 extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tensor* k, const ta_attn_tensor* v,
                                     int32_t n_src, const void* o_bf16, const void* o_src_bf16, int64_t o_src_stride,
-                                    const void* do_bf16, int64_t ldo, int64_t o_gs, const float* lse,
+                                    const void* do_bf16, int64_t ldo, int64_t o_gs, const float* lse, void* workspace,
                                     const ta_attn_tensor* dq, const ta_attn_tensor* dk, const ta_attn_tensor* dv,
                                     int32_t G, int32_t B, int32_t T, int32_t H, int32_t hs, float dropout_p, uint64_t seed,
                                     void* stream) {
-  TA_CHECK_ARG(q && k && v && o_bf16 && do_bf16 && lse && dq && dk && dv, "ta_attention_bwd: null pointer");
+  TA_CHECK_ARG(q && k && v && o_bf16 && do_bf16 && lse && dq && dk && dv && workspace, "ta_attention_bwd: null pointer");
+  TA_CHECK_ARG((reinterpret_cast<uintptr_t>(o_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(do_bf16) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(o_src_bf16) & 15) == 0 && o_src_stride % 8 == 0 && hs % 8 == 0,
+               "ta_attention_bwd: outputs must be 16-byte aligned");
   TA_CHECK_ARG(n_src >= 1 && n_src <= ATTB_MAX_SRC, "ta_attention_bwd: n_src must be in [1, %d]", ATTB_MAX_SRC);
   TA_CHECK_ARG(n_src == 1 || o_src_bf16, "ta_attention_bwd: per-source outputs are required when n_src > 1");
   TA_CHECK_ARG(hs >= 8 && hs <= 64 && hs % 8 == 0, "ta_attention_bwd: head_size %d not supported", hs);
@@ -584,17 +584,15 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
   for (int s = 0; s < n_src; ++s) {
     if (make_head_map(&maps.k[s], &k[s], hs, H, T, B, G, 128)) return 1;
     if (make_head_map(&maps.v[s], &v[s], hs, H, T, B, G, 128)) return 1;
-    if (grad_out(&p.dk[s], &dk[s], G) || grad_out(&p.dv[s], &dv[s], G)) return 1;
     if (make_head_map(&maps.dk[s], &dk[s], hs, H, T, B, G, 128)) return 1;
     if (make_head_map(&maps.dv[s], &dv[s], hs, H, T, B, G, 128)) return 1;
   }
-  if (grad_out(&p.dq, dq, G)) return 1;
   if (make_head_map(&maps.dq, dq, hs, H, T, B, G, 128)) return 1;
   p.T = T; p.B = B; p.H = H; p.G = G; p.hs = hs; p.n_src = n_src; p.n_qt = (T + 127) / 128;
   p.scale = (float)(1.0 / sqrt((double)hs));
   p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)hs));
   const long long total = (long long)G * B * H;
-  TA_CHECK_ARG(total < (1ll << 31), "attention grid too large");
+  TA_CHECK_ARG(total < (1ll << 26), "attention grid too large");
   p.total_work = (int)total;
   { const char* e = getenv("TA_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
@@ -602,12 +600,20 @@ extern "C" int32_t ta_attention_bwd(const ta_attn_tensor* q, const ta_attn_tenso
   p.drop_seed = seed;
   p.drop_step = dropout_step_counter();
   { const char* e = getenv("TA_ATTN_TRACE"); p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
-  p.d_o = (const __nv_bfloat16*)do_bf16;
-  p.o = (const __nv_bfloat16*)o_bf16;
-  p.o_src = n_src > 1 ? (const __nv_bfloat16*)o_src_bf16 : nullptr;
-  p.ldo = ldo; p.o_gs = o_gs; p.o_src_stride = o_src_stride;
   p.lse = lse;
+  p.dtab = (const float*)workspace;
   auto st = (cudaStream_t)stream;
+  {
+    const long long items = total * ((T + 3) / 4);
+    TA_CHECK_ARG(items < (1ll << 31), "ta_attention_bwd: G * B * H * T too large");
+    long long blocks = (items + 31) / 32;
+    if (blocks > 6ll * num_sms()) blocks = 6ll * num_sms();
+    launch_kernel(attn_bwd_dtab_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)do_bf16,
+                  (const __nv_bfloat16*)o_bf16, n_src > 1 ? (const __nv_bfloat16*)o_src_bf16 : (const __nv_bfloat16*)nullptr,
+                  (long long)ldo, (long long)o_gs, (long long)o_src_stride, (float*)workspace, (int)n_src, (int)G, (int)B, (int)T,
+                  (int)H, (int)hs, (int)items);
+    TA_CHECK_LAUNCH();
+  }
   const int DP = hs <= 16 ? 16 : (hs <= 32 ? 32 : 64);
   if (DP == 16) return launch_attn_bwd<16>(maps, p, st);
   if (DP == 32) return launch_attn_bwd<32>(maps, p, st);

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRADEAID_B200_LIB") or os.path.join(_HERE, "libtradeaid_b200.so")   # env override: dev A/B builds
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class TaOperand(C.Structure):
@@ -555,16 +555,33 @@ def adamw_step(p, g, m, v, shadow, scalars_dev, beta1=0.9, beta2=0.999, eps=1e-8
 
 _lib.ta_attention_bwd.restype = C.c_int32
 _lib.ta_attention_bwd.argtypes = [C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.c_int32,
-                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor), C.POINTER(TaAttnTensor),
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_void_p]
+_attn_bwd_ws_bytes = _sig("ta_attention_bwd_workspace_bytes", _I32, _I32, _I32, _I32, _I32, restype=_I64)
+_attn_bwd_ws = {}      # (device, bytes) -> fp32 tensor; never freed: captured CUDA graphs keep replaying into these addresses
+
+
+def attention_bwd_workspace(n_src, G, B, T, H, device):
+    """The D = rowsum(dO * O_s) table of ta_attention_bwd (fp32 [n_src, G, B, H, T]); one per size and device, shared by
+    every call on the compute stream (the table is consumed by the launch that follows the one that writes it)."""
+    import torch
+    nbytes = int(_attn_bwd_ws_bytes(n_src, G, B, T, H))
+    key = (str(device), nbytes)
+    ws = _attn_bwd_ws.get(key)
+    if ws is None:
+        ws = _attn_bwd_ws[key] = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+    return ws
 
 
 def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_stride_q=None, head_stride_kv=None,
-                  o_src=None, dropout_p=0.0, dropout_seed=0, dropout_step=None):
+                  o_src=None, dropout_p=0.0, dropout_seed=0, dropout_step=None, workspace=None):
     """Gradients of attention_fwd. d_o has the layout of o; dq of q; dks[s]/dvs[s] of ks[s]/vs[s] (bf16)."""
     n_src = len(ks)
     G = q.shape[0] if q.dim() == 3 else 1
+    if workspace is None:
+        workspace = attention_bwd_workspace(n_src, G, B, T, H, q.device)
+    assert workspace.dtype.itemsize * workspace.numel() >= int(_attn_bwd_ws_bytes(n_src, G, B, T, H)) and workspace.is_contiguous()
     hq = head_stride_q if head_stride_q is not None else hs
     hkv = head_stride_kv if head_stride_kv is not None else hs
     qa = (TaAttnTensor * 1)(_attn_tensor(q, hq))
@@ -578,7 +595,7 @@ def attention_bwd(q, ks, vs, o, d_o, lse, dq, dks, dvs, *, B, T, H, hs, head_str
     assert o.dim() < 3 or d_o.stride(0) == o.stride(0)
     with _step_counter(dropout_step if dropout_p > 0 else None):
         _check(_lib.ta_attention_bwd(qa, ka, va, n_src, _ptr(o), _ptr(o_src), o_src.stride(0) if o_src is not None else 0,
-                                     _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), dqa, dka, dva, G, B, T, H, hs, float(dropout_p),
+                                     _ptr(d_o), o.stride(-2), o_gs, _ptr(lse), _ptr(workspace), dqa, dka, dva, G, B, T, H, hs, float(dropout_p),
                                      int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()))
 
 
