@@ -20,8 +20,8 @@ def bwd(): lib.attention_bwd(q, ks, vs, o, d_o, lse, dq, dkv, [t[..., hs:] for t
 bwd(); torch.cuda.synchronize(); buf.zero_(); bwd(); torch.cuda.synchronize()
 t = buf.cpu().view(4, 1024)
 ev = []
-names = {0: {1: "L kv slot free", 2: "L q slot0 free", 3: "L q slot1 free"}, 1: {1: "I operands ready", 2: "I S/dP h0 issued", 3: "I S/dP h1 issued", 4: "I pds_full seen", 5: "I grads issued"},
-         2: {14: "M0 prefetch issued", 11: "M0 loads issued", 12: "M0 g_done(last) seen", 13: "M0 kv readout done", 7: "M0 prologue start", 8: "M0 bar1 passed", 9: "M0 readouts done", 10: "M0 D stored", 1: "M0 prologue done", 2: "M0 h0 avail", 3: "M0 h1 avail", 4: "M0 h0 math done", 5: "M0 g_done seen", 6: "M0 pds arrive"},
+names = {0: {1: "L kv slot free", 2: "L q slot0 free", 3: "L q slot1 free"}, 1: {1: "I operands ready", 2: "I S/dP h0 issued", 3: "I S/dP h1 issued", 4: "I pds_full seen", 5: "I grads issued", 6: "I S h0 issued", 7: "I S h1 issued"},
+         2: {14: "M0 prefetch issued", 11: "M0 loads issued", 12: "M0 g_done(last) seen", 13: "M0 kv readout done", 7: "M0 prologue start", 8: "M0 bar1 passed", 9: "M0 readouts done", 10: "M0 D stored", 1: "M0 prologue done", 2: "M0 h0 avail", 3: "M0 h1 avail", 4: "M0 h0 math done", 5: "M0 g_done seen", 6: "M0 pds arrive", 15: "M0 S avail", 16: "M0 pair top"},
          3: {4: "G pds_full seen", 5: "G grads issued"}}
 for role in range(4):
     for x in t[role].tolist():

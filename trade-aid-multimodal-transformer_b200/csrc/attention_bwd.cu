@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cuda_bf16.h>
+#include <type_traits>
 
 #include "../../include/tradeaid_b200.h"
 #include "common.cuh"
@@ -263,6 +264,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
             for (int kk = 0; kk < nk_qk; ++kk)
               umma_bf16_ws(tmem_base + hh * 64, aQ + kk * 2, aK + hh * 512 + kk * 2, idesc_s, kk != 0);
             umma_commit_ws(bb + 8 * (AB_S_FULL + hh));
+            AB_TRACE(1, tc, 6 + hh);   // S half issued
             mbar_wait_a(bb + 8 * (AB_DP_EMPTY + hh), (a.n & 1) ^ 1);
             tc_fence_after();
             for (int kk = 0; kk < nk_qk; ++kk)
@@ -389,6 +391,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
         nx.next(n_qt, n_src, stride);
         if (nx.work < total) load_row(nx);
       }
+      if (ttr) AB_TRACE(2, tc, 16);         // pair top
       #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int col_base = it.j * 128 + hh * 64 + qd * 16;
@@ -398,6 +401,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
         if (row >= p.T) nvalid = 0;
         uint32_t pp[8], dd[8];     // 16 columns of P and dS, packed bf16x2
         mbar_wait_a(bb + 8 * (AB_S_FULL + hh), it.n & 1);
+        if (ttr) AB_TRACE(2, tc, 15);       // S half available
         mbar_wait_a(bb + 8 * (AB_DP_FULL + hh), it.n & 1);   // issued right behind S: no register is held across a wait
         tc_fence_after();
         if (ttr) AB_TRACE(2, tc, 2 + hh);   // S/dP half available
@@ -419,22 +423,31 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant_
                    (dropout_keep8(sd, 1u, plane, (uint32_t)row, (uint32_t)(col_base >> 3) + 1, p.drop_thresh) << 8);
           }
           const float dsc = p.drop_scale;
+          // causal / ragged masking only where the warp's 32 rows x 16 columns touch the diagonal or the end of the
+          // sequence (a select per element otherwise: 8 % of the kernel's instructions)
+          auto pds16 = [&](auto masked) {
+            constexpr bool MASK = decltype(masked)::value;
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float p0 = ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - Lr);
-            float p1 = ex2_approx(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
-            p0 = e < nvalid ? p0 : 0.f;
-            p1 = e + 1 < nvalid ? p1 : 0.f;
-            float m0 = 1.f, m1 = 1.f;
-            if constexpr (DROPOUT) {
-              m0 = (keep >> e) & 1u ? dsc : 0.f;
-              m1 = (keep >> (e + 1)) & 1u ? dsc : 0.f;
+            for (int e = 0; e < 16; e += 2) {
+              float p0 = ex2_approx(__uint_as_float(sv[e]) * p.scale_log2 - Lr);
+              float p1 = ex2_approx(__uint_as_float(sv[e + 1]) * p.scale_log2 - Lr);
+              if constexpr (MASK) {
+                p0 = e < nvalid ? p0 : 0.f;
+                p1 = e + 1 < nvalid ? p1 : 0.f;
+              }
+              float x0 = __uint_as_float(dv[e]), x1 = __uint_as_float(dv[e + 1]), q0 = p0, q1 = p1;
+              if constexpr (DROPOUT) {
+                const float m0 = (keep >> e) & 1u ? dsc : 0.f, m1 = (keep >> (e + 1)) & 1u ? dsc : 0.f;
+                x0 *= m0; x1 *= m1; q0 *= m0; q1 *= m1;
+              }
+              const float d0 = p0 * (x0 - Dr), d1 = p1 * (x1 - Dr);
+              __nv_bfloat162 pv = __floats2bfloat162_rn(q0, q1), dh = __floats2bfloat162_rn(d0, d1);
+              pp[e / 2] = *reinterpret_cast<uint32_t*>(&pv);
+              dd[e / 2] = *reinterpret_cast<uint32_t*>(&dh);
             }
-            const float d0 = p0 * (__uint_as_float(dv[e]) * m0 - Dr), d1 = p1 * (__uint_as_float(dv[e + 1]) * m1 - Dr);
-            __nv_bfloat162 pv = __floats2bfloat162_rn(p0 * m0, p1 * m1), dh = __floats2bfloat162_rn(d0, d1);
-            pp[e / 2] = *reinterpret_cast<uint32_t*>(&pv);
-            dd[e / 2] = *reinterpret_cast<uint32_t*>(&dh);
-          }
+          };
+          if ((!diag || col_base + 15 <= it.i * 128 + wq * 32) && it.i * 128 + 128 <= p.T) pds16(std::false_type{});
+          else pds16(std::true_type{});
         } else {
           tc_fence_before();
           mbar_arrive_a(bb + 8 * (AB_S_EMPTY + hh));
