@@ -79,6 +79,27 @@ step = torch.zeros(1, dtype=torch.int64, device=dev); sc = torch.zeros(4, device
 lib.adamw_tick(step, sc, 3e-4)
 report("adamw_kernel", f"n={n}", n * 30, timeit(lambda: lib.adamw_step(p, gr, m1, v1, sh, sc), n=5))
 del p, gr, m1, v1, sh
+# K3 attention at the c4 shapes: self (8 modalities in one launch) and cross (one querier, 7 sources). Algorithmic bytes:
+# forward q, o + per source k, v (+ the per-source outputs when there is more than one source); backward q, dO, dq + per
+# source k, v, dk, dv, o_s (the D table pass reads dO and o_s; its 4-byte-per-row output and the lse tables are left out)
+def attn_case(Ga, S):
+    Ha, hsa, Ta, Ba = 16, 64, 256, 64
+    Ca = Ha * hsa
+    t = Ga * Ba * Ta * Ca * 2
+    qa = torch.randn(Ga, Ba * Ta, Ca, device=dev).to(torch.bfloat16)
+    kva = [torch.randn(Ga, Ba * Ta, 2 * Ca, device=dev).to(torch.bfloat16) for _ in range(S)]
+    doa = torch.randn(Ga, Ba * Ta, Ca, device=dev).to(torch.bfloat16)
+    oa = torch.zeros_like(qa); osa = torch.zeros(S, Ga, Ba * Ta, Ca, device=dev, dtype=torch.bfloat16) if S > 1 else None
+    lsea = torch.zeros(S, Ga, Ba, Ha, Ta, device=dev)
+    dqa = torch.zeros_like(qa); dkva = [torch.zeros_like(x) for x in kva]
+    ksa, vsa = kva, [x[..., hsa:] for x in kva]
+    kw = dict(B=Ba, T=Ta, H=Ha, hs=hsa, head_stride_kv=2 * hsa, o_src=osa)
+    what = f"G={Ga} B={Ba} T={Ta} H={Ha} hs={hsa} sources={S}"
+    report("attn_fwd2_kernel", what, t * (2 + 2 * S + (S if S > 1 else 0)), timeit(lambda: lib.attention_fwd(qa, ksa, vsa, oa, lsea, **kw)))
+    report("attn_bwd_dtab_kernel + attn_bwd_kernel", what, t * (3 + 5 * S),
+           timeit(lambda: lib.attention_bwd(qa, ksa, vsa, oa, doa, lsea, dqa, dkva, [x[..., hsa:] for x in dkva], **kw)))
+attn_case(8, 1)
+attn_case(1, 7)
 # K3d decode attention at c5 sizes: 4 modalities, batch 256, 12 heads x 64, 768 cached positions
 G, Bc, H, hs, cap, ln = 4, 256, 12, 64, 1024, 768
 Cc = H * hs
