@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--dropout", type=float, default=0.0, help="dropout probability of the training step (default 0: the parity configuration)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--all-cross", action="store_true", help="cross-attention on EVERY modality (SURVEY appendix E: 'also report "
-                    "all-T'); c4 then needs --batch 32 to fit 180 GB")
+                    "all-T'); c4 then needs --batch 32, or --recompute, to fit 180 GB")
+    ap.add_argument("--recompute", action="store_true", help="activation recompute (Engine(recompute=True)): one stream copy per block "
+                    "is kept, backward reruns each block's forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the bounded CPU sample")
@@ -340,7 +342,7 @@ def run_ours(args, cfg):
 
     # ---- model, data, trainer
     dims = Dims(V, cfg["cross"], T, cfg["n_embd"], cfg["n_head"], cfg["n_layer"], dropout=args.dropout)
-    eng = Engine(dims, dev, precision=args.precision)
+    eng = Engine(dims, dev, precision=args.precision, recompute=args.recompute)
     eng.layout.init_(eng.master, generator=torch.Generator(device=dev).manual_seed(0))   # same weights on every rank
     tr = Trainer(eng, lr=3e-4, process_group=pg, world_size=world, overlap=not args.no_overlap,
                  grad_buckets=args.buckets, sm_margin=args.sm_margin, grad_dtype=args.grad_dtype)
@@ -507,7 +509,7 @@ def run_ours(args, cfg):
         line = {"metric": "training tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split bf16 operands, fp32 activations)",
-                "data": "synthetic", "config": workload_config(args, cfg, B, world), "precision": args.precision, "tier": "engine",
+                "data": "synthetic", "config": workload_config(args, cfg, B, world), "precision": args.precision, "tier": "engine", "activation_recompute": bool(args.recompute),
                 "exchange": None if world == 1 else (
                     {"kind": f"bucketed {tr.grad_dtype} all-reduce overlapped with backward", "buckets": len(tr._buckets),
                      "bucket_bytes": tr.bucket_bytes(), "bytes_per_step": sum(tr.bucket_bytes()), "sm_margin": tr.sm_margin,

@@ -199,3 +199,27 @@ def test_decode_step_with_device_side_length_matches_the_full_forward(monkeypatc
         assert cache.length == t + 1 and int(cache.len_dev) == t + 1
         for i in range(M):
             assert (step[i][:, 0] - full[i][:, t]).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["m3", "nocross"])
+def test_activation_recompute_gives_the_same_gradients_with_fewer_buffers(name):
+    """Engine(recompute=True): forward keeps one stream copy per block, backward reruns each block's forward into one shared
+    set of buffers first. Same program, same order: losses and every gradient are bit-identical to the saving run."""
+    g, eng = build(name, torch.bfloat16)
+    idx, tgt = torch.stack(g["idx"]), torch.stack(g["tgt"])
+    _, losses = eng.forward(idx, tgt, save=True)
+    eng.backward()
+    ref_grad, ref_losses, ref_bytes = eng.grad.clone(), losses.clone(), eng.activation_bytes()
+    g2, eng2 = build(name, torch.bfloat16)
+    eng2.recompute = True
+    _, losses2 = eng2.forward(idx, tgt, save=True)
+    assert eng2._saved["recompute"] and set(eng2._saved["layers"][0]) == {"x0"}
+    eng2.backward()
+    assert torch.equal(losses2, ref_losses)
+    assert torch.equal(eng2.grad, ref_grad)
+    if eng.d.n_layer > 1:
+        assert eng2.activation_bytes() < ref_bytes
+    # a second step reuses the shared buffers
+    _, losses3 = eng2.forward(idx, tgt, save=True)
+    eng2.backward()
+    assert torch.equal(losses3, ref_losses) and torch.equal(eng2.grad, ref_grad)

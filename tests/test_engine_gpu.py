@@ -296,3 +296,46 @@ def test_decode_step_graph_replay_is_bit_identical_to_plain_launches(monkeypatch
             assert all(torch.equal(x, y) for x, y in zip(a, b))
         else:
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_activation_recompute_is_bit_identical(p):
+    """Engine(recompute=True) keeps one stream copy per block and reruns each block's forward inside backward(): the kernels are
+    deterministic and the dropout masks are functions of (seed, step, coordinates), so losses and every gradient equal the
+    saving run bit for bit - with and without dropout, eagerly and through the trainer's CUDA graph."""
+    from oracle import restatement as R
+    from tradeaid_b200.engine import Engine
+    from tradeaid_b200.params import Dims
+    from tradeaid_b200.trainer import Trainer
+    M, cross, V, B, T, C, H, L = 3, [True, False, True], [100, 64, 80], 2, 64, 128, 4, 3
+    cfg = R.Cfg(T, C, H, L, V, cross)
+    sd = R.random_state_dict(cfg, seed=4)
+    g = torch.Generator().manual_seed(6)
+    idx = torch.stack([torch.randint(0, V[i], (B, T), generator=g) for i in range(M)]).cuda()
+    tgt = torch.stack([torch.randint(0, V[i], (B, T), generator=g) for i in range(M)]).cuda()
+    out = []
+    for rc in (False, True):
+        eng = Engine(Dims(V, cross, T, C, H, L, dropout=p), "cuda", recompute=rc)
+        nv = eng.layout.named_views(eng.master)
+        for k, v in sd.items():
+            nv[k].copy_(v)
+        _, losses = eng.forward(idx, tgt, save=True, train=p > 0)
+        eng.backward()
+        torch.cuda.synchronize()
+        out.append((losses.clone(), eng.grad.clone(), eng.activation_bytes()))
+        if rc and p == 0.0:      # three optimizer steps as CUDA-graph replays equal three eager steps of the saving engine
+            tr = Trainer(eng, lr=1e-3)
+            tr.capture(idx.clone(), tgt.clone())
+            got = [tr.replay().clone() for _ in range(3)]
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[1][2] < out[0][2]
+    if p > 0.0:
+        return
+    eng = Engine(Dims(V, cross, T, C, H, L), "cuda")
+    nv = eng.layout.named_views(eng.master)
+    for k, v in sd.items():
+        nv[k].copy_(v)
+    tr = Trainer(eng, lr=1e-3)
+    want = [tr.step(idx, tgt).clone() for _ in range(3)]
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

@@ -70,8 +70,11 @@ class KVCache:
 class Engine:
     PRECISIONS = ("bf16", "bf16x3")
 
-    def __init__(self, dims: Dims, device, ops=None, act_dtype=None, precision=None):
+    def __init__(self, dims: Dims, device, ops=None, act_dtype=None, precision=None, recompute=None):
         self.d = dims
+        # activation recompute (TRADEAID_RECOMPUTE=1): forward(save=True) keeps one fp32 stream copy per block instead of the
+        # block's activations, backward() reruns each block's forward first (+1 forward of compute, ~1/10 of the activations)
+        self.recompute = bool(int(os.environ.get("TRADEAID_RECOMPUTE", "0"))) if recompute is None else bool(recompute)
         self.layout = Layout(dims)
         self.device = torch.device(device)
         if ops is None:
@@ -286,76 +289,27 @@ class Engine:
             ops.embed_fwd_at(idx.view(M, BT), P["tok"], self._voff, P["pos"], x, cache.len_dev)
         else:
             ops.embed_fwd(idx.view(M, BT), P["tok"], self._voff, P["pos"][t0:t0 + T] if cache is not None else P["pos"], x, T)
+        recompute = bool(self.recompute and save and cache is None)
+        if recompute:
+            # activation recompute: only each block's input is kept (a copy per layer, 2 x 4 bytes per stream element);
+            # everything else lives in one shared set of buffers that backward() refills layer by layer
+            def nbl(name, l, shape, dtype):
+                return self.buf("rc." + name, shape, dtype)
+        else:
+            nbl = nb
         for l in range(L):
-            Sl = {}
-            Sl["x0"] = x
-            h1 = nb("h1", l, (M, BT, C), bf)
-            st1 = nb("st1", l, (2, M * BT), f32)
-            ops.layernorm_fwd(x, P["ln1_w"][l], P["ln1_b"][l], h1, st1[0], st1[1])
-            # q/k/v tanh-MLPs, stage 1: all heads and q|k|v in one GEMM (N = 3*H*h2p)   model.py:36-50, 62-63, 71
-            hid = nb("hid", l, (M, BT, 3 * H * h2p), bf)
-            b1 = (self._padded["sa_b1"] if "sa_b1" in self._padded else P["sa_b1"])[l].reshape(M, 3 * H * h2p)
-            ops.gemm(h1, self.W("sa_w1")[l].reshape(M, 3 * H * h2p, C), bias=b1, act=ACT_TANH, out_bf16=hid)
-            # stage 2: block-diagonal [hs x h2] per (q|k|v, head): grouped GEMM, groups (3H within the row, modality)
-            qkv = nb("qkv", l, (M, BT, 3 * C), bf)
-            if self._bd is not None:
-                ops.gemm(self._hid_groups(hid, BT, self._bd[0]), self._bd[2][l], out_bf16=self._qkv_groups(qkv, BT, self._bd[0]))
-            else:
-                ops.gemm(self._hid_groups(hid, BT), self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1),
-                         out_bf16=self._qkv_groups(qkv, BT))
-            o = nb("o", l, (M, BT, C), bf)
-            lse = nb("lse", l, (1, M, B, H, T), f32)
-            if dyn:
-                ops.kv_append(qkv.view(M, B, 3 * C)[..., C:], cache.self_kv[l], cache.len_dev)
-            elif cache is not None:    # append this call's keys / values (a strided device copy: cache bookkeeping, not math)
-                cache.self_kv[l][:, :, t0:t0 + T].copy_(qkv.view(M, B, T, 3 * C)[..., C:])
-            if decode:
-                kc = cache.self_kv[l]
-                ops.attention_decode(qkv.view(M, B, 3 * C)[..., 0:C], [kc[..., 0:C]], [kc[..., C:2 * C]], o.view(M, B, C),
-                                     length=1 if dyn else t0 + 1, H=H, hs=hs, **({"len_dev": cache.len_dev} if dyn else {}))
-            else:
-                ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
-                                  **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
-            # projection MLP + residual   model.py:82-91, 224
-            p1 = nb("p1", l, (M, BT, C // 2), bf)
-            ops.gemm(o, self.W("sa_pw1")[l], bias=P["sa_pb1"][l], act=ACT_TANH, out_bf16=p1)
-            x1 = nb("x1", l, (M, BT, C), f32)
-            ops.gemm(p1, self.W("sa_pw2")[l], bias=P["sa_pb2"][l], residual=x, out_f32=x1,
-                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_PROJ, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
-            # feed-forward + residual   model.py:167-172, 225
-            hh = nb("h2", l, (M, BT, C), bf)
-            st2 = nb("st2", l, (2, M * BT), f32)
-            ops.layernorm_fwd(x1, P["ln2_w"][l], P["ln2_b"][l], hh, st2[0], st2[1])
-            ffh = nb("ffh", l, (M, BT, 4 * C), bf)
-            ops.gemm(hh, self.W("ff_w1")[l], bias=P["ff_b1"][l], act=ACT_RELU, out_bf16=ffh)
-            x2 = nb("x2", l, (M, BT, C), f32)
-            a_bf = nb("a_bf", l, (M, BT, C), bf) if d.Xc else None
-            x3 = None
-            if d.Xc and d.Xc < M and pd == 0.0:
-                # modalities without cross-attention leave the block unchanged (model.py:229-242 only rewrites the enabled
-                # ones): their feed-forward output is written straight into the block's output buffer instead of being copied
-                # there afterwards (4 of c4's 8 modalities: 0.5 GB read + written per layer). One launch per run of
-                # neighbouring modalities of the same kind. (With dropout the mask is keyed by the group index of ONE launch
-                # over all modalities - the copy form below is kept.)
-                x3 = nb("x3", l, (M, BT, C), f32)
-                flags = [i in d.xc for i in range(M)]
-                a = 0
-                while a < M:
-                    e = a + 1
-                    while e < M and flags[e] == flags[a]:
-                        e += 1
-                    ops.gemm(ffh[a:e], self.W("ff_w2")[l][a:e], bias=P["ff_b2"][l][a:e], residual=x1[a:e],
-                             out_f32=(x2 if flags[a] else x3)[a:e], out_bf16=a_bf[a:e])
-                    a = e
-            else:
-                ops.gemm(ffh, self.W("ff_w2")[l], bias=P["ff_b2"][l], residual=x1, out_f32=x2, out_bf16=a_bf,
-                         **({"dropout_p": pd, "dropout_seed": S_(self.SITE_FFN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
-            Sl.update(h1=h1, st1=st1, hid=hid, qkv=qkv, o=o, lse=lse, p1=p1, x1=x1, h2=hh, st2=st2, ffh=ffh, x2=x2,
-                      a_bf=a_bf)
-            x = x2
-            if d.Xc:
-                x = self._cross_forward(l, Sl, x2, a_bf, B, T, nb, pd, cache, t0, x3)
-            S["layers"].append(Sl)
+            if recompute and l > 0:
+                xin = self.buf(f"xin.{l}", (M, BT, C), f32)
+                xin.copy_(x)
+                x = xin
+            xi = x
+            x, Sl = self._layer_forward(l, x, B, T, nbl, pd, cache, t0)
+            S["layers"].append({"x0": xi} if recompute else Sl)
+        if recompute:
+            xin = self.buf(f"xin.{L}", (M, BT, C), f32)
+            xin.copy_(x)
+            x = xin
+        S["recompute"] = recompute
         # output heads   model.py:339-352
         hf = nb("hf", 0, (M, BT, C), bf)
         stf = nb("stf", 0, (2, M * BT), f32)
@@ -409,6 +363,88 @@ class Engine:
             else:
                 cache.len_dev.fill_(cache.length)
         return [lg.view(B, T, -1) for lg in logits], losses
+
+    def _layer_forward(self, l, x, B, T, nb, pd=0.0, cache=None, t0=0):
+        """One transformer block (model.py:214-244) on the residual stream x [M, B*T, C]: returns (stream out, the block's saved
+        activations). `nb(name, l, shape, dtype)` names the buffers: per layer when they are kept for backward(), shared when
+        not (inference, or activation recompute - backward() then calls this again for layer l right before it needs them)."""
+        d, ops, P = self.d, self.ops, self.P
+        S_ = self._seed
+        M, C, H, hs = d.M, d.n_embd, d.n_head, d.hs
+        h2p = d.h2p
+        BT = B * T
+        bf, f32 = self.act_dtype, torch.float32
+        decode = cache is not None and t0 > 0
+        dyn = decode and cache.dyn
+        Sl = {}
+        Sl["x0"] = x
+        h1 = nb("h1", l, (M, BT, C), bf)
+        st1 = nb("st1", l, (2, M * BT), f32)
+        ops.layernorm_fwd(x, P["ln1_w"][l], P["ln1_b"][l], h1, st1[0], st1[1])
+        # q/k/v tanh-MLPs, stage 1: all heads and q|k|v in one GEMM (N = 3*H*h2p)   model.py:36-50, 62-63, 71
+        hid = nb("hid", l, (M, BT, 3 * H * h2p), bf)
+        b1 = (self._padded["sa_b1"] if "sa_b1" in self._padded else P["sa_b1"])[l].reshape(M, 3 * H * h2p)
+        ops.gemm(h1, self.W("sa_w1")[l].reshape(M, 3 * H * h2p, C), bias=b1, act=ACT_TANH, out_bf16=hid)
+        # stage 2: block-diagonal [hs x h2] per (q|k|v, head): grouped GEMM, groups (3H within the row, modality)
+        qkv = nb("qkv", l, (M, BT, 3 * C), bf)
+        if self._bd is not None:
+            ops.gemm(self._hid_groups(hid, BT, self._bd[0]), self._bd[2][l], out_bf16=self._qkv_groups(qkv, BT, self._bd[0]))
+        else:
+            ops.gemm(self._hid_groups(hid, BT), self.W("sa_w2")[l].reshape(M, 3 * H, hs, -1),
+                     out_bf16=self._qkv_groups(qkv, BT))
+        o = nb("o", l, (M, BT, C), bf)
+        lse = nb("lse", l, (1, M, B, H, T), f32)
+        if dyn:
+            ops.kv_append(qkv.view(M, B, 3 * C)[..., C:], cache.self_kv[l], cache.len_dev)
+        elif cache is not None:    # append this call's keys / values (a strided device copy: cache bookkeeping, not math)
+            cache.self_kv[l][:, :, t0:t0 + T].copy_(qkv.view(M, B, T, 3 * C)[..., C:])
+        if decode:
+            kc = cache.self_kv[l]
+            ops.attention_decode(qkv.view(M, B, 3 * C)[..., 0:C], [kc[..., 0:C]], [kc[..., C:2 * C]], o.view(M, B, C),
+                                 length=1 if dyn else t0 + 1, H=H, hs=hs, **({"len_dev": cache.len_dev} if dyn else {}))
+        else:
+            ops.attention_fwd(qkv[..., 0:C], [qkv[..., C:2 * C]], [qkv[..., 2 * C:3 * C]], o, lse, B=B, T=T, H=H, hs=hs,
+                              **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_ATTN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
+        # projection MLP + residual   model.py:82-91, 224
+        p1 = nb("p1", l, (M, BT, C // 2), bf)
+        ops.gemm(o, self.W("sa_pw1")[l], bias=P["sa_pb1"][l], act=ACT_TANH, out_bf16=p1)
+        x1 = nb("x1", l, (M, BT, C), f32)
+        ops.gemm(p1, self.W("sa_pw2")[l], bias=P["sa_pb2"][l], residual=x, out_f32=x1,
+                 **({"dropout_p": pd, "dropout_seed": S_(self.SITE_SA_PROJ, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
+        # feed-forward + residual   model.py:167-172, 225
+        hh = nb("h2", l, (M, BT, C), bf)
+        st2 = nb("st2", l, (2, M * BT), f32)
+        ops.layernorm_fwd(x1, P["ln2_w"][l], P["ln2_b"][l], hh, st2[0], st2[1])
+        ffh = nb("ffh", l, (M, BT, 4 * C), bf)
+        ops.gemm(hh, self.W("ff_w1")[l], bias=P["ff_b1"][l], act=ACT_RELU, out_bf16=ffh)
+        x2 = nb("x2", l, (M, BT, C), f32)
+        a_bf = nb("a_bf", l, (M, BT, C), bf) if d.Xc else None
+        x3 = None
+        if d.Xc and d.Xc < M and pd == 0.0:
+            # modalities without cross-attention leave the block unchanged (model.py:229-242 only rewrites the enabled
+            # ones): their feed-forward output is written straight into the block's output buffer instead of being copied
+            # there afterwards (4 of c4's 8 modalities: 0.5 GB read + written per layer). One launch per run of
+            # neighbouring modalities of the same kind. (With dropout the mask is keyed by the group index of ONE launch
+            # over all modalities - the copy form below is kept.)
+            x3 = nb("x3", l, (M, BT, C), f32)
+            flags = [i in d.xc for i in range(M)]
+            a = 0
+            while a < M:
+                e = a + 1
+                while e < M and flags[e] == flags[a]:
+                    e += 1
+                ops.gemm(ffh[a:e], self.W("ff_w2")[l][a:e], bias=P["ff_b2"][l][a:e], residual=x1[a:e],
+                         out_f32=(x2 if flags[a] else x3)[a:e], out_bf16=a_bf[a:e])
+                a = e
+        else:
+            ops.gemm(ffh, self.W("ff_w2")[l], bias=P["ff_b2"][l], residual=x1, out_f32=x2, out_bf16=a_bf,
+                     **({"dropout_p": pd, "dropout_seed": S_(self.SITE_FFN, l), "dropout_step": self._drop_step} if pd > 0.0 else {}))
+        Sl.update(h1=h1, st1=st1, hid=hid, qkv=qkv, o=o, lse=lse, p1=p1, x1=x1, h2=hh, st2=st2, ffh=ffh, x2=x2,
+                  a_bf=a_bf)
+        x = x2
+        if d.Xc:
+            x = self._cross_forward(l, Sl, x2, a_bf, B, T, nb, pd, cache, t0, x3)
+        return x, Sl
 
     def decode_step(self, idx, cache):
         """One new position per sequence against the K/V cache (generate's growing phase; idx int64 [M, B, 1]). On a CUDA
@@ -652,8 +688,13 @@ class Engine:
         if stage_hook is not None:
             stage_hook("heads")
         # ---- layers, last to first
+        def nbr(name, l_, shape, dtype):
+            return self.buf("rc." + name, shape, dtype)
+
         for l in reversed(range(L)):
             Sl = S["layers"][l]
+            if S.get("recompute"):      # refill the shared activation buffers with this block's forward (same dropout masks:
+                _, Sl = self._layer_forward(l, Sl["x0"], B, T, nbr, pd)      # they are functions of (seed, step, coordinates))
             if d.Xc:
                 self._cross_backward(l, Sl, dx, dxb, B, T, cs_ws, ln_ws, pd, dxm, stage_hook)
             # feed-forward
