@@ -58,7 +58,11 @@ def test_two_gpu_parity_mode_equals_one_gpu(tmp_path, graph):
     assert dn <= 5e-2, dn
     assert dl <= 1e-4, dl
     assert de <= 1e-4, de
-    assert num(one["eval_text"]) == num(two["eval_text"])          # same directional counts, dealt over the ranks
+    # the directional counts are dealt over the ranks and summed: same totals; the wins may differ by a borderline
+    # prediction (the two runs' weights differ by up to 2 lr per element, see above)
+    a, b = num(one["eval_text"]), num(two["eval_text"])
+    assert len(a) == len(b) and [x.split("/")[1] for x in a] == [x.split("/")[1] for x in b]
+    assert max(abs(int(x.split("/")[0]) - int(y.split("/")[0])) for x, y in zip(a, b)) <= 1, (a, b)
 
 
 @two_gpus
