@@ -561,3 +561,57 @@ def test_augment_tokens_matches_reference_golden():
         random.seed(77)
         ref = R.add_rand_to_data_points(R.add_rand_to_data_points(list(data), size, V), size, V)
         assert store.store[0].tolist() == ref and tail == random.getrandbits(32)
+
+
+_WIDE_SCRIPT = r"""
+import sys, torch
+from tradeaid_b200 import lib
+torch.manual_seed(0)
+outs = []
+for (M, N, K, G, act) in [(300, 192, 128, 3, 0), (1024, 256, 128, 8, 0), (640, 512, 1024, 2, lib.ACT_RELU), (512, 128, 64, 1, lib.ACT_TANH),
+                          (2048, 1024, 512, 2, 0), (700, 64, 96, 2, 0)]:
+    A = torch.randn(G, M, K + 8, device="cuda").to(torch.bfloat16)[..., :K]
+    B = torch.randn(G, N, K + 8, device="cuda").to(torch.bfloat16)[..., :K]
+    bias = torch.randn(G, N, device="cuda") if act else None
+    ob = torch.full((G, M, N + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    lib.gemm(A, B, out_bf16=ob[..., :N], alpha=0.05, **({"bias": bias, "act": act} if act else {}))
+    ref = (A.float() @ B.float().transpose(-1, -2)) * 0.05
+    if act:
+        ref = ref + bias[:, None, :]
+        ref = torch.relu(ref) if act == lib.ACT_RELU else torch.tanh(ref)
+    assert (ob[..., :N].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3, (M, N, K, G, act)
+    assert (ob[..., N:] == 7.0).all(), "wrote past the last column"
+    outs.append(ob.cpu())
+# the saved-activation epilogues (dX = (dY W) * tanh'(a) / ReLU'(a)): the activation is TMA-loaded into the staging buffer
+for (M, N, K, G, mode) in [(300, 192, 256, 3, lib.AUX_TANH_BWD), (1024, 128, 256, 8, lib.AUX_TANH_BWD), (900, 1024, 512, 2, lib.AUX_RELU_BWD),
+                           (512, 64, 64, 2, lib.AUX_RELU_BWD)]:
+    A = torch.randn(G, M, K + 8, device="cuda").to(torch.bfloat16)[..., :K]
+    B = torch.randn(G, K, N + 8, device="cuda").to(torch.bfloat16)[..., :N]
+    aux = torch.randn(G, M, N + 8, device="cuda").to(torch.bfloat16)[..., :N]
+    ob = torch.full((G, M, N + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    lib.gemm(A, B, b_major=1, aux=aux, aux_mode=mode, out_bf16=ob[..., :N], alpha=0.05)
+    ref = (A.float() @ B.float()) * 0.05
+    ref = ref * (1 - aux.float() ** 2) if mode == lib.AUX_TANH_BWD else torch.where(aux.float() > 0, ref, torch.zeros_like(ref))
+    assert (ob[..., :N].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3, (M, N, K, G, mode)
+    assert (ob[..., N:] == 7.0).all(), "wrote past the last column"
+    outs.append(ob.cpu())
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_gemm_wide_bf16_store_boxes_are_bit_identical(tmp_path):
+    """The bf16-only epilogue with [32 x 64] store boxes (TA_GEMM_WIDE=2: wherever N % 64 == 0) against 32-column boxes
+    (TA_GEMM_WIDE=0): same accumulators, same rounding, a different way out - every output bit equal, nothing written past
+    N or M (ragged M, an N tail tile, 1-CTA 128/256-wide and CTA-pair tiles, bias + activation and tanh' / ReLU' epilogues). The switch is read
+    once per process, hence the subprocesses."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for mode in ("0", "2"):
+        out = tmp_path / f"wide_{mode}.pt"
+        env = dict(os.environ, TA_GEMM_WIDE=mode, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        r = subprocess.run([sys.executable, "-c", _WIDE_SCRIPT, str(out)], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(torch.load(out))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)

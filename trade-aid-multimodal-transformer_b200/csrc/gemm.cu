@@ -63,6 +63,7 @@ struct GemmParams {
   int nbf, nbb;        // staging buffers per epilogue warp: fp32 chunks / bf16 chunks
   int nst;             // rotation depth of the store-only buffers (2, or 4 for short-K problems bound by the store path)
   int bf16_direct;     // tma_epi with both outputs: bf16 goes out with row-per-thread stores
+  int bf16_wide;       // bf16-only output staged two chunks at a time: [32 x 64] boxes, 128-byte rows (nbb / 2 buffers of 4 KB)
   int epi_warp_bytes;
   int m_major;         // tile order, see decode_tile
   uint32_t drop_thresh;     // 16-bit lane threshold of the epilogue dropout (0 = off), see philox.cuh
@@ -74,6 +75,7 @@ struct GemmParams {
 
 struct EpiMaps {
   CUtensorMap f32, bf16, res, aux;
+  CUtensorMap bf16w;   // the bf16 output again with [32 rows x 64 columns] boxes (SWIZZLE_128B), see GemmParams::bf16_wide
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -132,6 +134,12 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
     const uint32_t brow = lane * 64, bsw = (lane >> 1) & 3;      // bf16 row offset, swizzle key
     uint32_t lphase = 0;    // bit b: parity the next wait on loaded buffer b uses
     uint32_t sc = 0;        // running count of chunks stored (rotation of the store-only buffers)
+    // wide bf16 staging: two neighbouring chunks share one [32 x 64] buffer with 128-byte rows and leave with ONE TMA store
+    // (full 128-byte lines; a 32-column box writes 64-byte row pieces and the store path, not the math, paced the short-K
+    // launches: profiles/r02_ncu stage-2 capture). Every warp owns an even number of chunks and N % 64 == 0 in this mode.
+    const bool wide = p.bf16_wide != 0;
+    const int nw = p.nbb >> 1;
+    int wb = 0;             // wide buffer being filled
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
       int g, m0, n0;
       decode_tile(p, tile, tiles_per_group, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M, g, m0, n0);
@@ -278,7 +286,11 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
 #pragma unroll
                 for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
               }
-              if (!p.bf16_direct) {
+              if (wide) {
+                const uint32_t wbuf = bbuf0 + wb * (2 * EPI_BF16_BYTES) + lane * 128, hf = ((c - c0) & 1) << 2;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sts128(wbuf + (((hf + j) ^ (lane & 7)) << 4), u[j]);
+              } else if (!p.bf16_direct) {
                 if (dbg != 4)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sts128(bbuf + brow + ((j ^ bsw) << 4), u[j]);
@@ -296,6 +308,22 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const EpiMaps
           } else if (has_load) {
             mbar_wait(&epi_bar[ep][lb], (lphase >> lb) & 1);
             lphase ^= 1u << lb;
+          }
+          if (wide) {
+            if ((c - c0) & 1) {       // second chunk of the pair: one store of the [32 x 64] buffer
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (dbg == 0) tma_store_4d(&em.bf16w, bbuf0 + wb * (2 * EPI_BF16_BYTES), col0 - 32, row0, g0, g1);
+                bulk_commit_group();
+                // the buffer the next pair writes has been drained by its store (nw - 1 younger stores may be in flight)
+                if (nw == 3) bulk_wait_read<2>(); else bulk_wait_read<1>();
+              }
+              if (++wb == nw) wb = 0;
+              __syncwarp();
+            }
+            ++sc;
+            continue;
           }
           if (dbg != 5) fence_proxy_async_smem();   // generic-proxy writes above -> visible to the TMA store
           __syncwarp();
@@ -800,7 +828,7 @@ static int make_operand_map(CUtensorMap* out, const ta_operand* op, int64_t MN, 
 // epilogue tile map: logical [rows x cols] matrix of `es`-byte elements with two group dims, 32x32 boxes.
 // Returns false when the operand does not satisfy TMA's alignment rules (caller takes the direct path).
 static bool make_epi_map(CUtensorMap* out, const void* ptr, long long ld, long long gs0, long long gs1, int64_t rows,
-                         int64_t cols, int G0, int G1, bool is_f32) {
+                         int64_t cols, int G0, int G1, bool is_f32, bool wide_bf16 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc || !ptr) return false;
   const int es = is_f32 ? 4 : 2;
@@ -809,11 +837,11 @@ static bool make_epi_map(CUtensorMap* out, const void* ptr, long long ld, long l
   if ((G0 > 1 && (gs0 % q || gs0 == 0)) || (G1 > 1 && (gs1 % q || gs1 == 0))) return false;
   cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)G0, (cuuint64_t)G1};
   cuuint64_t strides[3] = {(cuuint64_t)ld * es, G0 > 1 ? (cuuint64_t)gs0 * es : 16, G1 > 1 ? (cuuint64_t)gs1 * es : 16};
-  cuuint32_t box[4] = {32, 32, 1, 1};
+  cuuint32_t box[4] = {wide_bf16 ? 64u : 32u, 32, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   is_f32 || wide_bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -824,7 +852,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 // Epilogue plan: which outputs go through TMA staging, how many staging buffers, and how many A/B ring stages are left.
-static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes, int ep_warps) {
+static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes, int ep_warps, int chunks_per_warp) {
   static const int force_legacy = env_int("TA_GEMM_LEGACY_EPI", 0);
   static const int force_nl = env_int("TA_GEMM_NLOAD", 0);
   memset(&em, 0, sizeof(em));
@@ -839,6 +867,16 @@ static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes, int ep_wa
   p.tma_epi = tma_ok ? 1 : 0;
   p.nbf = p.nbb = 0;
   p.nst = 2;
+  p.bf16_wide = 0;
+  // TA_GEMM_WIDE (dev): 0 = 32-column bf16 store boxes everywhere; 1 = wide boxes where the epilogue paces the launch: short K
+  // (<= 512: q/k/v stage 2 forward 0.34 -> 0.30 ms) and activation epilogues (feed-forward 1 forward -4 %, the tanh GEMMs -5 %);
+  // not the tanh' / ReLU' epilogues, whose staging buffers double as the landing zone of the saved activation's TMA loads;
+  // 2 = wherever they apply (the plain long-K launches then lose an A/B ring stage to the larger buffers and gain nothing)
+  static const int wide_mode = env_int("TA_GEMM_WIDE", 1);
+  const bool wide_wanted = wide_mode == 2 || (wide_mode == 1 && (p.k_blocks <= 8 || p.act != TA_ACT_NONE));
+  if (tma_ok && wide_wanted && p.out_bf16 && !need_f && !p.aux && p.N % 64 == 0 && chunks_per_warp % 2 == 0 &&
+      make_epi_map(&em.bf16w, p.out_bf16, p.ld_bf16, p.bf16_gs0, p.bf16_gs1, p.M, p.N, p.G0, p.G1, false, true))
+    p.bf16_wide = 1;
   if (tma_ok) {
     // short K, bf16 store only (q/k/v stage 2 forward): the tile's math is a few hundred cycles, the kernel runs at the
     // rate its TMA stores drain - four 2 KB chunk buffers per warp keep three stores in flight instead of one
@@ -846,6 +884,7 @@ static void plan_epilogue(GemmParams& p, EpiMaps& em, int stage_bytes, int ep_wa
     if (!need_f && need_b && !p.aux && ((force_nst == 0 && p.k_blocks <= 4) || force_nst == 4)) p.nst = 4;
     if (need_f) p.nbf = p.res ? 3 : 2;
     else if (need_b) p.nbb = p.aux ? 3 : p.nst;
+    if (p.bf16_wide) p.nbb = p.nst == 4 ? 6 : 4;      // three / two 4 KB buffers per warp
     if (force_nl == 2 || force_nl == 3) { if (p.res) p.nbf = force_nl; if (p.aux) p.nbb = force_nl; }
     auto epi_bytes = [&]() { return ep_warps * (p.nbf * EPI_F32_BYTES + p.nbb * EPI_BF16_BYTES); };
     // long K: the epilogue has slack, the A/B ring does not - two buffers (no residual prefetch distance of 2) are enough
@@ -872,7 +911,7 @@ static int launch_gemm(const ta_operand* A, const ta_operand* B, GemmParams& p, 
   if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, BLOCK_N)) return 1;
   p.n_blocks = (int)ceil_div(p.N, BLOCK_N);
   EpiMaps em;
-  plan_epilogue(p, em, Cfg::STAGE_BYTES, Cfg::NW);
+  plan_epilogue(p, em, Cfg::STAGE_BYTES, Cfg::NW, (BLOCK_N / 32) / (Cfg::NW / 4));
   const int stages = p.stages;
   const int smem_bytes = stages * Cfg::STAGE_BYTES + Cfg::NW * p.epi_warp_bytes + 1024;
   static bool attr_set[TA_MAX_DEVICES] = {};
@@ -891,7 +930,7 @@ static int launch_gemm2(const ta_operand* A, const ta_operand* B, GemmParams& p,
   if (make_operand_map(&tmB, B, p.N, p.K, p.G0, p.G1, G2_B_HALF)) return 1;
   p.n_blocks = (int)ceil_div(p.N, G2_BLOCK_N);
   EpiMaps em;
-  plan_epilogue(p, em, G2_STAGE_BYTES, 8);
+  plan_epilogue(p, em, G2_STAGE_BYTES, 8, (G2_BLOCK_N / 32) / 2);
   const int smem_bytes = p.stages * G2_STAGE_BYTES + 8 * p.epi_warp_bytes + 1024;
   static bool attr_set[TA_MAX_DEVICES] = {};
   TA_CHECK_CUDA(ensure_dynamic_smem(gemm2_bf16_kernel, SMEM_LIMIT + 1024, attr_set));
