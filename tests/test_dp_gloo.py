@@ -89,6 +89,23 @@ def test_two_rank_dp_with_bf16_gradient_exchange(tmp_path, overlap):
     assert (dp_master - eng.master).norm().item() <= 0.05 * moved
 
 
+def test_two_rank_dp_with_activation_recompute(tmp_path, monkeypatch):
+    """TRADEAID_RECOMPUTE=1 under data parallelism: backward() reruns each block's forward before its backward, the stage hooks
+    (bucket all-reduces overlapped with backward) fire at the same points - the two-rank run still follows the single-process
+    saving run to fp32 summation order."""
+    out = str(tmp_path / "dp_master_rc.pt")
+    port = 33500 + os.getpid() % 2000
+    monkeypatch.setenv("TRADEAID_RECOMPUTE", "1")
+    mp.spawn(_worker, args=(2, port, out, True), nprocs=2, join=True)
+    monkeypatch.delenv("TRADEAID_RECOMPUTE")
+    dp_master = torch.load(out)
+    eng, tr, idx, tgt = _build(1, None)
+    assert not eng.recompute
+    for _ in range(3):
+        tr.step(idx, tgt)
+    assert (dp_master - eng.master).abs().max().item() <= 2e-5
+
+
 def test_gradient_buckets_partition_the_active_parameters():
     """Every element of every active parameter kind is in exactly one bucket (trainer.py: _make_buckets)."""
     _setup_paths()
