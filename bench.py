@@ -73,9 +73,10 @@ def peaks():
 
 def traffic_of_dominant_launch():
     """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` capture
-    (profiles/r01_roofline_traffic.json names the launch and its algorithmic bytes); None if the file is missing."""
-    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
-    if not os.path.exists(p):
+    (profiles/r02_roofline_traffic.json - the capture of the latest round - names the launch and its algorithmic bytes); None if
+    no such file exists."""
+    p = next((q for q in (os.path.join(ROOT, "profiles", f"r{r:02d}_roofline_traffic.json") for r in (2, 1)) if os.path.exists(q)), None)
+    if p is None:
         return None
     with open(p) as f:
         d = json.load(f)
