@@ -44,6 +44,8 @@ def parse(argv=None):
     ap.add_argument("--backend", default=None, help="torch.distributed backend (default: nccl on cuda, gloo on cpu)")
     ap.add_argument("--graph", action="store_true", help="replay the step as CUDA graphs (static batch buffers)")
     ap.add_argument("--precision", default=None, choices=["bf16", "bf16x3"])
+    ap.add_argument("--recompute", action="store_true", help="activation recompute (TRADEAID_RECOMPUTE=1): one stream copy per block "
+                    "is kept, backward reruns each block's forward")
     ap.add_argument("--buckets", type=int, default=None, help="gradient buckets of the overlapped exchange")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"], help="what the gradient buckets travel as; default: "
@@ -168,6 +170,8 @@ def main(argv=None):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.precision:
         our_model.set_precision(args.precision)
+    if args.recompute:
+        os.environ["TRADEAID_RECOMPUTE"] = "1"      # read by Engine.__init__ when main.py's preamble builds the model
     if torch.cuda.is_available():
         torch.cuda.set_device(local)       # config.yaml's `device: cuda` then means this rank's GPU
     torch.manual_seed(args.seed)
