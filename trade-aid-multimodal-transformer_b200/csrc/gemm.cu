@@ -23,7 +23,6 @@ namespace ta {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int GEMM_THREADS = 192;
 constexpr int SMEM_LIMIT = 227 * 1024 - 1024 - 512;  // opt-in maximum minus alignment slack and static barriers
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_F32_BYTES = 32 * 32 * 4;           // one 32x32 fp32 chunk, 128-byte rows (SWIZZLE_128B)
